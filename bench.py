@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Benchmark of the float_vector brute-force KNN hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W          our arm (CUDA, through the C ABI)
+  python bench.py --impl reference --gpus N ...          the reference's own CPU implementation on this box's host cores
+
+Workload at N=1 = BASELINE.json configs[1]: brute-force KNN, 10M x 768 fp32, inner product, k=10, batch of 1024 queries on one
+B200.  A "step" is one batch of 1024 queries against the resident index.  For N>1 the namespace is sharded by row range, 10M rows
+per GPU (weak scaling, configs[4] at N=8); every rank scans its shard for all 1024 queries and one NCCL all-gather + merge
+yields the global top-k; `value` counts the (query x 10M-row-shard) scans all ranks complete per second.
+Synthetic data: rows and queries from the counter-based generator in reindexer_b200/csrc/common.cuh (sigma 0.25, like the
+reference's own test generator), produced directly in HBM.  Inputs are far larger than L2 (30.7 GB vs 126 MB), so no flush.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "KNN QPS @ recall@10 (10Mx768, k=10) + HBM GB/s vs roofline"
+UNIT = "queries/s"
+DIM, K, NQ = 768, 10, 1024
+ROWS_FULL = 10_000_000
+SEED = 0x5EED0001
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                                          str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_qps(rows_sample, nq_per_round, rounds, threads):
+    """The reference's own hnswlib::BruteforceSearch::SearchKnn (oracle/_ref, AVX-512 dispatch) -- or the C port when the
+    reference build is absent -- on a bounded sample of the workload: `rows_sample` rows of the same generator, `threads`
+    host threads each issuing independent single-threaded queries (what the reference permits).  Brute force is linear in the
+    row count, so QPS at 10M rows = QPS(sample) * rows_sample / 10M (labelled "extrapolated")."""
+    from oracle import oracle as O
+
+    kind = "reference" if O.ref_knn_available() else "port"
+    vecs = np.empty((rows_sample, DIM), np.float32)
+    O.port_lib().port_synth_fill(SEED, 0, rows_sample * DIM, vecs.ctypes.data_as(O._f32p))
+    queries = O.synth_matrix(SEED + 1, nq_per_round, DIM)
+    labels = O.row_labels(rows_sample)
+    if kind == "reference":
+        bf = O.RefBF(O.IP, DIM, rows_sample)
+        assert bf.add_batch(labels, vecs) == 0
+        isa = {3: "avx512", 2: "avx2", 1: "avx", 0: "sse"}[O.ref_knn_lib().ref_isa_level()]
+
+        def run():
+            bf.search_knn_batch(queries, K, threads)
+    else:
+        bf = O.PortBF(O.IP, DIM, rows_sample)
+        assert bf.add_batch(labels, vecs) == 0
+        isa, threads = "scalar-c", 1
+
+        def run():
+            for q in queries:
+                bf.search_knn(q, K)
+    run()  # warm-up
+    times = []
+    for _ in range(rounds):
+        t0 = time.perf_counter()
+        run()
+        times.append(time.perf_counter() - t0)
+    qps_sample = nq_per_round / (sum(times) / len(times))
+    qps_full = qps_sample * rows_sample / ROWS_FULL
+    return {"value": qps_full, "unit": UNIT, "cores": threads, "kind": kind, "isa": isa,
+            "sample": f"{nq_per_round} queries x {rounds} rounds over {rows_sample} rows x {DIM} (same generator), "
+                      f"{threads} threads; QPS scaled linearly to {ROWS_FULL} rows (extrapolated)",
+            "qps_on_sample": qps_sample, "seconds_per_round": sum(times) / len(times)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    rows_sample = 200_000
+    nq = max(2 * threads, 16)
+    # size one step to ~2-4 s of wall clock: a single-thread query over 200k x 768 takes ~45 ms
+    t0 = time.perf_counter()
+    base = cpu_reference_qps(rows_sample, nq, 1, threads)
+    per_round = base["seconds_per_round"]
+    rounds_per_step = max(1, int(2.0 / max(per_round, 1e-3)))
+    vals = []
+    total_steps = args.warmup + args.steps
+    for s in range(total_steps):
+        r = cpu_reference_qps(rows_sample, nq, rounds_per_step, threads) if (s == 0 or True) else None
+        if s >= args.warmup:
+            vals.append(r)
+        if time.perf_counter() - t0 > 240:
+            break
+    value = float(np.mean([v["value"] for v in vals])) if vals else base["value"]
+    last = vals[-1] if vals else base
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals) or 1,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * NQ / value, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "brute-force KNN, 10M x 768 fp32, inner-product, k=10, batch=1024 queries (BASELINE configs[1])",
+                       "rows": ROWS_FULL, "dim": DIM, "k": K, "batch": NQ, "cpu_path": last["kind"], "isa": last["isa"]},
+            "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    line["cpu_baseline"]["value"] = value
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import reindexer_b200 as rx
+    from reindexer_b200 import binding as B
+    from reindexer_b200.sharded import ShardedBruteforceSearch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if rx.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device -- librxgpu has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rows = args.rows or ROWS_FULL
+    free_b, _ = torch.cuda.mem_get_info()
+    if rows * DIM * 4 * 1.05 > free_b:
+        raise SystemExit(f"bench.py: {rows} x {DIM} fp32 does not fit in {free_b / 1e9:.0f} GB of free HBM")
+
+    t_fill = time.perf_counter()
+    idx = rx.GpuBruteforceSearch(rx.IP, DIM, rows, device=local_rank)
+    idx.append_synth(SEED, rank * rows, rows)  # shard `rank` = global rows [rank*rows, (rank+1)*rows)
+    if args.query_tile:
+        idx.set_query_tile(args.query_tile)
+    fill_s = time.perf_counter() - t_fill
+    sharded = ShardedBruteforceSearch(idx, rows) if world > 1 else None
+
+    stream = torch.cuda.current_stream()
+    dq = torch.empty((NQ, DIM), dtype=torch.float32, device="cuda")
+    B._check(B.lib().rxgpu_synth_fill_device(dq.data_ptr(), SEED + 1, 0, NQ * DIM, local_rank, stream.cuda_stream))
+    hq = dq.cpu().numpy()
+    hq_pinned = torch.from_numpy(hq).pin_memory()
+    k1 = K + 1
+    od = torch.zeros((NQ, k1), dtype=torch.float32, device="cuda")
+    oi = torch.zeros((NQ, k1), dtype=torch.int32, device="cuda")
+    ol = torch.zeros((NQ, k1), dtype=torch.int64, device="cuda")
+    oc = torch.zeros((NQ,), dtype=torch.int32, device="cuda")
+
+    def step_resident():
+        if sharded is not None:
+            return sharded.search_knn(dq, K)
+        idx.search_knn_device(NQ, dq.data_ptr(), k1, od.data_ptr(), oi.data_ptr(), ol.data_ptr(), oc.data_ptr(), stream.cuda_stream)
+        return None
+
+    def step_e2e():
+        if sharded is not None:
+            return sharded.search_knn(hq_pinned.numpy(), K)
+        return idx.search_knn(hq, K)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg: CUDA events on the launching stream, max over ranks
+    B.lib().rxgpu_set_profile(1)
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = passes = 0
+    scan_ms = 0.0
+    scan_launches = 0
+    alg_bytes = 0
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+        st = rx.last_search_stats()
+        launches += st["launches"]
+        passes += st["passes"]
+        scan_ms += st["scan_kernel_ms"]
+        scan_launches += st["scan_launches"]
+        alg_bytes += st["algorithmic_bytes"]
+        qt = st["query_tile"]
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    B.lib().rxgpu_set_profile(0)
+    # ---- end-to-end leg: host buffers through the reference-facing C ABI call, copies inside the timed region
+    for _ in range(min(args.warmup, 1)):
+        res = step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_stats = rx.last_search_stats()
+    if world > 1:
+        t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e_s = float(t[0]), float(t[1])
+        tot = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tot)
+        launches_all = int(tot[0])
+    else:
+        launches_all = launches
+
+    # sanity on the timed work: every query of the last batch got k results, sorted, and (N=1) planted-free recompute of row 0
+    d_chk, l_chk, c_chk = res
+    assert (np.asarray(c_chk) == K).all() and (np.diff(d_chk[:, :K], axis=1) >= 0).all()
+
+    if rank == 0:
+        ms_per_step = ms_total / args.steps
+        value = world * NQ / (ms_per_step / 1000.0)
+        e2e_value = world * NQ / (e2e_s / args.steps)
+        peak, peak_src = load_peaks()
+        per_launch_bytes = alg_bytes / max(passes, 1)
+        avg_launch_ms = scan_ms / max(scan_launches, 1)
+        achieved = per_launch_bytes / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "brute-force KNN, 10M x 768 fp32, inner-product, k=10, batch=1024 queries (BASELINE configs[1])"
+                       if world == 1 else f"brute-force KNN, {world} x 10M x 768 fp32 sharded by row range, inner-product, k=10, "
+                                          f"batch=1024, NCCL all-gather top-k merge (BASELINE configs[4] at N=8)",
+                       "rows_per_gpu": rows, "total_rows": rows * world, "dim": DIM, "k": K, "batch": NQ, "query_tile": qt,
+                       "kernel": "knn_scan_warp (fp32 FMA, fused top-k)", "l2_policy": "inputs (30.7 GB/GPU) larger than L2, no flush",
+                       "global_queries_per_s": NQ / (ms_per_step / 1000.0), "index_fill_s": round(fill_s, 2),
+                       "value_definition": "(query x 10M-row shard) scans per second over all ranks"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "knn_scan_warp",
+                         "bytes_per_launch": per_launch_bytes, "avg_launch_ms": avg_launch_ms, "launches_timed": scan_launches,
+                         "kernel_share_of_step": scan_ms / ms_total if ms_total else None},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": NQ * DIM * 4,
+                    "d2h_bytes_per_step": NQ * k1 * 16 + NQ * 4, "ms_per_step": 1000.0 * e2e_s / args.steps,
+                    "tie_replays": e2e_stats["tie_replays"]},
+            "gpu_launches": launches_all,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            cb = cpu_reference_qps(200_000, max(2 * threads, 16), 3, threads)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "isa")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default 10M = BASELINE config)")
+    ap.add_argument("--query-tile", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

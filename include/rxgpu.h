@@ -1,0 +1,159 @@
+/* rxgpu.h -- C ABI of librxgpu.so: the B200 (sm_100a) replacement for Reindexer's float_vector KNN hot path.
+ *
+ * This is the drop-in boundary.  Every entry point names the reference interface it replaces
+ * (paths relative to /root/reference/cpp_src).  Plain C: opaque handles, pointers and sizes only, no exceptions,
+ * no torch types.  The C++ adapter reindexer_b200/host/gpu_bruteforce.h wraps these into the `Map` duck-type of
+ * HnswIndexBase<Map> (core/index/float_vector/hnsw_index.h:13-57); INTEGRATION.md shows the 3-line patch.
+ *
+ * Conventions
+ *  - return value: 0 = ok, otherwise a reindexer ErrorCode-compatible value (core/type_consts.h:136-181);
+ *    rxgpu_last_error() returns the thread-local message (texts match the reference's where its tests match on them).
+ *  - distances use the map-space sign convention of hnswlib::DistCalculator (hnswlib/hnswlib.h:147-165,192-197):
+ *    L2 -> +L2^2, InnerProduct -> -IP, Cosine -> -IP(q^, v)/||v||; smaller is better.  Queries for Cosine must be
+ *    pre-normalised by the caller (HnswIndexBase::search does it, core/index/float_vector/hnsw_index.cc:166-171) --
+ *    rxgpu_select_knn() below does that step too.
+ *  - labels are FloatVectorId::AsNumber() = rowId << 32 | arrayIdx (core/index/float_vector/float_vector_id.h:11).
+ *  - threading: searches are re-entrant and may run concurrently from many host threads ("Read-only concurrency
+ *    expected", hnswlib/hnswalg.h:1977); mutators are called by one thread at a time and never concurrently with
+ *    searches on the same handle (the namespace lock guarantees that in the reference).
+ *  - there is NO CPU fallback: every compute entry point fails with errSystem when no CUDA device is usable.
+ */
+#ifndef RXGPU_H
+#define RXGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RXGPU_ABI_VERSION 1
+
+/* subset of reindexer::ErrorCode (core/type_consts.h:136-181) that this library produces */
+enum { RXGPU_OK = 0, RXGPU_ERR_PARAMS = 3, RXGPU_ERR_LOGIC = 4, RXGPU_ERR_NOT_FOUND = 13, RXGPU_ERR_SYSTEM = 37 };
+
+/* reindexer::VectorMetric {L2, InnerProduct, Cosine} (core/enums.h:101) */
+typedef enum { RXGPU_L2 = 0, RXGPU_IP = 1, RXGPU_COS = 2 } rxgpu_metric;
+
+/* index creation flags */
+enum {
+	RXGPU_FLAG_HOST_MIRROR = 1u /* keep a host copy of the rows so rxgpu_index_get() returns a stable pointer
+								   (BruteforceSearch::FloatPtrByExternalLabel, hnswlib/bruteforce.cc:36-42) */
+};
+
+typedef struct rxgpu_index rxgpu_index; /* one hnswlib::BruteforceSearch replacement = one shard on one GPU */
+
+const char* rxgpu_last_error(void);
+int rxgpu_abi_version(void);
+/* number of usable CUDA devices (0 when there is no driver / GPU); never fails */
+int rxgpu_device_count(void);
+
+/* ---------------------------------------------------------------- lifetime / maintenance
+ * BruteforceSearch(metric, dim, maxElements)                 hnswlib/bruteforce.cc:11-18 */
+int rxgpu_index_create(rxgpu_index** out, rxgpu_metric metric, uint32_t dim, uint64_t capacity, int device, uint32_t flags);
+/* BruteforceSearch(const BruteforceSearch&, newMaxElements)  hnswlib/bruteforce.cc:20-34 (deep copy; COW namespace clone) */
+int rxgpu_index_clone(rxgpu_index** out, const rxgpu_index* src, uint64_t new_capacity);
+void rxgpu_index_destroy(rxgpu_index*);
+/* ResizeIndex                                                 hnswlib/bruteforce.cc:88-101 */
+int rxgpu_index_resize(rxgpu_index*, uint64_t new_capacity);
+/* AddPointNoLock (upsert by label)                            hnswlib/bruteforce.cc:44-64 */
+int rxgpu_index_upsert(rxgpu_index*, uint64_t label, const float* vec /* dim floats, host */);
+int rxgpu_index_upsert_batch(rxgpu_index*, uint64_t n, const uint64_t* labels, const float* vecs /* n x dim row-major, host */);
+/* RemovePoint (swap-with-last compaction)                     hnswlib/bruteforce.cc:70-86 */
+int rxgpu_index_remove(rxgpu_index*, uint64_t label);
+/* FloatPtrByExternalLabel                                     hnswlib/bruteforce.cc:36-42
+ * with RXGPU_FLAG_HOST_MIRROR the pointer stays valid until the row is modified; without it the row is fetched into a
+ * thread-local buffer that the next rxgpu_index_get() on the same thread overwrites. */
+int rxgpu_index_get(const rxgpu_index*, uint64_t label, const float** host_row);
+uint64_t rxgpu_index_size(const rxgpu_index*);         /* CurrentElementCount() */
+uint64_t rxgpu_index_capacity(const rxgpu_index*);     /* MaxElements() */
+uint64_t rxgpu_index_element_size(const rxgpu_index*); /* ElementSize() = dim*4 + 8, asserted by the reference's memstat test */
+uint64_t rxgpu_index_device_bytes(const rxgpu_index*); /* HBM held by this shard */
+uint32_t rxgpu_index_dim(const rxgpu_index*);
+int rxgpu_index_metric(const rxgpu_index*);
+int rxgpu_index_device(const rxgpu_index*);
+
+/* ---------------------------------------------------------------- search
+ * BruteforceSearch::SearchKnn, batched                        hnswlib/bruteforce.cc:103-127
+ * nq independent queries (the reference API is one query per call; nq > 1 is our extension, results identical to nq
+ * calls).  Per query: rows sorted best->worst exactly as HnswIndexBase::select drains the reference's max-heap
+ * (hnsw_index.cc:258-276), including the reference's tie rule (which of several bit-equal distances survive depends on
+ * insertion order and label, SURVEY.md §8a rule 2).  out_count[q] = min(k, size). */
+int rxgpu_search_knn(const rxgpu_index*, uint32_t nq, const float* queries /* nq x dim, host */, uint32_t k,
+					 float* out_dist /* nq x k */, uint64_t* out_label /* nq x k */, uint32_t* out_count /* nq */);
+/* BruteforceSearch::SearchRange (strict dist < radius)        hnswlib/bruteforce.cc:129-143
+ * writes the best min(*out_n, max_out) results best-first; *out_n = total number of matches (may exceed max_out). */
+int rxgpu_search_range(const rxgpu_index*, const float* query, float radius, uint64_t max_out, float* out_dist, uint64_t* out_label,
+					   uint64_t* out_n);
+
+/* Same scan with queries and outputs resident in HBM (device pointers), enqueued on `stream` (a cudaStream_t; NULL =
+ * the library's own stream).  Used by the benchmark's device-resident leg and by the multi-GPU shard merge.
+ * Outputs hold the top-k1 rows per query under the total order (distance, internal row index): out_idx is the shard-local
+ * internal index (insertion order with swap-deletes, as in the reference).  No tie replay is applied here. */
+int rxgpu_search_knn_device(const rxgpu_index*, uint32_t nq, const float* d_queries, uint32_t k1, float* d_out_dist,
+							uint32_t* d_out_idx, uint64_t* d_out_label, uint32_t* d_out_count, void* stream);
+/* rows with dist <= dstar in internal order: the first k of them (device in/out, one query); feeds the tie replay */
+int rxgpu_search_tie_rows_device(const rxgpu_index*, const float* d_query, float dstar, uint32_t k, float* d_out_dist,
+								 uint32_t* d_out_idx, uint64_t* d_out_label, uint32_t* d_out_count, void* stream);
+
+/* ---------------------------------------------------------------- shard merge (multi-GPU row of SURVEY.md §8e)
+ * Host-side, deterministic.  Inputs: nshards lists per query, each the output of rxgpu_search_knn_device copied to the host
+ * (k1 = k + 1 entries so that a tie at the k-th place is visible), shard s holding global rows [base[s], base[s+1]).
+ * Output: global top-k under (distance, global row index) and need_tie[q] != 0 where the reference's tie rule must be
+ * replayed with rxgpu_tie_replay(). */
+int rxgpu_merge_shards(uint32_t nshards, uint32_t nq, uint32_t k, uint32_t k1, const float* dist /* nshards x nq x k1 */,
+					   const uint32_t* idx, const uint64_t* label, const uint32_t* count /* nshards x nq */,
+					   const uint64_t* shard_base /* nshards */, float* out_dist /* nq x k */, uint64_t* out_gidx,
+					   uint64_t* out_label, uint32_t* out_count, uint8_t* need_tie /* nq */);
+/* The reference's heap tie rule in closed form (SURVEY.md §8a rule 2; derivation in DESIGN.md):
+ *  lower   = the m < k rows with dist < dstar (global index + label), from the merged top-k
+ *  first   = the first min(k, .) rows in global internal order with dist <= dstar (from rxgpu_search_tie_rows_device,
+ *            merged over shards by global index)
+ * writes the k survivors best-first into out_*. */
+int rxgpu_tie_replay(uint32_t k, float dstar, uint32_t n_lower, const float* lower_dist, const uint64_t* lower_gidx,
+					 const uint64_t* lower_label, uint32_t n_first, const float* first_dist, const uint64_t* first_gidx,
+					 const uint64_t* first_label, float* out_dist, uint64_t* out_label, uint32_t* out_count);
+
+/* ---------------------------------------------------------------- FloatVectorIndex::Select equivalent
+ * HnswIndexBase<BruteforceSearch>::search + select/selectRaw   core/index/float_vector/hnsw_index.cc:160-191, 206-229, 232-288
+ * query normalisation for Cosine (tools/normalize.h:16-22), k and/or radius, worst->best drain, sign flip for IP/Cosine,
+ * ascending row ids inside runs of equal rank when need_sort (KnnCtx::NeedSort), array-field dedup by rowId
+ * (float_vector_index.h:141-160) and removeOverK (:194-203). */
+typedef struct {
+	uint32_t k;           /* 0 = not set */
+	int has_radius;       /* params.Radius() or the index-level radius */
+	float radius;         /* user-space: squared distance for L2, similarity for IP / Cosine */
+	int need_sort;        /* KnnCtx::NeedSort() */
+	int is_array;         /* index over an array field */
+	int raw;              /* selectRaw(): no tie sort */
+} rxgpu_select_params;
+int rxgpu_select_knn(const rxgpu_index*, const float* query /* dim floats, NOT normalised */, const rxgpu_select_params*,
+					 uint64_t max_out, int32_t* out_row_ids, float* out_ranks, uint64_t* out_n);
+
+/* ---------------------------------------------------------------- benchmark / test support (not part of the reference surface)
+ * Appends n rows generated on the device: element (row r, col c) = synth(seed, (first_row + r) * dim + c), label =
+ * (first_row + r) << 32.  The generator is defined in csrc/synth.cuh and mirrored bit-for-bit by oracle/knn_port.c. */
+int rxgpu_index_append_synth(rxgpu_index*, uint64_t seed, uint64_t first_row, uint64_t n);
+/* fills a device buffer with synth(seed, first_index + i) */
+int rxgpu_synth_fill_device(float* d_out, uint64_t seed, uint64_t first_index, uint64_t count, int device, void* stream);
+/* tuning knobs, mainly for benchmarks: queries per DB pass (0 = auto) */
+int rxgpu_set_query_tile(rxgpu_index*, uint32_t qt);
+/* statistics of the last search on this thread: kernel launches, DB passes */
+typedef struct {
+	uint32_t launches;
+	uint32_t passes;
+	uint32_t query_tile;
+	uint32_t tie_replays;
+	uint64_t algorithmic_bytes; /* SURVEY.md §8d definition: passes x (N*D*4 [+N*4 for Cosine] + QT*D*4 + QT*k*12) */
+	uint32_t scan_launches;     /* with rxgpu_set_profile(1): scan-kernel launches timed ... */
+	float scan_kernel_ms;       /* ... and their summed device time (CUDA events on the launching stream) */
+} rxgpu_search_stats;
+void rxgpu_last_search_stats(rxgpu_search_stats* out);
+/* process-wide switch: bracket every scan-kernel launch with CUDA events (used by bench.py for the roofline figure) */
+int rxgpu_set_profile(int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RXGPU_H */

@@ -1,0 +1,263 @@
+"""ctypes binding of librxgpu.so (C ABI: include/rxgpu.h).
+
+Python is only the test / benchmark / multi-GPU driver here; the product is the C-ABI library plus the C++ adapter
+(reindexer_b200/host/gpu_bruteforce.h).  Method names follow the reference's ``Map`` duck-type
+(hnswlib::BruteforceSearch, cpp_src/core/index/float_vector/hnswlib/bruteforce.h).  There is no CPU fallback: every
+compute call raises RxGpuError when the CUDA extension or a device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librxgpu.so")
+
+L2, IP, COS = 0, 1, 2
+FLAG_HOST_MIRROR = 1
+
+_f32p = C.POINTER(C.c_float)
+_u64p = C.POINTER(C.c_uint64)
+_u32p = C.POINTER(C.c_uint32)
+_i32p = C.POINTER(C.c_int32)
+_u8p = C.POINTER(C.c_uint8)
+
+
+class RxGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+        self.what = msg
+
+
+class SelectParams(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("has_radius", C.c_int), ("radius", C.c_float), ("need_sort", C.c_int), ("is_array", C.c_int),
+                ("raw", C.c_int)]
+
+
+class SearchStats(C.Structure):
+    _fields_ = [("launches", C.c_uint32), ("passes", C.c_uint32), ("query_tile", C.c_uint32), ("tie_replays", C.c_uint32),
+                ("algorithmic_bytes", C.c_uint64), ("scan_launches", C.c_uint32), ("scan_kernel_ms", C.c_float)]
+
+
+# every symbol include/rxgpu.h declares (checked by tests/test_abi.py against the header text)
+_SIGNATURES = {
+    "rxgpu_last_error": (C.c_char_p, []),
+    "rxgpu_abi_version": (C.c_int, []),
+    "rxgpu_device_count": (C.c_int, []),
+    "rxgpu_index_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_uint32, C.c_uint64, C.c_int, C.c_uint32]),
+    "rxgpu_index_clone": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_uint64]),
+    "rxgpu_index_destroy": (None, [C.c_void_p]),
+    "rxgpu_index_resize": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "rxgpu_index_upsert": (C.c_int, [C.c_void_p, C.c_uint64, _f32p]),
+    "rxgpu_index_upsert_batch": (C.c_int, [C.c_void_p, C.c_uint64, _u64p, _f32p]),
+    "rxgpu_index_remove": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "rxgpu_index_get": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(_f32p)]),
+    "rxgpu_index_size": (C.c_uint64, [C.c_void_p]),
+    "rxgpu_index_capacity": (C.c_uint64, [C.c_void_p]),
+    "rxgpu_index_element_size": (C.c_uint64, [C.c_void_p]),
+    "rxgpu_index_device_bytes": (C.c_uint64, [C.c_void_p]),
+    "rxgpu_index_dim": (C.c_uint32, [C.c_void_p]),
+    "rxgpu_index_metric": (C.c_int, [C.c_void_p]),
+    "rxgpu_index_device": (C.c_int, [C.c_void_p]),
+    "rxgpu_search_knn": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, C.c_uint32, _f32p, _u64p, _u32p]),
+    "rxgpu_search_range": (C.c_int, [C.c_void_p, _f32p, C.c_float, C.c_uint64, _f32p, _u64p, _u64p]),
+    "rxgpu_search_knn_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]),
+    "rxgpu_search_tie_rows_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p]),
+    "rxgpu_merge_shards": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _f32p, _u32p, _u64p, _u32p, _u64p, _f32p, _u64p,
+                                     _u64p, _u32p, _u8p]),
+    "rxgpu_tie_replay": (C.c_int, [C.c_uint32, C.c_float, C.c_uint32, _f32p, _u64p, _u64p, C.c_uint32, _f32p, _u64p, _u64p, _f32p,
+                                   _u64p, _u32p]),
+    "rxgpu_select_knn": (C.c_int, [C.c_void_p, _f32p, C.POINTER(SelectParams), C.c_uint64, _i32p, _f32p, _u64p]),
+    "rxgpu_index_append_synth": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "rxgpu_synth_fill_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]),
+    "rxgpu_set_query_tile": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "rxgpu_last_search_stats": (None, [C.POINTER(SearchStats)]),
+    "rxgpu_set_profile": (C.c_int, [C.c_int]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load librxgpu.so; fails loudly when it has not been built (``python -c 'import __graft_entry__ as g; g.build()'``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RxGpuError(37, f"{LIB_PATH} is missing: build the CUDA extension first (no CPU fallback exists)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise RxGpuError(rc, lib().rxgpu_last_error().decode(errors="replace"))
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def device_count() -> int:
+    return lib().rxgpu_device_count()
+
+
+def last_search_stats() -> dict:
+    s = SearchStats()
+    lib().rxgpu_last_search_stats(C.byref(s))
+    return {f: getattr(s, f) for f, _ in SearchStats._fields_}
+
+
+class GpuBruteforceSearch:
+    """One shard of a float_vector brute-force index resident in the HBM of one GPU."""
+
+    def __init__(self, metric: int, dim: int, capacity: int, device: int = 0, host_mirror: bool = False, _handle=None):
+        self._lib = lib()
+        self.metric, self.dim = metric, dim
+        if _handle is not None:
+            self._h = _handle
+            return
+        h = C.c_void_p()
+        _check(self._lib.rxgpu_index_create(C.byref(h), metric, dim, capacity, device, FLAG_HOST_MIRROR if host_mirror else 0))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rxgpu_index_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    # -- BruteforceSearch surface ------------------------------------------------------------------------------------
+    def clone(self, new_capacity: int) -> "GpuBruteforceSearch":
+        h = C.c_void_p()
+        _check(self._lib.rxgpu_index_clone(C.byref(h), self._h, new_capacity))
+        return GpuBruteforceSearch(self.metric, self.dim, new_capacity, _handle=h)
+
+    def max_elements(self) -> int:
+        return self._lib.rxgpu_index_capacity(self._h)
+
+    def current_element_count(self) -> int:
+        return self._lib.rxgpu_index_size(self._h)
+
+    size = current_element_count
+
+    def element_size(self) -> int:
+        return self._lib.rxgpu_index_element_size(self._h)
+
+    def device_bytes(self) -> int:
+        return self._lib.rxgpu_index_device_bytes(self._h)
+
+    def add_point(self, vec, label: int):
+        vec = np.ascontiguousarray(vec, dtype=np.float32)
+        assert vec.size == self.dim
+        _check(self._lib.rxgpu_index_upsert(self._h, label, _p(vec, _f32p)))
+
+    def add_points(self, labels, vecs):
+        vecs = np.ascontiguousarray(vecs, dtype=np.float32)
+        labels = np.ascontiguousarray(labels, dtype=np.uint64)
+        assert vecs.shape == (len(labels), self.dim)
+        _check(self._lib.rxgpu_index_upsert_batch(self._h, len(labels), _p(labels, _u64p), _p(vecs, _f32p)))
+
+    def remove_point(self, label: int):
+        _check(self._lib.rxgpu_index_remove(self._h, label))
+
+    def resize_index(self, new_capacity: int):
+        _check(self._lib.rxgpu_index_resize(self._h, new_capacity))
+
+    def float_ptr_by_external_label(self, label: int) -> np.ndarray:
+        p = _f32p()
+        _check(self._lib.rxgpu_index_get(self._h, label, C.byref(p)))
+        return np.ctypeslib.as_array(p, (self.dim,)).copy()
+
+    def search_knn(self, queries, k: int):
+        """queries: [nq, dim] (or [dim]); returns (dists [nq,k], labels [nq,k], counts [nq]) best-first, map-space sign."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        single = q.ndim == 1
+        q = q.reshape(-1, self.dim)
+        nq = q.shape[0]
+        d = np.zeros((nq, max(k, 1)), np.float32)
+        l = np.zeros((nq, max(k, 1)), np.uint64)
+        c = np.zeros(nq, np.uint32)
+        _check(self._lib.rxgpu_search_knn(self._h, nq, _p(q, _f32p), k, _p(d, _f32p), _p(l, _u64p), _p(c, _u32p)))
+        if single:
+            return d[0, :c[0]], l[0, :c[0]]
+        return d[:, :k], l[:, :k], c
+
+    def search_range(self, query, radius: float, max_out: int | None = None):
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        max_out = self.size() if max_out is None else max_out
+        d = np.zeros(max(max_out, 1), np.float32)
+        l = np.zeros(max(max_out, 1), np.uint64)
+        n = C.c_uint64(0)
+        _check(self._lib.rxgpu_search_range(self._h, _p(q, _f32p), radius, max_out, _p(d, _f32p), _p(l, _u64p), C.byref(n)))
+        m = min(n.value, max_out)
+        return d[:m], l[:m], n.value
+
+    def select(self, query, k: int | None = None, radius: float | None = None, need_sort=True, is_array=False, raw=False,
+               max_out: int | None = None):
+        """FloatVectorIndex::Select equivalent: returns (row_ids int32, ranks float32)."""
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        prm = SelectParams(k or 0, int(radius is not None), float(radius or 0.0), int(need_sort), int(is_array), int(raw))
+        max_out = max_out if max_out is not None else max(self.size(), 1)
+        ids = np.zeros(max_out, np.int32)
+        ranks = np.zeros(max_out, np.float32)
+        n = C.c_uint64(0)
+        _check(self._lib.rxgpu_select_knn(self._h, _p(q, _f32p), C.byref(prm), max_out, _p(ids, _i32p), _p(ranks, _f32p), C.byref(n)))
+        m = min(n.value, max_out)
+        return ids[:m], ranks[:m]
+
+    # -- device-resident entry points ----------------------------------------------------------------------------------
+    def search_knn_device(self, nq, d_queries_ptr, k1, d_dist_ptr, d_idx_ptr, d_label_ptr, d_count_ptr, stream=0):
+        _check(self._lib.rxgpu_search_knn_device(self._h, nq, d_queries_ptr, k1, d_dist_ptr, d_idx_ptr, d_label_ptr, d_count_ptr,
+                                                 stream or None))
+
+    def search_tie_rows_device(self, d_query_ptr, dstar, k, d_dist_ptr, d_idx_ptr, d_label_ptr, d_count_ptr, stream=0):
+        _check(self._lib.rxgpu_search_tie_rows_device(self._h, d_query_ptr, dstar, k, d_dist_ptr, d_idx_ptr, d_label_ptr, d_count_ptr,
+                                                      stream or None))
+
+    # -- bench / test support ------------------------------------------------------------------------------------------
+    def append_synth(self, seed: int, first_row: int, n: int):
+        _check(self._lib.rxgpu_index_append_synth(self._h, seed, first_row, n))
+
+    def set_query_tile(self, qt: int):
+        _check(self._lib.rxgpu_set_query_tile(self._h, qt))
+
+
+def merge_shards(k, dist, idx, label, count, shard_base):
+    """dist/idx/label: [nshards, nq, k1]; count: [nshards, nq]; returns (dist, gidx, label, count, need_tie)."""
+    dist = np.ascontiguousarray(dist, np.float32)
+    idx = np.ascontiguousarray(idx, np.uint32)
+    label = np.ascontiguousarray(label, np.uint64)
+    count = np.ascontiguousarray(count, np.uint32)
+    base = np.ascontiguousarray(shard_base, np.uint64)
+    ns, nq, k1 = dist.shape
+    od = np.zeros((nq, max(k, 1)), np.float32)
+    og = np.zeros((nq, max(k, 1)), np.uint64)
+    ol = np.zeros((nq, max(k, 1)), np.uint64)
+    oc = np.zeros(nq, np.uint32)
+    nt = np.zeros(nq, np.uint8)
+    _check(lib().rxgpu_merge_shards(ns, nq, k, k1, _p(dist, _f32p), _p(idx, _u32p), _p(label, _u64p), _p(count, _u32p), _p(base, _u64p),
+                                    _p(od, _f32p), _p(og, _u64p), _p(ol, _u64p), _p(oc, _u32p), _p(nt, _u8p)))
+    return od, og, ol, oc, nt
+
+
+def tie_replay(k, dstar, lower, first):
+    """lower / first: tuples (dist, gidx, label) of equal-length arrays; returns (dist, label)."""
+    ld, lg, ll = (np.ascontiguousarray(a, t) for a, t in zip(lower, (np.float32, np.uint64, np.uint64)))
+    fd, fg, fl = (np.ascontiguousarray(a, t) for a, t in zip(first, (np.float32, np.uint64, np.uint64)))
+    od = np.zeros(max(k, 1), np.float32)
+    ol = np.zeros(max(k, 1), np.uint64)
+    oc = C.c_uint32(0)
+    _check(lib().rxgpu_tie_replay(k, dstar, len(ld), _p(ld, _f32p), _p(lg, _u64p), _p(ll, _u64p), len(fd), _p(fd, _f32p), _p(fg, _u64p),
+                                  _p(fl, _u64p), _p(od, _f32p), _p(ol, _u64p), C.byref(oc)))
+    return od[:oc.value], ol[:oc.value]

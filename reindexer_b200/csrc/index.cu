@@ -1,0 +1,1104 @@
+// librxgpu: C ABI (include/rxgpu.h) over the sm_100a brute-force float_vector kernels.
+// Host logic mirrors hnswlib::BruteforceSearch (cpp_src/core/index/float_vector/hnswlib/bruteforce.{h,cc}) and the
+// search/select wrappers of HnswIndexBase<Map> (cpp_src/core/index/float_vector/hnsw_index.cc:160-288).
+// There is no CPU fallback anywhere in this file: without a usable CUDA device every compute entry point fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rxgpu.h"
+#include "../host/flat_map.h"
+#include "../host/knn_select.h"
+#include "knn_scan.cuh"
+
+using namespace rxgpu;
+
+namespace {
+
+thread_local std::string g_err;
+thread_local rxgpu_search_stats g_stats{};
+thread_local std::vector<float> g_row_scratch;
+thread_local std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+std::atomic<int> g_profile{0};
+
+// sum the event pairs recorded by this thread's launches; call after the stream has been synchronised
+void collectProfile() {
+	for (auto& ev : g_prof_events) {
+		float ms = 0.f;
+		if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) {
+			g_stats.scan_kernel_ms += ms;
+			g_stats.scan_launches += 1;
+		}
+		cudaEventDestroy(ev.first);
+		cudaEventDestroy(ev.second);
+	}
+	g_prof_events.clear();
+}
+
+int fail(int code, std::string msg) {
+	g_err = std::move(msg);
+	return code;
+}
+
+#define RX_CUDA(expr)                                                                                        \
+	do {                                                                                                     \
+		cudaError_t e_ = (expr);                                                                             \
+		if (e_ != cudaSuccess) {                                                                             \
+			return fail(RXGPU_ERR_SYSTEM, std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #expr); \
+		}                                                                                                    \
+	} while (0)
+
+template <typename T>
+struct DevBuf {
+	T* p = nullptr;
+	size_t n = 0;
+	~DevBuf() { release(); }
+	void release() {
+		if (p) {
+			cudaFree(p);
+			p = nullptr;
+			n = 0;
+		}
+	}
+	cudaError_t ensure(size_t want) {
+		if (want <= n) {
+			return cudaSuccess;
+		}
+		release();
+		cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T));
+		if (e == cudaSuccess) {
+			n = want;
+		}
+		return e;
+	}
+};
+template <typename T>
+struct PinBuf {
+	T* p = nullptr;
+	size_t n = 0;
+	~PinBuf() {
+		if (p) {
+			cudaFreeHost(p);
+		}
+	}
+	cudaError_t ensure(size_t want) {
+		if (want <= n) {
+			return cudaSuccess;
+		}
+		if (p) {
+			cudaFreeHost(p);
+			p = nullptr;
+			n = 0;
+		}
+		cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&p), want * sizeof(T));
+		if (e == cudaSuccess) {
+			n = want;
+		}
+		return e;
+	}
+};
+
+// per-call scratch: searches are re-entrant, each takes one workspace from the pool
+struct Workspace {
+	cudaStream_t stream = nullptr;
+	DevBuf<float> d_queries;
+	DevBuf<uint64_t> d_lists;
+	DevBuf<float> d_out_dist;
+	DevBuf<uint32_t> d_out_idx;
+	DevBuf<uint64_t> d_out_label;
+	DevBuf<uint32_t> d_out_count;
+	DevBuf<uint64_t> d_range;
+	DevBuf<unsigned long long> d_range_count;
+	PinBuf<float> h_queries;
+	PinBuf<float> h_out_dist;
+	PinBuf<uint32_t> h_out_idx;
+	PinBuf<uint64_t> h_out_label;
+	PinBuf<uint32_t> h_out_count;
+	PinBuf<uint64_t> h_range;
+	~Workspace() {
+		if (stream) {
+			cudaStreamDestroy(stream);
+		}
+	}
+};
+
+}  // namespace
+
+struct rxgpu_index {
+	int metric = 0;
+	uint32_t dim = 0;
+	uint32_t pitch = 0;  // floats, multiple of 4
+	uint64_t capacity = 0;
+	uint64_t size = 0;
+	int device = 0;
+	uint32_t flags = 0;
+	int sm_count = 148;
+	uint32_t qt_override = 0;
+
+	float* d_rows = nullptr;
+	uint64_t* d_labels = nullptr;
+	float* d_norms = nullptr;  // Cosine only (DistCalculator::normCoefs_, hnswlib.h:33-35)
+
+	std::vector<uint64_t> h_labels;  // by internal index
+	LabelMap dict;
+	std::vector<float> h_rows;  // optional host mirror [capacity][dim]
+
+	cudaStream_t stream = nullptr;  // maintenance stream
+	mutable std::mutex ws_mtx;
+	mutable std::vector<std::unique_ptr<Workspace>> ws_free;
+
+	~rxgpu_index() {
+		cudaSetDevice(device);
+		ws_free.clear();
+		if (d_rows) {
+			cudaFree(d_rows);
+		}
+		if (d_labels) {
+			cudaFree(d_labels);
+		}
+		if (d_norms) {
+			cudaFree(d_norms);
+		}
+		if (stream) {
+			cudaStreamDestroy(stream);
+		}
+	}
+};
+
+namespace {
+
+struct WsLease {
+	const rxgpu_index* idx;
+	std::unique_ptr<Workspace> ws;
+	explicit WsLease(const rxgpu_index* i) : idx(i) {
+		{
+			std::lock_guard<std::mutex> lck(idx->ws_mtx);
+			if (!idx->ws_free.empty()) {
+				ws = std::move(idx->ws_free.back());
+				idx->ws_free.pop_back();
+			}
+		}
+		if (!ws) {
+			ws = std::make_unique<Workspace>();
+		}
+	}
+	~WsLease() {
+		std::lock_guard<std::mutex> lck(idx->ws_mtx);
+		idx->ws_free.emplace_back(std::move(ws));
+	}
+};
+
+int allocDevice(rxgpu_index* ix, uint64_t capacity, float** rows, uint64_t** labels, float** norms) {
+	const size_t cap = capacity ? capacity : 1;
+	RX_CUDA(cudaMalloc(reinterpret_cast<void**>(rows), cap * ix->pitch * sizeof(float)));
+	RX_CUDA(cudaMalloc(reinterpret_cast<void**>(labels), cap * sizeof(uint64_t)));
+	*norms = nullptr;
+	if (ix->metric == RXGPU_COS) {
+		RX_CUDA(cudaMalloc(reinterpret_cast<void**>(norms), cap * sizeof(float)));
+	}
+	return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- launches
+template <int QT, int RW, int CG>
+cudaError_t launchScanT(const rxgpu_index* ix, const ScanArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
+	cudaError_t e;
+	if (ix->metric == RXGPU_L2) {
+		auto kfn = knn_scan_warp<QT, RW, CG, true>;
+		e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+		if (e != cudaSuccess) {
+			return e;
+		}
+		kfn<<<grid, kScanThreads, smem, st>>>(a);
+	} else {
+		auto kfn = knn_scan_warp<QT, RW, CG, false>;
+		e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+		if (e != cudaSuccess) {
+			return e;
+		}
+		kfn<<<grid, kScanThreads, smem, st>>>(a);
+	}
+	return cudaGetLastError();
+}
+
+template <int QT>
+cudaError_t launchScanQ(const rxgpu_index* ix, const ScanArgs& a, uint32_t nch, unsigned* gridOut, cudaStream_t st, bool dryRun) {
+	// chunk group CG divides nch; RW*CG float4 loads in flight per lane
+	int cg, rw;
+	if (nch % 6 == 0) {
+		cg = 6, rw = 2;
+	} else if (nch % 4 == 0) {
+		cg = 4, rw = 2;
+	} else if (nch % 3 == 0) {
+		cg = 3, rw = 4;
+	} else if (nch % 2 == 0) {
+		cg = 2, rw = 4;
+	} else {
+		cg = 1, rw = 8;
+	}
+	const uint32_t nrows = a.row_end - a.row_begin;
+	const uint32_t ngroups = (nrows + rw - 1) / rw;
+	unsigned grid = std::min<unsigned>(unsigned(ix->sm_count) * 2u, std::max<unsigned>(1u, (ngroups + kScanWarps - 1) / kScanWarps));
+	*gridOut = grid;
+	if (dryRun) {
+		return cudaSuccess;
+	}
+	const size_t smem = scan_smem_bytes(QT, a.dim, a.k1);
+	switch (cg) {
+		case 6:
+			return launchScanT<QT, 2, 6>(ix, a, grid, smem, st);
+		case 4:
+			return launchScanT<QT, 2, 4>(ix, a, grid, smem, st);
+		case 3:
+			return launchScanT<QT, 4, 3>(ix, a, grid, smem, st);
+		case 2:
+			return launchScanT<QT, 4, 2>(ix, a, grid, smem, st);
+		default:
+			return launchScanT<QT, 8, 1>(ix, a, grid, smem, st);
+	}
+}
+
+cudaError_t launchScan(const rxgpu_index* ix, int qt, const ScanArgs& a, unsigned* gridOut, cudaStream_t st, bool dryRun = false) {
+	const uint32_t nch = (a.dim + 127u) / 128u;
+	switch (qt) {
+		case 4:
+			return launchScanQ<4>(ix, a, nch, gridOut, st, dryRun);
+		case 2:
+			return launchScanQ<2>(ix, a, nch, gridOut, st, dryRun);
+		default:
+			return launchScanQ<1>(ix, a, nch, gridOut, st, dryRun);
+	}
+}
+
+int pickQueryTile(const rxgpu_index* ix, uint32_t nq) {
+	uint32_t qt = ix->qt_override ? ix->qt_override : (nq >= 4 ? 4u : (nq >= 2 ? 2u : 1u));
+	return qt >= 4 ? 4 : (qt >= 2 ? 2 : 1);
+}
+
+// Top-k1 rows per query under the total order (dist, internal index) -- or, in tie mode, the first k1 rows in internal
+// order with dist <= bound.  Everything stays on the device; results land in d_out_* ([nq][k1]).
+int scanTopK(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, const float* d_queries, uint32_t nq, uint32_t k1, int mode,
+			 float bound, float* d_out_dist, uint32_t* d_out_idx, uint64_t* d_out_label, uint32_t* d_out_count) {
+	const int qt = mode == kModeTieRows ? 1 : pickQueryTile(ix, nq);
+	ScanArgs a{};
+	a.rows = ix->d_rows;
+	a.norm_coefs = ix->metric == RXGPU_COS ? ix->d_norms : nullptr;
+	a.pitch = ix->pitch;
+	a.dim = ix->dim;
+	a.row_begin = 0;
+	a.row_end = uint32_t(ix->size);
+	a.k1 = k1;
+	a.mode = mode;
+	a.bound = bound;
+	unsigned grid = 0;
+	RX_CUDA(launchScan(ix, qt, a, &grid, st, true));
+	RX_CUDA(ws.d_lists.ensure(size_t(grid) * qt * k1));
+	a.lists = ws.d_lists.p;
+	if (scan_smem_bytes(qt, ix->dim, k1) > 100 * 1024) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: dimension/k combination exceeds the fused top-k shared-memory budget");
+	}
+	for (uint32_t q0 = 0; q0 < nq; q0 += qt) {
+		a.queries = d_queries + size_t(q0) * ix->dim;
+		a.nq = std::min<uint32_t>(qt, nq - q0);
+		cudaEvent_t e0 = nullptr, e1 = nullptr;
+		if (g_profile.load(std::memory_order_relaxed)) {
+			RX_CUDA(cudaEventCreate(&e0));
+			RX_CUDA(cudaEventCreate(&e1));
+			RX_CUDA(cudaEventRecord(e0, st));
+		}
+		RX_CUDA(launchScan(ix, qt, a, &grid, st));
+		if (e0) {
+			RX_CUDA(cudaEventRecord(e1, st));
+			g_prof_events.emplace_back(e0, e1);
+		}
+		MergeArgs m{};
+		m.lists = ws.d_lists.p;
+		m.labels = ix->d_labels;
+		m.out_dist = d_out_dist;
+		m.out_idx = d_out_idx;
+		m.out_label = d_out_label;
+		m.out_count = d_out_count;
+		m.nlists = grid;
+		m.qt = qt;
+		m.k1 = k1;
+		m.q_offset = q0;
+		m.mode = mode;
+		knn_merge_lists<<<a.nq, 256, 0, st>>>(m);
+		RX_CUDA(cudaGetLastError());
+		g_stats.launches += 2;
+		g_stats.passes += 1;
+	}
+	g_stats.query_tile = uint32_t(qt);
+	const uint64_t perPass = uint64_t(ix->size) * ix->dim * 4 + (ix->metric == RXGPU_COS ? uint64_t(ix->size) * 4 : 0) +
+							 uint64_t(qt) * ix->dim * 4 + uint64_t(qt) * k1 * 12;
+	g_stats.algorithmic_bytes += perPass * ((nq + qt - 1) / qt);
+	return 0;
+}
+
+int checkIndex(const rxgpu_index* ix) {
+	if (!ix) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null index handle");
+	}
+	RX_CUDA(cudaSetDevice(ix->device));
+	return 0;
+}
+
+int normsForRange(rxgpu_index* ix, uint64_t begin, uint64_t end) {
+	if (ix->metric != RXGPU_COS || begin >= end) {
+		return 0;
+	}
+	const uint64_t rows = end - begin;
+	const unsigned blocks = unsigned((rows * 32 + 255) / 256);
+	norm_coef_kernel<<<blocks, 256, 0, ix->stream>>>(ix->d_rows, ix->pitch, ix->dim, uint32_t(begin), uint32_t(end), ix->d_norms);
+	RX_CUDA(cudaGetLastError());
+	return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rxgpu_last_error(void) { return g_err.c_str(); }
+int rxgpu_abi_version(void) { return RXGPU_ABI_VERSION; }
+int rxgpu_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+int rxgpu_index_create(rxgpu_index** out, rxgpu_metric metric, uint32_t dim, uint64_t capacity, int device, uint32_t flags) {
+	if (!out) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null output handle");
+	}
+	*out = nullptr;
+	if (dim == 0 || dim > 65536) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: vector dimension must be in [1, 65536]");
+	}
+	if (int(metric) < 0 || int(metric) > 2) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: unknown vector metric");
+	}
+	if (capacity >= (1ull << 31)) {  // the reference scans with an `int` index (bruteforce.cc:116)
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: capacity must be below 2^31 rows per shard");
+	}
+	if (rxgpu_device_count() <= device || device < 0) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: no usable CUDA device (this library has no CPU fallback)");
+	}
+	RX_CUDA(cudaSetDevice(device));
+	std::unique_ptr<rxgpu_index> ix;
+	try {
+		ix = std::make_unique<rxgpu_index>();
+		ix->metric = int(metric);
+		ix->dim = dim;
+		ix->pitch = (dim + 3u) & ~3u;
+		ix->capacity = capacity;
+		ix->device = device;
+		ix->flags = flags;
+		ix->h_labels.reserve(capacity);
+		ix->dict.reserve(capacity);
+		if (flags & RXGPU_FLAG_HOST_MIRROR) {
+			ix->h_rows.resize(size_t(capacity) * dim);
+		}
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "Not enough memory: BruteforceSearch failed to allocate data");
+	}
+	cudaDeviceProp prop{};
+	RX_CUDA(cudaGetDeviceProperties(&prop, device));
+	ix->sm_count = prop.multiProcessorCount;
+	RX_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+	if (int rc = allocDevice(ix.get(), capacity, &ix->d_rows, &ix->d_labels, &ix->d_norms)) {
+		return rc;
+	}
+	*out = ix.release();
+	return 0;
+}
+
+int rxgpu_index_clone(rxgpu_index** out, const rxgpu_index* src, uint64_t new_capacity) {
+	if (!out || !src) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null handle");
+	}
+	const uint64_t cap = std::max(src->capacity, new_capacity);  // bruteforce.cc:22
+	rxgpu_index* ix = nullptr;
+	if (int rc = rxgpu_index_create(&ix, rxgpu_metric(src->metric), src->dim, cap, src->device, src->flags)) {
+		return rc;
+	}
+	std::unique_ptr<rxgpu_index> guard(ix);
+	try {
+		ix->h_labels = src->h_labels;
+		ix->dict = src->dict;
+		if (src->flags & RXGPU_FLAG_HOST_MIRROR) {
+			std::memcpy(ix->h_rows.data(), src->h_rows.data(), size_t(src->size) * src->dim * sizeof(float));
+		}
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "Not enough memory: BruteforceSearch failed to allocate data");
+	}
+	ix->size = src->size;
+	ix->qt_override = src->qt_override;
+	RX_CUDA(cudaMemcpyAsync(ix->d_rows, src->d_rows, size_t(src->size) * src->pitch * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+	RX_CUDA(cudaMemcpyAsync(ix->d_labels, src->d_labels, size_t(src->size) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ix->stream));
+	if (src->d_norms) {
+		RX_CUDA(cudaMemcpyAsync(ix->d_norms, src->d_norms, size_t(src->size) * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+	}
+	RX_CUDA(cudaStreamSynchronize(ix->stream));
+	*out = guard.release();
+	return 0;
+}
+
+void rxgpu_index_destroy(rxgpu_index* ix) { delete ix; }
+
+int rxgpu_index_resize(rxgpu_index* ix, uint64_t new_capacity) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	if (new_capacity < ix->size) {
+		return fail(RXGPU_ERR_LOGIC, "Cannot resize, max element is less than the current number of elements");
+	}
+	if (new_capacity >= (1ull << 31)) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: capacity must be below 2^31 rows per shard");
+	}
+	if (new_capacity == ix->capacity) {
+		return 0;
+	}
+	float *rows = nullptr, *norms = nullptr;
+	uint64_t* labels = nullptr;
+	if (int rc = allocDevice(ix, new_capacity, &rows, &labels, &norms)) {
+		cudaFree(rows);
+		cudaFree(labels);
+		cudaFree(norms);
+		return fail(RXGPU_ERR_SYSTEM, "Not enough memory: resizeIndex failed to allocate data");
+	}
+	RX_CUDA(cudaMemcpyAsync(rows, ix->d_rows, size_t(ix->size) * ix->pitch * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+	RX_CUDA(cudaMemcpyAsync(labels, ix->d_labels, size_t(ix->size) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ix->stream));
+	if (norms) {
+		RX_CUDA(cudaMemcpyAsync(norms, ix->d_norms, size_t(ix->size) * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+	}
+	RX_CUDA(cudaStreamSynchronize(ix->stream));
+	cudaFree(ix->d_rows);
+	cudaFree(ix->d_labels);
+	cudaFree(ix->d_norms);
+	ix->d_rows = rows;
+	ix->d_labels = labels;
+	ix->d_norms = norms;
+	ix->capacity = new_capacity;
+	try {
+		if (ix->flags & RXGPU_FLAG_HOST_MIRROR) {
+			ix->h_rows.resize(size_t(new_capacity) * ix->dim);
+		}
+		ix->h_labels.reserve(new_capacity);
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "Not enough memory: resizeIndex failed to allocate data");
+	}
+	return 0;
+}
+
+int rxgpu_index_upsert_batch(rxgpu_index* ix, uint64_t n, const uint64_t* labels, const float* vecs) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	if (n == 0) {
+		return 0;
+	}
+	if (!labels || !vecs) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null labels / vectors");
+	}
+	// resolve destinations sequentially, exactly like n AddPointNoLock calls (bruteforce.cc:44-64)
+	std::vector<uint32_t> dst(n);
+	uint64_t newSize = ix->size;
+	bool pureAppend = true;
+	uint64_t accepted = n;
+	for (uint64_t i = 0; i < n; ++i) {
+		uint32_t idx = ix->dict.find(labels[i]);
+		if (idx == LabelMap::kNotFound) {
+			if (newSize >= ix->capacity) {
+				accepted = i;  // rows before i are applied, like the reference's sequential calls
+				break;
+			}
+			idx = uint32_t(newSize++);
+			ix->dict.put(labels[i], idx);
+			ix->h_labels.push_back(labels[i]);
+		} else {
+			pureAppend = false;
+		}
+		dst[i] = idx;
+	}
+	const uint64_t m = accepted;
+	if (m) {
+		if (ix->flags & RXGPU_FLAG_HOST_MIRROR) {
+			for (uint64_t i = 0; i < m; ++i) {
+				std::memcpy(ix->h_rows.data() + size_t(dst[i]) * ix->dim, vecs + i * ix->dim, ix->dim * sizeof(float));
+			}
+		}
+		if (pureAppend && ix->pitch == ix->dim) {
+			RX_CUDA(cudaMemcpyAsync(ix->d_rows + size_t(ix->size) * ix->pitch, vecs, size_t(m) * ix->dim * sizeof(float),
+									cudaMemcpyHostToDevice, ix->stream));
+			RX_CUDA(cudaMemcpyAsync(ix->d_labels + ix->size, labels, size_t(m) * sizeof(uint64_t), cudaMemcpyHostToDevice, ix->stream));
+			if (int rc = normsForRange(ix, ix->size, ix->size + m)) {
+				return rc;
+			}
+		} else {
+			// stage + scatter in bounded slices
+			const uint64_t slice = std::max<uint64_t>(1, (64ull << 20) / (ix->dim * sizeof(float)));
+			DevBuf<float> st;
+			DevBuf<uint32_t> sd;
+			DevBuf<uint64_t> sl;
+			RX_CUDA(st.ensure(size_t(std::min(slice, m)) * ix->dim));
+			RX_CUDA(sd.ensure(size_t(std::min(slice, m))));
+			RX_CUDA(sl.ensure(size_t(std::min(slice, m))));
+			for (uint64_t off = 0; off < m; off += slice) {
+				const uint64_t cnt = std::min(slice, m - off);
+				RX_CUDA(cudaMemcpyAsync(st.p, vecs + off * ix->dim, size_t(cnt) * ix->dim * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+				RX_CUDA(cudaMemcpyAsync(sd.p, dst.data() + off, size_t(cnt) * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
+				RX_CUDA(cudaMemcpyAsync(sl.p, labels + off, size_t(cnt) * sizeof(uint64_t), cudaMemcpyHostToDevice, ix->stream));
+				// duplicates of one label inside a slice must apply in order: fall back to one launch per row when present
+				bool dup = false;
+				{
+					std::vector<uint32_t> sorted(dst.begin() + off, dst.begin() + off + cnt);
+					std::sort(sorted.begin(), sorted.end());
+					dup = std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end();
+				}
+				if (!dup) {
+					scatter_rows_kernel<<<unsigned(cnt), 128, 0, ix->stream>>>(st.p, sd.p, sl.p, uint32_t(cnt), ix->dim, ix->pitch, ix->d_rows,
+																			   ix->d_labels);
+					RX_CUDA(cudaGetLastError());
+				} else {
+					for (uint64_t i = 0; i < cnt; ++i) {
+						scatter_rows_kernel<<<1, 128, 0, ix->stream>>>(st.p + i * ix->dim, sd.p + i, sl.p + i, 1, ix->dim, ix->pitch, ix->d_rows,
+																	   ix->d_labels);
+					}
+					RX_CUDA(cudaGetLastError());
+				}
+				if (ix->metric == RXGPU_COS) {
+					for (uint64_t i = 0; i < cnt;) {  // norms for maximal runs of consecutive destinations
+						uint64_t j = i + 1;
+						while (j < cnt && dst[off + j] == dst[off + j - 1] + 1) {
+							++j;
+						}
+						if (int rc = normsForRange(ix, dst[off + i], uint64_t(dst[off + j - 1]) + 1)) {
+							return rc;
+						}
+						i = j;
+					}
+				}
+				RX_CUDA(cudaStreamSynchronize(ix->stream));
+			}
+		}
+		ix->size = newSize;
+		RX_CUDA(cudaStreamSynchronize(ix->stream));
+	}
+	if (accepted < n) {
+		return fail(RXGPU_ERR_LOGIC, "The number of elements exceeds the specified limit\n");
+	}
+	return 0;
+}
+
+int rxgpu_index_upsert(rxgpu_index* ix, uint64_t label, const float* vec) { return rxgpu_index_upsert_batch(ix, 1, &label, vec); }
+
+int rxgpu_index_remove(rxgpu_index* ix, uint64_t label) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	const uint32_t cur = ix->dict.find(label);
+	if (cur == LabelMap::kNotFound) {
+		return 0;  // bruteforce.cc:72-74
+	}
+	ix->dict.erase(label);
+	const uint64_t last = ix->size - 1;
+	if (cur != last) {  // move the last row into the hole (bruteforce.cc:78-82)
+		const uint64_t lastLabel = ix->h_labels[last];
+		ix->dict.put(lastLabel, cur);
+		ix->h_labels[cur] = lastLabel;
+		RX_CUDA(cudaMemcpyAsync(ix->d_rows + size_t(cur) * ix->pitch, ix->d_rows + size_t(last) * ix->pitch, ix->pitch * sizeof(float),
+								cudaMemcpyDeviceToDevice, ix->stream));
+		RX_CUDA(cudaMemcpyAsync(ix->d_labels + cur, ix->d_labels + last, sizeof(uint64_t), cudaMemcpyDeviceToDevice, ix->stream));
+		if (ix->d_norms) {
+			RX_CUDA(cudaMemcpyAsync(ix->d_norms + cur, ix->d_norms + last, sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+		}
+		if (ix->flags & RXGPU_FLAG_HOST_MIRROR) {
+			std::memcpy(ix->h_rows.data() + size_t(cur) * ix->dim, ix->h_rows.data() + size_t(last) * ix->dim, ix->dim * sizeof(float));
+		}
+		RX_CUDA(cudaStreamSynchronize(ix->stream));
+	}
+	ix->h_labels.pop_back();
+	ix->size--;
+	return 0;
+}
+
+int rxgpu_index_get(const rxgpu_index* ix, uint64_t label, const float** host_row) {
+	if (!ix || !host_row) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null handle");
+	}
+	const uint32_t idx = ix->dict.find(label);
+	if (idx == LabelMap::kNotFound) {
+		return fail(RXGPU_ERR_NOT_FOUND, "Label not found");
+	}
+	if (ix->flags & RXGPU_FLAG_HOST_MIRROR) {
+		*host_row = ix->h_rows.data() + size_t(idx) * ix->dim;
+		return 0;
+	}
+	RX_CUDA(cudaSetDevice(ix->device));
+	g_row_scratch.resize(ix->dim);
+	RX_CUDA(cudaMemcpy(g_row_scratch.data(), ix->d_rows + size_t(idx) * ix->pitch, ix->dim * sizeof(float), cudaMemcpyDeviceToHost));
+	*host_row = g_row_scratch.data();
+	return 0;
+}
+
+uint64_t rxgpu_index_size(const rxgpu_index* ix) { return ix ? ix->size : 0; }
+uint64_t rxgpu_index_capacity(const rxgpu_index* ix) { return ix ? ix->capacity : 0; }
+uint64_t rxgpu_index_element_size(const rxgpu_index* ix) { return ix ? uint64_t(ix->dim) * 4 + 8 : 0; }
+uint64_t rxgpu_index_device_bytes(const rxgpu_index* ix) {
+	if (!ix) {
+		return 0;
+	}
+	const uint64_t cap = ix->capacity ? ix->capacity : 1;
+	return cap * ix->pitch * 4 + cap * 8 + (ix->d_norms ? cap * 4 : 0);
+}
+uint32_t rxgpu_index_dim(const rxgpu_index* ix) { return ix ? ix->dim : 0; }
+int rxgpu_index_metric(const rxgpu_index* ix) { return ix ? ix->metric : -1; }
+int rxgpu_index_device(const rxgpu_index* ix) { return ix ? ix->device : -1; }
+
+int rxgpu_set_query_tile(rxgpu_index* ix, uint32_t qt) {
+	if (!ix) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null handle");
+	}
+	ix->qt_override = qt;
+	return 0;
+}
+int rxgpu_set_profile(int on) {
+	g_profile.store(on ? 1 : 0);
+	return 0;
+}
+void rxgpu_last_search_stats(rxgpu_search_stats* out) {
+	if (out) {
+		*out = g_stats;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------- search
+int rxgpu_search_knn_device(const rxgpu_index* ix, uint32_t nq, const float* d_queries, uint32_t k1, float* d_out_dist,
+							uint32_t* d_out_idx, uint64_t* d_out_label, uint32_t* d_out_count, void* stream) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	g_stats = rxgpu_search_stats{};
+	if (nq == 0) {
+		return 0;
+	}
+	if (k1 == 0 || k1 > kMaxFusedK1) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: k must be in [1, 255] on the fused top-k path");
+	}
+	WsLease lease(ix);
+	Workspace& ws = *lease.ws;
+	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ix->stream;
+	if (ix->size == 0) {
+		RX_CUDA(cudaMemsetAsync(d_out_count, 0, nq * sizeof(uint32_t), st));
+		RX_CUDA(cudaStreamSynchronize(st));
+		return 0;
+	}
+	if (int rc = scanTopK(ix, ws, st, d_queries, nq, k1, kModeTopK, 0.f, d_out_dist, d_out_idx, d_out_label, d_out_count)) {
+		return rc;
+	}
+	RX_CUDA(cudaStreamSynchronize(st));  // the workspace goes back to the pool: nothing of this call may still be running
+	collectProfile();
+	return 0;
+}
+
+int rxgpu_search_tie_rows_device(const rxgpu_index* ix, const float* d_query, float dstar, uint32_t k, float* d_out_dist,
+								 uint32_t* d_out_idx, uint64_t* d_out_label, uint32_t* d_out_count, void* stream) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	if (k == 0 || k > kMaxFusedK1) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: k must be in [1, 255] on the fused top-k path");
+	}
+	WsLease lease(ix);
+	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ix->stream;
+	if (ix->size == 0) {
+		RX_CUDA(cudaMemsetAsync(d_out_count, 0, sizeof(uint32_t), st));
+		RX_CUDA(cudaStreamSynchronize(st));
+		return 0;
+	}
+	if (int rc = scanTopK(ix, *lease.ws, st, d_query, 1, k, kModeTieRows, dstar, d_out_dist, d_out_idx, d_out_label, d_out_count)) {
+		return rc;
+	}
+	RX_CUDA(cudaStreamSynchronize(st));
+	g_stats.tie_replays += 1;
+	return 0;
+}
+
+int rxgpu_merge_shards(uint32_t nshards, uint32_t nq, uint32_t k, uint32_t k1, const float* dist, const uint32_t* idx,
+					   const uint64_t* label, const uint32_t* count, const uint64_t* shard_base, float* out_dist, uint64_t* out_gidx,
+					   uint64_t* out_label, uint32_t* out_count, uint8_t* need_tie) {
+	if (!dist || !idx || !label || !count || !shard_base || !out_dist || !out_gidx || !out_label || !out_count || !need_tie) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	try {
+		std::vector<Hit> all;
+		for (uint32_t q = 0; q < nq; ++q) {
+			all.clear();
+			for (uint32_t s = 0; s < nshards; ++s) {
+				const size_t b = (size_t(s) * nq + q) * k1;
+				const uint32_t c = std::min(count[size_t(s) * nq + q], k1);
+				for (uint32_t j = 0; j < c; ++j) {
+					all.push_back(Hit{dist[b + j], shard_base[s] + idx[b + j], label[b + j]});
+				}
+			}
+			std::sort(all.begin(), all.end(), hitLessByIndex);
+			const uint32_t n = uint32_t(std::min<size_t>(all.size(), k));
+			// a tie straddling the k-th place: the reference's survivors depend on arrival order and labels
+			need_tie[q] = all.size() > k && k > 0 && !(all[k - 1].dist < all[k].dist) ? 1 : 0;
+			std::vector<Hit> top(all.begin(), all.begin() + n);
+			orderTiesByLabel(top);
+			for (uint32_t j = 0; j < n; ++j) {
+				out_dist[size_t(q) * k + j] = top[j].dist;
+				out_gidx[size_t(q) * k + j] = top[j].gidx;
+				out_label[size_t(q) * k + j] = top[j].label;
+			}
+			out_count[q] = n;
+		}
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
+	}
+	return 0;
+}
+
+int rxgpu_tie_replay(uint32_t k, float dstar, uint32_t n_lower, const float* lower_dist, const uint64_t* lower_gidx,
+					 const uint64_t* lower_label, uint32_t n_first, const float* first_dist, const uint64_t* first_gidx,
+					 const uint64_t* first_label, float* out_dist, uint64_t* out_label, uint32_t* out_count) {
+	try {
+		std::vector<Hit> lower(n_lower), first(n_first);
+		for (uint32_t i = 0; i < n_lower; ++i) {
+			lower[i] = Hit{lower_dist[i], lower_gidx[i], lower_label[i]};
+		}
+		for (uint32_t i = 0; i < n_first; ++i) {
+			first[i] = Hit{first_dist[i], first_gidx[i], first_label[i]};
+		}
+		const auto res = tieReplay(k, dstar, lower, first);
+		for (size_t i = 0; i < res.size(); ++i) {
+			out_dist[i] = res[i].dist;
+			out_label[i] = res[i].label;
+		}
+		*out_count = uint32_t(res.size());
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
+	}
+	return 0;
+}
+
+static int searchKnnHost(const rxgpu_index* ix, uint32_t nq, const float* queries, uint32_t k, std::vector<std::vector<Hit>>& results) {
+	results.assign(nq, {});
+	g_stats = rxgpu_search_stats{};
+	if (nq == 0 || k == 0 || ix->size == 0) {
+		return 0;  // bruteforce.cc:106-108
+	}
+	const uint32_t kEff = uint32_t(std::min<uint64_t>(k, ix->size));           // bruteforce.cc:111
+	const uint32_t k1 = uint32_t(std::min<uint64_t>(uint64_t(kEff) + 1, ix->size));  // one extra row exposes a tie at the k-th place
+	if (k1 > kMaxFusedK1) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: k must be in [1, 255] on the fused top-k path");
+	}
+	WsLease lease(ix);
+	Workspace& ws = *lease.ws;
+	if (!ws.stream) {
+		RX_CUDA(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
+	}
+	cudaStream_t st = ws.stream;
+	const size_t qn = size_t(nq) * ix->dim, on = size_t(nq) * k1;
+	RX_CUDA(ws.d_queries.ensure(qn));
+	RX_CUDA(ws.h_queries.ensure(qn));
+	RX_CUDA(ws.d_out_dist.ensure(on));
+	RX_CUDA(ws.d_out_idx.ensure(on));
+	RX_CUDA(ws.d_out_label.ensure(on));
+	RX_CUDA(ws.d_out_count.ensure(nq));
+	RX_CUDA(ws.h_out_dist.ensure(on));
+	RX_CUDA(ws.h_out_idx.ensure(on));
+	RX_CUDA(ws.h_out_label.ensure(on));
+	RX_CUDA(ws.h_out_count.ensure(nq));
+	std::memcpy(ws.h_queries.p, queries, qn * sizeof(float));
+	RX_CUDA(cudaMemcpyAsync(ws.d_queries.p, ws.h_queries.p, qn * sizeof(float), cudaMemcpyHostToDevice, st));
+	if (int rc = scanTopK(ix, ws, st, ws.d_queries.p, nq, k1, kModeTopK, 0.f, ws.d_out_dist.p, ws.d_out_idx.p, ws.d_out_label.p,
+						  ws.d_out_count.p)) {
+		return rc;
+	}
+	RX_CUDA(cudaMemcpyAsync(ws.h_out_dist.p, ws.d_out_dist.p, on * sizeof(float), cudaMemcpyDeviceToHost, st));
+	RX_CUDA(cudaMemcpyAsync(ws.h_out_idx.p, ws.d_out_idx.p, on * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+	RX_CUDA(cudaMemcpyAsync(ws.h_out_label.p, ws.d_out_label.p, on * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+	RX_CUDA(cudaMemcpyAsync(ws.h_out_count.p, ws.d_out_count.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+	RX_CUDA(cudaStreamSynchronize(st));
+	collectProfile();
+
+	for (uint32_t q = 0; q < nq; ++q) {
+		const uint32_t cnt = std::min(ws.h_out_count.p[q], k1);
+		const float* d = ws.h_out_dist.p + size_t(q) * k1;
+		const uint32_t* ii = ws.h_out_idx.p + size_t(q) * k1;
+		const uint64_t* ll = ws.h_out_label.p + size_t(q) * k1;
+		std::vector<Hit>& res = results[q];
+		const uint32_t n = std::min(cnt, kEff);
+		const bool tie = cnt > kEff && !(d[kEff - 1] < d[kEff]);
+		if (!tie) {
+			res.reserve(n);
+			for (uint32_t j = 0; j < n; ++j) {
+				res.push_back(Hit{d[j], ii[j], ll[j]});
+			}
+			orderTiesByLabel(res);
+			continue;
+		}
+		// replay the reference's heap tie rule: fetch the first kEff rows (internal order) with dist <= dstar
+		const float dstar = d[kEff - 1];
+		std::vector<Hit> lower;
+		for (uint32_t j = 0; j < kEff && d[j] < dstar; ++j) {
+			lower.push_back(Hit{d[j], ii[j], ll[j]});
+		}
+		if (int rc = scanTopK(ix, ws, st, ws.d_queries.p + size_t(q) * ix->dim, 1, kEff, kModeTieRows, dstar, ws.d_out_dist.p,
+							  ws.d_out_idx.p, ws.d_out_label.p, ws.d_out_count.p)) {
+			return rc;
+		}
+		std::vector<float> td(kEff);
+		std::vector<uint32_t> ti(kEff);
+		std::vector<uint64_t> tl(kEff);
+		uint32_t tc = 0;
+		RX_CUDA(cudaMemcpyAsync(td.data(), ws.d_out_dist.p, kEff * sizeof(float), cudaMemcpyDeviceToHost, st));
+		RX_CUDA(cudaMemcpyAsync(ti.data(), ws.d_out_idx.p, kEff * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+		RX_CUDA(cudaMemcpyAsync(tl.data(), ws.d_out_label.p, kEff * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+		RX_CUDA(cudaMemcpyAsync(&tc, ws.d_out_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+		RX_CUDA(cudaStreamSynchronize(st));
+		std::vector<Hit> first;
+		for (uint32_t j = 0; j < std::min(tc, kEff); ++j) {
+			first.push_back(Hit{td[j], ti[j], tl[j]});
+		}
+		res = tieReplay(kEff, dstar, lower, first);
+		g_stats.tie_replays += 1;
+	}
+	return 0;
+}
+
+int rxgpu_search_knn(const rxgpu_index* ix, uint32_t nq, const float* queries, uint32_t k, float* out_dist, uint64_t* out_label,
+					 uint32_t* out_count) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	if (nq && (!queries || !out_count || (k && (!out_dist || !out_label)))) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	try {
+		std::vector<std::vector<Hit>> results;
+		if (int rc = searchKnnHost(ix, nq, queries, k, results)) {
+			return rc;
+		}
+		for (uint32_t q = 0; q < nq; ++q) {
+			const auto& r = results[q];
+			for (size_t j = 0; j < r.size(); ++j) {
+				out_dist[size_t(q) * k + j] = r[j].dist;
+				out_label[size_t(q) * k + j] = r[j].label;
+			}
+			out_count[q] = uint32_t(r.size());
+		}
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
+	}
+	return 0;
+}
+
+static int searchRangeHost(const rxgpu_index* ix, const float* query, float radius, std::vector<Hit>& res) {
+	res.clear();
+	g_stats = rxgpu_search_stats{};
+	if (ix->size == 0) {
+		return 0;
+	}
+	WsLease lease(ix);
+	Workspace& ws = *lease.ws;
+	if (!ws.stream) {
+		RX_CUDA(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
+	}
+	cudaStream_t st = ws.stream;
+	RX_CUDA(ws.d_queries.ensure(ix->dim));
+	RX_CUDA(ws.d_range_count.ensure(1));
+	RX_CUDA(cudaMemcpyAsync(ws.d_queries.p, query, ix->dim * sizeof(float), cudaMemcpyHostToDevice, st));
+	uint64_t cap = std::max<uint64_t>(ws.d_range.n, 1u << 16);
+	for (;;) {
+		RX_CUDA(ws.d_range.ensure(cap));
+		RX_CUDA(cudaMemsetAsync(ws.d_range_count.p, 0, sizeof(unsigned long long), st));
+		ScanArgs a{};
+		a.rows = ix->d_rows;
+		a.norm_coefs = ix->metric == RXGPU_COS ? ix->d_norms : nullptr;
+		a.queries = ws.d_queries.p;
+		a.pitch = ix->pitch;
+		a.dim = ix->dim;
+		a.row_begin = 0;
+		a.row_end = uint32_t(ix->size);
+		a.nq = 1;
+		a.k1 = 1;
+		a.mode = kModeRange;
+		a.bound = radius;
+		a.range_out = ws.d_range.p;
+		a.range_count = ws.d_range_count.p;
+		a.range_cap = cap;
+		unsigned grid = 0;
+		RX_CUDA(launchScan(ix, 1, a, &grid, st));
+		g_stats.launches += 1;
+		g_stats.passes += 1;
+		unsigned long long total = 0;
+		RX_CUDA(cudaMemcpyAsync(&total, ws.d_range_count.p, sizeof(total), cudaMemcpyDeviceToHost, st));
+		RX_CUDA(cudaStreamSynchronize(st));
+		if (total > cap) {  // buffer too small: grow and rescan (results are a set, the scan is deterministic)
+			cap = total;
+			continue;
+		}
+		RX_CUDA(ws.h_range.ensure(std::max<uint64_t>(total, 1)));
+		RX_CUDA(cudaMemcpyAsync(ws.h_range.p, ws.d_range.p, total * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+		RX_CUDA(cudaStreamSynchronize(st));
+		res.reserve(total);
+		for (unsigned long long i = 0; i < total; ++i) {
+			const uint64_t key = ws.h_range.p[i];
+			const uint32_t row = uint32_t(key);
+			res.push_back(Hit{ord_float(uint32_t(key >> 32)), row, ix->h_labels[row]});
+		}
+		break;
+	}
+	g_stats.query_tile = 1;
+	g_stats.algorithmic_bytes = uint64_t(ix->size) * ix->dim * 4 + (ix->metric == RXGPU_COS ? uint64_t(ix->size) * 4 : 0) + ix->dim * 4 +
+								res.size() * 8;
+	std::sort(res.begin(), res.end(), hitLessByLabel);  // the order in which the reference's heap drains backwards
+	return 0;
+}
+
+int rxgpu_search_range(const rxgpu_index* ix, const float* query, float radius, uint64_t max_out, float* out_dist, uint64_t* out_label,
+					   uint64_t* out_n) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	if (!query || !out_n) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	try {
+		std::vector<Hit> res;
+		if (int rc = searchRangeHost(ix, query, radius, res)) {
+			return rc;
+		}
+		const uint64_t n = std::min<uint64_t>(res.size(), max_out);
+		for (uint64_t i = 0; i < n; ++i) {
+			out_dist[i] = res[i].dist;
+			out_label[i] = res[i].label;
+		}
+		*out_n = res.size();
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
+	}
+	return 0;
+}
+
+int rxgpu_select_knn(const rxgpu_index* ix, const float* query, const rxgpu_select_params* p, uint64_t max_out, int32_t* out_row_ids,
+					 float* out_ranks, uint64_t* out_n) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	if (!query || !p || !out_n) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	if (p->k == 0 && !p->has_radius) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: KNN query needs k or radius");
+	}
+	try {
+		// HnswIndexBase::search, hnsw_index.cc:160-191
+		std::vector<float> normalized;
+		const float* keyData = query;
+		if (ix->metric == RXGPU_COS) {
+			normalized.resize(ix->dim);
+			normalizeCopyVector(query, int32_t(ix->dim), normalized.data());
+			keyData = normalized.data();
+		}
+		std::vector<Hit> res;
+		if (p->has_radius) {
+			if (int rc = searchRangeHost(ix, keyData, ix->metric == RXGPU_L2 ? p->radius : -p->radius, res)) {
+				return rc;
+			}
+		} else {
+			std::vector<std::vector<Hit>> results;
+			if (int rc = searchKnnHost(ix, 1, keyData, p->k, results)) {
+				return rc;
+			}
+			res = std::move(results[0]);
+		}
+		SelectParams sp;
+		sp.metric = ix->metric;
+		sp.needSort = p->need_sort != 0;
+		sp.isArray = p->is_array != 0;
+		sp.raw = p->raw != 0;
+		sp.hasK = p->k != 0;
+		sp.k = p->k;
+		sp.hasRadius = p->has_radius != 0;
+		std::vector<int32_t> ids;
+		std::vector<float> ranks;
+		selectPostprocess(sp, res, ids, ranks);
+		const uint64_t n = std::min<uint64_t>(ids.size(), max_out);
+		for (uint64_t i = 0; i < n; ++i) {
+			out_row_ids[i] = ids[i];
+			out_ranks[i] = ranks[i];
+		}
+		*out_n = ids.size();
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
+	}
+	return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- bench support
+int rxgpu_index_append_synth(rxgpu_index* ix, uint64_t seed, uint64_t first_row, uint64_t n) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	if (ix->flags & RXGPU_FLAG_HOST_MIRROR) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: device-side synthetic fill is not available with a host mirror");
+	}
+	if (ix->size + n > ix->capacity) {
+		return fail(RXGPU_ERR_LOGIC, "The number of elements exceeds the specified limit\n");
+	}
+	if (n == 0) {
+		return 0;
+	}
+	try {
+		ix->h_labels.reserve(ix->size + n);
+		ix->dict.reserve(ix->size + n);
+		for (uint64_t r = 0; r < n; ++r) {
+			const uint64_t label = (first_row + r) << 32;
+			if (ix->dict.find(label) != LabelMap::kNotFound) {
+				return fail(RXGPU_ERR_LOGIC, "rxgpu: synthetic rows must have fresh labels");
+			}
+			ix->dict.put(label, uint32_t(ix->size + r));
+			ix->h_labels.push_back(label);
+		}
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
+	}
+	synth_rows_kernel<<<unsigned(ix->sm_count) * 8, 256, 0, ix->stream>>>(ix->d_rows, ix->d_labels, ix->pitch, ix->dim, uint32_t(ix->size),
+																		 seed, first_row, n);
+	RX_CUDA(cudaGetLastError());
+	if (int rc = normsForRange(ix, ix->size, ix->size + n)) {
+		return rc;
+	}
+	RX_CUDA(cudaStreamSynchronize(ix->stream));
+	ix->size += n;
+	return 0;
+}
+
+int rxgpu_synth_fill_device(float* d_out, uint64_t seed, uint64_t first_index, uint64_t count, int device, void* stream) {
+	if (rxgpu_device_count() <= device || device < 0) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: no usable CUDA device (this library has no CPU fallback)");
+	}
+	RX_CUDA(cudaSetDevice(device));
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	synth_fill_kernel<<<1184, 256, 0, st>>>(d_out, seed, first_index, count);
+	RX_CUDA(cudaGetLastError());
+	RX_CUDA(cudaStreamSynchronize(st));
+	return 0;
+}
+
+}  // extern "C"

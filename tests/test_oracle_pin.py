@@ -1,0 +1,123 @@
+"""CPU tests: the oracle restatement (oracle/knn_port.c) is pinned against
+ (a) the committed golden fixtures, which are outputs of the reference's own code (tests/golden/make_knn_golden.py), and
+ (b) the reference's own translation units (oracle/_ref) when that library is present (authoring container, GPU box)."""
+import numpy as np
+import pytest
+from conftest import GOLDEN_SYNTH_CASES, GOLDEN_TIE_CASES
+from helpers import ATOL, RTOL, prep_query
+
+from oracle import oracle as O
+
+
+def test_synth_twins_agree():
+    a = O.synth(0x5EED0001, 12345, 4097)
+    b = np.empty(4097, np.float32)
+    O.port_lib().port_synth_fill(0x5EED0001, 12345, 4097, b.ctypes.data_as(O._f32p))
+    assert (a == b).all()
+    big = O.synth(7, 0, 1 << 18)
+    assert abs(big.std() - 0.25) < 0.005 and abs(big.mean()) < 0.005
+
+
+@pytest.mark.parametrize("name", GOLDEN_SYNTH_CASES)
+def test_port_matches_golden_synth(golden, name):
+    metric, n, dim, k, nq, seed = (int(x) for x in golden[f"{name}/meta"])
+    vecs, queries, labels = O.synth_matrix(seed, n, dim), O.synth_matrix(seed + 1, nq, dim), O.row_labels(n)
+    bf = O.PortBF(metric, dim, n)
+    assert bf.add_batch(labels, vecs) == 0
+    for i in range(nq):
+        d, l = bf.search_knn(prep_query(metric, queries[i], use_ref=False), k)
+        cnt = int(golden[f"{name}/count"][i])
+        assert len(d) == cnt == min(k, n)
+        assert (l == golden[f"{name}/label"][i, :cnt]).all()
+        assert np.allclose(d, golden[f"{name}/dist"][i, :cnt], rtol=RTOL, atol=ATOL)
+    rd, rl = bf.search_range(prep_query(metric, queries[0], use_ref=False), float(golden[f"{name}/range_radius"]))
+    assert (rl == golden[f"{name}/range_label"]).all()
+    assert np.allclose(rd, golden[f"{name}/range_dist"], rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("name", GOLDEN_TIE_CASES)
+def test_port_matches_golden_ties(golden, name):
+    metric, n, dim, k, nq, _ = (int(x) for x in golden[f"{name}/meta"])
+    bf = O.PortBF(metric, dim, n)
+    assert bf.add_batch(golden[f"{name}/labels"], golden[f"{name}/vecs"]) == 0
+    for l in golden[f"{name}/removes"]:
+        bf.remove(int(l))
+    for i in range(nq):
+        d, l = bf.search_knn(prep_query(metric, golden[f"{name}/queries"][i], use_ref=False), k)
+        assert (l == golden[f"{name}/label"][i]).all(), (name, i)
+        assert np.allclose(d, golden[f"{name}/dist"][i], rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.skipif(not O.ref_knn_available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("metric", [O.L2, O.IP, O.COS])
+def test_port_matches_reference_build(metric):
+    rng = np.random.default_rng(metric + 11)
+    n, dim, k = 2500, 72, 12
+    vecs, labels = O.synth_matrix(100 + metric, n, dim), O.row_labels(n)
+    p, r = O.PortBF(metric, dim, n + 5), O.RefBF(metric, dim, n + 5)
+    p.add_batch(labels, vecs)
+    r.add_batch(labels, vecs)
+    for l in labels[rng.choice(n, 200, replace=False)]:
+        p.remove(int(l))
+        r.remove(int(l))
+    # upsert over existing labels and fresh ones
+    newv = O.synth_matrix(900 + metric, 50, dim)
+    newl = np.concatenate([labels[rng.choice(n, 25, replace=False)], O.row_labels(25, first_row=n + 100)])
+    p.add_batch(newl, newv)
+    r.add_batch(newl, newv)
+    assert p.size() == r.size() and p.element_size() == r.element_size() == dim * 4 + 8
+    for q in O.synth_matrix(200 + metric, 16, dim):
+        qp, qr = prep_query(metric, q, False), prep_query(metric, q, True)
+        dp, lp = p.search_knn(qp, k)
+        dr, lr = r.search_knn(qr, k)
+        assert (lp == lr).all()
+        assert np.allclose(dp, dr, rtol=RTOL, atol=ATOL)
+        radius = float((dr[5] + dr[6]) / 2)
+        dp, lp = p.search_range(qp, radius)
+        dr2, lr2 = r.search_range(qr, radius)
+        assert (lp == lr2).all() and len(lp) == 6
+    # capacity / resize errors
+    assert p.add(vecs[0], 1 << 50) == 0
+    small_p, small_r = O.PortBF(metric, dim, 2), O.RefBF(metric, dim, 2)
+    for i in range(2):
+        assert small_p.add(vecs[i], i) == 0 and small_r.add(vecs[i], i) == 0
+    assert small_p.add(vecs[2], 2) == 1 and small_r.add(vecs[2], 2) == 1
+    assert "exceeds the specified limit" in small_r._err()
+    assert small_p.resize(1) == 1 and small_r.resize(1) == 1
+
+
+def test_normalize_shortcut():
+    # tools/normalize.cc:19: vectors whose squared norm is within 1e-5 of 1 (or zero) keep coefficient exactly 1.0
+    x = np.zeros(8, np.float32)
+    assert O.normalize_copy(x, False)[1] == 1.0
+    x[0] = 1.0
+    assert O.normalize_copy(x, False)[1] == 1.0
+    x[0] = 3.0
+    out, k = O.normalize_copy(x, False)
+    assert abs(k - 1 / 3) < 1e-7 and abs(out[0] - 1.0) < 1e-6
+    if O.ref_knn_available():
+        for v in (np.zeros(8, np.float32), x, O.synth(3, 0, 100)):
+            a, ka = O.normalize_copy(v, False)
+            b, kb = O.normalize_copy(v, True)
+            assert np.allclose(a, b, rtol=1e-6) and abs(ka - kb) <= 1e-6 * abs(kb)
+
+
+def test_select_postprocess_properties():
+    """checkOrdering of the reference's own test (cpp_src/gtests/tests/unit/float_vector_index.cc:32-86): ranks monotone,
+    equal ranks ordered by ascending row id; IP/Cosine ranks have flipped sign; array fields are de-duplicated by row."""
+    d = np.array([1.0, 1.0, 1.0, 2.0, 3.0, 3.0], np.float32)
+    lab = (np.array([9, 4, 7, 1, 8, 2], np.uint64) << np.uint64(32))
+    # best-first as the heap drains: equal distances arrive in ascending label order
+    order = np.lexsort((lab, d))
+    ids, ranks = O.select_postprocess(O.L2, d[order], lab[order])
+    assert ids.tolist() == [4, 7, 9, 1, 2, 8] and ranks.tolist() == sorted(d.tolist())
+    ids, ranks = O.select_postprocess(O.IP, d[order], lab[order])
+    assert ranks.tolist() == (-np.sort(d)).tolist()
+    # array field: labels rowId<<32|arrayIdx, duplicates of a row keep the best
+    lab2 = np.array([(5 << 32) | 1, (5 << 32) | 0, (3 << 32) | 2, (5 << 32) | 2], np.uint64)
+    d2 = np.array([0.5, 0.6, 0.7, 0.8], np.float32)
+    ids, ranks = O.select_postprocess(O.L2, d2, lab2, is_array=True)
+    assert ids.tolist() == [5, 3] and np.allclose(ranks, [0.5, 0.7])
+    # k + radius => trimmed to k
+    ids, _ = O.select_postprocess(O.L2, d[order], lab[order], k=2, has_radius=True)
+    assert len(ids) == 2
