@@ -89,45 +89,46 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_qps(rows_sample, nq_per_round, rounds, threads):
-    """The reference's own hnswlib::BruteforceSearch::SearchKnn (oracle/_ref, AVX-512 dispatch) -- or the C port when the
-    reference build is absent -- on a bounded sample of the workload: `rows_sample` rows of the same generator, `threads`
-    host threads each issuing independent single-threaded queries (what the reference permits).  Brute force is linear in the
-    row count, so QPS at 10M rows = QPS(sample) * rows_sample / 10M (labelled "extrapolated")."""
-    from oracle import oracle as O
+class CpuReference:
+    """The reference's own hnswlib::BruteforceSearch::SearchKnn (oracle/_ref, runtime ISA dispatch -> AVX-512 here) -- or the C
+    port when the reference build is absent -- on a bounded sample of the workload: `rows_sample` rows of the same generator,
+    `threads` host threads each issuing independent single-threaded queries (the concurrency the reference permits).  Brute
+    force is linear in the row count, so QPS at 10M rows = QPS(sample) * rows_sample / 10M (labelled "extrapolated")."""
 
-    kind = "reference" if O.ref_knn_available() else "port"
-    vecs = np.empty((rows_sample, DIM), np.float32)
-    O.port_lib().port_synth_fill(SEED, 0, rows_sample * DIM, vecs.ctypes.data_as(O._f32p))
-    queries = O.synth_matrix(SEED + 1, nq_per_round, DIM)
-    labels = O.row_labels(rows_sample)
-    if kind == "reference":
-        bf = O.RefBF(O.IP, DIM, rows_sample)
-        assert bf.add_batch(labels, vecs) == 0
-        isa = {3: "avx512", 2: "avx2", 1: "avx", 0: "sse"}[O.ref_knn_lib().ref_isa_level()]
+    def __init__(self, rows_sample, nq_per_round, threads):
+        from oracle import oracle as O
 
-        def run():
-            bf.search_knn_batch(queries, K, threads)
-    else:
-        bf = O.PortBF(O.IP, DIM, rows_sample)
-        assert bf.add_batch(labels, vecs) == 0
-        isa, threads = "scalar-c", 1
+        self.kind = "reference" if O.ref_knn_available() else "port"
+        self.rows_sample, self.nq, self.threads = rows_sample, nq_per_round, threads
+        vecs = np.empty((rows_sample, DIM), np.float32)
+        O.port_lib().port_synth_fill(SEED, 0, rows_sample * DIM, vecs.ctypes.data_as(O._f32p))
+        self.queries = O.synth_matrix(SEED + 1, nq_per_round, DIM)
+        labels = O.row_labels(rows_sample)
+        if self.kind == "reference":
+            self.bf = O.RefBF(O.IP, DIM, rows_sample)
+            self.isa = {3: "avx512", 2: "avx2", 1: "avx", 0: "sse"}[O.ref_knn_lib().ref_isa_level()]
+        else:
+            self.bf = O.PortBF(O.IP, DIM, rows_sample)
+            self.isa, self.threads = "scalar-c", 1
+        assert self.bf.add_batch(labels, vecs) == 0
+        self.round()  # warm-up
 
-        def run():
-            for q in queries:
-                bf.search_knn(q, K)
-    run()  # warm-up
-    times = []
-    for _ in range(rounds):
+    def round(self):
         t0 = time.perf_counter()
-        run()
-        times.append(time.perf_counter() - t0)
-    qps_sample = nq_per_round / (sum(times) / len(times))
-    qps_full = qps_sample * rows_sample / ROWS_FULL
-    return {"value": qps_full, "unit": UNIT, "cores": threads, "kind": kind, "isa": isa,
-            "sample": f"{nq_per_round} queries x {rounds} rounds over {rows_sample} rows x {DIM} (same generator), "
-                      f"{threads} threads; QPS scaled linearly to {ROWS_FULL} rows (extrapolated)",
-            "qps_on_sample": qps_sample, "seconds_per_round": sum(times) / len(times)}
+        if self.kind == "reference":
+            self.bf.search_knn_batch(self.queries, K, self.threads)
+        else:
+            for q in self.queries:
+                self.bf.search_knn(q, K)
+        return time.perf_counter() - t0
+
+    def measure(self, rounds):
+        secs = sum(self.round() for _ in range(rounds)) / rounds
+        qps_sample = self.nq / secs
+        return {"value": qps_sample * self.rows_sample / ROWS_FULL, "unit": UNIT, "cores": self.threads, "kind": self.kind,
+                "isa": self.isa, "qps_on_sample": qps_sample, "seconds_per_round": secs,
+                "sample": f"{self.nq} queries x {rounds} rounds over {self.rows_sample} rows x {DIM} (same generator), "
+                          f"{self.threads} threads; QPS scaled linearly to {ROWS_FULL} rows (extrapolated)"}
 
 
 def run_reference(args):
@@ -135,31 +136,26 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    rows_sample = 200_000
-    nq = max(2 * threads, 16)
-    # size one step to ~2-4 s of wall clock: a single-thread query over 200k x 768 takes ~45 ms
+    ref = CpuReference(200_000, max(2 * threads, 16), threads)
+    per_round = ref.round()
+    rounds_per_step = max(1, int(2.0 / max(per_round, 1e-3)))  # ~2 s of wall clock per step
     t0 = time.perf_counter()
-    base = cpu_reference_qps(rows_sample, nq, 1, threads)
-    per_round = base["seconds_per_round"]
-    rounds_per_step = max(1, int(2.0 / max(per_round, 1e-3)))
+    for _ in range(args.warmup):
+        ref.measure(rounds_per_step)
     vals = []
-    total_steps = args.warmup + args.steps
-    for s in range(total_steps):
-        r = cpu_reference_qps(rows_sample, nq, rounds_per_step, threads) if (s == 0 or True) else None
-        if s >= args.warmup:
-            vals.append(r)
+    for _ in range(args.steps):
+        vals.append(ref.measure(rounds_per_step))
         if time.perf_counter() - t0 > 240:
             break
-    value = float(np.mean([v["value"] for v in vals])) if vals else base["value"]
-    last = vals[-1] if vals else base
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals) or 1,
+    value = float(np.mean([v["value"] for v in vals]))
+    last = vals[-1]
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
             "warmup": args.warmup, "ms_per_step": 1000.0 * NQ / value, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "brute-force KNN, 10M x 768 fp32, inner-product, k=10, batch=1024 queries (BASELINE configs[1])",
                        "rows": ROWS_FULL, "dim": DIM, "k": K, "batch": NQ, "cpu_path": last["kind"], "isa": last["isa"]},
-            "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    line["cpu_baseline"]["value"] = value
     print(json.dumps(line))
 
 
@@ -302,7 +298,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            cb = cpu_reference_qps(200_000, max(2 * threads, 16), 3, threads)
+            cb = CpuReference(200_000, max(2 * threads, 16), threads).measure(3)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "isa")}
         print(json.dumps(line))
     if world > 1:

@@ -36,10 +36,10 @@ class ShardedBruteforceSearch:
     def _all_gather_small(self, t: torch.Tensor) -> torch.Tensor:
         if self.world == 1:
             return t.reshape(1, *t.shape).cpu()
-        t = t.to(self.device)
-        out = torch.empty((self.world, *t.shape), dtype=t.dtype, device=self.device)
-        dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
-        return out.cpu()
+        t = t.to(self.device).contiguous()
+        out = torch.empty((self.world * t.numel(),), dtype=t.dtype, device=self.device)
+        dist.all_gather_into_tensor(out, t.reshape(-1), group=self.group)
+        return out.view(self.world, *t.shape).cpu()
 
     def _device_search(self, d_queries: torch.Tensor, k1: int):
         nq = d_queries.shape[0]
