@@ -131,6 +131,37 @@ typedef struct {
 int rxgpu_select_knn(const rxgpu_index*, const float* query /* dim floats, NOT normalised */, const rxgpu_select_params*,
 					 uint64_t max_out, int32_t* out_row_ids, float* out_ranks, uint64_t* out_n);
 
+/* ---------------------------------------------------------------- HNSW search on a reference-built graph
+ * hnswlib::HierarchicalNSWImpl<float>::SearchKnn                core/index/float_vector/hnswlib/hnswalg.h:1978-2012
+ *   = getLayer0EntryPoint (:799-827) + searchBaseLayerST<bareBone> (:829-975) + trim to k + internal id -> label.
+ * The graph is built by the reference's own CPU code (insert stays on the CPU) and imported here: internal id i
+ * of the graph must be row i of this index (same insertion order, no deleted nodes).  Layout of the arrays = what
+ * hnswalg.h:221-228 / :1034-1040 store per element, de-interleaved:
+ *   level0        n x (1 + maxM0) u32   [count | neighbour ids ...]           (get_linklist0)
+ *   levels        n i32                 element_levels_
+ *   upper_offsets (n + 1) i64           slot of the element's level-1 list; levels 1..L are consecutive slots
+ *   upper         slots x (1 + M) u32   [count | neighbour ids ...]           (get_linklist(id, level)) */
+typedef struct {
+	uint32_t n;
+	uint32_t M;
+	uint32_t maxM0;
+	int32_t maxlevel;
+	uint32_t enterpoint;
+	uint64_t upper_slots;
+	const uint32_t* level0;
+	const int32_t* levels;
+	const int64_t* upper_offsets;
+	const uint32_t* upper;
+} rxgpu_hnsw_graph;
+int rxgpu_hnsw_import(rxgpu_index*, const rxgpu_hnsw_graph* graph);
+/* nq independent searches, one warp each.  ef == 0 -> k*3/2 like hnswalg.h:1995.  Queries pre-normalised for Cosine.
+ * Results best-first in map space, ties by label; out_count[q] <= min(k, ef, n).  stats (may be NULL): per query
+ * [distance computations, hops] -- the reference's metric_distance_computations / metric_hops (hnswalg.h:250-251). */
+int rxgpu_hnsw_search_knn(const rxgpu_index*, uint32_t nq, const float* queries /* host */, uint32_t k, uint32_t ef, float* out_dist,
+						  uint64_t* out_label, uint32_t* out_count, uint32_t* stats /* nq x 2 or NULL */);
+int rxgpu_hnsw_search_knn_device(const rxgpu_index*, uint32_t nq, const float* d_queries, uint32_t k, uint32_t ef, float* d_out_dist,
+								 uint32_t* d_out_idx, uint32_t* d_out_count, uint32_t* d_stats /* nq x 2 or NULL */, void* stream);
+
 /* ---------------------------------------------------------------- benchmark / test support (not part of the reference surface)
  * Appends n rows generated on the device: element (row r, col c) = synth(seed, (first_row + r) * dim + c), label =
  * (first_row + r) << 32.  The generator is defined in csrc/synth.cuh and mirrored bit-for-bit by oracle/knn_port.c. */

@@ -37,6 +37,12 @@ class SelectParams(C.Structure):
                 ("raw", C.c_int)]
 
 
+class HnswGraph(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("M", C.c_uint32), ("maxM0", C.c_uint32), ("maxlevel", C.c_int32), ("enterpoint", C.c_uint32),
+                ("upper_slots", C.c_uint64), ("level0", C.c_void_p), ("levels", C.c_void_p), ("upper_offsets", C.c_void_p),
+                ("upper", C.c_void_p)]
+
+
 class SearchStats(C.Structure):
     _fields_ = [("launches", C.c_uint32), ("passes", C.c_uint32), ("query_tile", C.c_uint32), ("tie_replays", C.c_uint32),
                 ("algorithmic_bytes", C.c_uint64), ("scan_launches", C.c_uint32), ("scan_kernel_ms", C.c_float)]
@@ -73,6 +79,10 @@ _SIGNATURES = {
     "rxgpu_tie_replay": (C.c_int, [C.c_uint32, C.c_float, C.c_uint32, _f32p, _u64p, _u64p, C.c_uint32, _f32p, _u64p, _u64p, _f32p,
                                    _u64p, _u32p]),
     "rxgpu_select_knn": (C.c_int, [C.c_void_p, _f32p, C.POINTER(SelectParams), C.c_uint64, _i32p, _f32p, _u64p]),
+    "rxgpu_hnsw_import": (C.c_int, [C.c_void_p, C.POINTER(HnswGraph)]),
+    "rxgpu_hnsw_search_knn": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, C.c_uint32, C.c_uint32, _f32p, _u64p, _u32p, _u32p]),
+    "rxgpu_hnsw_search_knn_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_void_p]),
     "rxgpu_index_append_synth": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
     "rxgpu_synth_fill_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]),
     "rxgpu_set_query_tile": (C.c_int, [C.c_void_p, C.c_uint32]),
@@ -224,6 +234,29 @@ class GpuBruteforceSearch:
     def search_tie_rows_device(self, d_query_ptr, dstar, k, d_dist_ptr, d_idx_ptr, d_label_ptr, d_count_ptr, stream=0):
         _check(self._lib.rxgpu_search_tie_rows_device(self._h, d_query_ptr, dstar, k, d_dist_ptr, d_idx_ptr, d_label_ptr, d_count_ptr,
                                                       stream or None))
+
+    # -- HNSW (graph built by the reference's CPU code, searched on the device) ---------------------------------------
+    def hnsw_import(self, graph: dict):
+        """graph: arrays as produced by the reference's graph (level0 [n,1+maxM0] u32, levels [n] i32, upper_offsets [n+1] i64,
+        upper [slots,1+M] u32) plus n / M / maxM0 / maxlevel / enterpoint; internal id i must be row i of this index."""
+        l0 = np.ascontiguousarray(graph["level0"], np.uint32)
+        lv = np.ascontiguousarray(graph["levels"], np.int32)
+        uo = np.ascontiguousarray(graph["upper_offsets"], np.int64)
+        up = np.ascontiguousarray(graph["upper"], np.uint32)
+        g = HnswGraph(graph["n"], graph["M"], graph["maxM0"], graph["maxlevel"], graph["enterpoint"], len(up), l0.ctypes.data,
+                      lv.ctypes.data, uo.ctypes.data, up.ctypes.data if len(up) else None)
+        _check(self._lib.rxgpu_hnsw_import(self._h, C.byref(g)))
+
+    def hnsw_search_knn(self, queries, k: int, ef: int = 0, with_stats=False):
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
+        nq = q.shape[0]
+        d = np.zeros((nq, max(k, 1)), np.float32)
+        l = np.zeros((nq, max(k, 1)), np.uint64)
+        c = np.zeros(nq, np.uint32)
+        st = np.zeros((nq, 2), np.uint32)
+        _check(self._lib.rxgpu_hnsw_search_knn(self._h, nq, _p(q, _f32p), k, ef, _p(d, _f32p), _p(l, _u64p), _p(c, _u32p),
+                                               _p(st, _u32p)))
+        return (d, l, c, st) if with_stats else (d, l, c)
 
     # -- bench / test support ------------------------------------------------------------------------------------------
     def append_synth(self, seed: int, first_row: int, n: int):

@@ -1,0 +1,532 @@
+// HNSW search on the device over a graph built by the reference's CPU code.
+//
+// Replaces hnswlib::HierarchicalNSWImpl<float>::SearchKnn (cpp_src/core/index/float_vector/hnswlib/hnswalg.h:1988-2012):
+//   getLayer0EntryPoint  (:799-827)  greedy descent through levels maxlevel..1
+//   searchBaseLayerST<bare_bone=true> (:829-975: initLayer0SearchState, layer0ShouldStopBeforePop, runLayer0Step)
+//   trim to k, internal id -> label
+// One warp per query ("the HNSW neighbour-expansion step becomes a batched gather + distance kernel"): the neighbour list
+// of the expanded node is fetched with one coalesced load, the visited test is a batched atomicOr on a per-warp bitmap in
+// HBM, the rows of all unvisited neighbours are gathered with 128-bit coalesced loads (4 rows in flight per lane) and
+// reduced with the same per-row arithmetic as knn_scan_warp (so a row's distance is bit-identical on both paths), and then
+// the reference's sequential accept logic is replayed over the batch in neighbour order.
+//
+// The reference's two heaps (top_candidates: max-heap of <= ef; candidate_set: min-heap, both ordered by distance only,
+// hnswalg.h:581-585) are represented by ONE list of the <= ef best visited nodes, sorted by distance, each with an "expanded"
+// flag: the next node to expand is the first unexpanded entry, the search stops when none is left.  This is equivalent:
+// a candidate worse than the current ef-th best (lowerBound) can never be expanded (the loop stops at the first such pop and
+// lowerBound only decreases), and every candidate at or below lowerBound is in top_candidates.  Requires a graph without
+// deleted nodes (num_deleted_ == 0, the bare-bone branch of hnswalg.h:1982); distances tie only on duplicate vectors.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "internal.h"
+#include "../host/knn_select.h"
+
+using namespace rxgpu;
+
+namespace {
+
+constexpr int kHnswWarps = 4;
+constexpr int kHnswThreads = kHnswWarps * 32;
+constexpr uint32_t kExpanded = 0x80000000u;
+constexpr uint32_t kMaxEf = 1024;
+constexpr uint32_t kVlogCap = 1u << 15;
+constexpr int kMaxNeighbours = 64;  // maxM0 = 2*M; M <= 32 on the device path
+
+struct HnswArgs {
+	const float* rows;
+	const float* norm_coefs;
+	const uint32_t* level0;
+	const int32_t* levels;
+	const long long* upper_off;
+	const uint32_t* upper;
+	const float* queries;
+	uint32_t* visited;  // [slots][words]
+	uint32_t* vlog;     // [slots][kVlogCap]
+	unsigned int* next_query;
+	float* out_dist;    // [nq][k]
+	uint32_t* out_idx;  // [nq][k]
+	uint32_t* out_count;
+	uint32_t* stats;    // [nq][2] or null
+	uint32_t pitch, dim, n, l0_stride, up_stride;
+	int maxlevel;
+	uint32_t enterpoint;
+	uint32_t nq, k, ef, words;
+};
+
+__device__ __forceinline__ float4 ldg4(const float4* p) {
+	float4 v;
+	asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+	return v;
+}
+
+// distances of `cnt` rows (ids in s_ids) to the query in sq4; results to s_d.  Per-row arithmetic == knn_scan_warp.
+template <bool kIsL2>
+__device__ __forceinline__ void warp_dists(const HnswArgs& a, const float4* sq4, const uint32_t* s_ids, uint32_t cnt, float* s_d,
+										   int lane) {
+	const float4* rows4 = reinterpret_cast<const float4*>(a.rows);
+	const uint32_t pitch4 = a.pitch >> 2;
+	const uint32_t nch = (a.dim + 127u) / 128u;
+	for (uint32_t g = 0; g < cnt; g += 4) {
+		uint32_t id[4];
+		float acc[4];
+#pragma unroll
+		for (int r = 0; r < 4; ++r) {
+			id[r] = s_ids[min(g + r, cnt - 1)];
+			acc[r] = 0.f;
+		}
+#pragma unroll 2
+		for (uint32_t c = 0; c < nch; ++c) {
+			const uint32_t f4 = c * 32u + lane;
+			float4 db[4];
+#pragma unroll
+			for (int r = 0; r < 4; ++r) {
+				db[r] = f4 < pitch4 ? ldg4(rows4 + size_t(id[r]) * pitch4 + f4) : make_float4(0.f, 0.f, 0.f, 0.f);
+			}
+			const float4 q = sq4[f4];
+#pragma unroll
+			for (int r = 0; r < 4; ++r) {
+				float s = acc[r];
+				if constexpr (kIsL2) {
+					float d;
+					d = q.x - db[r].x;
+					s = fmaf(d, d, s);
+					d = q.y - db[r].y;
+					s = fmaf(d, d, s);
+					d = q.z - db[r].z;
+					s = fmaf(d, d, s);
+					d = q.w - db[r].w;
+					s = fmaf(d, d, s);
+				} else {
+					s = fmaf(q.x, db[r].x, s);
+					s = fmaf(q.y, db[r].y, s);
+					s = fmaf(q.z, db[r].z, s);
+					s = fmaf(q.w, db[r].w, s);
+				}
+				acc[r] = s;
+			}
+		}
+#pragma unroll
+		for (int r = 0; r < 4; ++r) {
+			float v = acc[r];
+#pragma unroll
+			for (int off = 16; off > 0; off >>= 1) {
+				v += __shfl_xor_sync(0xffffffffu, v, off);
+			}
+			float dist = kIsL2 ? v : -v;
+			if (!kIsL2 && a.norm_coefs != nullptr) {
+				dist *= a.norm_coefs[id[r]];
+			}
+			if (lane == 0 && g + r < cnt) {
+				s_d[g + r] = dist;
+			}
+		}
+	}
+	__syncwarp();
+}
+
+template <bool kIsL2>
+__global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(const HnswArgs a) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	const uint32_t nch = (a.dim + 127u) / 128u;
+	const uint32_t dp4 = nch * 32u;
+	// per-warp shared memory: query | list dist[ef] | list id[ef] | neighbour ids[64] | neighbour dists[64]
+	const uint32_t efp = (a.ef + 3u) & ~3u;  // keeps every warp's region 16-byte aligned
+	const size_t per_warp = size_t(dp4) * 16 + size_t(efp) * 8 + kMaxNeighbours * 8;
+	unsigned char* base = smem_raw + per_warp * warp;
+	float4* sq4 = reinterpret_cast<float4*>(base);
+	float* l_dist = reinterpret_cast<float*>(base + size_t(dp4) * 16);
+	uint32_t* l_id = reinterpret_cast<uint32_t*>(l_dist + efp);
+	uint32_t* s_ids = l_id + efp;
+	float* s_d = reinterpret_cast<float*>(s_ids + kMaxNeighbours);
+
+	const uint32_t slot = blockIdx.x * kHnswWarps + warp;
+	uint32_t* visited = a.visited + size_t(slot) * a.words;
+	uint32_t* vlog = a.vlog + size_t(slot) * kVlogCap;
+
+	for (;;) {
+		uint32_t qi = 0;
+		if (lane == 0) {
+			qi = atomicAdd(a.next_query, 1u);
+		}
+		qi = __shfl_sync(0xffffffffu, qi, 0);
+		if (qi >= a.nq) {
+			break;
+		}
+		{  // stage the query, zero padded
+			float* sq = reinterpret_cast<float*>(sq4);
+			const float* q = a.queries + size_t(qi) * a.dim;
+			for (uint32_t c = lane; c < dp4 * 4; c += 32) {
+				sq[c] = c < a.dim ? q[c] : 0.f;
+			}
+		}
+		__syncwarp();
+		uint32_t n_dist = 0, n_hops = 0;
+
+		// ---- getLayer0EntryPoint (hnswalg.h:799-827)
+		uint32_t cur = a.enterpoint;
+		if (lane == 0) {
+			s_ids[0] = cur;
+		}
+		__syncwarp();
+		warp_dists<kIsL2>(a, sq4, s_ids, 1, s_d, lane);
+		float curdist = s_d[0];
+		__syncwarp();
+		for (int level = a.maxlevel; level > 0; --level) {
+			bool changed = true;
+			while (changed) {
+				changed = false;
+				const uint32_t* ll = a.upper + (size_t(a.upper_off[cur]) + size_t(level - 1)) * a.up_stride;
+				const uint32_t cnt = min(ll[0], uint32_t(kMaxNeighbours));
+				for (uint32_t j = lane; j < cnt; j += 32) {
+					s_ids[j] = ll[1 + j];
+				}
+				__syncwarp();
+				n_hops++;
+				n_dist += cnt;
+				if (cnt) {
+					warp_dists<kIsL2>(a, sq4, s_ids, cnt, s_d, lane);
+				}
+				for (uint32_t j = 0; j < cnt; ++j) {  // sequential like the reference: strict <, first minimum wins
+					const float d = s_d[j];
+					if (d < curdist) {
+						curdist = d;
+						cur = s_ids[j];
+						changed = true;
+					}
+				}
+				__syncwarp();
+			}
+		}
+
+		// ---- searchBaseLayerST (hnswalg.h:829-975), unified sorted list
+		uint32_t size = 1;
+		uint32_t vcount = 0;
+		if (lane == 0) {
+			l_dist[0] = curdist;
+			l_id[0] = cur;
+			atomicOr(&visited[cur >> 5], 1u << (cur & 31));
+			vlog[0] = cur;
+		}
+		vcount = 1;
+		__syncwarp();
+		for (;;) {
+			// first unexpanded entry
+			int pos = -1;
+			for (uint32_t b = 0; b < size && pos < 0; b += 32) {
+				const uint32_t i = b + lane;
+				const bool un = i < size && !(l_id[i] & kExpanded);
+				const unsigned m = __ballot_sync(0xffffffffu, un);
+				if (m) {
+					pos = int(b) + __ffs(m) - 1;
+				}
+			}
+			if (pos < 0) {
+				break;  // candidate_set exhausted / next candidate worse than lowerBound (layer0ShouldStopBeforePop :860-869)
+			}
+			const uint32_t node = l_id[pos];
+			__syncwarp();
+			if (lane == 0) {
+				l_id[pos] = node | kExpanded;
+			}
+			const uint32_t* ll = a.level0 + size_t(node) * a.l0_stride;
+			const uint32_t cnt = min(ll[0], uint32_t(kMaxNeighbours));
+			n_hops++;
+			n_dist += cnt;
+			// batched visited test: lanes own neighbours lane, lane+32
+			uint32_t ucnt = 0;
+			for (uint32_t b = 0; b < cnt; b += 32) {
+				const uint32_t j = b + lane;
+				uint32_t nid = 0;
+				bool fresh = false;
+				if (j < cnt) {
+					nid = ll[1 + j];
+					const uint32_t bit = 1u << (nid & 31);
+					fresh = !(atomicOr(&visited[nid >> 5], bit) & bit);
+				}
+				const unsigned fm = __ballot_sync(0xffffffffu, fresh);
+				if (fresh) {
+					const uint32_t o = ucnt + __popc(fm & ((1u << lane) - 1u));
+					s_ids[o] = nid;  // neighbour order is preserved
+					if (vcount + o - ucnt < kVlogCap) {
+						vlog[vcount + o - ucnt] = nid;
+					}
+				}
+				ucnt += __popc(fm);
+				vcount += __popc(fm);
+			}
+			__syncwarp();
+			if (ucnt == 0) {
+				continue;
+			}
+			warp_dists<kIsL2>(a, sq4, s_ids, ucnt, s_d, lane);
+			// sequential accept logic of runLayer0Step (:931-957) over the batch, in neighbour order
+			for (uint32_t j = 0; j < ucnt; ++j) {
+				const float d = s_d[j];
+				const uint32_t nid = s_ids[j];
+				const bool consider = size < a.ef || l_dist[size - 1] > d;  // flag_consider_candidate
+				if (!consider) {
+					continue;
+				}
+				uint32_t p = 0;  // insert after every entry <= d
+				for (uint32_t b = 0; b < size; b += 32) {
+					const uint32_t i = b + lane;
+					p += __popc(__ballot_sync(0xffffffffu, i < size && l_dist[i] <= d));
+				}
+				const uint32_t newsize = min(size + 1, a.ef);
+				if (p < newsize) {
+					for (int b = int((newsize - 1) / 32) * 32; b >= 0; b -= 32) {  // shift right, highest chunk first
+						const uint32_t i = uint32_t(b) + lane;
+						const bool mv = i > p && i < newsize;
+						float td = 0.f;
+						uint32_t ti = 0;
+						if (mv) {
+							td = l_dist[i - 1];
+							ti = l_id[i - 1];
+						}
+						__syncwarp();
+						if (mv) {
+							l_dist[i] = td;
+							l_id[i] = ti;
+						}
+						__syncwarp();
+					}
+					if (lane == 0) {
+						l_dist[p] = d;
+						l_id[p] = nid;
+					}
+					__syncwarp();
+				}
+				size = newsize;
+			}
+		}
+
+		// ---- results: the k best of the list (SearchKnn :1998-2011), then clean the visited bitmap for the next query
+		const uint32_t outn = min(a.k, size);
+		for (uint32_t j = lane; j < outn; j += 32) {
+			a.out_dist[size_t(qi) * a.k + j] = l_dist[j];
+			a.out_idx[size_t(qi) * a.k + j] = l_id[j] & ~kExpanded;
+		}
+		if (lane == 0) {
+			a.out_count[qi] = outn;
+			if (a.stats) {
+				a.stats[size_t(qi) * 2] = n_dist;
+				a.stats[size_t(qi) * 2 + 1] = n_hops;
+			}
+		}
+		__syncwarp();
+		if (vcount <= kVlogCap) {
+			for (uint32_t j = lane; j < vcount; j += 32) {
+				visited[vlog[j] >> 5] = 0;
+			}
+		} else {
+			for (uint32_t j = lane; j < a.words; j += 32) {
+				visited[j] = 0;
+			}
+		}
+		__syncwarp();
+	}
+}
+
+}  // namespace
+
+struct rxgpu_hnsw_device {
+	uint32_t n = 0, M = 0, maxM0 = 0;
+	int32_t maxlevel = -1;
+	uint32_t enterpoint = 0;
+	uint64_t index_version = 0;
+	DevBuf<uint32_t> level0;
+	DevBuf<int32_t> levels;
+	DevBuf<long long> upper_off;
+	DevBuf<uint32_t> upper;
+	// search scratch (guarded by mtx: one HNSW batch at a time per index; batches are internally parallel)
+	std::mutex mtx;
+	DevBuf<uint32_t> visited;
+	DevBuf<uint32_t> vlog;
+	DevBuf<unsigned int> counter;
+	uint32_t slots = 0, words = 0;
+};
+
+namespace rxgpu {
+void hnswRelease(rxgpu_hnsw_device* h) { delete h; }
+}  // namespace rxgpu
+
+extern "C" {
+
+int rxgpu_hnsw_import(rxgpu_index* ix, const rxgpu_hnsw_graph* g) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	if (!g || !g->level0 || !g->levels || !g->upper_offsets) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null graph");
+	}
+	if (g->n != ix->size) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: HNSW graph size differs from the number of rows in the index");
+	}
+	if (g->maxM0 > uint32_t(kMaxNeighbours) || g->M > uint32_t(kMaxNeighbours) || g->n == 0 || g->enterpoint >= g->n) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: unsupported HNSW graph (M must be <= 32, graph must be non-empty)");
+	}
+	auto h = std::make_unique<rxgpu_hnsw_device>();
+	h->n = g->n;
+	h->M = g->M;
+	h->maxM0 = g->maxM0;
+	h->maxlevel = g->maxlevel;
+	h->enterpoint = g->enterpoint;
+	const size_t l0 = size_t(g->n) * (1 + g->maxM0), up = std::max<size_t>(1, size_t(g->upper_slots) * (1 + g->M));
+	RX_CUDA(h->level0.ensure(l0));
+	RX_CUDA(h->levels.ensure(g->n));
+	RX_CUDA(h->upper_off.ensure(size_t(g->n) + 1));
+	RX_CUDA(h->upper.ensure(up));
+	RX_CUDA(cudaMemcpy(h->level0.p, g->level0, l0 * 4, cudaMemcpyHostToDevice));
+	RX_CUDA(cudaMemcpy(h->levels.p, g->levels, size_t(g->n) * 4, cudaMemcpyHostToDevice));
+	RX_CUDA(cudaMemcpy(h->upper_off.p, g->upper_offsets, (size_t(g->n) + 1) * 8, cudaMemcpyHostToDevice));
+	if (g->upper_slots) {
+		RX_CUDA(cudaMemcpy(h->upper.p, g->upper, size_t(g->upper_slots) * (1 + g->M) * 4, cudaMemcpyHostToDevice));
+	}
+	h->slots = uint32_t(ix->sm_count) * 4 * kHnswWarps;
+	h->words = (g->n + 31) / 32;
+	RX_CUDA(h->visited.ensure(size_t(h->slots) * h->words));
+	RX_CUDA(h->vlog.ensure(size_t(h->slots) * kVlogCap));
+	RX_CUDA(h->counter.ensure(1));
+	RX_CUDA(cudaMemset(h->visited.p, 0, size_t(h->slots) * h->words * 4));
+	h->index_version = ix->version;
+	if (ix->hnsw) {
+		hnswRelease(ix->hnsw);
+	}
+	ix->hnsw = h.release();
+	return 0;
+}
+
+int rxgpu_hnsw_search_knn_device(const rxgpu_index* ix, uint32_t nq, const float* d_queries, uint32_t k, uint32_t ef, float* d_out_dist,
+								 uint32_t* d_out_idx, uint32_t* d_out_count, uint32_t* d_stats, void* stream) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	rxgpu_hnsw_device* h = ix->hnsw;
+	if (!h) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: no HNSW graph imported into this index");
+	}
+	if (h->n != ix->size || h->index_version != ix->version) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: the index changed after the HNSW graph was imported");
+	}
+	if (nq == 0) {
+		return 0;
+	}
+	k = uint32_t(std::min<uint64_t>(k, ix->size));  // hnswalg.h:1993
+	if (k == 0) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: k must be positive");
+	}
+	ef = ef ? ef : k * 3 / 2;  // hnswalg.h:1995
+	ef = std::max(ef, 1u);
+	if (ef > kMaxEf) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: ef must be <= 1024 on the device path");
+	}
+	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ix->stream;
+	std::lock_guard<std::mutex> lck(h->mtx);
+	HnswArgs a{};
+	a.rows = ix->d_rows;
+	a.norm_coefs = ix->metric == RXGPU_COS ? ix->d_norms : nullptr;
+	a.level0 = h->level0.p;
+	a.levels = h->levels.p;
+	a.upper_off = h->upper_off.p;
+	a.upper = h->upper.p;
+	a.queries = d_queries;
+	a.visited = h->visited.p;
+	a.vlog = h->vlog.p;
+	a.next_query = h->counter.p;
+	a.out_dist = d_out_dist;
+	a.out_idx = d_out_idx;
+	a.out_count = d_out_count;
+	a.stats = d_stats;
+	a.pitch = ix->pitch;
+	a.dim = ix->dim;
+	a.n = h->n;
+	a.l0_stride = 1 + h->maxM0;
+	a.up_stride = 1 + h->M;
+	a.maxlevel = h->maxlevel;
+	a.enterpoint = h->enterpoint;
+	a.nq = nq;
+	a.k = k;
+	a.ef = ef;
+	a.words = h->words;
+	const uint32_t dp4 = ((ix->dim + 127u) / 128u) * 32u;
+	const size_t smem = (size_t(dp4) * 16 + size_t((ef + 3u) & ~3u) * 8 + kMaxNeighbours * 8) * kHnswWarps;
+	if (smem > 200 * 1024) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: dimension/ef combination exceeds the shared-memory budget of the HNSW kernel");
+	}
+	const unsigned grid = std::min<unsigned>(h->slots / kHnswWarps, (nq + kHnswWarps - 1) / kHnswWarps);
+	RX_CUDA(cudaMemsetAsync(h->counter.p, 0, sizeof(unsigned int), st));
+	if (ix->metric == RXGPU_L2) {
+		RX_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+		hnsw_search_kernel<true><<<grid, kHnswThreads, smem, st>>>(a);
+	} else {
+		RX_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+		hnsw_search_kernel<false><<<grid, kHnswThreads, smem, st>>>(a);
+	}
+	RX_CUDA(cudaGetLastError());
+	RX_CUDA(cudaStreamSynchronize(st));
+	g_stats = rxgpu_search_stats{};
+	g_stats.launches = 1;
+	return 0;
+}
+
+int rxgpu_hnsw_search_knn(const rxgpu_index* ix, uint32_t nq, const float* queries, uint32_t k, uint32_t ef, float* out_dist,
+						  uint64_t* out_label, uint32_t* out_count, uint32_t* stats) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	if (nq == 0) {
+		return 0;
+	}
+	if (!queries || !out_dist || !out_label || !out_count) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	if (ix->size == 0) {  // hnswalg.h:1989-1991
+		std::memset(out_count, 0, nq * sizeof(uint32_t));
+		return 0;
+	}
+	const uint32_t kEff = uint32_t(std::min<uint64_t>(k, ix->size));
+	if (kEff == 0) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: k must be positive");
+	}
+	DevBuf<float> dq, dd;
+	DevBuf<uint32_t> di, dc, ds;
+	RX_CUDA(dq.ensure(size_t(nq) * ix->dim));
+	RX_CUDA(dd.ensure(size_t(nq) * kEff));
+	RX_CUDA(di.ensure(size_t(nq) * kEff));
+	RX_CUDA(dc.ensure(nq));
+	RX_CUDA(ds.ensure(size_t(nq) * 2));
+	RX_CUDA(cudaMemcpy(dq.p, queries, size_t(nq) * ix->dim * 4, cudaMemcpyHostToDevice));
+	if (int rc = rxgpu_hnsw_search_knn_device(ix, nq, dq.p, kEff, ef, dd.p, di.p, dc.p, ds.p, nullptr)) {
+		return rc;
+	}
+	std::vector<float> hd(size_t(nq) * kEff);
+	std::vector<uint32_t> hi(size_t(nq) * kEff), hc(nq);
+	RX_CUDA(cudaMemcpy(hd.data(), dd.p, hd.size() * 4, cudaMemcpyDeviceToHost));
+	RX_CUDA(cudaMemcpy(hi.data(), di.p, hi.size() * 4, cudaMemcpyDeviceToHost));
+	RX_CUDA(cudaMemcpy(hc.data(), dc.p, hc.size() * 4, cudaMemcpyDeviceToHost));
+	if (stats) {
+		RX_CUDA(cudaMemcpy(stats, ds.p, size_t(nq) * 2 * 4, cudaMemcpyDeviceToHost));
+	}
+	std::vector<Hit> hits;
+	for (uint32_t q = 0; q < nq; ++q) {
+		hits.clear();
+		for (uint32_t j = 0; j < hc[q]; ++j) {
+			const uint32_t row = hi[size_t(q) * kEff + j];
+			hits.push_back(Hit{hd[size_t(q) * kEff + j], row, ix->h_labels[row]});
+		}
+		orderTiesByLabel(hits);  // the final SearchResultQueue uses std::less<pair> (hnswalg.h:2003-2010)
+		for (size_t j = 0; j < hits.size(); ++j) {
+			out_dist[size_t(q) * k + j] = hits[j].dist;
+			out_label[size_t(q) * k + j] = hits[j].label;
+		}
+		out_count[q] = uint32_t(hits.size());
+	}
+	return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,207 @@
+// Internal declarations shared by the translation units of librxgpu (index.cu, hnsw.cu, ft_bm25.cu).  Not part of the ABI.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/rxgpu.h"
+#include "../host/flat_map.h"
+
+namespace rxgpu {
+
+extern thread_local std::string g_err;
+extern thread_local rxgpu_search_stats g_stats;
+extern thread_local std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+extern std::atomic<int> g_profile;
+
+// sum the event pairs recorded by this thread's launches; call after the stream has been synchronised
+inline void collectProfile() {
+	for (auto& ev : g_prof_events) {
+		float ms = 0.f;
+		if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) {
+			g_stats.scan_kernel_ms += ms;
+			g_stats.scan_launches += 1;
+		}
+		cudaEventDestroy(ev.first);
+		cudaEventDestroy(ev.second);
+	}
+	g_prof_events.clear();
+}
+
+inline int fail(int code, std::string msg) {
+	g_err = std::move(msg);
+	return code;
+}
+
+#define RX_CUDA(expr)                                                                                        \
+	do {                                                                                                     \
+		cudaError_t e_ = (expr);                                                                             \
+		if (e_ != cudaSuccess) {                                                                             \
+			return fail(RXGPU_ERR_SYSTEM, std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #expr); \
+		}                                                                                                    \
+	} while (0)
+
+template <typename T>
+struct DevBuf {
+	T* p = nullptr;
+	size_t n = 0;
+	~DevBuf() { release(); }
+	void release() {
+		if (p) {
+			cudaFree(p);
+			p = nullptr;
+			n = 0;
+		}
+	}
+	cudaError_t ensure(size_t want) {
+		if (want <= n) {
+			return cudaSuccess;
+		}
+		release();
+		cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T));
+		if (e == cudaSuccess) {
+			n = want;
+		}
+		return e;
+	}
+};
+template <typename T>
+struct PinBuf {
+	T* p = nullptr;
+	size_t n = 0;
+	~PinBuf() {
+		if (p) {
+			cudaFreeHost(p);
+		}
+	}
+	cudaError_t ensure(size_t want) {
+		if (want <= n) {
+			return cudaSuccess;
+		}
+		if (p) {
+			cudaFreeHost(p);
+			p = nullptr;
+			n = 0;
+		}
+		cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&p), want * sizeof(T));
+		if (e == cudaSuccess) {
+			n = want;
+		}
+		return e;
+	}
+};
+
+// per-call scratch: searches are re-entrant, each takes one workspace from the pool
+struct Workspace {
+	cudaStream_t stream = nullptr;
+	DevBuf<float> d_queries;
+	DevBuf<uint64_t> d_lists;
+	DevBuf<float> d_out_dist;
+	DevBuf<uint32_t> d_out_idx;
+	DevBuf<uint64_t> d_out_label;
+	DevBuf<uint32_t> d_out_count;
+	DevBuf<uint64_t> d_range;
+	DevBuf<unsigned long long> d_range_count;
+	PinBuf<float> h_queries;
+	PinBuf<float> h_out_dist;
+	PinBuf<uint32_t> h_out_idx;
+	PinBuf<uint64_t> h_out_label;
+	PinBuf<uint32_t> h_out_count;
+	PinBuf<uint64_t> h_range;
+	~Workspace() {
+		if (stream) {
+			cudaStreamDestroy(stream);
+		}
+	}
+};
+
+}  // namespace rxgpu
+
+struct rxgpu_hnsw_device;  // hnsw.cu
+namespace rxgpu {
+void hnswRelease(rxgpu_hnsw_device*);
+}
+
+struct rxgpu_index {
+	int metric = 0;
+	uint32_t dim = 0;
+	uint32_t pitch = 0;  // floats, multiple of 4
+	uint64_t capacity = 0;
+	uint64_t size = 0;
+	int device = 0;
+	uint32_t flags = 0;
+	int sm_count = 148;
+	uint32_t qt_override = 0;
+	uint64_t version = 0;  // bumped by every mutation of rows/labels (staleness check of attached structures)
+
+	float* d_rows = nullptr;
+	uint64_t* d_labels = nullptr;
+	float* d_norms = nullptr;  // Cosine only (DistCalculator::normCoefs_, hnswlib.h:33-35)
+
+	std::vector<uint64_t> h_labels;  // by internal index
+	rxgpu::LabelMap dict;
+	std::vector<float> h_rows;  // optional host mirror [capacity][dim]
+
+	cudaStream_t stream = nullptr;  // maintenance stream
+	mutable std::mutex ws_mtx;
+	mutable std::vector<std::unique_ptr<rxgpu::Workspace>> ws_free;
+	rxgpu_hnsw_device* hnsw = nullptr;  // graph attached by rxgpu_hnsw_import (hnsw.cu)
+
+	~rxgpu_index() {
+		cudaSetDevice(device);
+		ws_free.clear();
+		if (hnsw) {
+			rxgpu::hnswRelease(hnsw);
+		}
+		if (d_rows) {
+			cudaFree(d_rows);
+		}
+		if (d_labels) {
+			cudaFree(d_labels);
+		}
+		if (d_norms) {
+			cudaFree(d_norms);
+		}
+		if (stream) {
+			cudaStreamDestroy(stream);
+		}
+	}
+};
+
+namespace rxgpu {
+
+struct WsLease {
+	const rxgpu_index* idx;
+	std::unique_ptr<Workspace> ws;
+	explicit WsLease(const rxgpu_index* i) : idx(i) {
+		{
+			std::lock_guard<std::mutex> lck(idx->ws_mtx);
+			if (!idx->ws_free.empty()) {
+				ws = std::move(idx->ws_free.back());
+				idx->ws_free.pop_back();
+			}
+		}
+		if (!ws) {
+			ws = std::make_unique<Workspace>();
+		}
+	}
+	~WsLease() {
+		std::lock_guard<std::mutex> lck(idx->ws_mtx);
+		idx->ws_free.emplace_back(std::move(ws));
+	}
+};
+
+inline int checkIndex(const rxgpu_index* ix) {
+	if (!ix) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null index handle");
+	}
+	RX_CUDA(cudaSetDevice(ix->device));
+	return 0;
+}
+
+}  // namespace rxgpu
