@@ -162,6 +162,70 @@ int rxgpu_hnsw_search_knn(const rxgpu_index*, uint32_t nq, const float* queries 
 int rxgpu_hnsw_search_knn_device(const rxgpu_index*, uint32_t nq, const float* d_queries, uint32_t k, uint32_t ef, float* d_out_dist,
 								 uint32_t* d_out_idx, uint32_t* d_out_count, uint32_t* d_stats /* nq x 2 or NULL */, void* stream);
 
+/* ---------------------------------------------------------------- ft_fast full-text merge (BM25 scoring over posting lists)
+ * Replaces ft::Merger<IdCont, ft::MergeData, OffsetT>::Merge<Bm25Rx|Bm25Classic|TermCount>  core/ft/ft_fast/mergerimpl.h:466-566
+ * -- the seam is Selector<IdCont>::mergeResults (ft_fast/selecterimpl.h:609-627) -- for query parts that are plain terms
+ * (each with its variant subterms); phrases and multi-word synonyms stay on the reference's CPU path (returns errParams).
+ * Inputs mirror what the reference hands the merger: posting lists = IdRelVec contents (ft/idrelset.h:62-130) de-interleaved,
+ * document statistics = the DocsStatsGetter duck-type (index/indextext/indextext.h:245-258), FTConfig members the merger reads
+ * (ft/config/ftconfig.h:118-236), query parts = TermResults/SubtermResults + FtDslOpts (ft_fast/querymergedata.h, ft/ftdsl.h:13-30).
+ * Output = ft::MergeData (ft_fast/phrasemerger.h:57-78), bit-identical to the reference: same docs, same order for
+ * RankAndID / IDOnly, same uint8 ranks, same field. */
+typedef struct {
+	uint32_t ndocs;
+	const uint32_t* doc_ids;   /* ascending vdoc ids, >= 1 (vdoc 0 is the reference's dummy, mergerimpl.h:122) */
+	const uint32_t* pos_begin; /* ndocs + 1 offsets into positions */
+	const uint32_t* positions; /* PosType: pos | field << 24, ascending within a doc (arrayIdx 0) */
+} rxgpu_ft_postings;
+typedef struct { /* FTFieldConfig */
+	double bm25_boost, bm25_weight, term_len_boost, term_len_weight, position_boost, position_weight;
+} rxgpu_ft_field_config;
+typedef struct { /* FTConfig members read by the merger */
+	uint32_t merge_limit;
+	int32_t min_rank;
+	double bm25_k1, bm25_b;
+	int32_t bm25_type; /* 0 rx (default), 1 classic, 2 wordCount */
+	double distance_boost, distance_weight, full_match_boost;
+	uint32_t nfields;
+	const rxgpu_ft_field_config* fields;
+} rxgpu_ft_config;
+typedef struct { /* one TermResults */
+	int32_t op; /* OpType: 1 = OpOr, 2 = OpAnd, 3 = OpNot */
+	float boost;
+	float term_len_boost;
+	const float* field_boosts; /* nfields */
+	uint32_t nsubterms;
+	const uint32_t* postings; /* ids returned by rxgpu_ft_add_postings */
+	const float* procs;
+} rxgpu_ft_term;
+typedef struct { /* ft::MergeInfo */
+	int32_t id;
+	float proc;
+	uint8_t field;
+	uint8_t normalized_proc;
+} rxgpu_ft_merge_info;
+typedef struct rxgpu_ft_index rxgpu_ft_index;
+
+/* document statistics of the index: words_in_field[total_docs][nfields] (NumWordsInField), avg_words[nfields] (AvgWordsCount),
+ * removed[total_docs] or NULL (DocRemoved).  total_docs counts the dummy vdoc 0 like the reference's vdocs_.size(). */
+int rxgpu_ft_create(rxgpu_ft_index** out, uint32_t total_docs, uint32_t nfields, const uint32_t* words_in_field, const float* avg_words,
+					const uint8_t* removed, int device);
+void rxgpu_ft_destroy(rxgpu_ft_index*);
+int rxgpu_ft_add_postings(rxgpu_ft_index*, const rxgpu_ft_postings* list, uint32_t* out_id); /* uploads one word's postings to HBM */
+/* excluded: u8[total_docs] (FtMergeStatuses::Statuses docsExcluded) or NULL; rank_sort_type: reindexer::RankSortType.
+ * Writes min(*out_n, max_out) entries; *out_n = number of merged documents. */
+int rxgpu_ft_merge(rxgpu_ft_index*, const rxgpu_ft_config* cfg, uint32_t nterms, const rxgpu_ft_term* terms, const uint8_t* excluded,
+				   int rank_sort_type, uint64_t max_out, rxgpu_ft_merge_info* out, uint64_t* out_n);
+/* statistics of the last merge on this thread */
+typedef struct {
+	uint32_t launches;
+	uint32_t preselected;       /* 1 when preselectMostRelevantDocs ran */
+	uint64_t postings_scanned;  /* postings streamed over all passes */
+	uint64_t algorithmic_bytes; /* SURVEY.md §8d model: bytes the passes must touch */
+	float device_ms;            /* CUDA-event time of the device part */
+} rxgpu_ft_stats;
+void rxgpu_ft_last_stats(rxgpu_ft_stats* out);
+
 /* ---------------------------------------------------------------- benchmark / test support (not part of the reference surface)
  * Appends n rows generated on the device: element (row r, col c) = synth(seed, (first_row + r) * dim + c), label =
  * (first_row + r) << 32.  The generator is defined in csrc/synth.cuh and mirrored bit-for-bit by oracle/knn_port.c. */

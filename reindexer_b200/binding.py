@@ -43,6 +43,34 @@ class HnswGraph(C.Structure):
                 ("upper", C.c_void_p)]
 
 
+class FtPostings(C.Structure):
+    _fields_ = [("ndocs", C.c_uint32), ("doc_ids", _u32p), ("pos_begin", _u32p), ("positions", _u32p)]
+
+
+class FtFieldConfig(C.Structure):
+    _fields_ = [("bm25_boost", C.c_double), ("bm25_weight", C.c_double), ("term_len_boost", C.c_double), ("term_len_weight", C.c_double),
+                ("position_boost", C.c_double), ("position_weight", C.c_double)]
+
+
+class FtConfig(C.Structure):
+    _fields_ = [("merge_limit", C.c_uint32), ("min_rank", C.c_int32), ("bm25_k1", C.c_double), ("bm25_b", C.c_double),
+                ("bm25_type", C.c_int32), ("distance_boost", C.c_double), ("distance_weight", C.c_double),
+                ("full_match_boost", C.c_double), ("nfields", C.c_uint32), ("fields", C.POINTER(FtFieldConfig))]
+
+
+class FtTerm(C.Structure):
+    _fields_ = [("op", C.c_int32), ("boost", C.c_float), ("term_len_boost", C.c_float), ("field_boosts", _f32p), ("nsubterms", C.c_uint32),
+                ("postings", _u32p), ("procs", _f32p)]
+
+
+class FtStats(C.Structure):
+    _fields_ = [("launches", C.c_uint32), ("preselected", C.c_uint32), ("postings_scanned", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
+                ("device_ms", C.c_float)]
+
+
+FT_MERGE_INFO_DTYPE = np.dtype([("id", np.int32), ("proc", np.float32), ("field", np.uint8), ("normalized_proc", np.uint8)], align=True)
+
+
 class SearchStats(C.Structure):
     _fields_ = [("launches", C.c_uint32), ("passes", C.c_uint32), ("query_tile", C.c_uint32), ("tie_replays", C.c_uint32),
                 ("algorithmic_bytes", C.c_uint64), ("scan_launches", C.c_uint32), ("scan_kernel_ms", C.c_float)]
@@ -83,6 +111,12 @@ _SIGNATURES = {
     "rxgpu_hnsw_search_knn": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, C.c_uint32, C.c_uint32, _f32p, _u64p, _u32p, _u32p]),
     "rxgpu_hnsw_search_knn_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rxgpu_ft_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, _u32p, _f32p, _u8p, C.c_int]),
+    "rxgpu_ft_destroy": (None, [C.c_void_p]),
+    "rxgpu_ft_add_postings": (C.c_int, [C.c_void_p, C.POINTER(FtPostings), _u32p]),
+    "rxgpu_ft_merge": (C.c_int, [C.c_void_p, C.POINTER(FtConfig), C.c_uint32, C.POINTER(FtTerm), _u8p, C.c_int, C.c_uint64, C.c_void_p,
+                                 C.POINTER(C.c_uint64)]),
+    "rxgpu_ft_last_stats": (None, [C.POINTER(FtStats)]),
     "rxgpu_index_append_synth": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
     "rxgpu_synth_fill_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]),
     "rxgpu_set_query_tile": (C.c_int, [C.c_void_p, C.c_uint32]),
@@ -294,3 +328,61 @@ def tie_replay(k, dstar, lower, first):
     _check(lib().rxgpu_tie_replay(k, dstar, len(ld), _p(ld, _f32p), _p(lg, _u64p), _p(ll, _u64p), len(fd), _p(fd, _f32p), _p(fg, _u64p),
                                   _p(fl, _u64p), _p(od, _f32p), _p(ol, _u64p), C.byref(oc)))
     return od[:oc.value], ol[:oc.value]
+
+
+class GpuFtIndex:
+    """Device-resident ft_fast merge state: document statistics + posting lists; merge() = ft::Merger::Merge."""
+
+    def __init__(self, total_docs, words_in_field, avg_words, removed=None, device=0):
+        self._lib = lib()
+        w = np.ascontiguousarray(words_in_field, np.uint32).reshape(total_docs, -1)
+        self.total_docs, self.nfields = total_docs, w.shape[1]
+        a = np.ascontiguousarray(avg_words, np.float32)
+        r = None if removed is None else np.ascontiguousarray(removed, np.uint8)
+        h = C.c_void_p()
+        _check(self._lib.rxgpu_ft_create(C.byref(h), total_docs, self.nfields, _p(w, _u32p), _p(a, _f32p), None if r is None else _p(r, _u8p),
+                                         device))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rxgpu_ft_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def add_postings(self, doc_ids, pos_begin, positions) -> int:
+        d = np.ascontiguousarray(doc_ids, np.uint32)
+        b = np.ascontiguousarray(pos_begin, np.uint32)
+        p = np.ascontiguousarray(positions, np.uint32)
+        pl = FtPostings(len(d), _p(d, _u32p), _p(b, _u32p), _p(p, _u32p))
+        out = C.c_uint32(0)
+        _check(self._lib.rxgpu_ft_add_postings(self._h, C.byref(pl), C.byref(out)))
+        return out.value
+
+    def merge(self, cfg: dict, field_cfg: list, terms: list, excluded=None, rank_sort_type=1, max_out=None):
+        """cfg / field_cfg: dicts with the FtConfig / FtFieldConfig member names; terms: dicts(op, boost, term_len_boost, field_boosts,
+        postings, procs).  Returns a structured array (id, proc, field, normalized_proc)."""
+        fc = (FtFieldConfig * self.nfields)(*[FtFieldConfig(**f) for f in field_cfg])
+        c = FtConfig(cfg["merge_limit"], cfg["min_rank"], cfg["bm25_k1"], cfg["bm25_b"], cfg["bm25_type"], cfg["distance_boost"],
+                     cfg["distance_weight"], cfg["full_match_boost"], self.nfields, fc)
+        keep = []
+        arr = (FtTerm * max(len(terms), 1))()
+        for i, t in enumerate(terms):
+            fb = np.ascontiguousarray(t["field_boosts"], np.float32)
+            po = np.ascontiguousarray(t["postings"], np.uint32)
+            pr = np.ascontiguousarray(t["procs"], np.float32)
+            keep += [fb, po, pr]
+            arr[i] = FtTerm(t["op"], t["boost"], t["term_len_boost"], _p(fb, _f32p), len(po), _p(po, _u32p), _p(pr, _f32p))
+        ex = None if excluded is None else np.ascontiguousarray(excluded, np.uint8)
+        max_out = self.total_docs if max_out is None else max_out
+        out = np.zeros(max(max_out, 1), FT_MERGE_INFO_DTYPE)
+        n = C.c_uint64(0)
+        _check(self._lib.rxgpu_ft_merge(self._h, C.byref(c), len(terms), arr, None if ex is None else _p(ex, _u8p), rank_sort_type, max_out,
+                                        out.ctypes.data, C.byref(n)))
+        return out[:min(n.value, max_out)].copy()
+
+    def last_stats(self) -> dict:
+        s = FtStats()
+        self._lib.rxgpu_ft_last_stats(C.byref(s))
+        return {f: getattr(s, f) for f, _ in FtStats._fields_}

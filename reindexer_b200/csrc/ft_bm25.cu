@@ -1,0 +1,943 @@
+// ft_fast full-text merge on the device: BM25 / rank scoring over posting lists.
+//
+// Replaces ft::Merger::Merge (cpp_src/core/ft/ft_fast/mergerimpl.h:466-566) for term-only queries:
+//   buildRestrictingBitmask :326-384      -> ft_mask_* kernels (bitset ops on a docs-wide bitmap in HBM)
+//   preselectMostRelevantDocs :386-464    -> ft_score_pass (integer u16 scores) + ft_hist (65536-bin histogram) + ordered threshold
+//   mergeTerm :107-192 / mergeSimple :194-250 -> ft_rank_pass (calcTermRank phrasemergerimpl.h:13-91 with fp64 BM25, bm25.h:13-27,
+//                                            PositionsDistance :20-37) + ordered slot assignment (block scan) = addDoc order
+//   addFullMatchBoost merger.h:100-109    -> ft_full_match
+//   postProcessResults merger.h:111-155   -> host (<= mergeLimit entries): minRank filter with the reference's swap-removal order,
+//                                            uint8 normalisation, optional sort
+// Every posting list is streamed with coalesced loads (SoA: doc ids | position offsets | packed positions), one thread per
+// posting, per-document state (slot, score, mask bit) gathered from HBM.  The reference's order dependences are kept exactly:
+// subterms are processed in the reference's order, one pass per subterm, and new documents receive their slots in ascending
+// document order through an exclusive scan -- so the merge_limit cut-off and the output order are the reference's.
+// Floating point follows the reference expression by expression with explicitly rounded operations (no FMA contraction):
+// BM25 in fp64, the products in fp32, idf (two logs) computed once per subterm on the host.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "internal.h"
+
+using namespace rxgpu;
+
+namespace {
+
+constexpr int kFtThreads = 256;
+constexpr int kMaxFtFields = 64;  // kMaxFtCompositeFields = 63 (ft/idrelset.h:11)
+
+struct DevList {
+	uint32_t ndocs = 0;
+	uint64_t npos = 0;
+	uint32_t* doc_ids = nullptr;
+	uint32_t* pos_begin = nullptr;
+	uint32_t* positions = nullptr;
+};
+
+struct FieldCfgF {  // FTFieldConfig members converted to float where the reference's bound(float, float, float) takes them
+	float bm25_weight, bm25_boost, pos_weight, pos_boost, len_weight, len_boost;
+};
+
+struct TermParams {
+	float field_boosts[kMaxFtFields];
+	FieldCfgF fc[kMaxFtFields];
+	float boost, term_len_boost, proc;
+	double idf, k1, b;
+	int bm25_type;
+	uint32_t nfields;
+	float dist_weight, dist_boost;
+};
+
+struct MergeState {
+	// per document (total_docs)
+	uint32_t* mask;      // restrictingMask_
+	uint32_t* tmask;     // per-term scratch mask
+	uint32_t* idoff;     // idoffsets_: slot or sentinel
+	uint16_t* score;     // preselect scores
+	// per merged document (max_merged)
+	int32_t* md_id;
+	float* md_proc;
+	uint8_t* md_field;
+	unsigned long long* last_ptr;  // MergerDocumentData::lastTermPositions as (pointer, count) into the posting arrays
+	uint32_t* last_n;
+	unsigned long long* next_ptr;
+	uint32_t* next_n;
+	float* ext_rank;
+	uint16_t* ext_cnt;
+	uint16_t* ext_last_term;
+	uint32_t* n_docs;  // device counter numDocs()
+};
+
+// ---- exactly rounded helpers -------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bound_f(float k, float weight, float boost) {  // ftconfig.h:146
+	const float kbw = __fmul_rn(__fmul_rn(k, boost), weight);
+	return __double2float_rn(__dadd_rn(__dsub_rn(1.0, double(weight)), double(kbw)));
+}
+__device__ __forceinline__ float pos2rank(unsigned pos) {  // ftconfig.h:127-144
+	if (pos <= 10) {
+		return __double2float_rn(__dsub_rn(1.0, __ddiv_rn(double(pos), 100.0)));
+	}
+	if (pos <= 100) {
+		return __double2float_rn(__dsub_rn(0.9, __ddiv_rn(double(pos), 1000.0)));
+	}
+	if (pos <= 1000) {
+		return __double2float_rn(__dsub_rn(0.8, __ddiv_rn(double(pos), 10000.0)));
+	}
+	if (pos <= 10000) {
+		return __double2float_rn(__dsub_rn(0.7, __ddiv_rn(double(pos), 100000.0)));
+	}
+	if (pos <= 100000) {
+		return __double2float_rn(__dsub_rn(0.6, __ddiv_rn(double(pos), 1000000.0)));
+	}
+	return 0.5f;
+}
+__device__ __forceinline__ double bm25_get(const TermParams& t, double termCountInDoc, double wordsInDoc, double avgDocLen) {  // bm25.h
+	if (t.bm25_type == 2) {
+		return termCountInDoc;
+	}
+	const double tf = t.bm25_type == 0 ? termCountInDoc : __ddiv_rn(termCountInDoc, wordsInDoc);
+	const double num = __dmul_rn(__dmul_rn(t.idf, tf), __dadd_rn(t.k1, 1.0));
+	const double inner = __dadd_rn(__dsub_rn(1.0, t.b), __ddiv_rn(__dmul_rn(t.b, wordsInDoc), avgDocLen));
+	return __ddiv_rn(num, __dadd_rn(tf, __dmul_rn(t.k1, inner)));
+}
+
+// calcTermRank (phrasemergerimpl.h:13-91, summationRanksByFieldsRatio == 0)
+__device__ __forceinline__ float calc_term_rank(const TermParams& t, const uint32_t* words, const float* avg, uint32_t doc,
+												const uint32_t* pos, uint32_t npos, uint8_t* fieldOut) {
+	uint8_t best_field = 0;
+	float termRank = 0.f;
+	for (uint32_t idx = 0; idx < npos;) {
+		const uint32_t f = pos[idx] >> 24;
+		const uint32_t begin = idx;
+		++idx;
+		while (idx < npos && (pos[idx] >> 24) == f) {
+			++idx;
+		}
+		if (t.field_boosts[f] == 0.f) {
+			continue;
+		}
+		const float bm25 = __double2float_rn(bm25_get(t, double(idx - begin), double(words[size_t(doc) * t.nfields + f]), double(avg[f])));
+		const float normBm25 = bound_f(bm25, t.fc[f].bm25_weight, t.fc[f].bm25_boost);
+		const float positionRank = bound_f(pos2rank(pos[begin] & 0xFFFFFFu), t.fc[f].pos_weight, t.fc[f].pos_boost);
+		const float termLenBoost = bound_f(t.term_len_boost, t.fc[f].len_weight, t.fc[f].len_boost);
+		const float tmp = __fmul_rn(__fmul_rn(__fmul_rn(t.field_boosts[f], normBm25), termLenBoost), positionRank);
+		if (tmp > termRank) {
+			best_field = uint8_t(f);
+			termRank = tmp;
+		}
+	}
+	*fieldOut = best_field;
+	return __fmul_rn(__fmul_rn(t.boost, t.proc), termRank);
+}
+
+// PositionsDistance (mergerimpl.h:20-37): the walk advances by word position (fullPos() truncates the field away), a pair counts
+// only when the fields match
+__device__ __forceinline__ unsigned positions_distance(const uint32_t* a, uint32_t na, const uint32_t* b, uint32_t nb) {
+	unsigned res = 0xFFFFFFFFu;
+	uint32_t i = 0, j = 0;
+	while (i < na && j < nb) {
+		const uint32_t pa = a[i] & 0xFFFFFFu, pb = b[j] & 0xFFFFFFu;
+		const bool sign = pa > pb;
+		if ((a[i] >> 24) == (b[j] >> 24)) {
+			const unsigned dst = sign ? pa - pb : pb - pa;
+			if (dst < res) {
+				res = dst;
+				if (res <= 1) {
+					break;
+				}
+			}
+		}
+		if (sign) {
+			j++;
+		} else {
+			i++;
+		}
+	}
+	return res == 0xFFFFFFFFu ? 0 : res;
+}
+
+// ---- kernels -----------------------------------------------------------------------------------------------------------------------
+__global__ void ft_mask_init(uint32_t* mask, const uint8_t* excluded, uint32_t total_docs, uint32_t words) {
+	for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += gridDim.x * blockDim.x) {
+		uint32_t bits = 0;
+		for (uint32_t b = 0; b < 32; ++b) {
+			const uint32_t d = w * 32 + b;
+			if (d < total_docs && !(excluded && excluded[d])) {
+				bits |= 1u << b;
+			}
+		}
+		mask[w] = bits;
+	}
+}
+__global__ void ft_fill_u32(uint32_t* p, uint32_t v, uint64_t n) {
+	for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+		p[i] = v;
+	}
+}
+// calcTermBitmask (mergerimpl.h:252-274)
+__global__ void ft_and_mark(DevList l, TermParams t, int all_positive, uint32_t* tmask) {
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < l.ndocs; i += gridDim.x * blockDim.x) {
+		bool relevant = all_positive;
+		for (uint32_t p = l.pos_begin[i]; !relevant && p < l.pos_begin[i + 1]; ++p) {
+			relevant = t.field_boosts[l.positions[p] >> 24] != 0.f;
+		}
+		if (relevant) {
+			const uint32_t d = l.doc_ids[i];
+			atomicOr(&tmask[d >> 5], 1u << (d & 31));
+		}
+	}
+}
+__global__ void ft_mask_and(uint32_t* mask, const uint32_t* tmask, uint32_t words) {
+	for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += gridDim.x * blockDim.x) {
+		mask[w] &= tmask[w];
+	}
+}
+// excludeTermFromBitmask (mergerimpl.h:276-287)
+__global__ void ft_not_clear(DevList l, uint32_t* mask) {
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < l.ndocs; i += gridDim.x * blockDim.x) {
+		const uint32_t d = l.doc_ids[i];
+		atomicAnd(&mask[d >> 5], ~(1u << (d & 31)));
+	}
+}
+__global__ void ft_popcount(const uint32_t* mask, uint32_t words, unsigned long long* out) {
+	unsigned long long c = 0;
+	for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += gridDim.x * blockDim.x) {
+		c += __popc(mask[w]);
+	}
+	for (int off = 16; off > 0; off >>= 1) {
+		c += __shfl_xor_sync(0xffffffffu, c, off);
+	}
+	if ((threadIdx.x & 31) == 0 && c) {
+		atomicAdd(out, c);
+	}
+}
+// calcTermScores (mergerimpl.h:289-324): one pass per subterm; a document scores once per term (tmask)
+__global__ void ft_score_pass(DevList l, TermParams t, int all_same, const uint32_t* mask, uint32_t* tmask, uint16_t* score) {
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < l.ndocs; i += gridDim.x * blockDim.x) {
+		const uint32_t d = l.doc_ids[i];
+		const uint32_t bit = 1u << (d & 31);
+		if (!(mask[d >> 5] & bit)) {
+			continue;
+		}
+		float maxBoost = t.field_boosts[0];
+		if (!all_same) {
+			maxBoost = 0.f;
+			for (uint32_t p = l.pos_begin[i]; p < l.pos_begin[i + 1]; ++p) {
+				maxBoost = fmaxf(maxBoost, t.field_boosts[l.positions[p] >> 24]);
+			}
+		}
+		if (maxBoost > 0.f) {
+			if (!(atomicOr(&tmask[d >> 5], bit) & bit)) {  // docs are unique inside one list: exactly one thread scores d in this pass
+				const float proc = __fmul_rn(__fmul_rn(t.proc, maxBoost), t.boost);
+				uint32_t p16 = uint32_t(uint16_t(proc));
+				p16 = min(p16, 65535u / 4u);
+				p16 = min(p16, 65535u - uint32_t(score[d]));
+				score[d] = uint16_t(score[d] + p16);
+			}
+		}
+	}
+}
+// zero scores outside the mask / of removed docs and build the 65536-bin histogram (mergerimpl.h:416-423)
+__global__ void ft_hist(uint16_t* score, const uint32_t* mask, const uint8_t* removed, uint32_t total_docs, unsigned long long* hist) {
+	for (uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; d < total_docs; d += gridDim.x * blockDim.x) {
+		uint16_t s = score[d];
+		if (!(mask[d >> 5] & (1u << (d & 31))) || (removed && removed[d])) {
+			s = 0;
+			score[d] = 0;
+		}
+		if (s) {
+			atomicAdd(&hist[s], 1ull);
+		}
+	}
+}
+// ordered cut at the threshold score: keep score > min, and the first `budget` docs (ascending id) with score == min (:448-462)
+__global__ void ft_thresh_count(const uint16_t* score, const uint32_t* mask, uint32_t total_docs, uint32_t min_score, uint32_t* block_counts) {
+	__shared__ uint32_t s_cnt;
+	if (threadIdx.x == 0) {
+		s_cnt = 0;
+	}
+	__syncthreads();
+	const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool eq = d < total_docs && (mask[d >> 5] & (1u << (d & 31))) && score[d] == min_score;
+	const unsigned m = __ballot_sync(0xffffffffu, eq);
+	if ((threadIdx.x & 31) == 0 && m) {
+		atomicAdd(&s_cnt, __popc(m));
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		block_counts[blockIdx.x] = s_cnt;
+	}
+}
+// exclusive scan of block counts, single block (counts <= ~200k entries)
+__global__ void ft_scan_blocks(uint32_t* counts, uint32_t n, uint32_t* total) {
+	__shared__ uint32_t s_warp[32];
+	__shared__ uint32_t s_carry;
+	if (threadIdx.x == 0) {
+		s_carry = 0;
+	}
+	__syncthreads();
+	for (uint32_t base = 0; base < n; base += blockDim.x) {
+		const uint32_t i = base + threadIdx.x;
+		const uint32_t v = i < n ? counts[i] : 0;
+		uint32_t x = v;
+		for (int off = 1; off < 32; off <<= 1) {
+			const uint32_t y = __shfl_up_sync(0xffffffffu, x, off);
+			if ((threadIdx.x & 31) >= off) {
+				x += y;
+			}
+		}
+		if ((threadIdx.x & 31) == 31) {
+			s_warp[threadIdx.x >> 5] = x;
+		}
+		__syncthreads();
+		if (threadIdx.x < 32) {
+			uint32_t w = threadIdx.x < (blockDim.x >> 5) ? s_warp[threadIdx.x] : 0;
+			for (int off = 1; off < 32; off <<= 1) {
+				const uint32_t y = __shfl_up_sync(0xffffffffu, w, off);
+				if (threadIdx.x >= off) {
+					w += y;
+				}
+			}
+			s_warp[threadIdx.x] = w;
+		}
+		__syncthreads();
+		const uint32_t warp_off = (threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0;
+		const uint32_t incl = s_carry + warp_off + x;
+		if (i < n) {
+			counts[i] = incl - v;
+		}
+		__syncthreads();
+		if (threadIdx.x == blockDim.x - 1) {
+			s_carry = incl;
+		}
+		__syncthreads();
+	}
+	if (threadIdx.x == 0 && total) {
+		*total = s_carry;
+	}
+}
+__device__ __forceinline__ uint32_t block_exclusive_rank(bool flag, uint32_t* s_warp) {
+	const unsigned m = __ballot_sync(0xffffffffu, flag);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (lane == 0) {
+		s_warp[warp] = __popc(m);
+	}
+	__syncthreads();
+	uint32_t off = 0;
+	for (int w = 0; w < warp; ++w) {
+		off += s_warp[w];
+	}
+	__syncthreads();
+	return off + __popc(m & ((1u << lane) - 1u));
+}
+__global__ void ft_thresh_apply(const uint16_t* score, uint32_t* mask, uint32_t total_docs, uint32_t min_score, uint32_t budget,
+								const uint32_t* block_offsets) {
+	__shared__ uint32_t s_warp[kFtThreads / 32];
+	const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool in = d < total_docs && (mask[d >> 5] & (1u << (d & 31)));
+	const uint32_t s = in ? score[d] : 0;
+	const bool eq = in && s == min_score;
+	const uint32_t rank = block_offsets[blockIdx.x] + block_exclusive_rank(eq, s_warp);
+	const bool keep = in && (s > min_score || (eq && rank < budget));
+	if (in && !keep) {
+		atomicAnd(&mask[d >> 5], ~(1u << (d & 31)));
+	}
+}
+
+// switchToNextWord (merger.h:220-228)
+__global__ void ft_switch(MergeState st) {
+	const uint32_t n = *st.n_docs;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		if (st.next_n[i]) {
+			st.last_ptr[i] = st.next_ptr[i];
+			st.last_n[i] = st.next_n[i];
+			st.next_n[i] = 0;
+			st.ext_rank[i] = 0.f;
+		}
+	}
+}
+
+// one subterm pass of mergeTerm / mergeSimple: rank every posting, update documents already merged in place, flag new ones
+__global__ void ft_rank_pass(DevList l, TermParams t, MergeState st, const uint32_t* words, const float* avg, const uint8_t* removed,
+							 int check_removed, int simple, uint32_t sentinel, uint16_t qp_idx, float* tmp_rank, uint8_t* tmp_field,
+							 uint32_t* block_counts) {
+	__shared__ uint32_t s_cnt;
+	if (threadIdx.x == 0) {
+		s_cnt = 0;
+	}
+	__syncthreads();
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	bool is_new = false;
+	if (i < l.ndocs) {
+		const uint32_t d = l.doc_ids[i];
+		bool ok = (st.mask[d >> 5] >> (d & 31)) & 1u;
+		if (ok && check_removed && removed && removed[d]) {
+			ok = false;
+		}
+		if (ok) {
+			const uint32_t* pos = l.positions + l.pos_begin[i];
+			const uint32_t npos = l.pos_begin[i + 1] - l.pos_begin[i];
+			uint8_t field;
+			const float rank = calc_term_rank(t, words, avg, d, pos, npos, &field);
+			if (rank != 0.f) {
+				const uint32_t slot = st.idoff ? st.idoff[d] : sentinel;
+				if (slot == sentinel) {
+					is_new = true;
+					tmp_rank[i] = rank;
+					tmp_field[i] = field;
+				} else if (simple) {  // mergeSimple :236-241
+					if (st.md_proc[slot] < rank) {
+						st.md_proc[slot] = rank;
+						st.md_field[slot] = field;
+					}
+				} else {  // mergeTerm :167-188
+					if (st.ext_last_term[slot] < qp_idx) {
+						st.ext_cnt[slot]++;
+						st.ext_last_term[slot] = qp_idx;
+					}
+					unsigned distance = positions_distance(reinterpret_cast<const uint32_t*>(st.last_ptr[slot]), st.last_n[slot], pos, npos);
+					distance = max(distance, 1u);
+					const float normDist = bound_f(__double2float_rn(__ddiv_rn(1.0, double(float(distance)))), t.dist_weight, t.dist_boost);
+					const float finalRank = __fmul_rn(normDist, rank);
+					if (finalRank > st.ext_rank[slot]) {
+						float p = st.md_proc[slot];
+						p = __fsub_rn(p, st.ext_rank[slot]);
+						p = __fadd_rn(p, finalRank);
+						st.md_proc[slot] = p;
+						st.next_ptr[slot] = reinterpret_cast<unsigned long long>(pos);
+						st.next_n[slot] = npos;
+						st.ext_rank[slot] = finalRank;
+					}
+				}
+			}
+		}
+		if (!is_new) {
+			tmp_rank[i] = 0.f;  // 0 marks "not a new document" for ft_assign
+		}
+	}
+	const unsigned m = __ballot_sync(0xffffffffu, is_new);
+	if ((threadIdx.x & 31) == 0 && m) {
+		atomicAdd(&s_cnt, __popc(m));
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		block_counts[blockIdx.x] = s_cnt;
+	}
+}
+// addDoc in ascending document order (merger.h:160-179): slot = numDocs() + exclusive rank; the merge_limit cut-off drops the rest
+__global__ void ft_assign(DevList l, MergeState st, int simple, uint32_t max_merged, uint16_t qp_idx, const float* tmp_rank,
+						  const uint8_t* tmp_field, const uint32_t* block_offsets) {
+	__shared__ uint32_t s_warp[kFtThreads / 32];
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool is_new = i < l.ndocs && tmp_rank[i] != 0.f;
+	const uint32_t slot = *st.n_docs + block_offsets[blockIdx.x] + block_exclusive_rank(is_new, s_warp);
+	if (is_new && slot < max_merged) {
+		const uint32_t d = l.doc_ids[i];
+		st.md_id[slot] = int32_t(d);
+		st.md_proc[slot] = tmp_rank[i];
+		st.md_field[slot] = tmp_field[i];
+		if (st.idoff) {
+			st.idoff[d] = slot;
+		}
+		if (!simple) {
+			st.last_n[slot] = 0;
+			st.last_ptr[slot] = 0;
+			st.next_ptr[slot] = reinterpret_cast<unsigned long long>(l.positions + l.pos_begin[i]);
+			st.next_n[slot] = l.pos_begin[i + 1] - l.pos_begin[i];
+			st.ext_rank[slot] = tmp_rank[i];
+			st.ext_cnt[slot] = 1;
+			st.ext_last_term[slot] = qp_idx;
+		}
+	}
+}
+__global__ void ft_bump_count(uint32_t* n_docs, const uint32_t* total_new, uint32_t max_merged) {
+	*n_docs = min(*n_docs + *total_new, max_merged);
+}
+// addFullMatchBoost (merger.h:100-109) with canBeBoostedByFullMatch (mergerimpl.h:533-537)
+__global__ void ft_full_match(MergeState st, const uint32_t* words, uint32_t nfields, uint32_t num_terms, uint32_t need_cnt, int simple,
+							  double boost) {
+	const uint32_t n = *st.n_docs;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const bool can = simple || st.ext_cnt[i] == need_cnt;
+		if (can && words[size_t(st.md_id[i]) * nfields + st.md_field[i]] == num_terms) {
+			st.md_proc[i] = __double2float_rn(__dmul_rn(double(st.md_proc[i]), boost));
+		}
+	}
+}
+
+unsigned gridFor(uint64_t n, int sm) { return unsigned(std::min<uint64_t>((n + kFtThreads - 1) / kFtThreads, uint64_t(sm) * 16)); }
+
+thread_local rxgpu_ft_stats g_ft_stats{};
+
+}  // namespace
+
+struct rxgpu_ft_index {
+	int device = 0;
+	int sm_count = 148;
+	uint32_t total_docs = 0, nfields = 0;
+	DevBuf<uint32_t> words;
+	DevBuf<float> avg;
+	DevBuf<uint8_t> removed;
+	bool has_removed = false;
+	std::vector<DevList> lists;
+	uint32_t max_list = 0;
+	cudaStream_t stream = nullptr;
+	std::mutex mtx;  // one merge at a time per index (the per-document scratch below is shared)
+	// scratch
+	DevBuf<uint32_t> mask, tmask, idoff, block_counts, scalar_u32;
+	DevBuf<uint16_t> score;
+	DevBuf<unsigned long long> hist, popc;
+	DevBuf<uint8_t> excluded, tmp_field, md_field;
+	DevBuf<float> tmp_rank, md_proc, ext_rank;
+	DevBuf<int32_t> md_id;
+	DevBuf<unsigned long long> last_ptr, next_ptr;
+	DevBuf<uint32_t> last_n, next_n;
+	DevBuf<uint16_t> ext_cnt, ext_last_term;
+	~rxgpu_ft_index() {
+		cudaSetDevice(device);
+		for (auto& l : lists) {
+			cudaFree(l.doc_ids);
+			cudaFree(l.pos_begin);
+			cudaFree(l.positions);
+		}
+		if (stream) {
+			cudaStreamDestroy(stream);
+		}
+	}
+};
+
+extern "C" {
+
+int rxgpu_ft_create(rxgpu_ft_index** out, uint32_t total_docs, uint32_t nfields, const uint32_t* words_in_field, const float* avg_words,
+					const uint8_t* removed, int device) {
+	if (!out || !words_in_field || !avg_words) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	*out = nullptr;
+	if (nfields == 0 || nfields > uint32_t(kMaxFtFields)) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: full-text index needs 1..64 fields");
+	}
+	if (rxgpu_device_count() <= device || device < 0) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: no usable CUDA device (this library has no CPU fallback)");
+	}
+	RX_CUDA(cudaSetDevice(device));
+	auto ft = std::make_unique<rxgpu_ft_index>();
+	ft->device = device;
+	ft->total_docs = total_docs;
+	ft->nfields = nfields;
+	cudaDeviceProp prop{};
+	RX_CUDA(cudaGetDeviceProperties(&prop, device));
+	ft->sm_count = prop.multiProcessorCount;
+	RX_CUDA(cudaStreamCreateWithFlags(&ft->stream, cudaStreamNonBlocking));
+	const size_t nw = std::max<size_t>(1, size_t(total_docs) * nfields);
+	RX_CUDA(ft->words.ensure(nw));
+	RX_CUDA(ft->avg.ensure(nfields));
+	RX_CUDA(cudaMemcpy(ft->words.p, words_in_field, size_t(total_docs) * nfields * 4, cudaMemcpyHostToDevice));
+	RX_CUDA(cudaMemcpy(ft->avg.p, avg_words, nfields * 4, cudaMemcpyHostToDevice));
+	if (removed) {
+		RX_CUDA(ft->removed.ensure(std::max<size_t>(1, total_docs)));
+		RX_CUDA(cudaMemcpy(ft->removed.p, removed, total_docs, cudaMemcpyHostToDevice));
+		ft->has_removed = true;
+	}
+	*out = ft.release();
+	return 0;
+}
+
+void rxgpu_ft_destroy(rxgpu_ft_index* ft) { delete ft; }
+
+int rxgpu_ft_add_postings(rxgpu_ft_index* ft, const rxgpu_ft_postings* list, uint32_t* out_id) {
+	if (!ft || !list || !out_id) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	RX_CUDA(cudaSetDevice(ft->device));
+	DevList l;
+	l.ndocs = list->ndocs;
+	l.npos = list->ndocs ? list->pos_begin[list->ndocs] : 0;
+	for (uint32_t i = 0; i < list->ndocs; ++i) {
+		if (list->doc_ids[i] >= ft->total_docs || (i && list->doc_ids[i] <= list->doc_ids[i - 1])) {
+			return fail(RXGPU_ERR_PARAMS, "rxgpu: posting list must hold ascending document ids below total_docs");
+		}
+	}
+	for (uint64_t p = 0; p < l.npos; ++p) {
+		if ((list->positions[p] >> 24) >= ft->nfields) {
+			return fail(RXGPU_ERR_PARAMS, "rxgpu: posting position refers to a field outside the index");
+		}
+	}
+	RX_CUDA(cudaMalloc(reinterpret_cast<void**>(&l.doc_ids), std::max<size_t>(1, l.ndocs) * 4));
+	RX_CUDA(cudaMalloc(reinterpret_cast<void**>(&l.pos_begin), (size_t(l.ndocs) + 1) * 4));
+	RX_CUDA(cudaMalloc(reinterpret_cast<void**>(&l.positions), std::max<uint64_t>(1, l.npos) * 4));
+	if (l.ndocs) {
+		RX_CUDA(cudaMemcpy(l.doc_ids, list->doc_ids, size_t(l.ndocs) * 4, cudaMemcpyHostToDevice));
+		RX_CUDA(cudaMemcpy(l.pos_begin, list->pos_begin, (size_t(l.ndocs) + 1) * 4, cudaMemcpyHostToDevice));
+		RX_CUDA(cudaMemcpy(l.positions, list->positions, l.npos * 4, cudaMemcpyHostToDevice));
+	} else {
+		const uint32_t zero = 0;
+		RX_CUDA(cudaMemcpy(l.pos_begin, &zero, 4, cudaMemcpyHostToDevice));
+	}
+	ft->lists.push_back(l);
+	ft->max_list = std::max(ft->max_list, l.ndocs);
+	*out_id = uint32_t(ft->lists.size() - 1);
+	return 0;
+}
+
+void rxgpu_ft_last_stats(rxgpu_ft_stats* out) {
+	if (out) {
+		*out = g_ft_stats;
+	}
+}
+
+int rxgpu_ft_merge(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nterms, const rxgpu_ft_term* terms, const uint8_t* excluded,
+				   int rank_sort_type, uint64_t max_out, rxgpu_ft_merge_info* out, uint64_t* out_n) {
+	if (!ft || !cfg || !out_n || (nterms && !terms)) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	if (cfg->nfields != ft->nfields || !cfg->fields) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: config field count differs from the index");
+	}
+	if (rank_sort_type == 2) {
+		return fail(RXGPU_ERR_LOGIC, "RankSortType::ExternalExpression not implemented.");  // merger.h:151
+	}
+	RX_CUDA(cudaSetDevice(ft->device));
+	g_ft_stats = rxgpu_ft_stats{};
+	*out_n = 0;
+	const uint32_t N = ft->total_docs;
+	if (nterms == 0 || (nterms == 1 && terms[0].op == 3) || N == 0) {  // QueryMergeData::Empty(), mergerimpl.h:472
+		return 0;
+	}
+	for (uint32_t t = 0; t < nterms; ++t) {
+		if (terms[t].op < 1 || terms[t].op > 3 || !terms[t].field_boosts || (terms[t].nsubterms && (!terms[t].postings || !terms[t].procs))) {
+			return fail(RXGPU_ERR_PARAMS, "rxgpu: malformed query term");
+		}
+		for (uint32_t s = 0; s < terms[t].nsubterms; ++s) {
+			if (terms[t].postings[s] >= ft->lists.size()) {
+				return fail(RXGPU_ERR_PARAMS, "rxgpu: unknown posting list id");
+			}
+		}
+	}
+	std::lock_guard<std::mutex> lck(ft->mtx);
+	cudaStream_t st = ft->stream;
+	const int sm = ft->sm_count;
+
+	// SortSubterms: proc descending (querymergedata.h); stable here, the reference's pdqsort is not -- equal procs are a
+	// don't-care of the reference itself
+	struct Sub {
+		uint32_t list;
+		float proc;
+	};
+	std::vector<std::vector<Sub>> subs(nterms);
+	uint64_t totalORVids = 0;
+	for (uint32_t t = 0; t < nterms; ++t) {
+		for (uint32_t s = 0; s < terms[t].nsubterms; ++s) {
+			subs[t].push_back(Sub{terms[t].postings[s], terms[t].procs[s]});
+			totalORVids += ft->lists[terms[t].postings[s]].ndocs;
+		}
+		std::stable_sort(subs[t].begin(), subs[t].end(), [](const Sub& a, const Sub& b) { return a.proc > b.proc; });
+	}
+	const uint32_t maxMerged = uint32_t(std::min<uint64_t>(cfg->merge_limit, totalORVids));  // init(), merger.h:66-67
+	const bool simple = nterms == 1 && terms[0].op != 3;
+	const bool trivial = simple && terms[0].nsubterms == 1;
+	if (maxMerged == 0) {
+		return 0;
+	}
+
+	// scratch
+	const uint32_t mwords = (N + 31) / 32;
+	const uint32_t nblocks_list = (ft->max_list + kFtThreads - 1) / kFtThreads + 1;
+	const uint32_t nblocks_docs = (N + kFtThreads - 1) / kFtThreads + 1;
+	RX_CUDA(ft->mask.ensure(mwords));
+	RX_CUDA(ft->tmask.ensure(mwords));
+	RX_CUDA(ft->block_counts.ensure(std::max(nblocks_list, nblocks_docs)));
+	RX_CUDA(ft->scalar_u32.ensure(4));
+	RX_CUDA(ft->popc.ensure(1));
+	RX_CUDA(ft->tmp_rank.ensure(std::max<size_t>(1, ft->max_list)));
+	RX_CUDA(ft->tmp_field.ensure(std::max<size_t>(1, ft->max_list)));
+	RX_CUDA(ft->md_id.ensure(maxMerged));
+	RX_CUDA(ft->md_proc.ensure(maxMerged));
+	RX_CUDA(ft->md_field.ensure(maxMerged));
+	if (!trivial) {
+		RX_CUDA(ft->idoff.ensure(N));
+	}
+	if (!simple) {
+		RX_CUDA(ft->last_ptr.ensure(maxMerged));
+		RX_CUDA(ft->next_ptr.ensure(maxMerged));
+		RX_CUDA(ft->last_n.ensure(maxMerged));
+		RX_CUDA(ft->next_n.ensure(maxMerged));
+		RX_CUDA(ft->ext_rank.ensure(maxMerged));
+		RX_CUDA(ft->ext_cnt.ensure(maxMerged));
+		RX_CUDA(ft->ext_last_term.ensure(maxMerged));
+	}
+	const uint8_t* d_excluded = nullptr;
+	if (excluded) {
+		RX_CUDA(ft->excluded.ensure(N));
+		RX_CUDA(cudaMemcpyAsync(ft->excluded.p, excluded, N, cudaMemcpyHostToDevice, st));
+		d_excluded = ft->excluded.p;
+	}
+	MergeState ms{};
+	ms.mask = ft->mask.p;
+	ms.tmask = ft->tmask.p;
+	ms.idoff = trivial ? nullptr : ft->idoff.p;
+	ms.md_id = ft->md_id.p;
+	ms.md_proc = ft->md_proc.p;
+	ms.md_field = ft->md_field.p;
+	ms.last_ptr = ft->last_ptr.p;
+	ms.last_n = ft->last_n.p;
+	ms.next_ptr = ft->next_ptr.p;
+	ms.next_n = ft->next_n.p;
+	ms.ext_rank = ft->ext_rank.p;
+	ms.ext_cnt = ft->ext_cnt.p;
+	ms.ext_last_term = ft->ext_last_term.p;
+	ms.n_docs = ft->scalar_u32.p;            // [0] numDocs()
+	uint32_t* d_total_new = ft->scalar_u32.p + 1;  // [1] new docs of the current pass
+
+	cudaEvent_t e0, e1;
+	RX_CUDA(cudaEventCreate(&e0));
+	RX_CUDA(cudaEventCreate(&e1));
+	RX_CUDA(cudaEventRecord(e0, st));
+	RX_CUDA(cudaMemsetAsync(ft->scalar_u32.p, 0, 16, st));
+	if (!trivial) {
+		ft_fill_u32<<<gridFor(N, sm), kFtThreads, 0, st>>>(ft->idoff.p, maxMerged, N);
+		g_ft_stats.launches++;
+	}
+	ft_mask_init<<<gridFor(mwords, sm), kFtThreads, 0, st>>>(ft->mask.p, d_excluded, N, mwords);
+	g_ft_stats.launches++;
+
+	auto termParams = [&](uint32_t t, const Sub& sub, const DevList& l) {
+		TermParams p{};
+		for (uint32_t f = 0; f < ft->nfields; ++f) {
+			p.field_boosts[f] = terms[t].field_boosts[f];
+			p.fc[f] = FieldCfgF{float(cfg->fields[f].bm25_weight),     float(cfg->fields[f].bm25_boost),     float(cfg->fields[f].position_weight),
+								float(cfg->fields[f].position_boost), float(cfg->fields[f].term_len_weight), float(cfg->fields[f].term_len_boost)};
+		}
+		p.boost = terms[t].boost;
+		p.term_len_boost = terms[t].term_len_boost;
+		p.proc = sub.proc;
+		p.k1 = cfg->bm25_k1;
+		p.b = cfg->bm25_b;
+		p.bm25_type = cfg->bm25_type;
+		p.nfields = ft->nfields;
+		p.dist_weight = float(cfg->distance_weight);
+		p.dist_boost = float(cfg->distance_boost);
+		const double totalDocCount = double(N - 1), matched = double(l.ndocs);  // mergerimpl.h:122-124
+		if (cfg->bm25_type == 0) {  // Bm25Rx::IDF (bm25.h:21-27), on the host: the same libm as the reference
+			double f = std::log((totalDocCount - matched + 1) / matched) / std::log(1 + totalDocCount);
+			p.idf = f < 0.2 ? 0.2 : f;
+		} else if (cfg->bm25_type == 1) {
+			p.idf = std::log(totalDocCount / (matched + 1)) + 1;
+		}
+		return p;
+	};
+	auto bytesOfPass = [&](const DevList& l) { return uint64_t(l.ndocs) * 20 + l.npos * 4; };
+
+	int checkRemoved = 1;
+	if (!simple) {
+		// buildRestrictingBitmask (mergerimpl.h:326-384)
+		for (uint32_t t = 0; t < nterms; ++t) {
+			if (terms[t].op != 2) {
+				continue;
+			}
+			RX_CUDA(cudaMemsetAsync(ft->tmask.p, 0, size_t(mwords) * 4, st));
+			int allPositive = 1;
+			for (uint32_t f = 0; f < ft->nfields; ++f) {
+				allPositive &= terms[t].field_boosts[f] != 0.f;
+			}
+			for (const Sub& sub : subs[t]) {
+				const DevList& l = ft->lists[sub.list];
+				if (l.ndocs) {
+					ft_and_mark<<<gridFor(l.ndocs, sm), kFtThreads, 0, st>>>(l, termParams(t, sub, l), allPositive, ft->tmask.p);
+					g_ft_stats.launches++;
+					g_ft_stats.postings_scanned += l.ndocs;
+					g_ft_stats.algorithmic_bytes += bytesOfPass(l);
+				}
+			}
+			ft_mask_and<<<gridFor(mwords, sm), kFtThreads, 0, st>>>(ft->mask.p, ft->tmask.p, mwords);
+			g_ft_stats.launches++;
+		}
+		for (uint32_t t = 0; t < nterms; ++t) {
+			if (terms[t].op != 3) {
+				continue;
+			}
+			for (const Sub& sub : subs[t]) {
+				const DevList& l = ft->lists[sub.list];
+				if (l.ndocs) {
+					ft_not_clear<<<gridFor(l.ndocs, sm), kFtThreads, 0, st>>>(l, ft->mask.p);
+					g_ft_stats.launches++;
+					g_ft_stats.postings_scanned += l.ndocs;
+				}
+			}
+		}
+		// estimateNumDocsInMerge (merger.h:239-267)
+		uint64_t estOr = 0, estAnd = UINT64_MAX;
+		for (uint32_t t = 0; t < nterms; ++t) {
+			if (terms[t].op == 3) {
+				continue;
+			}
+			uint64_t nd = 0;
+			for (const Sub& sub : subs[t]) {
+				nd += ft->lists[sub.list].ndocs;
+			}
+			if (terms[t].op == 2) {
+				estAnd = std::min(estAnd, nd);
+			} else {
+				estOr += nd;
+			}
+		}
+		const uint64_t est = std::min<uint64_t>(std::min(estOr, estAnd), N);
+		bool preselect = est > cfg->merge_limit && N > cfg->merge_limit && !std::getenv("REINDEXER_NO_2PHASE_FT_MERGE");
+		if (preselect) {
+			RX_CUDA(cudaMemsetAsync(ft->popc.p, 0, 8, st));
+			ft_popcount<<<gridFor(mwords, sm), kFtThreads, 0, st>>>(ft->mask.p, mwords, ft->popc.p);
+			g_ft_stats.launches++;
+			unsigned long long pop = 0;
+			RX_CUDA(cudaMemcpyAsync(&pop, ft->popc.p, 8, cudaMemcpyDeviceToHost, st));
+			RX_CUDA(cudaStreamSynchronize(st));
+			preselect = pop > cfg->merge_limit;
+		}
+		if (preselect) {
+			// preselectMostRelevantDocs (mergerimpl.h:386-464)
+			g_ft_stats.preselected = 1;
+			RX_CUDA(ft->score.ensure(N));
+			RX_CUDA(ft->hist.ensure(65536));
+			RX_CUDA(cudaMemsetAsync(ft->score.p, 0, size_t(N) * 2, st));
+			RX_CUDA(cudaMemsetAsync(ft->hist.p, 0, 65536 * 8, st));
+			for (uint32_t t = 0; t < nterms; ++t) {
+				if (terms[t].op == 3) {
+					continue;
+				}
+				RX_CUDA(cudaMemsetAsync(ft->tmask.p, 0, size_t(mwords) * 4, st));
+				int allSame = 1;
+				for (uint32_t f = 0; f < ft->nfields; ++f) {
+					allSame &= terms[t].field_boosts[f] == terms[t].field_boosts[0];
+				}
+				for (const Sub& sub : subs[t]) {
+					const DevList& l = ft->lists[sub.list];
+					if (l.ndocs) {
+						ft_score_pass<<<gridFor(l.ndocs, sm), kFtThreads, 0, st>>>(l, termParams(t, sub, l), allSame, ft->mask.p, ft->tmask.p,
+																					ft->score.p);
+						g_ft_stats.launches++;
+						g_ft_stats.postings_scanned += l.ndocs;
+						g_ft_stats.algorithmic_bytes += bytesOfPass(l);
+					}
+				}
+			}
+			ft_hist<<<gridFor(N, sm), kFtThreads, 0, st>>>(ft->score.p, ft->mask.p, ft->has_removed ? ft->removed.p : nullptr, N, ft->hist.p);
+			g_ft_stats.launches++;
+			g_ft_stats.algorithmic_bytes += uint64_t(N) * 2;
+			std::vector<unsigned long long> hist(65536);
+			RX_CUDA(cudaMemcpyAsync(hist.data(), ft->hist.p, 65536 * 8, cudaMemcpyDeviceToHost, st));
+			RX_CUDA(cudaStreamSynchronize(st));
+			size_t minScore = 65535, minScoreDocs = 0, docsTaken = 0;
+			for (size_t sc = 65535; sc > 0; sc--) {
+				if (docsTaken >= maxMerged) {
+					break;
+				}
+				minScore = sc;
+				minScoreDocs = maxMerged - docsTaken;
+				docsTaken += hist[sc];
+			}
+			const unsigned db = (N + kFtThreads - 1) / kFtThreads;
+			ft_thresh_count<<<db, kFtThreads, 0, st>>>(ft->score.p, ft->mask.p, N, uint32_t(minScore), ft->block_counts.p);
+			ft_scan_blocks<<<1, 1024, 0, st>>>(ft->block_counts.p, db, nullptr);
+			ft_thresh_apply<<<db, kFtThreads, 0, st>>>(ft->score.p, ft->mask.p, N, uint32_t(minScore), uint32_t(minScoreDocs),
+													   ft->block_counts.p);
+			g_ft_stats.launches += 3;
+			g_ft_stats.algorithmic_bytes += uint64_t(N) * 4;
+			checkRemoved = 0;  // needToCheckRemoved_ = false (:463)
+		}
+	}
+
+	// mergeSimple / mergeTerm passes
+	const uint32_t* d_words = ft->words.p;
+	const uint8_t* d_removed = ft->has_removed ? ft->removed.p : nullptr;
+	uint16_t qpIdx = 0;
+	for (uint32_t t = 0; t < nterms; ++t) {
+		if (terms[t].op == 3) {
+			continue;
+		}
+		++qpIdx;
+		if (!simple) {
+			ft_switch<<<gridFor(maxMerged, sm), kFtThreads, 0, st>>>(ms);
+			g_ft_stats.launches++;
+		}
+		for (const Sub& sub : subs[t]) {
+			const DevList& l = ft->lists[sub.list];
+			if (!l.ndocs) {
+				continue;
+			}
+			const unsigned lb = (l.ndocs + kFtThreads - 1) / kFtThreads;
+			ft_rank_pass<<<lb, kFtThreads, 0, st>>>(l, termParams(t, sub, l), ms, d_words, ft->avg.p, d_removed, checkRemoved, simple ? 1 : 0,
+													maxMerged, qpIdx, ft->tmp_rank.p, ft->tmp_field.p, ft->block_counts.p);
+			ft_scan_blocks<<<1, 1024, 0, st>>>(ft->block_counts.p, lb, d_total_new);
+			ft_assign<<<lb, kFtThreads, 0, st>>>(l, ms, simple ? 1 : 0, maxMerged, qpIdx, ft->tmp_rank.p, ft->tmp_field.p, ft->block_counts.p);
+			ft_bump_count<<<1, 1, 0, st>>>(ms.n_docs, d_total_new, maxMerged);
+			g_ft_stats.launches += 4;
+			g_ft_stats.postings_scanned += l.ndocs;
+			g_ft_stats.algorithmic_bytes += bytesOfPass(l) + uint64_t(l.ndocs) * 9;
+		}
+	}
+	// canBeBoostedByFullMatch: termsCounter == queryParts.size() (NOT parts never count) ; QueryLength == nterms
+	ft_full_match<<<gridFor(maxMerged, sm), kFtThreads, 0, st>>>(ms, d_words, ft->nfields, simple ? 1u : nterms, nterms, simple ? 1 : 0,
+																 cfg->full_match_boost);
+	g_ft_stats.launches++;
+	RX_CUDA(cudaGetLastError());
+	uint32_t n = 0;
+	RX_CUDA(cudaMemcpyAsync(&n, ms.n_docs, 4, cudaMemcpyDeviceToHost, st));
+	RX_CUDA(cudaEventRecord(e1, st));
+	RX_CUDA(cudaStreamSynchronize(st));
+	RX_CUDA(cudaEventElapsedTime(&g_ft_stats.device_ms, e0, e1));
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+
+	// postProcessResults (merger.h:111-155) on the host: <= merge_limit entries
+	try {
+		std::vector<int32_t> ids(n);
+		std::vector<float> procs(n);
+		std::vector<uint8_t> fields(n);
+		if (n) {
+			RX_CUDA(cudaMemcpy(ids.data(), ms.md_id, size_t(n) * 4, cudaMemcpyDeviceToHost));
+			RX_CUDA(cudaMemcpy(procs.data(), ms.md_proc, size_t(n) * 4, cudaMemcpyDeviceToHost));
+			RX_CUDA(cudaMemcpy(fields.data(), ms.md_field, n, cudaMemcpyDeviceToHost));
+		}
+		std::vector<rxgpu_ft_merge_info> md(n);
+		float maxProc = 0.f;
+		for (uint32_t i = 0; i < n; ++i) {
+			md[i] = rxgpu_ft_merge_info{ids[i], procs[i], fields[i], 0};
+			maxProc = std::max(maxProc, procs[i]);
+		}
+		const float scalingFactor = maxProc > 255 ? float(255.0 / maxProc) : 1.0f;
+		const float minProc = float(cfg->min_rank);
+		size_t passed = md.size();
+		while (passed > 0 && md[passed - 1].proc < minProc) {
+			passed--;
+		}
+		for (size_t i = 0; i + 1 < passed; i++) {
+			if (md[i].proc < minProc) {
+				md[i] = md[passed - 1];
+				passed--;
+				while (passed > i && md[passed - 1].proc < minProc) {
+					passed--;
+				}
+			}
+		}
+		md.resize(passed);
+		for (auto& m : md) {
+			m.normalized_proc = uint8_t(m.proc * scalingFactor);
+			m.proc = m.normalized_proc;
+		}
+		if (rank_sort_type == 0 || rank_sort_type == 4) {  // RankOnly / IDAndPositions
+			std::stable_sort(md.begin(), md.end(),
+							 [](const rxgpu_ft_merge_info& l, const rxgpu_ft_merge_info& r) { return l.normalized_proc > r.normalized_proc; });
+		}
+		*out_n = md.size();
+		for (size_t i = 0; i < md.size() && i < max_out; ++i) {
+			out[i] = md[i];
+		}
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
+	}
+	return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+"""Random ft_fast merge problems for the oracle pin tests and the GPU parity tests (test infrastructure)."""
+import numpy as np
+
+from oracle import ft_oracle as F
+
+
+def random_problem(seed, total_docs=400, nfields=1, nterms=3, max_sub=3, density=0.2, merge_limit=20000, ops=None, removed_frac=0.0,
+                   excluded_frac=0.0, field_boost_zero=False, max_pos=3, doc_len=(3, 40)):
+    rng = np.random.default_rng(seed)
+    words = rng.integers(doc_len[0], doc_len[1], size=(total_docs, nfields)).astype(np.uint32)
+    words[0] = 0
+    removed = (rng.random(total_docs) < removed_frac).astype(np.uint8) if removed_frac else None
+    excluded = (rng.random(total_docs) < excluded_frac).astype(np.uint8) if excluded_frac else None
+    p = F.FtProblem(total_docs, words, removed=removed, excluded=excluded)
+    p.cfg["merge_limit"] = merge_limit
+    procs_pool = [100.0, 90.0, 85.0, 80.0, 72.0, 65.0, 57.0, 50.0, 43.0, 31.0]
+    for t in range(nterms):
+        nsub = int(rng.integers(1, max_sub + 1))
+        subs = []
+        procs = rng.choice(procs_pool, size=nsub, replace=False)  # distinct procs: SortSubterms is unstable for ties
+        for s in range(nsub):
+            dens = density * float(rng.uniform(0.3, 1.5)) / (1 + s)
+            ndocs = max(1, int(dens * (total_docs - 1)))
+            docs = np.sort(rng.choice(np.arange(1, total_docs), size=min(ndocs, total_docs - 1), replace=False))
+            pos_lists = []
+            for d in docs:
+                npos = int(rng.integers(1, max_pos + 1))
+                pp = []
+                for _ in range(npos):
+                    f = int(rng.integers(0, nfields))
+                    pp.append((int(rng.integers(0, max(int(words[d, f]), 1))), f))
+                pos_lists.append(pp)
+            subs.append((p.add_list(docs, pos_lists), float(procs[s])))
+        op = ops[t] if ops else int(rng.choice([F.OP_OR, F.OP_OR, F.OP_AND, F.OP_NOT])) if t else F.OP_OR
+        fb = np.ones(nfields, np.float32)
+        if nfields > 1:
+            fb = rng.choice([1.0, 0.5, 2.0, 1.5], size=nfields).astype(np.float32)
+            if field_boost_zero:
+                fb[int(rng.integers(0, nfields))] = 0.0
+        p.add_term(subs, op=op, boost=float(rng.choice([1.0, 1.0, 0.7, 1.3])), term_len_boost=float(rng.choice([1.0, 0.8, 0.5])),
+                   field_boosts=fb)
+    return p
+
+
+def assert_same_merge(a, b, rank_sort_type, ctx=""):
+    """a, b: MERGE_INFO arrays.  RankAndID / IDOnly keep the merge order (deterministic); RankOnly / IDAndPositions are sorted by an
+    unstable sort, so equal ranks compare as sets."""
+    assert len(a) == len(b), (ctx, len(a), len(b))
+    if rank_sort_type in (F.RANK_AND_ID, F.ID_ONLY):
+        assert (a["id"] == b["id"]).all(), ctx
+        assert (a["normalized_proc"] == b["normalized_proc"]).all(), (ctx, a[:8], b[:8])
+        assert (a["field"] == b["field"]).all(), ctx
+        assert (a["proc"] == b["proc"]).all(), ctx
+    else:
+        assert (a["normalized_proc"] == b["normalized_proc"]).all(), ctx
+        oa, ob = np.lexsort((a["id"], -a["normalized_proc"].astype(int))), np.lexsort((b["id"], -b["normalized_proc"].astype(int)))
+        assert (a["id"][oa] == b["id"][ob]).all() and (a["field"][oa] == b["field"][ob]).all(), ctx
+
+
+def load_golden_problem(g, name):
+    """Rebuild an FtProblem from tests/golden/ft_golden.npz (inputs are stored, not regenerated)."""
+    words = g[f"{name}/words"]
+    rem, exc = g[f"{name}/removed"], g[f"{name}/excluded"]
+    p = F.FtProblem(words.shape[0], words, avg=g[f"{name}/avg"], removed=rem if len(rem) else None, excluded=exc if len(exc) else None)
+    for i in range(int(g[f"{name}/nlists"])):
+        p.add_list_arrays(g[f"{name}/list{i}/docs"], g[f"{name}/list{i}/begin"], g[f"{name}/list{i}/pos"])
+    for i in range(int(g[f"{name}/nterms"])):
+        op, boost, tlb = g[f"{name}/term{i}/scalars"]
+        p.terms.append(dict(op=int(op), boost=float(boost), term_len_boost=float(tlb), field_boosts=g[f"{name}/term{i}/field_boosts"],
+                            postings=g[f"{name}/term{i}/postings"], procs=g[f"{name}/term{i}/procs"]))
+    p.cfg["merge_limit"] = int(g[f"{name}/merge_limit"])
+    return p
+
+
+def gpu_merge(prob, rank_sort_type=F.RANK_AND_ID):
+    """Run one problem through the product (rxgpu_ft_*); returns (result, stats)."""
+    import reindexer_b200 as rx
+
+    ft = rx.GpuFtIndex(prob.total_docs, prob.words, prob.avg, prob.removed)
+    ids = [ft.add_postings(d, b, p) for d, b, p in prob.lists]
+    terms = [dict(t, postings=[ids[int(x)] for x in t["postings"]]) for t in prob.terms]
+    res = ft.merge(prob.cfg, prob.field_cfg, terms, excluded=prob.excluded, rank_sort_type=rank_sort_type)
+    st = ft.last_stats()
+    ft.close()
+    return res, st

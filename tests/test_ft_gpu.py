@@ -1,0 +1,92 @@
+"""GPU parity tests of the ft_fast merge (rxgpu_ft_merge) against the oracle -- the reference's own ft::Merger::Merge when
+oracle/_ref is present, else the pinned C port -- and the committed golden fixtures.  Integer outputs (ids, order, uint8 ranks,
+fields) must match exactly: the device evaluates BM25 in fp64 and the rank products in fp32 in the reference's operation order."""
+import os
+
+import numpy as np
+import pytest
+from ft_helpers import assert_same_merge, gpu_merge, load_golden_problem, random_problem
+
+from oracle import ft_oracle as F
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_golden_fixtures():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ft_golden.npz"))
+    for name in g["names"]:
+        p = load_golden_problem(g, str(name))
+        for rst in (F.RANK_AND_ID, F.RANK_ONLY):
+            res, st = gpu_merge(p, rst)
+            assert_same_merge(g[f"{name}/result{rst}"], res, rst, ctx=f"{name} rst={rst}")
+        if "preselect" in str(name):
+            assert st["preselected"] == 1
+
+
+def test_known_answer_values():
+    p = F.FtProblem(6, np.array([0, 8, 3, 6, 12, 3], np.uint32))
+    p.add_term([(p.add_list([1], [[(0, 0)]]), 100.0), (p.add_list([1], [[(6, 0)]]), 80.0)])
+    assert gpu_merge(p)[0].tolist() == [(1, 97.0, 0, 97)]  # uint8(97.9844), FTGenericApi.DebugInfo ft_generic.cc:326
+    p2 = F.FtProblem(6, np.array([0, 8, 3, 6, 12, 3], np.uint32))
+    p2.add_term([(p2.add_list([1], [[(6, 0)]]), 80.0)])
+    assert gpu_merge(p2)[0].tolist() == [(1, 77.0, 0, 77)]  # uint8(77.91719), ft_generic.cc:327
+
+
+def test_random_problems_match_oracle():
+    preselects = 0
+    for seed in range(120):
+        rng = np.random.default_rng(seed)
+        kw = dict(total_docs=int(rng.integers(30, 3000)), nfields=1 + seed % 3, nterms=1 + seed % 4, removed_frac=0.05 * (seed % 2),
+                  excluded_frac=0.05 * (seed % 3 == 0), field_boost_zero=(seed % 5 == 0))
+        if seed % 4 == 1:
+            kw["merge_limit"] = int(rng.integers(5, 60))
+        p = random_problem(seed, **kw)
+        for rst in (F.RANK_AND_ID, F.RANK_ONLY):
+            a, _ = F.best_merge(p, rst)
+            b, st = gpu_merge(p, rst)
+            preselects += st["preselected"]
+            assert_same_merge(a, b, rst, ctx=f"seed {seed} rst {rst}")
+    assert preselects > 10
+
+
+def test_config_knobs_and_bm25_variants():
+    for seed in range(24):
+        p = random_problem(1000 + seed, total_docs=400, nfields=2, nterms=2)
+        p.cfg.update(bm25_type=seed % 3, bm25_k1=1.2 + 0.1 * (seed % 5), bm25_b=0.5 + 0.05 * (seed % 4), min_rank=seed % 40,
+                     distance_weight=0.3, distance_boost=1.5, full_match_boost=1.3)
+        p.field_cfg[0].update(bm25_weight=0.4, position_weight=0.3, term_len_weight=0.2, bm25_boost=1.2)
+        assert_same_merge(F.best_merge(p)[0], gpu_merge(p)[0], F.RANK_AND_ID, ctx=f"seed {seed}")
+
+
+def test_empty_and_degenerate_queries():
+    p = random_problem(5, total_docs=100, nterms=1)
+    p.terms[0]["op"] = F.OP_NOT  # a lone NOT term: Empty()
+    assert len(gpu_merge(p)[0]) == 0 and len(F.best_merge(p)[0]) == 0
+    p = random_problem(6, total_docs=100, nterms=2, ops=[F.OP_AND, F.OP_AND])  # pure AND: never preselects (estimate 0)
+    assert_same_merge(F.best_merge(p)[0], gpu_merge(p)[0], F.RANK_AND_ID)
+    p = random_problem(7, total_docs=100, nterms=2, ops=[F.OP_OR, F.OP_NOT])
+    assert_same_merge(F.best_merge(p)[0], gpu_merge(p)[0], F.RANK_AND_ID)
+
+
+def test_larger_corpus_three_term_or_with_preselect():
+    """BASELINE config 3 in miniature: 3-term OR with document frequencies 10% / 1% / 0.1%, more candidates than merge_limit,
+    top-100 of the final (rank desc, id asc) order."""
+    total, rng = 400_001, np.random.default_rng(3)
+    words = rng.poisson(100, size=(total, 1)).astype(np.uint32) + 1
+    words[0] = 0
+    p = F.FtProblem(total, words)
+    for df in (0.10, 0.01, 0.001):
+        docs = np.sort(rng.choice(np.arange(1, total), size=int(df * (total - 1)), replace=False)).astype(np.uint32)
+        npos = rng.integers(1, 4, size=len(docs))
+        begin = np.concatenate([[0], np.cumsum(npos)]).astype(np.uint32)
+        pos = np.zeros(begin[-1], np.uint32)
+        for i in range(len(docs)):  # ascending distinct positions inside the document
+            pos[begin[i]:begin[i + 1]] = np.sort(rng.choice(int(words[docs[i], 0]), size=min(int(npos[i]), int(words[docs[i], 0])),
+                                                            replace=False))[:npos[i]] if words[docs[i], 0] >= npos[i] else np.arange(npos[i])
+        p.add_term([(p.add_list_arrays(docs, begin, pos), 100.0)], op=F.OP_OR)
+    a, ns = F.best_merge(p)
+    b, st = gpu_merge(p)
+    assert st["preselected"] == 1 and len(a) > 1000
+    assert_same_merge(a, b, F.RANK_AND_ID)
+    assert (F.after_select_order(a)[:100] == F.after_select_order(b)[:100]).all()
