@@ -69,8 +69,12 @@ def test_hnsw_default_ef_small_k_and_errors():
         gpu.hnsw_search_knn(queries, 10, 64)
     assert "changed after the HNSW graph was imported" in e.value.what
     fresh = rx.GpuBruteforceSearch(metric, dim, 10)
-    with pytest.raises(rx.RxGpuError):
+    d, l, c = fresh.hnsw_search_knn(queries, 10, 64)  # empty index: empty result like hnswalg.h:1989-1991
+    assert (c == 0).all()
+    fresh.add_point(vecs[0], 7)
+    with pytest.raises(rx.RxGpuError) as e:
         fresh.hnsw_search_knn(queries, 10, 64)
+    assert "no HNSW graph imported" in e.value.what
 
 
 def test_hnsw_768_cosine_recall():
