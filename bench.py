@@ -186,6 +186,8 @@ def run_ours(args):
     idx.append_synth(SEED, rank * rows, rows)  # shard `rank` = global rows [rank*rows, (rank+1)*rows)
     if args.query_tile:
         idx.set_query_tile(args.query_tile)
+    if args.tc:
+        idx.set_tensor_core_filter(args.tc)
     fill_s = time.perf_counter() - t_fill
     sharded = ShardedBruteforceSearch(idx, rows) if world > 1 else None
 
@@ -238,6 +240,9 @@ def run_ours(args):
         scan_launches += st["scan_launches"]
         alg_bytes += st["algorithmic_bytes"]
         qt = st["query_tile"]
+        tc_used = st["tc_used"]
+        tc_cands = st["tc_candidates"]
+        tc_fallbacks = st["tc_fallbacks"]
     ev1.record(stream)
     barrier()
     clocks = sampler.stop()
@@ -272,7 +277,12 @@ def run_ours(args):
         value = world * NQ / (ms_per_step / 1000.0)
         e2e_value = world * NQ / (e2e_s / args.steps)
         peak, peak_src = load_peaks()
-        per_launch_bytes = alg_bytes / max(passes, 1)
+        if tc_used:  # dominant kernel = knn_tc_filter: bf16 shadow rows + row norms + the resident query block, per launch
+            per_launch_bytes = rows * DIM * 2 + rows * 4 + qt * DIM * 2
+            kernel_name = "knn_tc_filter (tcgen05 bf16 filter, certified bound) + knn_rerank (exact fp32)"
+        else:
+            per_launch_bytes = alg_bytes / max(passes, 1)
+            kernel_name = "knn_scan_warp (fp32 FMA, fused top-k)"
         avg_launch_ms = scan_ms / max(scan_launches, 1)
         achieved = per_launch_bytes / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms > 0 else 0.0
         line = {
@@ -283,11 +293,12 @@ def run_ours(args):
                        if world == 1 else f"brute-force KNN, {world} x 10M x 768 fp32 sharded by row range, inner-product, k=10, "
                                           f"batch=1024, NCCL all-gather top-k merge (BASELINE configs[4] at N=8)",
                        "rows_per_gpu": rows, "total_rows": rows * world, "dim": DIM, "k": K, "batch": NQ, "query_tile": qt,
-                       "kernel": "knn_scan_warp (fp32 FMA, fused top-k)", "l2_policy": "inputs (30.7 GB/GPU) larger than L2, no flush",
+"kernel": kernel_name, "tc_candidates_per_step": tc_cands, "tc_fallbacks": tc_fallbacks,
+                       "l2_policy": "inputs (30.7 GB/GPU) larger than L2, no flush",
                        "global_queries_per_s": NQ / (ms_per_step / 1000.0), "index_fill_s": round(fill_s, 2),
                        "value_definition": "(query x 10M-row shard) scans per second over all ranks"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "knn_scan_warp",
+                         "traffic": None, "peak_source": peak_src, "kernel": "knn_tc_filter" if tc_used else "knn_scan_warp",
                          "bytes_per_launch": per_launch_bytes, "avg_launch_ms": avg_launch_ms, "launches_timed": scan_launches,
                          "kernel_share_of_step": scan_ms / ms_total if ms_total else None},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": NQ * DIM * 4,
@@ -313,6 +324,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default 10M = BASELINE config)")
     ap.add_argument("--query-tile", type=int, default=0)
+    ap.add_argument("--tc", type=int, default=0, help="tensor-core filter: 0 auto, 1 on, 2 off (exact fp32 scan only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -241,10 +241,16 @@ typedef struct {
 	uint32_t query_tile;
 	uint32_t tie_replays;
 	uint64_t algorithmic_bytes; /* SURVEY.md §8d definition: passes x (N*D*4 [+N*4 for Cosine] + QT*D*4 + QT*k*12) */
-	uint32_t scan_launches;     /* with rxgpu_set_profile(1): scan-kernel launches timed ... */
+	uint32_t scan_launches;     /* with rxgpu_set_profile(1): launches of the dominant kernel timed ... */
 	float scan_kernel_ms;       /* ... and their summed device time (CUDA events on the launching stream) */
+	uint32_t tc_used;           /* 1 when the tensor-core filter + exact re-rank path answered the batch */
+	uint32_t tc_fallbacks;      /* queries whose candidate list overflowed and were answered by the exact scan */
+	uint64_t tc_candidates;     /* rows re-ranked exactly */
 } rxgpu_search_stats;
 void rxgpu_last_search_stats(rxgpu_search_stats* out);
+/* large query batches: bf16 tensor-core filter + exact fp32 re-rank (results identical to the exact scan).
+ * mode 0 = automatic (batches >= 64 queries on >= 100k rows, k <= 15), 1 = whenever possible, 2 = never */
+int rxgpu_set_tensor_core_filter(rxgpu_index*, int mode);
 /* process-wide switch: bracket every scan-kernel launch with CUDA events (used by bench.py for the roofline figure) */
 int rxgpu_set_profile(int on);
 

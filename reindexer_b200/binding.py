@@ -73,7 +73,8 @@ FT_MERGE_INFO_DTYPE = np.dtype([("id", np.int32), ("proc", np.float32), ("field"
 
 class SearchStats(C.Structure):
     _fields_ = [("launches", C.c_uint32), ("passes", C.c_uint32), ("query_tile", C.c_uint32), ("tie_replays", C.c_uint32),
-                ("algorithmic_bytes", C.c_uint64), ("scan_launches", C.c_uint32), ("scan_kernel_ms", C.c_float)]
+                ("algorithmic_bytes", C.c_uint64), ("scan_launches", C.c_uint32), ("scan_kernel_ms", C.c_float),
+                ("tc_used", C.c_uint32), ("tc_fallbacks", C.c_uint32), ("tc_candidates", C.c_uint64)]
 
 
 # every symbol include/rxgpu.h declares (checked by tests/test_abi.py against the header text)
@@ -122,6 +123,7 @@ _SIGNATURES = {
     "rxgpu_set_query_tile": (C.c_int, [C.c_void_p, C.c_uint32]),
     "rxgpu_last_search_stats": (None, [C.POINTER(SearchStats)]),
     "rxgpu_set_profile": (C.c_int, [C.c_int]),
+    "rxgpu_set_tensor_core_filter": (C.c_int, [C.c_void_p, C.c_int]),
 }
 
 _lib = None
@@ -298,6 +300,10 @@ class GpuBruteforceSearch:
 
     def set_query_tile(self, qt: int):
         _check(self._lib.rxgpu_set_query_tile(self._h, qt))
+
+    def set_tensor_core_filter(self, mode: int):
+        """0 = auto, 1 = whenever possible, 2 = never (exact fp32 scan only)"""
+        _check(self._lib.rxgpu_set_tensor_core_filter(self._h, mode))
 
 
 def merge_shards(k, dist, idx, label, count, shard_base):

@@ -18,6 +18,7 @@
 #include "internal.h"
 #include "../host/knn_select.h"
 #include "knn_scan.cuh"
+#include "knn_tc.cuh"
 
 using namespace rxgpu;
 
@@ -121,8 +122,8 @@ int pickQueryTile(const rxgpu_index* ix, uint32_t nq) {
 
 // Top-k1 rows per query under the total order (dist, internal index) -- or, in tie mode, the first k1 rows in internal
 // order with dist <= bound.  Everything stays on the device; results land in d_out_* ([nq][k1]).
-int scanTopK(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, const float* d_queries, uint32_t nq, uint32_t k1, int mode,
-			 float bound, float* d_out_dist, uint32_t* d_out_idx, uint64_t* d_out_label, uint32_t* d_out_count) {
+int scanTopKExact(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, const float* d_queries, uint32_t nq, uint32_t k1, int mode,
+				  float bound, float* d_out_dist, uint32_t* d_out_idx, uint64_t* d_out_label, uint32_t* d_out_count) {
 	const int qt = mode == kModeTieRows ? 1 : pickQueryTile(ix, nq);
 	ScanArgs a{};
 	a.rows = ix->d_rows;
@@ -177,6 +178,210 @@ int scanTopK(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, const float*
 							 uint64_t(qt) * ix->dim * 4 + uint64_t(qt) * k1 * 12;
 	g_stats.algorithmic_bytes += perPass * ((nq + qt - 1) / qt);
 	return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- tensor-core filter
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+								   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+								   CUtensorMapFloatOOBfill);
+EncodeTiledFn encodeTiled() {  // libcuda is never linked: resolve the one driver entry point we need at run time
+	static EncodeTiledFn fn = [] {
+		void* p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+			cudaGetLastError();
+			return EncodeTiledFn(nullptr);
+		}
+		return reinterpret_cast<EncodeTiledFn>(p);
+	}();
+	return fn;
+}
+int makeBf16Map(CUtensorMap* m, void* base, uint64_t cols, uint64_t rows, uint64_t pitchBytes, uint32_t boxRows) {
+	const cuuint64_t gdim[2] = {cols, rows};
+	const cuuint64_t gstr[1] = {pitchBytes};
+	const cuuint32_t box[2] = {uint32_t(kTcChunkK), boxRows};
+	const cuuint32_t estr[2] = {1, 1};
+	const CUresult r = encodeTiled()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+									  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: cuTensorMapEncodeTiled failed (" + std::to_string(int(r)) + ")");
+	}
+	return 0;
+}
+
+constexpr size_t kTcSmemLimit = 227 * 1024;
+constexpr uint32_t kTcCandCap = 4096;
+
+uint32_t tcQueryBlock(uint32_t nq, uint32_t kchunks) {
+	uint32_t nqb = std::min<uint32_t>(256, (nq + 31u) & ~31u);
+	while (nqb >= 32 && tc_smem_bytes(nqb, kchunks) > kTcSmemLimit) {
+		nqb -= 32;
+	}
+	if (nqb < 32) {
+		return 0;
+	}
+	const uint32_t blocks = (nq + nqb - 1) / nqb;
+	return std::min(nqb, (((nq + blocks - 1) / blocks) + 31u) & ~31u);  // even out the blocks
+}
+
+bool tcEligible(const rxgpu_index* ix, uint32_t nq, uint32_t k1, int mode) {
+	if (ix->tc_mode == 2 || mode != kModeTopK || k1 > kTcMaxK1 || !encodeTiled()) {
+		return false;
+	}
+	if (tcQueryBlock(nq, (ix->dim + kTcChunkK - 1) / kTcChunkK) == 0) {
+		return false;
+	}
+	return ix->tc_mode == 1 || (nq >= 64 && ix->size >= 100000);
+}
+
+// bf16 shadow + row norms, rebuilt when the rows changed since the last large-batch search (10M x 768: ~7 ms)
+int ensureShadow(const rxgpu_index* ix, cudaStream_t st) {
+	std::lock_guard<std::mutex> lck(ix->tc_mtx);
+	const uint32_t pitchBf = (ix->dim + kTcChunkK - 1) / kTcChunkK * kTcChunkK;
+	if (!ix->d_shadow) {
+		const size_t cap = ix->capacity ? ix->capacity : 1;
+		RX_CUDA(cudaMalloc(&ix->d_shadow, cap * pitchBf * 2));
+		RX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ix->d_vnorm), cap * sizeof(float)));
+		ix->pitch_bf = pitchBf;
+		ix->shadow_version = ~0ull;
+	}
+	if (ix->shadow_version != ix->version) {
+		const unsigned blocks = unsigned((uint64_t(ix->size) * 32 + 255) / 256);
+		tc_convert_rows<<<blocks, 256, 0, st>>>(ix->d_rows, ix->pitch, ix->dim, 0, uint32_t(ix->size),
+												static_cast<__nv_bfloat16*>(ix->d_shadow), pitchBf, ix->d_vnorm);
+		RX_CUDA(cudaGetLastError());
+		RX_CUDA(cudaStreamSynchronize(st));
+		ix->shadow_version = ix->version;
+		g_stats.launches += 1;
+	}
+	return 0;
+}
+
+int scanTopKExact(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, const float* d_queries, uint32_t nq, uint32_t k1, int mode,
+				  float bound, float* d_out_dist, uint32_t* d_out_idx, uint64_t* d_out_label, uint32_t* d_out_count);
+
+// Large batches: approximate bf16 tensor-core scores with a certified error bound select the candidates, the exact fp32 routine
+// re-ranks them.  Output = the same top-k1 under (dist, internal index) as scanTopKExact, bit for bit.
+int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, const float* d_queries, uint32_t nq, uint32_t k1,
+					   float* d_out_dist, uint32_t* d_out_idx, uint64_t* d_out_label, uint32_t* d_out_count) {
+	if (int rc = ensureShadow(ix, st)) {
+		return rc;
+	}
+	const uint32_t pitchBf = ix->pitch_bf, kchunks = pitchBf / kTcChunkK;
+	const uint32_t nqb = tcQueryBlock(nq, kchunks);
+	const uint32_t nblocks = (nq + nqb - 1) / nqb;
+	const uint32_t nqPad = nblocks * nqb;
+	RX_CUDA(ws.d_qbf.ensure(size_t(nqPad) * pitchBf));
+	RX_CUDA(ws.d_qnorm.ensure(nqPad));
+	RX_CUDA(ws.d_tau.ensure(nqPad));
+	RX_CUDA(ws.d_cand_count.ensure(nqPad));
+	RX_CUDA(ws.d_cand_rows.ensure(size_t(nqPad) * kTcCandCap));
+	RX_CUDA(ws.h_cand_count.ensure(nqPad));
+	RX_CUDA(ws.d_lists.ensure(size_t(nq) * k1));
+	tc_prepare_queries<<<(nqPad * 32 + 255) / 256, 256, 0, st>>>(d_queries, nq, nqPad, ix->dim, pitchBf,
+																 reinterpret_cast<__nv_bfloat16*>(ws.d_qbf.p), ws.d_qnorm.p);
+	tc_init_tau<<<nq, 256, 0, st>>>(ix->d_rows, ix->pitch, ix->dim, ix->metric == RXGPU_COS ? ix->d_norms : nullptr,
+									uint32_t(std::min<uint64_t>(ix->size, 1024)), d_queries, k1, ix->metric, ws.d_tau.p);
+	RX_CUDA(cudaMemsetAsync(ws.d_cand_count.p, 0, size_t(nqPad) * 4, st));
+	RX_CUDA(cudaGetLastError());
+	g_stats.launches += 2;
+	CUtensorMap mapRows, mapQ;
+	if (int rc = makeBf16Map(&mapRows, ix->d_shadow, pitchBf, std::max<uint64_t>(ix->capacity, 1), uint64_t(pitchBf) * 2, kTcTileRows)) {
+		return rc;
+	}
+	if (int rc = makeBf16Map(&mapQ, ws.d_qbf.p, pitchBf, nqPad, uint64_t(pitchBf) * 2, nqb)) {
+		return rc;
+	}
+	const size_t smem = tc_smem_bytes(nqb, kchunks);
+	RX_CUDA(cudaFuncSetAttribute(knn_tc_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+	const uint32_t ntiles = uint32_t((ix->size + kTcTileRows - 1) / kTcTileRows);
+	const unsigned grid = std::min<unsigned>(unsigned(ix->sm_count), ntiles);
+	for (uint32_t b = 0; b < nblocks; ++b) {
+		TcArgs a{};
+		a.vnorm = ix->d_vnorm;
+		a.vinv = ix->metric == RXGPU_COS ? ix->d_norms : nullptr;
+		a.qnorm = ws.d_qnorm.p;
+		a.tau = ws.d_tau.p;
+		a.cand_rows = ws.d_cand_rows.p;
+		a.cand_count = ws.d_cand_count.p;
+		a.cand_cap = kTcCandCap;
+		a.n = uint32_t(ix->size);
+		a.kchunks = kchunks;
+		a.nq_block = nqb;
+		a.q0 = b * nqb;
+		a.nq_valid = std::min(nqb, nq - a.q0);
+		a.k1 = k1;
+		a.metric = ix->metric;
+		cudaEvent_t e0 = nullptr, e1 = nullptr;
+		if (g_profile.load(std::memory_order_relaxed)) {
+			RX_CUDA(cudaEventCreate(&e0));
+			RX_CUDA(cudaEventCreate(&e1));
+			RX_CUDA(cudaEventRecord(e0, st));
+		}
+		knn_tc_filter<<<grid, kTcThreads, smem, st>>>(mapRows, mapQ, a);
+		RX_CUDA(cudaGetLastError());
+		if (e0) {
+			RX_CUDA(cudaEventRecord(e1, st));
+			g_prof_events.emplace_back(e0, e1);
+		}
+		g_stats.launches += 1;
+		g_stats.passes += 1;
+	}
+	// exact re-rank of the candidates with the arithmetic of knn_scan_warp, then decode + labels
+	const size_t rsmem = size_t((ix->dim + 127) / 128) * 512 + size_t(kScanWarps) * (k1 + kCandBuf) * 8;
+	const float* norms = ix->metric == RXGPU_COS ? ix->d_norms : nullptr;
+	if (ix->metric == RXGPU_L2) {
+		RX_CUDA(cudaFuncSetAttribute(knn_rerank<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rsmem)));
+		knn_rerank<true><<<nq, kScanThreads, rsmem, st>>>(ix->d_rows, ix->pitch, ix->dim, norms, d_queries, ws.d_cand_rows.p,
+														   ws.d_cand_count.p, kTcCandCap, k1, ws.d_lists.p);
+	} else {
+		RX_CUDA(cudaFuncSetAttribute(knn_rerank<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rsmem)));
+		knn_rerank<false><<<nq, kScanThreads, rsmem, st>>>(ix->d_rows, ix->pitch, ix->dim, norms, d_queries, ws.d_cand_rows.p,
+															ws.d_cand_count.p, kTcCandCap, k1, ws.d_lists.p);
+	}
+	MergeArgs m{};
+	m.lists = ws.d_lists.p;
+	m.labels = ix->d_labels;
+	m.out_dist = d_out_dist;
+	m.out_idx = d_out_idx;
+	m.out_label = d_out_label;
+	m.out_count = d_out_count;
+	m.nlists = 1;
+	m.qt = nq;
+	m.k1 = k1;
+	m.q_offset = 0;
+	m.mode = kModeTopK;
+	knn_merge_lists<<<nq, 256, 0, st>>>(m);
+	RX_CUDA(cudaGetLastError());
+	g_stats.launches += 2;
+	// a query whose candidate list overflowed (pathological data, e.g. masses of near-duplicates) is answered by the exact scan
+	RX_CUDA(cudaMemcpyAsync(ws.h_cand_count.p, ws.d_cand_count.p, size_t(nq) * 4, cudaMemcpyDeviceToHost, st));
+	RX_CUDA(cudaStreamSynchronize(st));
+	uint64_t cands = 0;
+	for (uint32_t q = 0; q < nq; ++q) {
+		cands += std::min<unsigned>(ws.h_cand_count.p[q], kTcCandCap);
+		if (ws.h_cand_count.p[q] > kTcCandCap) {
+			g_stats.tc_fallbacks += 1;
+			if (int rc = scanTopKExact(ix, ws, st, d_queries + size_t(q) * ix->dim, 1, k1, kModeTopK, 0.f, d_out_dist + size_t(q) * k1,
+									   d_out_idx + size_t(q) * k1, d_out_label ? d_out_label + size_t(q) * k1 : nullptr, d_out_count + q)) {
+				return rc;
+			}
+		}
+	}
+	g_stats.query_tile = nqb;
+	g_stats.tc_used = 1;
+	g_stats.tc_candidates = cands;
+	g_stats.algorithmic_bytes += uint64_t(nblocks) * (uint64_t(ix->size) * pitchBf * 2 + uint64_t(ix->size) * 4 + uint64_t(nqb) * pitchBf * 2) +
+								 cands * (uint64_t(ix->dim) * 4 + 4);
+	return 0;
+}
+
+int scanTopK(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, const float* d_queries, uint32_t nq, uint32_t k1, int mode, float bound,
+			 float* d_out_dist, uint32_t* d_out_idx, uint64_t* d_out_label, uint32_t* d_out_count) {
+	if (tcEligible(ix, nq, k1, mode)) {
+		return scanTopKTensorCore(ix, ws, st, d_queries, nq, k1, d_out_dist, d_out_idx, d_out_label, d_out_count);
+	}
+	return scanTopKExact(ix, ws, st, d_queries, nq, k1, mode, bound, d_out_dist, d_out_idx, d_out_label, d_out_count);
 }
 
 int normsForRange(rxgpu_index* ix, uint64_t begin, uint64_t end) {
@@ -272,6 +477,7 @@ int rxgpu_index_clone(rxgpu_index** out, const rxgpu_index* src, uint64_t new_ca
 	}
 	ix->size = src->size;
 	ix->qt_override = src->qt_override;
+	ix->tc_mode = src->tc_mode;
 	RX_CUDA(cudaMemcpyAsync(ix->d_rows, src->d_rows, size_t(src->size) * src->pitch * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
 	RX_CUDA(cudaMemcpyAsync(ix->d_labels, src->d_labels, size_t(src->size) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ix->stream));
 	if (src->d_norms) {
@@ -318,6 +524,12 @@ int rxgpu_index_resize(rxgpu_index* ix, uint64_t new_capacity) {
 	ix->d_labels = labels;
 	ix->d_norms = norms;
 	ix->capacity = new_capacity;
+	if (ix->d_shadow) {  // rebuilt lazily at the new capacity
+		cudaFree(ix->d_shadow);
+		cudaFree(ix->d_vnorm);
+		ix->d_shadow = nullptr;
+		ix->d_vnorm = nullptr;
+	}
 	try {
 		if (ix->flags & RXGPU_FLAG_HOST_MIRROR) {
 			ix->h_rows.resize(size_t(new_capacity) * ix->dim);
@@ -501,6 +713,13 @@ int rxgpu_set_query_tile(rxgpu_index* ix, uint32_t qt) {
 		return fail(RXGPU_ERR_PARAMS, "rxgpu: null handle");
 	}
 	ix->qt_override = qt;
+	return 0;
+}
+int rxgpu_set_tensor_core_filter(rxgpu_index* ix, int mode) {
+	if (!ix || mode < 0 || mode > 2) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: mode must be 0 (auto), 1 (on) or 2 (off)");
+	}
+	ix->tc_mode = uint32_t(mode);
 	return 0;
 }
 int rxgpu_set_profile(int on) {

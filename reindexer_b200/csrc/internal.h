@@ -107,6 +107,11 @@ struct Workspace {
 	DevBuf<uint32_t> d_out_count;
 	DevBuf<uint64_t> d_range;
 	DevBuf<unsigned long long> d_range_count;
+	DevBuf<uint16_t> d_qbf;  // bf16 query block for the tensor-core filter
+	DevBuf<float> d_qnorm;
+	DevBuf<unsigned int> d_tau, d_cand_count;
+	DevBuf<uint32_t> d_cand_rows;
+	PinBuf<unsigned int> h_cand_count;
 	PinBuf<float> h_queries;
 	PinBuf<float> h_out_dist;
 	PinBuf<uint32_t> h_out_idx;
@@ -152,6 +157,14 @@ struct rxgpu_index {
 	mutable std::vector<std::unique_ptr<rxgpu::Workspace>> ws_free;
 	rxgpu_hnsw_device* hnsw = nullptr;  // graph attached by rxgpu_hnsw_import (hnsw.cu)
 
+	// tensor-core filter state, built lazily by the first large-batch search: bf16 shadow of the rows + row norms
+	mutable std::mutex tc_mtx;
+	mutable void* d_shadow = nullptr;  // __nv_bfloat16 [capacity][pitch_bf]
+	mutable float* d_vnorm = nullptr;  // [capacity] ||row||_2
+	mutable uint32_t pitch_bf = 0;
+	mutable uint64_t shadow_version = ~0ull;
+	uint32_t tc_mode = 0;  // 0 auto, 1 force on, 2 off
+
 	~rxgpu_index() {
 		cudaSetDevice(device);
 		ws_free.clear();
@@ -166,6 +179,12 @@ struct rxgpu_index {
 		}
 		if (d_norms) {
 			cudaFree(d_norms);
+		}
+		if (d_shadow) {
+			cudaFree(d_shadow);
+		}
+		if (d_vnorm) {
+			cudaFree(d_vnorm);
 		}
 		if (stream) {
 			cudaStreamDestroy(stream);

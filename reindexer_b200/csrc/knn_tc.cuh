@@ -1,0 +1,541 @@
+// Tensor-core candidate filter for large query batches (sm_100a: TMA + tcgen05.mma + TMEM), exact results.
+//
+// knn_scan_warp is HBM-bound only while <= ~16 queries share a pass; a batch of 1024 queries is FMA-bound there.  This kernel
+// computes APPROXIMATE scores for a block of NQ queries against every row with bf16 operands on the 5th-gen tensor cores and
+// keeps, per query, only the rows that can still be among the k best under a CERTIFIED error bound; the survivors (a few hundred
+// per query) are then re-ranked with the exact fp32 routine of knn_scan_warp, so the final result is identical to the exact scan.
+//
+//   error bound   |q~.v~ - q.v| <= c * ||q|| * ||v||,  c = 2^-8 + 2^-18 (two bf16 roundings, unit roundoff 2^-9 each)
+//                                                        + 768 * 2^-23 (fp32 accumulation in the MMA) , used with 5% slack
+//   lower bound   lb = d~ - e, upper bound ub = d~ + e in map space (smaller is better)
+//   threshold     tau_q = k1-th smallest ub seen so far (any CTA) => a valid upper bound of the final k1-th best TRUE distance;
+//                 a row is a candidate iff lb <= tau_q.  tau starts from an exact scan of the first rows and only decreases.
+//
+// Roles (192 threads, 1 CTA per SM, persistent over 128-row tiles):
+//   warp 0    TMA producer: bf16 shadow rows, 128 x 64 tiles (16 KB, SWIZZLE_128B) through a 4-stage mbarrier ring
+//   warp 1    allocates TMEM (512 columns), issues tcgen05.mma (M=128 rows, N=NQ queries, K=16) from shared-memory descriptors;
+//             the query block (NQ x dim bf16) is loaded once by TMA and stays resident in shared memory
+//   warps 2-5 epilogue: tcgen05.ld the 128 x NQ fp32 accumulators (double buffered in TMEM so the next tile's MMAs overlap),
+//             apply the metric, test against tau, append candidates to per-query lists in HBM, tighten tau
+// Bound: HBM (bf16 shadow: n*dim*2 bytes per pass of NQ queries); MMA time per tile is ~4x below the tile's HBM time.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "knn_scan.cuh"
+
+namespace rxgpu {
+
+constexpr int kTcThreads = 192;
+constexpr int kTcTileRows = 128;     // UMMA M
+constexpr int kTcChunkK = 64;        // bf16 elements per 128-byte swizzle row
+constexpr int kTcStages = 4;
+constexpr int kTcStageBytes = kTcTileRows * kTcChunkK * 2;  // 16 KB
+constexpr uint32_t kTcMaxK1 = 16;
+constexpr uint32_t kTcQueueCap = 512;
+constexpr float kTcErrCoef = 0.0042f;  // see header comment
+
+struct TcArgs {
+	const float* vnorm;        // [n] ||row||_2 (fp32)
+	const float* vinv;         // [n] 1/||row|| (Cosine) or nullptr
+	const float* qnorm;        // [nq_total] ||q||_2
+	unsigned int* tau;         // [nq_total] ordered-uint of the current threshold (map space), shared by all CTAs
+	uint32_t* cand_rows;       // [nq_total][cand_cap]
+	unsigned int* cand_count;  // [nq_total]
+	uint32_t cand_cap;
+	uint32_t n;                // rows
+	uint32_t kchunks;          // padded dim / 64
+	uint32_t nq_block;         // UMMA N (multiple of 32, <= 256): queries resident in this launch
+	uint32_t nq_valid;         // real queries in this block
+	uint32_t q0;               // first query of the block
+	uint32_t k1;
+	int metric;                // kL2 / kIP / kCos
+};
+
+__host__ __device__ inline size_t tc_smem_bytes(uint32_t nq_block, uint32_t kchunks) {
+	return 1024 /*align slack*/ + size_t(nq_block) * kchunks * 128 + size_t(kTcStages) * kTcStageBytes + 256 /*barriers*/ +
+		   size_t(nq_block) * (4 + 4 + kTcMaxK1 * 4) + size_t(kTcQueueCap) * 8 + 64;
+}
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_%=:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra DONE_%=;\n"
+		"bra WAIT_%=;\n"
+		"DONE_%=:\n"
+		"}\n" ::"r"(smem_u32(bar)),
+		"r"(parity)
+		: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int32_t x, int32_t y) {
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+					 smem_u32(dst)),
+				 "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+				 : "memory");
+}
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B: 8-row groups are 1024 B apart (SBO), one swizzle atom along K (LBO unused)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+	uint64_t d = 0;
+	d |= uint64_t((smem_addr & 0x3FFFFu) >> 4);  // start address, bits [0,14)
+	d |= uint64_t(0) << 16;                      // leading byte offset (unused for swizzled K-major)
+	d |= uint64_t(1024 >> 4) << 32;              // stride byte offset, bits [32,46)
+	d |= uint64_t(1) << 46;                      // descriptor version (sm_100)
+	d |= uint64_t(2) << 61;                      // layout type: SWIZZLE_128B
+	return d;
+}
+// instruction descriptor, kind::f16: D = f32, A = B = bf16, both K-major, dense
+__device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
+	return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"setp.ne.b32 p, %4, 0;\n"
+		"tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+		"}\n" ::"r"(tmem_d),
+		"l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+		: "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+	asm volatile(
+		"tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+		"{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+		: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+		  "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+		  "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+		  "=r"(r[31])
+		: "r"(taddr));
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- the filter kernel -----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTcThreads, 1)
+	knn_tc_filter(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__ CUtensorMap map_queries, const TcArgs a) {
+	extern __shared__ unsigned char smem_raw[];
+	unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+	const uint32_t qchunk_bytes = a.nq_block * 128;                   // one K-chunk of the query block: nq_block rows x 128 B
+	unsigned char* s_q = base;                                        // [kchunks][nq_block][128 B], swizzled by TMA
+	unsigned char* s_rows = s_q + size_t(a.kchunks) * qchunk_bytes;   // [stages][128][128 B]   (1024-aligned: nq_block % 8 == 0)
+	uint64_t* bars = reinterpret_cast<uint64_t*>(s_rows + size_t(kTcStages) * kTcStageBytes);
+	uint64_t* full_bar = bars;                   // [stages] TMA -> MMA
+	uint64_t* empty_bar = bars + kTcStages;      // [stages] MMA -> TMA
+	uint64_t* q_bar = bars + 2 * kTcStages;      // queries resident
+	uint64_t* acc_full = q_bar + 1;              // [2] MMA -> epilogue
+	uint64_t* acc_empty = acc_full + 2;          // [2] epilogue -> MMA
+	uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + 2);
+	float* s_thr = reinterpret_cast<float*>(bars + 32);                // [nq_block] current tau (map space)
+	float* s_qe = s_thr + a.nq_block;                                  // [nq_block] c * ||q||
+	float* s_ub = s_qe + a.nq_block;                                   // [nq_block][kTcMaxK1] ascending upper bounds seen by this CTA
+	uint2* s_queue = reinterpret_cast<uint2*>(s_ub + size_t(a.nq_block) * kTcMaxK1);  // (query, ub bits)
+	uint32_t* s_qcount = reinterpret_cast<uint32_t*>(s_queue + kTcQueueCap);
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t ntiles = (a.n + kTcTileRows - 1) / kTcTileRows;
+
+	if (threadIdx.x == 0) {
+		for (int s = 0; s < kTcStages; ++s) {
+			mbar_init(&full_bar[s], 1);
+			mbar_init(&empty_bar[s], 1);
+		}
+		mbar_init(q_bar, 1);
+		for (int s = 0; s < 2; ++s) {
+			mbar_init(&acc_full[s], 1);
+			mbar_init(&acc_empty[s], 4);  // one arrive per epilogue warp
+		}
+		*s_qcount = 0;
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	for (uint32_t i = threadIdx.x; i < a.nq_block; i += blockDim.x) {
+		const bool valid = i < a.nq_valid;
+		s_thr[i] = valid ? ord_float(a.tau[a.q0 + i]) : -INFINITY;
+		s_qe[i] = valid ? kTcErrCoef * a.qnorm[a.q0 + i] : 0.f;
+		for (uint32_t j = 0; j < kTcMaxK1; ++j) {
+			s_ub[i * kTcMaxK1 + j] = INFINITY;
+		}
+	}
+	if (warp == 1) {  // TMEM: 512 columns = 2 accumulator buffers of up to 256 fp32 columns
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(s_tmem)) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	__syncthreads();
+	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+	const uint32_t tmem_base = *s_tmem;
+
+	if (warp == 0) {
+		// ===== TMA producer =====
+		if (lane == 0) {
+			mbar_expect_tx(q_bar, a.kchunks * qchunk_bytes);
+			for (uint32_t kc = 0; kc < a.kchunks; ++kc) {
+				tma_load_2d(s_q + size_t(kc) * qchunk_bytes, &map_queries, q_bar, int32_t(kc * kTcChunkK), int32_t(a.q0));
+			}
+			uint32_t stage = 0, phase = 0;
+			for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+				for (uint32_t kc = 0; kc < a.kchunks; ++kc) {
+					mbar_wait(&empty_bar[stage], phase ^ 1);
+					mbar_expect_tx(&full_bar[stage], kTcStageBytes);
+					tma_load_2d(s_rows + size_t(stage) * kTcStageBytes, &map_rows, &full_bar[stage], int32_t(kc * kTcChunkK),
+								int32_t(t * kTcTileRows));
+					if (++stage == kTcStages) {
+						stage = 0;
+						phase ^= 1;
+					}
+				}
+			}
+		}
+	} else if (warp == 1) {
+		// ===== MMA issuer =====
+		if (lane == 0) {
+			const uint32_t idesc = umma_idesc_bf16(kTcTileRows, a.nq_block);
+			mbar_wait(q_bar, 0);
+			uint32_t stage = 0, phase = 0, it = 0;
+			for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+				const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+				mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+				const uint32_t tmem_d = tmem_base + acc * 256;
+				for (uint32_t kc = 0; kc < a.kchunks; ++kc) {
+					mbar_wait(&full_bar[stage], phase);
+					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+					const uint32_t a_addr = smem_u32(s_rows + size_t(stage) * kTcStageBytes);
+					const uint32_t b_addr = smem_u32(s_q + size_t(kc) * qchunk_bytes);
+#pragma unroll
+					for (uint32_t k = 0; k < kTcChunkK / 16; ++k) {  // UMMA_K = 16 bf16 = 32 bytes inside the 128-byte swizzle row
+						umma_bf16(tmem_d, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (kc | k) != 0);
+					}
+					umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+					if (++stage == kTcStages) {
+						stage = 0;
+						phase ^= 1;
+					}
+				}
+				umma_commit(&acc_full[acc]);  // accumulator complete -> epilogue
+			}
+		}
+	} else {
+		// ===== epilogue warps 2..5: TMEM lane quadrant = warp % 4 =====
+		const uint32_t quad = warp & 3;
+		const uint32_t row_in_tile = quad * 32 + lane;
+		uint32_t it = 0;
+		for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+			const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+			const uint32_t row = t * kTcTileRows + row_in_tile;
+			const bool row_ok = row < a.n;
+			const float vn = row_ok ? a.vnorm[row] : 0.f;
+			const float vinv = (row_ok && a.vinv) ? a.vinv[row] : 1.f;
+			// refresh tau from the other CTAs (queries own threads 0..nq_block-1 of the epilogue group)
+			for (uint32_t i = threadIdx.x - 64; i < a.nq_valid; i += 128) {
+				s_thr[i] = fminf(s_thr[i], ord_float(a.tau[a.q0 + i]));
+			}
+			asm volatile("bar.sync 1, 128;" ::: "memory");
+			mbar_wait(&acc_full[acc], acc_phase);
+			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+			for (uint32_t c0 = 0; c0 < a.nq_block; c0 += 32) {
+				uint32_t v[32];
+				tmem_ld32(tmem_base + acc * 256 + c0 + ((quad * 32) << 16), v);
+				if (row_ok) {
+#pragma unroll
+					for (int j = 0; j < 32; ++j) {
+						const uint32_t q = c0 + j;
+						if (q >= a.nq_valid) {
+							break;
+						}
+						const float s = __uint_as_float(v[j]);
+						float d, e;
+						if (a.metric == kL2) {  // ||q||^2 + ||v||^2 - 2 q.v ; s_qe = c*||q||
+							const float qn = s_qe[q] * (1.f / kTcErrCoef);
+							d = fmaf(-2.f, s, fmaf(qn, qn, vn * vn));
+							e = 2.f * s_qe[q] * vn + 1e-5f * (qn * qn + vn * vn);
+						} else if (a.metric == kCos) {
+							d = -s * vinv;
+							e = s_qe[q] * vn * vinv;
+						} else {
+							d = -s;
+							e = s_qe[q] * vn;
+						}
+						if (d - e <= s_thr[q]) {
+							const unsigned pos = atomicAdd(&a.cand_count[a.q0 + q], 1u);
+							if (pos < a.cand_cap) {
+								a.cand_rows[size_t(a.q0 + q) * a.cand_cap + pos] = row;
+							}
+							const float ub = d + e;
+							if (ub < s_ub[q * kTcMaxK1 + a.k1 - 1]) {
+								const uint32_t slot = atomicAdd(s_qcount, 1u);
+								if (slot < kTcQueueCap) {
+									s_queue[slot] = make_uint2(q, __float_as_uint(ub));
+								}
+							}
+						}
+					}
+				}
+			}
+			// accumulator drained: hand the TMEM buffer back to the MMA warp
+			asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+			__syncwarp();
+			if (lane == 0) {
+				mbar_arrive(&acc_empty[acc]);
+			}
+			asm volatile("bar.sync 1, 128;" ::: "memory");
+			// tighten tau: one thread folds the queued upper bounds into the per-query sorted lists (rare after warm-up)
+			if (threadIdx.x == 64) {
+				const uint32_t cnt = min(*s_qcount, kTcQueueCap);
+				for (uint32_t i = 0; i < cnt; ++i) {
+					const uint32_t q = s_queue[i].x;
+					const float ub = __uint_as_float(s_queue[i].y);
+					float* list = s_ub + q * kTcMaxK1;
+					if (ub < list[a.k1 - 1]) {
+						int p = int(a.k1) - 1;
+						while (p > 0 && list[p - 1] > ub) {
+							list[p] = list[p - 1];
+							--p;
+						}
+						list[p] = ub;
+						const float kth = list[a.k1 - 1];
+						if (kth < s_thr[q]) {
+							s_thr[q] = kth;
+							atomicMin(&a.tau[a.q0 + q], float_ord(kth));
+						}
+					}
+				}
+				*s_qcount = 0;
+			}
+			asm volatile("bar.sync 1, 128;" ::: "memory");
+		}
+	}
+	__syncthreads();
+	if (warp == 1) {
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+	}
+}
+
+// ---- exact re-rank of the candidates ----------------------------------------------------------------------------------------------
+// One CTA per query: its 8 warps stream the candidate rows of that query (gathered 128-bit coalesced loads), compute the exact fp32
+// distance with the SAME per-row arithmetic sequence as knn_scan_warp (so distances are bit-identical to the exact scan), keep the
+// best k1 keys per warp, merge in the CTA and write one ascending list [k1] per query.
+template <bool kIsL2>
+__global__ void __launch_bounds__(kScanThreads) knn_rerank(const float* rows, uint32_t pitch, uint32_t dim, const float* norm_coefs,
+															const float* queries, const uint32_t* cand_rows, const unsigned int* cand_count,
+															uint32_t cand_cap, uint32_t k1, uint64_t* lists /* [nq][k1] */) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t q = blockIdx.x;
+	const uint32_t nch = (dim + 127u) / 128u, dp4 = nch * 32u, pitch4 = pitch >> 2;
+	const uint32_t m = k1 + kCandBuf;
+	float4* sq4 = reinterpret_cast<float4*>(smem_raw);
+	uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw + size_t(dp4) * 16);  // [8 warps][m]
+	{
+		float* sq = reinterpret_cast<float*>(sq4);
+		for (uint32_t i = threadIdx.x; i < dp4 * 4; i += blockDim.x) {
+			sq[i] = i < dim ? queries[size_t(q) * dim + i] : 0.f;
+		}
+		for (uint32_t i = threadIdx.x; i < kScanWarps * m; i += blockDim.x) {
+			skeys[i] = kKeyNone;
+		}
+	}
+	__syncthreads();
+	uint64_t* wkeys = skeys + size_t(warp) * m;
+	uint64_t thr = kKeyNone;
+	uint32_t cnt = 0;
+	const uint32_t ncand = min(cand_count[q], cand_cap);
+	const float4* rows4 = reinterpret_cast<const float4*>(rows);
+	const uint32_t* my = cand_rows + size_t(q) * cand_cap;
+	for (uint32_t i = warp; i < ncand; i += kScanWarps) {
+		const uint32_t row = my[i];
+		float s = 0.f;
+		for (uint32_t c = 0; c < nch; ++c) {
+			const uint32_t f4 = c * 32u + lane;
+			const float4 db = f4 < pitch4 ? ldg_stream(rows4 + size_t(row) * pitch4 + f4) : make_float4(0.f, 0.f, 0.f, 0.f);
+			const float4 qv = sq4[f4];
+			if constexpr (kIsL2) {
+				float d;
+				d = qv.x - db.x;
+				s = fmaf(d, d, s);
+				d = qv.y - db.y;
+				s = fmaf(d, d, s);
+				d = qv.z - db.z;
+				s = fmaf(d, d, s);
+				d = qv.w - db.w;
+				s = fmaf(d, d, s);
+			} else {
+				s = fmaf(qv.x, db.x, s);
+				s = fmaf(qv.y, db.y, s);
+				s = fmaf(qv.z, db.z, s);
+				s = fmaf(qv.w, db.w, s);
+			}
+		}
+#pragma unroll
+		for (int off = 16; off > 0; off >>= 1) {
+			s += __shfl_xor_sync(0xffffffffu, s, off);
+		}
+		float dist = kIsL2 ? s : -s;
+		if (!kIsL2 && norm_coefs != nullptr) {
+			dist *= norm_coefs[row];
+		}
+		const uint64_t key = make_key(dist, row);
+		if (key < thr) {  // warp-uniform
+			if (lane == 0) {
+				wkeys[k1 + cnt] = key;
+			}
+			++cnt;
+			__syncwarp();
+			if (cnt == kCandBuf) {
+				warp_select(wkeys, k1 + cnt, k1, lane);
+				thr = wkeys[k1 - 1];
+				cnt = 0;
+			}
+		}
+	}
+	if (cnt) {
+		warp_select(wkeys, k1 + cnt, k1, lane);
+	}
+	__syncthreads();
+	if (warp == 0) {  // CTA merge: strictly increasing selection over the 8 warp lists (keys are unique)
+		uint64_t last = 0;
+		bool first = true;
+		for (uint32_t r = 0; r < k1; ++r) {
+			uint64_t best = kKeyNone;
+			for (uint32_t i = lane; i < kScanWarps * k1; i += 32) {
+				const uint32_t w = i / k1, j = i - w * k1;
+				const uint64_t kx = skeys[size_t(w) * m + j];
+				if ((first || kx > last) && kx < best) {
+					best = kx;
+				}
+			}
+#pragma unroll
+			for (int off = 16; off > 0; off >>= 1) {
+				const uint64_t ok = __shfl_xor_sync(0xffffffffu, best, off);
+				best = ok < best ? ok : best;
+			}
+			if (lane == 0) {
+				lists[size_t(q) * k1 + r] = best;
+			}
+			last = best;
+			first = false;
+		}
+	}
+}
+
+// ---- helpers: bf16 shadow, norms, query preparation, threshold init ---------------------------------------------------------------
+// rows fp32 [n][pitch] -> shadow bf16 [n][pitch_bf] (zero padded to a multiple of 64) + ||row||_2
+__global__ void tc_convert_rows(const float* rows, uint32_t pitch, uint32_t dim, uint32_t row_begin, uint32_t row_end, __nv_bfloat16* shadow,
+								uint32_t pitch_bf, float* vnorm) {
+	const uint32_t row = row_begin + (blockIdx.x * blockDim.x + threadIdx.x) / 32;
+	const int lane = threadIdx.x & 31;
+	if (row >= row_end) {
+		return;
+	}
+	const float* p = rows + size_t(row) * pitch;
+	__nv_bfloat16* o = shadow + size_t(row) * pitch_bf;
+	float s = 0.f;
+	for (uint32_t c = lane; c < pitch_bf; c += 32) {
+		const float v = c < dim ? p[c] : 0.f;
+		s = fmaf(v, v, s);
+		o[c] = __float2bfloat16_rn(v);
+	}
+	for (int off = 16; off > 0; off >>= 1) {
+		s += __shfl_xor_sync(0xffffffffu, s, off);
+	}
+	if (lane == 0 && vnorm) {
+		vnorm[row] = sqrtf(s);
+	}
+}
+
+// tau_init[q] = upper bound of the k1-th best distance among the first `rows` rows (fp32 dot products, one block per query).
+// Any upper bound is valid; a small relative slack covers the difference to the arithmetic order of knn_scan_warp.
+__global__ void __launch_bounds__(256) tc_init_tau(const float* rows, uint32_t pitch, uint32_t dim, const float* norm_coefs, uint32_t nrows,
+												   const float* queries, uint32_t k1, int metric, unsigned int* tau) {
+	__shared__ float s_d[1024];
+	const uint32_t q = blockIdx.x;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const float* qv = queries + size_t(q) * dim;
+	for (uint32_t r = warp; r < 1024; r += 8) {
+		float d = INFINITY;
+		if (r < nrows) {
+			const float* p = rows + size_t(r) * pitch;
+			float s = 0.f;
+			for (uint32_t c = lane; c < dim; c += 32) {
+				if (metric == kL2) {
+					const float x = qv[c] - p[c];
+					s = fmaf(x, x, s);
+				} else {
+					s = fmaf(qv[c], p[c], s);
+				}
+			}
+			for (int off = 16; off > 0; off >>= 1) {
+				s += __shfl_xor_sync(0xffffffffu, s, off);
+			}
+			d = metric == kL2 ? s : -s;
+			if (metric == kCos) {
+				d *= norm_coefs[r];
+			}
+			d += 1e-4f * fabsf(d) + 1e-6f;
+		}
+		if (lane == 0) {
+			s_d[r] = d;
+		}
+	}
+	__syncthreads();
+	// bitonic sort of 1024 floats, 256 threads
+	for (uint32_t size = 2; size <= 1024; size <<= 1) {
+		for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+			for (uint32_t i = threadIdx.x; i < 512; i += 256) {
+				const uint32_t lo = 2 * i - (i & (stride - 1));
+				const uint32_t hi = lo + stride;
+				const bool up = (lo & size) == 0;
+				const float x = s_d[lo], y = s_d[hi];
+				if ((x > y) == up) {
+					s_d[lo] = y;
+					s_d[hi] = x;
+				}
+			}
+			__syncthreads();
+		}
+	}
+	if (threadIdx.x == 0) {
+		const uint32_t kth = min(k1, nrows) - 1;
+		tau[q] = float_ord(nrows >= k1 ? s_d[kth] : INFINITY);
+	}
+}
+
+// queries fp32 [nq][dim] -> bf16 [nq_pad][pitch_bf] (zero padded) + ||q||
+__global__ void tc_prepare_queries(const float* queries, uint32_t nq, uint32_t nq_pad, uint32_t dim, uint32_t pitch_bf, __nv_bfloat16* out,
+								   float* qnorm) {
+	const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) / 32;
+	const int lane = threadIdx.x & 31;
+	if (q >= nq_pad) {
+		return;
+	}
+	float s = 0.f;
+	for (uint32_t c = lane; c < pitch_bf; c += 32) {
+		const float v = (q < nq && c < dim) ? queries[size_t(q) * dim + c] : 0.f;
+		s = fmaf(v, v, s);
+		out[size_t(q) * pitch_bf + c] = __float2bfloat16_rn(v);
+	}
+	for (int off = 16; off > 0; off >>= 1) {
+		s += __shfl_xor_sync(0xffffffffu, s, off);
+	}
+	if (lane == 0 && q < nq) {
+		qnorm[q] = sqrtf(s);
+	}
+}
+
+}  // namespace rxgpu
