@@ -239,7 +239,7 @@ int ensureShadow(const rxgpu_index* ix, cudaStream_t st) {
 	std::lock_guard<std::mutex> lck(ix->tc_mtx);
 	const uint32_t pitchBf = (ix->dim + kTcChunkK - 1) / kTcChunkK * kTcChunkK;
 	if (!ix->d_shadow) {
-		const size_t cap = ix->capacity ? ix->capacity : 1;
+		const size_t cap = (size_t(ix->capacity ? ix->capacity : 1) + kTcTileRows - 1) / kTcTileRows * kTcTileRows;  // whole tiles
 		RX_CUDA(cudaMalloc(&ix->d_shadow, cap * pitchBf * 2));
 		RX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ix->d_vnorm), cap * sizeof(float)));
 		ix->pitch_bf = pitchBf;
@@ -248,7 +248,7 @@ int ensureShadow(const rxgpu_index* ix, cudaStream_t st) {
 	if (ix->shadow_version != ix->version) {
 		const unsigned blocks = unsigned((uint64_t(ix->size) * 32 + 255) / 256);
 		tc_convert_rows<<<blocks, 256, 0, st>>>(ix->d_rows, ix->pitch, ix->dim, 0, uint32_t(ix->size),
-												static_cast<__nv_bfloat16*>(ix->d_shadow), pitchBf, ix->d_vnorm);
+												static_cast<__nv_bfloat16*>(ix->d_shadow), pitchBf / kTcChunkK, ix->d_vnorm);
 		RX_CUDA(cudaGetLastError());
 		RX_CUDA(cudaStreamSynchronize(st));
 		ix->shadow_version = ix->version;
@@ -274,6 +274,8 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 	RX_CUDA(ws.d_qbf.ensure(size_t(nqPad) * pitchBf));
 	RX_CUDA(ws.d_qnorm.ensure(nqPad));
 	RX_CUDA(ws.d_tau.ensure(nqPad));
+	RX_CUDA(ws.d_ub_list.ensure(size_t(nqPad) * kTcMaxK1));
+	RX_CUDA(ws.d_ub_lock.ensure(nqPad));
 	RX_CUDA(ws.d_cand_count.ensure(nqPad));
 	RX_CUDA(ws.d_cand_rows.ensure(size_t(nqPad) * kTcCandCap));
 	RX_CUDA(ws.h_cand_count.ensure(nqPad));
@@ -281,12 +283,15 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 	tc_prepare_queries<<<(nqPad * 32 + 255) / 256, 256, 0, st>>>(d_queries, nq, nqPad, ix->dim, pitchBf,
 																 reinterpret_cast<__nv_bfloat16*>(ws.d_qbf.p), ws.d_qnorm.p);
 	tc_init_tau<<<nq, 256, 0, st>>>(ix->d_rows, ix->pitch, ix->dim, ix->metric == RXGPU_COS ? ix->d_norms : nullptr,
-									uint32_t(std::min<uint64_t>(ix->size, 1024)), d_queries, k1, ix->metric, ws.d_tau.p);
+									uint32_t(std::min<uint64_t>(ix->size, 1024)), d_queries, k1, ix->metric, ws.d_tau.p, ws.d_ub_list.p,
+									ws.d_ub_lock.p);
 	RX_CUDA(cudaMemsetAsync(ws.d_cand_count.p, 0, size_t(nqPad) * 4, st));
 	RX_CUDA(cudaGetLastError());
 	g_stats.launches += 2;
 	CUtensorMap mapRows, mapQ;
-	if (int rc = makeBf16Map(&mapRows, ix->d_shadow, pitchBf, std::max<uint64_t>(ix->capacity, 1), uint64_t(pitchBf) * 2, kTcTileRows)) {
+	// tiled shadow: a 2-D view of 64-element lines, one 128-line block per (row tile, K chunk)
+	const uint64_t shadowLines = (uint64_t(std::max<uint64_t>(ix->capacity, 1)) + kTcTileRows - 1) / kTcTileRows * kTcTileRows * kchunks;
+	if (int rc = makeBf16Map(&mapRows, ix->d_shadow, kTcChunkK, shadowLines, uint64_t(kTcChunkK) * 2, kTcTileRows)) {
 		return rc;
 	}
 	if (int rc = makeBf16Map(&mapQ, ws.d_qbf.p, pitchBf, nqPad, uint64_t(pitchBf) * 2, nqb)) {
@@ -302,6 +307,9 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 		a.vinv = ix->metric == RXGPU_COS ? ix->d_norms : nullptr;
 		a.qnorm = ws.d_qnorm.p;
 		a.tau = ws.d_tau.p;
+		a.ub_list = ws.d_ub_list.p;
+		a.ub_lock = ws.d_ub_lock.p;
+		a.init_rows = uint32_t(std::min<uint64_t>(ix->size, 1024));
 		a.cand_rows = ws.d_cand_rows.p;
 		a.cand_count = ws.d_cand_count.p;
 		a.cand_cap = kTcCandCap;

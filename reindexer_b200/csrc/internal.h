@@ -109,7 +109,8 @@ struct Workspace {
 	DevBuf<unsigned long long> d_range_count;
 	DevBuf<uint16_t> d_qbf;  // bf16 query block for the tensor-core filter
 	DevBuf<float> d_qnorm;
-	DevBuf<unsigned int> d_tau, d_cand_count;
+	DevBuf<unsigned int> d_tau, d_cand_count, d_ub_lock;
+	DevBuf<float> d_ub_list;
 	DevBuf<uint32_t> d_cand_rows;
 	PinBuf<unsigned int> h_cand_count;
 	PinBuf<float> h_queries;

@@ -8,11 +8,15 @@
 //   error bound   |q~.v~ - q.v| <= c * ||q|| * ||v||,  c = 2^-8 + 2^-18 (two bf16 roundings, unit roundoff 2^-9 each)
 //                                                        + 768 * 2^-23 (fp32 accumulation in the MMA) , used with 5% slack
 //   lower bound   lb = d~ - e, upper bound ub = d~ + e in map space (smaller is better)
-//   threshold     tau_q = k1-th smallest ub seen so far (any CTA) => a valid upper bound of the final k1-th best TRUE distance;
-//                 a row is a candidate iff lb <= tau_q.  tau starts from an exact scan of the first rows and only decreases.
+//   threshold     tau_q = k1-th smallest ub over all DISTINCT rows seen so far by any CTA (one small list per query in HBM,
+//                 updated under a per-query lock -- only O(k log n) successful inserts per query over a whole pass) => a valid
+//                 upper bound of the final k1-th best TRUE distance; a row is a candidate iff lb <= tau_q.  tau starts from an
+//                 exact scan of the first rows (tc_init_tau) and only decreases.
 //
 // Roles (192 threads, 1 CTA per SM, persistent over 128-row tiles):
-//   warp 0    TMA producer: bf16 shadow rows, 128 x 64 tiles (16 KB, SWIZZLE_128B) through a 4-stage mbarrier ring
+//   warp 0    TMA producer: bf16 shadow rows, 128 x 64 tiles (16 KB, SWIZZLE_128B) through a 4-stage mbarrier ring; the shadow
+//             is stored TILED in HBM -- [tile of 128 rows][K chunk][128 rows][64 bf16] -- so every stage is one contiguous
+//             16 KB read (row-major fp32 stays the source of truth; the shadow is a private, derived structure)
 //   warp 1    allocates TMEM (512 columns), issues tcgen05.mma (M=128 rows, N=NQ queries, K=16) from shared-memory descriptors;
 //             the query block (NQ x dim bf16) is loaded once by TMA and stays resident in shared memory
 //   warps 2-5 epilogue: tcgen05.ld the 128 x NQ fp32 accumulators (double buffered in TMEM so the next tile's MMAs overlap),
@@ -41,6 +45,9 @@ struct TcArgs {
 	const float* vinv;         // [n] 1/||row|| (Cosine) or nullptr
 	const float* qnorm;        // [nq_total] ||q||_2
 	unsigned int* tau;         // [nq_total] ordered-uint of the current threshold (map space), shared by all CTAs
+	float* ub_list;            // [nq_total][kTcMaxK1] the k1 smallest upper bounds over ALL rows seen by any CTA (guarded by ub_lock)
+	unsigned int* ub_lock;     // [nq_total]
+	uint32_t init_rows;        // rows [0, init_rows) are already represented in ub_list by tc_init_tau (never insert them twice)
 	uint32_t* cand_rows;       // [nq_total][cand_cap]
 	unsigned int* cand_count;  // [nq_total]
 	uint32_t cand_cap;
@@ -55,7 +62,7 @@ struct TcArgs {
 
 __host__ __device__ inline size_t tc_smem_bytes(uint32_t nq_block, uint32_t kchunks) {
 	return 1024 /*align slack*/ + size_t(nq_block) * kchunks * 128 + size_t(kTcStages) * kTcStageBytes + 256 /*barriers*/ +
-		   size_t(nq_block) * (4 + 4 + kTcMaxK1 * 4) + size_t(kTcQueueCap) * 8 + 64;
+		   size_t(nq_block) * (4 + 4) + size_t(kTcQueueCap) * 8 + 64;
 }
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------------------
@@ -144,8 +151,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 	uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + 2);
 	float* s_thr = reinterpret_cast<float*>(bars + 32);                // [nq_block] current tau (map space)
 	float* s_qe = s_thr + a.nq_block;                                  // [nq_block] c * ||q||
-	float* s_ub = s_qe + a.nq_block;                                   // [nq_block][kTcMaxK1] ascending upper bounds seen by this CTA
-	uint2* s_queue = reinterpret_cast<uint2*>(s_ub + size_t(a.nq_block) * kTcMaxK1);  // (query, ub bits)
+	uint2* s_queue = reinterpret_cast<uint2*>(s_qe + a.nq_block);     // (query, ub bits)
 	uint32_t* s_qcount = reinterpret_cast<uint32_t*>(s_queue + kTcQueueCap);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -168,9 +174,6 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 		const bool valid = i < a.nq_valid;
 		s_thr[i] = valid ? ord_float(a.tau[a.q0 + i]) : -INFINITY;
 		s_qe[i] = valid ? kTcErrCoef * a.qnorm[a.q0 + i] : 0.f;
-		for (uint32_t j = 0; j < kTcMaxK1; ++j) {
-			s_ub[i * kTcMaxK1 + j] = INFINITY;
-		}
 	}
 	if (warp == 1) {  // TMEM: 512 columns = 2 accumulator buffers of up to 256 fp32 columns
 		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(s_tmem)) : "memory");
@@ -193,8 +196,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 				for (uint32_t kc = 0; kc < a.kchunks; ++kc) {
 					mbar_wait(&empty_bar[stage], phase ^ 1);
 					mbar_expect_tx(&full_bar[stage], kTcStageBytes);
-					tma_load_2d(s_rows + size_t(stage) * kTcStageBytes, &map_rows, &full_bar[stage], int32_t(kc * kTcChunkK),
-								int32_t(t * kTcTileRows));
+					tma_load_2d(s_rows + size_t(stage) * kTcStageBytes, &map_rows, &full_bar[stage], 0,
+								int32_t((t * a.kchunks + kc) * kTcTileRows));
 					if (++stage == kTcStages) {
 						stage = 0;
 						phase ^= 1;
@@ -278,7 +281,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 								a.cand_rows[size_t(a.q0 + q) * a.cand_cap + pos] = row;
 							}
 							const float ub = d + e;
-							if (ub < s_ub[q * kTcMaxK1 + a.k1 - 1]) {
+							if (ub < s_thr[q] && row >= a.init_rows) {
 								const uint32_t slot = atomicAdd(s_qcount, 1u);
 								if (slot < kTcQueueCap) {
 									s_queue[slot] = make_uint2(q, __float_as_uint(ub));
@@ -295,26 +298,40 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 				mbar_arrive(&acc_empty[acc]);
 			}
 			asm volatile("bar.sync 1, 128;" ::: "memory");
-			// tighten tau: one thread folds the queued upper bounds into the per-query sorted lists (rare after warm-up)
+			// tighten tau: one thread folds the queued upper bounds into the per-query global lists (rare after the first tiles)
 			if (threadIdx.x == 64) {
 				const uint32_t cnt = min(*s_qcount, kTcQueueCap);
 				for (uint32_t i = 0; i < cnt; ++i) {
 					const uint32_t q = s_queue[i].x;
 					const float ub = __uint_as_float(s_queue[i].y);
-					float* list = s_ub + q * kTcMaxK1;
-					if (ub < list[a.k1 - 1]) {
-						int p = int(a.k1) - 1;
-						while (p > 0 && list[p - 1] > ub) {
-							list[p] = list[p - 1];
-							--p;
-						}
-						list[p] = ub;
-						const float kth = list[a.k1 - 1];
-						if (kth < s_thr[q]) {
-							s_thr[q] = kth;
-							atomicMin(&a.tau[a.q0 + q], float_ord(kth));
+					const uint32_t gq = a.q0 + q;
+					if (!(ub < ord_float(*reinterpret_cast<volatile unsigned int*>(&a.tau[gq])))) {
+						continue;
+					}
+					while (atomicCAS(&a.ub_lock[gq], 0u, 1u) != 0u) {
+					}
+					__threadfence();
+					volatile float* list = a.ub_list + size_t(gq) * kTcMaxK1;
+					uint32_t mi = 0;
+					float mx = list[0];
+					for (uint32_t j = 1; j < a.k1; ++j) {
+						const float v = list[j];
+						if (v > mx) {
+							mx = v;
+							mi = j;
 						}
 					}
+					if (ub < mx) {
+						list[mi] = ub;
+						float nmx = list[0];
+						for (uint32_t j = 1; j < a.k1; ++j) {
+							nmx = fmaxf(nmx, list[j]);
+						}
+						atomicMin(&a.tau[gq], float_ord(nmx));
+						s_thr[q] = fminf(s_thr[q], nmx);
+					}
+					__threadfence();
+					atomicExch(&a.ub_lock[gq], 0u);
 				}
 				*s_qcount = 0;
 			}
@@ -435,21 +452,22 @@ __global__ void __launch_bounds__(kScanThreads) knn_rerank(const float* rows, ui
 }
 
 // ---- helpers: bf16 shadow, norms, query preparation, threshold init ---------------------------------------------------------------
-// rows fp32 [n][pitch] -> shadow bf16 [n][pitch_bf] (zero padded to a multiple of 64) + ||row||_2
+// rows fp32 [n][pitch] -> bf16 shadow in the tiled layout [tile][kchunk][128 rows][64] (zero padded) + ||row||_2
 __global__ void tc_convert_rows(const float* rows, uint32_t pitch, uint32_t dim, uint32_t row_begin, uint32_t row_end, __nv_bfloat16* shadow,
-								uint32_t pitch_bf, float* vnorm) {
+								uint32_t kchunks, float* vnorm) {
 	const uint32_t row = row_begin + (blockIdx.x * blockDim.x + threadIdx.x) / 32;
 	const int lane = threadIdx.x & 31;
 	if (row >= row_end) {
 		return;
 	}
 	const float* p = rows + size_t(row) * pitch;
-	__nv_bfloat16* o = shadow + size_t(row) * pitch_bf;
+	const uint32_t tile = row / kTcTileRows, r = row % kTcTileRows;
 	float s = 0.f;
-	for (uint32_t c = lane; c < pitch_bf; c += 32) {
+	for (uint32_t c = lane; c < kchunks * kTcChunkK; c += 32) {
 		const float v = c < dim ? p[c] : 0.f;
 		s = fmaf(v, v, s);
-		o[c] = __float2bfloat16_rn(v);
+		const uint32_t kc = c / kTcChunkK, cc = c % kTcChunkK;
+		shadow[((size_t(tile) * kchunks + kc) * kTcTileRows + r) * kTcChunkK + cc] = __float2bfloat16_rn(v);
 	}
 	for (int off = 16; off > 0; off >>= 1) {
 		s += __shfl_xor_sync(0xffffffffu, s, off);
@@ -462,7 +480,8 @@ __global__ void tc_convert_rows(const float* rows, uint32_t pitch, uint32_t dim,
 // tau_init[q] = upper bound of the k1-th best distance among the first `rows` rows (fp32 dot products, one block per query).
 // Any upper bound is valid; a small relative slack covers the difference to the arithmetic order of knn_scan_warp.
 __global__ void __launch_bounds__(256) tc_init_tau(const float* rows, uint32_t pitch, uint32_t dim, const float* norm_coefs, uint32_t nrows,
-												   const float* queries, uint32_t k1, int metric, unsigned int* tau) {
+												   const float* queries, uint32_t k1, int metric, unsigned int* tau, float* ub_list,
+												   unsigned int* ub_lock) {
 	__shared__ float s_d[1024];
 	const uint32_t q = blockIdx.x;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -510,9 +529,12 @@ __global__ void __launch_bounds__(256) tc_init_tau(const float* rows, uint32_t p
 			__syncthreads();
 		}
 	}
+	if (threadIdx.x < kTcMaxK1) {  // the k1 smallest upper bounds of the first rows seed the shared list (rows < nrows sort first)
+		ub_list[size_t(q) * kTcMaxK1 + threadIdx.x] = threadIdx.x < k1 ? s_d[threadIdx.x] : -INFINITY;
+	}
 	if (threadIdx.x == 0) {
-		const uint32_t kth = min(k1, nrows) - 1;
-		tau[q] = float_ord(nrows >= k1 ? s_d[kth] : INFINITY);
+		tau[q] = float_ord(s_d[k1 - 1]);  // +inf while fewer than k1 rows exist
+		ub_lock[q] = 0;
 	}
 }
 
