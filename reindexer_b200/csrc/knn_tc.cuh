@@ -62,7 +62,7 @@ struct TcArgs {
 
 __host__ __device__ inline size_t tc_smem_bytes(uint32_t nq_block, uint32_t kchunks) {
 	return 1024 /*align slack*/ + size_t(nq_block) * kchunks * 128 + size_t(kTcStages) * kTcStageBytes + 256 /*barriers*/ +
-		   size_t(nq_block) * (4 + 4) + size_t(kTcQueueCap) * 8 + 64;
+		   size_t(nq_block) * (4 + 4 + 8) + size_t(kTcQueueCap) * 8 + 64;
 }
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------------------
@@ -134,6 +134,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// The candidate test  lb = d~ - e <= tau  rewritten as ONE fused multiply-add and one compare on the raw accumulator s = q~.v~:
+//   IP      d = -s,               e = qe*vn            <=>  s >= -tau - qe*vn                       P = -qe        R = -tau      w = 0
+//   Cosine  d = -s/vn,            e = qe               <=>  s >= (-tau - qe) * vn                   P = -tau - qe  R = 0         w = 0
+//   L2      d = qn2 + vn2 - 2s,   e = 2qe*vn + eps*(qn2+vn2)
+//                                                      <=>  s - (1-eps)/2*vn2 >= -qe*vn + ((1-eps)*qn2 - tau)/2   (w = (1-eps)/2*vn2 per row)
+// The error coefficient carries 5% slack, which also covers the one-ulp differences of these rearrangements.
+constexpr float kTcL2Eps = 1e-5f;
+__device__ __forceinline__ float2 tc_make_pr(int metric, float tau, float qe) {
+	if (metric == kIP) {
+		return make_float2(-qe, -tau);
+	}
+	if (metric == kCos) {
+		return make_float2(-tau - qe, 0.f);
+	}
+	const float qn = qe * (1.f / kTcErrCoef);
+	return make_float2(-qe, 0.5f * ((1.f - kTcL2Eps) * qn * qn - tau));
+}
+
 // ---- the filter kernel -----------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTcThreads, 1)
 	knn_tc_filter(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__ CUtensorMap map_queries, const TcArgs a) {
@@ -151,7 +169,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 	uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + 2);
 	float* s_thr = reinterpret_cast<float*>(bars + 32);                // [nq_block] current tau (map space)
 	float* s_qe = s_thr + a.nq_block;                                  // [nq_block] c * ||q||
-	uint2* s_queue = reinterpret_cast<uint2*>(s_qe + a.nq_block);     // (query, ub bits)
+	float2* s_pr = reinterpret_cast<float2*>(s_qe + a.nq_block);      // [nq_block] (P, R): candidate iff s - w_row >= fma(P, ||v||, R)
+	uint2* s_queue = reinterpret_cast<uint2*>(s_pr + a.nq_block);     // (query, ub bits)
 	uint32_t* s_qcount = reinterpret_cast<uint32_t*>(s_queue + kTcQueueCap);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -174,6 +193,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 		const bool valid = i < a.nq_valid;
 		s_thr[i] = valid ? ord_float(a.tau[a.q0 + i]) : -INFINITY;
 		s_qe[i] = valid ? kTcErrCoef * a.qnorm[a.q0 + i] : 0.f;
+		s_pr[i] = valid ? tc_make_pr(a.metric, s_thr[i], s_qe[i]) : make_float2(0.f, INFINITY);  // padding queries never match
 	}
 	if (warp == 1) {  // TMEM: 512 columns = 2 accumulator buffers of up to 256 fp32 columns
 		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(s_tmem)) : "memory");
@@ -245,9 +265,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 			const bool row_ok = row < a.n;
 			const float vn = row_ok ? a.vnorm[row] : 0.f;
 			const float vinv = (row_ok && a.vinv) ? a.vinv[row] : 1.f;
+			const float w_row = a.metric == kL2 ? 0.5f * (1.f - kTcL2Eps) * vn * vn : 0.f;
+			const float vn_t = fmaxf(vn, 1e-30f);  // keeps -inf * ||v|| = -inf (tau still +inf) for all-zero rows
 			// refresh tau from the other CTAs (queries own threads 0..nq_block-1 of the epilogue group)
 			for (uint32_t i = threadIdx.x - 64; i < a.nq_valid; i += 128) {
 				s_thr[i] = fminf(s_thr[i], ord_float(a.tau[a.q0 + i]));
+				s_pr[i] = tc_make_pr(a.metric, s_thr[i], s_qe[i]);
 			}
 			asm volatile("bar.sync 1, 128;" ::: "memory");
 			mbar_wait(&acc_full[acc], acc_phase);
@@ -255,38 +278,41 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 			for (uint32_t c0 = 0; c0 < a.nq_block; c0 += 32) {
 				uint32_t v[32];
 				tmem_ld32(tmem_base + acc * 256 + c0 + ((quad * 32) << 16), v);
-				if (row_ok) {
+				// hot path: one broadcast LDS.64, one FFMA, one compare per element; hits are collected in a bit mask
+				uint32_t hits = 0;
 #pragma unroll
-					for (int j = 0; j < 32; ++j) {
-						const uint32_t q = c0 + j;
-						if (q >= a.nq_valid) {
-							break;
-						}
-						const float s = __uint_as_float(v[j]);
-						float d, e;
-						if (a.metric == kL2) {  // ||q||^2 + ||v||^2 - 2 q.v ; s_qe = c*||q||
-							const float qn = s_qe[q] * (1.f / kTcErrCoef);
-							d = fmaf(-2.f, s, fmaf(qn, qn, vn * vn));
-							e = 2.f * s_qe[q] * vn + 1e-5f * (qn * qn + vn * vn);
-						} else if (a.metric == kCos) {
-							d = -s * vinv;
-							e = s_qe[q] * vn * vinv;
-						} else {
-							d = -s;
-							e = s_qe[q] * vn;
-						}
-						if (d - e <= s_thr[q]) {
-							const unsigned pos = atomicAdd(&a.cand_count[a.q0 + q], 1u);
-							if (pos < a.cand_cap) {
-								a.cand_rows[size_t(a.q0 + q) * a.cand_cap + pos] = row;
-							}
-							const float ub = d + e;
-							if (ub < s_thr[q] && row >= a.init_rows) {
-								const uint32_t slot = atomicAdd(s_qcount, 1u);
-								if (slot < kTcQueueCap) {
-									s_queue[slot] = make_uint2(q, __float_as_uint(ub));
-								}
-							}
+				for (int j = 0; j < 32; ++j) {
+					const float2 pr = s_pr[c0 + j];
+					const float sv = __uint_as_float(v[j]) - w_row;
+					hits |= uint32_t(sv >= fmaf(pr.x, vn_t, pr.y)) << j;
+				}
+				hits = row_ok ? hits : 0u;
+				while (hits) {  // rare path: exact bounds, candidate append, threshold tightening
+					const int j = __ffs(hits) - 1;
+					hits &= hits - 1;
+					const uint32_t q = c0 + j;
+					const float s = __uint_as_float(v[j]);
+					float d, e;
+					if (a.metric == kL2) {
+						const float qn = s_qe[q] * (1.f / kTcErrCoef);
+						d = fmaf(-2.f, s, fmaf(qn, qn, vn * vn));
+						e = 2.f * s_qe[q] * vn + kTcL2Eps * (qn * qn + vn * vn);
+					} else if (a.metric == kCos) {
+						d = -s * vinv;
+						e = s_qe[q] * vn * vinv;
+					} else {
+						d = -s;
+						e = s_qe[q] * vn;
+					}
+					const unsigned pos = atomicAdd(&a.cand_count[a.q0 + q], 1u);
+					if (pos < a.cand_cap) {
+						a.cand_rows[size_t(a.q0 + q) * a.cand_cap + pos] = row;
+					}
+					const float ub = d + e;
+					if (ub < s_thr[q] && row >= a.init_rows) {
+						const uint32_t slot = atomicAdd(s_qcount, 1u);
+						if (slot < kTcQueueCap) {
+							s_queue[slot] = make_uint2(q, __float_as_uint(ub));
 						}
 					}
 				}
@@ -329,6 +355,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 						}
 						atomicMin(&a.tau[gq], float_ord(nmx));
 						s_thr[q] = fminf(s_thr[q], nmx);
+						s_pr[q] = tc_make_pr(a.metric, s_thr[q], s_qe[q]);
 					}
 					__threadfence();
 					atomicExch(&a.ub_lock[gq], 0u);
