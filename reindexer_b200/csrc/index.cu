@@ -288,20 +288,24 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 	RX_CUDA(cudaMemsetAsync(ws.d_cand_count.p, 0, size_t(nqPad) * 4, st));
 	RX_CUDA(cudaGetLastError());
 	g_stats.launches += 2;
+	// Two CTAs per cluster share every row tile (TMA multicast) and own different query blocks: one pass serves 2*nqb queries.
+	const uint32_t ntiles = uint32_t((ix->size + kTcTileRows - 1) / kTcTileRows);
+	const int cluster = (ix->tc_cluster_off || nblocks < 2 || ix->sm_count < 2 || ntiles < 2) ? 1 : 2;
 	CUtensorMap mapRows, mapQ;
 	// tiled shadow: a 2-D view of 64-element lines, one 128-line block per (row tile, K chunk)
 	const uint64_t shadowLines = (uint64_t(std::max<uint64_t>(ix->capacity, 1)) + kTcTileRows - 1) / kTcTileRows * kTcTileRows * kchunks;
-	if (int rc = makeBf16Map(&mapRows, ix->d_shadow, kTcChunkK, shadowLines, uint64_t(kTcChunkK) * 2, kTcTileRows)) {
+	if (int rc = makeBf16Map(&mapRows, ix->d_shadow, kTcChunkK, shadowLines, uint64_t(kTcChunkK) * 2, kTcTileRows / cluster)) {
 		return rc;
 	}
 	if (int rc = makeBf16Map(&mapQ, ws.d_qbf.p, pitchBf, nqPad, uint64_t(pitchBf) * 2, nqb)) {
 		return rc;
 	}
 	const size_t smem = tc_smem_bytes(nqb, kchunks);
-	RX_CUDA(cudaFuncSetAttribute(knn_tc_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-	const uint32_t ntiles = uint32_t((ix->size + kTcTileRows - 1) / kTcTileRows);
-	const unsigned grid = std::min<unsigned>(unsigned(ix->sm_count), ntiles);
-	for (uint32_t b = 0; b < nblocks; ++b) {
+	RX_CUDA(cudaFuncSetAttribute(knn_tc_filter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+	RX_CUDA(cudaFuncSetAttribute(knn_tc_filter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+	unsigned grid = std::min<unsigned>(unsigned(ix->sm_count), ntiles * cluster);
+	grid -= grid % cluster;
+	for (uint32_t b = 0; b < nblocks; b += cluster) {
 		TcArgs a{};
 		a.vnorm = ix->d_vnorm;
 		a.vinv = ix->metric == RXGPU_COS ? ix->d_norms : nullptr;
@@ -317,7 +321,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 		a.kchunks = kchunks;
 		a.nq_block = nqb;
 		a.q0 = b * nqb;
-		a.nq_valid = std::min(nqb, nq - a.q0);
+		a.nq_total = nq;
 		a.k1 = k1;
 		a.metric = ix->metric;
 		cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -326,7 +330,23 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			RX_CUDA(cudaEventCreate(&e1));
 			RX_CUDA(cudaEventRecord(e0, st));
 		}
-		knn_tc_filter<<<grid, kTcThreads, smem, st>>>(mapRows, mapQ, a);
+		if (cluster == 2) {
+			cudaLaunchConfig_t cfg{};
+			cfg.gridDim = dim3(grid);
+			cfg.blockDim = dim3(kTcThreads);
+			cfg.dynamicSmemBytes = smem;
+			cfg.stream = st;
+			cudaLaunchAttribute attr[1];
+			attr[0].id = cudaLaunchAttributeClusterDimension;
+			attr[0].val.clusterDim.x = 2;
+			attr[0].val.clusterDim.y = 1;
+			attr[0].val.clusterDim.z = 1;
+			cfg.attrs = attr;
+			cfg.numAttrs = 1;
+			RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter<2>, mapRows, mapQ, a));
+		} else {
+			knn_tc_filter<1><<<grid, kTcThreads, smem, st>>>(mapRows, mapQ, a);
+		}
 		RX_CUDA(cudaGetLastError());
 		if (e0) {
 			RX_CUDA(cudaEventRecord(e1, st));
@@ -379,7 +399,8 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 	g_stats.query_tile = nqb;
 	g_stats.tc_used = 1;
 	g_stats.tc_candidates = cands;
-	g_stats.algorithmic_bytes += uint64_t(nblocks) * (uint64_t(ix->size) * pitchBf * 2 + uint64_t(ix->size) * 4 + uint64_t(nqb) * pitchBf * 2) +
+	g_stats.tc_cluster = uint32_t(cluster);
+	g_stats.algorithmic_bytes += uint64_t((nblocks + cluster - 1) / cluster) * (uint64_t(ix->size) * pitchBf * 2 + uint64_t(ix->size) * 4 + uint64_t(nqb) * pitchBf * 2) +
 								 cands * (uint64_t(ix->dim) * 4 + 4);
 	return 0;
 }
@@ -724,10 +745,11 @@ int rxgpu_set_query_tile(rxgpu_index* ix, uint32_t qt) {
 	return 0;
 }
 int rxgpu_set_tensor_core_filter(rxgpu_index* ix, int mode) {
-	if (!ix || mode < 0 || mode > 2) {
-		return fail(RXGPU_ERR_PARAMS, "rxgpu: mode must be 0 (auto), 1 (on) or 2 (off)");
+	if (!ix || mode < 0 || mode > 3) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: mode must be 0 (auto), 1 (on), 2 (off) or 3 (on, without CTA-pair multicast)");
 	}
-	ix->tc_mode = uint32_t(mode);
+	ix->tc_mode = uint32_t(mode == 3 ? 1 : mode);
+	ix->tc_cluster_off = mode == 3;
 	return 0;
 }
 int rxgpu_set_profile(int on) {

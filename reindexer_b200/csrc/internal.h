@@ -165,6 +165,7 @@ struct rxgpu_index {
 	mutable uint32_t pitch_bf = 0;
 	mutable uint64_t shadow_version = ~0ull;
 	uint32_t tc_mode = 0;  // 0 auto, 1 force on, 2 off
+	bool tc_cluster_off = false;
 
 	~rxgpu_index() {
 		cudaSetDevice(device);

@@ -54,8 +54,8 @@ struct TcArgs {
 	uint32_t n;                // rows
 	uint32_t kchunks;          // padded dim / 64
 	uint32_t nq_block;         // UMMA N (multiple of 32, <= 256): queries resident in this launch
-	uint32_t nq_valid;         // real queries in this block
-	uint32_t q0;               // first query of the block
+	uint32_t nq_total;         // queries in the whole batch
+	uint32_t q0;               // first query of this launch; CTA rank r of a cluster owns queries [q0 + r*nq_block, +nq_block)
 	uint32_t k1;
 	int metric;                // kL2 / kIP / kCos
 };
@@ -94,6 +94,27 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
 					 smem_u32(dst)),
 				 "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
 				 : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int32_t x, int32_t y, uint16_t mask) {
+	asm volatile(
+		"cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::
+			"r"(smem_u32(dst)),
+		"l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "h"(mask)
+		: "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+				 "h"(mask)
+				 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+	uint32_t r;
+	asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+	return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+	asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+	asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // shared-memory matrix descriptor, K-major, SWIZZLE_128B: 8-row groups are 1024 B apart (SBO), one swizzle atom along K (LBO unused)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -153,6 +174,9 @@ __device__ __forceinline__ float2 tc_make_pr(int metric, float tau, float qe) {
 }
 
 // ---- the filter kernel -----------------------------------------------------------------------------------------------------------
+// kCluster == 2: a cluster of two CTAs walks the same row tiles with DIFFERENT query blocks; each CTA fetches half of every
+// stage (64 rows) and TMA-multicasts it into both CTAs' shared memory, so one pass over the shadow serves 2 x nq_block queries.
+template <int kCluster>
 __global__ void __launch_bounds__(kTcThreads, 1)
 	knn_tc_filter(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__ CUtensorMap map_queries, const TcArgs a) {
 	extern __shared__ unsigned char smem_raw[];
@@ -175,11 +199,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint32_t ntiles = (a.n + kTcTileRows - 1) / kTcTileRows;
+	const uint32_t crank = kCluster > 1 ? cluster_ctarank() : 0u;
+	const uint32_t cid = blockIdx.x / kCluster, ncl = gridDim.x / kCluster;  // tile walkers
+	const uint32_t q0 = a.q0 + crank * a.nq_block;
+	const uint32_t nq_valid = q0 < a.nq_total ? min(a.nq_block, a.nq_total - q0) : 0u;
 
 	if (threadIdx.x == 0) {
 		for (int s = 0; s < kTcStages; ++s) {
 			mbar_init(&full_bar[s], 1);
-			mbar_init(&empty_bar[s], 1);
+			mbar_init(&empty_bar[s], kCluster);  // every consumer CTA of the stage must release it
 		}
 		mbar_init(q_bar, 1);
 		for (int s = 0; s < 2; ++s) {
@@ -190,9 +218,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	for (uint32_t i = threadIdx.x; i < a.nq_block; i += blockDim.x) {
-		const bool valid = i < a.nq_valid;
-		s_thr[i] = valid ? ord_float(a.tau[a.q0 + i]) : -INFINITY;
-		s_qe[i] = valid ? kTcErrCoef * a.qnorm[a.q0 + i] : 0.f;
+		const bool valid = i < nq_valid;
+		s_thr[i] = valid ? ord_float(a.tau[q0 + i]) : -INFINITY;
+		s_qe[i] = valid ? kTcErrCoef * a.qnorm[q0 + i] : 0.f;
 		s_pr[i] = valid ? tc_make_pr(a.metric, s_thr[i], s_qe[i]) : make_float2(0.f, INFINITY);  // padding queries never match
 	}
 	if (warp == 1) {  // TMEM: 512 columns = 2 accumulator buffers of up to 256 fp32 columns
@@ -201,6 +229,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 	}
 	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 	__syncthreads();
+	if constexpr (kCluster > 1) {
+		cluster_sync_all();  // the peer's barriers exist before anything of ours can signal them
+	}
 	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 	const uint32_t tmem_base = *s_tmem;
 
@@ -209,15 +240,21 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 		if (lane == 0) {
 			mbar_expect_tx(q_bar, a.kchunks * qchunk_bytes);
 			for (uint32_t kc = 0; kc < a.kchunks; ++kc) {
-				tma_load_2d(s_q + size_t(kc) * qchunk_bytes, &map_queries, q_bar, int32_t(kc * kTcChunkK), int32_t(a.q0));
+				tma_load_2d(s_q + size_t(kc) * qchunk_bytes, &map_queries, q_bar, int32_t(kc * kTcChunkK), int32_t(q0));
 			}
 			uint32_t stage = 0, phase = 0;
-			for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+			for (uint32_t t = cid; t < ntiles; t += ncl) {
 				for (uint32_t kc = 0; kc < a.kchunks; ++kc) {
 					mbar_wait(&empty_bar[stage], phase ^ 1);
 					mbar_expect_tx(&full_bar[stage], kTcStageBytes);
-					tma_load_2d(s_rows + size_t(stage) * kTcStageBytes, &map_rows, &full_bar[stage], 0,
-								int32_t((t * a.kchunks + kc) * kTcTileRows));
+					if constexpr (kCluster > 1) {  // my half of the stage, delivered to both CTAs (map_rows has a 64-row box here)
+						constexpr uint32_t half_rows = kTcTileRows / kCluster;
+						tma_load_2d_mc(s_rows + size_t(stage) * kTcStageBytes + size_t(crank) * half_rows * 128, &map_rows, &full_bar[stage], 0,
+									   int32_t((t * a.kchunks + kc) * kTcTileRows + crank * half_rows), uint16_t((1u << kCluster) - 1u));
+					} else {
+						tma_load_2d(s_rows + size_t(stage) * kTcStageBytes, &map_rows, &full_bar[stage], 0,
+									int32_t((t * a.kchunks + kc) * kTcTileRows));
+					}
 					if (++stage == kTcStages) {
 						stage = 0;
 						phase ^= 1;
@@ -231,7 +268,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 			const uint32_t idesc = umma_idesc_bf16(kTcTileRows, a.nq_block);
 			mbar_wait(q_bar, 0);
 			uint32_t stage = 0, phase = 0, it = 0;
-			for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+			for (uint32_t t = cid; t < ntiles; t += ncl, ++it) {
 				const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
 				mbar_wait(&acc_empty[acc], acc_phase ^ 1);
 				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -245,7 +282,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 					for (uint32_t k = 0; k < kTcChunkK / 16; ++k) {  // UMMA_K = 16 bf16 = 32 bytes inside the 128-byte swizzle row
 						umma_bf16(tmem_d, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (kc | k) != 0);
 					}
-					umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+					if constexpr (kCluster > 1) {  // the stage is rewritten by BOTH producers: release it in both CTAs
+						umma_commit_mc(&empty_bar[stage], uint16_t((1u << kCluster) - 1u));
+					} else {
+						umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+					}
 					if (++stage == kTcStages) {
 						stage = 0;
 						phase ^= 1;
@@ -259,7 +300,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 		const uint32_t quad = warp & 3;
 		const uint32_t row_in_tile = quad * 32 + lane;
 		uint32_t it = 0;
-		for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+		for (uint32_t t = cid; t < ntiles; t += ncl, ++it) {
 			const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
 			const uint32_t row = t * kTcTileRows + row_in_tile;
 			const bool row_ok = row < a.n;
@@ -268,8 +309,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 			const float w_row = a.metric == kL2 ? 0.5f * (1.f - kTcL2Eps) * vn * vn : 0.f;
 			const float vn_t = fmaxf(vn, 1e-30f);  // keeps -inf * ||v|| = -inf (tau still +inf) for all-zero rows
 			// refresh tau from the other CTAs (queries own threads 0..nq_block-1 of the epilogue group)
-			for (uint32_t i = threadIdx.x - 64; i < a.nq_valid; i += 128) {
-				s_thr[i] = fminf(s_thr[i], ord_float(a.tau[a.q0 + i]));
+			for (uint32_t i = threadIdx.x - 64; i < nq_valid; i += 128) {
+				s_thr[i] = fminf(s_thr[i], ord_float(a.tau[q0 + i]));
 				s_pr[i] = tc_make_pr(a.metric, s_thr[i], s_qe[i]);
 			}
 			asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -304,9 +345,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 						d = -s;
 						e = s_qe[q] * vn;
 					}
-					const unsigned pos = atomicAdd(&a.cand_count[a.q0 + q], 1u);
+					const unsigned pos = atomicAdd(&a.cand_count[q0 + q], 1u);
 					if (pos < a.cand_cap) {
-						a.cand_rows[size_t(a.q0 + q) * a.cand_cap + pos] = row;
+						a.cand_rows[size_t(q0 + q) * a.cand_cap + pos] = row;
 					}
 					const float ub = d + e;
 					if (ub < s_thr[q] && row >= a.init_rows) {
@@ -330,7 +371,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 				for (uint32_t i = 0; i < cnt; ++i) {
 					const uint32_t q = s_queue[i].x;
 					const float ub = __uint_as_float(s_queue[i].y);
-					const uint32_t gq = a.q0 + q;
+					const uint32_t gq = q0 + q;
 					if (!(ub < ord_float(*reinterpret_cast<volatile unsigned int*>(&a.tau[gq])))) {
 						continue;
 					}
@@ -366,6 +407,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 		}
 	}
 	__syncthreads();
+	if constexpr (kCluster > 1) {
+		cluster_sync_all();  // nobody leaves while the peer may still multicast into this CTA or signal its barriers
+	}
 	if (warp == 1) {
 		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 	}
