@@ -246,12 +246,14 @@ typedef struct {
 	uint32_t tc_used;           /* 1 when the tensor-core filter + exact re-rank path answered the batch */
 	uint32_t tc_fallbacks;      /* queries whose candidate list overflowed and were answered by the exact scan */
 	uint64_t tc_candidates;     /* rows re-ranked exactly */
-	uint32_t tc_cluster;        /* CTAs per cluster in the filter kernel (2 = row tiles TMA-multicast to a CTA pair) */
+	uint32_t tc_cluster;        /* CTAs per cluster in the filter kernel (row tiles are TMA-multicast inside a cluster) */
+	uint32_t tc_kernel;         /* 2 = query block in TMEM (knn_tc_filter_q), 1 = query block in shared memory (knn_tc_filter) */
 } rxgpu_search_stats;
 void rxgpu_last_search_stats(rxgpu_search_stats* out);
 /* large query batches: bf16 tensor-core filter + exact fp32 re-rank (results identical to the exact scan).
- * mode 0 = automatic (batches >= 64 queries on >= 100k rows, k <= 15), 1 = whenever possible, 2 = never,
- * 3 = like 1 but without the CTA-pair multicast variant */
+ * mode 0 = automatic (batches >= 64 queries on >= 100k rows, k <= 15), 1 = whenever possible, 2 = never;
+ * 3..6 force kernel variants for tests/benchmarks: 3 / 4 = first-generation kernel (queries in shared memory) with 1 CTA / a CTA
+ * pair per row tile, 5 / 6 = second-generation kernel (queries in TMEM) limited to clusters of 1 / 2 CTAs */
 int rxgpu_set_tensor_core_filter(rxgpu_index*, int mode);
 /* process-wide switch: bracket every scan-kernel launch with CUDA events (used by bench.py for the roofline figure) */
 int rxgpu_set_profile(int on);

@@ -74,7 +74,7 @@ FT_MERGE_INFO_DTYPE = np.dtype([("id", np.int32), ("proc", np.float32), ("field"
 class SearchStats(C.Structure):
     _fields_ = [("launches", C.c_uint32), ("passes", C.c_uint32), ("query_tile", C.c_uint32), ("tie_replays", C.c_uint32),
                 ("algorithmic_bytes", C.c_uint64), ("scan_launches", C.c_uint32), ("scan_kernel_ms", C.c_float),
-                ("tc_used", C.c_uint32), ("tc_fallbacks", C.c_uint32), ("tc_candidates", C.c_uint64), ("tc_cluster", C.c_uint32)]
+                ("tc_used", C.c_uint32), ("tc_fallbacks", C.c_uint32), ("tc_candidates", C.c_uint64), ("tc_cluster", C.c_uint32), ("tc_kernel", C.c_uint32)]
 
 
 # every symbol include/rxgpu.h declares (checked by tests/test_abi.py against the header text)

@@ -19,6 +19,7 @@
 #include "../host/knn_select.h"
 #include "knn_scan.cuh"
 #include "knn_tc.cuh"
+#include "knn_tc_q.cuh"
 
 using namespace rxgpu;
 
@@ -270,7 +271,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 	const uint32_t pitchBf = ix->pitch_bf, kchunks = pitchBf / kTcChunkK;
 	const uint32_t nqb = tcQueryBlock(nq, kchunks);
 	const uint32_t nblocks = (nq + nqb - 1) / nqb;
-	const uint32_t nqPad = nblocks * nqb;
+	const uint32_t nqPad = std::max<uint32_t>(nblocks * nqb, (nq + 511u) / 512u * 512u);  // both kernel generations index it
 	RX_CUDA(ws.d_qbf.ensure(size_t(nqPad) * pitchBf));
 	RX_CUDA(ws.d_qnorm.ensure(nqPad));
 	RX_CUDA(ws.d_tau.ensure(nqPad));
@@ -288,12 +289,121 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 	RX_CUDA(cudaMemsetAsync(ws.d_cand_count.p, 0, size_t(nqPad) * 4, st));
 	RX_CUDA(cudaGetLastError());
 	g_stats.launches += 2;
-	// Two CTAs per cluster share every row tile (TMA multicast) and own different query blocks: one pass serves 2*nqb queries.
 	const uint32_t ntiles = uint32_t((ix->size + kTcTileRows - 1) / kTcTileRows);
-	const int cluster = (ix->tc_cluster_off || nblocks < 2 || ix->sm_count < 2 || ntiles < 2) ? 1 : 2;
-	CUtensorMap mapRows, mapQ;
-	// tiled shadow: a 2-D view of 64-element lines, one 128-line block per (row tile, K chunk)
 	const uint64_t shadowLines = (uint64_t(std::max<uint64_t>(ix->capacity, 1)) + kTcTileRows - 1) / kTcTileRows * kTcTileRows * kchunks;
+	bool launched = false;
+	if (ix->tc_variant == 0 && kchunks <= kTqMaxKchunks) {
+		// second-generation filter: query block in TMEM, deep TMA ring, row tiles multicast to a cluster of up to 4 CTAs
+		const uint32_t qblocks = (nq + kTqQueries - 1) / kTqQueries;
+		uint32_t stages = 2;
+		while (tq_smem_bytes(stages + 1) <= kTcSmemLimit && stages < 64) {
+			++stages;
+		}
+		const size_t smem = tq_smem_bytes(stages);
+		RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+		RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+		RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+		int cluster = qblocks >= 3 ? 4 : (qblocks == 2 ? 2 : 1);
+		if (ix->tc_cluster_max && cluster > int(ix->tc_cluster_max)) {
+			cluster = int(ix->tc_cluster_max);
+		}
+		const uint32_t qtiles = uint32_t((ix->size + kTqTileRows - 1) / kTqTileRows);
+		unsigned grid = 0;
+		for (;;) {  // how many clusters of this size can be resident at once (GPC boundaries strand SMs for size 4)
+			cudaLaunchConfig_t cfg{};
+			cfg.gridDim = dim3(unsigned(ix->sm_count) / cluster * cluster);
+			cfg.blockDim = dim3(kTcThreads);
+			cfg.dynamicSmemBytes = smem;
+			cudaLaunchAttribute attr[1];
+			attr[0].id = cudaLaunchAttributeClusterDimension;
+			attr[0].val.clusterDim.x = unsigned(cluster);
+			attr[0].val.clusterDim.y = 1;
+			attr[0].val.clusterDim.z = 1;
+			cfg.attrs = attr;
+			cfg.numAttrs = 1;
+			int maxClusters = 0;
+			cudaError_t e = cluster == 4	? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q<4>, &cfg)
+							: cluster == 2 ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q<2>, &cfg)
+										   : cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q<1>, &cfg);
+			if (e == cudaSuccess && maxClusters > 0) {
+				grid = unsigned(std::min<uint64_t>(uint64_t(maxClusters), std::max<uint32_t>(qtiles, 1))) * cluster;
+				break;
+			}
+			cudaGetLastError();
+			if (cluster == 1) {
+				return fail(RXGPU_ERR_SYSTEM, "rxgpu: tensor-core filter kernel cannot be made resident");
+			}
+			cluster /= 2;
+		}
+		CUtensorMap mapRows;
+		if (int rc = makeBf16Map(&mapRows, ix->d_shadow, kTcChunkK, shadowLines, uint64_t(kTcChunkK) * 2, kTqTileRows / cluster)) {
+			return rc;
+		}
+		for (uint32_t b = 0; b < qblocks; b += cluster) {
+			TqArgs a{};
+			a.vnorm = ix->d_vnorm;
+			a.vinv = ix->metric == RXGPU_COS ? ix->d_norms : nullptr;
+			a.qnorm = ws.d_qnorm.p;
+			a.qbf = ws.d_qbf.p;
+			a.tau = ws.d_tau.p;
+			a.ub_list = ws.d_ub_list.p;
+			a.ub_lock = ws.d_ub_lock.p;
+			a.cand_rows = ws.d_cand_rows.p;
+			a.cand_count = ws.d_cand_count.p;
+			a.cand_cap = kTcCandCap;
+			a.init_rows = uint32_t(std::min<uint64_t>(ix->size, 1024));
+			a.n = uint32_t(ix->size);
+			a.kchunks = kchunks;
+			a.pitch_bf = pitchBf;
+			a.nq_total = nq;
+			a.q0 = b * kTqQueries;
+			a.k1 = k1;
+			a.stages = stages;
+			a.metric = ix->metric;
+			cudaEvent_t e0 = nullptr, e1 = nullptr;
+			if (g_profile.load(std::memory_order_relaxed)) {
+				RX_CUDA(cudaEventCreate(&e0));
+				RX_CUDA(cudaEventCreate(&e1));
+				RX_CUDA(cudaEventRecord(e0, st));
+			}
+			cudaLaunchConfig_t cfg{};
+			cfg.gridDim = dim3(grid);
+			cfg.blockDim = dim3(kTcThreads);
+			cfg.dynamicSmemBytes = smem;
+			cfg.stream = st;
+			cudaLaunchAttribute attr[1];
+			attr[0].id = cudaLaunchAttributeClusterDimension;
+			attr[0].val.clusterDim.x = unsigned(cluster);
+			attr[0].val.clusterDim.y = 1;
+			attr[0].val.clusterDim.z = 1;
+			cfg.attrs = attr;
+			cfg.numAttrs = 1;
+			if (cluster == 4) {
+				RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q<4>, mapRows, a));
+			} else if (cluster == 2) {
+				RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q<2>, mapRows, a));
+			} else {
+				RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q<1>, mapRows, a));
+			}
+			RX_CUDA(cudaGetLastError());
+			if (e0) {
+				RX_CUDA(cudaEventRecord(e1, st));
+				g_prof_events.emplace_back(e0, e1);
+			}
+			g_stats.launches += 1;
+			g_stats.passes += 1;
+		}
+		g_stats.tc_cluster = uint32_t(cluster);
+		g_stats.tc_kernel = 2;
+		g_stats.query_tile = uint32_t(kTqQueries * cluster);
+		g_stats.algorithmic_bytes += uint64_t((qblocks + cluster - 1) / cluster) * (uint64_t(ix->size) * pitchBf * 2 + uint64_t(ix->size) * 4) +
+									 uint64_t(nq) * pitchBf * 2;
+		launched = true;
+	}
+	if (!launched) {
+	// Two CTAs per cluster share every row tile (TMA multicast) and own different query blocks: one pass serves 2*nqb queries.
+	const int cluster = (ix->tc_variant == 3 || nblocks < 2 || ix->sm_count < 2 || ntiles < 2) ? 1 : 2;
+	CUtensorMap mapRows, mapQ;
 	if (int rc = makeBf16Map(&mapRows, ix->d_shadow, kTcChunkK, shadowLines, uint64_t(kTcChunkK) * 2, kTcTileRows / cluster)) {
 		return rc;
 	}
@@ -355,6 +465,12 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 		g_stats.launches += 1;
 		g_stats.passes += 1;
 	}
+	g_stats.tc_cluster = uint32_t(cluster);
+	g_stats.tc_kernel = 1;
+	g_stats.query_tile = nqb;
+	g_stats.algorithmic_bytes += uint64_t((nblocks + cluster - 1) / cluster) * (uint64_t(ix->size) * pitchBf * 2 + uint64_t(ix->size) * 4 +
+																			   uint64_t(nqb) * pitchBf * 2);
+	}
 	// exact re-rank of the candidates with the arithmetic of knn_scan_warp, then decode + labels
 	const size_t rsmem = size_t((ix->dim + 127) / 128) * 512 + size_t(kScanWarps) * (k1 + kCandBuf) * 8;
 	const float* norms = ix->metric == RXGPU_COS ? ix->d_norms : nullptr;
@@ -396,12 +512,9 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			}
 		}
 	}
-	g_stats.query_tile = nqb;
 	g_stats.tc_used = 1;
 	g_stats.tc_candidates = cands;
-	g_stats.tc_cluster = uint32_t(cluster);
-	g_stats.algorithmic_bytes += uint64_t((nblocks + cluster - 1) / cluster) * (uint64_t(ix->size) * pitchBf * 2 + uint64_t(ix->size) * 4 + uint64_t(nqb) * pitchBf * 2) +
-								 cands * (uint64_t(ix->dim) * 4 + 4);
+	g_stats.algorithmic_bytes += cands * (uint64_t(ix->dim) * 4 + 4);
 	return 0;
 }
 
@@ -507,6 +620,8 @@ int rxgpu_index_clone(rxgpu_index** out, const rxgpu_index* src, uint64_t new_ca
 	ix->size = src->size;
 	ix->qt_override = src->qt_override;
 	ix->tc_mode = src->tc_mode;
+	ix->tc_variant = src->tc_variant;
+	ix->tc_cluster_max = src->tc_cluster_max;
 	RX_CUDA(cudaMemcpyAsync(ix->d_rows, src->d_rows, size_t(src->size) * src->pitch * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
 	RX_CUDA(cudaMemcpyAsync(ix->d_labels, src->d_labels, size_t(src->size) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ix->stream));
 	if (src->d_norms) {
@@ -745,11 +860,12 @@ int rxgpu_set_query_tile(rxgpu_index* ix, uint32_t qt) {
 	return 0;
 }
 int rxgpu_set_tensor_core_filter(rxgpu_index* ix, int mode) {
-	if (!ix || mode < 0 || mode > 3) {
-		return fail(RXGPU_ERR_PARAMS, "rxgpu: mode must be 0 (auto), 1 (on), 2 (off) or 3 (on, without CTA-pair multicast)");
+	if (!ix || mode < 0 || mode > 6) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: tensor-core filter mode must be in 0..6");
 	}
-	ix->tc_mode = uint32_t(mode == 3 ? 1 : mode);
-	ix->tc_cluster_off = mode == 3;
+	ix->tc_mode = uint32_t(mode >= 3 ? 1 : mode);
+	ix->tc_variant = (mode == 3 || mode == 4) ? uint32_t(mode) : 0u;
+	ix->tc_cluster_max = mode == 5 ? 1u : (mode == 6 ? 2u : 0u);
 	return 0;
 }
 int rxgpu_set_profile(int on) {

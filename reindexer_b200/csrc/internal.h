@@ -165,7 +165,8 @@ struct rxgpu_index {
 	mutable uint32_t pitch_bf = 0;
 	mutable uint64_t shadow_version = ~0ull;
 	uint32_t tc_mode = 0;  // 0 auto, 1 force on, 2 off
-	bool tc_cluster_off = false;
+	uint32_t tc_variant = 0;      // 0 = query-in-TMEM kernel when the dimension allows; 3 / 4 = first-generation kernel (1 CTA / CTA pair)
+	uint32_t tc_cluster_max = 0;  // 0 = up to 4 CTAs per cluster
 
 	~rxgpu_index() {
 		cudaSetDevice(device);

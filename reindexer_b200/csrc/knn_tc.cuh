@@ -180,7 +180,7 @@ template <int kCluster>
 __global__ void __launch_bounds__(kTcThreads, 1)
 	knn_tc_filter(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__ CUtensorMap map_queries, const TcArgs a) {
 	extern __shared__ unsigned char smem_raw[];
-	unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+	unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset arithmetic keeps the shared window
 	const uint32_t qchunk_bytes = a.nq_block * 128;                   // one K-chunk of the query block: nq_block rows x 128 B
 	unsigned char* s_q = base;                                        // [kchunks][nq_block][128 B], swizzled by TMA
 	unsigned char* s_rows = s_q + size_t(a.kchunks) * qchunk_bytes;   // [stages][128][128 B]   (1024-aligned: nq_block % 8 == 0)
@@ -328,32 +328,37 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 					hits |= uint32_t(sv >= fmaf(pr.x, vn_t, pr.y)) << j;
 				}
 				hits = row_ok ? hits : 0u;
-				while (hits) {  // rare path: exact bounds, candidate append, threshold tightening
-					const int j = __ffs(hits) - 1;
-					hits &= hits - 1;
-					const uint32_t q = c0 + j;
-					const float s = __uint_as_float(v[j]);
-					float d, e;
-					if (a.metric == kL2) {
-						const float qn = s_qe[q] * (1.f / kTcErrCoef);
-						d = fmaf(-2.f, s, fmaf(qn, qn, vn * vn));
-						e = 2.f * s_qe[q] * vn + kTcL2Eps * (qn * qn + vn * vn);
-					} else if (a.metric == kCos) {
-						d = -s * vinv;
-						e = s_qe[q] * vn * vinv;
-					} else {
-						d = -s;
-						e = s_qe[q] * vn;
-					}
-					const unsigned pos = atomicAdd(&a.cand_count[q0 + q], 1u);
-					if (pos < a.cand_cap) {
-						a.cand_rows[size_t(q0 + q) * a.cand_cap + pos] = row;
-					}
-					const float ub = d + e;
-					if (ub < s_thr[q] && row >= a.init_rows) {
-						const uint32_t slot = atomicAdd(s_qcount, 1u);
-						if (slot < kTcQueueCap) {
-							s_queue[slot] = make_uint2(q, __float_as_uint(ub));
+				const unsigned any_hits = __reduce_or_sync(0xffffffffu, hits);
+				if (any_hits) {  // rare path: exact bounds, candidate append, threshold tightening (static indices into v[])
+#pragma unroll
+					for (int j = 0; j < 32; ++j) {
+						if (!(any_hits & (1u << j)) || !(hits & (1u << j))) {
+							continue;
+						}
+						const uint32_t q = c0 + j;
+						const float s = __uint_as_float(v[j]);
+						float d, e;
+						if (a.metric == kL2) {
+							const float qn = s_qe[q] * (1.f / kTcErrCoef);
+							d = fmaf(-2.f, s, fmaf(qn, qn, vn * vn));
+							e = 2.f * s_qe[q] * vn + kTcL2Eps * (qn * qn + vn * vn);
+						} else if (a.metric == kCos) {
+							d = -s * vinv;
+							e = s_qe[q] * vn * vinv;
+						} else {
+							d = -s;
+							e = s_qe[q] * vn;
+						}
+						const unsigned pos = atomicAdd(&a.cand_count[q0 + q], 1u);
+						if (pos < a.cand_cap) {
+							a.cand_rows[size_t(q0 + q) * a.cand_cap + pos] = row;
+						}
+						const float ub = d + e;
+						if (ub < s_thr[q] && row >= a.init_rows) {
+							const uint32_t slot = atomicAdd(s_qcount, 1u);
+							if (slot < kTcQueueCap) {
+								s_queue[slot] = make_uint2(q, __float_as_uint(ub));
+							}
 						}
 					}
 				}

@@ -1,0 +1,329 @@
+// Tensor-core candidate filter, second generation: the QUERY block lives in tensor memory (the A operand of tcgen05.mma read
+// from TMEM), so all of shared memory is a deep TMA ring for the bf16 shadow rows, and a cluster of C CTAs shares every row tile
+// through TMA multicast while each CTA owns a different block of 128 queries.
+//
+//   one pass over the shadow (n * dim * 2 bytes from HBM) now serves C * 128 queries           (knn_tc_filter: 96)
+//   bytes in flight per SM: up to 24 stages x 8 KB = 192 KB                                    (knn_tc_filter: 64 KB)
+//   per SM and pass: tiles_of_cluster x 48 MMAs (M=128 queries, N=64 rows, K=16)  -> with C=4 the kernel is balanced between
+//   the tensor pipe and HBM; same certified-bound candidate logic as knn_tc.cuh (see there), so results stay exact after re-rank.
+//
+// TMEM map (512 columns): [0, dim_padded/2) the 128 x dim bf16 query block (two K elements per 32-bit column, lane = query),
+//                         [384, 448) and [448, 512) two fp32 accumulators D[128 queries x 64 rows] (double buffered).
+// Roles (192 threads): warp 0 TMA producer (its 64/C-row slice of every stage, multicast to the cluster), warp 1 TMEM alloc + MMA
+// issue, warps 2-5 epilogue: thread = one query (TMEM lane): P/R/tau of its query in registers, per-row terms broadcast from
+// shared memory, one FFMA + compare per (query, row).  Requires dim_padded <= 768.
+#pragma once
+#include "knn_tc.cuh"
+
+namespace rxgpu {
+
+constexpr int kTqTileRows = 64;                           // UMMA N
+constexpr int kTqStageBytes = kTqTileRows * 128;          // 8 KB: 64 rows x 64 bf16
+constexpr int kTqQueries = 128;                           // UMMA M = queries per CTA
+constexpr uint32_t kTqAccCol0 = 384;                      // first accumulator column
+constexpr uint32_t kTqMaxKchunks = 12;                    // 768 / 64
+
+struct TqArgs {
+	const float* vnorm;
+	const float* vinv;
+	const float* qnorm;
+	const uint16_t* qbf;       // [nq_pad][pitch_bf] bf16 queries (row-major, zero padded)
+	unsigned int* tau;
+	float* ub_list;
+	unsigned int* ub_lock;
+	uint32_t* cand_rows;
+	unsigned int* cand_count;
+	uint32_t cand_cap;
+	uint32_t init_rows;
+	uint32_t n;
+	uint32_t kchunks;
+	uint32_t pitch_bf;
+	uint32_t nq_total;
+	uint32_t q0;               // first query of this launch; CTA rank r owns [q0 + 128 r, +128)
+	uint32_t k1;
+	uint32_t stages;
+	int metric;
+};
+
+__host__ __device__ inline size_t tq_smem_bytes(uint32_t stages) {
+	return 1024 + size_t(stages) * kTqStageBytes + (2 * size_t(stages) + 8) * 8 + 2 * kTqTileRows * 8 + 64;
+}
+
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"setp.ne.b32 p, %4, 0;\n"
+		"tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+		"}\n" ::"r"(tmem_d),
+		"r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+		: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+	asm volatile(
+		"tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+		"{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(
+			taddr),
+		"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+		"r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+		"r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+		: "memory");
+}
+
+template <int kCluster>
+__global__ void __launch_bounds__(kTcThreads, 1) knn_tc_filter_q(const __grid_constant__ CUtensorMap map_rows, const TqArgs a) {
+	extern __shared__ unsigned char smem_raw[];
+	unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+	unsigned char* s_rows = base;  // [stages][64 rows][128 B]
+	uint64_t* bars = reinterpret_cast<uint64_t*>(s_rows + size_t(a.stages) * kTqStageBytes);
+	uint64_t* full_bar = bars;
+	uint64_t* empty_bar = bars + a.stages;
+	uint64_t* acc_full = bars + 2 * a.stages;   // [2]
+	uint64_t* acc_empty = acc_full + 2;          // [2]
+	uint64_t* q_ready = acc_empty + 2;           // queries stored in TMEM
+	uint32_t* s_tmem = reinterpret_cast<uint32_t*>(q_ready + 1);
+	float2* s_vw = reinterpret_cast<float2*>(bars + 2 * a.stages + 8);  // [2][64] per-row (||v||, w) of the tile being drained / next
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t ntiles = (a.n + kTqTileRows - 1) / kTqTileRows;
+	const uint32_t crank = kCluster > 1 ? cluster_ctarank() : 0u;
+	const uint32_t cid = blockIdx.x / kCluster, ncl = gridDim.x / kCluster;
+	const uint32_t q0 = a.q0 + crank * kTqQueries;
+
+	if (threadIdx.x == 0) {
+		for (uint32_t s = 0; s < a.stages; ++s) {
+			mbar_init(&full_bar[s], 1);
+			mbar_init(&empty_bar[s], kCluster);
+		}
+		for (int s = 0; s < 2; ++s) {
+			mbar_init(&acc_full[s], 1);
+			mbar_init(&acc_empty[s], 4);
+		}
+		mbar_init(q_ready, 4);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if (warp == 1) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(s_tmem)) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	__syncthreads();
+	if constexpr (kCluster > 1) {
+		cluster_sync_all();
+	}
+	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+	const uint32_t tmem_base = *s_tmem;
+
+	if (warp == 0) {
+		// ===== TMA producer: my 64/C-row slice of every stage, multicast to the whole cluster =====
+		if (lane == 0) {
+			constexpr uint32_t slice_rows = kTqTileRows / kCluster;
+			uint32_t stage = 0, phase = 0;
+			for (uint32_t t = cid; t < ntiles; t += ncl) {
+				// tiled shadow: block (t/2, kc) holds 128 lines; the 64-row tile t is its upper or lower half
+				const uint32_t line0 = (t >> 1) * a.kchunks * 128u + (t & 1u) * 64u + crank * slice_rows;
+				for (uint32_t kc = 0; kc < a.kchunks; ++kc) {
+					mbar_wait(&empty_bar[stage], phase ^ 1);
+					mbar_expect_tx(&full_bar[stage], kTqStageBytes);
+					unsigned char* dst = s_rows + size_t(stage) * kTqStageBytes + size_t(crank) * slice_rows * 128;
+					if constexpr (kCluster > 1) {
+						tma_load_2d_mc(dst, &map_rows, &full_bar[stage], 0, int32_t(line0 + kc * 128u), uint16_t((1u << kCluster) - 1u));
+					} else {
+						tma_load_2d(dst, &map_rows, &full_bar[stage], 0, int32_t(line0 + kc * 128u));
+					}
+					if (++stage == a.stages) {
+						stage = 0;
+						phase ^= 1;
+					}
+				}
+			}
+		}
+	} else if (warp == 1) {
+		// ===== MMA issuer: D[128 queries x 64 rows] += A(TMEM) x B(smem stage)^T =====
+		if (lane == 0) {
+			const uint32_t idesc = umma_idesc_bf16(kTqQueries, kTqTileRows);
+			mbar_wait(q_ready, 0);
+			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+			uint32_t stage = 0, phase = 0, it = 0;
+			for (uint32_t t = cid; t < ntiles; t += ncl, ++it) {
+				const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+				mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+				const uint32_t tmem_d = tmem_base + kTqAccCol0 + acc * kTqTileRows;
+				for (uint32_t kc = 0; kc < a.kchunks; ++kc) {
+					mbar_wait(&full_bar[stage], phase);
+					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+					const uint32_t b_addr = smem_u32(s_rows + size_t(stage) * kTqStageBytes);
+#pragma unroll
+					for (uint32_t k = 0; k < kTcChunkK / 16; ++k) {  // K = 16 bf16 = 8 TMEM columns of A, 32 bytes of the B swizzle row
+						umma_bf16_ts(tmem_d, tmem_base + (kc * 4 + k) * 8, umma_desc_sw128(b_addr + k * 32), idesc, (kc | k) != 0);
+					}
+					if constexpr (kCluster > 1) {
+						umma_commit_mc(&empty_bar[stage], uint16_t((1u << kCluster) - 1u));
+					} else {
+						umma_commit(&empty_bar[stage]);
+					}
+					if (++stage == a.stages) {
+						stage = 0;
+						phase ^= 1;
+					}
+				}
+				umma_commit(&acc_full[acc]);
+			}
+		}
+	} else {
+		// ===== epilogue warps 2..5: thread = query (TMEM lane quadrant = warp % 4) =====
+		const uint32_t quad = warp & 3;
+		const uint32_t et = threadIdx.x - 64;              // 0..127 inside the epilogue group
+		const uint32_t my_q = q0 + quad * 32 + lane;       // global query index of this TMEM lane
+		const bool q_ok = my_q < a.nq_total;
+		// 1. my query -> TMEM (A operand): 32 columns (64 bf16) per store
+		{
+			const uint4* src = reinterpret_cast<const uint4*>(a.qbf + size_t(q_ok ? my_q : 0) * a.pitch_bf);
+			for (uint32_t kc = 0; kc < a.kchunks; ++kc) {
+				uint32_t r[32];
+#pragma unroll
+				for (int i = 0; i < 8; ++i) {
+					const uint4 x = q_ok ? src[kc * 8 + i] : make_uint4(0, 0, 0, 0);
+					r[4 * i] = x.x;
+					r[4 * i + 1] = x.y;
+					r[4 * i + 2] = x.z;
+					r[4 * i + 3] = x.w;
+				}
+				tmem_st32(tmem_base + kc * 32 + ((quad * 32) << 16), r);
+			}
+			asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+			asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+			__syncwarp();
+			if (lane == 0) {
+				mbar_arrive(q_ready);
+			}
+		}
+		const float qe = q_ok ? kTcErrCoef * a.qnorm[my_q] : 0.f;
+		float tau = q_ok ? ord_float(a.tau[my_q]) : -INFINITY;
+		float2 pr = q_ok ? tc_make_pr(a.metric, tau, qe) : make_float2(0.f, INFINITY);
+		// per-row terms of the first tile
+		auto load_vw = [&](uint32_t t, uint32_t buf) {
+			if (et < kTqTileRows) {
+				const uint32_t row = t * kTqTileRows + et;
+				float vn = 0.f, w = 0.f;
+				if (row < a.n) {
+					vn = a.vnorm[row];
+					w = a.metric == kL2 ? 0.5f * (1.f - kTcL2Eps) * vn * vn : 0.f;
+				}
+				s_vw[buf * kTqTileRows + et] = make_float2(fmaxf(vn, 1e-30f), w);
+			}
+		};
+		if (cid < ntiles) {
+			load_vw(cid, 0);
+		}
+		asm volatile("bar.sync 1, 128;" ::: "memory");
+		uint32_t it = 0;
+		for (uint32_t t = cid; t < ntiles; t += ncl, ++it) {
+			const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+			const uint32_t rows_valid = min(uint32_t(kTqTileRows), a.n - t * kTqTileRows);
+			// prefetch: tau of my query and the per-row terms of the next tile (consumed after this tile)
+			const unsigned int tau_next = q_ok ? a.tau[my_q] : 0u;
+			if (t + ncl < ntiles) {
+				load_vw(t + ncl, acc ^ 1);
+			}
+			mbar_wait(&acc_full[acc], acc_phase);
+			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+			for (uint32_t c0 = 0; c0 < kTqTileRows; c0 += 32) {
+				uint32_t v[32];
+				tmem_ld32(tmem_base + kTqAccCol0 + acc * kTqTileRows + c0 + ((quad * 32) << 16), v);
+				uint32_t hits = 0;
+#pragma unroll
+				for (int j = 0; j < 32; ++j) {
+					const float2 vw = s_vw[acc * kTqTileRows + c0 + j];
+					hits |= uint32_t(__uint_as_float(v[j]) - vw.y >= fmaf(pr.x, vw.x, pr.y)) << j;
+				}
+				const uint32_t nv = rows_valid > c0 ? min(32u, rows_valid - c0) : 0u;
+				hits &= nv >= 32 ? 0xFFFFFFFFu : ((1u << nv) - 1u);
+				const unsigned any_hits = __reduce_or_sync(0xffffffffu, hits);
+				if (any_hits) {
+#pragma unroll
+					for (int j = 0; j < 32; ++j) {
+						if (!(any_hits & (1u << j)) || !(hits & (1u << j))) {
+							continue;
+						}
+						const uint32_t row = t * kTqTileRows + c0 + j;
+						const float s = __uint_as_float(v[j]);
+						const float vn = a.vnorm[row];
+						float d, e;
+						if (a.metric == kL2) {
+							const float qn = qe * (1.f / kTcErrCoef);
+							d = fmaf(-2.f, s, fmaf(qn, qn, vn * vn));
+							e = 2.f * qe * vn + kTcL2Eps * (qn * qn + vn * vn);
+						} else if (a.metric == kCos) {
+							const float vinv = a.vinv[row];
+							d = -s * vinv;
+							e = qe * vn * vinv;
+						} else {
+							d = -s;
+							e = qe * vn;
+						}
+						const unsigned pos = atomicAdd(&a.cand_count[my_q], 1u);
+						if (pos < a.cand_cap) {
+							a.cand_rows[size_t(my_q) * a.cand_cap + pos] = row;
+						}
+						const float ub = d + e;
+						if (ub < tau && row >= a.init_rows) {
+							// this thread is the only one of the CTA that handles my_q; other clusters contend for the lock
+							while (atomicCAS(&a.ub_lock[my_q], 0u, 1u) != 0u) {
+							}
+							__threadfence();
+							volatile float* list = a.ub_list + size_t(my_q) * kTcMaxK1;
+							uint32_t mi = 0;
+							float mx = list[0];
+							for (uint32_t x = 1; x < a.k1; ++x) {
+								const float y = list[x];
+								if (y > mx) {
+									mx = y;
+									mi = x;
+								}
+							}
+							if (ub < mx) {
+								list[mi] = ub;
+								float nmx = list[0];
+								for (uint32_t x = 1; x < a.k1; ++x) {
+									nmx = fmaxf(nmx, list[x]);
+								}
+								atomicMin(&a.tau[my_q], float_ord(nmx));
+								tau = fminf(tau, nmx);
+							} else {
+								tau = fminf(tau, mx);
+							}
+							__threadfence();
+							atomicExch(&a.ub_lock[my_q], 0u);
+							pr = tc_make_pr(a.metric, tau, qe);
+						}
+					}
+				}
+			}
+			asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+			__syncwarp();
+			if (lane == 0) {
+				mbar_arrive(&acc_empty[acc]);
+			}
+			if (q_ok) {
+				const float tn = ord_float(tau_next);
+				if (tn < tau) {
+					tau = tn;
+					pr = tc_make_pr(a.metric, tau, qe);
+				}
+			}
+			asm volatile("bar.sync 1, 128;" ::: "memory");  // s_vw[acc ^ 1] written by everyone before the next tile reads it
+		}
+	}
+	__syncthreads();
+	if constexpr (kCluster > 1) {
+		cluster_sync_all();
+	}
+	if (warp == 1) {
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+	}
+}
+
+}  // namespace rxgpu

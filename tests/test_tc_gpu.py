@@ -24,7 +24,7 @@ def both_paths(gpu, queries, k):
 
 @pytest.mark.parametrize("metric", [rx.L2, rx.IP, rx.COS])
 @pytest.mark.parametrize("n,dim,nq,k", [(20000, 128, 64, 10), (30000, 100, 100, 10), (12000, 768, 96, 10), (9000, 64, 300, 15),
-                                        (5000, 200, 33, 1), (30000, 768, 400, 10), (40000, 256, 700, 5)])
+                                        (5000, 200, 33, 1), (30000, 768, 400, 10), (40000, 256, 700, 5), (6000, 1000, 150, 10)])
 def test_tc_path_is_bit_identical_to_exact_scan(metric, n, dim, nq, k):
     gpu = rx.GpuBruteforceSearch(metric, dim, n)
     gpu.append_synth(0xABC0 + dim, 0, n)
@@ -34,13 +34,18 @@ def test_tc_path_is_bit_identical_to_exact_scan(metric, n, dim, nq, k):
     assert (l0 == l1).all(), np.argwhere(l0 != l1)[:5]
     assert (d0.view(np.uint32) == d1.view(np.uint32)).all()
     assert st["tc_fallbacks"] == 0 and 0 < st["tc_candidates"] < nq * 4096
-    # the single-CTA variant (no TMA multicast across a CTA pair) gives the same bits
-    gpu.set_tensor_core_filter(3)
-    d2, l2, c2 = gpu.search_knn(queries, k)
-    assert rx.last_search_stats()["tc_cluster"] == 1
-    assert (l2 == l0).all() and (d2.view(np.uint32) == d0.view(np.uint32)).all()
-    if nq >= 300:
-        assert st["tc_cluster"] == 2
+    # every kernel variant gives the same bits: 3 / 4 = queries in shared memory (1 CTA / CTA pair with TMA multicast),
+    # 5 / 6 = queries in TMEM limited to clusters of 1 / 2 CTAs (the default above uses up to 4)
+    for mode, kernel in ((3, 1), (4, 1), (5, 2), (6, 2)):
+        gpu.set_tensor_core_filter(mode)
+        d2, l2, c2 = gpu.search_knn(queries, k)
+        s2 = rx.last_search_stats()
+        if dim <= 768:
+            assert s2["tc_kernel"] == kernel, (mode, s2)
+        assert (l2 == l0).all() and (d2.view(np.uint32) == d0.view(np.uint32)).all(), mode
+    assert st["tc_kernel"] == (2 if dim <= 768 else 1)
+    if nq > 256 and dim <= 768:
+        assert st["tc_cluster"] == 4
 
 
 def test_tc_path_matches_oracle():
