@@ -300,18 +300,42 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 		const uint32_t quad = warp & 3;
 		const uint32_t row_in_tile = quad * 32 + lane;
 		uint32_t it = 0;
+		unsigned int tau_ahead0 = float_ord(INFINITY), tau_ahead1 = float_ord(INFINITY);
+		float vn_ahead = 0.f, vinv_ahead = 1.f;
+		{
+			const uint32_t frow = cid * kTcTileRows + row_in_tile;
+			if (cid < ntiles && frow < a.n) {
+				vn_ahead = a.vnorm[frow];
+				vinv_ahead = a.vinv ? a.vinv[frow] : 1.f;
+			}
+		}
 		for (uint32_t t = cid; t < ntiles; t += ncl, ++it) {
 			const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
 			const uint32_t row = t * kTcTileRows + row_in_tile;
 			const bool row_ok = row < a.n;
-			const float vn = row_ok ? a.vnorm[row] : 0.f;
-			const float vinv = (row_ok && a.vinv) ? a.vinv[row] : 1.f;
+			// refresh tau from the other CTAs (thread i of the epilogue group owns queries i and i + 128).  The global loads were
+			// issued during the PREVIOUS tile, so their latency is hidden; the ones for the next tile are issued now.
+			{
+				const uint32_t i0 = threadIdx.x - 64, i1 = i0 + 128;
+				if (i0 < nq_valid) {
+					s_thr[i0] = fminf(s_thr[i0], ord_float(tau_ahead0));
+					s_pr[i0] = tc_make_pr(a.metric, s_thr[i0], s_qe[i0]);
+					tau_ahead0 = a.tau[q0 + i0];
+				}
+				if (i1 < nq_valid) {
+					s_thr[i1] = fminf(s_thr[i1], ord_float(tau_ahead1));
+					s_pr[i1] = tc_make_pr(a.metric, s_thr[i1], s_qe[i1]);
+					tau_ahead1 = a.tau[q0 + i1];
+				}
+			}
+			const float vn = vn_ahead, vinv = vinv_ahead;
 			const float w_row = a.metric == kL2 ? 0.5f * (1.f - kTcL2Eps) * vn * vn : 0.f;
 			const float vn_t = fmaxf(vn, 1e-30f);  // keeps -inf * ||v|| = -inf (tau still +inf) for all-zero rows
-			// refresh tau from the other CTAs (queries own threads 0..nq_block-1 of the epilogue group)
-			for (uint32_t i = threadIdx.x - 64; i < nq_valid; i += 128) {
-				s_thr[i] = fminf(s_thr[i], ord_float(a.tau[q0 + i]));
-				s_pr[i] = tc_make_pr(a.metric, s_thr[i], s_qe[i]);
+			{
+				const uint32_t nrow = (t + ncl) * kTcTileRows + row_in_tile;
+				const bool nok = t + ncl < ntiles && nrow < a.n;
+				vn_ahead = nok ? a.vnorm[nrow] : 0.f;
+				vinv_ahead = (nok && a.vinv) ? a.vinv[nrow] : 1.f;
 			}
 			asm volatile("bar.sync 1, 128;" ::: "memory");
 			mbar_wait(&acc_full[acc], acc_phase);

@@ -202,30 +202,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_filter_q(const __grid_co
 		const float qe = q_ok ? kTcErrCoef * a.qnorm[my_q] : 0.f;
 		float tau = q_ok ? ord_float(a.tau[my_q]) : -INFINITY;
 		float2 pr = q_ok ? tc_make_pr(a.metric, tau, qe) : make_float2(0.f, INFINITY);
-		// per-row terms of the first tile
-		auto load_vw = [&](uint32_t t, uint32_t buf) {
+		// per-row terms (||v||, w): global loads are issued ONE TILE AHEAD of the shared-memory store that consumes them, so their
+		// HBM latency overlaps a whole tile of work instead of stalling the epilogue (same for the tau refresh)
+		auto fetch_vn = [&](uint32_t t) -> float {
+			const uint32_t row = t * kTqTileRows + et;
+			return (et < kTqTileRows && t < ntiles && row < a.n) ? a.vnorm[row] : 0.f;
+		};
+		auto store_vw = [&](float vn, uint32_t buf) {
 			if (et < kTqTileRows) {
-				const uint32_t row = t * kTqTileRows + et;
-				float vn = 0.f, w = 0.f;
-				if (row < a.n) {
-					vn = a.vnorm[row];
-					w = a.metric == kL2 ? 0.5f * (1.f - kTcL2Eps) * vn * vn : 0.f;
-				}
+				const float w = a.metric == kL2 ? 0.5f * (1.f - kTcL2Eps) * vn * vn : 0.f;
 				s_vw[buf * kTqTileRows + et] = make_float2(fmaxf(vn, 1e-30f), w);
 			}
 		};
-		if (cid < ntiles) {
-			load_vw(cid, 0);
-		}
+		store_vw(fetch_vn(cid), 0);
+		float vn_ahead = fetch_vn(cid + ncl);            // for the tile after the first
+		unsigned int tau_ahead = q_ok ? a.tau[my_q] : 0u;
 		asm volatile("bar.sync 1, 128;" ::: "memory");
 		uint32_t it = 0;
 		for (uint32_t t = cid; t < ntiles; t += ncl, ++it) {
 			const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
 			const uint32_t rows_valid = min(uint32_t(kTqTileRows), a.n - t * kTqTileRows);
-			// prefetch: tau of my query and the per-row terms of the next tile (consumed after this tile)
-			const unsigned int tau_next = q_ok ? a.tau[my_q] : 0u;
-			if (t + ncl < ntiles) {
-				load_vw(t + ncl, acc ^ 1);
+			// consume what was fetched during the previous tile, then fetch for the one after next
+			store_vw(vn_ahead, acc ^ 1);
+			vn_ahead = fetch_vn(t + 2 * ncl);
+			if (q_ok) {
+				const float tn = ord_float(tau_ahead);
+				if (tn < tau) {
+					tau = tn;
+					pr = tc_make_pr(a.metric, tau, qe);
+				}
+				tau_ahead = a.tau[my_q];
 			}
 			mbar_wait(&acc_full[acc], acc_phase);
 			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -306,13 +312,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_filter_q(const __grid_co
 			__syncwarp();
 			if (lane == 0) {
 				mbar_arrive(&acc_empty[acc]);
-			}
-			if (q_ok) {
-				const float tn = ord_float(tau_next);
-				if (tn < tau) {
-					tau = tn;
-					pr = tc_make_pr(a.metric, tau, qe);
-				}
 			}
 			asm volatile("bar.sync 1, 128;" ::: "memory");  // s_vw[acc ^ 1] written by everyone before the next tile reads it
 		}
