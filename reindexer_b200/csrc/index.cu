@@ -312,7 +312,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 		for (;;) {  // how many clusters of this size can be resident at once (GPC boundaries strand SMs for size 4)
 			cudaLaunchConfig_t cfg{};
 			cfg.gridDim = dim3(unsigned(ix->sm_count) / cluster * cluster);
-			cfg.blockDim = dim3(kTcThreads);
+			cfg.blockDim = dim3(kTqThreads);
 			cfg.dynamicSmemBytes = smem;
 			cudaLaunchAttribute attr[1];
 			attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -368,7 +368,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			}
 			cudaLaunchConfig_t cfg{};
 			cfg.gridDim = dim3(grid);
-			cfg.blockDim = dim3(kTcThreads);
+			cfg.blockDim = dim3(kTqThreads);
 			cfg.dynamicSmemBytes = smem;
 			cfg.stream = st;
 			cudaLaunchAttribute attr[1];

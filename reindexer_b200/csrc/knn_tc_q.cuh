@@ -9,16 +9,20 @@
 //
 // TMEM map (512 columns): [0, dim_padded/2) the 128 x dim bf16 query block (two K elements per 32-bit column, lane = query),
 //                         [384, 448) and [448, 512) two fp32 accumulators D[128 queries x 64 rows] (double buffered).
-// Roles (192 threads): warp 0 TMA producer (its 64/C-row slice of every stage, multicast to the cluster), warp 1 TMEM alloc + MMA
-// issue, warps 2-5 epilogue: thread = one query (TMEM lane): P/R/tau of its query in registers, per-row terms broadcast from
-// shared memory, one FFMA + compare per (query, row).  Requires dim_padded <= 768.
+// Roles (224 threads): warp 0 TMA producer (its 64/C-row slice of every stage, multicast to the cluster); warps 1 and 6 issue the
+// MMAs of the even / odd tiles into accumulator 0 / 1 (two issuers keep the tensor pipe fed: the serial mbarrier-wait + issue +
+// commit latency of one thread is comparable to the MMA time of a tile); warps 2-5 epilogue: thread = one query (TMEM lane) with
+// P/R/tau of its query in registers, per-row terms broadcast from shared memory, one FFMA + compare per (query, row).
+// Requires dim_padded <= 768.
 #pragma once
 #include "knn_tc.cuh"
 
 namespace rxgpu {
 
 constexpr int kTqTileRows = 64;                           // UMMA N
-constexpr int kTqStageBytes = kTqTileRows * 128;          // 8 KB: 64 rows x 64 bf16
+constexpr int kTqSubBytes = kTqTileRows * 128;            // 8 KB: 64 rows x 64 bf16 (one 128-byte swizzle atom wide)
+constexpr int kTqStageBytes = 2 * kTqSubBytes;            // a stage = two K chunks (128 bf16 per row) = 16 KB, one mbarrier
+constexpr int kTqThreads = 224;                           // producer, issuer A, 4 epilogue warps, issuer B
 constexpr int kTqQueries = 128;                           // UMMA M = queries per CTA
 constexpr uint32_t kTqAccCol0 = 384;                      // first accumulator column
 constexpr uint32_t kTqMaxKchunks = 12;                    // 768 / 64
@@ -71,7 +75,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 }
 
 template <int kCluster>
-__global__ void __launch_bounds__(kTcThreads, 1) knn_tc_filter_q(const __grid_constant__ CUtensorMap map_rows, const TqArgs a) {
+__global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const __grid_constant__ CUtensorMap map_rows, const TqArgs a) {
 	extern __shared__ unsigned char smem_raw[];
 	unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 	unsigned char* s_rows = base;  // [stages][64 rows][128 B]
@@ -115,21 +119,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_filter_q(const __grid_co
 	const uint32_t tmem_base = *s_tmem;
 
 	if (warp == 0) {
-		// ===== TMA producer: my 64/C-row slice of every stage, multicast to the whole cluster =====
+		// ===== TMA producer: my 64/C-row slice of both K chunks of every stage, multicast to the whole cluster =====
 		if (lane == 0) {
 			constexpr uint32_t slice_rows = kTqTileRows / kCluster;
+			const uint32_t kpairs = (a.kchunks + 1) / 2;
 			uint32_t stage = 0, phase = 0;
 			for (uint32_t t = cid; t < ntiles; t += ncl) {
 				// tiled shadow: block (t/2, kc) holds 128 lines; the 64-row tile t is its upper or lower half
 				const uint32_t line0 = (t >> 1) * a.kchunks * 128u + (t & 1u) * 64u + crank * slice_rows;
-				for (uint32_t kc = 0; kc < a.kchunks; ++kc) {
+				for (uint32_t kp = 0; kp < kpairs; ++kp) {
+					const uint32_t nsub = (2 * kp + 1 < a.kchunks) ? 2u : 1u;
 					mbar_wait(&empty_bar[stage], phase ^ 1);
-					mbar_expect_tx(&full_bar[stage], kTqStageBytes);
-					unsigned char* dst = s_rows + size_t(stage) * kTqStageBytes + size_t(crank) * slice_rows * 128;
-					if constexpr (kCluster > 1) {
-						tma_load_2d_mc(dst, &map_rows, &full_bar[stage], 0, int32_t(line0 + kc * 128u), uint16_t((1u << kCluster) - 1u));
-					} else {
-						tma_load_2d(dst, &map_rows, &full_bar[stage], 0, int32_t(line0 + kc * 128u));
+					mbar_expect_tx(&full_bar[stage], nsub * kTqSubBytes);
+					for (uint32_t sub = 0; sub < nsub; ++sub) {
+						unsigned char* dst = s_rows + size_t(stage) * kTqStageBytes + sub * kTqSubBytes + size_t(crank) * slice_rows * 128;
+						const int32_t y = int32_t(line0 + (2 * kp + sub) * 128u);
+						if constexpr (kCluster > 1) {
+							tma_load_2d_mc(dst, &map_rows, &full_bar[stage], 0, y, uint16_t((1u << kCluster) - 1u));
+						} else {
+							tma_load_2d(dst, &map_rows, &full_bar[stage], 0, y);
+						}
 					}
 					if (++stage == a.stages) {
 						stage = 0;
@@ -138,37 +147,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_filter_q(const __grid_co
 				}
 			}
 		}
-	} else if (warp == 1) {
-		// ===== MMA issuer: D[128 queries x 64 rows] += A(TMEM) x B(smem stage)^T =====
+	} else if (warp == 1 || warp == 6) {
+		// ===== MMA issuers: warp 1 -> even tiles / accumulator 0, warp 6 -> odd tiles / accumulator 1 =====
+		// D[128 queries x 64 rows] += A(TMEM) x B(smem stage)^T
 		if (lane == 0) {
+			const uint32_t parity = warp == 1 ? 0u : 1u;
 			const uint32_t idesc = umma_idesc_bf16(kTqQueries, kTqTileRows);
+			const uint32_t kpairs = (a.kchunks + 1) / 2;
 			mbar_wait(q_ready, 0);
 			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-			uint32_t stage = 0, phase = 0, it = 0;
-			for (uint32_t t = cid; t < ntiles; t += ncl, ++it) {
-				const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-				mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+			const uint32_t tmem_d = tmem_base + kTqAccCol0 + parity * kTqTileRows;
+			for (uint32_t it = parity, t = cid + parity * ncl; t < ntiles; it += 2, t += 2 * ncl) {
+				mbar_wait(&acc_empty[parity], ((it >> 1) & 1) ^ 1);
 				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-				const uint32_t tmem_d = tmem_base + kTqAccCol0 + acc * kTqTileRows;
-				for (uint32_t kc = 0; kc < a.kchunks; ++kc) {
+				const uint32_t sidx0 = it * kpairs;  // stages are consumed in tile order by the two issuers alternately
+				for (uint32_t kp = 0; kp < kpairs; ++kp) {
+					const uint32_t sidx = sidx0 + kp;
+					const uint32_t stage = sidx % a.stages, phase = (sidx / a.stages) & 1;
+					const uint32_t nsub = (2 * kp + 1 < a.kchunks) ? 2u : 1u;
 					mbar_wait(&full_bar[stage], phase);
 					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 					const uint32_t b_addr = smem_u32(s_rows + size_t(stage) * kTqStageBytes);
+					for (uint32_t sub = 0; sub < nsub; ++sub) {
 #pragma unroll
-					for (uint32_t k = 0; k < kTcChunkK / 16; ++k) {  // K = 16 bf16 = 8 TMEM columns of A, 32 bytes of the B swizzle row
-						umma_bf16_ts(tmem_d, tmem_base + (kc * 4 + k) * 8, umma_desc_sw128(b_addr + k * 32), idesc, (kc | k) != 0);
+						for (uint32_t k = 0; k < kTcChunkK / 16; ++k) {  // K = 16 bf16 = 8 TMEM columns of A, 32 bytes of the B swizzle row
+							umma_bf16_ts(tmem_d, tmem_base + ((2 * kp + sub) * 4 + k) * 8, umma_desc_sw128(b_addr + sub * kTqSubBytes + k * 32),
+										 idesc, (kp | sub | k) != 0);
+						}
 					}
 					if constexpr (kCluster > 1) {
 						umma_commit_mc(&empty_bar[stage], uint16_t((1u << kCluster) - 1u));
 					} else {
 						umma_commit(&empty_bar[stage]);
 					}
-					if (++stage == a.stages) {
-						stage = 0;
-						phase ^= 1;
-					}
 				}
-				umma_commit(&acc_full[acc]);
+				umma_commit(&acc_full[parity]);
 			}
 		}
 	} else {
