@@ -21,7 +21,8 @@ namespace rxgpu {
 
 constexpr int kTqTileRows = 64;                           // UMMA N
 constexpr int kTqSubBytes = kTqTileRows * 128;            // 8 KB: 64 rows x 64 bf16 (one 128-byte swizzle atom wide)
-constexpr int kTqStageBytes = 2 * kTqSubBytes;            // a stage = two K chunks (128 bf16 per row) = 16 KB, one mbarrier
+constexpr int kTqSubsPerStage = 4;                        // K chunks per stage
+constexpr int kTqStageBytes = kTqSubsPerStage * kTqSubBytes;  // a stage = 64 rows x 256 bf16 = 32 KB behind ONE mbarrier
 constexpr int kTqThreads = 224;                           // producer, issuer A, 4 epilogue warps, issuer B
 constexpr int kTqQueries = 128;                           // UMMA M = queries per CTA
 constexpr uint32_t kTqAccCol0 = 384;                      // first accumulator column
@@ -122,18 +123,18 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const __grid_co
 		// ===== TMA producer: my 64/C-row slice of both K chunks of every stage, multicast to the whole cluster =====
 		if (lane == 0) {
 			constexpr uint32_t slice_rows = kTqTileRows / kCluster;
-			const uint32_t kpairs = (a.kchunks + 1) / 2;
+			const uint32_t kpairs = (a.kchunks + kTqSubsPerStage - 1) / kTqSubsPerStage;
 			uint32_t stage = 0, phase = 0;
 			for (uint32_t t = cid; t < ntiles; t += ncl) {
 				// tiled shadow: block (t/2, kc) holds 128 lines; the 64-row tile t is its upper or lower half
 				const uint32_t line0 = (t >> 1) * a.kchunks * 128u + (t & 1u) * 64u + crank * slice_rows;
 				for (uint32_t kp = 0; kp < kpairs; ++kp) {
-					const uint32_t nsub = (2 * kp + 1 < a.kchunks) ? 2u : 1u;
+					const uint32_t nsub = min(uint32_t(kTqSubsPerStage), a.kchunks - kTqSubsPerStage * kp);
 					mbar_wait(&empty_bar[stage], phase ^ 1);
 					mbar_expect_tx(&full_bar[stage], nsub * kTqSubBytes);
 					for (uint32_t sub = 0; sub < nsub; ++sub) {
 						unsigned char* dst = s_rows + size_t(stage) * kTqStageBytes + sub * kTqSubBytes + size_t(crank) * slice_rows * 128;
-						const int32_t y = int32_t(line0 + (2 * kp + sub) * 128u);
+						const int32_t y = int32_t(line0 + (kTqSubsPerStage * kp + sub) * 128u);
 						if constexpr (kCluster > 1) {
 							tma_load_2d_mc(dst, &map_rows, &full_bar[stage], 0, y, uint16_t((1u << kCluster) - 1u));
 						} else {
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const __grid_co
 		if (lane == 0) {
 			const uint32_t parity = warp == 1 ? 0u : 1u;
 			const uint32_t idesc = umma_idesc_bf16(kTqQueries, kTqTileRows);
-			const uint32_t kpairs = (a.kchunks + 1) / 2;
+			const uint32_t kpairs = (a.kchunks + kTqSubsPerStage - 1) / kTqSubsPerStage;
 			mbar_wait(q_ready, 0);
 			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 			const uint32_t tmem_d = tmem_base + kTqAccCol0 + parity * kTqTileRows;
@@ -164,14 +165,15 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const __grid_co
 				for (uint32_t kp = 0; kp < kpairs; ++kp) {
 					const uint32_t sidx = sidx0 + kp;
 					const uint32_t stage = sidx % a.stages, phase = (sidx / a.stages) & 1;
-					const uint32_t nsub = (2 * kp + 1 < a.kchunks) ? 2u : 1u;
+					const uint32_t nsub = min(uint32_t(kTqSubsPerStage), a.kchunks - kTqSubsPerStage * kp);
 					mbar_wait(&full_bar[stage], phase);
 					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 					const uint32_t b_addr = smem_u32(s_rows + size_t(stage) * kTqStageBytes);
 					for (uint32_t sub = 0; sub < nsub; ++sub) {
 #pragma unroll
 						for (uint32_t k = 0; k < kTcChunkK / 16; ++k) {  // K = 16 bf16 = 8 TMEM columns of A, 32 bytes of the B swizzle row
-							umma_bf16_ts(tmem_d, tmem_base + ((2 * kp + sub) * 4 + k) * 8, umma_desc_sw128(b_addr + sub * kTqSubBytes + k * 32),
+							umma_bf16_ts(tmem_d, tmem_base + ((kTqSubsPerStage * kp + sub) * 4 + k) * 8,
+										 umma_desc_sw128(b_addr + sub * kTqSubBytes + k * 32),
 										 idesc, (kp | sub | k) != 0);
 						}
 					}
@@ -248,10 +250,21 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const __grid_co
 			}
 			mbar_wait(&acc_full[acc], acc_phase);
 			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+			// pull the whole 128 x 64 accumulator into registers and hand the TMEM buffer back to its issuer BEFORE looking at the
+			// values: the buffer's turn-around time, not the compare loop, is on the critical path of the tensor pipe
+			uint32_t vall[2][32];
+			tmem_ld32_nowait(tmem_base + kTqAccCol0 + acc * kTqTileRows + ((quad * 32) << 16), vall[0]);
+			tmem_ld32_nowait(tmem_base + kTqAccCol0 + acc * kTqTileRows + 32 + ((quad * 32) << 16), vall[1]);
+			asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+			asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+			__syncwarp();
+			if (lane == 0) {
+				mbar_arrive(&acc_empty[acc]);
+			}
 #pragma unroll
-			for (uint32_t c0 = 0; c0 < kTqTileRows; c0 += 32) {
-				uint32_t v[32];
-				tmem_ld32(tmem_base + kTqAccCol0 + acc * kTqTileRows + c0 + ((quad * 32) << 16), v);
+			for (uint32_t ch = 0; ch < 2; ++ch) {
+				const uint32_t c0 = ch * 32;
+				uint32_t (&v)[32] = vall[ch];
 				uint32_t hits = 0;
 #pragma unroll
 				for (int j = 0; j < 32; ++j) {
@@ -320,11 +333,6 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const __grid_co
 						}
 					}
 				}
-			}
-			asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-			__syncwarp();
-			if (lane == 0) {
-				mbar_arrive(&acc_empty[acc]);
 			}
 			asm volatile("bar.sync 1, 128;" ::: "memory");  // s_vw[acc ^ 1] written by everyone before the next tile reads it
 		}
