@@ -290,7 +290,6 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 	RX_CUDA(cudaGetLastError());
 	g_stats.launches += 2;
 	const uint32_t ntiles = uint32_t((ix->size + kTcTileRows - 1) / kTcTileRows);
-	const uint64_t shadowLines = (uint64_t(std::max<uint64_t>(ix->capacity, 1)) + kTcTileRows - 1) / kTcTileRows * kTcTileRows * kchunks;
 	bool launched = false;
 	if (ix->tc_variant == 0 && kchunks <= kTqMaxKchunks) {
 		// second-generation filter: query block in TMEM, deep TMA ring, row tiles multicast to a cluster of up to 4 CTAs
@@ -335,12 +334,9 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			}
 			cluster /= 2;
 		}
-		CUtensorMap mapRows;
-		if (int rc = makeBf16Map(&mapRows, ix->d_shadow, kTcChunkK, shadowLines, uint64_t(kTcChunkK) * 2, kTqTileRows / cluster)) {
-			return rc;
-		}
 		for (uint32_t b = 0; b < qblocks; b += cluster) {
 			TqArgs a{};
+			a.shadow = static_cast<const unsigned char*>(ix->d_shadow);
 			a.vnorm = ix->d_vnorm;
 			a.vinv = ix->metric == RXGPU_COS ? ix->d_norms : nullptr;
 			a.qnorm = ws.d_qnorm.p;
@@ -379,11 +375,11 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			cfg.attrs = attr;
 			cfg.numAttrs = 1;
 			if (cluster == 4) {
-				RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q<4>, mapRows, a));
+				RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q<4>, a));
 			} else if (cluster == 2) {
-				RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q<2>, mapRows, a));
+				RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q<2>, a));
 			} else {
-				RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q<1>, mapRows, a));
+				RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q<1>, a));
 			}
 			RX_CUDA(cudaGetLastError());
 			if (e0) {
@@ -403,10 +399,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 	if (!launched) {
 	// Two CTAs per cluster share every row tile (TMA multicast) and own different query blocks: one pass serves 2*nqb queries.
 	const int cluster = (ix->tc_variant == 3 || nblocks < 2 || ix->sm_count < 2 || ntiles < 2) ? 1 : 2;
-	CUtensorMap mapRows, mapQ;
-	if (int rc = makeBf16Map(&mapRows, ix->d_shadow, kTcChunkK, shadowLines, uint64_t(kTcChunkK) * 2, kTcTileRows / cluster)) {
-		return rc;
-	}
+	CUtensorMap mapQ;
 	if (int rc = makeBf16Map(&mapQ, ws.d_qbf.p, pitchBf, nqPad, uint64_t(pitchBf) * 2, nqb)) {
 		return rc;
 	}
@@ -417,6 +410,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 	grid -= grid % cluster;
 	for (uint32_t b = 0; b < nblocks; b += cluster) {
 		TcArgs a{};
+		a.shadow = static_cast<const unsigned char*>(ix->d_shadow);
 		a.vnorm = ix->d_vnorm;
 		a.vinv = ix->metric == RXGPU_COS ? ix->d_norms : nullptr;
 		a.qnorm = ws.d_qnorm.p;
@@ -453,9 +447,9 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			attr[0].val.clusterDim.z = 1;
 			cfg.attrs = attr;
 			cfg.numAttrs = 1;
-			RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter<2>, mapRows, mapQ, a));
+			RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter<2>, mapQ, a));
 		} else {
-			knn_tc_filter<1><<<grid, kTcThreads, smem, st>>>(mapRows, mapQ, a);
+			knn_tc_filter<1><<<grid, kTcThreads, smem, st>>>(mapQ, a);
 		}
 		RX_CUDA(cudaGetLastError());
 		if (e0) {

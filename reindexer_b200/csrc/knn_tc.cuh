@@ -14,9 +14,9 @@
 //                 exact scan of the first rows (tc_init_tau) and only decreases.
 //
 // Roles (192 threads, 1 CTA per SM, persistent over 128-row tiles):
-//   warp 0    TMA producer: bf16 shadow rows, 128 x 64 tiles (16 KB, SWIZZLE_128B) through a 4-stage mbarrier ring; the shadow
-//             is stored TILED in HBM -- [tile of 128 rows][K chunk][128 rows][64 bf16] -- so every stage is one contiguous
-//             16 KB read (row-major fp32 stays the source of truth; the shadow is a private, derived structure)
+//   warp 0    producer: bf16 shadow rows, 128 x 64 tiles (16 KB) through a 4-stage mbarrier ring.  The shadow is stored TILED and
+//             PRE-SWIZZLED in HBM ([tile of 64 rows][K chunk][64 x 128 B in the SWIZZLE_128B pattern]) so a stage is two
+//             contiguous 8 KB cp.async.bulk copies (row-major fp32 stays the source of truth; the shadow is private, derived)
 //   warp 1    allocates TMEM (512 columns), issues tcgen05.mma (M=128 rows, N=NQ queries, K=16) from shared-memory descriptors;
 //             the query block (NQ x dim bf16) is loaded once by TMA and stays resident in shared memory
 //   warps 2-5 epilogue: tcgen05.ld the 128 x NQ fp32 accumulators (double buffered in TMEM so the next tile's MMAs overlap),
@@ -41,6 +41,7 @@ constexpr uint32_t kTcQueueCap = 512;
 constexpr float kTcErrCoef = 0.0042f;  // see header comment
 
 struct TcArgs {
+	const unsigned char* shadow;  // bf16 shadow, [tile of 64 rows][K chunk][64 rows x 128 B, SWIZZLE_128B pattern pre-applied]
 	const float* vnorm;        // [n] ||row||_2 (fp32)
 	const float* vinv;         // [n] 1/||row|| (Cosine) or nullptr
 	const float* qnorm;        // [nq_total] ||q||_2
@@ -93,6 +94,18 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
 	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
 					 smem_u32(dst)),
 				 "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+				 : "memory");
+}
+// 1-D bulk copies (TMA engine, no tensor map): the shadow is stored pre-swizzled, so a stage is a verbatim contiguous copy
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+				 "r"(bytes), "r"(smem_u32(bar))
+				 : "memory");
+}
+__device__ __forceinline__ void bulk_load_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+					 smem_u32(dst)),
+				 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
 				 : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int32_t x, int32_t y, uint16_t mask) {
@@ -189,7 +202,7 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
 // stage (64 rows) and TMA-multicasts it into both CTAs' shared memory, so one pass over the shadow serves 2 x nq_block queries.
 template <int kCluster>
 __global__ void __launch_bounds__(kTcThreads, 1)
-	knn_tc_filter(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__ CUtensorMap map_queries, const TcArgs a) {
+	knn_tc_filter(const __grid_constant__ CUtensorMap map_queries, const TcArgs a) {
 	extern __shared__ unsigned char smem_raw[];
 	unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset arithmetic keeps the shared window
 	const uint32_t qchunk_bytes = a.nq_block * 128;                   // one K-chunk of the query block: nq_block rows x 128 B
@@ -258,13 +271,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 				for (uint32_t kc = 0; kc < a.kchunks; ++kc) {
 					mbar_wait(&empty_bar[stage], phase ^ 1);
 					mbar_expect_tx(&full_bar[stage], kTcStageBytes);
-					if constexpr (kCluster > 1) {  // my half of the stage, delivered to both CTAs (map_rows has a 64-row box here)
-						constexpr uint32_t half_rows = kTcTileRows / kCluster;
-						tma_load_2d_mc(s_rows + size_t(stage) * kTcStageBytes + size_t(crank) * half_rows * 128, &map_rows, &full_bar[stage], 0,
-									   int32_t((t * a.kchunks + kc) * kTcTileRows + crank * half_rows), uint16_t((1u << kCluster) - 1u));
+					// a 128-row stage = the 64-row shadow sub-tiles 2t and 2t+1 of this K chunk, 8 KB each, contiguous in HBM
+					const unsigned char* src = a.shadow + (size_t(2 * t) * a.kchunks + kc) * 8192u;
+					unsigned char* dst = s_rows + size_t(stage) * kTcStageBytes;
+					if constexpr (kCluster > 1) {  // my half of the stage, delivered to both CTAs
+						bulk_load_mc(dst + crank * 8192u, src + size_t(crank) * a.kchunks * 8192u, 8192u, &full_bar[stage],
+									 uint16_t((1u << kCluster) - 1u));
 					} else {
-						tma_load_2d(s_rows + size_t(stage) * kTcStageBytes, &map_rows, &full_bar[stage], 0,
-									int32_t((t * a.kchunks + kc) * kTcTileRows));
+						bulk_load(dst, src, 8192u, &full_bar[stage]);
+						bulk_load(dst + 8192u, src + size_t(a.kchunks) * 8192u, 8192u, &full_bar[stage]);
 					}
 					if (++stage == kTcStages) {
 						stage = 0;
@@ -563,7 +578,9 @@ __global__ void __launch_bounds__(kScanThreads) knn_rerank(const float* rows, ui
 }
 
 // ---- helpers: bf16 shadow, norms, query preparation, threshold init ---------------------------------------------------------------
-// rows fp32 [n][pitch] -> bf16 shadow in the tiled layout [tile][kchunk][128 rows][64] (zero padded) + ||row||_2
+// rows fp32 [n][pitch] -> bf16 shadow + ||row||_2.  Shadow layout: [tile of 64 rows][K chunk of 64][64 rows x 128 bytes], and inside
+// every 8 KB block the 16-byte units of row r are XOR-permuted with (r % 8) -- the SWIZZLE_128B pattern tcgen05.mma expects in
+// shared memory -- so that a plain contiguous cp.async.bulk brings a ready-to-multiply operand tile.
 __global__ void tc_convert_rows(const float* rows, uint32_t pitch, uint32_t dim, uint32_t row_begin, uint32_t row_end, __nv_bfloat16* shadow,
 								uint32_t kchunks, float* vnorm) {
 	const uint32_t row = row_begin + (blockIdx.x * blockDim.x + threadIdx.x) / 32;
@@ -572,13 +589,14 @@ __global__ void tc_convert_rows(const float* rows, uint32_t pitch, uint32_t dim,
 		return;
 	}
 	const float* p = rows + size_t(row) * pitch;
-	const uint32_t tile = row / kTcTileRows, r = row % kTcTileRows;
+	const uint32_t tile = row / 64u, r = row % 64u;
 	float s = 0.f;
 	for (uint32_t c = lane; c < kchunks * kTcChunkK; c += 32) {
 		const float v = c < dim ? p[c] : 0.f;
 		s = fmaf(v, v, s);
 		const uint32_t kc = c / kTcChunkK, cc = c % kTcChunkK;
-		shadow[((size_t(tile) * kchunks + kc) * kTcTileRows + r) * kTcChunkK + cc] = __float2bfloat16_rn(v);
+		const uint32_t unit = (cc >> 3) ^ (r & 7u);  // 16-byte unit = 8 bf16
+		shadow[(size_t(tile) * kchunks + kc) * 4096u + r * 64u + unit * 8u + (cc & 7u)] = __float2bfloat16_rn(v);
 	}
 	for (int off = 16; off > 0; off >>= 1) {
 		s += __shfl_xor_sync(0xffffffffu, s, off);

@@ -29,6 +29,7 @@ constexpr uint32_t kTqAccCol0 = 384;                      // first accumulator c
 constexpr uint32_t kTqMaxKchunks = 12;                    // 768 / 64
 
 struct TqArgs {
+	const unsigned char* shadow;  // see tc_convert_rows: [tile64][K chunk][8 KB pre-swizzled]
 	const float* vnorm;
 	const float* vinv;
 	const float* qnorm;
@@ -76,7 +77,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 }
 
 template <int kCluster>
-__global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const __grid_constant__ CUtensorMap map_rows, const TqArgs a) {
+__global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a) {
 	extern __shared__ unsigned char smem_raw[];
 	unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 	unsigned char* s_rows = base;  // [stages][64 rows][128 B]
@@ -120,26 +121,26 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const __grid_co
 	const uint32_t tmem_base = *s_tmem;
 
 	if (warp == 0) {
-		// ===== TMA producer: my 64/C-row slice of both K chunks of every stage, multicast to the whole cluster =====
+		// ===== producer: contiguous 8 KB bulk copies; in a cluster CTA r fetches the K chunks with (chunk % C == r) of every stage and
+		// multicasts them to all CTAs =====
 		if (lane == 0) {
-			constexpr uint32_t slice_rows = kTqTileRows / kCluster;
 			const uint32_t kpairs = (a.kchunks + kTqSubsPerStage - 1) / kTqSubsPerStage;
 			uint32_t stage = 0, phase = 0;
 			for (uint32_t t = cid; t < ntiles; t += ncl) {
-				// tiled shadow: block (t/2, kc) holds 128 lines; the 64-row tile t is its upper or lower half
-				const uint32_t line0 = (t >> 1) * a.kchunks * 128u + (t & 1u) * 64u + crank * slice_rows;
+				const unsigned char* tile_src = a.shadow + size_t(t) * a.kchunks * kTqSubBytes;
 				for (uint32_t kp = 0; kp < kpairs; ++kp) {
 					const uint32_t nsub = min(uint32_t(kTqSubsPerStage), a.kchunks - kTqSubsPerStage * kp);
 					mbar_wait(&empty_bar[stage], phase ^ 1);
 					mbar_expect_tx(&full_bar[stage], nsub * kTqSubBytes);
-					for (uint32_t sub = 0; sub < nsub; ++sub) {
-						unsigned char* dst = s_rows + size_t(stage) * kTqStageBytes + sub * kTqSubBytes + size_t(crank) * slice_rows * 128;
-						const int32_t y = int32_t(line0 + (kTqSubsPerStage * kp + sub) * 128u);
-						if constexpr (kCluster > 1) {
-							tma_load_2d_mc(dst, &map_rows, &full_bar[stage], 0, y, uint16_t((1u << kCluster) - 1u));
-						} else {
-							tma_load_2d(dst, &map_rows, &full_bar[stage], 0, y);
+					unsigned char* dst = s_rows + size_t(stage) * kTqStageBytes;
+					const unsigned char* src = tile_src + size_t(kTqSubsPerStage * kp) * kTqSubBytes;
+					if constexpr (kCluster > 1) {
+						for (uint32_t sub = crank; sub < nsub; sub += kCluster) {
+							bulk_load_mc(dst + sub * kTqSubBytes, src + size_t(sub) * kTqSubBytes, kTqSubBytes, &full_bar[stage],
+										 uint16_t((1u << kCluster) - 1u));
 						}
+					} else {
+						bulk_load(dst, src, nsub * kTqSubBytes, &full_bar[stage]);  // the K chunks of a tile are contiguous
 					}
 					if (++stage == a.stages) {
 						stage = 0;
