@@ -356,6 +356,13 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			a.k1 = k1;
 			a.stages = stages;
 			a.metric = ix->metric;
+			static DevBuf<unsigned long long> traceBuf;  // profiling aid: RXGPU_TC_TRACE=<file> dumps per-tile timestamps of CTA 0
+			const char* tracePath = std::getenv("RXGPU_TC_TRACE");
+			if (tracePath && b == 0) {
+				RX_CUDA(traceBuf.ensure(256 * 16));
+				RX_CUDA(cudaMemsetAsync(traceBuf.p, 0, 256 * 16 * 8, st));
+				a.trace = traceBuf.p;
+			}
 			cudaEvent_t e0 = nullptr, e1 = nullptr;
 			if (g_profile.load(std::memory_order_relaxed)) {
 				RX_CUDA(cudaEventCreate(&e0));
@@ -388,6 +395,19 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			}
 			g_stats.launches += 1;
 			g_stats.passes += 1;
+			if (a.trace) {
+				std::vector<unsigned long long> h(256 * 16);
+				RX_CUDA(cudaStreamSynchronize(st));
+				RX_CUDA(cudaMemcpy(h.data(), a.trace, h.size() * 8, cudaMemcpyDeviceToHost));
+				if (FILE* f = std::fopen(std::getenv("RXGPU_TC_TRACE"), "w")) {
+					for (int i = 0; i < 256; ++i) {
+						for (int j = 0; j < 16; ++j) {
+							std::fprintf(f, "%llu%c", h[i * 16 + j], j == 15 ? '\n' : ' ');
+						}
+					}
+					std::fclose(f);
+				}
+			}
 		}
 		g_stats.tc_cluster = uint32_t(cluster);
 		g_stats.tc_kernel = 2;

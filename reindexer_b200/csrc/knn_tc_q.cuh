@@ -49,6 +49,7 @@ struct TqArgs {
 	uint32_t k1;
 	uint32_t stages;
 	int metric;
+	unsigned long long* trace;  // profiling aid (RXGPU_TC_TRACE): per-tile timestamps of CTA 0, or nullptr
 };
 
 __host__ __device__ inline size_t tq_smem_bytes(uint32_t stages) {
@@ -75,6 +76,18 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 		"r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
 		: "memory");
 }
+
+__device__ __forceinline__ unsigned long long tq_clock() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+#define TQ_TRACE(slot, idx)                                                        \
+	do {                                                                           \
+		if (a.trace && blockIdx.x == 0 && (idx) < 256) {                           \
+			a.trace[(idx) * 16 + (slot)] = tq_clock();                             \
+		}                                                                          \
+	} while (0)
 
 template <int kCluster>
 __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a) {
@@ -130,7 +143,13 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 				const unsigned char* tile_src = a.shadow + size_t(t) * a.kchunks * kTqSubBytes;
 				for (uint32_t kp = 0; kp < kpairs; ++kp) {
 					const uint32_t nsub = min(uint32_t(kTqSubsPerStage), a.kchunks - kTqSubsPerStage * kp);
+					if (kp == 0) {
+						TQ_TRACE(9, (t - cid) / ncl);
+					}
 					mbar_wait(&empty_bar[stage], phase ^ 1);
+					if (kp == 0) {
+						TQ_TRACE(10, (t - cid) / ncl);
+					}
 					mbar_expect_tx(&full_bar[stage], nsub * kTqSubBytes);
 					unsigned char* dst = s_rows + size_t(stage) * kTqStageBytes;
 					const unsigned char* src = tile_src + size_t(kTqSubsPerStage * kp) * kTqSubBytes;
@@ -160,8 +179,10 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 			const uint32_t tmem_d = tmem_base + kTqAccCol0 + parity * kTqTileRows;
 			for (uint32_t it = parity, t = cid + parity * ncl; t < ntiles; it += 2, t += 2 * ncl) {
+				TQ_TRACE(0, it);
 				mbar_wait(&acc_empty[parity], ((it >> 1) & 1) ^ 1);
 				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+				TQ_TRACE(1, it);
 				const uint32_t sidx0 = it * kpairs;  // stages are consumed in tile order by the two issuers alternately
 				for (uint32_t kp = 0; kp < kpairs; ++kp) {
 					const uint32_t sidx = sidx0 + kp;
@@ -169,6 +190,9 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 					const uint32_t nsub = min(uint32_t(kTqSubsPerStage), a.kchunks - kTqSubsPerStage * kp);
 					mbar_wait(&full_bar[stage], phase);
 					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+					if (kp == 0) {
+						TQ_TRACE(2, it);
+					}
 					const uint32_t b_addr = smem_u32(s_rows + size_t(stage) * kTqStageBytes);
 					for (uint32_t sub = 0; sub < nsub; ++sub) {
 #pragma unroll
@@ -185,6 +209,7 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 					}
 				}
 				umma_commit(&acc_full[parity]);
+				TQ_TRACE(3, it);
 			}
 		}
 	} else {
@@ -249,8 +274,14 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 				}
 				tau_ahead = a.tau[my_q];
 			}
+			if (threadIdx.x == 64) {
+				TQ_TRACE(4, it);
+			}
 			mbar_wait(&acc_full[acc], acc_phase);
 			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+			if (threadIdx.x == 64) {
+				TQ_TRACE(5, it);
+			}
 			// pull the whole 128 x 64 accumulator into registers and hand the TMEM buffer back to its issuer BEFORE looking at the
 			// values: the buffer's turn-around time, not the compare loop, is on the critical path of the tensor pipe
 			uint32_t vall[2][32];
@@ -261,6 +292,9 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 			__syncwarp();
 			if (lane == 0) {
 				mbar_arrive(&acc_empty[acc]);
+			}
+			if (threadIdx.x == 64) {
+				TQ_TRACE(6, it);
 			}
 #pragma unroll
 			for (uint32_t ch = 0; ch < 2; ++ch) {
@@ -335,7 +369,13 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 					}
 				}
 			}
+			if (threadIdx.x == 64) {
+				TQ_TRACE(7, it);
+			}
 			asm volatile("bar.sync 1, 128;" ::: "memory");  // s_vw[acc ^ 1] written by everyone before the next tile reads it
+			if (threadIdx.x == 64) {
+				TQ_TRACE(8, it);
+			}
 		}
 	}
 	__syncthreads();
