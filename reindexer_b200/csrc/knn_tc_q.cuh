@@ -53,7 +53,7 @@ struct TqArgs {
 };
 
 __host__ __device__ inline size_t tq_smem_bytes(uint32_t stages) {
-	return 1024 + size_t(stages) * kTqStageBytes + (2 * size_t(stages) + 8) * 8 + 2 * kTqTileRows * 8 + 64;
+	return 1024 + size_t(stages) * kTqStageBytes + (2 * size_t(stages) + 8) * 8 + 2 * kTqTileRows * 8 + 64;  // 8 barrier slots: acc_full[2] acc_empty[2] q_ready turn[2] tmem
 }
 
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 	uint64_t* acc_full = bars + 2 * a.stages;   // [2]
 	uint64_t* acc_empty = acc_full + 2;          // [2]
 	uint64_t* q_ready = acc_empty + 2;           // queries stored in TMEM
-	uint32_t* s_tmem = reinterpret_cast<uint32_t*>(q_ready + 1);
+	uint64_t* turn = q_ready + 1;                // [2] issue token: MMAs of one tile must enter the tensor queue back to back
+	uint32_t* s_tmem = reinterpret_cast<uint32_t*>(turn + 2);
 	float2* s_vw = reinterpret_cast<float2*>(bars + 2 * a.stages + 8);  // [2][64] per-row (||v||, w) of the tile being drained / next
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -119,6 +120,8 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 			mbar_init(&acc_empty[s], 4);
 		}
 		mbar_init(q_ready, 4);
+		mbar_init(&turn[0], 1);
+		mbar_init(&turn[1], 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	if (warp == 1) {
@@ -178,28 +181,35 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 			mbar_wait(q_ready, 0);
 			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 			const uint32_t tmem_d = tmem_base + kTqAccCol0 + parity * kTqTileRows;
-			for (uint32_t it = parity, t = cid + parity * ncl; t < ntiles; it += 2, t += 2 * ncl) {
+			// The two issuers alternate tile by tile.  Each first waits for everything its tile needs (accumulator drained, all
+			// stages landed), THEN takes the issue token, pushes its 48 MMAs + commits into the tensor queue back to back and passes
+			// the token on: MMAs of different accumulators must not interleave in the queue (an accumulator switch between two MMAs
+			// costs a TMEM round trip of the 32 KB tile), and the mbarrier wake-up latencies stay off the issue path.
+			uint32_t n_mine = 0;
+			for (uint32_t it = parity, t = cid + parity * ncl; t < ntiles; it += 2, t += 2 * ncl, ++n_mine) {
 				TQ_TRACE(0, it);
 				mbar_wait(&acc_empty[parity], ((it >> 1) & 1) ^ 1);
-				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 				TQ_TRACE(1, it);
 				const uint32_t sidx0 = it * kpairs;  // stages are consumed in tile order by the two issuers alternately
 				for (uint32_t kp = 0; kp < kpairs; ++kp) {
 					const uint32_t sidx = sidx0 + kp;
-					const uint32_t stage = sidx % a.stages, phase = (sidx / a.stages) & 1;
+					mbar_wait(&full_bar[sidx % a.stages], (sidx / a.stages) & 1);
+				}
+				TQ_TRACE(2, it);
+				if (it > 0) {  // token: the other issuer finished issuing tile it - 1 (its (it-1)/2-th arrive on my turn barrier)
+					mbar_wait(&turn[parity], ((it - 1) >> 1) & 1);
+				}
+				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+				for (uint32_t kp = 0; kp < kpairs; ++kp) {
+					const uint32_t sidx = sidx0 + kp;
+					const uint32_t stage = sidx % a.stages;
 					const uint32_t nsub = min(uint32_t(kTqSubsPerStage), a.kchunks - kTqSubsPerStage * kp);
-					mbar_wait(&full_bar[stage], phase);
-					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-					if (kp == 0) {
-						TQ_TRACE(2, it);
-					}
 					const uint32_t b_addr = smem_u32(s_rows + size_t(stage) * kTqStageBytes);
 					for (uint32_t sub = 0; sub < nsub; ++sub) {
 #pragma unroll
 						for (uint32_t k = 0; k < kTcChunkK / 16; ++k) {  // K = 16 bf16 = 8 TMEM columns of A, 32 bytes of the B swizzle row
 							umma_bf16_ts(tmem_d, tmem_base + ((kTqSubsPerStage * kp + sub) * 4 + k) * 8,
-										 umma_desc_sw128(b_addr + sub * kTqSubBytes + k * 32),
-										 idesc, (kp | sub | k) != 0);
+										 umma_desc_sw128(b_addr + sub * kTqSubBytes + k * 32), idesc, (kp | sub | k) != 0);
 						}
 					}
 					if constexpr (kCluster > 1) {
@@ -209,6 +219,7 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 					}
 				}
 				umma_commit(&acc_full[parity]);
+				mbar_arrive(&turn[parity ^ 1]);
 				TQ_TRACE(3, it);
 			}
 		}
