@@ -53,7 +53,7 @@ struct TqArgs {
 };
 
 __host__ __device__ inline size_t tq_smem_bytes(uint32_t stages) {
-	return 1024 + size_t(stages) * kTqStageBytes + (2 * size_t(stages) + 8) * 8 + 2 * kTqTileRows * 8 + 64;  // 8 barrier slots: acc_full[2] acc_empty[2] q_ready turn[2] tmem
+	return 1024 + size_t(stages) * kTqStageBytes + (2 * size_t(stages) + 16) * 8 + 4 * kTqTileRows * 4 + 64;  // 16 slots: acc_full[2] acc_empty[2] q_ready turn[2] vn_full[4] tmem
 }
 
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -101,8 +101,9 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 	uint64_t* acc_empty = acc_full + 2;          // [2]
 	uint64_t* q_ready = acc_empty + 2;           // queries stored in TMEM
 	uint64_t* turn = q_ready + 1;                // [2] issue token: MMAs of one tile must enter the tensor queue back to back
-	uint32_t* s_tmem = reinterpret_cast<uint32_t*>(turn + 2);
-	float2* s_vw = reinterpret_cast<float2*>(bars + 2 * a.stages + 8);  // [2][64] per-row (||v||, w) of the tile being drained / next
+	uint64_t* vn_full = turn + 2;                // [4] row norms of a tile landed
+	uint32_t* s_tmem = reinterpret_cast<uint32_t*>(vn_full + 4);
+	float* s_vn = reinterpret_cast<float*>(bars + 2 * a.stages + 16);  // [4][64] ||row|| of tiles it, it+1, ... (slot = it & 3)
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint32_t ntiles = (a.n + kTqTileRows - 1) / kTqTileRows;
@@ -122,6 +123,9 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 		mbar_init(q_ready, 4);
 		mbar_init(&turn[0], 1);
 		mbar_init(&turn[1], 1);
+		for (int i = 0; i < 4; ++i) {
+			mbar_init(&vn_full[i], 1);
+		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	if (warp == 1) {
@@ -152,6 +156,11 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 					mbar_wait(&empty_bar[stage], phase ^ 1);
 					if (kp == 0) {
 						TQ_TRACE(10, (t - cid) / ncl);
+					}
+					if (kp == 0) {  // the 64 row norms of this tile ride along (own barrier, own CTA only): no epilogue thread ever waits
+						const uint32_t slot = ((t - cid) / ncl) & 3u;  // on a plain global load under a saturated HBM
+						mbar_expect_tx(&vn_full[slot], kTqTileRows * 4);
+						bulk_load(s_vn + slot * kTqTileRows, a.vnorm + size_t(t) * kTqTileRows, kTqTileRows * 4, &vn_full[slot]);
 					}
 					mbar_expect_tx(&full_bar[stage], nsub * kTqSubBytes);
 					unsigned char* dst = s_rows + size_t(stage) * kTqStageBytes;
@@ -226,7 +235,6 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 	} else {
 		// ===== epilogue warps 2..5: thread = query (TMEM lane quadrant = warp % 4) =====
 		const uint32_t quad = warp & 3;
-		const uint32_t et = threadIdx.x - 64;              // 0..127 inside the epilogue group
 		const uint32_t my_q = q0 + quad * 32 + lane;       // global query index of this TMEM lane
 		const bool q_ok = my_q < a.nq_total;
 		// 1. my query -> TMEM (A operand): 32 columns (64 bf16) per store
@@ -254,30 +262,15 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 		const float qe = q_ok ? kTcErrCoef * a.qnorm[my_q] : 0.f;
 		float tau = q_ok ? ord_float(a.tau[my_q]) : -INFINITY;
 		float2 pr = q_ok ? tc_make_pr(a.metric, tau, qe) : make_float2(0.f, INFINITY);
-		// per-row terms (||v||, w): global loads are issued ONE TILE AHEAD of the shared-memory store that consumes them, so their
-		// HBM latency overlaps a whole tile of work instead of stalling the epilogue (same for the tau refresh)
-		auto fetch_vn = [&](uint32_t t) -> float {
-			const uint32_t row = t * kTqTileRows + et;
-			return (et < kTqTileRows && t < ntiles && row < a.n) ? a.vnorm[row] : 0.f;
-		};
-		auto store_vw = [&](float vn, uint32_t buf) {
-			if (et < kTqTileRows) {
-				const float w = a.metric == kL2 ? 0.5f * (1.f - kTcL2Eps) * vn * vn : 0.f;
-				s_vw[buf * kTqTileRows + et] = make_float2(fmaxf(vn, 1e-30f), w);
-			}
-		};
-		store_vw(fetch_vn(cid), 0);
-		float vn_ahead = fetch_vn(cid + ncl);            // for the tile after the first
+		// Nothing in this loop may wait on a plain global load: under a saturated HBM such a load takes many microseconds, the
+		// accumulator is then released late and the tensor pipe idles.  Row norms arrive by bulk copy (vn_full), and the shared
+		// threshold is re-read only every 8th tile with the load issued 8 tiles earlier.
 		unsigned int tau_ahead = q_ok ? a.tau[my_q] : 0u;
-		asm volatile("bar.sync 1, 128;" ::: "memory");
 		uint32_t it = 0;
 		for (uint32_t t = cid; t < ntiles; t += ncl, ++it) {
 			const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
 			const uint32_t rows_valid = min(uint32_t(kTqTileRows), a.n - t * kTqTileRows);
-			// consume what was fetched during the previous tile, then fetch for the one after next
-			store_vw(vn_ahead, acc ^ 1);
-			vn_ahead = fetch_vn(t + 2 * ncl);
-			if (q_ok) {
+			if ((it & 7u) == 7u && q_ok) {
 				const float tn = ord_float(tau_ahead);
 				if (tn < tau) {
 					tau = tn;
@@ -287,6 +280,19 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 			}
 			if (threadIdx.x == 64) {
 				TQ_TRACE(4, it);
+			}
+			mbar_wait(&vn_full[it & 3u], (it >> 2) & 1u);
+			float vn[kTqTileRows];
+			{
+				const float4* p = reinterpret_cast<const float4*>(s_vn + (it & 3u) * kTqTileRows);
+#pragma unroll
+				for (int i = 0; i < kTqTileRows / 4; ++i) {
+					const float4 x = p[i];
+					vn[4 * i] = fmaxf(x.x, 1e-30f);
+					vn[4 * i + 1] = fmaxf(x.y, 1e-30f);
+					vn[4 * i + 2] = fmaxf(x.z, 1e-30f);
+					vn[4 * i + 3] = fmaxf(x.w, 1e-30f);
+				}
 			}
 			mbar_wait(&acc_full[acc], acc_phase);
 			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -307,6 +313,7 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 			if (threadIdx.x == 64) {
 				TQ_TRACE(6, it);
 			}
+			const float wcoef = a.metric == kL2 ? 0.5f * (1.f - kTcL2Eps) : 0.f;
 #pragma unroll
 			for (uint32_t ch = 0; ch < 2; ++ch) {
 				const uint32_t c0 = ch * 32;
@@ -314,8 +321,8 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 				uint32_t hits = 0;
 #pragma unroll
 				for (int j = 0; j < 32; ++j) {
-					const float2 vw = s_vw[acc * kTqTileRows + c0 + j];
-					hits |= uint32_t(__uint_as_float(v[j]) - vw.y >= fmaf(pr.x, vw.x, pr.y)) << j;
+					const float x = vn[c0 + j];
+					hits |= uint32_t(fmaf(-wcoef * x, x, __uint_as_float(v[j])) >= fmaf(pr.x, x, pr.y)) << j;
 				}
 				const uint32_t nv = rows_valid > c0 ? min(32u, rows_valid - c0) : 0u;
 				hits &= nv >= 32 ? 0xFFFFFFFFu : ((1u << nv) - 1u);
@@ -328,19 +335,19 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 						}
 						const uint32_t row = t * kTqTileRows + c0 + j;
 						const float s = __uint_as_float(v[j]);
-						const float vn = a.vnorm[row];
+						const float vnr = vn[c0 + j];
 						float d, e;
 						if (a.metric == kL2) {
 							const float qn = qe * (1.f / kTcErrCoef);
-							d = fmaf(-2.f, s, fmaf(qn, qn, vn * vn));
-							e = 2.f * qe * vn + kTcL2Eps * (qn * qn + vn * vn);
+							d = fmaf(-2.f, s, fmaf(qn, qn, vnr * vnr));
+							e = 2.f * qe * vnr + kTcL2Eps * (qn * qn + vnr * vnr);
 						} else if (a.metric == kCos) {
-							const float vinv = a.vinv[row];
+							const float vinv = 1.f / vnr;  // within 1e-5 of the stored coefficient (normalize.cc shortcut), covered by the slack
 							d = -s * vinv;
-							e = qe * vn * vinv;
+							e = qe * 1.0001f;
 						} else {
 							d = -s;
-							e = qe * vn;
+							e = qe * vnr;
 						}
 						const unsigned pos = atomicAdd(&a.cand_count[my_q], 1u);
 						if (pos < a.cand_cap) {
@@ -382,9 +389,6 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 			}
 			if (threadIdx.x == 64) {
 				TQ_TRACE(7, it);
-			}
-			asm volatile("bar.sync 1, 128;" ::: "memory");  // s_vw[acc ^ 1] written by everyone before the next tile reads it
-			if (threadIdx.x == 64) {
 				TQ_TRACE(8, it);
 			}
 		}
