@@ -391,6 +391,7 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 				TQ_TRACE(7, it);
 				TQ_TRACE(8, it);
 			}
+			__syncwarp();  // the rare path diverges (per-lane lock loops): reconverge before the .aligned tcgen05 ops of the next tile
 		}
 	}
 	__syncthreads();
