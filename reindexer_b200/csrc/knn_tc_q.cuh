@@ -53,7 +53,7 @@ struct TqArgs {
 };
 
 __host__ __device__ inline size_t tq_smem_bytes(uint32_t stages) {
-	return 1024 + size_t(stages) * kTqStageBytes + (2 * size_t(stages) + 16) * 8 + 4 * kTqTileRows * 4 + 64;  // 16 slots: acc_full[2] acc_empty[2] q_ready turn[2] vn_full[4] tmem
+	return 1024 + size_t(stages) * kTqStageBytes + (2 * size_t(stages) + 8) * 8 + 2 * kTqTileRows * 8 + 64;
 }
 
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -100,10 +100,8 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 	uint64_t* acc_full = bars + 2 * a.stages;   // [2]
 	uint64_t* acc_empty = acc_full + 2;          // [2]
 	uint64_t* q_ready = acc_empty + 2;           // queries stored in TMEM
-	uint64_t* turn = q_ready + 1;                // [2] issue token: MMAs of one tile must enter the tensor queue back to back
-	uint64_t* vn_full = turn + 2;                // [4] row norms of a tile landed
-	uint32_t* s_tmem = reinterpret_cast<uint32_t*>(vn_full + 4);
-	float* s_vn = reinterpret_cast<float*>(bars + 2 * a.stages + 16);  // [4][64] ||row|| of tiles it, it+1, ... (slot = it & 3)
+	uint32_t* s_tmem = reinterpret_cast<uint32_t*>(q_ready + 1);
+	float2* s_vw = reinterpret_cast<float2*>(bars + 2 * a.stages + 8);  // [2][64] per-row (||v||, w) of the tile being drained / next
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint32_t ntiles = (a.n + kTqTileRows - 1) / kTqTileRows;
@@ -121,11 +119,6 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 			mbar_init(&acc_empty[s], 4);
 		}
 		mbar_init(q_ready, 4);
-		mbar_init(&turn[0], 1);
-		mbar_init(&turn[1], 1);
-		for (int i = 0; i < 4; ++i) {
-			mbar_init(&vn_full[i], 1);
-		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	if (warp == 1) {
@@ -157,11 +150,6 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 					if (kp == 0) {
 						TQ_TRACE(10, (t - cid) / ncl);
 					}
-					if (kp == 0) {  // the 64 row norms of this tile ride along (own barrier, own CTA only): no epilogue thread ever waits
-						const uint32_t slot = ((t - cid) / ncl) & 3u;  // on a plain global load under a saturated HBM
-						mbar_expect_tx(&vn_full[slot], kTqTileRows * 4);
-						bulk_load(s_vn + slot * kTqTileRows, a.vnorm + size_t(t) * kTqTileRows, kTqTileRows * 4, &vn_full[slot]);
-					}
 					mbar_expect_tx(&full_bar[stage], nsub * kTqSubBytes);
 					unsigned char* dst = s_rows + size_t(stage) * kTqStageBytes;
 					const unsigned char* src = tile_src + size_t(kTqSubsPerStage * kp) * kTqSubBytes;
@@ -190,35 +178,28 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 			mbar_wait(q_ready, 0);
 			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 			const uint32_t tmem_d = tmem_base + kTqAccCol0 + parity * kTqTileRows;
-			// The two issuers alternate tile by tile.  Each first waits for everything its tile needs (accumulator drained, all
-			// stages landed), THEN takes the issue token, pushes its 48 MMAs + commits into the tensor queue back to back and passes
-			// the token on: MMAs of different accumulators must not interleave in the queue (an accumulator switch between two MMAs
-			// costs a TMEM round trip of the 32 KB tile), and the mbarrier wake-up latencies stay off the issue path.
-			uint32_t n_mine = 0;
-			for (uint32_t it = parity, t = cid + parity * ncl; t < ntiles; it += 2, t += 2 * ncl, ++n_mine) {
+			for (uint32_t it = parity, t = cid + parity * ncl; t < ntiles; it += 2, t += 2 * ncl) {
 				TQ_TRACE(0, it);
 				mbar_wait(&acc_empty[parity], ((it >> 1) & 1) ^ 1);
+				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 				TQ_TRACE(1, it);
 				const uint32_t sidx0 = it * kpairs;  // stages are consumed in tile order by the two issuers alternately
 				for (uint32_t kp = 0; kp < kpairs; ++kp) {
 					const uint32_t sidx = sidx0 + kp;
-					mbar_wait(&full_bar[sidx % a.stages], (sidx / a.stages) & 1);
-				}
-				TQ_TRACE(2, it);
-				if (it > 0) {  // token: the other issuer finished issuing tile it - 1 (its (it-1)/2-th arrive on my turn barrier)
-					mbar_wait(&turn[parity], ((it - 1) >> 1) & 1);
-				}
-				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-				for (uint32_t kp = 0; kp < kpairs; ++kp) {
-					const uint32_t sidx = sidx0 + kp;
-					const uint32_t stage = sidx % a.stages;
+					const uint32_t stage = sidx % a.stages, phase = (sidx / a.stages) & 1;
 					const uint32_t nsub = min(uint32_t(kTqSubsPerStage), a.kchunks - kTqSubsPerStage * kp);
+					mbar_wait(&full_bar[stage], phase);
+					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+					if (kp == 0) {
+						TQ_TRACE(2, it);
+					}
 					const uint32_t b_addr = smem_u32(s_rows + size_t(stage) * kTqStageBytes);
 					for (uint32_t sub = 0; sub < nsub; ++sub) {
 #pragma unroll
 						for (uint32_t k = 0; k < kTcChunkK / 16; ++k) {  // K = 16 bf16 = 8 TMEM columns of A, 32 bytes of the B swizzle row
 							umma_bf16_ts(tmem_d, tmem_base + ((kTqSubsPerStage * kp + sub) * 4 + k) * 8,
-										 umma_desc_sw128(b_addr + sub * kTqSubBytes + k * 32), idesc, (kp | sub | k) != 0);
+										 umma_desc_sw128(b_addr + sub * kTqSubBytes + k * 32),
+										 idesc, (kp | sub | k) != 0);
 						}
 					}
 					if constexpr (kCluster > 1) {
@@ -228,13 +209,13 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 					}
 				}
 				umma_commit(&acc_full[parity]);
-				mbar_arrive(&turn[parity ^ 1]);
 				TQ_TRACE(3, it);
 			}
 		}
 	} else {
 		// ===== epilogue warps 2..5: thread = query (TMEM lane quadrant = warp % 4) =====
 		const uint32_t quad = warp & 3;
+		const uint32_t et = threadIdx.x - 64;              // 0..127 inside the epilogue group
 		const uint32_t my_q = q0 + quad * 32 + lane;       // global query index of this TMEM lane
 		const bool q_ok = my_q < a.nq_total;
 		// 1. my query -> TMEM (A operand): 32 columns (64 bf16) per store
@@ -262,14 +243,34 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 		const float qe = q_ok ? kTcErrCoef * a.qnorm[my_q] : 0.f;
 		float tau = q_ok ? ord_float(a.tau[my_q]) : -INFINITY;
 		float2 pr = q_ok ? tc_make_pr(a.metric, tau, qe) : make_float2(0.f, INFINITY);
-		// Nothing in this loop may wait on a plain global load: under a saturated HBM such a load takes many microseconds, the
-		// accumulator is then released late and the tensor pipe idles.  Row norms arrive by bulk copy (vn_full), and the shared
-		// threshold is re-read only every 8th tile with the load issued 8 tiles earlier.
+		// per-row terms (||v||, w): global loads are issued ONE TILE AHEAD of the shared-memory store that consumes them, so their
+		// HBM latency overlaps a whole tile of work instead of stalling the epilogue (same for the tau refresh)
+		auto fetch_vn = [&](uint32_t t) -> float {
+			const uint32_t row = t * kTqTileRows + et;
+			return (et < kTqTileRows && t < ntiles && row < a.n) ? a.vnorm[row] : 0.f;
+		};
+		auto store_vw = [&](float vn, uint32_t buf) {
+			if (et < kTqTileRows) {
+				const float w = a.metric == kL2 ? 0.5f * (1.f - kTcL2Eps) * vn * vn : 0.f;
+				s_vw[buf * kTqTileRows + et] = make_float2(fmaxf(vn, 1e-30f), w);
+			}
+		};
+		// Under a saturated HBM a plain global load takes many microseconds (queueing behind the bulk copies), and a stall here delays
+		// the release of the accumulator and idles the tensor pipe.  So the per-row norms are fetched FOUR tiles before the tile that
+		// consumes them (register queue), and the shared threshold is re-read only every 8th tile, issued 8 tiles earlier.
+		store_vw(fetch_vn(cid), 0);
+		float vq0 = fetch_vn(cid + ncl), vq1 = fetch_vn(cid + 2 * ncl), vq2 = fetch_vn(cid + 3 * ncl), vq3 = fetch_vn(cid + 4 * ncl);
 		unsigned int tau_ahead = q_ok ? a.tau[my_q] : 0u;
+		asm volatile("bar.sync 1, 128;" ::: "memory");
 		uint32_t it = 0;
 		for (uint32_t t = cid; t < ntiles; t += ncl, ++it) {
 			const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
 			const uint32_t rows_valid = min(uint32_t(kTqTileRows), a.n - t * kTqTileRows);
+			store_vw(vq0, acc ^ 1);  // tile t + ncl, loaded four tiles ago
+			vq0 = vq1;
+			vq1 = vq2;
+			vq2 = vq3;
+			vq3 = fetch_vn(t + 5 * ncl);
 			if ((it & 7u) == 7u && q_ok) {
 				const float tn = ord_float(tau_ahead);
 				if (tn < tau) {
@@ -280,19 +281,6 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 			}
 			if (threadIdx.x == 64) {
 				TQ_TRACE(4, it);
-			}
-			mbar_wait(&vn_full[it & 3u], (it >> 2) & 1u);
-			float vn[kTqTileRows];
-			{
-				const float4* p = reinterpret_cast<const float4*>(s_vn + (it & 3u) * kTqTileRows);
-#pragma unroll
-				for (int i = 0; i < kTqTileRows / 4; ++i) {
-					const float4 x = p[i];
-					vn[4 * i] = fmaxf(x.x, 1e-30f);
-					vn[4 * i + 1] = fmaxf(x.y, 1e-30f);
-					vn[4 * i + 2] = fmaxf(x.z, 1e-30f);
-					vn[4 * i + 3] = fmaxf(x.w, 1e-30f);
-				}
 			}
 			mbar_wait(&acc_full[acc], acc_phase);
 			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -313,7 +301,6 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 			if (threadIdx.x == 64) {
 				TQ_TRACE(6, it);
 			}
-			const float wcoef = a.metric == kL2 ? 0.5f * (1.f - kTcL2Eps) : 0.f;
 #pragma unroll
 			for (uint32_t ch = 0; ch < 2; ++ch) {
 				const uint32_t c0 = ch * 32;
@@ -321,8 +308,8 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 				uint32_t hits = 0;
 #pragma unroll
 				for (int j = 0; j < 32; ++j) {
-					const float x = vn[c0 + j];
-					hits |= uint32_t(fmaf(-wcoef * x, x, __uint_as_float(v[j])) >= fmaf(pr.x, x, pr.y)) << j;
+					const float2 vw = s_vw[acc * kTqTileRows + c0 + j];
+					hits |= uint32_t(__uint_as_float(v[j]) - vw.y >= fmaf(pr.x, vw.x, pr.y)) << j;
 				}
 				const uint32_t nv = rows_valid > c0 ? min(32u, rows_valid - c0) : 0u;
 				hits &= nv >= 32 ? 0xFFFFFFFFu : ((1u << nv) - 1u);
@@ -335,19 +322,19 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 						}
 						const uint32_t row = t * kTqTileRows + c0 + j;
 						const float s = __uint_as_float(v[j]);
-						const float vnr = vn[c0 + j];
+						const float vn = s_vw[acc * kTqTileRows + c0 + j].x;
 						float d, e;
 						if (a.metric == kL2) {
 							const float qn = qe * (1.f / kTcErrCoef);
-							d = fmaf(-2.f, s, fmaf(qn, qn, vnr * vnr));
-							e = 2.f * qe * vnr + kTcL2Eps * (qn * qn + vnr * vnr);
+							d = fmaf(-2.f, s, fmaf(qn, qn, vn * vn));
+							e = 2.f * qe * vn + kTcL2Eps * (qn * qn + vn * vn);
 						} else if (a.metric == kCos) {
-							const float vinv = 1.f / vnr;  // within 1e-5 of the stored coefficient (normalize.cc shortcut), covered by the slack
+							const float vinv = 1.f / vn;  // within 1e-5 of the stored coefficient (normalize.cc shortcut), inside the slack
 							d = -s * vinv;
 							e = qe * 1.0001f;
 						} else {
 							d = -s;
-							e = qe * vnr;
+							e = qe * vn;
 						}
 						const unsigned pos = atomicAdd(&a.cand_count[my_q], 1u);
 						if (pos < a.cand_cap) {
@@ -389,9 +376,12 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 			}
 			if (threadIdx.x == 64) {
 				TQ_TRACE(7, it);
+			}
+			__syncwarp();  // the rare path diverges (per-lane lock loops): reconverge before the .aligned ops below and of the next tile
+			asm volatile("bar.sync 1, 128;" ::: "memory");  // s_vw[acc ^ 1] written by everyone before the next tile reads it
+			if (threadIdx.x == 64) {
 				TQ_TRACE(8, it);
 			}
-			__syncwarp();  // the rare path diverges (per-lane lock loops): reconverge before the .aligned tcgen05 ops of the next tile
 		}
 	}
 	__syncthreads();
