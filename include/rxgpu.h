@@ -253,7 +253,7 @@ void rxgpu_last_search_stats(rxgpu_search_stats* out);
 /* large query batches: bf16 tensor-core filter + exact fp32 re-rank (results identical to the exact scan).
  * mode 0 = automatic (batches >= 64 queries on >= 100k rows, k <= 15), 1 = whenever possible, 2 = never;
  * 3..6 force kernel variants for tests/benchmarks: 3 / 4 = first-generation kernel (queries in shared memory) with 1 CTA / a CTA
- * pair per row tile, 5 / 6 = second-generation kernel (queries in TMEM) limited to clusters of 1 / 2 CTAs */
+ * pair per row tile, 5 / 6 = second-generation kernel (queries in TMEM) with clusters of 1 / up to 4 CTAs (default: CTA pairs) */
 int rxgpu_set_tensor_core_filter(rxgpu_index*, int mode);
 /* process-wide switch: bracket every scan-kernel launch with CUDA events (used by bench.py for the roofline figure) */
 int rxgpu_set_profile(int on);

@@ -302,10 +302,11 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 		RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
 		RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
 		RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+		// measured on B200 (10M x 768, 1024 queries): CTA pairs 20.4 ms, clusters of four 21.9 ms, single CTAs 25.5 ms per batch --
+		// the pass is bound by the per-SM turn-around of the two TMEM accumulators, not by HBM, so pairs are the default
+		const uint32_t clusterMax = ix->tc_cluster_max ? ix->tc_cluster_max : 2u;
 		int cluster = qblocks >= 3 ? 4 : (qblocks == 2 ? 2 : 1);
-		if (ix->tc_cluster_max && cluster > int(ix->tc_cluster_max)) {
-			cluster = int(ix->tc_cluster_max);
-		}
+		cluster = std::min<int>(cluster, int(clusterMax));
 		const uint32_t qtiles = uint32_t((ix->size + kTqTileRows - 1) / kTqTileRows);
 		unsigned grid = 0;
 		for (;;) {  // how many clusters of this size can be resident at once (GPC boundaries strand SMs for size 4)
@@ -879,7 +880,7 @@ int rxgpu_set_tensor_core_filter(rxgpu_index* ix, int mode) {
 	}
 	ix->tc_mode = uint32_t(mode >= 3 ? 1 : mode);
 	ix->tc_variant = (mode == 3 || mode == 4) ? uint32_t(mode) : 0u;
-	ix->tc_cluster_max = mode == 5 ? 1u : (mode == 6 ? 2u : 0u);
+	ix->tc_cluster_max = mode == 5 ? 1u : (mode == 6 ? 4u : 0u);
 	return 0;
 }
 int rxgpu_set_profile(int on) {

@@ -255,23 +255,18 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 				s_vw[buf * kTqTileRows + et] = make_float2(fmaxf(vn, 1e-30f), w);
 			}
 		};
-		// Under a saturated HBM a plain global load takes many microseconds (queueing behind the bulk copies), and a stall here delays
-		// the release of the accumulator and idles the tensor pipe.  So the per-row norms are fetched FOUR tiles before the tile that
-		// consumes them (register queue), and the shared threshold is re-read only every 8th tile, issued 8 tiles earlier.
 		store_vw(fetch_vn(cid), 0);
-		float vq0 = fetch_vn(cid + ncl), vq1 = fetch_vn(cid + 2 * ncl), vq2 = fetch_vn(cid + 3 * ncl), vq3 = fetch_vn(cid + 4 * ncl);
+		float vn_ahead = fetch_vn(cid + ncl);            // for the tile after the first
 		unsigned int tau_ahead = q_ok ? a.tau[my_q] : 0u;
 		asm volatile("bar.sync 1, 128;" ::: "memory");
 		uint32_t it = 0;
 		for (uint32_t t = cid; t < ntiles; t += ncl, ++it) {
 			const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
 			const uint32_t rows_valid = min(uint32_t(kTqTileRows), a.n - t * kTqTileRows);
-			store_vw(vq0, acc ^ 1);  // tile t + ncl, loaded four tiles ago
-			vq0 = vq1;
-			vq1 = vq2;
-			vq2 = vq3;
-			vq3 = fetch_vn(t + 5 * ncl);
-			if ((it & 7u) == 7u && q_ok) {
+			// consume what was fetched during the previous tile, then fetch for the one after next
+			store_vw(vn_ahead, acc ^ 1);
+			vn_ahead = fetch_vn(t + 2 * ncl);
+			if (q_ok) {
 				const float tn = ord_float(tau_ahead);
 				if (tn < tau) {
 					tau = tn;
@@ -377,7 +372,7 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 			if (threadIdx.x == 64) {
 				TQ_TRACE(7, it);
 			}
-			__syncwarp();  // the rare path diverges (per-lane lock loops): reconverge before the .aligned ops below and of the next tile
+			__syncwarp();  // the rare path diverges (per-lane lock loops): reconverge before the .aligned tcgen05 ops of the next tile
 			asm volatile("bar.sync 1, 128;" ::: "memory");  // s_vw[acc ^ 1] written by everyone before the next tile reads it
 			if (threadIdx.x == 64) {
 				TQ_TRACE(8, it);
