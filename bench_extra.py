@@ -1,0 +1,140 @@
+#!/usr/bin/env python
+"""Measurements of the other two hot-path rows (not the driver's bench line; see bench.py for that):
+
+  python bench_extra.py hnsw [--rows 500000]   BASELINE configs[2] shape: HNSW M=16 efC=200, 768-dim, Cosine, ef=128, k=10
+  python bench_extra.py ft   [--docs 50000000] BASELINE configs[3]: ft_fast BM25, 3-term OR (df 10% / 1% / 0.1%), top-100
+
+Each prints one JSON line with our device number, the reference's own CPU code timed on this box (oracle/_ref) and the
+algorithmic-bytes roofline figure of SURVEY.md §8d.  The HNSW graph is built by the reference's CPU code (multithreaded insert);
+building 10M x 768 takes hours, so the default is 500k rows -- stated in the output.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return (json.load(open(p))["hbm_gbs"], "measured") if os.path.exists(p) else (6650.0, "fallback")
+
+
+def lowrank(seed, n, dim, latent=32, noise=0.05):
+    a = np.random.default_rng(99).normal(0, 1.0, size=(latent, dim)).astype(np.float32)
+    rng = np.random.default_rng(seed)
+    out = np.empty((n, dim), np.float32)
+    for i in range(0, n, 100000):
+        m = min(100000, n - i)
+        out[i:i + m] = rng.normal(0, 1, size=(m, latent)).astype(np.float32) @ a + rng.normal(0, noise, size=(m, dim)).astype(np.float32)
+    return out
+
+
+def run_hnsw(args):
+    import reindexer_b200 as rx
+    from oracle import oracle as O
+
+    n, dim, k, ef, nq = args.rows, 768, 10, 128, args.queries
+    threads = os.cpu_count() or 1
+    vecs, labels = lowrank(1, n, dim), O.row_labels(n)
+    t0 = time.perf_counter()
+    ref = O.RefHnsw(O.COS, dim, n, M=16, ef_construction=200, seed=100, multithread=True)
+    ref.add_batch(labels, vecs, threads=threads)
+    build_s = time.perf_counter() - t0
+    g = ref.export(with_vectors=False)
+    gpu = rx.GpuBruteforceSearch(rx.COS, dim, n)  # multithreaded insert: internal id != insertion order, so rows follow the graph
+    gpu.add_points(g["labels"], vecs[(g["labels"] >> np.uint64(32)).astype(np.int64)])  # row i of the index = internal id i
+    gpu.hnsw_import(g)
+    queries = np.stack([O.normalize_copy(q)[0] for q in lowrank(2, nq, dim)])
+    gpu.hnsw_search_knn(queries[:64], k, ef)  # warm-up
+    reps = 5
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        d, l, c, st = gpu.hnsw_search_knn(queries, k, ef, with_stats=True)
+    gpu_s = (time.perf_counter() - t0) / reps
+    t0 = time.perf_counter()
+    dr, lr, cr = ref.search_knn_batch(queries, k, ef, threads=threads)
+    cpu_s = time.perf_counter() - t0
+    db, lb, _ = gpu.search_knn(queries[:512], k)
+    rec_gpu = float(np.mean([len(set(l[i]) & set(lb[i])) / k for i in range(512)]))
+    rec_ref = float(np.mean([len(set(lr[i]) & set(lb[i])) / k for i in range(512)]))
+    same = float(np.mean([(l[i] == lr[i]).all() for i in range(nq)]))
+    ndist, nhops = float(st[:, 0].mean()), float(st[:, 1].mean())
+    bytes_per_query = ndist * (dim * 4 + 4) + nhops * (4 + 8 * 16)
+    peak, src = peak_hbm()
+    print(json.dumps({
+        "workload": f"HNSW float_vector, {n} x {dim} fp32, cosine, M=16 efC=200, ef_search={ef}, k={k}, batch={nq} (BASELINE configs[2] shape; "
+                    f"10M rows would need hours of CPU graph build)",
+        "qps_gpu_e2e": nq / gpu_s, "qps_reference_cpu": nq / cpu_s, "cpu_threads": threads, "speedup": cpu_s / gpu_s,
+        "recall_at_10_gpu": rec_gpu, "recall_at_10_reference": rec_ref, "identical_top10_fraction": same,
+        "dist_evals_per_query": ndist, "hops_per_query": nhops, "algorithmic_bytes_per_query": bytes_per_query,
+        "roofline": {"bound": "hbm (random 3 KB row gathers)", "achieved": bytes_per_query * nq / gpu_s / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": bytes_per_query * nq / gpu_s / 1e9 / peak, "peak_source": src},
+        "graph_build_s_reference_cpu": build_s, "data": "synthetic low-rank (latent 32) vectors"}))
+
+
+def run_ft(args):
+    import reindexer_b200 as rx
+    from ft_helpers import assert_same_merge
+
+    from oracle import ft_oracle as F
+
+    total = args.docs + 1
+    rng = np.random.default_rng(7)
+    words = (rng.poisson(100, size=total).astype(np.uint32) + 1).reshape(-1, 1)
+    words[0] = 0
+    p = F.FtProblem(total, words)
+    npost = 0
+    for df in (0.10, 0.01, 0.001):
+        nd = int(df * args.docs)
+        docs = np.unique(rng.integers(1, total, size=int(nd * 1.06), dtype=np.int64))[:nd].astype(np.uint32)
+        npos = rng.integers(1, 4, size=len(docs)).astype(np.uint32)
+        begin = np.concatenate([[0], np.cumsum(npos, dtype=np.int64)]).astype(np.uint32)
+        first = (rng.random(len(docs)) * np.minimum(words[docs, 0], 60)).astype(np.uint32)
+        pos = np.repeat(first, npos) + (np.arange(begin[-1], dtype=np.uint32) - np.repeat(begin[:-1], npos)) * 2  # ascending inside a doc
+        p.add_term([(p.add_list_arrays(docs, begin, pos), 100.0)], op=F.OP_OR)
+        npost += len(docs)
+    ft = rx.GpuFtIndex(total, p.words, p.avg)
+    ids = [ft.add_postings(d, b, q) for d, b, q in p.lists]
+    terms = [dict(t, postings=[ids[int(x)] for x in t["postings"]]) for t in p.terms]
+    res = ft.merge(p.cfg, p.field_cfg, terms)  # warm-up (allocates scratch)
+    reps = 5
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(reps):
+        res = ft.merge(p.cfg, p.field_cfg, terms)
+        dev_ms += ft.last_stats()["device_ms"]
+    gpu_s = (time.perf_counter() - t0) / reps
+    st = ft.last_stats()
+    ref_res, ref_ns = F.ref_merge(p) if F.ref_available() else F.port_merge(p)
+    assert_same_merge(ref_res, res, F.RANK_AND_ID)
+    top_gpu, top_ref = F.after_select_order(res)[:100], F.after_select_order(ref_res)[:100]
+    assert (top_gpu == top_ref).all()
+    peak, src = peak_hbm()
+    print(json.dumps({
+        "workload": f"ft_fast BM25 merge, {args.docs} docs, 3-term OR (df 10% / 1% / 0.1% = {npost} postings), merge_limit 20000, top-100 "
+                    f"(BASELINE configs[3])",
+        "queries_per_s_gpu_e2e": 1.0 / gpu_s, "ms_per_query_gpu_e2e": gpu_s * 1e3, "ms_per_query_gpu_device": dev_ms / reps,
+        "ms_per_query_reference_cpu_merge_only": ref_ns / 1e6, "cpu_threads": 1, "speedup_vs_reference_merge": ref_ns / 1e9 / gpu_s,
+        "merged_docs": int(len(res)), "preselected": st["preselected"], "launches": st["launches"], "postings_scanned": st["postings_scanned"],
+        "identical_to_reference": True,
+        "roofline": {"bound": "hbm (posting streams + per-document gathers)", "achieved": st["algorithmic_bytes"] / (dev_ms / reps * 1e-3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": st["algorithmic_bytes"] / (dev_ms / reps * 1e-3) / 1e9 / peak, "peak_source": src,
+                     "algorithmic_bytes": st["algorithmic_bytes"]},
+        "data": "synthetic postings, Poisson(100) document lengths"}))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", choices=["hnsw", "ft"])
+    ap.add_argument("--rows", type=int, default=500000)
+    ap.add_argument("--queries", type=int, default=4096)
+    ap.add_argument("--docs", type=int, default=50_000_000)
+    a = ap.parse_args()
+    run_hnsw(a) if a.what == "hnsw" else run_ft(a)
