@@ -162,6 +162,14 @@ int rxgpu_hnsw_search_knn(const rxgpu_index*, uint32_t nq, const float* queries 
 int rxgpu_hnsw_search_knn_device(const rxgpu_index*, uint32_t nq, const float* d_queries, uint32_t k, uint32_t ef, float* d_out_dist,
 								 uint32_t* d_out_idx, uint32_t* d_out_count, uint32_t* d_stats /* nq x 2 or NULL */, void* stream);
 
+/* HierarchicalNSWImpl::SearchRange                              hnswlib/hnswalg.h:2015-2070
+ * The ef-search result seeds a breadth-first expansion over level-0 neighbours with dist < radius (strict); the result is that
+ * closure (independent of traversal order).  Writes the best min(*out_n, max_out) results best-first (ties by label);
+ * *out_n = total number of matches.  Query pre-normalised for Cosine, radius in map space (IP / Cosine: negated by the caller,
+ * hnsw_index.cc:185).  ef == 0 is treated as 1. */
+int rxgpu_hnsw_search_range(const rxgpu_index*, const float* query /* host */, float radius, uint32_t ef, uint64_t max_out,
+							float* out_dist, uint64_t* out_label, uint64_t* out_n);
+
 /* ---------------------------------------------------------------- ft_fast full-text merge (BM25 scoring over posting lists)
  * Replaces ft::Merger<IdCont, ft::MergeData, OffsetT>::Merge<Bm25Rx|Bm25Classic|TermCount>  core/ft/ft_fast/mergerimpl.h:466-566
  * -- the seam is Selector<IdCont>::mergeResults (ft_fast/selecterimpl.h:609-627) -- for query parts that are plain terms

@@ -123,6 +123,8 @@ def ref_knn_lib():
         lib.ref_hnsw_add_batch.argtypes = [C.c_void_p, C.c_size_t, _u64p, _f32p, C.c_int]
         lib.ref_hnsw_search_knn.restype = C.c_int64
         lib.ref_hnsw_search_knn.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, C.c_size_t, C.c_size_t, _f32p, _u64p]
+        lib.ref_hnsw_search_range.restype = C.c_int64
+        lib.ref_hnsw_search_range.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, C.c_float, C.c_size_t, C.c_size_t, _f32p, _u64p]
         lib.ref_hnsw_search_knn_batch.argtypes = [C.c_void_p, C.c_uint32, _f32p, _f32p, C.c_size_t, C.c_size_t, C.c_int, _f32p,
                                                   _u64p, _u32p]
         lib.ref_hnsw_search_metrics.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, C.c_size_t, _i64p, _i64p]
@@ -365,6 +367,17 @@ class RefHnsw:
                                          _p(l, _u64p))
         assert n >= 0, self.lib.ref_last_error().decode()
         return d[:n].copy(), l[:n].copy()
+
+    def search_range(self, q, radius, ef, qnorm=None, max_out=None):
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        max_out = self.size() if max_out is None else max_out
+        d = np.empty(max(max_out, 1), np.float32)
+        l = np.empty(max(max_out, 1), np.uint64)
+        n = self.lib.ref_hnsw_search_range(self.h, _p(q, _f32p), int(qnorm is not None), float(qnorm or 0.0), float(radius), ef, max_out,
+                                           _p(d, _f32p), _p(l, _u64p))
+        assert n >= 0, self.lib.ref_last_error().decode()
+        m = min(n, max_out)
+        return d[:m].copy(), l[:m].copy(), n
 
     def search_knn_batch(self, queries, k, ef=0, threads=1):
         queries = np.ascontiguousarray(queries, dtype=np.float32)

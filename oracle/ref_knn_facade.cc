@@ -277,6 +277,19 @@ int64_t ref_hnsw_search_knn(const void* hv, const float* query, int has_norm, fl
 	});
 	return n;
 }
+// HierarchicalNSWImpl::SearchRange (hnswalg.h:2015-2070): ef-search seed, then BFS over neighbours with dist < radius
+int64_t ref_hnsw_search_range(const void* hv, const float* query, int has_norm, float qnorm, float radius, size_t ef, size_t maxOut,
+							  float* dists, uint64_t* labels) {
+	int64_t n = -1;
+	auto* h = const_cast<HnswHandle*>(static_cast<const HnswHandle*>(hv));
+	guarded([&] {
+		withHnsw(h, [&](auto& g) {
+			auto q = g.SearchRange(query, has_norm ? std::optional<float>(qnorm) : std::nullopt, radius, ef);
+			n = int64_t(drain(q, maxOut, dists, labels));
+		});
+	});
+	return n;
+}
 int ref_hnsw_search_knn_batch(const void* hv, uint32_t nq, const float* queries, const float* qnorms, size_t k, size_t ef, int threads,
 							  float* dists, uint64_t* labels, uint32_t* counts) {
 	auto* h = const_cast<HnswHandle*>(static_cast<const HnswHandle*>(hv));

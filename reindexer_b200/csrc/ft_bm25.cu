@@ -27,6 +27,7 @@ using namespace rxgpu;
 namespace {
 
 constexpr int kFtThreads = 256;
+constexpr uint32_t kNoSlot = 0xFFFFFFFFu;  // idoffsets_ entry of a document that is not in the merge yet
 constexpr int kMaxFtFields = 64;  // kMaxFtCompositeFields = 63 (ft/idrelset.h:11)
 
 struct DevList {
@@ -240,35 +241,227 @@ __global__ void ft_score_pass(DevList l, TermParams t, int all_same, const uint3
 		}
 	}
 }
-// zero scores outside the mask / of removed docs and build the 65536-bin histogram (mergerimpl.h:416-423)
-__global__ void ft_hist(uint16_t* score, const uint32_t* mask, const uint8_t* removed, uint32_t total_docs, unsigned long long* hist) {
-	for (uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; d < total_docs; d += gridDim.x * blockDim.x) {
-		uint16_t s = score[d];
-		if (!(mask[d >> 5] & (1u << (d & 31))) || (removed && removed[d])) {
-			s = 0;
-			score[d] = 0;
+// ---- preselect, per-document passes.  A thread owns one mask word = 32 consecutive documents (64 bytes of u16 scores as four
+// 128-bit loads); the score array is padded to a whole number of mask words.
+struct Scores32 {
+	uint32_t w[16];
+	__device__ __forceinline__ uint32_t at(int i) const { return (w[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu; }
+	__device__ __forceinline__ bool any() const {
+		uint32_t o = 0;
+#pragma unroll
+		for (int i = 0; i < 16; ++i) {
+			o |= w[i];
 		}
-		if (s) {
-			atomicAdd(&hist[s], 1ull);
+		return o != 0;
+	}
+};
+__device__ __forceinline__ Scores32 load_scores32(const uint16_t* score, uint32_t word) {
+	const uint4* p = reinterpret_cast<const uint4*>(score + size_t(word) * 32);
+	Scores32 r;
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		const uint4 v = __ldg(p + j);
+		r.w[j * 4 + 0] = v.x;
+		r.w[j * 4 + 1] = v.y;
+		r.w[j * 4 + 2] = v.z;
+		r.w[j * 4 + 3] = v.w;
+	}
+	return r;
+}
+// zero scores outside the mask / of removed docs and build the 65536-bin histogram (mergerimpl.h:416-423).  Scores cluster on a
+// handful of values (sums of a few subterm procs), so the histogram is privatised: a persistent grid keeps the low 8192 bins in
+// shared memory and flushes them once; only scores >= 8192 go to the global bins directly.
+constexpr uint32_t kFtHistSmemBins = 8192;
+__global__ void __launch_bounds__(kFtThreads) ft_hist(uint16_t* score, const uint32_t* mask, const uint8_t* removed, uint32_t words,
+													  unsigned long long* hist) {
+	__shared__ uint32_t s_hist[kFtHistSmemBins];
+	for (uint32_t i = threadIdx.x; i < kFtHistSmemBins; i += blockDim.x) {
+		s_hist[i] = 0;
+	}
+	__syncthreads();
+	for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += gridDim.x * blockDim.x) {
+		const Scores32 sc = load_scores32(score, w);
+		if (!sc.any()) {
+			continue;
+		}
+		const uint32_t m = mask[w];
+#pragma unroll
+		for (int i = 0; i < 32; ++i) {
+			const uint32_t s = sc.at(i);
+			if (s) {
+				const uint32_t d = w * 32u + i;
+				if (!((m >> i) & 1u) || (removed && removed[d])) {
+					score[d] = 0;
+				} else if (s < kFtHistSmemBins) {
+					atomicAdd(&s_hist[s], 1u);
+				} else {
+					atomicAdd(&hist[s], 1ull);
+				}
+			}
+		}
+	}
+	__syncthreads();
+	for (uint32_t i = threadIdx.x; i < kFtHistSmemBins; i += blockDim.x) {
+		if (s_hist[i]) {
+			atomicAdd(&hist[i], (unsigned long long)s_hist[i]);
 		}
 	}
 }
-// ordered cut at the threshold score: keep score > min, and the first `budget` docs (ascending id) with score == min (:448-462)
-__global__ void ft_thresh_count(const uint16_t* score, const uint32_t* mask, uint32_t total_docs, uint32_t min_score, uint32_t* block_counts) {
+// threshold of the counting sort (mergerimpl.h:425-446), on the device so the merge does not stop for the host:
+//   A(sc) = number of docs with score > sc;  minScore = the smallest sc >= 1 with A(sc) < maxMerged (sc = 65535 always qualifies);
+//   minScoreDocs = maxMerged - A(minScore).   thr[0] = minScore, thr[1] = minScoreDocs.  One block of 1024 threads, 64 bins each.
+__global__ void __launch_bounds__(1024) ft_pick_threshold(const unsigned long long* hist, uint32_t max_merged, uint32_t* thr) {
+	__shared__ unsigned long long s_tot[1024];
+	__shared__ uint32_t s_min;
+	const uint32_t t = threadIdx.x;
+	unsigned long long mine = 0;
+	for (uint32_t i = 0; i < 64; ++i) {
+		mine += hist[t * 64 + i];
+	}
+	s_tot[t] = mine;
+	if (t == 0) {
+		s_min = 65535;
+	}
+	__syncthreads();
+	unsigned long long above = 0;  // docs in the bins of all higher threads
+	for (uint32_t u = t + 1; u < 1024; ++u) {
+		above += s_tot[u];
+	}
+	unsigned long long a = above;
+	uint32_t local = 0xFFFFFFFFu;
+	for (int sc = int(t * 64 + 63); sc >= int(t * 64); --sc) {
+		if (sc >= 1 && a < max_merged) {
+			local = uint32_t(sc);
+		}
+		a += hist[sc];
+	}
+	if (local != 0xFFFFFFFFu) {
+		atomicMin(&s_min, local);
+	}
+	__syncthreads();
+	const uint32_t ms = s_min;
+	if (ms / 64 == t) {
+		a = above;
+		for (int sc = int(t * 64 + 63); sc > int(ms); --sc) {
+			a += hist[sc];
+		}
+		thr[0] = ms;
+		thr[1] = uint32_t(max_merged - a);
+	}
+}
+// ordered cut at the threshold score: keep score > min, and the first `budget` docs (ascending id) with score == min (:448-462).
+// Block b owns a contiguous chunk of mask words: pass 1 counts its threshold docs, pass 2 ranks them behind the earlier blocks.
+__device__ __forceinline__ uint32_t ft_chunk_words(uint32_t words) {
+	const uint32_t per = (words + gridDim.x - 1) / gridDim.x;
+	return (per + kFtThreads - 1) / kFtThreads * kFtThreads;
+}
+__device__ __forceinline__ void ft_classify(const Scores32& sc, uint32_t m, uint32_t min_score, uint32_t& eq, uint32_t& gt) {
+	eq = gt = 0;
+#pragma unroll
+	for (int i = 0; i < 32; ++i) {
+		const uint32_t s = sc.at(i);
+		eq |= uint32_t(s == min_score) << i;
+		gt |= uint32_t(s > min_score) << i;
+	}
+	eq &= m;
+	gt &= m;
+}
+__global__ void __launch_bounds__(kFtThreads) ft_thresh_count(const uint16_t* score, const uint32_t* mask, uint32_t words, const uint32_t* thr,
+															  uint32_t* block_counts) {
 	__shared__ uint32_t s_cnt;
 	if (threadIdx.x == 0) {
 		s_cnt = 0;
 	}
 	__syncthreads();
-	const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
-	const bool eq = d < total_docs && (mask[d >> 5] & (1u << (d & 31))) && score[d] == min_score;
-	const unsigned m = __ballot_sync(0xffffffffu, eq);
-	if ((threadIdx.x & 31) == 0 && m) {
-		atomicAdd(&s_cnt, __popc(m));
+	const uint32_t min_score = thr[0];
+	const uint32_t chunk = ft_chunk_words(words);
+	const uint32_t begin = blockIdx.x * chunk, end = min(words, begin + chunk);
+	uint32_t cnt = 0;
+	for (uint32_t w = begin + threadIdx.x; w < end; w += blockDim.x) {
+		const uint32_t m = mask[w];
+		if (m) {
+			uint32_t eq, gt;
+			ft_classify(load_scores32(score, w), m, min_score, eq, gt);
+			cnt += __popc(eq);
+		}
+	}
+	for (int off = 16; off > 0; off >>= 1) {
+		cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+	}
+	if ((threadIdx.x & 31) == 0 && cnt) {
+		atomicAdd(&s_cnt, cnt);
 	}
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		block_counts[blockIdx.x] = s_cnt;
+	}
+}
+__global__ void __launch_bounds__(kFtThreads) ft_thresh_apply(const uint16_t* score, uint32_t* mask, uint32_t words, const uint32_t* thr,
+															  const uint32_t* block_counts) {
+	__shared__ uint32_t s_warp[kFtThreads / 32];
+	__shared__ uint32_t s_base;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t min_score = thr[0], budget = thr[1];
+	{  // threshold docs in the chunks of all earlier blocks
+		uint32_t before = 0;
+		for (uint32_t b = threadIdx.x; b < blockIdx.x; b += blockDim.x) {
+			before += block_counts[b];
+		}
+		for (int off = 16; off > 0; off >>= 1) {
+			before += __shfl_xor_sync(0xffffffffu, before, off);
+		}
+		if (threadIdx.x == 0) {
+			s_base = 0;
+		}
+		__syncthreads();
+		if (lane == 0 && before) {
+			atomicAdd(&s_base, before);
+		}
+		__syncthreads();
+	}
+	uint32_t running = s_base;
+	const uint32_t chunk = ft_chunk_words(words);
+	const uint32_t begin = blockIdx.x * chunk, end = min(words, begin + chunk);
+	for (uint32_t w0 = begin; w0 < end; w0 += blockDim.x) {
+		const uint32_t w = w0 + threadIdx.x;
+		uint32_t m = 0, eq = 0, gt = 0;
+		if (w < end) {
+			m = mask[w];
+			if (m) {
+				ft_classify(load_scores32(score, w), m, min_score, eq, gt);
+			}
+		}
+		// exclusive block scan of popc(eq)
+		const uint32_t cnt = __popc(eq);
+		uint32_t incl = cnt;
+		for (int off = 1; off < 32; off <<= 1) {
+			const uint32_t y = __shfl_up_sync(0xffffffffu, incl, off);
+			if (lane >= off) {
+				incl += y;
+			}
+		}
+		if (lane == 31) {
+			s_warp[warp] = incl;
+		}
+		__syncthreads();
+		uint32_t warp_off = 0, total = 0;
+#pragma unroll
+		for (int x = 0; x < kFtThreads / 32; ++x) {
+			const uint32_t v = s_warp[x];
+			warp_off += x < warp ? v : 0;
+			total += v;
+		}
+		__syncthreads();
+		const uint32_t rank0 = running + warp_off + incl - cnt;
+		uint32_t keep_eq = eq;
+		const uint32_t allowed = budget > rank0 ? budget - rank0 : 0;
+		while (uint32_t(__popc(keep_eq)) > allowed) {  // keep the lowest ids
+			keep_eq &= ~(0x80000000u >> __clz(keep_eq));
+		}
+		if (w < end && m != (gt | keep_eq)) {
+			mask[w] = gt | keep_eq;
+		}
+		running += total;
 	}
 }
 // exclusive scan of block counts, single block (counts <= ~200k entries)
@@ -333,20 +526,6 @@ __device__ __forceinline__ uint32_t block_exclusive_rank(bool flag, uint32_t* s_
 	__syncthreads();
 	return off + __popc(m & ((1u << lane) - 1u));
 }
-__global__ void ft_thresh_apply(const uint16_t* score, uint32_t* mask, uint32_t total_docs, uint32_t min_score, uint32_t budget,
-								const uint32_t* block_offsets) {
-	__shared__ uint32_t s_warp[kFtThreads / 32];
-	const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
-	const bool in = d < total_docs && (mask[d >> 5] & (1u << (d & 31)));
-	const uint32_t s = in ? score[d] : 0;
-	const bool eq = in && s == min_score;
-	const uint32_t rank = block_offsets[blockIdx.x] + block_exclusive_rank(eq, s_warp);
-	const bool keep = in && (s > min_score || (eq && rank < budget));
-	if (in && !keep) {
-		atomicAnd(&mask[d >> 5], ~(1u << (d & 31)));
-	}
-}
-
 // switchToNextWord (merger.h:220-228)
 __global__ void ft_switch(MergeState st) {
 	const uint32_t n = *st.n_docs;
@@ -453,6 +632,12 @@ __global__ void ft_assign(DevList l, MergeState st, int simple, uint32_t max_mer
 		}
 	}
 }
+__global__ void ft_reset_idoff(const int32_t* md_id, const uint32_t* n_docs, uint32_t* idoff) {
+	const uint32_t n = *n_docs;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		idoff[md_id[i]] = kNoSlot;
+	}
+}
 __global__ void ft_bump_count(uint32_t* n_docs, const uint32_t* total_new, uint32_t max_merged) {
 	*n_docs = min(*n_docs + *total_new, max_merged);
 }
@@ -488,6 +673,7 @@ struct rxgpu_ft_index {
 	std::mutex mtx;  // one merge at a time per index (the per-document scratch below is shared)
 	// scratch
 	DevBuf<uint32_t> mask, tmask, idoff, block_counts, scalar_u32;
+	bool idoff_clean = false;  // idoff holds kNoSlot everywhere
 	DevBuf<uint16_t> score;
 	DevBuf<unsigned long long> hist, popc;
 	DevBuf<uint8_t> excluded, tmp_field, md_field;
@@ -697,9 +883,12 @@ int rxgpu_ft_merge(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nter
 	RX_CUDA(cudaEventCreate(&e1));
 	RX_CUDA(cudaEventRecord(e0, st));
 	RX_CUDA(cudaMemsetAsync(ft->scalar_u32.p, 0, 16, st));
-	if (!trivial) {
-		ft_fill_u32<<<gridFor(N, sm), kFtThreads, 0, st>>>(ft->idoff.p, maxMerged, N);
-		g_ft_stats.launches++;
+	if (!trivial) {  // idoffsets_: every merge leaves the table clean again (ft_reset_idoff), so the 4 N byte fill runs only once
+		if (!ft->idoff_clean) {
+			ft_fill_u32<<<gridFor(N, sm), kFtThreads, 0, st>>>(ft->idoff.p, kNoSlot, N);
+			g_ft_stats.launches++;
+		}
+		ft->idoff_clean = false;
 	}
 	ft_mask_init<<<gridFor(mwords, sm), kFtThreads, 0, st>>>(ft->mask.p, d_excluded, N, mwords);
 	g_ft_stats.launches++;
@@ -798,9 +987,9 @@ int rxgpu_ft_merge(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nter
 		if (preselect) {
 			// preselectMostRelevantDocs (mergerimpl.h:386-464)
 			g_ft_stats.preselected = 1;
-			RX_CUDA(ft->score.ensure(N));
+			RX_CUDA(ft->score.ensure(size_t(mwords) * 32));
 			RX_CUDA(ft->hist.ensure(65536));
-			RX_CUDA(cudaMemsetAsync(ft->score.p, 0, size_t(N) * 2, st));
+			RX_CUDA(cudaMemsetAsync(ft->score.p, 0, size_t(mwords) * 64, st));
 			RX_CUDA(cudaMemsetAsync(ft->hist.p, 0, 65536 * 8, st));
 			for (uint32_t t = 0; t < nterms; ++t) {
 				if (terms[t].op == 3) {
@@ -822,28 +1011,15 @@ int rxgpu_ft_merge(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nter
 					}
 				}
 			}
-			ft_hist<<<gridFor(N, sm), kFtThreads, 0, st>>>(ft->score.p, ft->mask.p, ft->has_removed ? ft->removed.p : nullptr, N, ft->hist.p);
-			g_ft_stats.launches++;
-			g_ft_stats.algorithmic_bytes += uint64_t(N) * 2;
-			std::vector<unsigned long long> hist(65536);
-			RX_CUDA(cudaMemcpyAsync(hist.data(), ft->hist.p, 65536 * 8, cudaMemcpyDeviceToHost, st));
-			RX_CUDA(cudaStreamSynchronize(st));
-			size_t minScore = 65535, minScoreDocs = 0, docsTaken = 0;
-			for (size_t sc = 65535; sc > 0; sc--) {
-				if (docsTaken >= maxMerged) {
-					break;
-				}
-				minScore = sc;
-				minScoreDocs = maxMerged - docsTaken;
-				docsTaken += hist[sc];
-			}
-			const unsigned db = (N + kFtThreads - 1) / kFtThreads;
-			ft_thresh_count<<<db, kFtThreads, 0, st>>>(ft->score.p, ft->mask.p, N, uint32_t(minScore), ft->block_counts.p);
-			ft_scan_blocks<<<1, 1024, 0, st>>>(ft->block_counts.p, db, nullptr);
-			ft_thresh_apply<<<db, kFtThreads, 0, st>>>(ft->score.p, ft->mask.p, N, uint32_t(minScore), uint32_t(minScoreDocs),
-													   ft->block_counts.p);
-			g_ft_stats.launches += 3;
-			g_ft_stats.algorithmic_bytes += uint64_t(N) * 4;
+			const unsigned pg = unsigned(sm) * 4;  // persistent grid of the per-document passes
+			uint32_t* d_thr = ft->scalar_u32.p + 2;  // [2] minScore, [3] minScoreDocs
+			RX_CUDA(ft->block_counts.ensure(pg));
+			ft_hist<<<pg, kFtThreads, 0, st>>>(ft->score.p, ft->mask.p, ft->has_removed ? ft->removed.p : nullptr, mwords, ft->hist.p);
+			ft_pick_threshold<<<1, 1024, 0, st>>>(ft->hist.p, maxMerged, d_thr);
+			ft_thresh_count<<<pg, kFtThreads, 0, st>>>(ft->score.p, ft->mask.p, mwords, d_thr, ft->block_counts.p);
+			ft_thresh_apply<<<pg, kFtThreads, 0, st>>>(ft->score.p, ft->mask.p, mwords, d_thr, ft->block_counts.p);
+			g_ft_stats.launches += 4;
+			g_ft_stats.algorithmic_bytes += uint64_t(N) * 6;
 			checkRemoved = 0;  // needToCheckRemoved_ = false (:463)
 		}
 	}
@@ -868,7 +1044,7 @@ int rxgpu_ft_merge(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nter
 			}
 			const unsigned lb = (l.ndocs + kFtThreads - 1) / kFtThreads;
 			ft_rank_pass<<<lb, kFtThreads, 0, st>>>(l, termParams(t, sub, l), ms, d_words, ft->avg.p, d_removed, checkRemoved, simple ? 1 : 0,
-													maxMerged, qpIdx, ft->tmp_rank.p, ft->tmp_field.p, ft->block_counts.p);
+													kNoSlot, qpIdx, ft->tmp_rank.p, ft->tmp_field.p, ft->block_counts.p);
 			ft_scan_blocks<<<1, 1024, 0, st>>>(ft->block_counts.p, lb, d_total_new);
 			ft_assign<<<lb, kFtThreads, 0, st>>>(l, ms, simple ? 1 : 0, maxMerged, qpIdx, ft->tmp_rank.p, ft->tmp_field.p, ft->block_counts.p);
 			ft_bump_count<<<1, 1, 0, st>>>(ms.n_docs, d_total_new, maxMerged);
@@ -881,12 +1057,17 @@ int rxgpu_ft_merge(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nter
 	ft_full_match<<<gridFor(maxMerged, sm), kFtThreads, 0, st>>>(ms, d_words, ft->nfields, simple ? 1u : nterms, nterms, simple ? 1 : 0,
 																 cfg->full_match_boost);
 	g_ft_stats.launches++;
+	if (!trivial) {
+		ft_reset_idoff<<<gridFor(maxMerged, sm), kFtThreads, 0, st>>>(ms.md_id, ms.n_docs, ft->idoff.p);
+		g_ft_stats.launches++;
+	}
 	RX_CUDA(cudaGetLastError());
 	uint32_t n = 0;
 	RX_CUDA(cudaMemcpyAsync(&n, ms.n_docs, 4, cudaMemcpyDeviceToHost, st));
 	RX_CUDA(cudaEventRecord(e1, st));
 	RX_CUDA(cudaStreamSynchronize(st));
 	RX_CUDA(cudaEventElapsedTime(&g_ft_stats.device_ms, e0, e1));
+	ft->idoff_clean = !trivial;
 	cudaEventDestroy(e0);
 	cudaEventDestroy(e1);
 

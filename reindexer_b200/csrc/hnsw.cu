@@ -332,6 +332,102 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(const HnswArg
 	}
 }
 
+
+// ---- SearchRange (hnswalg.h:2015-2070): the ef-search result seeds a breadth-first expansion over level-0 neighbours with
+// dist < radius.  The closure is independent of the traversal order, so the reference's FIFO queue becomes a level-synchronous
+// frontier: the result array IS the queue (every accepted node is appended exactly once, guarded by the visited bitmap), one warp
+// expands one frontier node, all frontier nodes of a level in parallel.
+struct RangeArgs {
+	const float* rows;
+	const float* norm_coefs;
+	const uint32_t* level0;
+	const float* query;
+	uint32_t* visited;   // [words] one bitmap for the whole search (fresh: only the ef-search results are pre-marked, :2034-2041)
+	float* out_dist;     // [n]
+	uint32_t* out_idx;   // [n]
+	unsigned int* tail;  // entries in out_*
+	uint32_t pitch, dim, l0_stride;
+	float radius;
+};
+__global__ void hnsw_range_seed(RangeArgs a, const float* seed_dist, const uint32_t* seed_idx, const uint32_t* seed_count) {
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j < *seed_count) {
+		const uint32_t id = seed_idx[j];
+		atomicOr(&a.visited[id >> 5], 1u << (id & 31));
+		if (seed_dist[j] < a.radius) {
+			const unsigned pos = atomicAdd(a.tail, 1u);
+			a.out_dist[pos] = seed_dist[j];
+			a.out_idx[pos] = id;
+		}
+	}
+}
+template <bool kIsL2>
+__global__ void __launch_bounds__(kHnswThreads) hnsw_range_expand(RangeArgs a, uint32_t begin, uint32_t end) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t nch = (a.dim + 127u) / 128u;
+	const uint32_t dp4 = nch * 32u;
+	float4* sq4 = reinterpret_cast<float4*>(smem_raw);  // one query for the CTA
+	uint32_t* s_ids = reinterpret_cast<uint32_t*>(smem_raw + size_t(dp4) * 16) + warp * 2 * kMaxNeighbours;
+	float* s_d = reinterpret_cast<float*>(s_ids + kMaxNeighbours);
+	{
+		float* sq = reinterpret_cast<float*>(sq4);
+		for (uint32_t c = threadIdx.x; c < dp4 * 4; c += blockDim.x) {
+			sq[c] = c < a.dim ? a.query[c] : 0.f;
+		}
+	}
+	__syncthreads();
+	HnswArgs h{};  // warp_dists reads rows / pitch / dim / norm_coefs only
+	h.rows = a.rows;
+	h.norm_coefs = a.norm_coefs;
+	h.pitch = a.pitch;
+	h.dim = a.dim;
+	for (uint32_t f = begin + blockIdx.x * kHnswWarps + warp; f < end; f += gridDim.x * kHnswWarps) {
+		const uint32_t node = a.out_idx[f];
+		const uint32_t* ll = a.level0 + size_t(node) * a.l0_stride;
+		const uint32_t cnt = min(ll[0], uint32_t(kMaxNeighbours));
+		uint32_t ucnt = 0;
+		for (uint32_t b = 0; b < cnt; b += 32) {
+			const uint32_t j = b + lane;
+			uint32_t nid = 0;
+			bool fresh = false;
+			if (j < cnt) {
+				nid = ll[1 + j];
+				const uint32_t bit = 1u << (nid & 31);
+				fresh = !(atomicOr(&a.visited[nid >> 5], bit) & bit);  // exactly one warp of the grid wins a node
+			}
+			const unsigned fm = __ballot_sync(0xffffffffu, fresh);
+			if (fresh) {
+				s_ids[ucnt + __popc(fm & ((1u << lane) - 1u))] = nid;
+			}
+			ucnt += __popc(fm);
+		}
+		__syncwarp();
+		if (ucnt == 0) {
+			continue;
+		}
+		warp_dists<kIsL2>(h, sq4, s_ids, ucnt, s_d, lane);
+		for (uint32_t b = 0; b < ucnt; b += 32) {
+			const uint32_t j = b + lane;
+			const bool hit = j < ucnt && s_d[j] < a.radius;  // strict, :2060
+			const unsigned hm = __ballot_sync(0xffffffffu, hit);
+			if (hm) {
+				unsigned base = 0;
+				if (lane == 0) {
+					base = atomicAdd(a.tail, unsigned(__popc(hm)));
+				}
+				base = __shfl_sync(0xffffffffu, base, 0);
+				if (hit) {
+					const unsigned pos = base + __popc(hm & ((1u << lane) - 1u));
+					a.out_dist[pos] = s_d[j];
+					a.out_idx[pos] = s_ids[j];
+				}
+			}
+		}
+		__syncwarp();
+	}
+}
+
 }  // namespace
 
 struct rxgpu_hnsw_device {
@@ -348,6 +444,8 @@ struct rxgpu_hnsw_device {
 	DevBuf<uint32_t> visited;
 	DevBuf<uint32_t> vlog;
 	DevBuf<unsigned int> counter;
+	DevBuf<uint32_t> range_visited, range_idx;  // SearchRange scratch: one bitmap, result/queue arrays of n entries
+	DevBuf<float> range_dist;
 	uint32_t slots = 0, words = 0;
 };
 
@@ -525,6 +623,107 @@ int rxgpu_hnsw_search_knn(const rxgpu_index* ix, uint32_t nq, const float* queri
 			out_label[size_t(q) * k + j] = hits[j].label;
 		}
 		out_count[q] = uint32_t(hits.size());
+	}
+	return 0;
+}
+
+int rxgpu_hnsw_search_range(const rxgpu_index* ix, const float* query, float radius, uint32_t ef, uint64_t max_out, float* out_dist,
+							uint64_t* out_label, uint64_t* out_n) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	if (!query || !out_n || (max_out && (!out_dist || !out_label))) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	*out_n = 0;
+	if (ix->size == 0) {  // hnswalg.h:2017-2019
+		return 0;
+	}
+	rxgpu_hnsw_device* h = ix->hnsw;
+	if (!h) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: no HNSW graph imported into this index");
+	}
+	ef = std::max(ef, 1u);
+	const uint32_t kSeed = uint32_t(std::min<uint64_t>(ef, ix->size));
+	DevBuf<float> dq, dd;
+	DevBuf<uint32_t> di, dc;
+	RX_CUDA(dq.ensure(ix->dim));
+	RX_CUDA(dd.ensure(kSeed));
+	RX_CUDA(di.ensure(kSeed));
+	RX_CUDA(dc.ensure(1));
+	RX_CUDA(cudaMemcpy(dq.p, query, size_t(ix->dim) * 4, cudaMemcpyHostToDevice));
+	// search(): the whole top_candidates heap of the ef-search = its ef best nodes (SearchKnn with k = ef on the same routine)
+	if (int rc = rxgpu_hnsw_search_knn_device(ix, 1, dq.p, kSeed, ef, dd.p, di.p, dc.p, nullptr, nullptr)) {
+		return rc;
+	}
+	cudaStream_t st = ix->stream;
+	std::lock_guard<std::mutex> lck(h->mtx);
+	RX_CUDA(h->range_visited.ensure(h->words));
+	RX_CUDA(h->range_idx.ensure(h->n));
+	RX_CUDA(h->range_dist.ensure(h->n));
+	RX_CUDA(cudaMemsetAsync(h->range_visited.p, 0, size_t(h->words) * 4, st));
+	RX_CUDA(cudaMemsetAsync(h->counter.p, 0, sizeof(unsigned int), st));
+	RangeArgs a{};
+	a.rows = ix->d_rows;
+	a.norm_coefs = ix->metric == RXGPU_COS ? ix->d_norms : nullptr;
+	a.level0 = h->level0.p;
+	a.query = dq.p;
+	a.visited = h->range_visited.p;
+	a.out_dist = h->range_dist.p;
+	a.out_idx = h->range_idx.p;
+	a.tail = h->counter.p;
+	a.pitch = ix->pitch;
+	a.dim = ix->dim;
+	a.l0_stride = 1 + h->maxM0;
+	a.radius = radius;
+	hnsw_range_seed<<<(kSeed + 255) / 256, 256, 0, st>>>(a, dd.p, di.p, dc.p);
+	RX_CUDA(cudaGetLastError());
+	uint32_t launches = 2;
+	const uint32_t dp4 = ((ix->dim + 127u) / 128u) * 32u;
+	const size_t smem = size_t(dp4) * 16 + size_t(kHnswWarps) * kMaxNeighbours * 8;
+	if (ix->metric == RXGPU_L2) {
+		RX_CUDA(cudaFuncSetAttribute(hnsw_range_expand<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+	} else {
+		RX_CUDA(cudaFuncSetAttribute(hnsw_range_expand<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+	}
+	unsigned int begin = 0, end = 0;
+	RX_CUDA(cudaMemcpyAsync(&end, h->counter.p, 4, cudaMemcpyDeviceToHost, st));
+	RX_CUDA(cudaStreamSynchronize(st));
+	while (begin < end) {  // one launch per BFS level
+		const unsigned grid = std::min<unsigned>((end - begin + kHnswWarps - 1) / kHnswWarps, unsigned(ix->sm_count) * 8);
+		if (ix->metric == RXGPU_L2) {
+			hnsw_range_expand<true><<<grid, kHnswThreads, smem, st>>>(a, begin, end);
+		} else {
+			hnsw_range_expand<false><<<grid, kHnswThreads, smem, st>>>(a, begin, end);
+		}
+		RX_CUDA(cudaGetLastError());
+		++launches;
+		begin = end;
+		RX_CUDA(cudaMemcpyAsync(&end, h->counter.p, 4, cudaMemcpyDeviceToHost, st));
+		RX_CUDA(cudaStreamSynchronize(st));
+	}
+	g_stats = rxgpu_search_stats{};
+	g_stats.launches = launches;
+	*out_n = end;
+	try {
+		std::vector<float> hd(end);
+		std::vector<uint32_t> hi(end);
+		if (end) {
+			RX_CUDA(cudaMemcpy(hd.data(), h->range_dist.p, size_t(end) * 4, cudaMemcpyDeviceToHost));
+			RX_CUDA(cudaMemcpy(hi.data(), h->range_idx.p, size_t(end) * 4, cudaMemcpyDeviceToHost));
+		}
+		std::vector<Hit> hits(end);
+		for (uint32_t j = 0; j < end; ++j) {
+			hits[j] = Hit{hd[j], hi[j], ix->h_labels[hi[j]]};
+		}
+		std::sort(hits.begin(), hits.end(), [](const Hit& l, const Hit& r) { return l.dist < r.dist || (l.dist == r.dist && l.label < r.label); });
+		const uint64_t nout = std::min<uint64_t>(end, max_out);  // best-first = the drain order of the reference's max-heap (std::less<pair>)
+		for (uint64_t j = 0; j < nout; ++j) {
+			out_dist[j] = hits[j].dist;
+			out_label[j] = hits[j].label;
+		}
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
 	}
 	return 0;
 }

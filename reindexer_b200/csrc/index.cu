@@ -125,7 +125,17 @@ int pickQueryTile(const rxgpu_index* ix, uint32_t nq) {
 // order with dist <= bound.  Everything stays on the device; results land in d_out_* ([nq][k1]).
 int scanTopKExact(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, const float* d_queries, uint32_t nq, uint32_t k1, int mode,
 				  float bound, float* d_out_dist, uint32_t* d_out_idx, uint64_t* d_out_label, uint32_t* d_out_count) {
-	const int qt = mode == kModeTieRows ? 1 : pickQueryTile(ix, nq);
+	// k1 > kMaxFusedK1: rounds of <= kMaxFusedK1 results; a round only admits keys above the previous round's last key, so the
+	// rounds concatenate to the top-k1 under the same total order (one pass over the rows per round)
+	const uint32_t kr = std::min<uint32_t>(k1, kMaxFusedK1);
+	const uint32_t rounds = (k1 + kr - 1) / kr;
+	int qt = mode == kModeTieRows ? 1 : pickQueryTile(ix, nq);
+	while (qt > 1 && scan_smem_bytes(qt, ix->dim, kr) > 100 * 1024) {
+		qt /= 2;
+	}
+	if (scan_smem_bytes(qt, ix->dim, kr) > 100 * 1024) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: dimension/k combination exceeds the fused top-k shared-memory budget");
+	}
 	ScanArgs a{};
 	a.rows = ix->d_rows;
 	a.norm_coefs = ix->metric == RXGPU_COS ? ix->d_norms : nullptr;
@@ -133,51 +143,61 @@ int scanTopKExact(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, const f
 	a.dim = ix->dim;
 	a.row_begin = 0;
 	a.row_end = uint32_t(ix->size);
-	a.k1 = k1;
+	a.k1 = kr;
 	a.mode = mode;
 	a.bound = bound;
 	unsigned grid = 0;
 	RX_CUDA(launchScan(ix, qt, a, &grid, st, true));
-	RX_CUDA(ws.d_lists.ensure(size_t(grid) * qt * k1));
+	if (grid > 256u * kMergeOwn) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: scan grid exceeds the merge fan-in");
+	}
+	RX_CUDA(ws.d_lists.ensure(size_t(grid) * qt * kr));
 	a.lists = ws.d_lists.p;
-	if (scan_smem_bytes(qt, ix->dim, k1) > 100 * 1024) {
-		return fail(RXGPU_ERR_PARAMS, "rxgpu: dimension/k combination exceeds the fused top-k shared-memory budget");
+	if (rounds > 1) {
+		RX_CUDA(ws.d_floor.ensure(size_t(qt)));
 	}
 	for (uint32_t q0 = 0; q0 < nq; q0 += qt) {
 		a.queries = d_queries + size_t(q0) * ix->dim;
 		a.nq = std::min<uint32_t>(qt, nq - q0);
-		cudaEvent_t e0 = nullptr, e1 = nullptr;
-		if (g_profile.load(std::memory_order_relaxed)) {
-			RX_CUDA(cudaEventCreate(&e0));
-			RX_CUDA(cudaEventCreate(&e1));
-			RX_CUDA(cudaEventRecord(e0, st));
+		for (uint32_t round = 0; round < rounds; ++round) {
+			a.k1 = std::min(kr, k1 - round * kr);
+			a.floor_keys = round ? ws.d_floor.p : nullptr;
+			cudaEvent_t e0 = nullptr, e1 = nullptr;
+			if (g_profile.load(std::memory_order_relaxed)) {
+				RX_CUDA(cudaEventCreate(&e0));
+				RX_CUDA(cudaEventCreate(&e1));
+				RX_CUDA(cudaEventRecord(e0, st));
+			}
+			RX_CUDA(launchScan(ix, qt, a, &grid, st));
+			if (e0) {
+				RX_CUDA(cudaEventRecord(e1, st));
+				g_prof_events.emplace_back(e0, e1);
+			}
+			MergeArgs m{};
+			m.lists = ws.d_lists.p;
+			m.labels = ix->d_labels;
+			m.out_dist = d_out_dist;
+			m.out_idx = d_out_idx;
+			m.out_label = d_out_label;
+			m.out_count = d_out_count;
+			m.floor_out = rounds > 1 ? ws.d_floor.p : nullptr;
+			m.nlists = grid;
+			m.qt = qt;
+			m.k1 = a.k1;
+			m.q_offset = q0;
+			m.out_stride = k1;
+			m.out_offset = round * kr;
+			m.mode = mode;
+			knn_merge_lists<<<a.nq, 256, 0, st>>>(m);
+			RX_CUDA(cudaGetLastError());
+			g_stats.launches += 2;
+			g_stats.passes += 1;
 		}
-		RX_CUDA(launchScan(ix, qt, a, &grid, st));
-		if (e0) {
-			RX_CUDA(cudaEventRecord(e1, st));
-			g_prof_events.emplace_back(e0, e1);
-		}
-		MergeArgs m{};
-		m.lists = ws.d_lists.p;
-		m.labels = ix->d_labels;
-		m.out_dist = d_out_dist;
-		m.out_idx = d_out_idx;
-		m.out_label = d_out_label;
-		m.out_count = d_out_count;
-		m.nlists = grid;
-		m.qt = qt;
-		m.k1 = k1;
-		m.q_offset = q0;
-		m.mode = mode;
-		knn_merge_lists<<<a.nq, 256, 0, st>>>(m);
-		RX_CUDA(cudaGetLastError());
-		g_stats.launches += 2;
-		g_stats.passes += 1;
 	}
 	g_stats.query_tile = uint32_t(qt);
 	const uint64_t perPass = uint64_t(ix->size) * ix->dim * 4 + (ix->metric == RXGPU_COS ? uint64_t(ix->size) * 4 : 0) +
-							 uint64_t(qt) * ix->dim * 4 + uint64_t(qt) * k1 * 12;
-	g_stats.algorithmic_bytes += perPass * ((nq + qt - 1) / qt);
+							 uint64_t(qt) * ix->dim * 4 + uint64_t(qt) * kr * 12;
+	g_stats.algorithmic_bytes += perPass * ((nq + qt - 1) / qt) * rounds;
 	return 0;
 }
 
@@ -243,6 +263,7 @@ int ensureShadow(const rxgpu_index* ix, cudaStream_t st) {
 		const size_t cap = (size_t(ix->capacity ? ix->capacity : 1) + kTcTileRows - 1) / kTcTileRows * kTcTileRows;  // whole tiles
 		RX_CUDA(cudaMalloc(&ix->d_shadow, cap * pitchBf * 2));
 		RX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ix->d_vnorm), cap * sizeof(float)));
+		RX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ix->d_vw), cap * sizeof(float2)));
 		ix->pitch_bf = pitchBf;
 		ix->shadow_version = ~0ull;
 	}
@@ -250,6 +271,8 @@ int ensureShadow(const rxgpu_index* ix, cudaStream_t st) {
 		const unsigned blocks = unsigned((uint64_t(ix->size) * 32 + 255) / 256);
 		tc_convert_rows<<<blocks, 256, 0, st>>>(ix->d_rows, ix->pitch, ix->dim, 0, uint32_t(ix->size),
 												static_cast<__nv_bfloat16*>(ix->d_shadow), pitchBf / kTcChunkK, ix->d_vnorm);
+		const uint32_t padded = uint32_t((ix->size + kTcTileRows - 1) / kTcTileRows * kTcTileRows);
+		tc_make_vw<<<(padded + 255) / 256, 256, 0, st>>>(ix->d_vnorm, uint32_t(ix->size), padded, ix->metric, ix->d_vw);
 		RX_CUDA(cudaGetLastError());
 		RX_CUDA(cudaStreamSynchronize(st));
 		ix->shadow_version = ix->version;
@@ -339,6 +362,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			TqArgs a{};
 			a.shadow = static_cast<const unsigned char*>(ix->d_shadow);
 			a.vnorm = ix->d_vnorm;
+			a.vw = ix->d_vw;
 			a.vinv = ix->metric == RXGPU_COS ? ix->d_norms : nullptr;
 			a.qnorm = ws.d_qnorm.p;
 			a.qbf = ws.d_qbf.p;
@@ -509,6 +533,8 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 	m.qt = nq;
 	m.k1 = k1;
 	m.q_offset = 0;
+	m.out_stride = k1;
+	m.out_offset = 0;
 	m.mode = kModeTopK;
 	knn_merge_lists<<<nq, 256, 0, st>>>(m);
 	RX_CUDA(cudaGetLastError());
@@ -686,6 +712,8 @@ int rxgpu_index_resize(rxgpu_index* ix, uint64_t new_capacity) {
 	if (ix->d_shadow) {  // rebuilt lazily at the new capacity
 		cudaFree(ix->d_shadow);
 		cudaFree(ix->d_vnorm);
+		cudaFree(ix->d_vw);
+		ix->d_vw = nullptr;
 		ix->d_shadow = nullptr;
 		ix->d_vnorm = nullptr;
 	}
@@ -903,8 +931,8 @@ int rxgpu_search_knn_device(const rxgpu_index* ix, uint32_t nq, const float* d_q
 	if (nq == 0) {
 		return 0;
 	}
-	if (k1 == 0 || k1 > kMaxFusedK1) {
-		return fail(RXGPU_ERR_PARAMS, "rxgpu: k must be in [1, 255] on the fused top-k path");
+	if (k1 == 0 || k1 > kMaxSearchK1) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: k must be in [1, 65535]");
 	}
 	WsLease lease(ix);
 	Workspace& ws = *lease.ws;
@@ -927,8 +955,8 @@ int rxgpu_search_tie_rows_device(const rxgpu_index* ix, const float* d_query, fl
 	if (int rc = checkIndex(ix)) {
 		return rc;
 	}
-	if (k == 0 || k > kMaxFusedK1) {
-		return fail(RXGPU_ERR_PARAMS, "rxgpu: k must be in [1, 255] on the fused top-k path");
+	if (k == 0 || k > kMaxSearchK1) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: k must be in [1, 65535]");
 	}
 	WsLease lease(ix);
 	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ix->stream;
@@ -1012,8 +1040,8 @@ static int searchKnnHost(const rxgpu_index* ix, uint32_t nq, const float* querie
 	}
 	const uint32_t kEff = uint32_t(std::min<uint64_t>(k, ix->size));           // bruteforce.cc:111
 	const uint32_t k1 = uint32_t(std::min<uint64_t>(uint64_t(kEff) + 1, ix->size));  // one extra row exposes a tie at the k-th place
-	if (k1 > kMaxFusedK1) {
-		return fail(RXGPU_ERR_PARAMS, "rxgpu: k must be in [1, 255] on the fused top-k path");
+	if (k1 > kMaxSearchK1) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: k must be in [1, 65535]");
 	}
 	WsLease lease(ix);
 	Workspace& ws = *lease.ws;

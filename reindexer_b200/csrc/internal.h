@@ -101,6 +101,7 @@ struct Workspace {
 	cudaStream_t stream = nullptr;
 	DevBuf<float> d_queries;
 	DevBuf<uint64_t> d_lists;
+	DevBuf<uint64_t> d_floor;  // per-query floor keys between the rounds of a k > 255 search
 	DevBuf<float> d_out_dist;
 	DevBuf<uint32_t> d_out_idx;
 	DevBuf<uint64_t> d_out_label;
@@ -162,6 +163,7 @@ struct rxgpu_index {
 	mutable std::mutex tc_mtx;
 	mutable void* d_shadow = nullptr;  // __nv_bfloat16 [capacity][pitch_bf]
 	mutable float* d_vnorm = nullptr;  // [capacity] ||row||_2
+	mutable float2* d_vw = nullptr;    // [capacity] per-row (max(||row||, tiny), w) pairs the filter epilogue consumes, 512 B per 64-row tile
 	mutable uint32_t pitch_bf = 0;
 	mutable uint64_t shadow_version = ~0ull;
 	uint32_t tc_mode = 0;  // 0 auto, 1 force on, 2 off
@@ -188,6 +190,9 @@ struct rxgpu_index {
 		}
 		if (d_vnorm) {
 			cudaFree(d_vnorm);
+		}
+		if (d_vw) {
+			cudaFree(d_vw);
 		}
 		if (stream) {
 			cudaStreamDestroy(stream);

@@ -25,7 +25,8 @@ namespace rxgpu {
 constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kCandBuf = 32;  // candidate buffer entries per (warp, query)
-constexpr uint32_t kMaxFusedK1 = 256;
+constexpr uint32_t kMaxFusedK1 = 256;   // results per scan round (k + 1 <= 256 is answered by a single pass)
+constexpr uint32_t kMaxSearchK1 = 65536;  // larger k: ceil(k1 / 256) rounds
 
 struct ScanArgs {
 	const float* rows;        // [n][pitch] fp32
@@ -43,6 +44,7 @@ struct ScanArgs {
 	uint32_t k1;              // keys kept per list
 	int mode;                 // ScanMode or kModeRange
 	float bound;              // tie mode: dstar (dist <= bound); range mode: radius (dist < bound)
+	const uint64_t* floor_keys;  // [nq] only keys ABOVE the floor compete (rounds of a k > 255 search), or nullptr
 };
 enum : int { kModeRange = 2 };
 
@@ -137,6 +139,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_warp(const ScanArgs 
 		qpattern |= 1u << (r * QT);
 	}
 	const int my_r = lane / QT, my_q = lane % QT;
+	const bool has_floor = a.floor_keys != nullptr;
+	const uint64_t my_floor = has_floor && uint32_t(my_q) < a.nq ? a.floor_keys[my_q] : 0;
 
 	for (uint32_t g = blockIdx.x * kScanWarps + warp; g < ngroups; g += total_warps) {
 		float acc[RW][QT];
@@ -240,7 +244,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_warp(const ScanArgs 
 			key = make_key(dist, row);
 			cand = valid;
 		}
-		cand = cand && key < wthr[my_q];
+		cand = cand && key < wthr[my_q] && (!has_floor || key > my_floor);
 		const unsigned cm = __ballot_sync(0xffffffffu, cand);
 		if (cm) {
 			const unsigned mineq = cm & (qpattern << my_q);
@@ -318,39 +322,47 @@ __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_warp(const ScanArgs 
 	}
 }
 
-// One CTA per query: merge nlists lists of k1 ascending-or-not keys into the final ascending top-k1, decode and gather labels.
+// One CTA per query: k-way merge of nlists ASCENDING lists of k1 unique keys (kKeyNone padded) into the ascending top-k1, then decode
+// and gather labels.  Thread t owns the heads of lists t, t+256, ...; a round is one block-wide min over the heads and the owner of
+// the winner advances -- O(k1) rounds of O(1) work per thread.  Rounds of a k > 255 search write at out_offset and hand the last key
+// to the next round as its floor.
+constexpr int kMergeOwn = 4;  // lists per thread => nlists <= 1024
 struct MergeArgs {
-	uint64_t* lists;  // [nlists][qt][k1], clobbered
+	const uint64_t* lists;  // [nlists][qt][k1]
 	const uint64_t* labels;
-	float* out_dist;       // [nq][k1]
-	uint32_t* out_idx;     // [nq][k1]
-	uint64_t* out_label;   // [nq][k1] (may be null)
+	float* out_dist;       // [nq][out_stride]
+	uint32_t* out_idx;     // [nq][out_stride]
+	uint64_t* out_label;   // [nq][out_stride] (may be null)
 	uint32_t* out_count;   // [nq]
+	uint64_t* floor_out;   // [qt] last key written per query of this pass (kKeyNone when the lists ran dry), or null
 	uint32_t nlists;
 	uint32_t qt;           // list stride in queries
-	uint32_t k1;
+	uint32_t k1;           // keys per list = results of this round
 	uint32_t q_offset;     // first output query of this pass
+	uint32_t out_stride;   // result slots per query
+	uint32_t out_offset;   // first slot of this round
 	int mode;
 };
 
 __global__ void __launch_bounds__(256) knn_merge_lists(const MergeArgs a) {
-	__shared__ uint64_t s_best[8];
-	__shared__ uint64_t s_last;
+	__shared__ uint64_t s_best[2][8];
+	__shared__ uint64_t s_res[kMaxFusedK1];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t qi = blockIdx.x;
-	const uint32_t total = a.nlists * a.k1;
-	uint64_t last = 0;
-	bool first = true;
+	uint32_t head[kMergeOwn];
+	uint64_t hk[kMergeOwn];
+#pragma unroll
+	for (int j = 0; j < kMergeOwn; ++j) {
+		const uint32_t l = threadIdx.x + j * 256u;
+		head[j] = 0;
+		hk[j] = l < a.nlists ? a.lists[(size_t(l) * a.qt + qi) * a.k1] : kKeyNone;
+	}
 	uint32_t count = 0;
-	const size_t ob = size_t(a.q_offset + qi) * a.k1;
 	for (uint32_t r = 0; r < a.k1; ++r) {
-		uint64_t best = kKeyNone;
-		for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
-			const uint32_t l = i / a.k1, j = i - l * a.k1;
-			const uint64_t kx = a.lists[(size_t(l) * a.qt + qi) * a.k1 + j];
-			if ((first || kx > last) && kx < best) {
-				best = kx;
-			}
+		uint64_t best = hk[0];
+#pragma unroll
+		for (int j = 1; j < kMergeOwn; ++j) {
+			best = hk[j] < best ? hk[j] : best;
 		}
 #pragma unroll
 		for (int off = 16; off > 0; off >>= 1) {
@@ -358,42 +370,53 @@ __global__ void __launch_bounds__(256) knn_merge_lists(const MergeArgs a) {
 			best = ok < best ? ok : best;
 		}
 		if (lane == 0) {
-			s_best[warp] = best;
+			s_best[r & 1][warp] = best;
 		}
 		__syncthreads();
-		if (threadIdx.x == 0) {
-			uint64_t b = s_best[0];
-			for (int w = 1; w < 8; ++w) {
-				b = s_best[w] < b ? s_best[w] : b;
-			}
-			s_last = b;
-			if (b != kKeyNone) {
-				float dist;
-				uint32_t idx;
-				if (a.mode == kModeTieRows) {
-					idx = uint32_t(b >> 32);
-					dist = ord_float(uint32_t(b));
-				} else {
-					idx = uint32_t(b);
-					dist = ord_float(uint32_t(b >> 32));
-				}
-				a.out_dist[ob + r] = dist;
-				a.out_idx[ob + r] = idx;
-				if (a.out_label) {
-					a.out_label[ob + r] = a.labels[idx];
-				}
-			}
+		uint64_t b = s_best[r & 1][0];
+#pragma unroll
+		for (int w = 1; w < 8; ++w) {
+			const uint64_t o = s_best[r & 1][w];
+			b = o < b ? o : b;
 		}
-		__syncthreads();
-		last = s_last;
-		first = false;
-		if (last == kKeyNone) {
+		if (b == kKeyNone) {
 			break;
+		}
+#pragma unroll
+		for (int j = 0; j < kMergeOwn; ++j) {
+			if (hk[j] == b) {  // keys are unique: exactly one owner
+				const uint32_t l = threadIdx.x + j * 256u;
+				++head[j];
+				hk[j] = head[j] < a.k1 ? a.lists[(size_t(l) * a.qt + qi) * a.k1 + head[j]] : kKeyNone;
+				s_res[r] = b;
+			}
 		}
 		++count;
 	}
+	__syncthreads();
+	const size_t ob = size_t(a.q_offset + qi) * a.out_stride + a.out_offset;
+	for (uint32_t r = threadIdx.x; r < count; r += blockDim.x) {
+		const uint64_t b = s_res[r];
+		float dist;
+		uint32_t idx;
+		if (a.mode == kModeTieRows) {
+			idx = uint32_t(b >> 32);
+			dist = ord_float(uint32_t(b));
+		} else {
+			idx = uint32_t(b);
+			dist = ord_float(uint32_t(b >> 32));
+		}
+		a.out_dist[ob + r] = dist;
+		a.out_idx[ob + r] = idx;
+		if (a.out_label) {
+			a.out_label[ob + r] = a.labels[idx];
+		}
+	}
 	if (threadIdx.x == 0) {
-		a.out_count[a.q_offset + qi] = count;
+		a.out_count[a.q_offset + qi] = (a.out_offset ? a.out_count[a.q_offset + qi] : 0u) + count;
+		if (a.floor_out) {
+			a.floor_out[qi] = count == a.k1 ? s_res[count - 1] : kKeyNone;
+		}
 	}
 }
 

@@ -577,6 +577,16 @@ __global__ void __launch_bounds__(kScanThreads) knn_rerank(const float* rows, ui
 	}
 }
 
+// per-row constants of the filter epilogue, one float2 per row: (max(||v||, tiny), w) with w = the row's share of the L2 expansion
+// (0 for IP / Cosine); rows beyond n are zero.  A 64-row tile's pairs are one contiguous 512-byte block (one cp.async.bulk).
+__global__ void tc_make_vw(const float* vnorm, uint32_t n, uint32_t padded, int metric, float2* vw) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < padded) {
+		const float vn = i < n ? vnorm[i] : 0.f;
+		vw[i] = make_float2(fmaxf(vn, 1e-30f), metric == kL2 ? 0.5f * (1.f - kTcL2Eps) * vn * vn : 0.f);
+	}
+}
+
 // ---- helpers: bf16 shadow, norms, query preparation, threshold init ---------------------------------------------------------------
 // rows fp32 [n][pitch] -> bf16 shadow + ||row||_2.  Shadow layout: [tile of 64 rows][K chunk of 64][64 rows x 128 bytes], and inside
 // every 8 KB block the 16-byte units of row r are XOR-permuted with (r % 8) -- the SWIZZLE_128B pattern tcgen05.mma expects in

@@ -31,6 +31,7 @@ constexpr uint32_t kTqMaxKchunks = 12;                    // 768 / 64
 struct TqArgs {
 	const unsigned char* shadow;  // see tc_convert_rows: [tile64][K chunk][8 KB pre-swizzled]
 	const float* vnorm;
+	const float2* vw;         // tc_make_vw: [tiles x 64] (||v||, w)
 	const float* vinv;
 	const float* qnorm;
 	const uint16_t* qbf;       // [nq_pad][pitch_bf] bf16 queries (row-major, zero padded)
@@ -52,8 +53,10 @@ struct TqArgs {
 	unsigned long long* trace;  // profiling aid (RXGPU_TC_TRACE): per-tile timestamps of CTA 0, or nullptr
 };
 
+constexpr uint32_t kTqVwSlots = 8;  // ring of per-tile (||v||, w) blocks, filled kTqVwAhead tiles ahead by the epilogue itself
+constexpr uint32_t kTqVwAhead = 4;  // slots >= ahead + 4: see the reuse argument in the epilogue
 __host__ __device__ inline size_t tq_smem_bytes(uint32_t stages) {
-	return 1024 + size_t(stages) * kTqStageBytes + (2 * size_t(stages) + 8) * 8 + 2 * kTqTileRows * 8 + 64;
+	return 1024 + size_t(stages) * kTqStageBytes + kTqVwSlots * kTqTileRows * 8 + (2 * size_t(stages) + 8 + kTqVwSlots) * 8 + 64;
 }
 
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -94,14 +97,15 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 	extern __shared__ unsigned char smem_raw[];
 	unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 	unsigned char* s_rows = base;  // [stages][64 rows][128 B]
-	uint64_t* bars = reinterpret_cast<uint64_t*>(s_rows + size_t(a.stages) * kTqStageBytes);
+	float2* s_vw = reinterpret_cast<float2*>(s_rows + size_t(a.stages) * kTqStageBytes);  // [kTqVwSlots][64] per-row (||v||, w)
+	uint64_t* bars = reinterpret_cast<uint64_t*>(s_vw + kTqVwSlots * kTqTileRows);
 	uint64_t* full_bar = bars;
 	uint64_t* empty_bar = bars + a.stages;
 	uint64_t* acc_full = bars + 2 * a.stages;   // [2]
 	uint64_t* acc_empty = acc_full + 2;          // [2]
 	uint64_t* q_ready = acc_empty + 2;           // queries stored in TMEM
-	uint32_t* s_tmem = reinterpret_cast<uint32_t*>(q_ready + 1);
-	float2* s_vw = reinterpret_cast<float2*>(bars + 2 * a.stages + 8);  // [2][64] per-row (||v||, w) of the tile being drained / next
+	uint64_t* vw_full = q_ready + 1;             // [kTqVwSlots]
+	uint32_t* s_tmem = reinterpret_cast<uint32_t*>(vw_full + kTqVwSlots);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint32_t ntiles = (a.n + kTqTileRows - 1) / kTqTileRows;
@@ -119,6 +123,9 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 			mbar_init(&acc_empty[s], 4);
 		}
 		mbar_init(q_ready, 4);
+		for (uint32_t s = 0; s < kTqVwSlots; ++s) {
+			mbar_init(&vw_full[s], 1);
+		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	if (warp == 1) {
@@ -243,30 +250,36 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 		const float qe = q_ok ? kTcErrCoef * a.qnorm[my_q] : 0.f;
 		float tau = q_ok ? ord_float(a.tau[my_q]) : -INFINITY;
 		float2 pr = q_ok ? tc_make_pr(a.metric, tau, qe) : make_float2(0.f, INFINITY);
-		// per-row terms (||v||, w): global loads are issued ONE TILE AHEAD of the shared-memory store that consumes them, so their
-		// HBM latency overlaps a whole tile of work instead of stalling the epilogue (same for the tau refresh)
-		auto fetch_vn = [&](uint32_t t) -> float {
-			const uint32_t row = t * kTqTileRows + et;
-			return (et < kTqTileRows && t < ntiles && row < a.n) ? a.vnorm[row] : 0.f;
-		};
-		auto store_vw = [&](float vn, uint32_t buf) {
-			if (et < kTqTileRows) {
-				const float w = a.metric == kL2 ? 0.5f * (1.f - kTcL2Eps) * vn * vn : 0.f;
-				s_vw[buf * kTqTileRows + et] = make_float2(fmaxf(vn, 1e-30f), w);
+		// per-row terms (||v||, w): one 512-byte bulk copy per tile into a ring of kTqVwSlots slots, issued kTqVwAhead tiles ahead by
+		// the first epilogue thread, so no global-load latency and no CTA barrier sits on the epilogue path.  Slot reuse is safe
+		// without an "empty" barrier: when this thread starts tile `it` it has passed acc_full(it - 1); those MMAs waited for the
+		// acc_empty arrivals of tile it - 3 from all four warps, which every warp issues after finishing tile it - 4 -- the last
+		// reader of slot (it + kTqVwAhead) % kTqVwSlots.
+		static_assert(kTqVwSlots >= kTqVwAhead + 4, "vw ring reuse distance");
+		auto issue_vw = [&](uint32_t j) {
+			const uint64_t t = uint64_t(cid) + uint64_t(j) * ncl;
+			if (t < ntiles) {
+				const uint32_t slot = j % kTqVwSlots;
+				mbar_expect_tx(&vw_full[slot], kTqTileRows * 8);
+				bulk_load(reinterpret_cast<unsigned char*>(s_vw + slot * kTqTileRows),
+						  reinterpret_cast<const unsigned char*>(a.vw + t * kTqTileRows), kTqTileRows * 8, &vw_full[slot]);
 			}
 		};
-		store_vw(fetch_vn(cid), 0);
-		float vn_ahead = fetch_vn(cid + ncl);            // for the tile after the first
+		if (et == 0) {
+			for (uint32_t j = 0; j < kTqVwAhead; ++j) {
+				issue_vw(j);
+			}
+		}
 		unsigned int tau_ahead = q_ok ? a.tau[my_q] : 0u;
-		asm volatile("bar.sync 1, 128;" ::: "memory");
 		uint32_t it = 0;
 		for (uint32_t t = cid; t < ntiles; t += ncl, ++it) {
 			const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
 			const uint32_t rows_valid = min(uint32_t(kTqTileRows), a.n - t * kTqTileRows);
-			// consume what was fetched during the previous tile, then fetch for the one after next
-			store_vw(vn_ahead, acc ^ 1);
-			vn_ahead = fetch_vn(t + 2 * ncl);
-			if (q_ok) {
+			if (et == 0) {
+				issue_vw(it + kTqVwAhead);
+			}
+			const float2* vw_tile = s_vw + (it % kTqVwSlots) * kTqTileRows;
+			if (q_ok) {  // the threshold other CTAs tightened: loaded one tile ago, consumed now
 				const float tn = ord_float(tau_ahead);
 				if (tn < tau) {
 					tau = tn;
@@ -296,6 +309,7 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 			if (threadIdx.x == 64) {
 				TQ_TRACE(6, it);
 			}
+			mbar_wait(&vw_full[it % kTqVwSlots], (it / kTqVwSlots) & 1);
 #pragma unroll
 			for (uint32_t ch = 0; ch < 2; ++ch) {
 				const uint32_t c0 = ch * 32;
@@ -303,7 +317,7 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 				uint32_t hits = 0;
 #pragma unroll
 				for (int j = 0; j < 32; ++j) {
-					const float2 vw = s_vw[acc * kTqTileRows + c0 + j];
+					const float2 vw = vw_tile[c0 + j];
 					hits |= uint32_t(__uint_as_float(v[j]) - vw.y >= fmaf(pr.x, vw.x, pr.y)) << j;
 				}
 				const uint32_t nv = rows_valid > c0 ? min(32u, rows_valid - c0) : 0u;
@@ -317,7 +331,7 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 						}
 						const uint32_t row = t * kTqTileRows + c0 + j;
 						const float s = __uint_as_float(v[j]);
-						const float vn = s_vw[acc * kTqTileRows + c0 + j].x;
+						const float vn = vw_tile[c0 + j].x;
 						float d, e;
 						if (a.metric == kL2) {
 							const float qn = qe * (1.f / kTcErrCoef);
@@ -373,7 +387,6 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 				TQ_TRACE(7, it);
 			}
 			__syncwarp();  // the rare path diverges (per-lane lock loops): reconverge before the .aligned tcgen05 ops of the next tile
-			asm volatile("bar.sync 1, 128;" ::: "memory");  // s_vw[acc ^ 1] written by everyone before the next tile reads it
 			if (threadIdx.x == 64) {
 				TQ_TRACE(8, it);
 			}

@@ -117,3 +117,35 @@ def test_hnsw_recall_on_structured_data():
     rec_ref = np.mean([len(set(lr[i]) & set(lb[i])) / k for i in range(nq)])
     assert rec >= 0.99 and abs(rec - rec_ref) <= 0.005, (rec, rec_ref)
     assert sum(int((l[i] == lr[i]).all()) for i in range(nq)) >= 0.95 * nq
+
+
+@pytest.mark.parametrize("metric,dim", [(rx.L2, 48), (rx.IP, 64), (rx.COS, 96)])
+def test_hnsw_search_range_matches_reference(metric, dim):
+    """SearchRange (hnswalg.h:2015-2070): ef-search seeds + BFS closure under the radius.  The closure does not depend on the
+    traversal order, so the device's level-synchronous expansion must return the reference's set whenever the seeds agree."""
+    n, ef, nq = 15000, 64, 40
+    ref, gpu, vecs, labels = build(metric, n, dim, 1300 + metric)
+    queries = np.stack([prep_query(metric, q) for q in O.synth_matrix(1400 + metric, nq, dim)])
+    same = 0
+    sizes = []
+    for i in range(nq):
+        db, lb, _ = gpu.search_knn(queries[i:i + 1], 201)
+        j = [3, 40, 120, 200][i % 4]
+        radius = float((np.float64(db[0, j - 1]) + np.float64(db[0, j])) / 2)  # halfway between two neighbours: no fp coin flips
+        d, l, total = gpu.hnsw_search_range(queries[i], radius, ef)
+        dr, lr, tr = ref.search_range(queries[i], radius, ef)
+        assert total == len(l) and tr == len(lr)
+        assert (np.diff(d) >= 0).all() and (d < radius).all()
+        sizes.append(total)
+        if total == tr and (l == lr).all():
+            same += 1
+            assert np.allclose(d, dr, rtol=RTOL, atol=ATOL)
+        assert set(l) <= set(lb[0, :j]), "a result outside the exact radius ball"
+    assert same >= nq - 2, (same, nq)
+    assert max(sizes) >= 20, sizes  # the expansion really found neighbourhoods, not just seeds
+    # max_out truncation keeps the best, out_n still reports the total
+    d2, l2, t2 = gpu.hnsw_search_range(queries[1], 1e9, ef, max_out=5)
+    dr2, lr2, tr2 = ref.search_range(queries[1], 1e9, ef, max_out=5)
+    assert len(l2) == 5 and t2 == tr2 and t2 > n * 0.99 and (l2 == lr2).all()  # an unbounded radius floods the reachable graph
+    fresh = rx.GpuBruteforceSearch(metric, dim, 10)
+    assert fresh.hnsw_search_range(queries[0], 1.0, ef)[2] == 0  # empty index: empty result (:2017-2019)

@@ -98,6 +98,37 @@ def test_parity_k_and_batch(metric, k, nq):
         compare_queries(metric, gpu, cpu, O.synth_matrix(78, nq, dim), k)
 
 
+@pytest.mark.parametrize("metric", [rx.L2, rx.IP, rx.COS])
+@pytest.mark.parametrize("k", [255, 256, 300, 1000, 2500, 6000])
+def test_parity_large_k(metric, k):
+    """k + 1 > 256 is answered in rounds of 256 results (one pass per round, floor key between rounds); the reference's tests go to
+    k = 1000 (gtests/tests/unit/float_vector_index.cc)."""
+    n, dim = 5000, 64
+    vecs, labels = O.synth_matrix(177, n, dim), O.row_labels(n)
+    gpu, cpu = build_pair(metric, vecs, labels)
+    compare_queries(metric, gpu, cpu, O.synth_matrix(178, 3, dim), k)
+    assert rx.last_search_stats()["passes"] >= (min(k + 1, n) + 255) // 256
+
+
+@pytest.mark.parametrize("metric", [rx.L2, rx.IP])
+@pytest.mark.parametrize("k", [300, 777])
+def test_large_k_ties_bit_exact(metric, k):
+    """tie-heavy integer vectors with k beyond one round: labels and order equal the reference's heap result bit for bit, including
+    the tie replay over a first-k-rows scan that itself spans several rounds"""
+    n, dim = 4000, 6
+    rng = np.random.default_rng(4242 + k)
+    vecs = rng.integers(-2, 3, size=(n, dim)).astype(np.float32)
+    labels = O.row_labels(n)[rng.permutation(n)]
+    gpu, cpu = build_pair(metric, vecs, labels)
+    for lab in labels[rng.choice(n, 40, replace=False)]:
+        gpu.remove_point(int(lab))
+        cpu.remove(int(lab))
+    qs = rng.integers(-2, 3, size=(4, dim)).astype(np.float32)
+    compare_queries(metric, gpu, cpu, qs, k, exact_ids=True)
+    d1, l1 = gpu.search_knn(qs[0], k)
+    assert rx.last_search_stats()["tie_replays"] == 1
+
+
 def test_batch_equals_single_queries_bitwise():
     n, dim = 20000, 128
     gpu = rx.GpuBruteforceSearch(rx.L2, dim, n)
