@@ -52,7 +52,7 @@ class ClockSampler:
         q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50", "-i",
                                           str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -61,9 +61,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """samples taken inside [t_begin, t_end] (the timed region); nvidia-smi is started before the warm-up so that it is
+        already reporting when the region begins"""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -72,7 +74,11 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
-        for ln in self.lines:
+        inside = [ln for (ts, ln) in self.lines if t_begin is None or (t_begin <= ts <= t_end + 0.2)]
+        window = "timed region"
+        if not inside:  # region shorter than one sampling period: report the samples under the same load (warm-up + region)
+            inside, window = [ln for (_, ln) in self.lines], "warm-up + timed region"
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -85,7 +91,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ----------------------------------------------------------------------------------------------------------------- CPU arm
@@ -220,11 +226,12 @@ def run_ours(args):
 
     # ---- device-resident leg: CUDA events on the launching stream, max over ranks
     B.lib().rxgpu_set_profile(1)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step_resident()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    t_begin = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = passes = 0
     scan_ms = 0.0
@@ -245,7 +252,7 @@ def run_ours(args):
         tc_fallbacks = st["tc_fallbacks"]
     ev1.record(stream)
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, time.perf_counter())
     ms_total = ev0.elapsed_time(ev1)
     B.lib().rxgpu_set_profile(0)
     # ---- end-to-end leg: host buffers through the reference-facing C ABI call, copies inside the timed region
@@ -278,8 +285,8 @@ def run_ours(args):
         e2e_value = world * NQ / (e2e_s / args.steps)
         peak, peak_src = load_peaks()
         if tc_used:  # dominant kernel = knn_tc_filter: bf16 shadow rows + row norms + the resident query block, per launch
-            per_launch_bytes = rows * DIM * 2 + rows * 4 + qt * DIM * 2
-            kernel_name = "knn_tc_filter (tcgen05 bf16 filter, certified bound) + knn_rerank (exact fp32)"
+            per_launch_bytes = rows * DIM * 2 + rows * 8 + qt * DIM * 2
+            kernel_name = "knn_tc_filter_q (tcgen05 bf16 filter, queries in TMEM, certified bound) + knn_rerank (exact fp32)"
         else:
             per_launch_bytes = alg_bytes / max(passes, 1)
             kernel_name = "knn_scan_warp (fp32 FMA, fused top-k)"
@@ -298,7 +305,11 @@ def run_ours(args):
                        "global_queries_per_s": NQ / (ms_per_step / 1000.0), "index_fill_s": round(fill_s, 2),
                        "value_definition": "(query x 10M-row shard) scans per second over all ranks"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "knn_tc_filter" if tc_used else "knn_scan_warp",
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/
+                         # (r1_knn_tc_filter_q_full_raw.csv, r1_knn_scan_warp_full_raw.csv), valid for the full-size workload only
+                         "traffic": (None if rows != 10_000_000 else 15.4224e9 if tc_used else 30.7201e9),
+                         "peak_source": peak_src, "kernel": "knn_tc_filter_q" if tc_used else "knn_scan_warp",
+                         "tensor_tflops": (2.0 * rows * DIM * qt / (avg_launch_ms * 1e-3) / 1e12) if tc_used and avg_launch_ms > 0 else None,
                          "bytes_per_launch": per_launch_bytes, "avg_launch_ms": avg_launch_ms, "launches_timed": scan_launches,
                          "kernel_share_of_step": scan_ms / ms_total if ms_total else None},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": NQ * DIM * 4,
@@ -319,7 +330,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default 10M = BASELINE config)")

@@ -19,7 +19,7 @@
 #include "../host/knn_select.h"
 #include "knn_scan.cuh"
 #include "knn_tc.cuh"
-#include "knn_tc_q.cuh"
+#include "knn_tc_q2.cuh"
 
 using namespace rxgpu;
 
@@ -314,14 +314,17 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 	g_stats.launches += 2;
 	const uint32_t ntiles = uint32_t((ix->size + kTcTileRows - 1) / kTcTileRows);
 	bool launched = false;
-	if (ix->tc_variant == 0 && kchunks <= kTqMaxKchunks) {
+	if ((ix->tc_variant == 0 || ix->tc_variant == 7) && kchunks <= kTqMaxKchunks) {
 		// second-generation filter: query block in TMEM, deep TMA ring, row tiles multicast to a cluster of up to 4 CTAs
 		const uint32_t qblocks = (nq + kTqQueries - 1) / kTqQueries;
+		// mode 7: the CTA pair multiplies as one (cta_group::2), each SM stages half of every row tile
+		const bool pairMma = ix->tc_variant == 7 && qblocks >= 2 && ix->sm_count >= 2;
 		uint32_t stages = 2;
-		while (tq_smem_bytes(stages + 1) <= kTcSmemLimit && stages < 64) {
+		while ((pairMma ? t2_smem_bytes(stages + 1) : tq_smem_bytes(stages + 1)) <= kTcSmemLimit && stages < 64) {
 			++stages;
 		}
-		const size_t smem = tq_smem_bytes(stages);
+		const size_t smem = pairMma ? t2_smem_bytes(stages) : tq_smem_bytes(stages);
+		RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q2, cudaFuncAttributeMaxDynamicSharedMemorySize, int(t2_smem_bytes(pairMma ? stages : 2))));
 		RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
 		RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
 		RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -329,7 +332,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 		// the pass is bound by the per-SM turn-around of the two TMEM accumulators, not by HBM, so pairs are the default
 		const uint32_t clusterMax = ix->tc_cluster_max ? ix->tc_cluster_max : 2u;
 		int cluster = qblocks >= 3 ? 4 : (qblocks == 2 ? 2 : 1);
-		cluster = std::min<int>(cluster, int(clusterMax));
+		cluster = pairMma ? 2 : std::min<int>(cluster, int(clusterMax));
 		const uint32_t qtiles = uint32_t((ix->size + kTqTileRows - 1) / kTqTileRows);
 		unsigned grid = 0;
 		for (;;) {  // how many clusters of this size can be resident at once (GPC boundaries strand SMs for size 4)
@@ -345,7 +348,8 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			cfg.attrs = attr;
 			cfg.numAttrs = 1;
 			int maxClusters = 0;
-			cudaError_t e = cluster == 4	? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q<4>, &cfg)
+			cudaError_t e = pairMma		   ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q2, &cfg)
+							: cluster == 4 ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q<4>, &cfg)
 							: cluster == 2 ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q<2>, &cfg)
 										   : cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q<1>, &cfg);
 			if (e == cudaSuccess && maxClusters > 0) {
@@ -353,7 +357,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 				break;
 			}
 			cudaGetLastError();
-			if (cluster == 1) {
+			if (cluster == 1 || pairMma) {
 				return fail(RXGPU_ERR_SYSTEM, "rxgpu: tensor-core filter kernel cannot be made resident");
 			}
 			cluster /= 2;
@@ -387,6 +391,8 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 				RX_CUDA(traceBuf.ensure(256 * 16));
 				RX_CUDA(cudaMemsetAsync(traceBuf.p, 0, 256 * 16 * 8, st));
 				a.trace = traceBuf.p;
+				const char* first = std::getenv("RXGPU_TC_TRACE_FIRST");
+				a.trace_first = first ? uint32_t(std::atoi(first)) : 0u;
 			}
 			cudaEvent_t e0 = nullptr, e1 = nullptr;
 			if (g_profile.load(std::memory_order_relaxed)) {
@@ -406,7 +412,9 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			attr[0].val.clusterDim.z = 1;
 			cfg.attrs = attr;
 			cfg.numAttrs = 1;
-			if (cluster == 4) {
+			if (pairMma) {
+				RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q2, a));
+			} else if (cluster == 4) {
 				RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q<4>, a));
 			} else if (cluster == 2) {
 				RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q<2>, a));
@@ -435,7 +443,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			}
 		}
 		g_stats.tc_cluster = uint32_t(cluster);
-		g_stats.tc_kernel = 2;
+		g_stats.tc_kernel = pairMma ? 3 : 2;
 		g_stats.query_tile = uint32_t(kTqQueries * cluster);
 		g_stats.algorithmic_bytes += uint64_t((qblocks + cluster - 1) / cluster) * (uint64_t(ix->size) * pitchBf * 2 + uint64_t(ix->size) * 4) +
 									 uint64_t(nq) * pitchBf * 2;
@@ -903,11 +911,11 @@ int rxgpu_set_query_tile(rxgpu_index* ix, uint32_t qt) {
 	return 0;
 }
 int rxgpu_set_tensor_core_filter(rxgpu_index* ix, int mode) {
-	if (!ix || mode < 0 || mode > 6) {
-		return fail(RXGPU_ERR_PARAMS, "rxgpu: tensor-core filter mode must be in 0..6");
+	if (!ix || mode < 0 || mode > 7) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: tensor-core filter mode must be in 0..7");
 	}
 	ix->tc_mode = uint32_t(mode >= 3 ? 1 : mode);
-	ix->tc_variant = (mode == 3 || mode == 4) ? uint32_t(mode) : 0u;
+	ix->tc_variant = (mode == 3 || mode == 4 || mode == 7) ? uint32_t(mode) : 0u;
 	ix->tc_cluster_max = mode == 5 ? 1u : (mode == 6 ? 4u : 0u);
 	return 0;
 }

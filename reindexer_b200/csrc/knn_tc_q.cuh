@@ -51,6 +51,7 @@ struct TqArgs {
 	uint32_t stages;
 	int metric;
 	unsigned long long* trace;  // profiling aid (RXGPU_TC_TRACE): per-tile timestamps of CTA 0, or nullptr
+	uint32_t trace_first;       // first local tile index recorded (RXGPU_TC_TRACE_FIRST)
 };
 
 constexpr uint32_t kTqVwSlots = 8;  // ring of per-tile (||v||, w) blocks, filled kTqVwAhead tiles ahead by the epilogue itself
@@ -87,10 +88,73 @@ __device__ __forceinline__ unsigned long long tq_clock() {
 }
 #define TQ_TRACE(slot, idx)                                                        \
 	do {                                                                           \
-		if (a.trace && blockIdx.x == 0 && (idx) < 256) {                           \
-			a.trace[(idx) * 16 + (slot)] = tq_clock();                             \
+		if (a.trace && blockIdx.x == 0 && uint32_t((idx) - a.trace_first) < 256u) { \
+			a.trace[((idx) - a.trace_first) * 16 + (slot)] = tq_clock();           \
 		}                                                                          \
 	} while (0)
+
+// The rare path of the epilogue: row `row` passed the test for query `my_q` (raw accumulator s, row norm vn).  Appends the candidate,
+// and when its upper bound beats the current threshold, inserts it into the query's global bound list (under the per-query lock;
+// this thread is the only one of its CTA that handles my_q, other clusters contend) and tightens tau.  Returns the new threshold.
+// Kept out of line: it runs for ~350 of 10M rows per query, and inlining it 64 times per tile only costs instruction cache.
+struct TqCandCtx {
+	unsigned int* cand_count;
+	uint32_t* cand_rows;
+	unsigned int* ub_lock;
+	float* ub_list;
+	unsigned int* tau;
+	uint32_t cand_cap, init_rows, k1;
+	int metric;
+};
+__device__ __noinline__ float tq_candidate(const TqCandCtx c, uint32_t my_q, uint32_t row, float s, float vn, float qe, float tau) {
+	float d, e;
+	if (c.metric == kL2) {
+		const float qn = qe * (1.f / kTcErrCoef);
+		d = fmaf(-2.f, s, fmaf(qn, qn, vn * vn));
+		e = 2.f * qe * vn + kTcL2Eps * (qn * qn + vn * vn);
+	} else if (c.metric == kCos) {
+		const float vinv = 1.f / vn;  // within 1e-5 of the stored coefficient (normalize.cc shortcut), inside the slack
+		d = -s * vinv;
+		e = qe * 1.0001f;
+	} else {
+		d = -s;
+		e = qe * vn;
+	}
+	const unsigned pos = atomicAdd(&c.cand_count[my_q], 1u);
+	if (pos < c.cand_cap) {
+		c.cand_rows[size_t(my_q) * c.cand_cap + pos] = row;
+	}
+	const float ub = d + e;
+	if (ub < tau && row >= c.init_rows) {
+		while (atomicCAS(&c.ub_lock[my_q], 0u, 1u) != 0u) {
+		}
+		__threadfence();
+		volatile float* list = c.ub_list + size_t(my_q) * kTcMaxK1;
+		uint32_t mi = 0;
+		float mx = list[0];
+		for (uint32_t x = 1; x < c.k1; ++x) {
+			const float y = list[x];
+			if (y > mx) {
+				mx = y;
+				mi = x;
+			}
+		}
+		if (ub < mx) {
+			list[mi] = ub;
+			float nmx = list[0];
+			for (uint32_t x = 1; x < c.k1; ++x) {
+				nmx = fmaxf(nmx, list[x]);
+			}
+			atomicMin(&c.tau[my_q], float_ord(nmx));
+			tau = fminf(tau, nmx);
+		} else {
+			tau = fminf(tau, mx);
+		}
+		__threadfence();
+		atomicExch(&c.ub_lock[my_q], 0u);
+	}
+	return tau;
+}
 
 template <int kCluster>
 __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a) {
@@ -247,6 +311,7 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 				mbar_arrive(q_ready);
 			}
 		}
+		const TqCandCtx cc{a.cand_count, a.cand_rows, a.ub_lock, a.ub_list, a.tau, a.cand_cap, a.init_rows, a.k1, a.metric};
 		const float qe = q_ok ? kTcErrCoef * a.qnorm[my_q] : 0.f;
 		float tau = q_ok ? ord_float(a.tau[my_q]) : -INFINITY;
 		float2 pr = q_ok ? tc_make_pr(a.metric, tau, qe) : make_float2(0.f, INFINITY);
@@ -329,55 +394,9 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 						if (!(any_hits & (1u << j)) || !(hits & (1u << j))) {
 							continue;
 						}
-						const uint32_t row = t * kTqTileRows + c0 + j;
-						const float s = __uint_as_float(v[j]);
-						const float vn = vw_tile[c0 + j].x;
-						float d, e;
-						if (a.metric == kL2) {
-							const float qn = qe * (1.f / kTcErrCoef);
-							d = fmaf(-2.f, s, fmaf(qn, qn, vn * vn));
-							e = 2.f * qe * vn + kTcL2Eps * (qn * qn + vn * vn);
-						} else if (a.metric == kCos) {
-							const float vinv = 1.f / vn;  // within 1e-5 of the stored coefficient (normalize.cc shortcut), inside the slack
-							d = -s * vinv;
-							e = qe * 1.0001f;
-						} else {
-							d = -s;
-							e = qe * vn;
-						}
-						const unsigned pos = atomicAdd(&a.cand_count[my_q], 1u);
-						if (pos < a.cand_cap) {
-							a.cand_rows[size_t(my_q) * a.cand_cap + pos] = row;
-						}
-						const float ub = d + e;
-						if (ub < tau && row >= a.init_rows) {
-							// this thread is the only one of the CTA that handles my_q; other clusters contend for the lock
-							while (atomicCAS(&a.ub_lock[my_q], 0u, 1u) != 0u) {
-							}
-							__threadfence();
-							volatile float* list = a.ub_list + size_t(my_q) * kTcMaxK1;
-							uint32_t mi = 0;
-							float mx = list[0];
-							for (uint32_t x = 1; x < a.k1; ++x) {
-								const float y = list[x];
-								if (y > mx) {
-									mx = y;
-									mi = x;
-								}
-							}
-							if (ub < mx) {
-								list[mi] = ub;
-								float nmx = list[0];
-								for (uint32_t x = 1; x < a.k1; ++x) {
-									nmx = fmaxf(nmx, list[x]);
-								}
-								atomicMin(&a.tau[my_q], float_ord(nmx));
-								tau = fminf(tau, nmx);
-							} else {
-								tau = fminf(tau, mx);
-							}
-							__threadfence();
-							atomicExch(&a.ub_lock[my_q], 0u);
+						const float nt = tq_candidate(cc, my_q, t * kTqTileRows + c0 + j, __uint_as_float(v[j]), vw_tile[c0 + j].x, qe, tau);
+						if (nt < tau) {
+							tau = nt;
 							pr = tc_make_pr(a.metric, tau, qe);
 						}
 					}
