@@ -20,6 +20,7 @@
 #include "knn_scan.cuh"
 #include "knn_tc.cuh"
 #include "knn_tc_q2.cuh"
+#include "knn_tc_w.cuh"
 
 using namespace rxgpu;
 
@@ -314,20 +315,30 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 	g_stats.launches += 2;
 	const uint32_t ntiles = uint32_t((ix->size + kTcTileRows - 1) / kTcTileRows);
 	bool launched = false;
-	if ((ix->tc_variant == 0 || ix->tc_variant == 7) && kchunks <= kTqMaxKchunks) {
+	if ((ix->tc_variant == 0 || ix->tc_variant == 7 || ix->tc_variant == 8) && kchunks <= kTqMaxKchunks) {
 		// second-generation filter: query block in TMEM, deep TMA ring, row tiles multicast to a cluster of up to 4 CTAs
 		const uint32_t qblocks = (nq + kTqQueries - 1) / kTqQueries;
 		// mode 7: the CTA pair multiplies as one (cta_group::2), each SM stages half of every row tile
 		const bool pairMma = ix->tc_variant == 7 && qblocks >= 2 && ix->sm_count >= 2;
+		// mode 8..10: one accumulator of 128 rows (UMMA N = 128 runs the tensor pipe at its full rate, N = 64 at 67 %)
+		const bool wide = ix->tc_variant == 8;
+		auto smemOf = [&](uint32_t st) { return pairMma ? t2_smem_bytes(st) : (wide ? tw_smem_bytes(st) : tq_smem_bytes(st)); };
 		uint32_t stages = 2;
-		while ((pairMma ? t2_smem_bytes(stages + 1) : tq_smem_bytes(stages + 1)) <= kTcSmemLimit && stages < 64) {
+		while (smemOf(stages + 1) <= kTcSmemLimit && stages < 64) {
 			++stages;
 		}
-		const size_t smem = pairMma ? t2_smem_bytes(stages) : tq_smem_bytes(stages);
+		const size_t smem = smemOf(stages);
+		if (wide) {
+			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_w<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_w<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_w<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+		}
 		RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q2, cudaFuncAttributeMaxDynamicSharedMemorySize, int(t2_smem_bytes(pairMma ? stages : 2))));
-		RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-		RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-		RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+		if (!wide && !pairMma) {
+			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+		}
 		// measured on B200 (10M x 768, 1024 queries): CTA pairs 20.4 ms, clusters of four 21.9 ms, single CTAs 25.5 ms per batch --
 		// the pass is bound by the per-SM turn-around of the two TMEM accumulators, not by HBM, so pairs are the default
 		const uint32_t clusterMax = ix->tc_cluster_max ? ix->tc_cluster_max : 2u;
@@ -338,7 +349,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 		for (;;) {  // how many clusters of this size can be resident at once (GPC boundaries strand SMs for size 4)
 			cudaLaunchConfig_t cfg{};
 			cfg.gridDim = dim3(unsigned(ix->sm_count) / cluster * cluster);
-			cfg.blockDim = dim3(kTqThreads);
+			cfg.blockDim = dim3(wide ? kTwThreads : kTqThreads);
 			cfg.dynamicSmemBytes = smem;
 			cudaLaunchAttribute attr[1];
 			attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -348,12 +359,15 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			cfg.attrs = attr;
 			cfg.numAttrs = 1;
 			int maxClusters = 0;
-			cudaError_t e = pairMma		   ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q2, &cfg)
+			cudaError_t e = wide && cluster == 4 ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_w<4>, &cfg)
+							: wide && cluster == 2 ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_w<2>, &cfg)
+							: wide				   ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_w<1>, &cfg)
+							: pairMma			   ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q2, &cfg)
 							: cluster == 4 ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q<4>, &cfg)
 							: cluster == 2 ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q<2>, &cfg)
 										   : cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q<1>, &cfg);
 			if (e == cudaSuccess && maxClusters > 0) {
-				grid = unsigned(std::min<uint64_t>(uint64_t(maxClusters), std::max<uint32_t>(qtiles, 1))) * cluster;
+				grid = unsigned(std::min<uint64_t>(uint64_t(maxClusters), std::max<uint32_t>(wide ? (qtiles + 1) / 2 : qtiles, 1))) * cluster;
 				break;
 			}
 			cudaGetLastError();
@@ -385,6 +399,10 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			a.k1 = k1;
 			a.stages = stages;
 			a.metric = ix->metric;
+			{
+				static const char* pf = std::getenv("RXGPU_TC_PREFETCH");  // tuning aid: L2 prefetch distance in tiles
+				a.prefetch = pf ? uint32_t(std::atoi(pf)) : (wide ? 2u : 3u);
+			}
 			static DevBuf<unsigned long long> traceBuf;  // profiling aid: RXGPU_TC_TRACE=<file> dumps per-tile timestamps of CTA 0
 			const char* tracePath = std::getenv("RXGPU_TC_TRACE");
 			if (tracePath && b == 0) {
@@ -402,7 +420,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			}
 			cudaLaunchConfig_t cfg{};
 			cfg.gridDim = dim3(grid);
-			cfg.blockDim = dim3(kTqThreads);
+			cfg.blockDim = dim3(wide ? kTwThreads : kTqThreads);
 			cfg.dynamicSmemBytes = smem;
 			cfg.stream = st;
 			cudaLaunchAttribute attr[1];
@@ -412,7 +430,15 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			attr[0].val.clusterDim.z = 1;
 			cfg.attrs = attr;
 			cfg.numAttrs = 1;
-			if (pairMma) {
+			if (wide) {
+				if (cluster == 4) {
+					RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_w<4>, a));
+				} else if (cluster == 2) {
+					RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_w<2>, a));
+				} else {
+					RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_w<1>, a));
+				}
+			} else if (pairMma) {
 				RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q2, a));
 			} else if (cluster == 4) {
 				RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q<4>, a));
@@ -443,7 +469,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			}
 		}
 		g_stats.tc_cluster = uint32_t(cluster);
-		g_stats.tc_kernel = pairMma ? 3 : 2;
+		g_stats.tc_kernel = wide ? 4 : (pairMma ? 3 : 2);
 		g_stats.query_tile = uint32_t(kTqQueries * cluster);
 		g_stats.algorithmic_bytes += uint64_t((qblocks + cluster - 1) / cluster) * (uint64_t(ix->size) * pitchBf * 2 + uint64_t(ix->size) * 4) +
 									 uint64_t(nq) * pitchBf * 2;
@@ -911,12 +937,12 @@ int rxgpu_set_query_tile(rxgpu_index* ix, uint32_t qt) {
 	return 0;
 }
 int rxgpu_set_tensor_core_filter(rxgpu_index* ix, int mode) {
-	if (!ix || mode < 0 || mode > 7) {
-		return fail(RXGPU_ERR_PARAMS, "rxgpu: tensor-core filter mode must be in 0..7");
+	if (!ix || mode < 0 || mode > 10) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: tensor-core filter mode must be in 0..10");
 	}
 	ix->tc_mode = uint32_t(mode >= 3 ? 1 : mode);
-	ix->tc_variant = (mode == 3 || mode == 4 || mode == 7) ? uint32_t(mode) : 0u;
-	ix->tc_cluster_max = mode == 5 ? 1u : (mode == 6 ? 4u : 0u);
+	ix->tc_variant = (mode == 3 || mode == 4 || mode == 7) ? uint32_t(mode) : (mode >= 8 ? 8u : 0u);
+	ix->tc_cluster_max = (mode == 5 || mode == 10) ? 1u : ((mode == 6 || mode == 9) ? 4u : 0u);
 	return 0;
 }
 int rxgpu_set_profile(int on) {

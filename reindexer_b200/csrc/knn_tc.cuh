@@ -102,6 +102,11 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
 				 "r"(bytes), "r"(smem_u32(bar))
 				 : "memory");
 }
+// warm the L2 with a block this SM will copy a few tiles from now: the later bulk copy then pays the L2 latency, not the HBM one,
+// which a shared-memory ring of only one or two tiles cannot hide
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+	asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_load_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
 					 smem_u32(dst)),

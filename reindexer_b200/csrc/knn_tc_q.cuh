@@ -52,6 +52,7 @@ struct TqArgs {
 	int metric;
 	unsigned long long* trace;  // profiling aid (RXGPU_TC_TRACE): per-tile timestamps of CTA 0, or nullptr
 	uint32_t trace_first;       // first local tile index recorded (RXGPU_TC_TRACE_FIRST)
+	uint32_t prefetch;          // L2 prefetch distance of the producers in tiles (0 = off)
 };
 
 constexpr uint32_t kTqVwSlots = 8;  // ring of per-tile (||v||, w) blocks, filled kTqVwAhead tiles ahead by the epilogue itself
@@ -231,6 +232,12 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 						}
 					} else {
 						bulk_load(dst, src, nsub * kTqSubBytes, &full_bar[stage]);  // the K chunks of a tile are contiguous
+					}
+					if (a.prefetch && uint64_t(t) + uint64_t(a.prefetch) * ncl < ntiles) {  // my share of the same stage, a.prefetch tiles ahead
+						const unsigned char* ahead = src + size_t(a.prefetch) * ncl * a.kchunks * kTqSubBytes;
+						for (uint32_t sub = crank; sub < nsub; sub += kCluster) {
+							bulk_prefetch_l2(ahead + size_t(sub) * kTqSubBytes, kTqSubBytes);
+						}
 					}
 					if (++stage == a.stages) {
 						stage = 0;

@@ -48,6 +48,13 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
 	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
 	asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
+// same, without release semantics: for hand-offs whose payload is tensor memory (ordered by the tcgen05 fences around the
+// arrive), so that the arrive does not wait for this thread's outstanding global stores and atomics (measured: 0.8 us per tile)
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t* bar, uint32_t cta) {
+	uint32_t remote;
+	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+	asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
 // wait on a local barrier whose arrivals come from the peer CTA
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
 	asm volatile(
@@ -129,6 +136,12 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q2(const TqArgs a
 					const unsigned char* src = tile_src + size_t(kT2SubsPerStage * kp) * kTqSubBytes;
 					for (uint32_t sub = 0; sub < nsub; ++sub) {
 						bulk_load(dst + sub * kT2SubBytes, src + size_t(sub) * kTqSubBytes, kT2SubBytes, &full_bar[stage]);
+					}
+					if (a.prefetch && uint64_t(t) + uint64_t(a.prefetch) * ncl < ntiles) {
+						const unsigned char* ahead = src + size_t(a.prefetch) * ncl * a.kchunks * kTqSubBytes;
+						for (uint32_t sub = 0; sub < nsub; ++sub) {
+							bulk_prefetch_l2(ahead + size_t(sub) * kTqSubBytes, kT2SubBytes);
+						}
 					}
 					if (++stage == a.stages) {
 						stage = 0;
@@ -270,7 +283,7 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q2(const TqArgs a
 			asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 			__syncwarp();
 			if (lane == 0) {
-				mbar_arrive_cluster(&acc_empty[acc], 0);
+				mbar_arrive_cluster_relaxed(&acc_empty[acc], 0);
 			}
 			if (threadIdx.x == 64) {
 				TQ_TRACE(6, it);

@@ -11,3 +11,6 @@ print("mean per-tile period (ns), epilogue full_done:", np.diff(d[:,5]).mean())
 print("ep: wait_full", (d[:,5]-d[:,4]).mean(), "ld+arrive", (d[:,6]-d[:,5]).mean(), "compute", (d[:,7]-d[:,6]).mean(), "bar", (d[:,8]-d[:,7]).mean())
 print("issuer: wait acc_empty", (d[:,1]-d[:,0]).mean(), "wait first full", (d[:,2]-d[:,1]).mean(), "issue rest", (d[:,3]-d[:,2]).mean())
 print("producer: wait empty at tile start", (d[:,10]-d[:,9]).mean())
+raw=np.loadtxt(sys.argv[1],dtype=np.uint64).astype(np.int64)
+if raw.shape[1] > 11 and raw[40:200,11].max() > 0:
+    print("issuer: time inside 'issue rest' spent waiting for the later stages' data (ns):", raw[40:200,11].mean())
