@@ -21,6 +21,7 @@
 #include "knn_tc.cuh"
 #include "knn_tc_q2.cuh"
 #include "knn_tc_w.cuh"
+#include "knn_tc_q4.cuh"
 
 using namespace rxgpu;
 
@@ -315,26 +316,35 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 	g_stats.launches += 2;
 	const uint32_t ntiles = uint32_t((ix->size + kTcTileRows - 1) / kTcTileRows);
 	bool launched = false;
-	if ((ix->tc_variant == 0 || ix->tc_variant == 7 || ix->tc_variant == 8) && kchunks <= kTqMaxKchunks) {
+	if ((ix->tc_variant == 0 || ix->tc_variant == 7 || ix->tc_variant == 8 || ix->tc_variant == 11) && kchunks <= kTqMaxKchunks) {
 		// second-generation filter: query block in TMEM, deep TMA ring, row tiles multicast to a cluster of up to 4 CTAs
 		const uint32_t qblocks = (nq + kTqQueries - 1) / kTqQueries;
 		// mode 7: the CTA pair multiplies as one (cta_group::2), each SM stages half of every row tile
 		const bool pairMma = ix->tc_variant == 7 && qblocks >= 2 && ix->sm_count >= 2;
 		// mode 8..10: one accumulator of 128 rows (UMMA N = 128 runs the tensor pipe at its full rate, N = 64 at 67 %)
 		const bool wide = ix->tc_variant == 8;
-		auto smemOf = [&](uint32_t st) { return pairMma ? t2_smem_bytes(st) : (wide ? tw_smem_bytes(st) : tq_smem_bytes(st)); };
+		// mode 11: four MMA issuers (two per tile, splitting its K range)
+		const bool four = ix->tc_variant == 11;
+		auto smemOf = [&](uint32_t st) {
+			return pairMma ? t2_smem_bytes(st) : (wide ? tw_smem_bytes(st) : (four ? t4_smem_bytes(st) : tq_smem_bytes(st)));
+		};
 		uint32_t stages = 2;
 		while (smemOf(stages + 1) <= kTcSmemLimit && stages < 64) {
 			++stages;
 		}
 		const size_t smem = smemOf(stages);
+		if (four) {
+			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q4<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q4<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q4<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+		}
 		if (wide) {
 			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_w<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
 			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_w<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
 			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_w<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
 		}
 		RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q2, cudaFuncAttributeMaxDynamicSharedMemorySize, int(t2_smem_bytes(pairMma ? stages : 2))));
-		if (!wide && !pairMma) {
+		if (!wide && !pairMma && !four) {
 			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
 			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
 			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -349,7 +359,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 		for (;;) {  // how many clusters of this size can be resident at once (GPC boundaries strand SMs for size 4)
 			cudaLaunchConfig_t cfg{};
 			cfg.gridDim = dim3(unsigned(ix->sm_count) / cluster * cluster);
-			cfg.blockDim = dim3(wide ? kTwThreads : kTqThreads);
+			cfg.blockDim = dim3(wide ? kTwThreads : (four ? kT4Threads : kTqThreads));
 			cfg.dynamicSmemBytes = smem;
 			cudaLaunchAttribute attr[1];
 			attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -359,7 +369,10 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			cfg.attrs = attr;
 			cfg.numAttrs = 1;
 			int maxClusters = 0;
-			cudaError_t e = wide && cluster == 4 ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_w<4>, &cfg)
+			cudaError_t e = four && cluster == 4 ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q4<4>, &cfg)
+							: four && cluster == 2 ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q4<2>, &cfg)
+							: four				   ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q4<1>, &cfg)
+							: wide && cluster == 4 ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_w<4>, &cfg)
 							: wide && cluster == 2 ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_w<2>, &cfg)
 							: wide				   ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_w<1>, &cfg)
 							: pairMma			   ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q2, &cfg)
@@ -401,7 +414,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			a.metric = ix->metric;
 			{
 				static const char* pf = std::getenv("RXGPU_TC_PREFETCH");  // tuning aid: L2 prefetch distance in tiles
-				a.prefetch = pf ? uint32_t(std::atoi(pf)) : (wide ? 2u : 3u);
+				a.prefetch = pf ? uint32_t(std::atoi(pf)) : 0u;  // measured: no effect (the ring is not what limits the kernel), off by default
 			}
 			static DevBuf<unsigned long long> traceBuf;  // profiling aid: RXGPU_TC_TRACE=<file> dumps per-tile timestamps of CTA 0
 			const char* tracePath = std::getenv("RXGPU_TC_TRACE");
@@ -420,7 +433,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			}
 			cudaLaunchConfig_t cfg{};
 			cfg.gridDim = dim3(grid);
-			cfg.blockDim = dim3(wide ? kTwThreads : kTqThreads);
+			cfg.blockDim = dim3(wide ? kTwThreads : (four ? kT4Threads : kTqThreads));
 			cfg.dynamicSmemBytes = smem;
 			cfg.stream = st;
 			cudaLaunchAttribute attr[1];
@@ -430,7 +443,15 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			attr[0].val.clusterDim.z = 1;
 			cfg.attrs = attr;
 			cfg.numAttrs = 1;
-			if (wide) {
+			if (four) {
+				if (cluster == 4) {
+					RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q4<4>, a));
+				} else if (cluster == 2) {
+					RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q4<2>, a));
+				} else {
+					RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q4<1>, a));
+				}
+			} else if (wide) {
 				if (cluster == 4) {
 					RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_w<4>, a));
 				} else if (cluster == 2) {
@@ -469,7 +490,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			}
 		}
 		g_stats.tc_cluster = uint32_t(cluster);
-		g_stats.tc_kernel = wide ? 4 : (pairMma ? 3 : 2);
+		g_stats.tc_kernel = four ? 5 : (wide ? 4 : (pairMma ? 3 : 2));
 		g_stats.query_tile = uint32_t(kTqQueries * cluster);
 		g_stats.algorithmic_bytes += uint64_t((qblocks + cluster - 1) / cluster) * (uint64_t(ix->size) * pitchBf * 2 + uint64_t(ix->size) * 4) +
 									 uint64_t(nq) * pitchBf * 2;
@@ -937,12 +958,12 @@ int rxgpu_set_query_tile(rxgpu_index* ix, uint32_t qt) {
 	return 0;
 }
 int rxgpu_set_tensor_core_filter(rxgpu_index* ix, int mode) {
-	if (!ix || mode < 0 || mode > 10) {
-		return fail(RXGPU_ERR_PARAMS, "rxgpu: tensor-core filter mode must be in 0..10");
+	if (!ix || mode < 0 || mode > 13) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: tensor-core filter mode must be in 0..13");
 	}
 	ix->tc_mode = uint32_t(mode >= 3 ? 1 : mode);
-	ix->tc_variant = (mode == 3 || mode == 4 || mode == 7) ? uint32_t(mode) : (mode >= 8 ? 8u : 0u);
-	ix->tc_cluster_max = (mode == 5 || mode == 10) ? 1u : ((mode == 6 || mode == 9) ? 4u : 0u);
+	ix->tc_variant = (mode == 3 || mode == 4 || mode == 7) ? uint32_t(mode) : (mode >= 11 ? 11u : (mode >= 8 ? 8u : 0u));
+	ix->tc_cluster_max = (mode == 5 || mode == 10 || mode == 13) ? 1u : ((mode == 6 || mode == 9 || mode == 12) ? 4u : 0u);
 	return 0;
 }
 int rxgpu_set_profile(int on) {

@@ -38,7 +38,8 @@ def test_tc_path_is_bit_identical_to_exact_scan(metric, n, dim, nq, k):
     # 5 / 6 = queries in TMEM with single CTAs / clusters of up to 4 CTAs (the default above uses CTA pairs),
     # 7 = queries in TMEM, the CTA pair multiplies as one (tcgen05.mma.cta_group::2, half a row tile staged per SM),
     # 8 / 9 / 10 = queries in TMEM, one accumulator of 128 rows (UMMA N = 128), CTA pairs / clusters of up to 4 / single CTAs
-    for mode, kernel in ((3, 1), (4, 1), (5, 2), (6, 2), (7, 3), (8, 4), (9, 4), (10, 4)):
+    # 11 / 12 / 13 = queries in TMEM, four MMA issuers (two per tile), CTA pairs / clusters of up to 4 / single CTAs
+    for mode, kernel in ((3, 1), (4, 1), (5, 2), (6, 2), (7, 3), (8, 4), (9, 4), (10, 4), (11, 5), (12, 5), (13, 5)):
         gpu.set_tensor_core_filter(mode)
         d2, l2, c2 = gpu.search_knn(queries, k)
         s2 = rx.last_search_stats()
