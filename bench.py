@@ -284,6 +284,7 @@ def run_ours(args):
         value = world * NQ / (ms_per_step / 1000.0)
         e2e_value = world * NQ / (e2e_s / args.steps)
         peak, peak_src = load_peaks()
+        peaks_all = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         if tc_used:  # dominant kernel = knn_tc_filter: bf16 shadow rows + row norms + the resident query block, per launch
             per_launch_bytes = rows * DIM * 2 + rows * 8 + qt * DIM * 2
             kernel_name = "knn_tc_filter_q (tcgen05 bf16 filter, queries in TMEM, certified bound) + knn_rerank (exact fp32)"
@@ -310,6 +311,7 @@ def run_ours(args):
                          "traffic": (None if rows != 10_000_000 else 15.4224e9 if tc_used else 30.7201e9),
                          "peak_source": peak_src, "kernel": "knn_tc_filter_q" if tc_used else "knn_scan_warp",
                          "tensor_tflops": (2.0 * rows * DIM * qt / (avg_launch_ms * 1e-3) / 1e12) if tc_used and avg_launch_ms > 0 else None,
+                         "tensor_peak_tflops": peaks_all.get("bf16_tflops"), "tensor_peak_sustained_tflops": peaks_all.get("bf16_tflops_sustained"),
                          "bytes_per_launch": per_launch_bytes, "avg_launch_ms": avg_launch_ms, "launches_timed": scan_launches,
                          "kernel_share_of_step": scan_ms / ms_total if ms_total else None},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": NQ * DIM * 4,
