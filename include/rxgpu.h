@@ -162,6 +162,9 @@ int rxgpu_hnsw_search_knn(const rxgpu_index*, uint32_t nq, const float* queries 
 int rxgpu_hnsw_search_knn_device(const rxgpu_index*, uint32_t nq, const float* d_queries, uint32_t k, uint32_t ef, float* d_out_dist,
 								 uint32_t* d_out_idx, uint32_t* d_out_count, uint32_t* d_stats /* nq x 2 or NULL */, void* stream);
 
+/* labels of n shard-local internal indices (device pointers; enqueued on `stream`): the HNSW device search returns indices, the
+ * multi-GPU merge needs labels */
+int rxgpu_gather_labels_device(const rxgpu_index*, uint64_t n, const uint32_t* d_idx, uint64_t* d_out_label, void* stream);
 /* HierarchicalNSWImpl::SearchRange                              hnswlib/hnswalg.h:2015-2070
  * The ef-search result seeds a breadth-first expansion over level-0 neighbours with dist < radius (strict); the result is that
  * closure (independent of traversal order).  Writes the best min(*out_n, max_out) results best-first (ties by label);

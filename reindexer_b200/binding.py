@@ -110,6 +110,7 @@ _SIGNATURES = {
     "rxgpu_select_knn": (C.c_int, [C.c_void_p, _f32p, C.POINTER(SelectParams), C.c_uint64, _i32p, _f32p, _u64p]),
     "rxgpu_hnsw_import": (C.c_int, [C.c_void_p, C.POINTER(HnswGraph)]),
     "rxgpu_hnsw_search_knn": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, C.c_uint32, C.c_uint32, _f32p, _u64p, _u32p, _u32p]),
+    "rxgpu_gather_labels_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rxgpu_hnsw_search_range": (C.c_int, [C.c_void_p, _f32p, C.c_float, C.c_uint32, C.c_uint64, _f32p, _u64p, C.POINTER(C.c_uint64)]),
     "rxgpu_hnsw_search_knn_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -294,6 +295,13 @@ class GpuBruteforceSearch:
         _check(self._lib.rxgpu_hnsw_search_knn(self._h, nq, _p(q, _f32p), k, ef, _p(d, _f32p), _p(l, _u64p), _p(c, _u32p),
                                                _p(st, _u32p)))
         return (d, l, c, st) if with_stats else (d, l, c)
+
+    def hnsw_search_knn_device(self, nq, d_queries_ptr, k, ef, d_dist_ptr, d_idx_ptr, d_count_ptr, d_stats_ptr=0, stream=0):
+        _check(self._lib.rxgpu_hnsw_search_knn_device(self._h, nq, d_queries_ptr, k, ef, d_dist_ptr, d_idx_ptr, d_count_ptr,
+                                                      d_stats_ptr or None, stream or None))
+
+    def gather_labels_device(self, n, d_idx_ptr, d_label_ptr, stream=0):
+        _check(self._lib.rxgpu_gather_labels_device(self._h, n, d_idx_ptr, d_label_ptr, stream or None))
 
     def hnsw_search_range(self, query, radius: float, ef: int, max_out: int | None = None):
         q = np.ascontiguousarray(query, dtype=np.float32)

@@ -428,6 +428,13 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_range_expand(RangeArgs a, u
 	}
 }
 
+__global__ void gather_labels_kernel(const uint64_t* labels, uint64_t size, uint64_t n, const uint32_t* idx, uint64_t* out) {
+	const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+	if (i < n) {
+		out[i] = idx[i] < size ? labels[idx[i]] : ~0ull;
+	}
+}
+
 }  // namespace
 
 struct rxgpu_hnsw_device {
@@ -724,6 +731,25 @@ int rxgpu_hnsw_search_range(const rxgpu_index* ix, const float* query, float rad
 		}
 	} catch (const std::bad_alloc&) {
 		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
+	}
+	return 0;
+}
+
+int rxgpu_gather_labels_device(const rxgpu_index* ix, uint64_t n, const uint32_t* d_idx, uint64_t* d_out_label, void* stream) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	if (n == 0) {
+		return 0;
+	}
+	if (!d_idx || !d_out_label) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ix->stream;
+	gather_labels_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(ix->d_labels, ix->size, n, d_idx, d_out_label);
+	RX_CUDA(cudaGetLastError());
+	if (!stream) {
+		RX_CUDA(cudaStreamSynchronize(st));
 	}
 	return 0;
 }

@@ -31,6 +31,7 @@ class ShardedBruteforceSearch:
         self.total_rows = int(sizes.sum())
         self._local_search = local_search or self._device_search
         self._local_tie_rows = local_tie_rows or self._device_tie_rows
+        self.replay_ties = True  # the brute-force map reproduces the reference's heap tie rule; approximate maps have none
 
     # -- plumbing ----------------------------------------------------------------------------------------------------------
     def _all_gather_small(self, t: torch.Tensor) -> torch.Tensor:
@@ -89,7 +90,7 @@ class ShardedBruteforceSearch:
         out_d = np.zeros((nq, k), np.float32)
         out_l = np.zeros((nq, k), np.uint64)
         out_d[:, :k_eff], out_l[:, :k_eff] = rd, rl
-        for q in np.nonzero(need_tie)[0]:  # rare: bit-equal distances straddle the k-th place -> replay the reference's heap rule
+        for q in (np.nonzero(need_tie)[0] if self.replay_ties else ()):  # rare: bit-equal distances straddle the k-th place -> replay the reference's heap rule
             c = int(rc[q])
             dstar = float(rd[q, c - 1])
             td, ti, tl, tc = self._local_tie_rows(d_queries[q], dstar, k_eff)
@@ -112,3 +113,28 @@ class ShardedBruteforceSearch:
                                     (fd[order], fg[order], fl[order]))
             out_d[q, :len(td2)], out_l[q, :len(td2)] = td2, tl2
         return out_d, out_l, rc
+
+
+class ShardedHnswSearch(ShardedBruteforceSearch):
+    """Multi-GPU HNSW: every GPU holds an independent sub-graph over its row range (built by the reference's
+    inserter over that shard, imported with hnsw_import), all shards are searched for every query, and the per-shard top-k lists
+    are merged exactly like the brute-force shards (one all-gather).  Recall is that of the per-shard graphs; there is no
+    reference tie rule to replay (HierarchicalNSW::SearchKnn orders bit-equal distances by heap mechanics), results are ordered
+    by (distance, global row)."""
+
+    def __init__(self, local_index, shard_rows: int, ef: int, group=None, device=None, local_search=None):
+        super().__init__(local_index, shard_rows, group=group, device=device, local_search=local_search)
+        self.ef = ef
+        self.replay_ties = False
+
+    def _device_search(self, d_queries: torch.Tensor, k1: int):
+        nq = d_queries.shape[0]
+        od = torch.zeros((nq, k1), dtype=torch.float32, device=self.device)
+        oi = torch.zeros((nq, k1), dtype=torch.int32, device=self.device)
+        ol = torch.zeros((nq, k1), dtype=torch.int64, device=self.device)
+        oc = torch.zeros((nq,), dtype=torch.int32, device=self.device)
+        stream = torch.cuda.current_stream().cuda_stream
+        self.idx.hnsw_search_knn_device(nq, d_queries.data_ptr(), k1, max(self.ef, k1), od.data_ptr(), oi.data_ptr(), oc.data_ptr(),
+                                        0, stream)
+        self.idx.gather_labels_device(nq * k1, oi.data_ptr(), ol.data_ptr(), stream)
+        return od, oi, ol, oc

@@ -149,3 +149,57 @@ def test_hnsw_search_range_matches_reference(metric, dim):
     assert len(l2) == 5 and t2 == tr2 and t2 > n * 0.99 and (l2 == lr2).all()  # an unbounded radius floods the reachable graph
     fresh = rx.GpuBruteforceSearch(metric, dim, 10)
     assert fresh.hnsw_search_range(queries[0], 1.0, ef)[2] == 0  # empty index: empty result (:2017-2019)
+
+
+def test_sharded_hnsw_two_shards_on_one_gpu():
+    """§8e for HNSW: two independent sub-graphs (one per row range), both searched on the device, merged like brute-force shards.
+    world = 1 here, so the two shards are merged through rxgpu_merge_shards directly; the NCCL exchange itself is the one the
+    brute-force path uses."""
+    import torch
+    from reindexer_b200 import binding as B
+
+    metric, n, dim, k, ef, nq = rx.L2, 12000, 48, 10, 96, 64
+    half = n // 2
+    vecs, labels = O.synth_matrix(2100, n, dim), O.row_labels(n)
+    queries = O.synth_matrix(2101, nq, dim)
+    shards, refs = [], []
+    for s in range(2):
+        ref = O.RefHnsw(metric, dim, half, M=16, ef_construction=200, seed=100 + s, multithread=False)
+        ref.add_batch(labels[s * half:(s + 1) * half], vecs[s * half:(s + 1) * half])
+        g = ref.export(with_vectors=False)
+        gpu = rx.GpuBruteforceSearch(metric, dim, half)
+        gpu.add_points(labels[s * half:(s + 1) * half], vecs[s * half:(s + 1) * half])
+        gpu.hnsw_import(g)
+        shards.append(gpu)
+        refs.append(ref)
+    dq = torch.from_numpy(queries).cuda()
+    D = np.zeros((2, nq, k), np.float32)
+    I = np.zeros((2, nq, k), np.uint32)
+    L = np.zeros((2, nq, k), np.uint64)
+    Cn = np.zeros((2, nq), np.uint32)
+    for s, gpu in enumerate(shards):
+        od = torch.zeros((nq, k), dtype=torch.float32, device="cuda")
+        oi = torch.zeros((nq, k), dtype=torch.int32, device="cuda")
+        ol = torch.zeros((nq, k), dtype=torch.int64, device="cuda")
+        oc = torch.zeros((nq,), dtype=torch.int32, device="cuda")
+        gpu.hnsw_search_knn_device(nq, dq.data_ptr(), k, ef, od.data_ptr(), oi.data_ptr(), oc.data_ptr())
+        gpu.gather_labels_device(nq * k, oi.data_ptr(), ol.data_ptr())
+        torch.cuda.synchronize()
+        D[s], I[s], L[s], Cn[s] = od.cpu().numpy(), oi.cpu().numpy().view(np.uint32), ol.cpu().numpy().view(np.uint64), oc.cpu().numpy()
+    rd, rg, rl, rc, _ = B.merge_shards(k, D, I, L, Cn, np.array([0, half], np.uint64))
+    # the same thing with the reference's CPU searches per shard, merged by (dist, label)
+    same = 0
+    for i in range(nq):
+        cand = []
+        for s in range(2):
+            dr, lr = refs[s].search_knn(queries[i], k, ef)
+            cand += list(zip(dr.tolist(), lr.tolist()))
+        cand.sort()
+        same += int([c[1] for c in cand[:k]] == rl[i].tolist())
+    assert same >= nq - 2, same
+    # recall of the sharded search against exact brute force over all rows
+    full = rx.GpuBruteforceSearch(metric, dim, n)
+    full.add_points(labels, vecs)
+    db, lb, _ = full.search_knn(queries, k)
+    recall = np.mean([len(set(rl[i]) & set(lb[i])) / k for i in range(nq)])
+    assert recall > 0.6, recall

@@ -92,3 +92,66 @@ def test_sharded_search_world2_matches_sequential_reference():
             assert c[i] == len(dr)
             assert (l[i, :c[i]] == lr).all(), (k, i, l[i, :c[i]], lr)
             assert (d[i, :c[i]] == dr).all()
+
+
+def _hnsw_worker(rank, world, port, n_per, seed, out_q):
+    sys.path.insert(0, ROOT)
+    from reindexer_b200.sharded import ShardedHnswSearch
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(seed)
+    n = n_per * world
+    vecs = rng.normal(size=(n, 8)).astype(np.float32)
+    labels = (rng.permutation(n).astype(np.uint64) << np.uint64(32))
+    lo = rank * n_per
+    my_vecs, my_labels = vecs[lo:lo + n_per], labels[lo:lo + n_per]
+    # an APPROXIMATE local search (a graph search misses some rows): this shard only "sees" the rows with an even local index
+    seen = np.arange(0, n_per, 2)
+
+    def local_search(d_queries, k1):
+        q = d_queries.numpy()
+        nq = q.shape[0]
+        od, oi = torch.zeros((nq, k1), dtype=torch.float32), torch.zeros((nq, k1), dtype=torch.int32)
+        ol, oc = torch.zeros((nq, k1), dtype=torch.int64), torch.zeros((nq,), dtype=torch.int32)
+        for i in range(nq):
+            d = ((my_vecs[seen] - q[i]) ** 2).sum(axis=1).astype(np.float32)
+            order = np.argsort(d, kind="stable")[:k1]
+            c = len(order)
+            od[i, :c] = torch.from_numpy(d[order])
+            oi[i, :c] = torch.from_numpy(seen[order].astype(np.int32))
+            ol[i, :c] = torch.from_numpy(my_labels[seen[order]].view(np.int64))
+            oc[i] = c
+        return od, oi, ol, oc
+
+    sh = ShardedHnswSearch(None, n_per, ef=32, device=torch.device("cpu"), local_search=local_search)
+    queries = rng.normal(size=(7, 8)).astype(np.float32)
+    res = {k: sh.search_knn(queries, k) for k in (1, 5, 10)}
+    if rank == 0:
+        out_q.put((vecs, labels, queries, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_hnsw_merge_world2():
+    """multi-GPU HNSW = independent per-shard searches + the same one-all-gather merge: the result is the global top-k of the union of
+    what the shards returned (no tie replay)"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    n_per = 40
+    procs = [ctx.Process(target=_hnsw_worker, args=(r, 2, port, n_per, 77, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    vecs, labels, queries, res = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    visible = np.concatenate([np.arange(0, n_per, 2), n_per + np.arange(0, n_per, 2)])
+    for k, (d, l, c) in res.items():
+        for i in range(len(queries)):
+            dist_all = ((vecs[visible] - queries[i]) ** 2).sum(axis=1).astype(np.float32)
+            order = np.argsort(dist_all, kind="stable")[:k]
+            assert c[i] == k
+            assert (l[i, :k] == labels[visible[order]]).all()
+            assert np.allclose(d[i, :k], dist_all[order])
