@@ -223,6 +223,14 @@ int rxgpu_ft_create(rxgpu_ft_index** out, uint32_t total_docs, uint32_t nfields,
 					const uint8_t* removed, int device);
 void rxgpu_ft_destroy(rxgpu_ft_index*);
 int rxgpu_ft_add_postings(rxgpu_ft_index*, const rxgpu_ft_postings* list, uint32_t* out_id); /* uploads one word's postings to HBM */
+/* The same from the reference's packed container: `data` = PackedIdRelVec::data_ (core/ft/idrelset.h:154-281, records written by
+ * IdRelType::packWithoutArrayIdxs, idrelset.cc:139-183), `count` = its size().  Decoded once on the host (the varint-delta stream has
+ * no skip pointers) and uploaded as SoA.  Lists that contain array indexes (arrayFoundPos_ set) are not supported (errParams). */
+int rxgpu_ft_add_postings_packed(rxgpu_ft_index*, const uint8_t* data, uint64_t len, uint32_t count, uint32_t* out_id);
+/* The decoder alone (no device involved): fills doc_ids[count], pos_begin[count + 1] and at most max_positions positions; *npos =
+ * number of positions in the list (call with max_positions = 0 to size the buffer). */
+int rxgpu_ft_decode_packed(const uint8_t* data, uint64_t len, uint32_t count, uint32_t* doc_ids, uint32_t* pos_begin,
+						   uint32_t* positions, uint64_t max_positions, uint64_t* npos);
 /* excluded: u8[total_docs] (FtMergeStatuses::Statuses docsExcluded) or NULL; rank_sort_type: reindexer::RankSortType.
  * Writes min(*out_n, max_out) entries; *out_n = number of merged documents. */
 int rxgpu_ft_merge(rxgpu_ft_index*, const rxgpu_ft_config* cfg, uint32_t nterms, const rxgpu_ft_term* terms, const uint8_t* excluded,

@@ -145,8 +145,23 @@ def ref_lib():
         lib.ref_ft_calc_term_rank.restype = C.c_int
         lib.ref_ft_calc_term_rank.argtypes = [C.c_uint32, C.POINTER(Config), C.POINTER(Term), C.c_float, C.c_double, C.c_double, C.c_uint32,
                                               _u32p, _u32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.POINTER(C.c_int)]
+        lib.ref_ft_pack_list.restype = C.c_int64
+        lib.ref_ft_pack_list.argtypes = [C.POINTER(Postings), _u8p, C.c_uint64]
         _ref = lib
     return _ref
+
+
+def ref_pack_list(doc_ids, pos_begin, positions):
+    """the reference's packed posting stream (PackedIdRelVec::data_) of one list, produced by the reference's own encoder"""
+    d = np.ascontiguousarray(doc_ids, np.uint32)
+    b = np.ascontiguousarray(pos_begin, np.uint32)
+    q = np.ascontiguousarray(positions, np.uint32)
+    pl = Postings(len(d), d.ctypes.data_as(_u32p), b.ctypes.data_as(_u32p), q.ctypes.data_as(_u32p))
+    cap = 16 + len(d) * 16 + len(q) * 12
+    out = np.zeros(cap, np.uint8)
+    n = ref_lib().ref_ft_pack_list(C.byref(pl), out.ctypes.data_as(_u8p), cap)
+    assert n >= 0, n
+    return out[:n].copy()
 
 
 def port_lib():

@@ -228,4 +228,27 @@ int ref_ft_calc_term_rank(uint32_t nfields, const ft_config* cfg, const ft_term*
 	}
 }
 
+// The reference's packed posting stream for one list: IdRelType::packWithoutArrayIdxs (core/ft/idrelset.cc:139-183) applied record
+// by record with the state chain of PackedIdRelVec::insert_back (core/ft/idrelset.h:226-260; data_ is private, so the loop is
+// repeated here around the reference's own encoder).  Returns the number of bytes, or -1 when `cap` is too small.
+int64_t ref_ft_pack_list(const ft_postings* list, uint8_t* out, uint64_t cap) {
+	try {
+		uint64_t p = 0;
+		uint32_t lastId = 0, lastField = 0;
+		for (uint32_t i = 0; i < list->ndocs; ++i) {
+			const reindexer::IdRelType r = makeRel(*list, i);
+			if (p + r.maxpackedsize() > cap) {
+				return -1;
+			}
+			p += r.packWithoutArrayIdxs(out + p, lastId, lastField);
+			lastId = r.Id();
+			lastField = r.Pos()[0].field();
+		}
+		return int64_t(p);
+	} catch (const std::exception& e) {
+		g_err = e.what();
+		return -2;
+	}
+}
+
 }  // extern "C"

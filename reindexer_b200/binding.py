@@ -117,6 +117,8 @@ _SIGNATURES = {
     "rxgpu_ft_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, _u32p, _f32p, _u8p, C.c_int]),
     "rxgpu_ft_destroy": (None, [C.c_void_p]),
     "rxgpu_ft_add_postings": (C.c_int, [C.c_void_p, C.POINTER(FtPostings), _u32p]),
+    "rxgpu_ft_add_postings_packed": (C.c_int, [C.c_void_p, _u8p, C.c_uint64, C.c_uint32, _u32p]),
+    "rxgpu_ft_decode_packed": (C.c_int, [_u8p, C.c_uint64, C.c_uint32, _u32p, _u32p, _u32p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "rxgpu_ft_merge": (C.c_int, [C.c_void_p, C.POINTER(FtConfig), C.c_uint32, C.POINTER(FtTerm), _u8p, C.c_int, C.c_uint64, C.c_void_p,
                                  C.POINTER(C.c_uint64)]),
     "rxgpu_ft_last_stats": (None, [C.POINTER(FtStats)]),
@@ -385,6 +387,13 @@ class GpuFtIndex:
         _check(self._lib.rxgpu_ft_add_postings(self._h, C.byref(pl), C.byref(out)))
         return out.value
 
+    def add_postings_packed(self, data, count: int) -> int:
+        """data: the bytes of a PackedIdRelVec (the reference's varint-delta posting stream), count: its number of records"""
+        b = np.ascontiguousarray(data, np.uint8)
+        out = C.c_uint32(0)
+        _check(self._lib.rxgpu_ft_add_postings_packed(self._h, _p(b, _u8p), len(b), count, C.byref(out)))
+        return out.value
+
     def merge(self, cfg: dict, field_cfg: list, terms: list, excluded=None, rank_sort_type=1, max_out=None):
         """cfg / field_cfg: dicts with the FtConfig / FtFieldConfig member names; terms: dicts(op, boost, term_len_boost, field_boosts,
         postings, procs).  Returns a structured array (id, proc, field, normalized_proc)."""
@@ -411,3 +420,16 @@ class GpuFtIndex:
         s = FtStats()
         self._lib.rxgpu_ft_last_stats(C.byref(s))
         return {f: getattr(s, f) for f, _ in FtStats._fields_}
+
+
+def ft_decode_packed(data, count: int):
+    """host-only decoder of the reference's packed posting stream -> (doc_ids, pos_begin, positions)"""
+    b = np.ascontiguousarray(data, np.uint8)
+    npos = C.c_uint64(0)
+    lib_ = lib()
+    _check(lib_.rxgpu_ft_decode_packed(_p(b, _u8p), len(b), count, None, None, None, 0, C.byref(npos)))
+    d = np.zeros(count, np.uint32)
+    pb = np.zeros(count + 1, np.uint32)
+    ps = np.zeros(max(npos.value, 1), np.uint32)
+    _check(lib_.rxgpu_ft_decode_packed(_p(b, _u8p), len(b), count, _p(d, _u32p), _p(pb, _u32p), _p(ps, _u32p), npos.value, C.byref(npos)))
+    return d, pb, ps[:npos.value]

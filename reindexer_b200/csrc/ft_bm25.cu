@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "internal.h"
+#include "../host/packed_postings.h"
 
 using namespace rxgpu;
 
@@ -767,6 +768,60 @@ int rxgpu_ft_add_postings(rxgpu_ft_index* ft, const rxgpu_ft_postings* list, uin
 	ft->max_list = std::max(ft->max_list, l.ndocs);
 	*out_id = uint32_t(ft->lists.size() - 1);
 	return 0;
+}
+
+int rxgpu_ft_decode_packed(const uint8_t* data, uint64_t len, uint32_t count, uint32_t* doc_ids, uint32_t* pos_begin, uint32_t* positions,
+						   uint64_t max_positions, uint64_t* npos) {
+	if ((len && !data) || !npos) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	try {
+		DecodedPostings d;
+		const int rc = decodePackedPostings(data, len, count, d);
+		if (rc == -2) {
+			return fail(RXGPU_ERR_PARAMS, "rxgpu: packed posting list holds a field > 255 or a word position >= 2^24");
+		}
+		if (rc) {
+			return fail(RXGPU_ERR_PARAMS, "rxgpu: malformed packed posting list (or it contains array indexes / a different record count)");
+		}
+		*npos = d.positions.size();
+		if (doc_ids) {
+			std::copy(d.doc_ids.begin(), d.doc_ids.end(), doc_ids);
+		}
+		if (pos_begin) {
+			std::copy(d.pos_begin.begin(), d.pos_begin.end(), pos_begin);
+		}
+		if (positions) {
+			std::copy(d.positions.begin(), d.positions.begin() + std::min<uint64_t>(max_positions, d.positions.size()), positions);
+		}
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
+	}
+	return 0;
+}
+
+int rxgpu_ft_add_postings_packed(rxgpu_ft_index* ft, const uint8_t* data, uint64_t len, uint32_t count, uint32_t* out_id) {
+	if (!ft || !out_id || (len && !data)) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	try {
+		DecodedPostings d;
+		const int rc = decodePackedPostings(data, len, count, d);
+		if (rc == -2) {
+			return fail(RXGPU_ERR_PARAMS, "rxgpu: packed posting list holds a field > 255 or a word position >= 2^24");
+		}
+		if (rc) {
+			return fail(RXGPU_ERR_PARAMS, "rxgpu: malformed packed posting list (or it contains array indexes / a different record count)");
+		}
+		rxgpu_ft_postings l{};
+		l.ndocs = uint32_t(d.doc_ids.size());
+		l.doc_ids = d.doc_ids.data();
+		l.pos_begin = d.pos_begin.data();
+		l.positions = d.positions.data();
+		return rxgpu_ft_add_postings(ft, &l, out_id);
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
+	}
 }
 
 void rxgpu_ft_last_stats(rxgpu_ft_stats* out) {

@@ -72,12 +72,16 @@ def load_golden_problem(g, name):
     return p
 
 
-def gpu_merge(prob, rank_sort_type=F.RANK_AND_ID):
-    """Run one problem through the product (rxgpu_ft_*); returns (result, stats)."""
+def gpu_merge(prob, rank_sort_type=F.RANK_AND_ID, packed=None):
+    """Run one problem through the product (rxgpu_ft_*); returns (result, stats).  packed: per-list byte streams of the reference's
+    PackedIdRelVec -- the lists are then uploaded through rxgpu_ft_add_postings_packed."""
     import reindexer_b200 as rx
 
     ft = rx.GpuFtIndex(prob.total_docs, prob.words, prob.avg, prob.removed)
-    ids = [ft.add_postings(d, b, p) for d, b, p in prob.lists]
+    if packed is not None:
+        ids = [ft.add_postings_packed(packed[i], len(prob.lists[i][0])) for i in range(len(prob.lists))]
+    else:
+        ids = [ft.add_postings(d, b, p) for d, b, p in prob.lists]
     terms = [dict(t, postings=[ids[int(x)] for x in t["postings"]]) for t in prob.terms]
     res = ft.merge(prob.cfg, prob.field_cfg, terms, excluded=prob.excluded, rank_sort_type=rank_sort_type)
     st = ft.last_stats()

@@ -90,3 +90,27 @@ def test_larger_corpus_three_term_or_with_preselect():
     assert st["preselected"] == 1 and len(a) > 1000
     assert_same_merge(a, b, F.RANK_AND_ID)
     assert (F.after_select_order(a)[:100] == F.after_select_order(b)[:100]).all()
+
+
+def test_packed_posting_lists_give_the_same_merge():
+    """lists handed over in the reference's packed container format (PackedIdRelVec bytes from the reference's own encoder, committed
+    in tests/golden/packed_golden.npz for one case and produced live when oracle/_ref is present)"""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "packed_golden.npz"))
+    d, b, pp = (g[f"multi_field/{k}"] for k in ("doc_ids", "pos_begin", "positions"))
+    total = int(d.max()) + 2
+    rng = np.random.default_rng(3)
+    words = rng.integers(3000, 4000, size=(total, 5)).astype(np.uint32)
+    words[0] = 0
+    p = F.FtProblem(total, words)
+    p.add_term([(p.add_list_arrays(d, b, pp), 100.0)], field_boosts=np.ones(5, np.float32))
+    a, _ = gpu_merge(p)
+    c, _ = gpu_merge(p, packed=[g["multi_field/packed"]])
+    assert_same_merge(a, c, F.RANK_AND_ID)
+    assert len(a) > 100
+    if F.ref_available():
+        for seed in range(10):
+            q = random_problem(1000 + seed, total_docs=1500, nfields=1 + seed % 3, nterms=2 + seed % 2)
+            packed = [F.ref_pack_list(*lst) for lst in q.lists]
+            x, _ = F.best_merge(q)
+            y, _ = gpu_merge(q, packed=packed)
+            assert_same_merge(x, y, F.RANK_AND_ID, ctx=f"seed {seed}")
