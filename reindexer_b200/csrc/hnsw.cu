@@ -17,6 +17,7 @@
 // lowerBound only decreases), and every candidate at or below lowerBound is in top_candidates.  Requires a graph without
 // deleted nodes (num_deleted_ == 0, the bare-bone branch of hnswalg.h:1982); distances tie only on duplicate vectors.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -453,6 +454,10 @@ struct rxgpu_hnsw_device {
 	DevBuf<unsigned int> counter;
 	DevBuf<uint32_t> range_visited, range_idx;  // SearchRange scratch: one bitmap, result/queue arrays of n entries
 	DevBuf<float> range_dist;
+	// staging of the host-pointer entry points (guarded by host_mtx; cudaMalloc per call would cost more than a small batch)
+	std::mutex host_mtx;
+	DevBuf<float> h_q, h_d;
+	DevBuf<uint32_t> h_i, h_c, h_s;
 	uint32_t slots = 0, words = 0;
 };
 
@@ -492,7 +497,12 @@ int rxgpu_hnsw_import(rxgpu_index* ix, const rxgpu_hnsw_graph* g) {
 	if (g->upper_slots) {
 		RX_CUDA(cudaMemcpy(h->upper.p, g->upper, size_t(g->upper_slots) * (1 + g->M) * 4, cudaMemcpyHostToDevice));
 	}
-	h->slots = uint32_t(ix->sm_count) * 4 * kHnswWarps;
+	{  // resident warps: the search is a chain of dependent gathers, so occupancy hides its latency; 64 registers per thread allow
+		// 8 CTAs (32 warps) per SM.  RXGPU_HNSW_CTAS_PER_SM is a tuning aid.
+		const char* e = std::getenv("RXGPU_HNSW_CTAS_PER_SM");
+		const uint32_t perSm = e ? std::max(1, std::min(16, std::atoi(e))) : 8u;
+		h->slots = uint32_t(ix->sm_count) * perSm * kHnswWarps;
+	}
 	h->words = (g->n + 31) / 32;
 	RX_CUDA(h->visited.ensure(size_t(h->slots) * h->words));
 	RX_CUDA(h->vlog.ensure(size_t(h->slots) * kVlogCap));
@@ -598,8 +608,12 @@ int rxgpu_hnsw_search_knn(const rxgpu_index* ix, uint32_t nq, const float* queri
 	if (kEff == 0) {
 		return fail(RXGPU_ERR_PARAMS, "rxgpu: k must be positive");
 	}
-	DevBuf<float> dq, dd;
-	DevBuf<uint32_t> di, dc, ds;
+	if (!ix->hnsw) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: no HNSW graph imported into this index");
+	}
+	std::lock_guard<std::mutex> hostLock(ix->hnsw->host_mtx);
+	DevBuf<float>&dq = ix->hnsw->h_q, &dd = ix->hnsw->h_d;
+	DevBuf<uint32_t>&di = ix->hnsw->h_i, &dc = ix->hnsw->h_c, &ds = ix->hnsw->h_s;
 	RX_CUDA(dq.ensure(size_t(nq) * ix->dim));
 	RX_CUDA(dd.ensure(size_t(nq) * kEff));
 	RX_CUDA(di.ensure(size_t(nq) * kEff));
