@@ -675,6 +675,11 @@ struct rxgpu_ft_index {
 	// scratch
 	DevBuf<uint32_t> mask, tmask, idoff, block_counts, scalar_u32;
 	bool idoff_clean = false;  // idoff holds kNoSlot everywhere
+	PinBuf<int32_t> h_id;  // results of the last merge (pinned: one asynchronous copy per array, one synchronisation per query)
+	PinBuf<float> h_proc;
+	PinBuf<uint8_t> h_field;
+	PinBuf<uint32_t> h_n;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	DevBuf<uint16_t> score;
 	DevBuf<unsigned long long> hist, popc;
 	DevBuf<uint8_t> excluded, tmp_field, md_field;
@@ -689,6 +694,10 @@ struct rxgpu_ft_index {
 			cudaFree(l.doc_ids);
 			cudaFree(l.pos_begin);
 			cudaFree(l.positions);
+		}
+		if (ev0) {
+			cudaEventDestroy(ev0);
+			cudaEventDestroy(ev1);
 		}
 		if (stream) {
 			cudaStreamDestroy(stream);
@@ -933,9 +942,15 @@ int rxgpu_ft_merge(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nter
 	ms.n_docs = ft->scalar_u32.p;            // [0] numDocs()
 	uint32_t* d_total_new = ft->scalar_u32.p + 1;  // [1] new docs of the current pass
 
-	cudaEvent_t e0, e1;
-	RX_CUDA(cudaEventCreate(&e0));
-	RX_CUDA(cudaEventCreate(&e1));
+	if (!ft->ev0) {
+		RX_CUDA(cudaEventCreate(&ft->ev0));
+		RX_CUDA(cudaEventCreate(&ft->ev1));
+	}
+	const cudaEvent_t e0 = ft->ev0, e1 = ft->ev1;
+	RX_CUDA(ft->h_id.ensure(maxMerged));
+	RX_CUDA(ft->h_proc.ensure(maxMerged));
+	RX_CUDA(ft->h_field.ensure(maxMerged));
+	RX_CUDA(ft->h_n.ensure(1));
 	RX_CUDA(cudaEventRecord(e0, st));
 	RX_CUDA(cudaMemsetAsync(ft->scalar_u32.p, 0, 16, st));
 	if (!trivial) {  // idoffsets_: every merge leaves the table clean again (ft_reset_idoff), so the 4 N byte fill runs only once
@@ -1117,25 +1132,22 @@ int rxgpu_ft_merge(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nter
 		g_ft_stats.launches++;
 	}
 	RX_CUDA(cudaGetLastError());
-	uint32_t n = 0;
-	RX_CUDA(cudaMemcpyAsync(&n, ms.n_docs, 4, cudaMemcpyDeviceToHost, st));
 	RX_CUDA(cudaEventRecord(e1, st));
+	// the merged documents (<= merge_limit entries, 9 bytes each) come back in full: their number is not known before the copy
+	RX_CUDA(cudaMemcpyAsync(ft->h_n.p, ms.n_docs, 4, cudaMemcpyDeviceToHost, st));
+	RX_CUDA(cudaMemcpyAsync(ft->h_id.p, ms.md_id, size_t(maxMerged) * 4, cudaMemcpyDeviceToHost, st));
+	RX_CUDA(cudaMemcpyAsync(ft->h_proc.p, ms.md_proc, size_t(maxMerged) * 4, cudaMemcpyDeviceToHost, st));
+	RX_CUDA(cudaMemcpyAsync(ft->h_field.p, ms.md_field, size_t(maxMerged), cudaMemcpyDeviceToHost, st));
 	RX_CUDA(cudaStreamSynchronize(st));
 	RX_CUDA(cudaEventElapsedTime(&g_ft_stats.device_ms, e0, e1));
 	ft->idoff_clean = !trivial;
-	cudaEventDestroy(e0);
-	cudaEventDestroy(e1);
+	const uint32_t n = ft->h_n.p[0];
 
 	// postProcessResults (merger.h:111-155) on the host: <= merge_limit entries
 	try {
-		std::vector<int32_t> ids(n);
-		std::vector<float> procs(n);
-		std::vector<uint8_t> fields(n);
-		if (n) {
-			RX_CUDA(cudaMemcpy(ids.data(), ms.md_id, size_t(n) * 4, cudaMemcpyDeviceToHost));
-			RX_CUDA(cudaMemcpy(procs.data(), ms.md_proc, size_t(n) * 4, cudaMemcpyDeviceToHost));
-			RX_CUDA(cudaMemcpy(fields.data(), ms.md_field, n, cudaMemcpyDeviceToHost));
-		}
+		const int32_t* ids = ft->h_id.p;
+		const float* procs = ft->h_proc.p;
+		const uint8_t* fields = ft->h_field.p;
 		std::vector<rxgpu_ft_merge_info> md(n);
 		float maxProc = 0.f;
 		for (uint32_t i = 0; i < n; ++i) {
