@@ -266,13 +266,17 @@ typedef struct {
 	uint32_t tc_fallbacks;      /* queries whose candidate list overflowed and were answered by the exact scan */
 	uint64_t tc_candidates;     /* rows re-ranked exactly */
 	uint32_t tc_cluster;        /* CTAs per cluster in the filter kernel (row tiles are TMA-multicast inside a cluster) */
-	uint32_t tc_kernel;         /* 2 = query block in TMEM (knn_tc_filter_q), 1 = query block in shared memory (knn_tc_filter) */
+	uint32_t tc_kernel;         /* 1 = knn_tc_filter (queries in shared memory), 2 = knn_tc_filter_q (queries in TMEM), 3 = _q2
+								 * (cta_group::2), 4 = _w (UMMA N = 128), 5 = _q4 (four issuers) */
 } rxgpu_search_stats;
 void rxgpu_last_search_stats(rxgpu_search_stats* out);
 /* large query batches: bf16 tensor-core filter + exact fp32 re-rank (results identical to the exact scan).
  * mode 0 = automatic (batches >= 64 queries on >= 100k rows, k <= 15), 1 = whenever possible, 2 = never;
- * 3..6 force kernel variants for tests/benchmarks: 3 / 4 = first-generation kernel (queries in shared memory) with 1 CTA / a CTA
- * pair per row tile, 5 / 6 = second-generation kernel (queries in TMEM) with clusters of 1 / up to 4 CTAs (default: CTA pairs) */
+ * 3..13 force kernel variants for tests/benchmarks (all give the same bits): 3 / 4 = first-generation kernel (queries in shared
+ * memory) with 1 CTA / a CTA pair per row tile; 5 / 6 = knn_tc_filter_q (queries in TMEM) with single CTAs / clusters of up to 4
+ * (the default); 7 = knn_tc_filter_q2 (the CTA pair multiplies as one, tcgen05.mma.cta_group::2); 8 / 9 / 10 = knn_tc_filter_w
+ * (one accumulator of 128 rows) with pairs / clusters of 4 / single CTAs; 11 / 12 / 13 = knn_tc_filter_q4 (four MMA issuers) with
+ * pairs / clusters of 4 / single CTAs.  DESIGN.md section 9 has the measurements. */
 int rxgpu_set_tensor_core_filter(rxgpu_index*, int mode);
 /* process-wide switch: bracket every scan-kernel launch with CUDA events (used by bench.py for the roofline figure) */
 int rxgpu_set_profile(int on);

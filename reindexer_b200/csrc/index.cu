@@ -349,9 +349,10 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
 			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
 		}
-		// measured on B200 (10M x 768, 1024 queries): CTA pairs 20.4 ms, clusters of four 21.9 ms, single CTAs 25.5 ms per batch --
-		// the pass is bound by the per-SM turn-around of the two TMEM accumulators, not by HBM, so pairs are the default
-		const uint32_t clusterMax = ix->tc_cluster_max ? ix->tc_cluster_max : 2u;
+		// measured on B200 (10M x 768, 1024 queries, same box, two rounds): CTA pairs 50.3 / 50.8 k queries/s, clusters of four
+		// 51.8 / 52.0 k, single CTAs ~40 k -- the kernel runs under the board's power cap, and a cluster of four reads every row tile
+		// from HBM once for 512 queries instead of 256
+		const uint32_t clusterMax = ix->tc_cluster_max ? ix->tc_cluster_max : 4u;
 		int cluster = qblocks >= 3 ? 4 : (qblocks == 2 ? 2 : 1);
 		cluster = pairMma ? 2 : std::min<int>(cluster, int(clusterMax));
 		const uint32_t qtiles = uint32_t((ix->size + kTqTileRows - 1) / kTqTileRows);
@@ -963,7 +964,7 @@ int rxgpu_set_tensor_core_filter(rxgpu_index* ix, int mode) {
 	}
 	ix->tc_mode = uint32_t(mode >= 3 ? 1 : mode);
 	ix->tc_variant = (mode == 3 || mode == 4 || mode == 7) ? uint32_t(mode) : (mode >= 11 ? 11u : (mode >= 8 ? 8u : 0u));
-	ix->tc_cluster_max = (mode == 5 || mode == 10 || mode == 13) ? 1u : ((mode == 6 || mode == 9 || mode == 12) ? 4u : 0u);
+	ix->tc_cluster_max = (mode == 5 || mode == 10 || mode == 13) ? 1u : ((mode == 6 || mode == 9 || mode == 12) ? 4u : ((mode == 8 || mode == 11) ? 2u : 0u));
 	return 0;
 }
 int rxgpu_set_profile(int on) {
