@@ -173,6 +173,19 @@ int rxgpu_gather_labels_device(const rxgpu_index*, uint64_t n, const uint32_t* d
 int rxgpu_hnsw_search_range(const rxgpu_index*, const float* query /* host */, float radius, uint32_t ef, uint64_t max_out,
 							float* out_dist, uint64_t* out_label, uint64_t* out_n);
 
+/* ---------------------------------------------------------------- IVF index (faiss::IndexIVFFlat as reindexer::IvfIndex drives it)
+ * Replaces the search side of IvfIndex: map_->search(1, key, k, dists, ids, &IVFSearchParameters{nprobe})
+ *   core/index/float_vector/ivf_index.cc:150-204 (callers), vendor_subdirs/faiss/IndexIVF.cpp (search_preassigned), IndexIVFFlat.cpp
+ *   (the flat list scanner).  Training (k-means) and list assignment stay with the reference's FAISS on the CPU; the adapter fills
+ * the device index with the rows GROUPED BY LIST (list 0's vectors first, then list 1's, ...; label = the FAISS id) and hands
+ * over the centroids and list sizes.  A search = coarse quantiser (distance to every centroid, nprobe nearest) + a scan of the
+ * probed lists with the exact-scan kernel (fused top-k per list) + one merge; L2 and inner product (Cosine: next).
+ * Results best-first in map space (L2: squared distance; IP: -inner product), bit-equal distances ordered by label;
+ * out_count[q] = min(k, rows in the probed lists).  k <= 256, nprobe <= 1024, at most 16384 centroids. */
+int rxgpu_ivf_import(rxgpu_index*, uint32_t nlist, const float* centroids /* nlist x dim, host */, const uint64_t* list_sizes /* nlist */);
+int rxgpu_ivf_search_knn(const rxgpu_index*, uint32_t nq, const float* queries /* host */, uint32_t k, uint32_t nprobe, float* out_dist,
+						 uint64_t* out_label, uint32_t* out_count);
+
 /* ---------------------------------------------------------------- ft_fast full-text merge (BM25 scoring over posting lists)
  * Replaces ft::Merger<IdCont, ft::MergeData, OffsetT>::Merge<Bm25Rx|Bm25Classic|TermCount>  core/ft/ft_fast/mergerimpl.h:466-566
  * -- the seam is Selector<IdCont>::mergeResults (ft_fast/selecterimpl.h:609-627) -- for query parts that are plain terms

@@ -413,3 +413,70 @@ class RefHnsw:
         assert rc == 0, self.lib.ref_last_error().decode()
         return dict(n=n, maxlevel=maxlevel, enterpoint=ep, M=M, maxM0=m0, level0=level0, levels=levels, upper_offsets=offs,
                     upper=upper[:upper_slots], labels=labels, vectors=vecs)
+
+
+# ---- IVF: the reference's vendored FAISS (oracle/_ref/liboracle_ref_ivf.so) ----------------------------------------------------
+_ref_ivf = None
+
+
+def ref_ivf_available():
+    return os.path.exists(os.path.join(HERE, "_ref", "liboracle_ref_ivf.so"))
+
+
+def ref_ivf_lib():
+    global _ref_ivf
+    if _ref_ivf is None:
+        lib = C.CDLL(os.path.join(HERE, "_ref", "liboracle_ref_ivf.so"))
+        lib.ref_ivf_last_error.restype = C.c_char_p
+        lib.ref_ivf_create.restype = C.c_void_p
+        lib.ref_ivf_create.argtypes = [C.c_int, C.c_size_t, C.c_size_t]
+        lib.ref_ivf_destroy.argtypes = [C.c_void_p]
+        lib.ref_ivf_train_add.argtypes = [C.c_void_p, C.c_size_t, _f32p, _i64p]
+        lib.ref_ivf_search.restype = C.c_int64
+        lib.ref_ivf_search.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_size_t, _f32p, _i64p]
+        lib.ref_ivf_export_header.argtypes = [C.c_void_p, _i64p]
+        lib.ref_ivf_export.argtypes = [C.c_void_p, _f32p, _i64p, _i64p, _f32p]
+        _ref_ivf = lib
+    return _ref_ivf
+
+
+class RefIvf:
+    """faiss::IndexIVFFlat of the reference, driven like reindexer::IvfIndex (L2 / IP)."""
+
+    def __init__(self, metric, dim, nlist):
+        self.lib = ref_ivf_lib()
+        self.metric, self.dim, self.nlist = metric, dim, nlist
+        self.h = self.lib.ref_ivf_create(metric, dim, nlist)
+        assert self.h, self.lib.ref_ivf_last_error().decode()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.ref_ivf_destroy(self.h)
+            self.h = None
+
+    def train_add(self, labels, vecs):
+        vecs = np.ascontiguousarray(vecs, np.float32)
+        ids = np.ascontiguousarray(labels).astype(np.int64)
+        rc = self.lib.ref_ivf_train_add(self.h, len(ids), _p(vecs, _f32p), _p(ids, _i64p))
+        assert rc == 0, self.lib.ref_ivf_last_error().decode()
+
+    def search(self, q, k, nprobe):
+        """returns (dist, label) best first; dist in FAISS' convention (L2: squared distance, IP: +inner product)"""
+        q = np.ascontiguousarray(q, np.float32)
+        d = np.zeros(k, np.float32)
+        i = np.zeros(k, np.int64)
+        n = self.lib.ref_ivf_search(self.h, _p(q, _f32p), k, nprobe, _p(d, _f32p), _p(i, _i64p))
+        assert n >= 0, self.lib.ref_ivf_last_error().decode()
+        return d[:n].copy(), i[:n].astype(np.uint64)
+
+    def export(self):
+        hdr = np.zeros(2, np.int64)
+        assert self.lib.ref_ivf_export_header(self.h, _p(hdr, _i64p)) == 0
+        nlist, ntotal = int(hdr[0]), int(hdr[1])
+        cent = np.zeros((nlist, self.dim), np.float32)
+        sizes = np.zeros(nlist, np.int64)
+        ids = np.zeros(ntotal, np.int64)
+        vecs = np.zeros((ntotal, self.dim), np.float32)
+        rc = self.lib.ref_ivf_export(self.h, _p(cent, _f32p), _p(sizes, _i64p), _p(ids, _i64p), _p(vecs, _f32p))
+        assert rc == 0, self.lib.ref_ivf_last_error().decode()
+        return dict(centroids=cent, list_sizes=sizes.astype(np.uint64), labels=ids.astype(np.uint64), vecs=vecs)

@@ -114,6 +114,8 @@ _SIGNATURES = {
     "rxgpu_hnsw_search_range": (C.c_int, [C.c_void_p, _f32p, C.c_float, C.c_uint32, C.c_uint64, _f32p, _u64p, C.POINTER(C.c_uint64)]),
     "rxgpu_hnsw_search_knn_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rxgpu_ivf_import": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, _u64p]),
+    "rxgpu_ivf_search_knn": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, C.c_uint32, C.c_uint32, _f32p, _u64p, _u32p]),
     "rxgpu_ft_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, _u32p, _f32p, _u8p, C.c_int]),
     "rxgpu_ft_destroy": (None, [C.c_void_p]),
     "rxgpu_ft_add_postings": (C.c_int, [C.c_void_p, C.POINTER(FtPostings), _u32p]),
@@ -314,6 +316,21 @@ class GpuBruteforceSearch:
         _check(self._lib.rxgpu_hnsw_search_range(self._h, _p(q, _f32p), radius, ef, max_out, _p(d, _f32p), _p(l, _u64p), C.byref(n)))
         m = min(n.value, max_out)
         return d[:m], l[:m], n.value
+
+    # -- IVF (lists trained and assigned by the reference's FAISS; rows of this index grouped by list) -------------------
+    def ivf_import(self, centroids, list_sizes):
+        c = np.ascontiguousarray(centroids, np.float32)
+        ls = np.ascontiguousarray(list_sizes, np.uint64)
+        _check(self._lib.rxgpu_ivf_import(self._h, len(ls), _p(c, _f32p), _p(ls, _u64p)))
+
+    def ivf_search_knn(self, queries, k: int, nprobe: int):
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
+        nq = q.shape[0]
+        d = np.zeros((nq, max(k, 1)), np.float32)
+        l = np.zeros((nq, max(k, 1)), np.uint64)
+        c = np.zeros(nq, np.uint32)
+        _check(self._lib.rxgpu_ivf_search_knn(self._h, nq, _p(q, _f32p), k, nprobe, _p(d, _f32p), _p(l, _u64p), _p(c, _u32p)))
+        return d, l, c
 
     # -- bench / test support ------------------------------------------------------------------------------------------
     def append_synth(self, seed: int, first_row: int, n: int):

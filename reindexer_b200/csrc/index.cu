@@ -87,6 +87,9 @@ cudaError_t launchScanQ(const rxgpu_index* ix, const ScanArgs& a, uint32_t nch, 
 	const uint32_t nrows = a.row_end - a.row_begin;
 	const uint32_t ngroups = (nrows + rw - 1) / rw;
 	unsigned grid = std::min<unsigned>(unsigned(ix->sm_count) * 2u, std::max<unsigned>(1u, (ngroups + kScanWarps - 1) / kScanWarps));
+	if (a.work != nullptr) {
+		grid = a.nwork;  // one CTA per (query, inverted list)
+	}
 	*gridOut = grid;
 	if (dryRun) {
 		return cudaSuccess;
@@ -1393,6 +1396,186 @@ int rxgpu_synth_fill_device(float* d_out, uint64_t seed, uint64_t first_index, u
 	synth_fill_kernel<<<1184, 256, 0, st>>>(d_out, seed, first_index, count);
 	RX_CUDA(cudaGetLastError());
 	RX_CUDA(cudaStreamSynchronize(st));
+	return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- IVF
+}  // extern "C"
+
+struct rxgpu_ivf_device {
+	uint32_t nlist = 0;
+	uint64_t index_version = 0;
+	DevBuf<float> centroids;       // [nlist][pitch]
+	DevBuf<uint32_t> list_begin;   // [nlist + 1] rows of list l = [list_begin[l], list_begin[l + 1])
+	std::mutex mtx;                // one IVF batch at a time per index (scratch below)
+	DevBuf<float> d_q, d_dist;
+	DevBuf<uint4> d_work;
+	DevBuf<uint64_t> d_lists, d_label;
+	DevBuf<uint32_t> d_idx, d_count;
+};
+namespace rxgpu {
+void ivfRelease(rxgpu_ivf_device* p) { delete p; }
+}  // namespace rxgpu
+
+extern "C" {
+
+int rxgpu_ivf_import(rxgpu_index* ix, uint32_t nlist, const float* centroids, const uint64_t* list_sizes) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	if (!centroids || !list_sizes || nlist == 0) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	if (ix->metric == RXGPU_COS) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: the IVF device path supports L2 and inner product");
+	}
+	if (nlist > 16384) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: at most 16384 IVF centroids on the device path");
+	}
+	try {
+		std::vector<uint32_t> begin(size_t(nlist) + 1, 0u);
+		uint64_t total = 0;
+		for (uint32_t l = 0; l < nlist; ++l) {
+			total += list_sizes[l];
+			if (total > ix->size) {
+				break;
+			}
+			begin[l + 1] = uint32_t(total);
+		}
+		if (total != ix->size) {
+			return fail(RXGPU_ERR_LOGIC, "rxgpu: IVF list sizes do not add up to the number of rows in the index");
+		}
+		auto h = std::make_unique<rxgpu_ivf_device>();
+		h->nlist = nlist;
+		RX_CUDA(h->centroids.ensure(size_t(nlist) * ix->pitch));
+		RX_CUDA(h->list_begin.ensure(size_t(nlist) + 1));
+		RX_CUDA(cudaMemset(h->centroids.p, 0, size_t(nlist) * ix->pitch * sizeof(float)));
+		RX_CUDA(cudaMemcpy2D(h->centroids.p, size_t(ix->pitch) * 4, centroids, size_t(ix->dim) * 4, size_t(ix->dim) * 4, nlist,
+							 cudaMemcpyHostToDevice));
+		RX_CUDA(cudaMemcpy(h->list_begin.p, begin.data(), begin.size() * 4, cudaMemcpyHostToDevice));
+		h->index_version = ix->version;
+		if (ix->ivf) {
+			ivfRelease(ix->ivf);
+		}
+		ix->ivf = h.release();
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
+	}
+	return 0;
+}
+
+int rxgpu_ivf_search_knn(const rxgpu_index* ix, uint32_t nq, const float* queries, uint32_t k, uint32_t nprobe, float* out_dist,
+						 uint64_t* out_label, uint32_t* out_count) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	g_stats = rxgpu_search_stats{};
+	if (nq == 0) {
+		return 0;
+	}
+	if (!queries || !out_count || (k && (!out_dist || !out_label))) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	rxgpu_ivf_device* h = ix->ivf;
+	if (!h) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: no IVF lists imported into this index");
+	}
+	if (h->index_version != ix->version) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: the index changed after the IVF lists were imported");
+	}
+	if (k == 0 || k > kMaxFusedK1) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: IVF search needs k in [1, 256]");
+	}
+	nprobe = std::max(1u, std::min(nprobe, h->nlist));  // faiss::IndexIVF::search clamps nprobe to nlist
+	if (nprobe > 256u * kMergeOwn) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: nprobe exceeds the merge fan-in (1024)");
+	}
+	const uint32_t nch = (ix->dim + 127u) / 128u;
+	const size_t coarseSmem = size_t(nch) * 512 + size_t(h->nlist) * 8;
+	if (coarseSmem > 200 * 1024) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: dimension / centroid count exceeds the coarse quantiser's shared memory");
+	}
+	std::lock_guard<std::mutex> lck(h->mtx);
+	cudaStream_t st = ix->stream;
+	const size_t nwork = size_t(nq) * nprobe;
+	RX_CUDA(h->d_q.ensure(size_t(nq) * ix->dim));
+	RX_CUDA(h->d_work.ensure(nwork));
+	RX_CUDA(h->d_lists.ensure(nwork * k));
+	RX_CUDA(h->d_dist.ensure(size_t(nq) * k));
+	RX_CUDA(h->d_idx.ensure(size_t(nq) * k));
+	RX_CUDA(h->d_label.ensure(size_t(nq) * k));
+	RX_CUDA(h->d_count.ensure(nq));
+	RX_CUDA(cudaMemcpyAsync(h->d_q.p, queries, size_t(nq) * ix->dim * 4, cudaMemcpyHostToDevice, st));
+	if (ix->metric == RXGPU_L2) {
+		RX_CUDA(cudaFuncSetAttribute(ivf_coarse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(coarseSmem)));
+		ivf_coarse_kernel<true><<<nq, kScanThreads, coarseSmem, st>>>(h->centroids.p, ix->pitch, ix->dim, h->nlist, h->d_q.p, nq, nprobe,
+																	   h->list_begin.p, h->d_work.p);
+	} else {
+		RX_CUDA(cudaFuncSetAttribute(ivf_coarse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(coarseSmem)));
+		ivf_coarse_kernel<false><<<nq, kScanThreads, coarseSmem, st>>>(h->centroids.p, ix->pitch, ix->dim, h->nlist, h->d_q.p, nq, nprobe,
+																		h->list_begin.p, h->d_work.p);
+	}
+	RX_CUDA(cudaGetLastError());
+	// list scans: the exact scan kernel in work-item mode, one CTA per (query, probed list), fused top-k per CTA
+	ScanArgs a{};
+	a.rows = ix->d_rows;
+	a.queries = h->d_q.p;
+	a.pitch = ix->pitch;
+	a.dim = ix->dim;
+	a.nq = 1;
+	a.k1 = k;
+	a.mode = kModeTopK;
+	a.lists = h->d_lists.p;
+	a.work = h->d_work.p;
+	a.nwork = uint32_t(nwork);
+	if (scan_smem_bytes(1, ix->dim, k) > 100 * 1024) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: dimension/k combination exceeds the fused top-k shared-memory budget");
+	}
+	unsigned grid = 0;
+	RX_CUDA(launchScan(ix, 1, a, &grid, st));
+	MergeArgs m{};
+	m.lists = h->d_lists.p;
+	m.labels = ix->d_labels;
+	m.out_dist = h->d_dist.p;
+	m.out_idx = h->d_idx.p;
+	m.out_label = h->d_label.p;
+	m.out_count = h->d_count.p;
+	m.nlists = nprobe;
+	m.qt = nq;  // lists are probe-major: list of (probe p, query q) = p * nq + q
+	m.k1 = k;
+	m.q_offset = 0;
+	m.out_stride = k;
+	m.out_offset = 0;
+	m.mode = kModeTopK;
+	knn_merge_lists<<<nq, 256, 0, st>>>(m);
+	RX_CUDA(cudaGetLastError());
+	g_stats.launches = 3;
+	g_stats.passes = 1;
+	try {
+		std::vector<float> hd(size_t(nq) * k);
+		std::vector<uint64_t> hl(size_t(nq) * k);
+		std::vector<uint32_t> hi(size_t(nq) * k), hc(nq);
+		RX_CUDA(cudaMemcpyAsync(hd.data(), h->d_dist.p, hd.size() * 4, cudaMemcpyDeviceToHost, st));
+		RX_CUDA(cudaMemcpyAsync(hl.data(), h->d_label.p, hl.size() * 8, cudaMemcpyDeviceToHost, st));
+		RX_CUDA(cudaMemcpyAsync(hi.data(), h->d_idx.p, hi.size() * 4, cudaMemcpyDeviceToHost, st));
+		RX_CUDA(cudaMemcpyAsync(hc.data(), h->d_count.p, hc.size() * 4, cudaMemcpyDeviceToHost, st));
+		RX_CUDA(cudaStreamSynchronize(st));
+		std::vector<Hit> hits;
+		for (uint32_t q = 0; q < nq; ++q) {
+			hits.clear();
+			for (uint32_t j = 0; j < std::min(hc[q], k); ++j) {
+				hits.push_back(Hit{hd[size_t(q) * k + j], hi[size_t(q) * k + j], hl[size_t(q) * k + j]});
+			}
+			orderTiesByLabel(hits);  // FAISS' heap leaves bit-equal distances in no particular order: (distance, label) here
+			for (size_t j = 0; j < hits.size(); ++j) {
+				out_dist[size_t(q) * k + j] = hits[j].dist;
+				out_label[size_t(q) * k + j] = hits[j].label;
+			}
+			out_count[q] = uint32_t(hits.size());
+		}
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
+	}
 	return 0;
 }
 

@@ -130,8 +130,10 @@ struct Workspace {
 }  // namespace rxgpu
 
 struct rxgpu_hnsw_device;  // hnsw.cu
+struct rxgpu_ivf_device;   // index.cu
 namespace rxgpu {
 void hnswRelease(rxgpu_hnsw_device*);
+void ivfRelease(rxgpu_ivf_device*);
 }
 
 struct rxgpu_index {
@@ -158,6 +160,7 @@ struct rxgpu_index {
 	mutable std::mutex ws_mtx;
 	mutable std::vector<std::unique_ptr<rxgpu::Workspace>> ws_free;
 	rxgpu_hnsw_device* hnsw = nullptr;  // graph attached by rxgpu_hnsw_import (hnsw.cu)
+	rxgpu_ivf_device* ivf = nullptr;    // centroids + list boundaries attached by rxgpu_ivf_import
 
 	// tensor-core filter state, built lazily by the first large-batch search: bf16 shadow of the rows + row norms
 	mutable std::mutex tc_mtx;
@@ -175,6 +178,9 @@ struct rxgpu_index {
 		ws_free.clear();
 		if (hnsw) {
 			rxgpu::hnswRelease(hnsw);
+		}
+		if (ivf) {
+			rxgpu::ivfRelease(ivf);
 		}
 		if (d_rows) {
 			cudaFree(d_rows);

@@ -45,6 +45,10 @@ struct ScanArgs {
 	int mode;                 // ScanMode or kModeRange
 	float bound;              // tie mode: dstar (dist <= bound); range mode: radius (dist < bound)
 	const uint64_t* floor_keys;  // [nq] only keys ABOVE the floor compete (rounds of a k > 255 search), or nullptr
+	// work-item mode (IVF list scans, QT = 1): CTA b scans rows [work[b].y, work[b].z) for query work[b].x with its own 8 warps and
+	// writes list b; row_begin / row_end / nq are ignored (nq = 1)
+	const uint4* work;
+	uint32_t nwork;
 };
 enum : int { kModeRange = 2 };
 
@@ -94,6 +98,17 @@ template <int QT, int RW, int CG, bool kIsL2>
 __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_warp(const ScanArgs a) {
 	static_assert(RW * QT <= 32, "one lane per (row, query) result");
 	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const float* qsrc = a.queries;
+	uint32_t row_begin = a.row_begin, row_end = a.row_end;
+	uint32_t gfirst = blockIdx.x * kScanWarps + (threadIdx.x >> 5), gstride = gridDim.x * kScanWarps;
+	if (a.work != nullptr) {
+		const uint4 w = a.work[blockIdx.x];
+		qsrc += size_t(w.x) * a.dim;
+		row_begin = w.y;
+		row_end = w.z;
+		gfirst = threadIdx.x >> 5;
+		gstride = kScanWarps;
+	}
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
 	const uint32_t nch = (a.dim + 127u) / 128u;
@@ -111,7 +126,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_warp(const ScanArgs 
 		const uint32_t dp = dp4 * 4;
 		for (uint32_t i = threadIdx.x; i < QT * dp; i += blockDim.x) {
 			const uint32_t qi = i / dp, c = i - qi * dp;
-			sq[i] = (qi < a.nq && c < a.dim) ? a.queries[size_t(qi) * a.dim + c] : 0.f;
+			sq[i] = (qi < a.nq && c < a.dim) ? qsrc[size_t(qi) * a.dim + c] : 0.f;
 		}
 		for (uint32_t i = threadIdx.x; i < kScanWarps * QT * m; i += blockDim.x) {
 			skeys[i] = kKeyNone;
@@ -128,9 +143,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_warp(const ScanArgs 
 	uint32_t* wcnt = scnt + warp * QT;
 
 	const float4* rows4 = reinterpret_cast<const float4*>(a.rows);
-	const uint32_t nrows = a.row_end - a.row_begin;
+	const uint32_t nrows = row_end - row_begin;
 	const uint32_t ngroups = (nrows + RW - 1) / RW;
-	const uint32_t total_warps = gridDim.x * kScanWarps;
 
 	// lanes {r*QT + qi} hold the result of (row r, query qi)
 	unsigned qpattern = 0;
@@ -142,7 +156,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_warp(const ScanArgs 
 	const bool has_floor = a.floor_keys != nullptr;
 	const uint64_t my_floor = has_floor && uint32_t(my_q) < a.nq ? a.floor_keys[my_q] : 0;
 
-	for (uint32_t g = blockIdx.x * kScanWarps + warp; g < ngroups; g += total_warps) {
+	for (uint32_t g = gfirst; g < ngroups; g += gstride) {
 		float acc[RW][QT];
 #pragma unroll
 		for (int r = 0; r < RW; ++r) {
@@ -151,7 +165,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_warp(const ScanArgs 
 				acc[r][qi] = 0.f;
 			}
 		}
-		const uint32_t row0 = a.row_begin + g * RW;
+		const uint32_t row0 = row_begin + g * RW;
 		for (uint32_t c0 = 0; c0 < nch; c0 += CG) {
 			float4 db[RW][CG];
 #pragma unroll
@@ -160,7 +174,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_warp(const ScanArgs 
 				for (int j = 0; j < CG; ++j) {
 					const uint32_t f4 = (c0 + j) * 32u + lane;
 					const uint32_t row = row0 + r;
-					if (row < a.row_end && f4 < pitch4) {
+					if (row < row_end && f4 < pitch4) {
 						db[r][j] = ldg_stream(rows4 + size_t(row) * pitch4 + f4);
 					} else {
 						db[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -214,7 +228,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) knn_scan_warp(const ScanArgs 
 		}
 		// epilogue: lane (r, qi) owns one distance
 		const uint32_t row = row0 + my_r;
-		const bool valid = lane < RW * QT && row < a.row_end && uint32_t(my_q) < a.nq;
+		const bool valid = lane < RW * QT && row < row_end && uint32_t(my_q) < a.nq;
 		float dist = kIsL2 ? mine : -mine;  // DistCalculator::l2 / ::ip (hnswlib.h:192-197), alpha2 = 1, offsets 0
 		if (!kIsL2 && a.norm_coefs != nullptr && valid) {
 			dist *= a.norm_coefs[row];  // Cosine: hnswlib.h:160-161
@@ -417,6 +431,104 @@ __global__ void __launch_bounds__(256) knn_merge_lists(const MergeArgs a) {
 		if (a.floor_out) {
 			a.floor_out[qi] = count == a.k1 ? s_res[count - 1] : kKeyNone;
 		}
+	}
+}
+
+// ---- IVF ----------------------------------------------------------------------------------------------------------------
+// distance of one row to the query staged in sq4, all lanes return the sum: the per-row arithmetic of knn_scan_warp (per-lane
+// sequential FMA over the 128-float chunks, then the xor butterfly), so a row's distance has the same bits on every path
+template <bool kIsL2>
+__device__ __forceinline__ float row_dist_warp(const float4* rows4, uint32_t pitch4, uint32_t nch, uint32_t row, const float4* sq4, int lane) {
+	float s = 0.f;
+	for (uint32_t c = 0; c < nch; ++c) {
+		const uint32_t f4 = c * 32u + lane;
+		const float4 v = f4 < pitch4 ? ldg_stream(rows4 + size_t(row) * pitch4 + f4) : make_float4(0.f, 0.f, 0.f, 0.f);
+		const float4 q = sq4[f4];
+		if constexpr (kIsL2) {
+			float d;
+			d = q.x - v.x;
+			s = fmaf(d, d, s);
+			d = q.y - v.y;
+			s = fmaf(d, d, s);
+			d = q.z - v.z;
+			s = fmaf(d, d, s);
+			d = q.w - v.w;
+			s = fmaf(d, d, s);
+		} else {
+			s = fmaf(q.x, v.x, s);
+			s = fmaf(q.y, v.y, s);
+			s = fmaf(q.z, v.z, s);
+			s = fmaf(q.w, v.w, s);
+		}
+	}
+#pragma unroll
+	for (int off = 16; off > 0; off >>= 1) {
+		s += __shfl_xor_sync(0xffffffffu, s, off);
+	}
+	return kIsL2 ? s : -s;
+}
+// coarse quantiser (faiss::IndexIVF::search -> quantizer->search(nprobe), IndexIVF.cpp): one CTA per query computes the distance to
+// every centroid (a warp per centroid) and selects the nprobe nearest under (distance, centroid id); then it emits the work items
+// of the list scan, probe-major: work[p * nq + q] = (q, list_begin[c], list_begin[c + 1], c)
+template <bool kIsL2>
+__global__ void __launch_bounds__(kScanThreads) ivf_coarse_kernel(const float* centroids, uint32_t pitch, uint32_t dim, uint32_t nlist,
+																  const float* queries, uint32_t nq, uint32_t nprobe, const uint32_t* list_begin,
+																  uint4* work) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	__shared__ uint64_t s_best[kScanWarps];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t nch = (dim + 127u) / 128u, dp4 = nch * 32u, pitch4 = pitch >> 2;
+	float4* sq4 = reinterpret_cast<float4*>(smem_raw);
+	uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw + size_t(dp4) * 16);
+	const uint32_t q = blockIdx.x;
+	{
+		float* sq = reinterpret_cast<float*>(sq4);
+		for (uint32_t c = threadIdx.x; c < dp4 * 4; c += blockDim.x) {
+			sq[c] = c < dim ? queries[size_t(q) * dim + c] : 0.f;
+		}
+	}
+	__syncthreads();
+	const float4* rows4 = reinterpret_cast<const float4*>(centroids);
+	for (uint32_t c = warp; c < nlist; c += kScanWarps) {
+		const float d = row_dist_warp<kIsL2>(rows4, pitch4, nch, c, sq4, lane);
+		if (lane == 0) {
+			keys[c] = make_key(d, c);
+		}
+	}
+	__syncthreads();
+	uint64_t last = 0;
+	for (uint32_t p = 0; p < nprobe; ++p) {  // keys are unique: select strictly increasing keys
+		uint64_t best = kKeyNone;
+		for (uint32_t c = threadIdx.x; c < nlist; c += blockDim.x) {
+			const uint64_t kx = keys[c];
+			if ((p == 0 || kx > last) && kx < best) {
+				best = kx;
+			}
+		}
+#pragma unroll
+		for (int off = 16; off > 0; off >>= 1) {
+			const uint64_t o = __shfl_xor_sync(0xffffffffu, best, off);
+			best = o < best ? o : best;
+		}
+		if (lane == 0) {
+			s_best[warp] = best;
+		}
+		__syncthreads();
+		best = s_best[0];
+#pragma unroll
+		for (int w = 1; w < kScanWarps; ++w) {
+			best = s_best[w] < best ? s_best[w] : best;
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			uint4 w = make_uint4(q, 0, 0, 0xFFFFFFFFu);  // fewer centroids than nprobe: an empty range
+			if (best != kKeyNone) {
+				const uint32_t c = uint32_t(best);
+				w = make_uint4(q, list_begin[c], list_begin[c + 1], c);
+			}
+			work[size_t(p) * nq + q] = w;
+		}
+		last = best;
 	}
 }
 

@@ -1,0 +1,64 @@
+"""GPU parity tests of the IVF search: the index is trained and filled by the REFERENCE's own FAISS
+(oracle/_ref/liboracle_ref_ivf.so: vendor_subdirs/faiss compiled in place, driven like reindexer::IvfIndex), its centroids and
+inverted lists are imported into the device index, and every search is compared with faiss::IndexIVFFlat::search on the same state."""
+import numpy as np
+import pytest
+from helpers import ATOL, RTOL
+
+import reindexer_b200 as rx
+from oracle import oracle as O
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not O.ref_ivf_available(), reason="needs oracle/_ref (reference FAISS build)")]
+
+
+def build(metric, n, dim, nlist, seed):
+    vecs, labels = O.synth_matrix(seed, n, dim), O.row_labels(n)
+    ref = O.RefIvf(metric, dim, nlist)
+    ref.train_add(labels, vecs)
+    st = ref.export()
+    assert int(st["list_sizes"].sum()) == n and sorted(st["labels"].tolist()) == sorted(labels.tolist())
+    gpu = rx.GpuBruteforceSearch(metric, dim, n)
+    gpu.add_points(st["labels"], st["vecs"])  # rows grouped by list, label = FAISS id
+    gpu.ivf_import(st["centroids"], st["list_sizes"])
+    return ref, gpu, st
+
+
+@pytest.mark.parametrize("metric,dim,nlist", [(rx.L2, 32, 16), (rx.L2, 96, 64), (rx.IP, 64, 32), (rx.L2, 768, 24), (rx.IP, 200, 50)])
+def test_ivf_search_matches_reference_faiss(metric, dim, nlist):
+    n = 12000 if dim < 500 else 4000
+    ref, gpu, st = build(metric, n, dim, nlist, 3100 + dim)
+    queries = O.synth_matrix(3200 + dim, 40, dim)
+    for k, nprobe in [(10, 1), (10, 4), (1, 8), (50, nlist // 2), (10, nlist), (10, nlist + 7)]:
+        d, l, c = gpu.ivf_search_knn(queries, k, nprobe)
+        for i in range(len(queries)):
+            dr, lr = ref.search(queries[i], k, nprobe)
+            assert c[i] == len(lr), (k, nprobe, i, c[i], len(lr))
+            dr_map = dr if metric == rx.L2 else -dr  # FAISS reports +IP (descending); the map space is -IP (ascending)
+            assert np.allclose(d[i, :c[i]], dr_map, rtol=RTOL, atol=ATOL), (k, nprobe, i)
+            if not (l[i, :c[i]] == lr).all():  # ids may differ only where neighbouring distances are within fp noise
+                bad = np.nonzero(l[i, :c[i]] != lr)[0]
+                assert set(l[i, :c[i]]) == set(lr) or np.allclose(d[i, bad], dr_map[bad], rtol=1e-5), (k, nprobe, i, l[i, :c[i]], lr)
+    # nprobe = nlist scans every list: the result is the exact brute-force answer
+    d, l, c = gpu.ivf_search_knn(queries[:8], 10, nlist)
+    db, lb, _ = gpu.search_knn(queries[:8], 10)
+    assert (l == lb).all() and (d.view(np.uint32) == db.view(np.uint32)).all()  # same per-row arithmetic => same bits
+
+
+def test_ivf_errors_and_staleness():
+    ref, gpu, st = build(rx.L2, 3000, 16, 8, 77)
+    q = O.synth_matrix(78, 2, 16)
+    with pytest.raises(rx.RxGpuError):
+        gpu.ivf_search_knn(q, 0, 4)
+    with pytest.raises(rx.RxGpuError):
+        gpu.ivf_search_knn(q, 300, 4)
+    gpu.add_point(st["vecs"][0], int(st["labels"][5]))  # a row was overwritten: the imported lists are stale
+    with pytest.raises(rx.RxGpuError) as e:
+        gpu.ivf_search_knn(q, 5, 4)
+    assert "changed after the IVF lists were imported" in e.value.what
+    fresh = rx.GpuBruteforceSearch(rx.L2, 16, 10)
+    fresh.add_point(st["vecs"][0], 1)
+    with pytest.raises(rx.RxGpuError) as e:
+        fresh.ivf_search_knn(q, 5, 4)
+    assert "no IVF lists imported" in e.value.what
+    with pytest.raises(rx.RxGpuError):
+        fresh.ivf_import(st["centroids"], st["list_sizes"])  # sizes do not add up to the rows of this index

@@ -121,3 +121,29 @@ def test_select_postprocess_properties():
     # k + radius => trimmed to k
     ids, _ = O.select_postprocess(O.L2, d[order], lab[order], k=2, has_radius=True)
     assert len(ids) == 2
+
+
+@pytest.mark.skipif(not O.ref_ivf_available(), reason="needs oracle/_ref (reference FAISS build)")
+def test_reference_ivf_oracle_is_self_consistent():
+    """the IVF oracle is the reference's own FAISS; pin the facade's export against its search: scanning the exported lists of the
+    nprobe nearest exported centroids by brute force reproduces IndexIVFFlat::search"""
+    n, dim, nlist, k, nprobe = 4000, 24, 16, 10, 3
+    vecs, labels = O.synth_matrix(901, n, dim), O.row_labels(n)
+    for metric in (O.L2, O.IP):
+        ref = O.RefIvf(metric, dim, nlist)
+        ref.train_add(labels, vecs)
+        st = ref.export()
+        begin = np.concatenate([[0], np.cumsum(st["list_sizes"].astype(np.int64))])
+        for q in O.synth_matrix(902, 12, dim):
+            if metric == O.L2:
+                cd = ((st["centroids"] - q) ** 2).sum(axis=1)
+            else:
+                cd = -(st["centroids"] @ q)
+            probe = np.argsort(cd, kind="stable")[:nprobe]
+            rows = np.concatenate([np.arange(begin[c], begin[c + 1]) for c in probe])
+            sub = st["vecs"][rows]
+            dd = ((sub - q) ** 2).sum(axis=1) if metric == O.L2 else -(sub @ q)
+            order = np.argsort(dd, kind="stable")[:k]
+            dr, lr = ref.search(q, k, nprobe)
+            assert (st["labels"][rows[order]] == lr).all()
+            assert np.allclose(dd[order], dr if metric == O.L2 else -dr, rtol=1e-4, atol=1e-5)
