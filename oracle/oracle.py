@@ -434,6 +434,7 @@ def ref_ivf_lib():
         lib.ref_ivf_train_add.argtypes = [C.c_void_p, C.c_size_t, _f32p, _i64p]
         lib.ref_ivf_search.restype = C.c_int64
         lib.ref_ivf_search.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_size_t, _f32p, _i64p]
+        lib.ref_ivf_search_batch.argtypes = [C.c_void_p, C.c_size_t, _f32p, C.c_size_t, C.c_size_t, _f32p, _i64p]
         lib.ref_ivf_export_header.argtypes = [C.c_void_p, _i64p]
         lib.ref_ivf_export.argtypes = [C.c_void_p, _f32p, _i64p, _i64p, _f32p]
         _ref_ivf = lib
@@ -468,6 +469,14 @@ class RefIvf:
         n = self.lib.ref_ivf_search(self.h, _p(q, _f32p), k, nprobe, _p(d, _f32p), _p(i, _i64p))
         assert n >= 0, self.lib.ref_ivf_last_error().decode()
         return d[:n].copy(), i[:n].astype(np.uint64)
+
+    def search_batch(self, queries, k, nprobe):
+        q = np.ascontiguousarray(queries, np.float32)
+        d = np.zeros((len(q), k), np.float32)
+        i = np.zeros((len(q), k), np.int64)
+        rc = self.lib.ref_ivf_search_batch(self.h, len(q), _p(q, _f32p), k, nprobe, _p(d, _f32p), _p(i, _i64p))
+        assert rc == 0, self.lib.ref_ivf_last_error().decode()
+        return d, i.astype(np.uint64)
 
     def export(self):
         hdr = np.zeros(2, np.int64)

@@ -97,6 +97,16 @@ int64_t ref_ivf_search(const void* hv, const float* query, size_t k, size_t npro
 	return n;
 }
 
+// nq queries in one call: FAISS parallelises over queries with OpenMP (the most favourable way to run the reference's engine)
+int ref_ivf_search_batch(const void* hv, size_t nq, const float* queries, size_t k, size_t nprobe, float* dists, int64_t* ids) {
+	auto* h = static_cast<const IvfHandle*>(hv);
+	return guarded([&] {
+		faiss::IVFSearchParameters p;
+		p.nprobe = nprobe;
+		h->map->search(faiss::idx_t(nq), queries, faiss::idx_t(k), dists, reinterpret_cast<faiss::idx_t*>(ids), &p);
+	});
+}
+
 // hdr: [nlist, ntotal]
 int ref_ivf_export_header(const void* hv, int64_t* hdr) {
 	auto* h = static_cast<const IvfHandle*>(hv);
