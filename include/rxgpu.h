@@ -179,8 +179,9 @@ int rxgpu_hnsw_search_range(const rxgpu_index*, const float* query /* host */, f
  *   (the flat list scanner).  Training (k-means) and list assignment stay with the reference's FAISS on the CPU; the adapter fills
  * the device index with the rows GROUPED BY LIST (list 0's vectors first, then list 1's, ...; label = the FAISS id) and hands
  * over the centroids and list sizes.  A search = coarse quantiser (distance to every centroid, nprobe nearest) + a scan of the
- * probed lists with the exact-scan kernel (fused top-k per list) + one merge; L2 and inner product (Cosine: next).
- * Results best-first in map space (L2: squared distance; IP: -inner product), bit-equal distances ordered by label;
+ * probed lists with the exact-scan kernel (fused top-k per list) + one merge.  Cosine: queries pre-normalised, rows and centroids
+ * carry their norm coefficients like the reference's patched FAISS (IndexFlatCosine, IndexIVFFlat(..., is_cosine)).
+ * Results best-first in map space (L2: squared distance; IP / Cosine: -inner product / -cos), bit-equal distances ordered by label;
  * out_count[q] = min(k, rows in the probed lists).  k <= 256, nprobe <= 1024, at most 16384 centroids. */
 int rxgpu_ivf_import(rxgpu_index*, uint32_t nlist, const float* centroids /* nlist x dim, host */, const uint64_t* list_sizes /* nlist */);
 int rxgpu_ivf_search_knn(const rxgpu_index*, uint32_t nq, const float* queries /* host */, uint32_t k, uint32_t nprobe, float* out_dist,

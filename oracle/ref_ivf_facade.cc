@@ -15,11 +15,13 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "faiss/IndexFlat.h"
 #include "faiss/IndexIVFFlat.h"
 #include "faiss/impl/AuxIndexStructures.h"
 #include "faiss/invlists/DirectMap.h"
+#include "tools/normalize.h"
 
 namespace {
 thread_local std::string g_err;
@@ -49,7 +51,7 @@ extern "C" {
 
 const char* ref_ivf_last_error() { return g_err.c_str(); }
 
-// metric: 0 = L2, 1 = InnerProduct (reindexer::VectorMetric); Cosine is not exposed yet
+// metric: 0 = L2, 1 = InnerProduct, 2 = Cosine (reindexer::VectorMetric)
 void* ref_ivf_create(int metric, size_t dim, size_t nlist) {
 	IvfHandle* h = nullptr;
 	guarded([&] {
@@ -60,11 +62,13 @@ void* ref_ivf_create(int metric, size_t dim, size_t nlist) {
 			hh->space = std::make_unique<faiss::IndexFlatL2>(dim);
 		} else if (metric == 1) {
 			hh->space = std::make_unique<faiss::IndexFlatIP>(dim);
+		} else if (metric == 2) {
+			hh->space = std::make_unique<faiss::IndexFlatCosine>(dim);  // IvfIndex::newSpace, ivf_index.cc:686-695
 		} else {
-			throw std::runtime_error("ref_ivf_create: metric must be L2 (0) or InnerProduct (1)");
+			throw std::runtime_error("ref_ivf_create: unknown metric");
 		}
 		hh->map = std::make_unique<faiss::IndexIVFFlat>(hh->space.get(), dim, nlist, metric == 0 ? faiss::METRIC_L2 : faiss::METRIC_INNER_PRODUCT,
-														 false);
+														 metric == 2);
 		h = hh.release();
 	});
 	return h;
@@ -75,8 +79,16 @@ int ref_ivf_train_add(void* hv, size_t n, const float* vecs, const int64_t* ids)
 	auto* h = static_cast<IvfHandle*>(hv);
 	return guarded([&] {
 		h->map->set_direct_map_type(faiss::DirectMap::Type::Hashtable);
-		h->map->train(faiss::idx_t(n), vecs, nullptr);
-		h->map->add_with_ids(faiss::idx_t(n), vecs, nullptr, reinterpret_cast<const faiss::idx_t*>(ids));
+		std::vector<float> norms;  // Cosine: the norm coefficients IvfIndex hands over (space_->get_xb_norms(), ivf_index.cc:101-102)
+		if (h->metric == 2) {
+			norms.resize(n);
+			for (size_t i = 0; i < n; ++i) {
+				norms[i] = reindexer::ann::CalculateL2Module(vecs + i * h->dim, int32_t(h->dim));
+			}
+		}
+		const float* np = norms.empty() ? nullptr : norms.data();
+		h->map->train(faiss::idx_t(n), vecs, np);
+		h->map->add_with_ids(faiss::idx_t(n), vecs, np, reinterpret_cast<const faiss::idx_t*>(ids));
 	});
 }
 

@@ -1406,6 +1406,7 @@ struct rxgpu_ivf_device {
 	uint32_t nlist = 0;
 	uint64_t index_version = 0;
 	DevBuf<float> centroids;       // [nlist][pitch]
+	DevBuf<float> cnorm;           // Cosine: 1/||centroid|| (IndexFlatCosine's norm coefficients)
 	DevBuf<uint32_t> list_begin;   // [nlist + 1] rows of list l = [list_begin[l], list_begin[l + 1])
 	std::mutex mtx;                // one IVF batch at a time per index (scratch below)
 	DevBuf<float> d_q, d_dist;
@@ -1425,9 +1426,6 @@ int rxgpu_ivf_import(rxgpu_index* ix, uint32_t nlist, const float* centroids, co
 	}
 	if (!centroids || !list_sizes || nlist == 0) {
 		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
-	}
-	if (ix->metric == RXGPU_COS) {
-		return fail(RXGPU_ERR_PARAMS, "rxgpu: the IVF device path supports L2 and inner product");
 	}
 	if (nlist > 16384) {
 		return fail(RXGPU_ERR_PARAMS, "rxgpu: at most 16384 IVF centroids on the device path");
@@ -1453,6 +1451,12 @@ int rxgpu_ivf_import(rxgpu_index* ix, uint32_t nlist, const float* centroids, co
 		RX_CUDA(cudaMemcpy2D(h->centroids.p, size_t(ix->pitch) * 4, centroids, size_t(ix->dim) * 4, size_t(ix->dim) * 4, nlist,
 							 cudaMemcpyHostToDevice));
 		RX_CUDA(cudaMemcpy(h->list_begin.p, begin.data(), begin.size() * 4, cudaMemcpyHostToDevice));
+		if (ix->metric == RXGPU_COS) {
+			RX_CUDA(h->cnorm.ensure(nlist));
+			norm_coef_kernel<<<(nlist * 32 + 255) / 256, 256, 0, ix->stream>>>(h->centroids.p, ix->pitch, ix->dim, 0, nlist, h->cnorm.p);
+			RX_CUDA(cudaGetLastError());
+			RX_CUDA(cudaStreamSynchronize(ix->stream));
+		}
 		h->index_version = ix->version;
 		if (ix->ivf) {
 			ivfRelease(ix->ivf);
@@ -1509,16 +1513,17 @@ int rxgpu_ivf_search_knn(const rxgpu_index* ix, uint32_t nq, const float* querie
 	if (ix->metric == RXGPU_L2) {
 		RX_CUDA(cudaFuncSetAttribute(ivf_coarse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(coarseSmem)));
 		ivf_coarse_kernel<true><<<nq, kScanThreads, coarseSmem, st>>>(h->centroids.p, ix->pitch, ix->dim, h->nlist, h->d_q.p, nq, nprobe,
-																	   h->list_begin.p, h->d_work.p);
+																	   h->list_begin.p, nullptr, h->d_work.p);
 	} else {
 		RX_CUDA(cudaFuncSetAttribute(ivf_coarse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(coarseSmem)));
 		ivf_coarse_kernel<false><<<nq, kScanThreads, coarseSmem, st>>>(h->centroids.p, ix->pitch, ix->dim, h->nlist, h->d_q.p, nq, nprobe,
-																		h->list_begin.p, h->d_work.p);
+																		h->list_begin.p, ix->metric == RXGPU_COS ? h->cnorm.p : nullptr, h->d_work.p);
 	}
 	RX_CUDA(cudaGetLastError());
 	// list scans: the exact scan kernel in work-item mode, one CTA per (query, probed list), fused top-k per CTA
 	ScanArgs a{};
 	a.rows = ix->d_rows;
+	a.norm_coefs = ix->metric == RXGPU_COS ? ix->d_norms : nullptr;
 	a.queries = h->d_q.p;
 	a.pitch = ix->pitch;
 	a.dim = ix->dim;

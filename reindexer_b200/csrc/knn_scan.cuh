@@ -473,7 +473,7 @@ __device__ __forceinline__ float row_dist_warp(const float4* rows4, uint32_t pit
 template <bool kIsL2>
 __global__ void __launch_bounds__(kScanThreads) ivf_coarse_kernel(const float* centroids, uint32_t pitch, uint32_t dim, uint32_t nlist,
 																  const float* queries, uint32_t nq, uint32_t nprobe, const uint32_t* list_begin,
-																  uint4* work) {
+																  const float* centroid_norm_coefs, uint4* work) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	__shared__ uint64_t s_best[kScanWarps];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -490,7 +490,10 @@ __global__ void __launch_bounds__(kScanThreads) ivf_coarse_kernel(const float* c
 	__syncthreads();
 	const float4* rows4 = reinterpret_cast<const float4*>(centroids);
 	for (uint32_t c = warp; c < nlist; c += kScanWarps) {
-		const float d = row_dist_warp<kIsL2>(rows4, pitch4, nch, c, sq4, lane);
+		float d = row_dist_warp<kIsL2>(rows4, pitch4, nch, c, sq4, lane);
+		if (!kIsL2 && centroid_norm_coefs != nullptr) {
+			d *= centroid_norm_coefs[c];  // IndexFlatCosine: knn_cosine = IP * norm coefficient of the centroid
+		}
 		if (lane == 0) {
 			keys[c] = make_key(d, c);
 		}

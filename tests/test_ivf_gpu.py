@@ -3,7 +3,7 @@
 inverted lists are imported into the device index, and every search is compared with faiss::IndexIVFFlat::search on the same state."""
 import numpy as np
 import pytest
-from helpers import ATOL, RTOL
+from helpers import ATOL, RTOL, prep_query
 
 import reindexer_b200 as rx
 from oracle import oracle as O
@@ -23,17 +23,18 @@ def build(metric, n, dim, nlist, seed):
     return ref, gpu, st
 
 
-@pytest.mark.parametrize("metric,dim,nlist", [(rx.L2, 32, 16), (rx.L2, 96, 64), (rx.IP, 64, 32), (rx.L2, 768, 24), (rx.IP, 200, 50)])
+@pytest.mark.parametrize("metric,dim,nlist", [(rx.L2, 32, 16), (rx.L2, 96, 64), (rx.IP, 64, 32), (rx.L2, 768, 24), (rx.IP, 200, 50),
+                                              (rx.COS, 48, 20), (rx.COS, 384, 32)])
 def test_ivf_search_matches_reference_faiss(metric, dim, nlist):
     n = 12000 if dim < 500 else 4000
     ref, gpu, st = build(metric, n, dim, nlist, 3100 + dim)
-    queries = O.synth_matrix(3200 + dim, 40, dim)
+    queries = np.stack([prep_query(metric, q) for q in O.synth_matrix(3200 + dim, 40, dim)])
     for k, nprobe in [(10, 1), (10, 4), (1, 8), (50, nlist // 2), (10, nlist), (10, nlist + 7)]:
         d, l, c = gpu.ivf_search_knn(queries, k, nprobe)
         for i in range(len(queries)):
             dr, lr = ref.search(queries[i], k, nprobe)
             assert c[i] == len(lr), (k, nprobe, i, c[i], len(lr))
-            dr_map = dr if metric == rx.L2 else -dr  # FAISS reports +IP (descending); the map space is -IP (ascending)
+            dr_map = dr if metric == rx.L2 else -dr  # FAISS reports +IP / +cos (descending); the map space is the negation (ascending)
             assert np.allclose(d[i, :c[i]], dr_map, rtol=RTOL, atol=ATOL), (k, nprobe, i)
             if not (l[i, :c[i]] == lr).all():  # ids may differ only where neighbouring distances are within fp noise
                 bad = np.nonzero(l[i, :c[i]] != lr)[0]

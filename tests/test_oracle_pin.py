@@ -129,20 +129,26 @@ def test_reference_ivf_oracle_is_self_consistent():
     nprobe nearest exported centroids by brute force reproduces IndexIVFFlat::search"""
     n, dim, nlist, k, nprobe = 4000, 24, 16, 10, 3
     vecs, labels = O.synth_matrix(901, n, dim), O.row_labels(n)
-    for metric in (O.L2, O.IP):
+    def coef(m):  # CalculateL2Module: 1/||v|| with the "already normalised" shortcut (tools/normalize.cc:10-23)
+        s2 = (m.astype(np.float64) ** 2).sum(axis=1)
+        return np.where(np.abs(1.0 - s2) > 1e-5, 1.0 / np.sqrt(np.maximum(s2, 1e-30)), 1.0).astype(np.float32)
+
+    for metric in (O.L2, O.IP, O.COS):
         ref = O.RefIvf(metric, dim, nlist)
         ref.train_add(labels, vecs)
         st = ref.export()
         begin = np.concatenate([[0], np.cumsum(st["list_sizes"].astype(np.int64))])
         for q in O.synth_matrix(902, 12, dim):
+            if metric == O.COS:
+                q = O.normalize_copy(q)[0]  # the caller normalises the key (ivf_index.cc: NormalizeCopyVector)
             if metric == O.L2:
                 cd = ((st["centroids"] - q) ** 2).sum(axis=1)
             else:
-                cd = -(st["centroids"] @ q)
+                cd = -(st["centroids"] @ q) * (coef(st["centroids"]) if metric == O.COS else 1.0)
             probe = np.argsort(cd, kind="stable")[:nprobe]
             rows = np.concatenate([np.arange(begin[c], begin[c + 1]) for c in probe])
             sub = st["vecs"][rows]
-            dd = ((sub - q) ** 2).sum(axis=1) if metric == O.L2 else -(sub @ q)
+            dd = ((sub - q) ** 2).sum(axis=1) if metric == O.L2 else -(sub @ q) * (coef(sub) if metric == O.COS else 1.0)
             order = np.argsort(dd, kind="stable")[:k]
             dr, lr = ref.search(q, k, nprobe)
             assert (st["labels"][rows[order]] == lr).all()
