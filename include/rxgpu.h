@@ -186,6 +186,10 @@ int rxgpu_hnsw_search_range(const rxgpu_index*, const float* query /* host */, f
 int rxgpu_ivf_import(rxgpu_index*, uint32_t nlist, const float* centroids /* nlist x dim, host */, const uint64_t* list_sizes /* nlist */);
 int rxgpu_ivf_search_knn(const rxgpu_index*, uint32_t nq, const float* queries /* host */, uint32_t k, uint32_t nprobe, float* out_dist,
 						 uint64_t* out_label, uint32_t* out_count);
+/* map_->range_search(1, key, radius, &result, &params) (ivf_index.cc:205-300): every row of the nprobe probed lists with
+ * dist < radius in map space (strict; IP / Cosine radius negated by the caller), best first; *out_n = total number of matches. */
+int rxgpu_ivf_search_range(const rxgpu_index*, const float* query /* host */, float radius, uint32_t nprobe, uint64_t max_out,
+						   float* out_dist, uint64_t* out_label, uint64_t* out_n);
 
 /* ---------------------------------------------------------------- ft_fast full-text merge (BM25 scoring over posting lists)
  * Replaces ft::Merger<IdCont, ft::MergeData, OffsetT>::Merge<Bm25Rx|Bm25Classic|TermCount>  core/ft/ft_fast/mergerimpl.h:466-566

@@ -435,6 +435,8 @@ def ref_ivf_lib():
         lib.ref_ivf_search.restype = C.c_int64
         lib.ref_ivf_search.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_size_t, _f32p, _i64p]
         lib.ref_ivf_search_batch.argtypes = [C.c_void_p, C.c_size_t, _f32p, C.c_size_t, C.c_size_t, _f32p, _i64p]
+        lib.ref_ivf_range_search.restype = C.c_int64
+        lib.ref_ivf_range_search.argtypes = [C.c_void_p, _f32p, C.c_float, C.c_size_t, C.c_size_t, _f32p, _i64p]
         lib.ref_ivf_export_header.argtypes = [C.c_void_p, _i64p]
         lib.ref_ivf_export.argtypes = [C.c_void_p, _f32p, _i64p, _i64p, _f32p]
         _ref_ivf = lib
@@ -468,6 +470,15 @@ class RefIvf:
         i = np.zeros(k, np.int64)
         n = self.lib.ref_ivf_search(self.h, _p(q, _f32p), k, nprobe, _p(d, _f32p), _p(i, _i64p))
         assert n >= 0, self.lib.ref_ivf_last_error().decode()
+        return d[:n].copy(), i[:n].astype(np.uint64)
+
+    def range_search(self, q, radius, nprobe, max_out=100000):
+        """(dist, label) unsorted; radius and dist in FAISS' convention"""
+        q = np.ascontiguousarray(q, np.float32)
+        d = np.zeros(max_out, np.float32)
+        i = np.zeros(max_out, np.int64)
+        n = self.lib.ref_ivf_range_search(self.h, _p(q, _f32p), float(radius), nprobe, max_out, _p(d, _f32p), _p(i, _i64p))
+        assert 0 <= n <= max_out, (n, self.lib.ref_ivf_last_error().decode())
         return d[:n].copy(), i[:n].astype(np.uint64)
 
     def search_batch(self, queries, k, nprobe):

@@ -119,6 +119,25 @@ int ref_ivf_search_batch(const void* hv, size_t nq, const float* queries, size_t
 	});
 }
 
+// map_->range_search(1, key, radius, &result, &params) (ivf_index.cc:211-212); returns the number of results, writes at most maxOut
+// (unsorted, as FAISS returns them); radius in FAISS' convention (L2: dis < radius, IP / Cosine: dis > radius)
+int64_t ref_ivf_range_search(const void* hv, const float* query, float radius, size_t nprobe, size_t maxOut, float* dists, int64_t* ids) {
+	auto* h = static_cast<const IvfHandle*>(hv);
+	int64_t n = -1;
+	guarded([&] {
+		faiss::IVFSearchParameters p;
+		p.nprobe = nprobe;
+		faiss::RangeSearchResult res(1);
+		h->map->range_search(1, query, radius, &res, &p);
+		n = int64_t(res.lims[1] - res.lims[0]);
+		for (int64_t i = 0; i < n && size_t(i) < maxOut; ++i) {
+			dists[i] = res.distances[res.lims[0] + i];
+			ids[i] = res.labels[res.lims[0] + i];
+		}
+	});
+	return n;
+}
+
 // hdr: [nlist, ntotal]
 int ref_ivf_export_header(const void* hv, int64_t* hdr) {
 	auto* h = static_cast<const IvfHandle*>(hv);

@@ -116,6 +116,7 @@ _SIGNATURES = {
                                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "rxgpu_ivf_import": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, _u64p]),
     "rxgpu_ivf_search_knn": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, C.c_uint32, C.c_uint32, _f32p, _u64p, _u32p]),
+    "rxgpu_ivf_search_range": (C.c_int, [C.c_void_p, _f32p, C.c_float, C.c_uint32, C.c_uint64, _f32p, _u64p, C.POINTER(C.c_uint64)]),
     "rxgpu_ft_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, _u32p, _f32p, _u8p, C.c_int]),
     "rxgpu_ft_destroy": (None, [C.c_void_p]),
     "rxgpu_ft_add_postings": (C.c_int, [C.c_void_p, C.POINTER(FtPostings), _u32p]),
@@ -331,6 +332,16 @@ class GpuBruteforceSearch:
         c = np.zeros(nq, np.uint32)
         _check(self._lib.rxgpu_ivf_search_knn(self._h, nq, _p(q, _f32p), k, nprobe, _p(d, _f32p), _p(l, _u64p), _p(c, _u32p)))
         return d, l, c
+
+    def ivf_search_range(self, query, radius: float, nprobe: int, max_out: int | None = None):
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        max_out = self.size() if max_out is None else max_out
+        d = np.zeros(max(max_out, 1), np.float32)
+        l = np.zeros(max(max_out, 1), np.uint64)
+        n = C.c_uint64(0)
+        _check(self._lib.rxgpu_ivf_search_range(self._h, _p(q, _f32p), radius, nprobe, max_out, _p(d, _f32p), _p(l, _u64p), C.byref(n)))
+        m = min(n.value, max_out)
+        return d[:m], l[:m], n.value
 
     # -- bench / test support ------------------------------------------------------------------------------------------
     def append_synth(self, seed: int, first_row: int, n: int):

@@ -1413,6 +1413,8 @@ struct rxgpu_ivf_device {
 	DevBuf<uint4> d_work;
 	DevBuf<uint64_t> d_lists, d_label;
 	DevBuf<uint32_t> d_idx, d_count;
+	DevBuf<uint64_t> d_range;
+	DevBuf<unsigned long long> d_range_count;
 };
 namespace rxgpu {
 void ivfRelease(rxgpu_ivf_device* p) { delete p; }
@@ -1577,6 +1579,100 @@ int rxgpu_ivf_search_knn(const rxgpu_index* ix, uint32_t nq, const float* querie
 				out_label[size_t(q) * k + j] = hits[j].label;
 			}
 			out_count[q] = uint32_t(hits.size());
+		}
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
+	}
+	return 0;
+}
+
+int rxgpu_ivf_search_range(const rxgpu_index* ix, const float* query, float radius, uint32_t nprobe, uint64_t max_out, float* out_dist,
+						   uint64_t* out_label, uint64_t* out_n) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	if (!query || !out_n || (max_out && (!out_dist || !out_label))) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	*out_n = 0;
+	g_stats = rxgpu_search_stats{};
+	rxgpu_ivf_device* h = ix->ivf;
+	if (!h) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: no IVF lists imported into this index");
+	}
+	if (h->index_version != ix->version) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: the index changed after the IVF lists were imported");
+	}
+	nprobe = std::max(1u, std::min(nprobe, h->nlist));
+	const uint32_t nch = (ix->dim + 127u) / 128u;
+	const size_t coarseSmem = size_t(nch) * 512 + size_t(h->nlist) * 8;
+	if (coarseSmem > 200 * 1024) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: dimension / centroid count exceeds the coarse quantiser's shared memory");
+	}
+	std::lock_guard<std::mutex> lck(h->mtx);
+	cudaStream_t st = ix->stream;
+	RX_CUDA(h->d_q.ensure(ix->dim));
+	RX_CUDA(h->d_work.ensure(nprobe));
+	RX_CUDA(h->d_range_count.ensure(1));
+	RX_CUDA(cudaMemcpyAsync(h->d_q.p, query, size_t(ix->dim) * 4, cudaMemcpyHostToDevice, st));
+	if (ix->metric == RXGPU_L2) {
+		RX_CUDA(cudaFuncSetAttribute(ivf_coarse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(coarseSmem)));
+		ivf_coarse_kernel<true><<<1, kScanThreads, coarseSmem, st>>>(h->centroids.p, ix->pitch, ix->dim, h->nlist, h->d_q.p, 1, nprobe,
+																	  h->list_begin.p, nullptr, h->d_work.p);
+	} else {
+		RX_CUDA(cudaFuncSetAttribute(ivf_coarse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(coarseSmem)));
+		ivf_coarse_kernel<false><<<1, kScanThreads, coarseSmem, st>>>(h->centroids.p, ix->pitch, ix->dim, h->nlist, h->d_q.p, 1, nprobe,
+																	   h->list_begin.p, ix->metric == RXGPU_COS ? h->cnorm.p : nullptr,
+																	   h->d_work.p);
+	}
+	RX_CUDA(cudaGetLastError());
+	g_stats.launches = 1;
+	uint64_t cap = std::max<uint64_t>(h->d_range.n, 1u << 14);
+	unsigned long long total = 0;
+	for (;;) {  // like the brute-force range search: grow the result buffer and rescan when it was too small
+		RX_CUDA(h->d_range.ensure(cap));
+		RX_CUDA(cudaMemsetAsync(h->d_range_count.p, 0, sizeof(unsigned long long), st));
+		ScanArgs a{};
+		a.rows = ix->d_rows;
+		a.norm_coefs = ix->metric == RXGPU_COS ? ix->d_norms : nullptr;
+		a.queries = h->d_q.p;
+		a.pitch = ix->pitch;
+		a.dim = ix->dim;
+		a.nq = 1;
+		a.k1 = 1;
+		a.mode = kModeRange;
+		a.bound = radius;
+		a.range_out = h->d_range.p;
+		a.range_count = h->d_range_count.p;
+		a.range_cap = cap;
+		a.work = h->d_work.p;
+		a.nwork = nprobe;
+		unsigned grid = 0;
+		RX_CUDA(launchScan(ix, 1, a, &grid, st));
+		g_stats.launches += 1;
+		RX_CUDA(cudaMemcpyAsync(&total, h->d_range_count.p, sizeof(total), cudaMemcpyDeviceToHost, st));
+		RX_CUDA(cudaStreamSynchronize(st));
+		if (total <= cap) {
+			break;
+		}
+		cap = total;
+	}
+	*out_n = total;
+	try {
+		std::vector<uint64_t> keys(total);
+		if (total) {
+			RX_CUDA(cudaMemcpy(keys.data(), h->d_range.p, total * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+		}
+		std::vector<Hit> res(total);
+		for (unsigned long long i = 0; i < total; ++i) {
+			const uint32_t row = uint32_t(keys[i]);
+			res[i] = Hit{ord_float(uint32_t(keys[i] >> 32)), row, ix->h_labels[row]};
+		}
+		std::sort(res.begin(), res.end(), hitLessByLabel);  // IvfIndex sorts the range result by distance (ivf_index.cc:220-224); ties by label here
+		const uint64_t nout = std::min<uint64_t>(total, max_out);
+		for (uint64_t j = 0; j < nout; ++j) {
+			out_dist[j] = res[j].dist;
+			out_label[j] = res[j].label;
 		}
 	} catch (const std::bad_alloc&) {
 		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");

@@ -63,3 +63,21 @@ def test_ivf_errors_and_staleness():
     assert "no IVF lists imported" in e.value.what
     with pytest.raises(rx.RxGpuError):
         fresh.ivf_import(st["centroids"], st["list_sizes"])  # sizes do not add up to the rows of this index
+
+
+@pytest.mark.parametrize("metric", [rx.L2, rx.IP, rx.COS])
+def test_ivf_range_search_matches_reference_faiss(metric):
+    n, dim, nlist, nprobe = 8000, 40, 16, 5
+    ref, gpu, st = build(metric, n, dim, nlist, 3500 + metric)
+    queries = np.stack([prep_query(metric, q) for q in O.synth_matrix(3600 + metric, 12, dim)])
+    for i, q in enumerate(queries):
+        d, l, c = gpu.ivf_search_knn(q, 60, nprobe)
+        j = [5, 20, 59][i % 3]
+        radius = float((np.float64(d[0, j - 1]) + np.float64(d[0, j])) / 2)  # map space, halfway between two neighbours
+        rd, rl, total = gpu.ivf_search_range(q, radius, nprobe)
+        fd, fl = ref.range_search(q, radius if metric == rx.L2 else -radius, nprobe)
+        assert total == len(rl) == len(fl) == j
+        assert sorted(rl.tolist()) == sorted(fl.tolist())
+        assert (np.diff(rd) >= 0).all() and (rl == l[0, :j]).all()
+    rd, rl, total = gpu.ivf_search_range(queries[0], 1e30, nlist, max_out=7)  # everything, truncated output
+    assert total == n and len(rl) == 7
