@@ -257,6 +257,11 @@ bool tcEligible(const rxgpu_index* ix, uint32_t nq, uint32_t k1, int mode) {
 	if (tcQueryBlock(nq, (ix->dim + kTcChunkK - 1) / kTcChunkK) == 0) {
 		return false;
 	}
+	// the error coefficient kTcErrCoef = 0.0042 certifies |q~.v~ - q.v| <= c ||q|| ||v|| only while
+	// 2^-8 + 2^-18 + dim * 2^-23 <= 0.0042 (two bf16 roundings + fp32 accumulation): dim <= 2400; beyond 2048 dims the exact scan answers
+	if (ix->dim > 2048) {
+		return false;
+	}
 	return ix->tc_mode == 1 || (nq >= 64 && ix->size >= 100000);
 }
 

@@ -6,7 +6,8 @@
 // per query) are then re-ranked with the exact fp32 routine of knn_scan_warp, so the final result is identical to the exact scan.
 //
 //   error bound   |q~.v~ - q.v| <= c * ||q|| * ||v||,  c = 2^-8 + 2^-18 (two bf16 roundings, unit roundoff 2^-9 each)
-//                                                        + 768 * 2^-23 (fp32 accumulation in the MMA) , used with 5% slack
+//                                                        + dim * 2^-23 (fp32 accumulation in the MMA); c = 0.0042 leaves 5% slack
+//                                                        at 768 dims and 1% at 2048 dims, the largest dimension the filter accepts
 //   lower bound   lb = d~ - e, upper bound ub = d~ + e in map space (smaller is better)
 //   threshold     tau_q = k1-th smallest ub over all DISTINCT rows seen so far by any CTA (one small list per query in HBM,
 //                 updated under a per-query lock -- only O(k log n) successful inserts per query over a whole pass) => a valid
