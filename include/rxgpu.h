@@ -162,6 +162,11 @@ int rxgpu_hnsw_search_knn(const rxgpu_index*, uint32_t nq, const float* queries 
 int rxgpu_hnsw_search_knn_device(const rxgpu_index*, uint32_t nq, const float* d_queries, uint32_t k, uint32_t ef, float* d_out_dist,
 								 uint32_t* d_out_idx, uint32_t* d_out_count, uint32_t* d_stats /* nq x 2 or NULL */, void* stream);
 
+/* HierarchicalNSWImpl::MarkDelete (hnswalg.h:1303-1335): the row stays in the graph as a tombstone -- searches traverse it but never
+ * return it (searchBaseLayerST<bare_bone = false>, :829-975).  Errors: label unknown (errNotFound), already deleted (errLogic).
+ * A search that meets more than 128 deleted nodes waiting for expansion at once fails with errLogic (rebuild the graph). */
+int rxgpu_hnsw_mark_deleted(rxgpu_index*, uint64_t label);
+uint64_t rxgpu_hnsw_deleted_count(const rxgpu_index*); /* DeletedCountUnsafe */
 /* labels of n shard-local internal indices (device pointers; enqueued on `stream`): the HNSW device search returns indices, the
  * multi-GPU merge needs labels */
 int rxgpu_gather_labels_device(const rxgpu_index*, uint64_t n, const uint32_t* d_idx, uint64_t* d_out_label, void* stream);

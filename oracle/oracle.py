@@ -123,6 +123,7 @@ def ref_knn_lib():
         lib.ref_hnsw_add_batch.argtypes = [C.c_void_p, C.c_size_t, _u64p, _f32p, C.c_int]
         lib.ref_hnsw_search_knn.restype = C.c_int64
         lib.ref_hnsw_search_knn.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, C.c_size_t, C.c_size_t, _f32p, _u64p]
+        lib.ref_hnsw_mark_delete.argtypes = [C.c_void_p, C.c_uint64]
         lib.ref_hnsw_search_range.restype = C.c_int64
         lib.ref_hnsw_search_range.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, C.c_float, C.c_size_t, C.c_size_t, _f32p, _u64p]
         lib.ref_hnsw_search_knn_batch.argtypes = [C.c_void_p, C.c_uint32, _f32p, _f32p, C.c_size_t, C.c_size_t, C.c_int, _f32p,
@@ -367,6 +368,10 @@ class RefHnsw:
                                          _p(l, _u64p))
         assert n >= 0, self.lib.ref_last_error().decode()
         return d[:n].copy(), l[:n].copy()
+
+    def mark_delete(self, label):
+        rc = self.lib.ref_hnsw_mark_delete(self.h, int(label))
+        assert rc == 0, self.lib.ref_last_error().decode()
 
     def search_range(self, q, radius, ef, qnorm=None, max_out=None):
         q = np.ascontiguousarray(q, dtype=np.float32)

@@ -277,6 +277,11 @@ int64_t ref_hnsw_search_knn(const void* hv, const float* query, int has_norm, fl
 	});
 	return n;
 }
+int ref_hnsw_mark_delete(void* hv, uint64_t label) {
+	auto* h = static_cast<HnswHandle*>(hv);
+	return guarded([&] { withHnsw(h, [&](auto& g) { g.MarkDelete(label); }); });
+}
+
 // HierarchicalNSWImpl::SearchRange (hnswalg.h:2015-2070): ef-search seed, then BFS over neighbours with dist < radius
 int64_t ref_hnsw_search_range(const void* hv, const float* query, int has_norm, float qnorm, float radius, size_t ef, size_t maxOut,
 							  float* dists, uint64_t* labels) {
@@ -312,7 +317,11 @@ int ref_hnsw_search_metrics(const void* hv, const float* query, int has_norm, fl
 			g.metric_hops = 0;
 			(void)has_norm, (void)qnorm;  // queryNormCoef() is 1 for a non-quantised graph (hnswalg.h:1855-1863)
 			const auto ep = g.getLayer0EntryPoint(query, 1.f);
-			auto top = g.template searchBaseLayerST<true, true>(ep, query, 1.f, ef);
+			if (g.DeletedCountUnsafe() == 0) {  // the branch search() takes (hnswalg.h:1982)
+				auto top = g.template searchBaseLayerST<true, true>(ep, query, 1.f, ef);
+			} else {
+				auto top = g.template searchBaseLayerST<false, true>(ep, query, 1.f, ef);
+			}
 			*distComps = g.metric_distance_computations.load();
 			*hops = g.metric_hops.load();
 		});

@@ -110,6 +110,8 @@ _SIGNATURES = {
     "rxgpu_select_knn": (C.c_int, [C.c_void_p, _f32p, C.POINTER(SelectParams), C.c_uint64, _i32p, _f32p, _u64p]),
     "rxgpu_hnsw_import": (C.c_int, [C.c_void_p, C.POINTER(HnswGraph)]),
     "rxgpu_hnsw_search_knn": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, C.c_uint32, C.c_uint32, _f32p, _u64p, _u32p, _u32p]),
+    "rxgpu_hnsw_mark_deleted": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "rxgpu_hnsw_deleted_count": (C.c_uint64, [C.c_void_p]),
     "rxgpu_gather_labels_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rxgpu_hnsw_search_range": (C.c_int, [C.c_void_p, _f32p, C.c_float, C.c_uint32, C.c_uint64, _f32p, _u64p, C.POINTER(C.c_uint64)]),
     "rxgpu_hnsw_search_knn_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
@@ -300,6 +302,12 @@ class GpuBruteforceSearch:
         _check(self._lib.rxgpu_hnsw_search_knn(self._h, nq, _p(q, _f32p), k, ef, _p(d, _f32p), _p(l, _u64p), _p(c, _u32p),
                                                _p(st, _u32p)))
         return (d, l, c, st) if with_stats else (d, l, c)
+
+    def hnsw_mark_deleted(self, label: int):
+        _check(self._lib.rxgpu_hnsw_mark_deleted(self._h, int(label)))
+
+    def hnsw_deleted_count(self) -> int:
+        return int(self._lib.rxgpu_hnsw_deleted_count(self._h))
 
     def hnsw_search_knn_device(self, nq, d_queries_ptr, k, ef, d_dist_ptr, d_idx_ptr, d_count_ptr, d_stats_ptr=0, stream=0):
         _check(self._lib.rxgpu_hnsw_search_knn_device(self._h, nq, d_queries_ptr, k, ef, d_dist_ptr, d_idx_ptr, d_count_ptr,

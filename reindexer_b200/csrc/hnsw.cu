@@ -35,6 +35,7 @@ constexpr uint32_t kExpanded = 0x80000000u;
 constexpr uint32_t kMaxEf = 1024;
 constexpr uint32_t kVlogCap = 1u << 15;
 constexpr int kMaxNeighbours = 64;  // maxM0 = 2*M; M <= 32 on the device path
+constexpr uint32_t kHnswXCap = 128;  // deleted nodes waiting for expansion (per query), see the search kernel
 
 struct HnswArgs {
 	const float* rows;
@@ -51,6 +52,8 @@ struct HnswArgs {
 	uint32_t* out_idx;  // [nq][k]
 	uint32_t* out_count;
 	uint32_t* stats;    // [nq][2] or null
+	const uint32_t* deleted;  // bitmap by internal id (MarkDelete, hnswalg.h:1303-1335) or null: the bare-bone search
+	uint32_t* overflow;       // [nq] set when more than kHnswXCap deleted nodes were waiting at once (result not trustworthy)
 	uint32_t pitch, dim, n, l0_stride, up_stride;
 	int maxlevel;
 	uint32_t enterpoint;
@@ -137,13 +140,15 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(const HnswArg
 	const uint32_t dp4 = nch * 32u;
 	// per-warp shared memory: query | list dist[ef] | list id[ef] | neighbour ids[64] | neighbour dists[64]
 	const uint32_t efp = (a.ef + 3u) & ~3u;  // keeps every warp's region 16-byte aligned
-	const size_t per_warp = size_t(dp4) * 16 + size_t(efp) * 8 + kMaxNeighbours * 8;
+	const size_t per_warp = size_t(dp4) * 16 + size_t(efp) * 8 + kMaxNeighbours * 8 + kHnswXCap * 8;
 	unsigned char* base = smem_raw + per_warp * warp;
 	float4* sq4 = reinterpret_cast<float4*>(base);
 	float* l_dist = reinterpret_cast<float*>(base + size_t(dp4) * 16);
 	uint32_t* l_id = reinterpret_cast<uint32_t*>(l_dist + efp);
 	uint32_t* s_ids = l_id + efp;
 	float* s_d = reinterpret_cast<float*>(s_ids + kMaxNeighbours);
+	float* x_dist = s_d + kMaxNeighbours;  // deleted candidates (in candidate_set, never in top_candidates), ascending
+	uint32_t* x_id = reinterpret_cast<uint32_t*>(x_dist + kHnswXCap);
 
 	const uint32_t slot = blockIdx.x * kHnswWarps + warp;
 	uint32_t* visited = a.visited + size_t(slot) * a.words;
@@ -205,18 +210,35 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(const HnswArg
 		}
 
 		// ---- searchBaseLayerST (hnswalg.h:829-975), unified sorted list
-		uint32_t size = 1;
+		// With deleted nodes (a.deleted != nullptr, the reference's non-bare-bone branch) the two heaps differ: a deleted node is a
+		// candidate (it is expanded) but never a result.  Deleted candidates wait in a second small sorted list X; the next node to
+		// expand is the closer of (first unexpanded entry of the result list, head of X); the stop rule becomes "closest candidate
+		// worse than the ef-th result AND the result list is full" (layer0ShouldStopBeforePop :860-869).
+		const bool has_deleted = a.deleted != nullptr;
+		auto is_deleted = [&](uint32_t id) { return has_deleted && ((a.deleted[id >> 5] >> (id & 31)) & 1u); };
+		uint32_t size = 0, xsize = 0;
 		uint32_t vcount = 0;
+		bool x_overflow = false;
 		if (lane == 0) {
-			l_dist[0] = curdist;
-			l_id[0] = cur;
+			if (!is_deleted(cur)) {  // initLayer0SearchState :844-855
+				l_dist[0] = curdist;
+				l_id[0] = cur;
+			} else {
+				x_dist[0] = 3.402823466e+38f;
+				x_id[0] = cur;
+			}
 			atomicOr(&visited[cur >> 5], 1u << (cur & 31));
 			vlog[0] = cur;
+		}
+		if (!is_deleted(cur)) {
+			size = 1;
+		} else {
+			xsize = 1;
 		}
 		vcount = 1;
 		__syncwarp();
 		for (;;) {
-			// first unexpanded entry
+			// first unexpanded entry of the result list
 			int pos = -1;
 			for (uint32_t b = 0; b < size && pos < 0; b += 32) {
 				const uint32_t i = b + lane;
@@ -226,13 +248,39 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(const HnswArg
 					pos = int(b) + __ffs(m) - 1;
 				}
 			}
-			if (pos < 0) {
-				break;  // candidate_set exhausted / next candidate worse than lowerBound (layer0ShouldStopBeforePop :860-869)
-			}
-			const uint32_t node = l_id[pos];
-			__syncwarp();
-			if (lane == 0) {
-				l_id[pos] = node | kExpanded;
+			uint32_t node;
+			if (xsize && (pos < 0 || x_dist[0] < l_dist[pos])) {
+				// a deleted candidate is the closest one: expanded unless it is worse than a full result list
+				if (size >= a.ef && x_dist[0] > l_dist[size - 1]) {
+					break;
+				}
+				node = x_id[0];
+				__syncwarp();
+				for (uint32_t b = 0; b + 1 < xsize; b += 32) {  // pop the head
+					const uint32_t i = b + lane;
+					float td = 0.f;
+					uint32_t ti = 0;
+					if (i + 1 < xsize) {
+						td = x_dist[i + 1];
+						ti = x_id[i + 1];
+					}
+					__syncwarp();
+					if (i + 1 < xsize) {
+						x_dist[i] = td;
+						x_id[i] = ti;
+					}
+					__syncwarp();
+				}
+				--xsize;
+			} else {
+				if (pos < 0) {
+					break;  // candidate_set exhausted / next candidate worse than lowerBound (layer0ShouldStopBeforePop :860-869)
+				}
+				node = l_id[pos];
+				__syncwarp();
+				if (lane == 0) {
+					l_id[pos] = node | kExpanded;
+				}
 			}
 			const uint32_t* ll = a.level0 + size_t(node) * a.l0_stride;
 			const uint32_t cnt = min(ll[0], uint32_t(kMaxNeighbours));
@@ -273,6 +321,40 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(const HnswArg
 				if (!consider) {
 					continue;
 				}
+				if (is_deleted(nid)) {  // candidate_set only (:943-953): sorted insert into X
+					if (xsize == kHnswXCap) {
+						x_overflow = true;
+						continue;
+					}
+					uint32_t p = 0;
+					for (uint32_t b = 0; b < xsize; b += 32) {
+						const uint32_t i = b + lane;
+						p += __popc(__ballot_sync(0xffffffffu, i < xsize && x_dist[i] <= d));
+					}
+					for (int b = int(xsize / 32) * 32; b >= 0; b -= 32) {
+						const uint32_t i = uint32_t(b) + lane;
+						const bool mv = i > p && i <= xsize;
+						float td = 0.f;
+						uint32_t ti = 0;
+						if (mv) {
+							td = x_dist[i - 1];
+							ti = x_id[i - 1];
+						}
+						__syncwarp();
+						if (mv) {
+							x_dist[i] = td;
+							x_id[i] = ti;
+						}
+						__syncwarp();
+					}
+					if (lane == 0) {
+						x_dist[p] = d;
+						x_id[p] = nid;
+					}
+					__syncwarp();
+					++xsize;
+					continue;
+				}
 				uint32_t p = 0;  // insert after every entry <= d
 				for (uint32_t b = 0; b < size; b += 32) {
 					const uint32_t i = b + lane;
@@ -304,6 +386,9 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(const HnswArg
 				}
 				size = newsize;
 			}
+		}
+		if (lane == 0 && a.overflow) {
+			a.overflow[qi] = x_overflow ? 1u : 0u;
 		}
 
 		// ---- results: the k best of the list (SearchKnn :1998-2011), then clean the visited bitmap for the next query
@@ -344,6 +429,7 @@ struct RangeArgs {
 	const uint32_t* level0;
 	const float* query;
 	uint32_t* visited;   // [words] one bitmap for the whole search (fresh: only the ef-search results are pre-marked, :2034-2041)
+	const uint32_t* deleted;  // MarkDelete bitmap or null: deleted neighbours are skipped (:2053-2055)
 	float* out_dist;     // [n]
 	uint32_t* out_idx;   // [n]
 	unsigned int* tail;  // entries in out_*
@@ -395,7 +481,8 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_range_expand(RangeArgs a, u
 			if (j < cnt) {
 				nid = ll[1 + j];
 				const uint32_t bit = 1u << (nid & 31);
-				fresh = !(atomicOr(&a.visited[nid >> 5], bit) & bit);  // exactly one warp of the grid wins a node
+				const bool gone = a.deleted != nullptr && (a.deleted[nid >> 5] & bit);
+				fresh = !gone && !(atomicOr(&a.visited[nid >> 5], bit) & bit);  // exactly one warp of the grid wins a node
 			}
 			const unsigned fm = __ballot_sync(0xffffffffu, fresh);
 			if (fresh) {
@@ -452,6 +539,10 @@ struct rxgpu_hnsw_device {
 	DevBuf<uint32_t> visited;
 	DevBuf<uint32_t> vlog;
 	DevBuf<unsigned int> counter;
+	DevBuf<uint32_t> deleted;        // bitmap by internal id (MarkDelete)
+	std::vector<uint32_t> h_deleted;
+	uint32_t num_deleted = 0;
+	DevBuf<uint32_t> overflow;       // [nq] per-query flag of the deleted-candidate list
 	DevBuf<uint32_t> range_visited, range_idx;  // SearchRange scratch: one bitmap, result/queue arrays of n entries
 	DevBuf<float> range_dist;
 	// staging of the host-pointer entry points (guarded by host_mtx; cudaMalloc per call would cost more than a small batch)
@@ -508,6 +599,9 @@ int rxgpu_hnsw_import(rxgpu_index* ix, const rxgpu_hnsw_graph* g) {
 	RX_CUDA(h->vlog.ensure(size_t(h->slots) * kVlogCap));
 	RX_CUDA(h->counter.ensure(1));
 	RX_CUDA(cudaMemset(h->visited.p, 0, size_t(h->slots) * h->words * 4));
+	RX_CUDA(h->deleted.ensure(h->words));
+	RX_CUDA(cudaMemset(h->deleted.p, 0, size_t(h->words) * 4));
+	h->h_deleted.assign(h->words, 0u);
 	h->index_version = ix->version;
 	if (ix->hnsw) {
 		hnswRelease(ix->hnsw);
@@ -557,6 +651,11 @@ int rxgpu_hnsw_search_knn_device(const rxgpu_index* ix, uint32_t nq, const float
 	a.out_idx = d_out_idx;
 	a.out_count = d_out_count;
 	a.stats = d_stats;
+	a.deleted = h->num_deleted ? h->deleted.p : nullptr;  // num_deleted_ == 0 -> the bare-bone search (hnswalg.h:1982)
+	if (h->num_deleted) {
+		RX_CUDA(h->overflow.ensure(nq));
+	}
+	a.overflow = h->num_deleted ? h->overflow.p : nullptr;
 	a.pitch = ix->pitch;
 	a.dim = ix->dim;
 	a.n = h->n;
@@ -569,7 +668,7 @@ int rxgpu_hnsw_search_knn_device(const rxgpu_index* ix, uint32_t nq, const float
 	a.ef = ef;
 	a.words = h->words;
 	const uint32_t dp4 = ((ix->dim + 127u) / 128u) * 32u;
-	const size_t smem = (size_t(dp4) * 16 + size_t((ef + 3u) & ~3u) * 8 + kMaxNeighbours * 8) * kHnswWarps;
+	const size_t smem = (size_t(dp4) * 16 + size_t((ef + 3u) & ~3u) * 8 + kMaxNeighbours * 8 + kHnswXCap * 8) * kHnswWarps;
 	if (smem > 200 * 1024) {
 		return fail(RXGPU_ERR_PARAMS, "rxgpu: dimension/ef combination exceeds the shared-memory budget of the HNSW kernel");
 	}
@@ -586,6 +685,16 @@ int rxgpu_hnsw_search_knn_device(const rxgpu_index* ix, uint32_t nq, const float
 	RX_CUDA(cudaStreamSynchronize(st));
 	g_stats = rxgpu_search_stats{};
 	g_stats.launches = 1;
+	if (h->num_deleted) {  // a query that met more deleted nodes than the device keeps track of cannot be trusted
+		std::vector<uint32_t> flags(nq);
+		RX_CUDA(cudaMemcpy(flags.data(), h->overflow.p, size_t(nq) * 4, cudaMemcpyDeviceToHost));
+		for (uint32_t q = 0; q < nq; ++q) {
+			if (flags[q]) {
+				return fail(RXGPU_ERR_LOGIC, "rxgpu: too many deleted nodes around query " + std::to_string(q) +
+												 " for the device search (more than 128 waiting at once); rebuild the graph or search on the CPU map");
+			}
+		}
+	}
 	return 0;
 }
 
@@ -690,6 +799,7 @@ int rxgpu_hnsw_search_range(const rxgpu_index* ix, const float* query, float rad
 	a.level0 = h->level0.p;
 	a.query = dq.p;
 	a.visited = h->range_visited.p;
+	a.deleted = h->num_deleted ? h->deleted.p : nullptr;
 	a.out_dist = h->range_dist.p;
 	a.out_idx = h->range_idx.p;
 	a.tail = h->counter.p;
@@ -767,5 +877,32 @@ int rxgpu_gather_labels_device(const rxgpu_index* ix, uint64_t n, const uint32_t
 	}
 	return 0;
 }
+
+int rxgpu_hnsw_mark_deleted(rxgpu_index* ix, uint64_t label) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	rxgpu_hnsw_device* h = ix->hnsw;
+	if (!h) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: no HNSW graph imported into this index");
+	}
+	if (h->n != ix->size || h->index_version != ix->version) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: the index changed after the HNSW graph was imported");
+	}
+	const uint32_t idx = ix->dict.find(label);
+	if (idx == LabelMap::kNotFound) {
+		return fail(RXGPU_ERR_NOT_FOUND, "markDelete: Label not found: " + std::to_string(label));  // hnswalg.h:1307
+	}
+	std::lock_guard<std::mutex> lck(h->mtx);
+	const uint32_t bit = 1u << (idx & 31);
+	if (h->h_deleted[idx >> 5] & bit) {
+		return fail(RXGPU_ERR_LOGIC, "The requested to delete element is already deleted");  // hnswalg.h:1335
+	}
+	h->h_deleted[idx >> 5] |= bit;
+	RX_CUDA(cudaMemcpy(h->deleted.p + (idx >> 5), &h->h_deleted[idx >> 5], 4, cudaMemcpyHostToDevice));
+	h->num_deleted += 1;
+	return 0;
+}
+uint64_t rxgpu_hnsw_deleted_count(const rxgpu_index* ix) { return ix && ix->hnsw ? ix->hnsw->num_deleted : 0; }
 
 }  // extern "C"

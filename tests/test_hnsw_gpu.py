@@ -203,3 +203,41 @@ def test_sharded_hnsw_two_shards_on_one_gpu():
     db, lb, _ = full.search_knn(queries, k)
     recall = np.mean([len(set(rl[i]) & set(lb[i])) / k for i in range(nq)])
     assert recall > 0.6, recall
+
+
+@pytest.mark.parametrize("metric,frac", [(rx.L2, 0.02), (rx.COS, 0.15), (rx.IP, 0.4)])
+def test_hnsw_search_with_deleted_nodes_matches_reference(metric, frac):
+    """MarkDelete leaves tombstones in the graph: the reference switches to searchBaseLayerST<bare_bone = false> -- deleted nodes are
+    traversed, never returned, and the stop rule waits for a full result list.  Same graph, same deletions, same answers."""
+    n, dim, k, ef, nq = 8000, 48, 10, 64, 120
+    ref, gpu, vecs, labels = build(metric, n, dim, 4100 + metric)
+    rng = np.random.default_rng(4200 + metric)
+    dead = labels[rng.choice(n, int(frac * n), replace=False)]
+    for lab in dead:
+        ref.mark_delete(int(lab))
+        gpu.hnsw_mark_deleted(int(lab))
+    assert gpu.hnsw_deleted_count() == len(dead)
+    queries = np.stack([prep_query(metric, q) for q in O.synth_matrix(4300 + metric, nq, dim)])
+    d, l, c, st = gpu.hnsw_search_knn(queries, k, ef, with_stats=True)
+    dr, lr, cr = ref.search_knn_batch(queries, k, ef, threads=4)
+    assert (c == cr).all()
+    dead_set = set(dead.tolist())
+    assert not (set(l[c[:, None] > np.arange(k)[None, :]].tolist()) & dead_set), "a deleted row was returned"
+    same = sum(int((l[i, :c[i]] == lr[i, :cr[i]]).all()) for i in range(nq))
+    assert same >= 0.95 * nq, f"only {same}/{nq} queries returned the reference's exact top-{k}"
+    agree = 0
+    for i in range(30):
+        dc, hops = ref.search_metrics(queries[i], ef)
+        agree += int(st[i, 0] == dc and st[i, 1] == hops)
+    assert agree >= 26, agree
+    # range search skips tombstones too
+    db, lb, _ = gpu.search_knn(queries[:1], 60)
+    radius = float((np.float64(db[0, 39]) + np.float64(db[0, 40])) / 2)
+    rd, rl, total = gpu.hnsw_search_range(queries[0], radius, ef)
+    fr, fl, ft = ref.search_range(queries[0], radius, ef)
+    assert not (set(rl.tolist()) & dead_set) and total == ft and (rl == fl).all()
+    with pytest.raises(rx.RxGpuError) as e:
+        gpu.hnsw_mark_deleted(int(dead[0]))
+    assert "already deleted" in e.value.what
+    with pytest.raises(rx.RxGpuError):
+        gpu.hnsw_mark_deleted(0xDEAD << 40)
