@@ -675,10 +675,10 @@ int rxgpu_hnsw_search_knn_device(const rxgpu_index* ix, uint32_t nq, const float
 	const unsigned grid = std::min<unsigned>(h->slots / kHnswWarps, (nq + kHnswWarps - 1) / kHnswWarps);
 	RX_CUDA(cudaMemsetAsync(h->counter.p, 0, sizeof(unsigned int), st));
 	if (ix->metric == RXGPU_L2) {
-		RX_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+		RX_CUDA(raiseSmemCeilingOnce(hnsw_search_kernel<true>, ix->device, 200 * 1024));
 		hnsw_search_kernel<true><<<grid, kHnswThreads, smem, st>>>(a);
 	} else {
-		RX_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+		RX_CUDA(raiseSmemCeilingOnce(hnsw_search_kernel<false>, ix->device, 200 * 1024));
 		hnsw_search_kernel<false><<<grid, kHnswThreads, smem, st>>>(a);
 	}
 	RX_CUDA(cudaGetLastError());
@@ -813,9 +813,9 @@ int rxgpu_hnsw_search_range(const rxgpu_index* ix, const float* query, float rad
 	const uint32_t dp4 = ((ix->dim + 127u) / 128u) * 32u;
 	const size_t smem = size_t(dp4) * 16 + size_t(kHnswWarps) * kMaxNeighbours * 8;
 	if (ix->metric == RXGPU_L2) {
-		RX_CUDA(cudaFuncSetAttribute(hnsw_range_expand<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+		RX_CUDA(raiseSmemCeilingOnce(hnsw_range_expand<true>, ix->device, 100 * 1024));
 	} else {
-		RX_CUDA(cudaFuncSetAttribute(hnsw_range_expand<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+		RX_CUDA(raiseSmemCeilingOnce(hnsw_range_expand<false>, ix->device, 100 * 1024));
 	}
 	unsigned int begin = 0, end = 0;
 	RX_CUDA(cudaMemcpyAsync(&end, h->counter.p, 4, cudaMemcpyDeviceToHost, st));

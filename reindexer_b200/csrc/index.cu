@@ -50,18 +50,18 @@ int allocDevice(rxgpu_index* ix, uint64_t capacity, float** rows, uint64_t** lab
 // ---------------------------------------------------------------------------------------------------------------- launches
 template <int QT, int RW, int CG>
 cudaError_t launchScanT(const rxgpu_index* ix, const ScanArgs& a, unsigned grid, size_t smem, cudaStream_t st) {
-	cudaError_t e;
+	if (smem > size_t(kScanSmemBudget)) {
+		return cudaErrorInvalidValue;
+	}
 	if (ix->metric == RXGPU_L2) {
 		auto kfn = knn_scan_warp<QT, RW, CG, true>;
-		e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-		if (e != cudaSuccess) {
+		if (const cudaError_t e = raiseSmemCeilingOnce(kfn, ix->device, kScanSmemBudget); e != cudaSuccess) {
 			return e;
 		}
 		kfn<<<grid, kScanThreads, smem, st>>>(a);
 	} else {
 		auto kfn = knn_scan_warp<QT, RW, CG, false>;
-		e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-		if (e != cudaSuccess) {
+		if (const cudaError_t e = raiseSmemCeilingOnce(kfn, ix->device, kScanSmemBudget); e != cudaSuccess) {
 			return e;
 		}
 		kfn<<<grid, kScanThreads, smem, st>>>(a);
@@ -342,20 +342,20 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 		}
 		const size_t smem = smemOf(stages);
 		if (four) {
-			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q4<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q4<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q4<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+			RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_q4<1>, ix->device, int(kTcSmemLimit)));
+			RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_q4<2>, ix->device, int(kTcSmemLimit)));
+			RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_q4<4>, ix->device, int(kTcSmemLimit)));
 		}
 		if (wide) {
-			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_w<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_w<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_w<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+			RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_w<1>, ix->device, int(kTcSmemLimit)));
+			RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_w<2>, ix->device, int(kTcSmemLimit)));
+			RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_w<4>, ix->device, int(kTcSmemLimit)));
 		}
-		RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q2, cudaFuncAttributeMaxDynamicSharedMemorySize, int(t2_smem_bytes(pairMma ? stages : 2))));
+		RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_q2, ix->device, int(kTcSmemLimit)));
 		if (!wide && !pairMma && !four) {
-			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-			RX_CUDA(cudaFuncSetAttribute(knn_tc_filter_q<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+			RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_q<1>, ix->device, int(kTcSmemLimit)));
+			RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_q<2>, ix->device, int(kTcSmemLimit)));
+			RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_q<4>, ix->device, int(kTcSmemLimit)));
 		}
 		// measured on B200 (10M x 768, 1024 queries, same box, two rounds): CTA pairs 50.3 / 50.8 k queries/s, clusters of four
 		// 51.8 / 52.0 k, single CTAs ~40 k -- the kernel runs under the board's power cap, and a cluster of four reads every row tile
@@ -513,8 +513,8 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 		return rc;
 	}
 	const size_t smem = tc_smem_bytes(nqb, kchunks);
-	RX_CUDA(cudaFuncSetAttribute(knn_tc_filter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-	RX_CUDA(cudaFuncSetAttribute(knn_tc_filter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+	RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter<1>, ix->device, int(kTcSmemLimit)));
+	RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter<2>, ix->device, int(kTcSmemLimit)));
 	unsigned grid = std::min<unsigned>(unsigned(ix->sm_count), ntiles * cluster);
 	grid -= grid % cluster;
 	for (uint32_t b = 0; b < nblocks; b += cluster) {
@@ -578,11 +578,11 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 	const size_t rsmem = size_t((ix->dim + 127) / 128) * 512 + size_t(kScanWarps) * (k1 + kCandBuf) * 8;
 	const float* norms = ix->metric == RXGPU_COS ? ix->d_norms : nullptr;
 	if (ix->metric == RXGPU_L2) {
-		RX_CUDA(cudaFuncSetAttribute(knn_rerank<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rsmem)));
+		RX_CUDA(raiseSmemCeilingOnce(knn_rerank<true>, ix->device, kScanSmemBudget));
 		knn_rerank<true><<<nq, kScanThreads, rsmem, st>>>(ix->d_rows, ix->pitch, ix->dim, norms, d_queries, ws.d_cand_rows.p,
 														   ws.d_cand_count.p, kTcCandCap, k1, ws.d_lists.p);
 	} else {
-		RX_CUDA(cudaFuncSetAttribute(knn_rerank<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rsmem)));
+		RX_CUDA(raiseSmemCeilingOnce(knn_rerank<false>, ix->device, kScanSmemBudget));
 		knn_rerank<false><<<nq, kScanThreads, rsmem, st>>>(ix->d_rows, ix->pitch, ix->dim, norms, d_queries, ws.d_cand_rows.p,
 															ws.d_cand_count.p, kTcCandCap, k1, ws.d_lists.p);
 	}
@@ -1518,11 +1518,11 @@ int rxgpu_ivf_search_knn(const rxgpu_index* ix, uint32_t nq, const float* querie
 	RX_CUDA(h->d_count.ensure(nq));
 	RX_CUDA(cudaMemcpyAsync(h->d_q.p, queries, size_t(nq) * ix->dim * 4, cudaMemcpyHostToDevice, st));
 	if (ix->metric == RXGPU_L2) {
-		RX_CUDA(cudaFuncSetAttribute(ivf_coarse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(coarseSmem)));
+		RX_CUDA(raiseSmemCeilingOnce(ivf_coarse_kernel<true>, ix->device, 200 * 1024));
 		ivf_coarse_kernel<true><<<nq, kScanThreads, coarseSmem, st>>>(h->centroids.p, ix->pitch, ix->dim, h->nlist, h->d_q.p, nq, nprobe,
 																	   h->list_begin.p, nullptr, h->d_work.p);
 	} else {
-		RX_CUDA(cudaFuncSetAttribute(ivf_coarse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(coarseSmem)));
+		RX_CUDA(raiseSmemCeilingOnce(ivf_coarse_kernel<false>, ix->device, 200 * 1024));
 		ivf_coarse_kernel<false><<<nq, kScanThreads, coarseSmem, st>>>(h->centroids.p, ix->pitch, ix->dim, h->nlist, h->d_q.p, nq, nprobe,
 																		h->list_begin.p, ix->metric == RXGPU_COS ? h->cnorm.p : nullptr, h->d_work.p);
 	}
@@ -1621,11 +1621,11 @@ int rxgpu_ivf_search_range(const rxgpu_index* ix, const float* query, float radi
 	RX_CUDA(h->d_range_count.ensure(1));
 	RX_CUDA(cudaMemcpyAsync(h->d_q.p, query, size_t(ix->dim) * 4, cudaMemcpyHostToDevice, st));
 	if (ix->metric == RXGPU_L2) {
-		RX_CUDA(cudaFuncSetAttribute(ivf_coarse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(coarseSmem)));
+		RX_CUDA(raiseSmemCeilingOnce(ivf_coarse_kernel<true>, ix->device, 200 * 1024));
 		ivf_coarse_kernel<true><<<1, kScanThreads, coarseSmem, st>>>(h->centroids.p, ix->pitch, ix->dim, h->nlist, h->d_q.p, 1, nprobe,
 																	  h->list_begin.p, nullptr, h->d_work.p);
 	} else {
-		RX_CUDA(cudaFuncSetAttribute(ivf_coarse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(coarseSmem)));
+		RX_CUDA(raiseSmemCeilingOnce(ivf_coarse_kernel<false>, ix->device, 200 * 1024));
 		ivf_coarse_kernel<false><<<1, kScanThreads, coarseSmem, st>>>(h->centroids.p, ix->pitch, ix->dim, h->nlist, h->d_q.p, 1, nprobe,
 																	   h->list_begin.p, ix->metric == RXGPU_COS ? h->cnorm.p : nullptr,
 																	   h->d_work.p);

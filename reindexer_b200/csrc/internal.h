@@ -96,6 +96,27 @@ struct PinBuf {
 	}
 };
 
+// The dynamic shared-memory ceiling of a kernel is a per-device FUNCTION attribute: searches run concurrently from many threads
+// (the reference's read-side concurrency), so it is raised once per (kernel, device) to the budget every caller stays within --
+// never per launch, where a thread asking for less would lower it under another thread's launch (cudaErrorInvalidValue).
+constexpr int kScanSmemBudget = 100 * 1024;
+template <typename Kernel>
+inline cudaError_t raiseSmemCeilingOnce(Kernel kfn, int device, int bytes) {
+	static std::mutex mtx;
+	static bool done[64] = {};
+	std::lock_guard<std::mutex> lck(mtx);
+	if (device < 0 || device >= 64 || !done[device]) {
+		const cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+		if (e != cudaSuccess) {
+			return e;
+		}
+		if (device >= 0 && device < 64) {
+			done[device] = true;
+		}
+	}
+	return cudaSuccess;
+}
+
 // per-call scratch: searches are re-entrant, each takes one workspace from the pool
 struct Workspace {
 	cudaStream_t stream = nullptr;
