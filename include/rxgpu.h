@@ -164,7 +164,7 @@ int rxgpu_hnsw_search_knn_device(const rxgpu_index*, uint32_t nq, const float* d
 
 /* HierarchicalNSWImpl::MarkDelete (hnswalg.h:1303-1335): the row stays in the graph as a tombstone -- searches traverse it but never
  * return it (searchBaseLayerST<bare_bone = false>, :829-975).  Errors: label unknown (errNotFound), already deleted (errLogic).
- * A search that meets more than 128 deleted nodes waiting for expansion at once fails with errLogic (rebuild the graph). */
+ * A search that meets more than 4096 deleted nodes waiting for expansion at once fails with errLogic (rebuild the graph). */
 int rxgpu_hnsw_mark_deleted(rxgpu_index*, uint64_t label);
 uint64_t rxgpu_hnsw_deleted_count(const rxgpu_index*); /* DeletedCountUnsafe */
 /* labels of n shard-local internal indices (device pointers; enqueued on `stream`): the HNSW device search returns indices, the

@@ -35,7 +35,7 @@ constexpr uint32_t kExpanded = 0x80000000u;
 constexpr uint32_t kMaxEf = 1024;
 constexpr uint32_t kVlogCap = 1u << 15;
 constexpr int kMaxNeighbours = 64;  // maxM0 = 2*M; M <= 32 on the device path
-constexpr uint32_t kHnswXCap = 128;  // deleted nodes waiting for expansion (per query), see the search kernel
+constexpr uint32_t kHnswXCap = 4096;  // deleted nodes waiting for expansion (per query, in HBM), see the search kernel
 
 struct HnswArgs {
 	const float* rows;
@@ -54,6 +54,8 @@ struct HnswArgs {
 	uint32_t* stats;    // [nq][2] or null
 	const uint32_t* deleted;  // bitmap by internal id (MarkDelete, hnswalg.h:1303-1335) or null: the bare-bone search
 	uint32_t* overflow;       // [nq] set when more than kHnswXCap deleted nodes were waiting at once (result not trustworthy)
+	float* x_dist;            // [slots][kHnswXCap] deleted candidates of the slot's current query, ascending (only with `deleted`)
+	uint32_t* x_id;
 	uint32_t pitch, dim, n, l0_stride, up_stride;
 	int maxlevel;
 	uint32_t enterpoint;
@@ -140,19 +142,21 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(const HnswArg
 	const uint32_t dp4 = nch * 32u;
 	// per-warp shared memory: query | list dist[ef] | list id[ef] | neighbour ids[64] | neighbour dists[64]
 	const uint32_t efp = (a.ef + 3u) & ~3u;  // keeps every warp's region 16-byte aligned
-	const size_t per_warp = size_t(dp4) * 16 + size_t(efp) * 8 + kMaxNeighbours * 8 + kHnswXCap * 8;
+	const size_t per_warp = size_t(dp4) * 16 + size_t(efp) * 8 + kMaxNeighbours * 8;
 	unsigned char* base = smem_raw + per_warp * warp;
 	float4* sq4 = reinterpret_cast<float4*>(base);
 	float* l_dist = reinterpret_cast<float*>(base + size_t(dp4) * 16);
 	uint32_t* l_id = reinterpret_cast<uint32_t*>(l_dist + efp);
 	uint32_t* s_ids = l_id + efp;
 	float* s_d = reinterpret_cast<float*>(s_ids + kMaxNeighbours);
-	float* x_dist = s_d + kMaxNeighbours;  // deleted candidates (in candidate_set, never in top_candidates), ascending
-	uint32_t* x_id = reinterpret_cast<uint32_t*>(x_dist + kHnswXCap);
 
 	const uint32_t slot = blockIdx.x * kHnswWarps + warp;
 	uint32_t* visited = a.visited + size_t(slot) * a.words;
 	uint32_t* vlog = a.vlog + size_t(slot) * kVlogCap;
+	// deleted candidates (in candidate_set, never in top_candidates): a sorted list per slot in HBM, touched only when the graph
+	// holds tombstones
+	float* x_dist = a.x_dist ? a.x_dist + size_t(slot) * kHnswXCap : nullptr;
+	uint32_t* x_id = a.x_id ? a.x_id + size_t(slot) * kHnswXCap : nullptr;
 
 	for (;;) {
 		uint32_t qi = 0;
@@ -543,6 +547,8 @@ struct rxgpu_hnsw_device {
 	std::vector<uint32_t> h_deleted;
 	uint32_t num_deleted = 0;
 	DevBuf<uint32_t> overflow;       // [nq] per-query flag of the deleted-candidate list
+	DevBuf<float> x_dist;            // [slots][kHnswXCap], allocated with the first tombstone
+	DevBuf<uint32_t> x_id;
 	DevBuf<uint32_t> range_visited, range_idx;  // SearchRange scratch: one bitmap, result/queue arrays of n entries
 	DevBuf<float> range_dist;
 	// staging of the host-pointer entry points (guarded by host_mtx; cudaMalloc per call would cost more than a small batch)
@@ -656,6 +662,12 @@ int rxgpu_hnsw_search_knn_device(const rxgpu_index* ix, uint32_t nq, const float
 		RX_CUDA(h->overflow.ensure(nq));
 	}
 	a.overflow = h->num_deleted ? h->overflow.p : nullptr;
+	if (h->num_deleted) {
+		RX_CUDA(h->x_dist.ensure(size_t(h->slots) * kHnswXCap));
+		RX_CUDA(h->x_id.ensure(size_t(h->slots) * kHnswXCap));
+	}
+	a.x_dist = h->num_deleted ? h->x_dist.p : nullptr;
+	a.x_id = h->num_deleted ? h->x_id.p : nullptr;
 	a.pitch = ix->pitch;
 	a.dim = ix->dim;
 	a.n = h->n;
@@ -668,7 +680,7 @@ int rxgpu_hnsw_search_knn_device(const rxgpu_index* ix, uint32_t nq, const float
 	a.ef = ef;
 	a.words = h->words;
 	const uint32_t dp4 = ((ix->dim + 127u) / 128u) * 32u;
-	const size_t smem = (size_t(dp4) * 16 + size_t((ef + 3u) & ~3u) * 8 + kMaxNeighbours * 8 + kHnswXCap * 8) * kHnswWarps;
+	const size_t smem = (size_t(dp4) * 16 + size_t((ef + 3u) & ~3u) * 8 + kMaxNeighbours * 8) * kHnswWarps;
 	if (smem > 200 * 1024) {
 		return fail(RXGPU_ERR_PARAMS, "rxgpu: dimension/ef combination exceeds the shared-memory budget of the HNSW kernel");
 	}
@@ -691,7 +703,7 @@ int rxgpu_hnsw_search_knn_device(const rxgpu_index* ix, uint32_t nq, const float
 		for (uint32_t q = 0; q < nq; ++q) {
 			if (flags[q]) {
 				return fail(RXGPU_ERR_LOGIC, "rxgpu: too many deleted nodes around query " + std::to_string(q) +
-												 " for the device search (more than 128 waiting at once); rebuild the graph or search on the CPU map");
+												 " for the device search (more than 4096 waiting at once); rebuild the graph or search on the CPU map");
 			}
 		}
 	}

@@ -100,21 +100,24 @@ struct PinBuf {
 // (the reference's read-side concurrency), so it is raised once per (kernel, device) to the budget every caller stays within --
 // never per launch, where a thread asking for less would lower it under another thread's launch (cudaErrorInvalidValue).
 constexpr int kScanSmemBudget = 100 * 1024;
-template <typename Kernel>
-inline cudaError_t raiseSmemCeilingOnce(Kernel kfn, int device, int bytes) {
+inline cudaError_t raiseSmemCeilingOnceImpl(const void* fn, int device, int bytes) {
 	static std::mutex mtx;
-	static bool done[64] = {};
+	static std::vector<std::pair<const void*, int>> done;  // (kernel entry point, device); a handful of entries
 	std::lock_guard<std::mutex> lck(mtx);
-	if (device < 0 || device >= 64 || !done[device]) {
-		const cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-		if (e != cudaSuccess) {
-			return e;
-		}
-		if (device >= 0 && device < 64) {
-			done[device] = true;
+	for (const auto& d : done) {
+		if (d.first == fn && d.second == device) {
+			return cudaSuccess;
 		}
 	}
-	return cudaSuccess;
+	const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+	if (e == cudaSuccess) {
+		done.emplace_back(fn, device);
+	}
+	return e;
+}
+template <typename Kernel>
+inline cudaError_t raiseSmemCeilingOnce(Kernel kfn, int device, int bytes) {  // keyed by the entry point, not by its type
+	return raiseSmemCeilingOnceImpl(reinterpret_cast<const void*>(kfn), device, bytes);
 }
 
 // per-call scratch: searches are re-entrant, each takes one workspace from the pool
