@@ -181,7 +181,19 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- librxgpu has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # the contract is ONE JSON line on stdout: NCCL announces its version on stdout when the first communicator is created, so
+        # stdout points at stderr while the process group comes up
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     rows = args.rows or ROWS_FULL
     free_b, _ = torch.cuda.mem_get_info()
     if rows * DIM * 4 * 1.05 > free_b:
