@@ -312,39 +312,53 @@ __global__ void __launch_bounds__(kFtThreads) ft_hist(uint16_t* score, const uin
 //   A(sc) = number of docs with score > sc;  minScore = the smallest sc >= 1 with A(sc) < maxMerged (sc = 65535 always qualifies);
 //   minScoreDocs = maxMerged - A(minScore).   thr[0] = minScore, thr[1] = minScoreDocs.  One block of 1024 threads, 64 bins each.
 __global__ void __launch_bounds__(1024) ft_pick_threshold(const unsigned long long* hist, uint32_t max_merged, uint32_t* thr) {
-	__shared__ unsigned long long s_tot[1024];
+	// thread r owns the 64 scores [hi - 63, hi], hi = 65535 - 64 r (thread 0 the highest), cached in registers: one read of the
+	// histogram; A(hi) = docs in the bins of the threads before r = an exclusive prefix sum over r
+	__shared__ unsigned long long s_scan[1024];
 	__shared__ uint32_t s_min;
-	const uint32_t t = threadIdx.x;
+	const uint32_t r = threadIdx.x;
+	const uint32_t hi = 65535u - 64u * r;
+	uint32_t bins[64];  // bins[i] = hist[hi - i]; a bin holds at most total_docs < 2^32 documents
 	unsigned long long mine = 0;
-	for (uint32_t i = 0; i < 64; ++i) {
-		mine += hist[t * 64 + i];
+#pragma unroll
+	for (int i = 0; i < 64; ++i) {
+		bins[i] = uint32_t(hist[hi - i]);
+		mine += bins[i];
 	}
-	s_tot[t] = mine;
-	if (t == 0) {
+	s_scan[r] = mine;
+	if (r == 0) {
 		s_min = 65535;
 	}
 	__syncthreads();
-	unsigned long long above = 0;  // docs in the bins of all higher threads
-	for (uint32_t u = t + 1; u < 1024; ++u) {
-		above += s_tot[u];
+	for (uint32_t off = 1; off < 1024; off <<= 1) {  // inclusive Hillis-Steele scan over the thread totals
+		const unsigned long long add = r >= off ? s_scan[r - off] : 0ull;
+		__syncthreads();
+		s_scan[r] += add;
+		__syncthreads();
 	}
+	const unsigned long long above = s_scan[r] - mine;  // docs with score > hi
 	unsigned long long a = above;
 	uint32_t local = 0xFFFFFFFFu;
-	for (int sc = int(t * 64 + 63); sc >= int(t * 64); --sc) {
+#pragma unroll
+	for (int i = 0; i < 64; ++i) {
+		const uint32_t sc = hi - i;
 		if (sc >= 1 && a < max_merged) {
-			local = uint32_t(sc);
+			local = sc;
 		}
-		a += hist[sc];
+		a += bins[i];
 	}
 	if (local != 0xFFFFFFFFu) {
 		atomicMin(&s_min, local);
 	}
 	__syncthreads();
 	const uint32_t ms = s_min;
-	if (ms / 64 == t) {
+	if ((65535u - ms) / 64u == r) {
 		a = above;
-		for (int sc = int(t * 64 + 63); sc > int(ms); --sc) {
-			a += hist[sc];
+#pragma unroll
+		for (int i = 0; i < 64; ++i) {
+			if (hi - i > ms) {
+				a += bins[i];
+			}
 		}
 		thr[0] = ms;
 		thr[1] = uint32_t(max_merged - a);
