@@ -52,3 +52,16 @@ def test_product_package_never_imports_oracle():
                 body = open(os.path.join(dirpath, f)).read()
                 code = "\n".join(l for l in body.splitlines() if not l.strip().startswith(("//", "#", "*", "/*", '"""')))
                 assert "import oracle" not in code and "from oracle" not in code and "liboracle" not in code, os.path.join(dirpath, f)
+
+
+def test_header_is_plain_c():
+    """the boundary is a C ABI: include/rxgpu.h must compile as C99 with no C++ or torch types in it"""
+    import subprocess
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as tmp:
+        src = os.path.join(tmp, "hdr_check.c")
+        with open(src, "w") as f:
+            f.write('#include "rxgpu.h"\nint main(void) { rxgpu_search_stats s; (void)s; return 0; }\n')
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                               "-I", os.path.join(ROOT, "include"), src])
