@@ -124,6 +124,11 @@ def ref_knn_lib():
         lib.ref_hnsw_search_knn.restype = C.c_int64
         lib.ref_hnsw_search_knn.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, C.c_size_t, C.c_size_t, _f32p, _u64p]
         lib.ref_hnsw_mark_delete.argtypes = [C.c_void_p, C.c_uint64]
+        lib.ref_hnsw_stream_begin.restype = C.c_void_p
+        lib.ref_hnsw_stream_begin.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, C.c_size_t]
+        lib.ref_hnsw_stream_next.restype = C.c_int64
+        lib.ref_hnsw_stream_next.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, _f32p, _u64p, C.POINTER(C.c_int)]
+        lib.ref_hnsw_stream_end.argtypes = [C.c_void_p]
         lib.ref_hnsw_search_range.restype = C.c_int64
         lib.ref_hnsw_search_range.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, C.c_float, C.c_size_t, C.c_size_t, _f32p, _u64p]
         lib.ref_hnsw_search_knn_batch.argtypes = [C.c_void_p, C.c_uint32, _f32p, _f32p, C.c_size_t, C.c_size_t, C.c_int, _f32p,
@@ -368,6 +373,24 @@ class RefHnsw:
                                          _p(l, _u64p))
         assert n >= 0, self.lib.ref_last_error().decode()
         return d[:n].copy(), l[:n].copy()
+
+    def stream(self, q, batch_size, ef=0, max_batches=10**9):
+        """BeginStreamingSearch / ContinueStreamingSearch (hnswalg.h:1864-1975): yields (dist, label) batches, best first inside a batch"""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        s = self.lib.ref_hnsw_stream_begin(self.h, _p(q, _f32p), 0, 0.0, ef)
+        assert s, self.lib.ref_last_error().decode()
+        try:
+            for _ in range(max_batches):
+                d = np.empty(batch_size, np.float32)
+                l = np.empty(batch_size, np.uint64)
+                ex = C.c_int(0)
+                n = self.lib.ref_hnsw_stream_next(self.h, s, batch_size, _p(d, _f32p), _p(l, _u64p), C.byref(ex))
+                assert n >= 0, self.lib.ref_last_error().decode()
+                yield d[:n].copy(), l[:n].copy()
+                if ex.value:
+                    break
+        finally:
+            self.lib.ref_hnsw_stream_end(s)
 
     def mark_delete(self, label):
         rc = self.lib.ref_hnsw_mark_delete(self.h, int(label))

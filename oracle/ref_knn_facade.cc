@@ -277,6 +277,41 @@ int64_t ref_hnsw_search_knn(const void* hv, const float* query, int has_norm, fl
 	});
 	return n;
 }
+// Streaming search (hnswalg.h:1864-1975): BeginStreamingSearch once, then ContinueStreamingSearch(batchSize) until exhausted.
+// The session borrows the graph: destroy it before the graph.
+struct StreamHandle {
+	hnswlib::StreamingSearchSession session;
+	std::vector<float> query;  // the session keeps a pointer into the caller's query for non-quantised graphs: keep it alive
+};
+void* ref_hnsw_stream_begin(const void* hv, const float* query, int has_norm, float qnorm, size_t ef) {
+	auto* h = const_cast<HnswHandle*>(static_cast<const HnswHandle*>(hv));
+	StreamHandle* out = nullptr;
+	guarded([&] {
+		withHnsw(h, [&](auto& g) {
+			std::vector<float> q(query, query + h->dim);
+			const float* qp = q.data();  // std::vector's buffer survives the move below
+			auto sess = g.BeginStreamingSearch(qp, has_norm ? std::optional<float>(qnorm) : std::nullopt, hnswlib::StreamingSearchOptions{ef});
+			out = new StreamHandle{std::move(sess), std::move(q)};
+		});
+	});
+	return out;
+}
+// returns the number of results of this batch (best first), -1 on error; *exhausted = 1 when the search has nothing more to give
+int64_t ref_hnsw_stream_next(const void* hv, void* sv, size_t batchSize, float* dists, uint64_t* labels, int* exhausted) {
+	auto* h = const_cast<HnswHandle*>(static_cast<const HnswHandle*>(hv));
+	auto* s = static_cast<StreamHandle*>(sv);
+	int64_t n = -1;
+	guarded([&] {
+		withHnsw(h, [&](auto& g) {
+			auto batch = g.ContinueStreamingSearch(s->session, batchSize);
+			*exhausted = batch.exhausted ? 1 : 0;
+			n = int64_t(drain(batch.results, batchSize, dists, labels));
+		});
+	});
+	return n;
+}
+void ref_hnsw_stream_end(void* sv) { delete static_cast<StreamHandle*>(sv); }
+
 int ref_hnsw_mark_delete(void* hv, uint64_t label) {
 	auto* h = static_cast<HnswHandle*>(hv);
 	return guarded([&] { withHnsw(h, [&](auto& g) { g.MarkDelete(label); }); });

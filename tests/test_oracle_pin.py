@@ -153,3 +153,25 @@ def test_reference_ivf_oracle_is_self_consistent():
             dr, lr = ref.search(q, k, nprobe)
             assert (st["labels"][rows[order]] == lr).all()
             assert np.allclose(dd[order], dr if metric == O.L2 else -dr, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.skipif(not O.ref_knn_available(), reason="needs oracle/_ref (reference HNSW build)")
+def test_reference_streaming_search_contract():
+    """groundwork for the device streaming search: the contract of the reference's Begin/ContinueStreamingSearch, pinned
+    on its own code -- batches never repeat a label, every batch is sorted, the stream ends exhausted, and on a connected graph it
+    eventually yields every row; the first batch is close to (not necessarily equal to) the k best of SearchKnn"""
+    n, dim = 3000, 24
+    vecs, labels = O.synth_matrix(1501, n, dim), O.row_labels(n)
+    ref = O.RefHnsw(O.L2, dim, n, M=16, ef_construction=200, seed=100, multithread=False)
+    ref.add_batch(labels, vecs)
+    q = O.synth_matrix(1502, 1, dim)[0]
+    seen, batches = [], 0
+    for d, l in ref.stream(q, 64, ef=100):
+        assert (np.diff(d) >= 0).all()
+        seen += l.tolist()
+        batches += 1
+    assert len(seen) == len(set(seen)), "a label was streamed twice"
+    assert len(seen) >= 0.99 * n and batches >= n // 64
+    dk, lk = ref.search_knn(q, 10, 100)
+    first = next(iter(ref.stream(q, 10, ef=100)))[1]
+    assert len(set(first.tolist()) & set(lk.tolist())) >= 8
