@@ -124,6 +124,14 @@ def ref_knn_lib():
         lib.ref_hnsw_search_knn.restype = C.c_int64
         lib.ref_hnsw_search_knn.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, C.c_size_t, C.c_size_t, _f32p, _u64p]
         lib.ref_hnsw_mark_delete.argtypes = [C.c_void_p, C.c_uint64]
+        lib.ref_hnsw_quantize.restype = C.c_void_p
+        lib.ref_hnsw_quantize.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_size_t]
+        lib.ref_hnsw_q_destroy.argtypes = [C.c_void_p]
+        lib.ref_hnsw_q_params.argtypes = [C.c_void_p, _f32p]
+        lib.ref_hnsw_q_export.argtypes = [C.c_void_p, C.c_void_p, _f32p]
+        lib.ref_hnsw_q_prepare_query.argtypes = [C.c_void_p, _f32p, C.c_void_p, _f32p]
+        lib.ref_hnsw_q_search_knn.restype = C.c_int64
+        lib.ref_hnsw_q_search_knn.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, C.c_size_t, C.c_size_t, _f32p, _u64p]
         lib.ref_hnsw_stream_begin.restype = C.c_void_p
         lib.ref_hnsw_stream_begin.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, C.c_size_t]
         lib.ref_hnsw_stream_next.restype = C.c_int64
@@ -374,6 +382,10 @@ class RefHnsw:
         assert n >= 0, self.lib.ref_last_error().decode()
         return d[:n].copy(), l[:n].copy()
 
+    def quantize(self, quantile=None, sample_size=0):
+        """the reference's SQ8 copy of this graph (HierarchicalNSW::Impl::Quantize) -> RefHnswSq8"""
+        return RefHnswSq8(self, quantile, sample_size)
+
     def stream(self, q, batch_size, ef=0, max_batches=10**9):
         """BeginStreamingSearch / ContinueStreamingSearch (hnswalg.h:1864-1975): yields (dist, label) batches, best first inside a batch"""
         q = np.ascontiguousarray(q, dtype=np.float32)
@@ -441,6 +453,47 @@ class RefHnsw:
         assert rc == 0, self.lib.ref_last_error().decode()
         return dict(n=n, maxlevel=maxlevel, enterpoint=ep, M=M, maxM0=m0, level0=level0, levels=levels, upper_offsets=offs,
                     upper=upper[:upper_slots], labels=labels, vectors=vecs)
+
+
+class RefHnswSq8:
+    """HierarchicalNSWImpl<uint8_t> built by the reference from a float graph (scalar_quantization/quantizer.h, hnswlib.h:192-197)"""
+
+    def __init__(self, graph, quantile, sample_size):
+        self.lib, self.dim, self.graph = graph.lib, graph.dim, graph
+        self.h = self.lib.ref_hnsw_quantize(graph.h, int(quantile is not None), float(quantile or 0.0), sample_size)
+        assert self.h, self.lib.ref_last_error().decode()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.ref_hnsw_q_destroy(self.h)
+            self.h = None
+
+    def params(self):
+        p = np.zeros(5, np.float32)
+        assert self.lib.ref_hnsw_q_params(self.h, _p(p, _f32p)) == 0
+        return dict(minQ=p[0], maxQ=p[1], alpha=p[2], alpha_2=p[3], delta=p[4])
+
+    def export(self):
+        n = self.graph.size()
+        codes = np.zeros((n, self.dim), np.uint8)
+        offs = np.zeros(n, np.float32)
+        assert self.lib.ref_hnsw_q_export(self.h, codes.ctypes.data, _p(offs, _f32p)) == 0
+        return codes, offs
+
+    def prepare_query(self, q):
+        q = np.ascontiguousarray(q, np.float32)
+        codes = np.zeros(self.dim, np.uint8)
+        off = np.zeros(1, np.float32)
+        assert self.lib.ref_hnsw_q_prepare_query(self.h, _p(q, _f32p), codes.ctypes.data, _p(off, _f32p)) == 0
+        return codes, float(off[0])
+
+    def search_knn(self, q, k, ef=0):
+        q = np.ascontiguousarray(q, np.float32)
+        d = np.empty(max(k, 1), np.float32)
+        l = np.empty(max(k, 1), np.uint64)
+        n = self.lib.ref_hnsw_q_search_knn(self.h, _p(q, _f32p), 0, 0.0, k, ef, _p(d, _f32p), _p(l, _u64p))
+        assert n >= 0, self.lib.ref_last_error().decode()
+        return d[:n].copy(), l[:n].copy()
 
 
 # ---- IVF: the reference's vendored FAISS (oracle/_ref/liboracle_ref_ivf.so) ----------------------------------------------------

@@ -277,6 +277,80 @@ int64_t ref_hnsw_search_knn(const void* hv, const float* query, int has_norm, fl
 	});
 	return n;
 }
+// ---- SQ8: the reference's scalar quantisation of an HNSW graph (groundwork for SURVEY §8 f2) ------------------------------------
+// HierarchicalNSW::Impl::Quantize (hnsw.cc:133-139) builds HierarchicalNSWImpl<uint8_t> from the float graph: codes
+// u8 = clamp((x - minQ) / alpha, 0, 255) (scalar_quantization/quantizer.h:64-66), one corrective offset per vector (:93-125),
+// distances alpha^2 * int_dist(u8, u8) + offset_l + offset_r (hnswlib.h:192-197).  Single-threaded graphs only.
+using HnswQ = hnswlib::HierarchicalNSWImpl<uint8_t, hnswlib::Synchronization::None>;
+struct QuantHandle {
+	std::unique_ptr<HnswQ> q;
+	size_t dim = 0;
+};
+void* ref_hnsw_quantize(const void* hv, int has_quantile, float quantile, size_t sample_size) {
+	auto* h = static_cast<const HnswHandle*>(hv);
+	QuantHandle* out = nullptr;
+	guarded([&] {
+		if (!h->st) {
+			throw std::runtime_error("ref_hnsw_quantize: single-threaded graph expected");
+		}
+		hnswlib::QuantizationConfig cfg;
+		if (has_quantile) {
+			cfg.quantile = quantile;
+		}
+		if (sample_size) {
+			cfg.sampleSize = sample_size;
+		}
+		auto qh = std::make_unique<QuantHandle>();
+		qh->dim = h->dim;
+		qh->q = std::make_unique<HnswQ>(*h->st, h->st->MaxElements(), std::optional(cfg));
+		out = qh.release();
+	});
+	return out;
+}
+void ref_hnsw_q_destroy(void* qv) { delete static_cast<QuantHandle*>(qv); }
+// params: [minQ, maxQ, alpha, alpha_2, delta]
+int ref_hnsw_q_params(const void* qv, float* params) {
+	auto* q = static_cast<const QuantHandle*>(qv);
+	return guarded([&] {
+		const auto& p = q->q->quantizer_->Params();
+		params[0] = p.minQ;
+		params[1] = p.maxQ;
+		params[2] = p.alpha;
+		params[3] = p.alpha_2;
+		params[4] = p.delta;
+	});
+}
+// codes [n][dim] u8 and corrective offsets [n] by internal id
+int ref_hnsw_q_export(const void* qv, uint8_t* codes, float* offsets) {
+	auto* q = static_cast<const QuantHandle*>(qv);
+	return guarded([&] {
+		const size_t n = q->q->CurrentElementCount();
+		for (size_t i = 0; i < n; ++i) {
+			std::memcpy(codes + i * q->dim, q->q->getDataByInternalId(hnswlib::tableint(i)), q->dim);
+			offsets[i] = q->q->fstdistfunc_.Sq8CorrectiveOffsets()[i];
+		}
+	});
+}
+// the quantised query exactly as search() prepares it (prepareData, hnswalg.h:510-535): codes [dim] + its corrective offset
+int ref_hnsw_q_prepare_query(const void* qv, const float* query, uint8_t* codes, float* offset) {
+	auto* q = static_cast<const QuantHandle*>(qv);
+	return guarded([&] {
+		auto holder = q->q->prepareData(query, 1.f);
+		std::memcpy(codes, holder.get(), q->dim);
+		std::memcpy(offset, holder.get() + q->dim, sizeof(float));
+	});
+}
+int64_t ref_hnsw_q_search_knn(const void* qv, const float* query, int has_norm, float qnorm, size_t k, size_t ef, float* dists,
+							  uint64_t* labels) {
+	auto* q = static_cast<const QuantHandle*>(qv);
+	int64_t n = -1;
+	guarded([&] {
+		auto res = q->q->SearchKnn(query, has_norm ? std::optional<float>(qnorm) : std::nullopt, k, ef);
+		n = int64_t(drain(res, k, dists, labels));
+	});
+	return n;
+}
+
 // Streaming search (hnswalg.h:1864-1975): BeginStreamingSearch once, then ContinueStreamingSearch(batchSize) until exhausted.
 // The session borrows the graph: destroy it before the graph.
 struct StreamHandle {

@@ -175,3 +175,37 @@ def test_reference_streaming_search_contract():
     dk, lk = ref.search_knn(q, 10, 100)
     first = next(iter(ref.stream(q, 10, ef=100)))[1]
     assert len(set(first.tolist()) & set(lk.tolist())) >= 8
+
+
+@pytest.mark.skipif(not O.ref_knn_available(), reason="needs oracle/_ref (reference HNSW build)")
+@pytest.mark.parametrize("metric", [O.L2, O.IP])
+def test_reference_sq8_distance_formula(metric):
+    """groundwork for SQ8 on the device: the reference's quantised distance is integer arithmetic plus stored
+    corrections -- alpha^2 * int_dist(u8, u8) + offset(query) + offset(row) (hnswlib.h:192-197, quantizer.h:93-125) -- so a dp4a
+    kernel can reproduce it exactly.  Pinned on the reference's own quantised graph: codes, offsets and the quantised query are
+    read back through the facade, the formula is restated here, and it must give the distances SearchKnn returns."""
+    n, dim, k = 3000, 32, 10
+    vecs, labels = O.synth_matrix(1601, n, dim), O.row_labels(n)
+    g = O.RefHnsw(metric, dim, n, M=16, ef_construction=200, seed=100, multithread=False)
+    g.add_batch(labels, vecs)
+    sq = g.quantize()
+    p = sq.params()
+    codes, offs = sq.export()
+    assert codes.shape == (n, dim) and abs(p["alpha"] - (p["maxQ"] - p["minQ"]) / 255.0) < 1e-6 * abs(p["alpha"])
+    # the codes are the documented clamp((x - minQ) / alpha, 0, 255) truncated to u8
+    expect = np.clip((vecs - p["minQ"]) / p["alpha"], 0.0, 255.0).astype(np.uint8)
+    assert (codes == expect).mean() > 0.999  # fp rounding at the bin edges only
+    for q in O.synth_matrix(1602, 8, dim):
+        d, l = sq.search_knn(q, k, 64)
+        cq, oq = sq.prepare_query(q)
+        rows = (l >> np.uint64(32)).astype(np.int64)  # single-threaded build: internal id = insertion order = row id
+        a = codes[rows].astype(np.int64)
+        b = cq.astype(np.int64)[None, :]
+        if metric == O.L2:
+            mine = np.float32(p["alpha_2"]) * ((a - b) ** 2).sum(axis=1).astype(np.float32) + np.float32(oq) + offs[rows]
+        else:
+            mine = -(np.float32(p["alpha_2"]) * (a * b).sum(axis=1).astype(np.float32) + np.float32(oq) + offs[rows])
+        assert np.allclose(mine, d, rtol=1e-5, atol=1e-5), (mine, d)
+        # and the quantised search still finds most of the true neighbours
+        exact = np.argsort(((vecs - q) ** 2).sum(axis=1) if metric == O.L2 else -(vecs @ q), kind="stable")[:k]
+        assert len(set(rows.tolist()) & set(exact.tolist())) >= 6
