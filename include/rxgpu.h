@@ -87,6 +87,10 @@ int rxgpu_search_knn(const rxgpu_index*, uint32_t nq, const float* queries /* nq
 int rxgpu_search_range(const rxgpu_index*, const float* query, float radius, uint64_t max_out, float* out_dist, uint64_t* out_label,
 					   uint64_t* out_n);
 
+/* The result of this thread's last rxgpu_search_range stays retained in the library: entries [offset, offset + n) of it (best first),
+ * so a caller that sized its buffers too small fetches the rest WITHOUT a second scan of the rows. */
+int rxgpu_last_range_results(uint64_t offset, uint64_t n, float* out_dist, uint64_t* out_label);
+
 /* Same scan with queries and outputs resident in HBM (device pointers), enqueued on `stream` (a cudaStream_t; NULL =
  * the library's own stream).  Used by the benchmark's device-resident leg and by the multi-GPU shard merge.
  * Outputs hold the top-k1 rows per query under the total order (distance, internal row index): out_idx is the shard-local
@@ -289,17 +293,14 @@ typedef struct {
 	uint32_t tc_fallbacks;      /* queries whose candidate list overflowed and were answered by the exact scan */
 	uint64_t tc_candidates;     /* rows re-ranked exactly */
 	uint32_t tc_cluster;        /* CTAs per cluster in the filter kernel (row tiles are TMA-multicast inside a cluster) */
-	uint32_t tc_kernel;         /* 1 = knn_tc_filter (queries in shared memory), 2 = knn_tc_filter_q (queries in TMEM), 3 = _q2
-								 * (cta_group::2), 4 = _w (UMMA N = 128), 5 = _q4 (four issuers) */
+	uint32_t tc_kernel;         /* 1 = knn_tc_filter (queries in shared memory), 2 = knn_tc_filter_q (queries in TMEM) */
 } rxgpu_search_stats;
 void rxgpu_last_search_stats(rxgpu_search_stats* out);
 /* large query batches: bf16 tensor-core filter + exact fp32 re-rank (results identical to the exact scan).
  * mode 0 = automatic (batches >= 64 queries on >= 100k rows, k <= 15), 1 = whenever possible, 2 = never;
- * 3..13 force kernel variants for tests/benchmarks (all give the same bits): 3 / 4 = first-generation kernel (queries in shared
+ * 3..6 force kernel variants for tests/benchmarks (all give the same bits): 3 / 4 = first-generation kernel (queries in shared
  * memory) with 1 CTA / a CTA pair per row tile; 5 / 6 = knn_tc_filter_q (queries in TMEM) with single CTAs / clusters of up to 4
- * (the default); 7 = knn_tc_filter_q2 (the CTA pair multiplies as one, tcgen05.mma.cta_group::2); 8 / 9 / 10 = knn_tc_filter_w
- * (one accumulator of 128 rows) with pairs / clusters of 4 / single CTAs; 11 / 12 / 13 = knn_tc_filter_q4 (four MMA issuers) with
- * pairs / clusters of 4 / single CTAs.  DESIGN.md section 9 has the measurements. */
+ * (the default).  DESIGN.md section 9 has the measurements. */
 int rxgpu_set_tensor_core_filter(rxgpu_index*, int mode);
 /* process-wide switch: bracket every scan-kernel launch with CUDA events (used by bench.py for the roofline figure) */
 int rxgpu_set_profile(int on);

@@ -763,9 +763,24 @@ int rxgpu_ft_add_postings(rxgpu_ft_index* ft, const rxgpu_ft_postings* list, uin
 		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
 	}
 	RX_CUDA(cudaSetDevice(ft->device));
+	if (list->ndocs && (!list->doc_ids || !list->pos_begin)) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
 	DevList l;
 	l.ndocs = list->ndocs;
 	l.npos = list->ndocs ? list->pos_begin[list->ndocs] : 0;
+	// the kernels index positions[] with these offsets: they must start at 0 and never decrease
+	if (list->ndocs && list->pos_begin[0] != 0) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: posting list: pos_begin must start at 0");
+	}
+	for (uint32_t i = 0; i < list->ndocs; ++i) {
+		if (list->pos_begin[i + 1] < list->pos_begin[i]) {
+			return fail(RXGPU_ERR_PARAMS, "rxgpu: posting list: pos_begin must be non-decreasing");
+		}
+	}
+	if (l.npos && !list->positions) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
 	for (uint32_t i = 0; i < list->ndocs; ++i) {
 		if (list->doc_ids[i] >= ft->total_docs || (i && list->doc_ids[i] <= list->doc_ids[i - 1])) {
 			return fail(RXGPU_ERR_PARAMS, "rxgpu: posting list must hold ascending document ids below total_docs");

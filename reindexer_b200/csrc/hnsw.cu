@@ -60,6 +60,7 @@ struct HnswArgs {
 	int maxlevel;
 	uint32_t enterpoint;
 	uint32_t nq, k, ef, words;
+	uint32_t out_stride;  // entries per query in out_dist / out_idx: the caller's k (a.k may be clamped to the row count)
 };
 
 __device__ __forceinline__ float4 ldg4(const float4* p) {
@@ -398,8 +399,8 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(const HnswArg
 		// ---- results: the k best of the list (SearchKnn :1998-2011), then clean the visited bitmap for the next query
 		const uint32_t outn = min(a.k, size);
 		for (uint32_t j = lane; j < outn; j += 32) {
-			a.out_dist[size_t(qi) * a.k + j] = l_dist[j];
-			a.out_idx[size_t(qi) * a.k + j] = l_id[j] & ~kExpanded;
+			a.out_dist[size_t(qi) * a.out_stride + j] = l_dist[j];
+			a.out_idx[size_t(qi) * a.out_stride + j] = l_id[j] & ~kExpanded;
 		}
 		if (lane == 0) {
 			a.out_count[qi] = outn;
@@ -577,6 +578,47 @@ int rxgpu_hnsw_import(rxgpu_index* ix, const rxgpu_hnsw_graph* g) {
 	if (g->maxM0 > uint32_t(kMaxNeighbours) || g->M > uint32_t(kMaxNeighbours) || g->n == 0 || g->enterpoint >= g->n) {
 		return fail(RXGPU_ERR_PARAMS, "rxgpu: unsupported HNSW graph (M must be <= 32, graph must be non-empty)");
 	}
+	if (g->upper_slots && !g->upper) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null graph");
+	}
+	{  // one host pass over the lists: the search kernel indexes rows, the visited bitmap and the upper-level slab with these values
+		const size_t s0 = size_t(1) + g->maxM0;
+		for (uint32_t i = 0; i < g->n; ++i) {
+			const uint32_t* l = g->level0 + size_t(i) * s0;
+			if (l[0] > g->maxM0) {
+				return fail(RXGPU_ERR_PARAMS, "rxgpu: HNSW graph: level-0 neighbour count of node " + std::to_string(i) + " exceeds maxM0");
+			}
+			for (uint32_t j = 1; j <= l[0]; ++j) {
+				if (l[j] >= g->n) {
+					return fail(RXGPU_ERR_PARAMS, "rxgpu: HNSW graph: level-0 neighbour id of node " + std::to_string(i) + " is out of range");
+				}
+			}
+		}
+		if (g->upper_offsets[0] < 0 || uint64_t(g->upper_offsets[g->n]) > g->upper_slots) {
+			return fail(RXGPU_ERR_PARAMS, "rxgpu: HNSW graph: upper_offsets do not fit upper_slots");
+		}
+		for (uint32_t i = 0; i < g->n; ++i) {
+			const int64_t span = g->upper_offsets[i + 1] - g->upper_offsets[i];
+			if (g->levels[i] < 0 || g->levels[i] > g->maxlevel || span < 0 || span < int64_t(g->levels[i])) {
+				return fail(RXGPU_ERR_PARAMS, "rxgpu: HNSW graph: levels / upper_offsets of node " + std::to_string(i) + " are inconsistent");
+			}
+		}
+		if (g->levels[g->enterpoint] != g->maxlevel) {
+			return fail(RXGPU_ERR_PARAMS, "rxgpu: HNSW graph: the enter point is not on the top level");
+		}
+		const size_t s1 = size_t(1) + g->M;
+		for (uint64_t sl = 0; sl < g->upper_slots; ++sl) {
+			const uint32_t* l = g->upper + sl * s1;
+			if (l[0] > g->M) {
+				return fail(RXGPU_ERR_PARAMS, "rxgpu: HNSW graph: an upper-level neighbour count exceeds M");
+			}
+			for (uint32_t j = 1; j <= l[0]; ++j) {
+				if (l[j] >= g->n) {
+					return fail(RXGPU_ERR_PARAMS, "rxgpu: HNSW graph: an upper-level neighbour id is out of range");
+				}
+			}
+		}
+	}
 	auto h = std::make_unique<rxgpu_hnsw_device>();
 	h->n = g->n;
 	h->M = g->M;
@@ -631,6 +673,7 @@ int rxgpu_hnsw_search_knn_device(const rxgpu_index* ix, uint32_t nq, const float
 	if (nq == 0) {
 		return 0;
 	}
+	const uint32_t outStride = k;  // the caller's buffers are [nq][k]; only the number of entries written is clamped
 	k = uint32_t(std::min<uint64_t>(k, ix->size));  // hnswalg.h:1993
 	if (k == 0) {
 		return fail(RXGPU_ERR_PARAMS, "rxgpu: k must be positive");
@@ -677,6 +720,7 @@ int rxgpu_hnsw_search_knn_device(const rxgpu_index* ix, uint32_t nq, const float
 	a.enterpoint = h->enterpoint;
 	a.nq = nq;
 	a.k = k;
+	a.out_stride = outStride;
 	a.ef = ef;
 	a.words = h->words;
 	const uint32_t dp4 = ((ix->dim + 127u) / 128u) * 32u;

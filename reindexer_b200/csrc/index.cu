@@ -12,6 +12,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/rxgpu.h"
@@ -19,9 +20,7 @@
 #include "../host/knn_select.h"
 #include "knn_scan.cuh"
 #include "knn_tc.cuh"
-#include "knn_tc_q2.cuh"
-#include "knn_tc_w.cuh"
-#include "knn_tc_q4.cuh"
+#include "knn_tc_q.cuh"
 
 using namespace rxgpu;
 
@@ -35,6 +34,7 @@ std::atomic<int> g_profile{0};
 namespace {
 
 thread_local std::vector<float> g_row_scratch;
+thread_local std::vector<Hit> g_range_result;  // the last range search of this thread, retained for rxgpu_last_range_results()
 
 int allocDevice(rxgpu_index* ix, uint64_t capacity, float** rows, uint64_t** labels, float** norms) {
 	const size_t cap = capacity ? capacity : 1;
@@ -324,51 +324,27 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 	g_stats.launches += 2;
 	const uint32_t ntiles = uint32_t((ix->size + kTcTileRows - 1) / kTcTileRows);
 	bool launched = false;
-	if ((ix->tc_variant == 0 || ix->tc_variant == 7 || ix->tc_variant == 8 || ix->tc_variant == 11) && kchunks <= kTqMaxKchunks) {
+	if (ix->tc_variant == 0 && kchunks <= kTqMaxKchunks) {
 		// second-generation filter: query block in TMEM, deep TMA ring, row tiles multicast to a cluster of up to 4 CTAs
 		const uint32_t qblocks = (nq + kTqQueries - 1) / kTqQueries;
-		// mode 7: the CTA pair multiplies as one (cta_group::2), each SM stages half of every row tile
-		const bool pairMma = ix->tc_variant == 7 && qblocks >= 2 && ix->sm_count >= 2;
-		// mode 8..10: one accumulator of 128 rows (UMMA N = 128 runs the tensor pipe at its full rate, N = 64 at 67 %)
-		const bool wide = ix->tc_variant == 8;
-		// mode 11: four MMA issuers (two per tile, splitting its K range)
-		const bool four = ix->tc_variant == 11;
-		auto smemOf = [&](uint32_t st) {
-			return pairMma ? t2_smem_bytes(st) : (wide ? tw_smem_bytes(st) : (four ? t4_smem_bytes(st) : tq_smem_bytes(st)));
-		};
 		uint32_t stages = 2;
-		while (smemOf(stages + 1) <= kTcSmemLimit && stages < 64) {
+		while (tq_smem_bytes(stages + 1) <= kTcSmemLimit && stages < 64) {
 			++stages;
 		}
-		const size_t smem = smemOf(stages);
-		if (four) {
-			RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_q4<1>, ix->device, int(kTcSmemLimit)));
-			RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_q4<2>, ix->device, int(kTcSmemLimit)));
-			RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_q4<4>, ix->device, int(kTcSmemLimit)));
-		}
-		if (wide) {
-			RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_w<1>, ix->device, int(kTcSmemLimit)));
-			RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_w<2>, ix->device, int(kTcSmemLimit)));
-			RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_w<4>, ix->device, int(kTcSmemLimit)));
-		}
-		RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_q2, ix->device, int(kTcSmemLimit)));
-		if (!wide && !pairMma && !four) {
-			RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_q<1>, ix->device, int(kTcSmemLimit)));
-			RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_q<2>, ix->device, int(kTcSmemLimit)));
-			RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_q<4>, ix->device, int(kTcSmemLimit)));
-		}
-		// measured on B200 (10M x 768, 1024 queries, same box, two rounds): CTA pairs 50.3 / 50.8 k queries/s, clusters of four
-		// 51.8 / 52.0 k, single CTAs ~40 k -- the kernel runs under the board's power cap, and a cluster of four reads every row tile
-		// from HBM once for 512 queries instead of 256
+		const size_t smem = tq_smem_bytes(stages);
+		RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_q<1>, ix->device, int(kTcSmemLimit)));
+		RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_q<2>, ix->device, int(kTcSmemLimit)));
+		RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_q<4>, ix->device, int(kTcSmemLimit)));
+		// a cluster of C CTAs reads every row tile from HBM once for C x 128 queries (TMA multicast)
 		const uint32_t clusterMax = ix->tc_cluster_max ? ix->tc_cluster_max : 4u;
 		int cluster = qblocks >= 3 ? 4 : (qblocks == 2 ? 2 : 1);
-		cluster = pairMma ? 2 : std::min<int>(cluster, int(clusterMax));
+		cluster = std::min<int>(cluster, int(clusterMax));
 		const uint32_t qtiles = uint32_t((ix->size + kTqTileRows - 1) / kTqTileRows);
 		unsigned grid = 0;
 		for (;;) {  // how many clusters of this size can be resident at once (GPC boundaries strand SMs for size 4)
 			cudaLaunchConfig_t cfg{};
 			cfg.gridDim = dim3(unsigned(ix->sm_count) / cluster * cluster);
-			cfg.blockDim = dim3(wide ? kTwThreads : (four ? kT4Threads : kTqThreads));
+			cfg.blockDim = dim3(kTqThreads);
 			cfg.dynamicSmemBytes = smem;
 			cudaLaunchAttribute attr[1];
 			attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -378,22 +354,15 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			cfg.attrs = attr;
 			cfg.numAttrs = 1;
 			int maxClusters = 0;
-			cudaError_t e = four && cluster == 4 ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q4<4>, &cfg)
-							: four && cluster == 2 ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q4<2>, &cfg)
-							: four				   ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q4<1>, &cfg)
-							: wide && cluster == 4 ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_w<4>, &cfg)
-							: wide && cluster == 2 ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_w<2>, &cfg)
-							: wide				   ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_w<1>, &cfg)
-							: pairMma			   ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q2, &cfg)
-							: cluster == 4 ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q<4>, &cfg)
+			cudaError_t e = cluster == 4   ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q<4>, &cfg)
 							: cluster == 2 ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q<2>, &cfg)
 										   : cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q<1>, &cfg);
 			if (e == cudaSuccess && maxClusters > 0) {
-				grid = unsigned(std::min<uint64_t>(uint64_t(maxClusters), std::max<uint32_t>(wide ? (qtiles + 1) / 2 : qtiles, 1))) * cluster;
+				grid = unsigned(std::min<uint64_t>(uint64_t(maxClusters), std::max<uint32_t>(qtiles, 1))) * cluster;
 				break;
 			}
 			cudaGetLastError();
-			if (cluster == 1 || pairMma) {
+			if (cluster == 1) {
 				return fail(RXGPU_ERR_SYSTEM, "rxgpu: tensor-core filter kernel cannot be made resident");
 			}
 			cluster /= 2;
@@ -442,7 +411,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			}
 			cudaLaunchConfig_t cfg{};
 			cfg.gridDim = dim3(grid);
-			cfg.blockDim = dim3(wide ? kTwThreads : (four ? kT4Threads : kTqThreads));
+			cfg.blockDim = dim3(kTqThreads);
 			cfg.dynamicSmemBytes = smem;
 			cfg.stream = st;
 			cudaLaunchAttribute attr[1];
@@ -452,25 +421,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			attr[0].val.clusterDim.z = 1;
 			cfg.attrs = attr;
 			cfg.numAttrs = 1;
-			if (four) {
-				if (cluster == 4) {
-					RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q4<4>, a));
-				} else if (cluster == 2) {
-					RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q4<2>, a));
-				} else {
-					RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q4<1>, a));
-				}
-			} else if (wide) {
-				if (cluster == 4) {
-					RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_w<4>, a));
-				} else if (cluster == 2) {
-					RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_w<2>, a));
-				} else {
-					RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_w<1>, a));
-				}
-			} else if (pairMma) {
-				RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q2, a));
-			} else if (cluster == 4) {
+			if (cluster == 4) {
 				RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q<4>, a));
 			} else if (cluster == 2) {
 				RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q<2>, a));
@@ -499,7 +450,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			}
 		}
 		g_stats.tc_cluster = uint32_t(cluster);
-		g_stats.tc_kernel = four ? 5 : (wide ? 4 : (pairMma ? 3 : 2));
+		g_stats.tc_kernel = 2;
 		g_stats.query_tile = uint32_t(kTqQueries * cluster);
 		g_stats.algorithmic_bytes += uint64_t((qblocks + cluster - 1) / cluster) * (uint64_t(ix->size) * pitchBf * 2 + uint64_t(ix->size) * 4) +
 									 uint64_t(nq) * pitchBf * 2;
@@ -802,93 +753,112 @@ int rxgpu_index_upsert_batch(rxgpu_index* ix, uint64_t n, const uint64_t* labels
 	if (!labels || !vecs) {
 		return fail(RXGPU_ERR_PARAMS, "rxgpu: null labels / vectors");
 	}
-	// resolve destinations sequentially, exactly like n AddPointNoLock calls (bruteforce.cc:44-64)
-	std::vector<uint32_t> dst(n);
-	uint64_t newSize = ix->size;
-	bool pureAppend = true;
-	uint64_t accepted = n;
-	for (uint64_t i = 0; i < n; ++i) {
-		uint32_t idx = ix->dict.find(labels[i]);
-		if (idx == LabelMap::kNotFound) {
-			if (newSize >= ix->capacity) {
-				accepted = i;  // rows before i are applied, like the reference's sequential calls
-				break;
-			}
-			idx = uint32_t(newSize++);
-			ix->dict.put(labels[i], idx);
-			ix->h_labels.push_back(labels[i]);
-		} else {
-			pureAppend = false;
-		}
-		dst[i] = idx;
-	}
-	const uint64_t m = accepted;
-	if (m) {
-		ix->version++;
-		if (ix->flags & RXGPU_FLAG_HOST_MIRROR) {
-			for (uint64_t i = 0; i < m; ++i) {
-				std::memcpy(ix->h_rows.data() + size_t(dst[i]) * ix->dim, vecs + i * ix->dim, ix->dim * sizeof(float));
-			}
-		}
-		if (pureAppend && ix->pitch == ix->dim) {
-			RX_CUDA(cudaMemcpyAsync(ix->d_rows + size_t(ix->size) * ix->pitch, vecs, size_t(m) * ix->dim * sizeof(float),
-									cudaMemcpyHostToDevice, ix->stream));
-			RX_CUDA(cudaMemcpyAsync(ix->d_labels + ix->size, labels, size_t(m) * sizeof(uint64_t), cudaMemcpyHostToDevice, ix->stream));
-			if (int rc = normsForRange(ix, ix->size, ix->size + m)) {
-				return rc;
-			}
-		} else {
-			// stage + scatter in bounded slices
-			const uint64_t slice = std::max<uint64_t>(1, (64ull << 20) / (ix->dim * sizeof(float)));
-			DevBuf<float> st;
-			DevBuf<uint32_t> sd;
-			DevBuf<uint64_t> sl;
-			RX_CUDA(st.ensure(size_t(std::min(slice, m)) * ix->dim));
-			RX_CUDA(sd.ensure(size_t(std::min(slice, m))));
-			RX_CUDA(sl.ensure(size_t(std::min(slice, m))));
-			for (uint64_t off = 0; off < m; off += slice) {
-				const uint64_t cnt = std::min(slice, m - off);
-				RX_CUDA(cudaMemcpyAsync(st.p, vecs + off * ix->dim, size_t(cnt) * ix->dim * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
-				RX_CUDA(cudaMemcpyAsync(sd.p, dst.data() + off, size_t(cnt) * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
-				RX_CUDA(cudaMemcpyAsync(sl.p, labels + off, size_t(cnt) * sizeof(uint64_t), cudaMemcpyHostToDevice, ix->stream));
-				// duplicates of one label inside a slice must apply in order: fall back to one launch per row when present
-				bool dup = false;
-				{
-					std::vector<uint32_t> sorted(dst.begin() + off, dst.begin() + off + cnt);
-					std::sort(sorted.begin(), sorted.end());
-					dup = std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end();
-				}
-				if (!dup) {
-					scatter_rows_kernel<<<unsigned(cnt), 128, 0, ix->stream>>>(st.p, sd.p, sl.p, uint32_t(cnt), ix->dim, ix->pitch, ix->d_rows,
-																			   ix->d_labels);
-					RX_CUDA(cudaGetLastError());
+	// Resolve destinations sequentially, exactly like n AddPointNoLock calls (bruteforce.cc:44-64) -- into temporaries: the
+	// dictionary, h_labels, the host mirror and size are committed only after every device operation of the batch succeeded, so a
+	// failed call (staging allocation, copy or launch error) leaves the index exactly as it was.
+	try {
+		std::vector<uint32_t> dst(n);
+		std::vector<uint64_t> fresh;  // new labels in arrival order; fresh[i] goes to row size + i
+		std::unordered_map<uint64_t, uint32_t> pending;  // new label -> row, for repeats of a new label inside the batch
+		uint64_t newSize = ix->size;
+		bool pureAppend = true;
+		uint64_t accepted = n;
+		for (uint64_t i = 0; i < n; ++i) {
+			uint32_t idx = ix->dict.find(labels[i]);
+			if (idx == LabelMap::kNotFound) {
+				const auto it = pending.find(labels[i]);
+				if (it != pending.end()) {
+					idx = it->second;
+					pureAppend = false;
 				} else {
-					for (uint64_t i = 0; i < cnt; ++i) {
-						scatter_rows_kernel<<<1, 128, 0, ix->stream>>>(st.p + i * ix->dim, sd.p + i, sl.p + i, 1, ix->dim, ix->pitch, ix->d_rows,
-																	   ix->d_labels);
+					if (newSize >= ix->capacity) {
+						accepted = i;  // rows before i are applied, like the reference's sequential calls
+						break;
 					}
-					RX_CUDA(cudaGetLastError());
+					idx = uint32_t(newSize++);
+					pending.emplace(labels[i], idx);
+					fresh.push_back(labels[i]);
 				}
-				if (ix->metric == RXGPU_COS) {
-					for (uint64_t i = 0; i < cnt;) {  // norms for maximal runs of consecutive destinations
-						uint64_t j = i + 1;
-						while (j < cnt && dst[off + j] == dst[off + j - 1] + 1) {
-							++j;
-						}
-						if (int rc = normsForRange(ix, dst[off + i], uint64_t(dst[off + j - 1]) + 1)) {
-							return rc;
-						}
-						i = j;
-					}
-				}
-				RX_CUDA(cudaStreamSynchronize(ix->stream));
+			} else {
+				pureAppend = false;
 			}
+			dst[i] = idx;
 		}
-		ix->size = newSize;
-		RX_CUDA(cudaStreamSynchronize(ix->stream));
-	}
-	if (accepted < n) {
-		return fail(RXGPU_ERR_LOGIC, "The number of elements exceeds the specified limit\n");
+		const uint64_t m = accepted;
+		if (m) {
+			if (pureAppend && ix->pitch == ix->dim) {
+				RX_CUDA(cudaMemcpyAsync(ix->d_rows + size_t(ix->size) * ix->pitch, vecs, size_t(m) * ix->dim * sizeof(float),
+										cudaMemcpyHostToDevice, ix->stream));
+				RX_CUDA(cudaMemcpyAsync(ix->d_labels + ix->size, labels, size_t(m) * sizeof(uint64_t), cudaMemcpyHostToDevice, ix->stream));
+				if (int rc = normsForRange(ix, ix->size, ix->size + m)) {
+					return rc;
+				}
+			} else {
+				// stage + scatter in bounded slices; the staging buffers live in the index (no cudaMalloc / cudaFree per call)
+				const uint64_t slice = std::max<uint64_t>(1, (64ull << 20) / (ix->dim * sizeof(float)));
+				RX_CUDA(ix->st_rows.ensure(size_t(std::min(slice, m)) * ix->dim));
+				RX_CUDA(ix->st_dst.ensure(size_t(std::min(slice, m))));
+				RX_CUDA(ix->st_labels.ensure(size_t(std::min(slice, m))));
+				for (uint64_t off = 0; off < m; off += slice) {
+					const uint64_t cnt = std::min(slice, m - off);
+					RX_CUDA(cudaMemcpyAsync(ix->st_rows.p, vecs + off * ix->dim, size_t(cnt) * ix->dim * sizeof(float), cudaMemcpyHostToDevice,
+											ix->stream));
+					RX_CUDA(cudaMemcpyAsync(ix->st_dst.p, dst.data() + off, size_t(cnt) * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
+					RX_CUDA(cudaMemcpyAsync(ix->st_labels.p, labels + off, size_t(cnt) * sizeof(uint64_t), cudaMemcpyHostToDevice, ix->stream));
+					// duplicates of one label inside a slice must apply in order: one launch per row when present
+					bool dup = false;
+					if (cnt > 1) {
+						std::vector<uint32_t> sorted(dst.begin() + off, dst.begin() + off + cnt);
+						std::sort(sorted.begin(), sorted.end());
+						dup = std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end();
+					}
+					if (!dup) {
+						scatter_rows_kernel<<<unsigned(cnt), 128, 0, ix->stream>>>(ix->st_rows.p, ix->st_dst.p, ix->st_labels.p, uint32_t(cnt), ix->dim,
+																				   ix->pitch, ix->d_rows, ix->d_labels);
+						RX_CUDA(cudaGetLastError());
+					} else {
+						for (uint64_t i = 0; i < cnt; ++i) {
+							scatter_rows_kernel<<<1, 128, 0, ix->stream>>>(ix->st_rows.p + i * ix->dim, ix->st_dst.p + i, ix->st_labels.p + i, 1, ix->dim,
+																		   ix->pitch, ix->d_rows, ix->d_labels);
+						}
+						RX_CUDA(cudaGetLastError());
+					}
+					if (ix->metric == RXGPU_COS) {
+						for (uint64_t i = 0; i < cnt;) {  // norms for maximal runs of consecutive destinations
+							uint64_t j = i + 1;
+							while (j < cnt && dst[off + j] == dst[off + j - 1] + 1) {
+								++j;
+							}
+							if (int rc = normsForRange(ix, dst[off + i], uint64_t(dst[off + j - 1]) + 1)) {
+								return rc;
+							}
+							i = j;
+						}
+					}
+					if (off + slice < m) {
+						RX_CUDA(cudaStreamSynchronize(ix->stream));  // the staging buffers are reused by the next slice
+					}
+				}
+			}
+			RX_CUDA(cudaStreamSynchronize(ix->stream));
+			// ---- commit (host state only; nothing below can fail except by std::bad_alloc, which reserve() at create/resize precludes)
+			for (size_t i = 0; i < fresh.size(); ++i) {
+				ix->dict.put(fresh[i], uint32_t(ix->size + i));
+				ix->h_labels.push_back(fresh[i]);
+			}
+			if (ix->flags & RXGPU_FLAG_HOST_MIRROR) {
+				for (uint64_t i = 0; i < m; ++i) {
+					std::memcpy(ix->h_rows.data() + size_t(dst[i]) * ix->dim, vecs + i * ix->dim, ix->dim * sizeof(float));
+				}
+			}
+			ix->size = newSize;
+			ix->version++;
+		}
+		if (accepted < n) {
+			return fail(RXGPU_ERR_LOGIC, "The number of elements exceeds the specified limit\n");
+		}
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
 	}
 	return 0;
 }
@@ -967,12 +937,12 @@ int rxgpu_set_query_tile(rxgpu_index* ix, uint32_t qt) {
 	return 0;
 }
 int rxgpu_set_tensor_core_filter(rxgpu_index* ix, int mode) {
-	if (!ix || mode < 0 || mode > 13) {
-		return fail(RXGPU_ERR_PARAMS, "rxgpu: tensor-core filter mode must be in 0..13");
+	if (!ix || mode < 0 || mode > 6) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: tensor-core filter mode must be in 0..6");
 	}
 	ix->tc_mode = uint32_t(mode >= 3 ? 1 : mode);
-	ix->tc_variant = (mode == 3 || mode == 4 || mode == 7) ? uint32_t(mode) : (mode >= 11 ? 11u : (mode >= 8 ? 8u : 0u));
-	ix->tc_cluster_max = (mode == 5 || mode == 10 || mode == 13) ? 1u : ((mode == 6 || mode == 9 || mode == 12) ? 4u : ((mode == 8 || mode == 11) ? 2u : 0u));
+	ix->tc_variant = (mode == 3 || mode == 4) ? uint32_t(mode) : 0u;
+	ix->tc_cluster_max = mode == 5 ? 1u : (mode == 6 ? 4u : 0u);
 	return 0;
 }
 int rxgpu_set_profile(int on) {
@@ -1224,7 +1194,8 @@ static int searchRangeHost(const rxgpu_index* ix, const float* query, float radi
 	RX_CUDA(ws.d_queries.ensure(ix->dim));
 	RX_CUDA(ws.d_range_count.ensure(1));
 	RX_CUDA(cudaMemcpyAsync(ws.d_queries.p, query, ix->dim * sizeof(float), cudaMemcpyHostToDevice, st));
-	uint64_t cap = std::max<uint64_t>(ws.d_range.n, 1u << 16);
+	// result buffer: up to 4M matches (32 MB) without a rescan; a larger result grows the buffer and scans once more
+	uint64_t cap = std::max<uint64_t>(ws.d_range.n, std::min<uint64_t>(std::max<uint64_t>(ix->size, 1), 1u << 22));
 	for (;;) {
 		RX_CUDA(ws.d_range.ensure(cap));
 		RX_CUDA(cudaMemsetAsync(ws.d_range_count.p, 0, sizeof(unsigned long long), st));
@@ -1281,7 +1252,7 @@ int rxgpu_search_range(const rxgpu_index* ix, const float* query, float radius, 
 		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
 	}
 	try {
-		std::vector<Hit> res;
+		std::vector<Hit>& res = g_range_result;
 		if (int rc = searchRangeHost(ix, query, radius, res)) {
 			return rc;
 		}
@@ -1293,6 +1264,17 @@ int rxgpu_search_range(const rxgpu_index* ix, const float* query, float radius, 
 		*out_n = res.size();
 	} catch (const std::bad_alloc&) {
 		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
+	}
+	return 0;
+}
+
+int rxgpu_last_range_results(uint64_t offset, uint64_t n, float* out_dist, uint64_t* out_label) {
+	if (offset > g_range_result.size() || n > g_range_result.size() - offset || (n && (!out_dist || !out_label))) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: range outside the retained result of this thread's last rxgpu_search_range");
+	}
+	for (uint64_t i = 0; i < n; ++i) {
+		out_dist[i] = g_range_result[offset + i].dist;
+		out_label[i] = g_range_result[offset + i].label;
 	}
 	return 0;
 }

@@ -181,6 +181,9 @@ struct rxgpu_index {
 	std::vector<float> h_rows;  // optional host mirror [capacity][dim]
 
 	cudaStream_t stream = nullptr;  // maintenance stream
+	rxgpu::DevBuf<float> st_rows;   // staging of scattered upserts (mutators run one at a time under the namespace write lock)
+	rxgpu::DevBuf<uint32_t> st_dst;
+	rxgpu::DevBuf<uint64_t> st_labels;
 	mutable std::mutex ws_mtx;
 	mutable std::vector<std::unique_ptr<rxgpu::Workspace>> ws_free;
 	rxgpu_hnsw_device* hnsw = nullptr;  // graph attached by rxgpu_hnsw_import (hnsw.cu)

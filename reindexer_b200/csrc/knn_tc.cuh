@@ -126,6 +126,19 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
 				 "h"(mask)
 				 : "memory");
 }
+// true in exactly one lane of a converged warp (elect.sync): the single-thread tcgen05 / TMA instructions are issued under this
+// predicate from warp-uniform code, so their operands stay in uniform registers
+__device__ __forceinline__ bool elect_one_sync() {
+	uint32_t p;
+	asm volatile(
+		"{\n"
+		".reg .pred P;\n"
+		"elect.sync _|P, 0xffffffff;\n"
+		"selp.u32 %0, 1, 0, P;\n"
+		"}\n"
+		: "=r"(p));
+	return p != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
 	uint32_t r;
 	asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -227,7 +240,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 	uint2* s_queue = reinterpret_cast<uint2*>(s_pr + a.nq_block);     // (query, ub bits)
 	uint32_t* s_qcount = reinterpret_cast<uint32_t*>(s_queue + kTcQueueCap);
 
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
 	const uint32_t ntiles = (a.n + kTcTileRows - 1) / kTcTileRows;
 	const uint32_t crank = kCluster > 1 ? cluster_ctarank() : 0u;
 	const uint32_t cid = blockIdx.x / kCluster, ncl = gridDim.x / kCluster;  // tile walkers
@@ -266,20 +279,23 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 	const uint32_t tmem_base = *s_tmem;
 
 	if (warp == 0) {
-		// ===== TMA producer =====
-		if (lane == 0) {
+		// ===== TMA producer: the whole warp walks the loop, one elected lane issues (operands stay in uniform registers) =====
+		if (elect_one_sync()) {
 			mbar_expect_tx(q_bar, a.kchunks * qchunk_bytes);
 			for (uint32_t kc = 0; kc < a.kchunks; ++kc) {
 				tma_load_2d(s_q + size_t(kc) * qchunk_bytes, &map_queries, q_bar, int32_t(kc * kTcChunkK), int32_t(q0));
 			}
-			uint32_t stage = 0, phase = 0;
-			for (uint32_t t = cid; t < ntiles; t += ncl) {
-				for (uint32_t kc = 0; kc < a.kchunks; ++kc) {
-					mbar_wait(&empty_bar[stage], phase ^ 1);
+		}
+		__syncwarp();
+		uint32_t stage = 0, phase = 0;
+		for (uint32_t t = cid; t < ntiles; t += ncl) {
+			for (uint32_t kc = 0; kc < a.kchunks; ++kc) {
+				mbar_wait(&empty_bar[stage], phase ^ 1);
+				// a 128-row stage = the 64-row shadow sub-tiles 2t and 2t+1 of this K chunk, 8 KB each, contiguous in HBM
+				const unsigned char* src = a.shadow + (size_t(2 * t) * a.kchunks + kc) * 8192u;
+				unsigned char* dst = s_rows + size_t(stage) * kTcStageBytes;
+				if (elect_one_sync()) {
 					mbar_expect_tx(&full_bar[stage], kTcStageBytes);
-					// a 128-row stage = the 64-row shadow sub-tiles 2t and 2t+1 of this K chunk, 8 KB each, contiguous in HBM
-					const unsigned char* src = a.shadow + (size_t(2 * t) * a.kchunks + kc) * 8192u;
-					unsigned char* dst = s_rows + size_t(stage) * kTcStageBytes;
 					if constexpr (kCluster > 1) {  // my half of the stage, delivered to both CTAs
 						bulk_load_mc(dst + crank * 8192u, src + size_t(crank) * a.kchunks * 8192u, 8192u, &full_bar[stage],
 									 uint16_t((1u << kCluster) - 1u));
@@ -287,29 +303,30 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 						bulk_load(dst, src, 8192u, &full_bar[stage]);
 						bulk_load(dst + 8192u, src + size_t(a.kchunks) * 8192u, 8192u, &full_bar[stage]);
 					}
-					if (++stage == kTcStages) {
-						stage = 0;
-						phase ^= 1;
-					}
+				}
+				__syncwarp();
+				if (++stage == kTcStages) {
+					stage = 0;
+					phase ^= 1;
 				}
 			}
 		}
 	} else if (warp == 1) {
-		// ===== MMA issuer =====
-		if (lane == 0) {
-			const uint32_t idesc = umma_idesc_bf16(kTcTileRows, a.nq_block);
-			mbar_wait(q_bar, 0);
-			uint32_t stage = 0, phase = 0, it = 0;
-			for (uint32_t t = cid; t < ntiles; t += ncl, ++it) {
-				const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-				mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+		// ===== MMA issuer (same structure: convergent loop, elected issue) =====
+		const uint32_t idesc = umma_idesc_bf16(kTcTileRows, a.nq_block);
+		mbar_wait(q_bar, 0);
+		uint32_t stage = 0, phase = 0, it = 0;
+		for (uint32_t t = cid; t < ntiles; t += ncl, ++it) {
+			const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+			mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+			const uint32_t tmem_d = tmem_base + acc * 256;
+			for (uint32_t kc = 0; kc < a.kchunks; ++kc) {
+				mbar_wait(&full_bar[stage], phase);
 				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-				const uint32_t tmem_d = tmem_base + acc * 256;
-				for (uint32_t kc = 0; kc < a.kchunks; ++kc) {
-					mbar_wait(&full_bar[stage], phase);
-					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-					const uint32_t a_addr = smem_u32(s_rows + size_t(stage) * kTcStageBytes);
-					const uint32_t b_addr = smem_u32(s_q + size_t(kc) * qchunk_bytes);
+				const uint32_t a_addr = smem_u32(s_rows + size_t(stage) * kTcStageBytes);
+				const uint32_t b_addr = smem_u32(s_q + size_t(kc) * qchunk_bytes);
+				if (elect_one_sync()) {
 #pragma unroll
 					for (uint32_t k = 0; k < kTcChunkK / 16; ++k) {  // UMMA_K = 16 bf16 = 32 bytes inside the 128-byte swizzle row
 						umma_bf16(tmem_d, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (kc | k) != 0);
@@ -319,12 +336,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 					} else {
 						umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
 					}
-					if (++stage == kTcStages) {
-						stage = 0;
-						phase ^= 1;
+					if (kc + 1 == a.kchunks) {
+						umma_commit(&acc_full[acc]);  // accumulator complete -> epilogue
 					}
 				}
-				umma_commit(&acc_full[acc]);  // accumulator complete -> epilogue
+				__syncwarp();
+				if (++stage == kTcStages) {
+					stage = 0;
+					phase ^= 1;
+				}
 			}
 		}
 	} else {

@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 	uint64_t* vw_full = q_ready + 1;             // [kTqVwSlots]
 	uint32_t* s_tmem = reinterpret_cast<uint32_t*>(vw_full + kTqVwSlots);
 
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // warp index provably uniform
 	const uint32_t ntiles = (a.n + kTqTileRows - 1) / kTqTileRows;
 	const uint32_t crank = kCluster > 1 ? cluster_ctarank() : 0u;
 	const uint32_t cid = blockIdx.x / kCluster, ncl = gridDim.x / kCluster;
@@ -207,24 +207,26 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 
 	if (warp == 0) {
 		// ===== producer: contiguous 8 KB bulk copies; in a cluster CTA r fetches the K chunks with (chunk % C == r) of every stage and
-		// multicasts them to all CTAs =====
-		if (lane == 0) {
-			const uint32_t kpairs = (a.kchunks + kTqSubsPerStage - 1) / kTqSubsPerStage;
-			uint32_t stage = 0, phase = 0;
-			for (uint32_t t = cid; t < ntiles; t += ncl) {
-				const unsigned char* tile_src = a.shadow + size_t(t) * a.kchunks * kTqSubBytes;
-				for (uint32_t kp = 0; kp < kpairs; ++kp) {
-					const uint32_t nsub = min(uint32_t(kTqSubsPerStage), a.kchunks - kTqSubsPerStage * kp);
-					if (kp == 0) {
-						TQ_TRACE(9, (t - cid) / ncl);
-					}
-					mbar_wait(&empty_bar[stage], phase ^ 1);
-					if (kp == 0) {
-						TQ_TRACE(10, (t - cid) / ncl);
-					}
+		// multicasts them to all CTAs.  The WHOLE warp walks the loop (convergent code: addresses and counters live in uniform
+		// registers) and one elected lane issues the copies -- inside an `if (lane == 0)` region ptxas cannot prove the operands
+		// warp-uniform and wraps every UBLKCP / UTCHMMA into an ELECT + R2UR waterfall loop. =====
+		const uint32_t kpairs = (a.kchunks + kTqSubsPerStage - 1) / kTqSubsPerStage;
+		uint32_t stage = 0, phase = 0;
+		for (uint32_t t = cid; t < ntiles; t += ncl) {
+			const unsigned char* tile_src = a.shadow + size_t(t) * a.kchunks * kTqSubBytes;
+			for (uint32_t kp = 0; kp < kpairs; ++kp) {
+				const uint32_t nsub = min(uint32_t(kTqSubsPerStage), a.kchunks - kTqSubsPerStage * kp);
+				if (kp == 0 && lane == 0) {
+					TQ_TRACE(9, (t - cid) / ncl);
+				}
+				mbar_wait(&empty_bar[stage], phase ^ 1);
+				if (kp == 0 && lane == 0) {
+					TQ_TRACE(10, (t - cid) / ncl);
+				}
+				unsigned char* dst = s_rows + size_t(stage) * kTqStageBytes;
+				const unsigned char* src = tile_src + size_t(kTqSubsPerStage * kp) * kTqSubBytes;
+				if (elect_one_sync()) {
 					mbar_expect_tx(&full_bar[stage], nsub * kTqSubBytes);
-					unsigned char* dst = s_rows + size_t(stage) * kTqStageBytes;
-					const unsigned char* src = tile_src + size_t(kTqSubsPerStage * kp) * kTqSubBytes;
 					if constexpr (kCluster > 1) {
 						for (uint32_t sub = crank; sub < nsub; sub += kCluster) {
 							bulk_load_mc(dst + sub * kTqSubBytes, src + size_t(sub) * kTqSubBytes, kTqSubBytes, &full_bar[stage],
@@ -239,45 +241,49 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 							bulk_prefetch_l2(ahead + size_t(sub) * kTqSubBytes, kTqSubBytes);
 						}
 					}
-					if (++stage == a.stages) {
-						stage = 0;
-						phase ^= 1;
-					}
+				}
+				__syncwarp();
+				if (++stage == a.stages) {
+					stage = 0;
+					phase ^= 1;
 				}
 			}
 		}
 	} else if (warp == 1 || warp == 6) {
 		// ===== MMA issuers: warp 1 -> even tiles / accumulator 0, warp 6 -> odd tiles / accumulator 1 =====
-		// D[128 queries x 64 rows] += A(TMEM) x B(smem stage)^T
-		if (lane == 0) {
-			const uint32_t parity = warp == 1 ? 0u : 1u;
-			const uint32_t idesc = umma_idesc_bf16(kTqQueries, kTqTileRows);
-			const uint32_t kpairs = (a.kchunks + kTqSubsPerStage - 1) / kTqSubsPerStage;
-			mbar_wait(q_ready, 0);
-			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-			const uint32_t tmem_d = tmem_base + kTqAccCol0 + parity * kTqTileRows;
-			for (uint32_t it = parity, t = cid + parity * ncl; t < ntiles; it += 2, t += 2 * ncl) {
+		// D[128 queries x 64 rows] += A(TMEM) x B(smem stage)^T.  Whole warp in the loop, one elected lane issues (see the producer).
+		const uint32_t parity = warp == 1 ? 0u : 1u;
+		const uint32_t idesc = umma_idesc_bf16(kTqQueries, kTqTileRows);
+		const uint32_t kpairs = (a.kchunks + kTqSubsPerStage - 1) / kTqSubsPerStage;
+		mbar_wait(q_ready, 0);
+		asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+		const uint32_t tmem_d = tmem_base + kTqAccCol0 + parity * kTqTileRows;
+		// stages are consumed in tile order by the two issuers alternately: mine are [it * kpairs, (it + 1) * kpairs) for it = parity, parity + 2, ...
+		uint32_t stage = (parity * kpairs) % a.stages, phase = ((parity * kpairs) / a.stages) & 1;
+		for (uint32_t it = parity, t = cid + parity * ncl; t < ntiles; it += 2, t += 2 * ncl) {
+			if (lane == 0) {
 				TQ_TRACE(0, it);
-				mbar_wait(&acc_empty[parity], ((it >> 1) & 1) ^ 1);
-				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+			}
+			mbar_wait(&acc_empty[parity], ((it >> 1) & 1) ^ 1);
+			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+			if (lane == 0) {
 				TQ_TRACE(1, it);
-				const uint32_t sidx0 = it * kpairs;  // stages are consumed in tile order by the two issuers alternately
-				for (uint32_t kp = 0; kp < kpairs; ++kp) {
-					const uint32_t sidx = sidx0 + kp;
-					const uint32_t stage = sidx % a.stages, phase = (sidx / a.stages) & 1;
-					const uint32_t nsub = min(uint32_t(kTqSubsPerStage), a.kchunks - kTqSubsPerStage * kp);
-					mbar_wait(&full_bar[stage], phase);
-					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-					if (kp == 0) {
-						TQ_TRACE(2, it);
-					}
-					const uint32_t b_addr = smem_u32(s_rows + size_t(stage) * kTqStageBytes);
+			}
+			for (uint32_t kp = 0; kp < kpairs; ++kp) {
+				const uint32_t nsub = min(uint32_t(kTqSubsPerStage), a.kchunks - kTqSubsPerStage * kp);
+				mbar_wait(&full_bar[stage], phase);
+				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+				if (kp == 0 && lane == 0) {
+					TQ_TRACE(2, it);
+				}
+				const uint32_t b_addr = smem_u32(s_rows + size_t(stage) * kTqStageBytes);
+				const uint32_t a_col = tmem_base + kTqSubsPerStage * kp * 32;
+				if (elect_one_sync()) {
 					for (uint32_t sub = 0; sub < nsub; ++sub) {
 #pragma unroll
 						for (uint32_t k = 0; k < kTcChunkK / 16; ++k) {  // K = 16 bf16 = 8 TMEM columns of A, 32 bytes of the B swizzle row
-							umma_bf16_ts(tmem_d, tmem_base + ((kTqSubsPerStage * kp + sub) * 4 + k) * 8,
-										 umma_desc_sw128(b_addr + sub * kTqSubBytes + k * 32),
-										 idesc, (kp | sub | k) != 0);
+							umma_bf16_ts(tmem_d, a_col + (sub * 4 + k) * 8, umma_desc_sw128(b_addr + sub * kTqSubBytes + k * 32), idesc,
+										 (kp | sub | k) != 0);
 						}
 					}
 					if constexpr (kCluster > 1) {
@@ -285,15 +291,29 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 					} else {
 						umma_commit(&empty_bar[stage]);
 					}
+					if (kp + 1 == kpairs) {
+						umma_commit(&acc_full[parity]);
+					}
 				}
-				umma_commit(&acc_full[parity]);
+				__syncwarp();
+				if (++stage == a.stages) {
+					stage = 0;
+					phase ^= 1;
+				}
+			}
+			if (lane == 0) {
 				TQ_TRACE(3, it);
+			}
+			for (uint32_t kp = 0; kp < kpairs; ++kp) {  // skip the other issuer's stages
+				if (++stage == a.stages) {
+					stage = 0;
+					phase ^= 1;
+				}
 			}
 		}
 	} else {
 		// ===== epilogue warps 2..5: thread = query (TMEM lane quadrant = warp % 4) =====
 		const uint32_t quad = warp & 3;
-		const uint32_t et = threadIdx.x - 64;              // 0..127 inside the epilogue group
 		const uint32_t my_q = q0 + quad * 32 + lane;       // global query index of this TMEM lane
 		const bool q_ok = my_q < a.nq_total;
 		// 1. my query -> TMEM (A operand): 32 columns (64 bf16) per store
@@ -323,7 +343,7 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 		float tau = q_ok ? ord_float(a.tau[my_q]) : -INFINITY;
 		float2 pr = q_ok ? tc_make_pr(a.metric, tau, qe) : make_float2(0.f, INFINITY);
 		// per-row terms (||v||, w): one 512-byte bulk copy per tile into a ring of kTqVwSlots slots, issued kTqVwAhead tiles ahead by
-		// the first epilogue thread, so no global-load latency and no CTA barrier sits on the epilogue path.  Slot reuse is safe
+		// the first epilogue warp, so no global-load latency and no CTA barrier sits on the epilogue path.  Slot reuse is safe
 		// without an "empty" barrier: when this thread starts tile `it` it has passed acc_full(it - 1); those MMAs waited for the
 		// acc_empty arrivals of tile it - 3 from all four warps, which every warp issues after finishing tile it - 4 -- the last
 		// reader of slot (it + kTqVwAhead) % kTqVwSlots.
@@ -337,18 +357,24 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 						  reinterpret_cast<const unsigned char*>(a.vw + t * kTqTileRows), kTqTileRows * 8, &vw_full[slot]);
 			}
 		};
-		if (et == 0) {
-			for (uint32_t j = 0; j < kTqVwAhead; ++j) {
-				issue_vw(j);
+		if (warp == 2) {  // first epilogue warp: convergent, one elected lane issues the copies
+			if (elect_one_sync()) {
+				for (uint32_t j = 0; j < kTqVwAhead; ++j) {
+					issue_vw(j);
+				}
 			}
+			__syncwarp();
 		}
 		unsigned int tau_ahead = q_ok ? a.tau[my_q] : 0u;
 		uint32_t it = 0;
 		for (uint32_t t = cid; t < ntiles; t += ncl, ++it) {
 			const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
 			const uint32_t rows_valid = min(uint32_t(kTqTileRows), a.n - t * kTqTileRows);
-			if (et == 0) {
-				issue_vw(it + kTqVwAhead);
+			if (warp == 2) {
+				if (elect_one_sync()) {
+					issue_vw(it + kTqVwAhead);
+				}
+				__syncwarp();
 			}
 			const float2* vw_tile = s_vw + (it % kTqVwSlots) * kTqTileRows;
 			if (q_ok) {  // the threshold other CTAs tightened: loaded one tile ago, consumed now

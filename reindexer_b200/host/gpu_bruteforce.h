@@ -74,10 +74,11 @@ public:
 		std::vector<float> dists(64);
 		std::vector<uint64_t> labels(64);
 		check(rxgpu_search_range(h_, queryData, radius, dists.size(), dists.data(), labels.data(), &total));
-		if (total > dists.size()) {
+		if (total > dists.size()) {  // the library retained the whole result of this thread's scan: fetch the tail, no rescan
+			const uint64_t have = dists.size();
 			dists.resize(total);
 			labels.resize(total);
-			check(rxgpu_search_range(h_, queryData, radius, dists.size(), dists.data(), labels.data(), &total));
+			check(rxgpu_last_range_results(have, total - have, dists.data() + have, labels.data() + have));
 		}
 		std::vector<pair_t> container;
 		container.reserve(total);

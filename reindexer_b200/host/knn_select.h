@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstring>
 #include <utility>
+#include <unordered_set>
 #include <vector>
 
 namespace rxgpu {
@@ -121,8 +122,10 @@ inline void selectPostprocess(const SelectParams& p, const std::vector<Hit>& res
 	}
 	if (p.isArray) {
 		size_t to = 0;
+		std::unordered_set<int32_t> seen;  // the reference dedups through a hash set too (float_vector_index.h:141-160)
+		seen.reserve(n);
 		for (size_t from = 0; from < n; ++from) {
-			if (std::find(rowIds.begin(), rowIds.begin() + to, rowIds[from]) == rowIds.begin() + to) {
+			if (seen.insert(rowIds[from]).second) {
 				rowIds[to] = rowIds[from];
 				ranks[to] = ranks[from];
 				++to;

@@ -35,16 +35,13 @@ def test_tc_path_is_bit_identical_to_exact_scan(metric, n, dim, nq, k):
     assert (d0.view(np.uint32) == d1.view(np.uint32)).all()
     assert st["tc_fallbacks"] == 0 and 0 < st["tc_candidates"] < nq * 4096
     # every kernel variant gives the same bits: 3 / 4 = queries in shared memory (1 CTA / CTA pair with TMA multicast),
-    # 5 / 6 = queries in TMEM with single CTAs / clusters of up to 4 CTAs (the default above uses CTA pairs),
-    # 7 = queries in TMEM, the CTA pair multiplies as one (tcgen05.mma.cta_group::2, half a row tile staged per SM),
-    # 8 / 9 / 10 = queries in TMEM, one accumulator of 128 rows (UMMA N = 128), CTA pairs / clusters of up to 4 / single CTAs
-    # 11 / 12 / 13 = queries in TMEM, four MMA issuers (two per tile), CTA pairs / clusters of up to 4 / single CTAs
-    for mode, kernel in ((3, 1), (4, 1), (5, 2), (6, 2), (7, 3), (8, 4), (9, 4), (10, 4), (11, 5), (12, 5), (13, 5)):
+    # 5 / 6 = queries in TMEM with single CTAs / clusters of up to 4 CTAs
+    for mode, kernel in ((3, 1), (4, 1), (5, 2), (6, 2)):
         gpu.set_tensor_core_filter(mode)
         d2, l2, c2 = gpu.search_knn(queries, k)
         s2 = rx.last_search_stats()
         if dim <= 768:
-            assert s2["tc_kernel"] == (kernel if kernel != 3 or nq > 128 else 2), (mode, s2)
+            assert s2["tc_kernel"] == kernel, (mode, s2)
         assert (l2 == l0).all() and (d2.view(np.uint32) == d0.view(np.uint32)).all(), mode
     assert st["tc_kernel"] == (2 if dim <= 768 else 1)
     if nq > 128 and dim <= 768:
