@@ -36,12 +36,18 @@ def lowrank(seed, n, dim, latent=32, noise=0.05):
     return out
 
 
-def run_hnsw(args):
+def hnsw_record(rows, queries=4096, threads=None, sweep=False):
+    """BASELINE configs[2] shape at `rows` rows: returns the sub-record bench.py embeds (workload, value, e2e, roofline, cpu_baseline)."""
     import reindexer_b200 as rx
     from oracle import oracle as O
 
+    class A:
+        pass
+
+    args = A()
+    args.rows, args.queries, args.sweep = rows, queries, sweep
     n, dim, k, ef, nq = args.rows, 768, 10, 128, args.queries
-    threads = os.cpu_count() or 1
+    threads = threads or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     vecs, labels = lowrank(1, n, dim), O.row_labels(n)
     t0 = time.perf_counter()
     ref = O.RefHnsw(O.COS, dim, n, M=16, ef_construction=200, seed=100, multithread=True)
@@ -96,15 +102,26 @@ def run_hnsw(args):
     ndist, nhops = float(st[:, 0].mean()), float(st[:, 1].mean())
     bytes_per_query = ndist * (dim * 4 + 4) + nhops * (4 + 8 * 16)
     peak, src = peak_hbm()
-    print(json.dumps({
-        "workload": f"HNSW float_vector, {n} x {dim} fp32, cosine, M=16 efC=200, ef_search={ef}, k={k}, batch={nq} (BASELINE configs[2] shape; "
-                    f"10M rows would need hours of CPU graph build)",
-        "qps_gpu_device_resident": qps_device, "qps_gpu_e2e": nq / gpu_s, "sweep_ctas_per_sm": sweep, "qps_reference_cpu": nq / cpu_s, "cpu_threads": threads, "speedup": cpu_s / gpu_s,
+    gpu.close()
+    return {
+        "workload": f"HNSW float_vector, {n} x {dim} fp32, cosine, M=16 efC=200, ef_search={ef}, k={k}, batch={nq} (BASELINE configs[2] shape at "
+                    f"{n} rows: the graph is built by the reference's CPU inserter, 10M rows would need hours)",
+        "metric": "HNSW KNN queries/s", "value": qps_device, "unit": "queries/s", "higher_is_better": True,
+        "e2e": {"value": nq / gpu_s, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * k * 12 + nq * 12},
+        "qps_gpu_device_resident": qps_device, "qps_gpu_e2e": nq / gpu_s, "sweep_ctas_per_sm": sweep,
+        "cpu_baseline": {"value": nq / cpu_s, "unit": "queries/s", "cores": threads, "kind": "reference",
+                         "sample": f"{nq} queries, {threads} threads, HierarchicalNSW::SearchKnn on the same graph"},
+        "speedup_e2e": cpu_s / gpu_s,
         "recall_at_10_gpu": rec_gpu, "recall_at_10_reference": rec_ref, "identical_top10_fraction": same,
         "dist_evals_per_query": ndist, "hops_per_query": nhops, "algorithmic_bytes_per_query": bytes_per_query,
-        "roofline": {"bound": "hbm (random 3 KB row gathers)", "achieved": bytes_per_query * qps_device / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": bytes_per_query * qps_device / 1e9 / peak, "peak_source": src},
-        "graph_build_s_reference_cpu": build_s, "data": "synthetic low-rank (latent 32) vectors"}))
+        "roofline": {"bound": "hbm (random 3 KB row gathers)", "kernel": "hnsw_search_kernel", "achieved": bytes_per_query * qps_device / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": bytes_per_query * qps_device / 1e9 / peak, "peak_source": src,
+                     "note": "algorithmic gather bytes; at this row count part of the set is L2-resident", "traffic": None},
+        "graph_build_s_reference_cpu": build_s, "data": "synthetic low-rank (latent 32) vectors"}
+
+
+def run_hnsw(args):
+    print(json.dumps(hnsw_record(args.rows, args.queries, sweep=args.sweep)))
 
 
 def run_ivf(args):
@@ -148,12 +165,18 @@ def run_ivf(args):
         "train_add_s_reference_cpu": build_s, "data": "synthetic low-rank vectors"}))
 
 
-def run_ft(args):
+def ft_record(ndocs):
+    """BASELINE configs[3] at `ndocs` documents: returns the sub-record bench.py embeds."""
     import reindexer_b200 as rx
     from ft_helpers import assert_same_merge
 
     from oracle import ft_oracle as F
 
+    class A:
+        pass
+
+    args = A()
+    args.docs = ndocs
     total = args.docs + 1
     rng = np.random.default_rng(7)
     words = (rng.poisson(100, size=total).astype(np.uint32) + 1).reshape(-1, 1)
@@ -186,17 +209,28 @@ def run_ft(args):
     top_gpu, top_ref = F.after_select_order(res)[:100], F.after_select_order(ref_res)[:100]
     assert (top_gpu == top_ref).all()
     peak, src = peak_hbm()
-    print(json.dumps({
+    return {
         "workload": f"ft_fast BM25 merge, {args.docs} docs, 3-term OR (df 10% / 1% / 0.1% = {npost} postings), merge_limit 20000, top-100 "
                     f"(BASELINE configs[3])",
-        "queries_per_s_gpu_e2e": 1.0 / gpu_s, "ms_per_query_gpu_e2e": gpu_s * 1e3, "ms_per_query_gpu_device": dev_ms / reps,
-        "ms_per_query_reference_cpu_merge_only": ref_ns / 1e6, "cpu_threads": 1, "speedup_vs_reference_merge": ref_ns / 1e9 / gpu_s,
+        "metric": "ft_fast merge queries/s", "value": 1e3 / (dev_ms / reps), "unit": "queries/s", "higher_is_better": True,
+        "e2e": {"value": 1.0 / gpu_s, "unit": "queries/s", "h2d_bytes_per_step": 512, "d2h_bytes_per_step": int(len(res)) * 12,
+                "ms_per_query": gpu_s * 1e3},
+        "ms_per_query_gpu_e2e": gpu_s * 1e3, "ms_per_query_gpu_device": dev_ms / reps,
+        "cpu_baseline": {"value": 1e9 / ref_ns, "unit": "queries/s", "cores": 1, "kind": "reference" if F.ref_available() else "port",
+                         "sample": "1 query, ft::Merger::Merge on one thread (the reference merges a query on one thread)",
+                         "ms_per_query": ref_ns / 1e6},
+        "speedup_vs_reference_merge": ref_ns / 1e9 / gpu_s,
         "merged_docs": int(len(res)), "preselected": st["preselected"], "launches": st["launches"], "postings_scanned": st["postings_scanned"],
         "identical_to_reference": True,
-        "roofline": {"bound": "hbm (posting streams + per-document gathers)", "achieved": st["algorithmic_bytes"] / (dev_ms / reps * 1e-3) / 1e9,
+        "roofline": {"bound": "hbm (posting streams + per-document gathers)", "kernel": "ft_rank_pass / ft_hist / ft_score_pass",
+                     "achieved": st["algorithmic_bytes"] / (dev_ms / reps * 1e-3) / 1e9,
                      "peak": peak, "unit": "GB/s", "frac": st["algorithmic_bytes"] / (dev_ms / reps * 1e-3) / 1e9 / peak, "peak_source": src,
-                     "algorithmic_bytes": st["algorithmic_bytes"]},
-        "data": "synthetic postings, Poisson(100) document lengths"}))
+                     "algorithmic_bytes": st["algorithmic_bytes"], "traffic": None},
+        "data": "synthetic postings, Poisson(100) document lengths"}
+
+
+def run_ft(args):
+    print(json.dumps(ft_record(args.docs)))
 
 
 if __name__ == "__main__":

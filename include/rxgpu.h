@@ -119,6 +119,34 @@ int rxgpu_tie_replay(uint32_t k, float dstar, uint32_t n_lower, const float* low
 					 const uint64_t* lower_label, uint32_t n_first, const float* first_dist, const uint64_t* first_gidx,
 					 const uint64_t* first_label, float* out_dist, uint64_t* out_label, uint32_t* out_count);
 
+/* ---------------------------------------------------------------- multi-GPU: one shard per GPU / rank, NCCL exchange, device merge
+ * The sharded equivalent of BruteforceSearch::SearchKnn over the concatenation of all shards (shard r holds the global internal rows
+ * [base_r, base_r + size_r), rows are appended shard by shard): ONE call per rank does the local fused scan + top-(k+1), one
+ * ncclAllGather of the per-shard lists (NVLink / NVSwitch), a device-side k-way merge under (distance, global row), and -- only when
+ * bit-equal distances straddle the k-th place -- the reference's heap tie rule replayed globally from the filter's candidate lists
+ * (no second pass over any shard) with a second, tiny all-gather.  Every rank gets the same answer, identical to what the reference
+ * returns for one index holding all rows.  NCCL is loaded with dlopen("libnccl.so.2") at the first rxgpu_comm_* call.
+ * Bootstrap: rank 0 calls rxgpu_comm_unique_id and ships the 128 bytes to the other ranks by any channel (Reindexer's own RPC; the
+ * tests use torch.distributed), then every rank calls rxgpu_comm_create.  nranks == 1 needs no id and no NCCL. */
+#define RXGPU_COMM_ID_BYTES 128
+typedef struct rxgpu_comm rxgpu_comm;
+int rxgpu_comm_unique_id(void* out_id /* RXGPU_COMM_ID_BYTES */);
+int rxgpu_comm_create(rxgpu_comm** out, int nranks, int rank, const void* id /* RXGPU_COMM_ID_BYTES, or NULL when nranks == 1 */, int device);
+void rxgpu_comm_destroy(rxgpu_comm*);
+int rxgpu_comm_rank(const rxgpu_comm*);
+int rxgpu_comm_size(const rxgpu_comm*);
+/* collective: every rank calls it with its own shard and the SAME queries / k.  queries: nq x dim floats, host pointer
+ * (queries_on_device == 0) or device pointer on the shard's GPU (!= 0).  Outputs: host buffers nq x k, best first, reference tie rule
+ * applied globally; out_count[q] = min(k, total rows). */
+int rxgpu_sharded_search_knn(rxgpu_comm*, const rxgpu_index* shard, uint32_t nq, const float* queries, int queries_on_device, uint32_t k,
+							 float* out_dist, uint64_t* out_label, uint32_t* out_count);
+/* the device-side merge alone: d_payloads = nshards contributions of rxgpu_shard_payload_bytes(nq, k1) bytes each, laid out as
+ * [dist f32 nq*k1][idx u32 nq*k1][label u64 nq*k1][count u32 nq][shard size u64] (sections 16-byte aligned) -- what
+ * rxgpu_search_knn_device writes; outputs (device) as rxgpu_merge_shards, ties NOT yet ordered by label. */
+uint64_t rxgpu_shard_payload_bytes(uint32_t nq, uint32_t k1);
+int rxgpu_merge_shards_device(uint32_t nshards, uint32_t nq, uint32_t k, uint32_t k1, const void* d_payloads, float* d_out_dist,
+							  uint64_t* d_out_gidx, uint64_t* d_out_label, uint32_t* d_out_count, uint8_t* d_need_tie, void* stream);
+
 /* ---------------------------------------------------------------- FloatVectorIndex::Select equivalent
  * HnswIndexBase<BruteforceSearch>::search + select/selectRaw   core/index/float_vector/hnsw_index.cc:160-191, 206-229, 232-288
  * query normalisation for Cosine (tools/normalize.h:16-22), k and/or radius, worst->best drain, sign flip for IP/Cosine,
@@ -285,7 +313,8 @@ typedef struct {
 	uint32_t launches;
 	uint32_t passes;
 	uint32_t query_tile;
-	uint32_t tie_replays;
+	uint32_t tie_replays;       /* queries whose k-th place was a bit-equal tie: the reference's heap rule was replayed */
+	uint32_t tie_from_lists;    /* ... of which answered from the filter's candidate lists (no second pass over the rows) */
 	uint64_t algorithmic_bytes; /* SURVEY.md §8d definition: passes x (N*D*4 [+N*4 for Cosine] + QT*D*4 + QT*k*12) */
 	uint32_t scan_launches;     /* with rxgpu_set_profile(1): launches of the dominant kernel timed ... */
 	float scan_kernel_ms;       /* ... and their summed device time (CUDA events on the launching stream) */
@@ -293,14 +322,16 @@ typedef struct {
 	uint32_t tc_fallbacks;      /* queries whose candidate list overflowed and were answered by the exact scan */
 	uint64_t tc_candidates;     /* rows re-ranked exactly */
 	uint32_t tc_cluster;        /* CTAs per cluster in the filter kernel (row tiles are TMA-multicast inside a cluster) */
-	uint32_t tc_kernel;         /* 1 = knn_tc_filter (queries in shared memory), 2 = knn_tc_filter_q (queries in TMEM) */
+	uint32_t tc_kernel;         /* 1 = knn_tc_filter (queries in shared memory), 2 = knn_tc_filter_q (queries in TMEM), 3 = knn_tc_filter_k
+								 * (K-split query block: TMEM + shared memory, UMMA N = 128) */
 } rxgpu_search_stats;
 void rxgpu_last_search_stats(rxgpu_search_stats* out);
 /* large query batches: bf16 tensor-core filter + exact fp32 re-rank (results identical to the exact scan).
  * mode 0 = automatic (batches >= 64 queries on >= 100k rows, k <= 15), 1 = whenever possible, 2 = never;
- * 3..6 force kernel variants for tests/benchmarks (all give the same bits): 3 / 4 = first-generation kernel (queries in shared
- * memory) with 1 CTA / a CTA pair per row tile; 5 / 6 = knn_tc_filter_q (queries in TMEM) with single CTAs / clusters of up to 4
- * (the default).  DESIGN.md section 9 has the measurements. */
+ * 3..8 force kernel variants for tests/benchmarks (all give the same bits): 3 / 4 = first-generation kernel (queries in shared
+ * memory) with 1 CTA / a CTA pair per row tile; 5 / 6 = knn_tc_filter_q (query block in TMEM, accumulators of 64 rows) with single
+ * CTAs / clusters of up to 4; 7 / 8 = knn_tc_filter_k (K-split query block, accumulators of 128 rows; the default) with single CTAs /
+ * clusters of up to 4.  DESIGN.md section 9 has the measurements. */
 int rxgpu_set_tensor_core_filter(rxgpu_index*, int mode);
 /* process-wide switch: bracket every scan-kernel launch with CUDA events (used by bench.py for the roofline figure) */
 int rxgpu_set_profile(int on);

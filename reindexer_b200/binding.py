@@ -72,7 +72,7 @@ FT_MERGE_INFO_DTYPE = np.dtype([("id", np.int32), ("proc", np.float32), ("field"
 
 
 class SearchStats(C.Structure):
-    _fields_ = [("launches", C.c_uint32), ("passes", C.c_uint32), ("query_tile", C.c_uint32), ("tie_replays", C.c_uint32),
+    _fields_ = [("launches", C.c_uint32), ("passes", C.c_uint32), ("query_tile", C.c_uint32), ("tie_replays", C.c_uint32), ("tie_from_lists", C.c_uint32),
                 ("algorithmic_bytes", C.c_uint64), ("scan_launches", C.c_uint32), ("scan_kernel_ms", C.c_float),
                 ("tc_used", C.c_uint32), ("tc_fallbacks", C.c_uint32), ("tc_candidates", C.c_uint64), ("tc_cluster", C.c_uint32), ("tc_kernel", C.c_uint32)]
 
@@ -99,6 +99,16 @@ _SIGNATURES = {
     "rxgpu_index_device": (C.c_int, [C.c_void_p]),
     "rxgpu_search_knn": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, C.c_uint32, _f32p, _u64p, _u32p]),
     "rxgpu_search_range": (C.c_int, [C.c_void_p, _f32p, C.c_float, C.c_uint64, _f32p, _u64p, _u64p]),
+    "rxgpu_last_range_results": (C.c_int, [C.c_uint64, C.c_uint64, _f32p, _u64p]),
+    "rxgpu_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "rxgpu_comm_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "rxgpu_comm_destroy": (None, [C.c_void_p]),
+    "rxgpu_comm_rank": (C.c_int, [C.c_void_p]),
+    "rxgpu_comm_size": (C.c_int, [C.c_void_p]),
+    "rxgpu_sharded_search_knn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_uint32, _f32p, _u64p, _u32p]),
+    "rxgpu_shard_payload_bytes": (C.c_uint64, [C.c_uint32, C.c_uint32]),
+    "rxgpu_merge_shards_device": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]),
     "rxgpu_search_knn_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p]),
     "rxgpu_search_tie_rows_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -361,6 +371,50 @@ class GpuBruteforceSearch:
     def set_tensor_core_filter(self, mode: int):
         """0 = auto, 1 = whenever possible, 2 = never (exact fp32 scan only)"""
         _check(self._lib.rxgpu_set_tensor_core_filter(self._h, mode))
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    _check(lib().rxgpu_comm_unique_id(buf))
+    return buf.raw
+
+
+class ShardComm:
+    """rxgpu_comm: this rank's end of the NCCL communicator the sharded search exchanges its per-shard lists over."""
+
+    def __init__(self, nranks: int, rank: int, comm_id: bytes | None, device: int):
+        self._lib = lib()
+        self._h = C.c_void_p()
+        idbuf = C.create_string_buffer(comm_id, COMM_ID_BYTES) if comm_id is not None else None
+        _check(self._lib.rxgpu_comm_create(C.byref(self._h), nranks, rank, idbuf, device))
+
+    def close(self):
+        if self._h:
+            self._lib.rxgpu_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def search_knn(self, shard: "GpuBruteforceSearch", queries, k: int, nq: int | None = None):
+        """queries: host ndarray [nq, dim] or a device pointer (int) with nq given.  Collective: every rank calls it."""
+        if isinstance(queries, np.ndarray):
+            q = np.ascontiguousarray(queries, np.float32)
+            nq, qp, on_dev = q.shape[0], q.ctypes.data_as(C.c_void_p), 0
+        else:
+            qp, on_dev = C.c_void_p(int(queries)), 1
+        kk = max(k, 1)
+        od = np.zeros((nq, kk), np.float32)
+        ol = np.zeros((nq, kk), np.uint64)
+        oc = np.zeros(nq, np.uint32)
+        _check(self._lib.rxgpu_sharded_search_knn(self._h, shard._h, nq, qp, on_dev, k, _p(od, _f32p), _p(ol, _u64p), _p(oc, _u32p)))
+        return od, ol, oc
 
 
 def merge_shards(k, dist, idx, label, count, shard_base):

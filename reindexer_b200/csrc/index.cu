@@ -21,6 +21,7 @@
 #include "knn_scan.cuh"
 #include "knn_tc.cuh"
 #include "knn_tc_q.cuh"
+#include "knn_tc_k.cuh"
 
 using namespace rxgpu;
 
@@ -324,27 +325,34 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 	g_stats.launches += 2;
 	const uint32_t ntiles = uint32_t((ix->size + kTcTileRows - 1) / kTcTileRows);
 	bool launched = false;
-	if (ix->tc_variant == 0 && kchunks <= kTqMaxKchunks) {
-		// second-generation filter: query block in TMEM, deep TMA ring, row tiles multicast to a cluster of up to 4 CTAs
+	if ((ix->tc_variant == 0 || ix->tc_variant == 5) && kchunks <= kTqMaxKchunks) {
+		// query block in tensor memory, deep TMA ring, row tiles multicast to a cluster of up to 4 CTAs.  Default: knn_tc_filter_k
+		// (K-split query block, accumulators of 128 rows); tc_variant 5: knn_tc_filter_q (whole block in TMEM, accumulators of 64 rows)
+		using TqKernel = void (*)(TqArgs);
+		const bool ksplit = ix->tc_variant == 0;
+		const TqKernel kernels[3] = {ksplit ? knn_tc_filter_k<1> : knn_tc_filter_q<1>, ksplit ? knn_tc_filter_k<2> : knn_tc_filter_q<2>,
+									 ksplit ? knn_tc_filter_k<4> : knn_tc_filter_q<4>};
+		const uint32_t tileRows = ksplit ? kTkTileRows : kTqTileRows;
+		auto smemOf = [&](uint32_t st) { return ksplit ? tk_smem_bytes(st) : tq_smem_bytes(st); };
 		const uint32_t qblocks = (nq + kTqQueries - 1) / kTqQueries;
 		uint32_t stages = 2;
-		while (tq_smem_bytes(stages + 1) <= kTcSmemLimit && stages < 64) {
+		while (smemOf(stages + 1) <= kTcSmemLimit && stages < 64) {
 			++stages;
 		}
-		const size_t smem = tq_smem_bytes(stages);
-		RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_q<1>, ix->device, int(kTcSmemLimit)));
-		RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_q<2>, ix->device, int(kTcSmemLimit)));
-		RX_CUDA(raiseSmemCeilingOnce(knn_tc_filter_q<4>, ix->device, int(kTcSmemLimit)));
+		const size_t smem = smemOf(stages);
+		for (const TqKernel kfn : kernels) {
+			RX_CUDA(raiseSmemCeilingOnce(kfn, ix->device, int(kTcSmemLimit)));
+		}
 		// a cluster of C CTAs reads every row tile from HBM once for C x 128 queries (TMA multicast)
 		const uint32_t clusterMax = ix->tc_cluster_max ? ix->tc_cluster_max : 4u;
 		int cluster = qblocks >= 3 ? 4 : (qblocks == 2 ? 2 : 1);
 		cluster = std::min<int>(cluster, int(clusterMax));
-		const uint32_t qtiles = uint32_t((ix->size + kTqTileRows - 1) / kTqTileRows);
+		const uint32_t qtiles = uint32_t((ix->size + tileRows - 1) / tileRows);
 		unsigned grid = 0;
 		for (;;) {  // how many clusters of this size can be resident at once (GPC boundaries strand SMs for size 4)
 			cudaLaunchConfig_t cfg{};
 			cfg.gridDim = dim3(unsigned(ix->sm_count) / cluster * cluster);
-			cfg.blockDim = dim3(kTqThreads);
+			cfg.blockDim = dim3(ksplit ? kTkThreads : kTqThreads);
 			cfg.dynamicSmemBytes = smem;
 			cudaLaunchAttribute attr[1];
 			attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -354,9 +362,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			cfg.attrs = attr;
 			cfg.numAttrs = 1;
 			int maxClusters = 0;
-			cudaError_t e = cluster == 4   ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q<4>, &cfg)
-							: cluster == 2 ? cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q<2>, &cfg)
-										   : cudaOccupancyMaxActiveClusters(&maxClusters, knn_tc_filter_q<1>, &cfg);
+			const cudaError_t e = cudaOccupancyMaxActiveClusters(&maxClusters, kernels[cluster == 4 ? 2 : (cluster == 2 ? 1 : 0)], &cfg);
 			if (e == cudaSuccess && maxClusters > 0) {
 				grid = unsigned(std::min<uint64_t>(uint64_t(maxClusters), std::max<uint32_t>(qtiles, 1))) * cluster;
 				break;
@@ -411,7 +417,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			}
 			cudaLaunchConfig_t cfg{};
 			cfg.gridDim = dim3(grid);
-			cfg.blockDim = dim3(kTqThreads);
+			cfg.blockDim = dim3(ksplit ? kTkThreads : kTqThreads);
 			cfg.dynamicSmemBytes = smem;
 			cfg.stream = st;
 			cudaLaunchAttribute attr[1];
@@ -421,13 +427,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			attr[0].val.clusterDim.z = 1;
 			cfg.attrs = attr;
 			cfg.numAttrs = 1;
-			if (cluster == 4) {
-				RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q<4>, a));
-			} else if (cluster == 2) {
-				RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q<2>, a));
-			} else {
-				RX_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_q<1>, a));
-			}
+			RX_CUDA(cudaLaunchKernelEx(&cfg, kernels[cluster == 4 ? 2 : (cluster == 2 ? 1 : 0)], a));
 			RX_CUDA(cudaGetLastError());
 			if (e0) {
 				RX_CUDA(cudaEventRecord(e1, st));
@@ -450,7 +450,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			}
 		}
 		g_stats.tc_cluster = uint32_t(cluster);
-		g_stats.tc_kernel = 2;
+		g_stats.tc_kernel = ksplit ? 3 : 2;
 		g_stats.query_tile = uint32_t(kTqQueries * cluster);
 		g_stats.algorithmic_bytes += uint64_t((qblocks + cluster - 1) / cluster) * (uint64_t(ix->size) * pitchBf * 2 + uint64_t(ix->size) * 4) +
 									 uint64_t(nq) * pitchBf * 2;
@@ -568,19 +568,88 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			}
 		}
 	}
+	ws.tc_lists_valid = true;
+	ws.tc_lists_nq = nq;
+	ws.tc_lists_version = ix->version;
 	g_stats.tc_used = 1;
 	g_stats.tc_candidates = cands;
 	g_stats.algorithmic_bytes += cands * (uint64_t(ix->dim) * 4 + 4);
 	return 0;
 }
 
+}  // namespace
+
+namespace rxgpu {
 int scanTopK(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, const float* d_queries, uint32_t nq, uint32_t k1, int mode, float bound,
 			 float* d_out_dist, uint32_t* d_out_idx, uint64_t* d_out_label, uint32_t* d_out_count) {
 	if (tcEligible(ix, nq, k1, mode)) {
 		return scanTopKTensorCore(ix, ws, st, d_queries, nq, k1, d_out_dist, d_out_idx, d_out_label, d_out_count);
 	}
+	if (mode == kModeTopK) {
+		ws.tc_lists_valid = false;
+	}
 	return scanTopKExact(ix, ws, st, d_queries, nq, k1, mode, bound, d_out_dist, d_out_idx, d_out_label, d_out_count);
 }
+
+int tieRowsAfterScan(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, const float* d_queries, uint32_t nsel, const uint32_t* sel,
+					 const float* dstar, uint32_t k, float* d_out_dist, uint32_t* d_out_idx, uint64_t* d_out_label, uint32_t* d_out_count) {
+	if (nsel == 0) {
+		return 0;
+	}
+	bool fromLists = ws.tc_lists_valid && ws.tc_lists_version == ix->version && k <= kTcMaxK1;
+	for (uint32_t i = 0; fromLists && i < nsel; ++i) {  // a query whose list overflowed was answered by the exact scan: no list
+		fromLists = sel[i] < ws.tc_lists_nq && ws.h_cand_count.p[sel[i]] <= kTcCandCap;
+	}
+	if (!fromLists) {
+		for (uint32_t i = 0; i < nsel; ++i) {
+			if (int rc = scanTopKExact(ix, ws, st, d_queries + size_t(sel[i]) * ix->dim, 1, k, kModeTieRows, dstar[i], d_out_dist + size_t(i) * k,
+									   d_out_idx + size_t(i) * k, d_out_label ? d_out_label + size_t(i) * k : nullptr, d_out_count + i)) {
+				return rc;
+			}
+		}
+		g_stats.tie_replays += nsel;
+		return 0;
+	}
+	RX_CUDA(ws.d_sel.ensure(nsel));
+	RX_CUDA(ws.d_selbound.ensure(nsel));
+	RX_CUDA(ws.d_lists.ensure(size_t(nsel) * k));
+	RX_CUDA(cudaMemcpyAsync(ws.d_sel.p, sel, size_t(nsel) * 4, cudaMemcpyHostToDevice, st));
+	RX_CUDA(cudaMemcpyAsync(ws.d_selbound.p, dstar, size_t(nsel) * 4, cudaMemcpyHostToDevice, st));
+	const size_t rsmem = size_t((ix->dim + 127) / 128) * 512 + size_t(kScanWarps) * (k + kCandBuf) * 8;
+	const float* norms = ix->metric == RXGPU_COS ? ix->d_norms : nullptr;
+	if (ix->metric == RXGPU_L2) {
+		RX_CUDA(raiseSmemCeilingOnce(knn_rerank<true>, ix->device, kScanSmemBudget));
+		knn_rerank<true><<<nsel, kScanThreads, rsmem, st>>>(ix->d_rows, ix->pitch, ix->dim, norms, d_queries, ws.d_cand_rows.p, ws.d_cand_count.p,
+															 kTcCandCap, k, ws.d_lists.p, ws.d_sel.p, ws.d_selbound.p);
+	} else {
+		RX_CUDA(raiseSmemCeilingOnce(knn_rerank<false>, ix->device, kScanSmemBudget));
+		knn_rerank<false><<<nsel, kScanThreads, rsmem, st>>>(ix->d_rows, ix->pitch, ix->dim, norms, d_queries, ws.d_cand_rows.p, ws.d_cand_count.p,
+															  kTcCandCap, k, ws.d_lists.p, ws.d_sel.p, ws.d_selbound.p);
+	}
+	MergeArgs m{};
+	m.lists = ws.d_lists.p;
+	m.labels = ix->d_labels;
+	m.out_dist = d_out_dist;
+	m.out_idx = d_out_idx;
+	m.out_label = d_out_label;
+	m.out_count = d_out_count;
+	m.nlists = 1;
+	m.qt = nsel;
+	m.k1 = k;
+	m.q_offset = 0;
+	m.out_stride = k;
+	m.out_offset = 0;
+	m.mode = kModeTieRows;
+	knn_merge_lists<<<nsel, 256, 0, st>>>(m);
+	RX_CUDA(cudaGetLastError());
+	g_stats.launches += 2;
+	g_stats.tie_replays += nsel;
+	g_stats.tie_from_lists += nsel;
+	return 0;
+}
+}  // namespace rxgpu
+
+namespace {
 
 int normsForRange(rxgpu_index* ix, uint64_t begin, uint64_t end) {
 	if (ix->metric != RXGPU_COS || begin >= end) {
@@ -937,12 +1006,12 @@ int rxgpu_set_query_tile(rxgpu_index* ix, uint32_t qt) {
 	return 0;
 }
 int rxgpu_set_tensor_core_filter(rxgpu_index* ix, int mode) {
-	if (!ix || mode < 0 || mode > 6) {
-		return fail(RXGPU_ERR_PARAMS, "rxgpu: tensor-core filter mode must be in 0..6");
+	if (!ix || mode < 0 || mode > 8) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: tensor-core filter mode must be in 0..8");
 	}
 	ix->tc_mode = uint32_t(mode >= 3 ? 1 : mode);
-	ix->tc_variant = (mode == 3 || mode == 4) ? uint32_t(mode) : 0u;
-	ix->tc_cluster_max = mode == 5 ? 1u : (mode == 6 ? 4u : 0u);
+	ix->tc_variant = (mode == 3 || mode == 4) ? uint32_t(mode) : ((mode == 5 || mode == 6) ? 5u : 0u);
+	ix->tc_cluster_max = (mode == 5 || mode == 7) ? 1u : ((mode == 6 || mode == 8) ? 4u : 0u);
 	return 0;
 }
 int rxgpu_set_profile(int on) {
@@ -1123,31 +1192,35 @@ static int searchKnnHost(const rxgpu_index* ix, uint32_t nq, const float* querie
 			orderTiesByLabel(res);
 			continue;
 		}
-		// replay the reference's heap tie rule: fetch the first kEff rows (internal order) with dist <= dstar
+		// replay the reference's heap tie rule: fetch the first kEff rows (internal order) with dist <= dstar -- from the filter's
+		// candidate lists when this batch went through the tensor-core path (no second pass over the rows)
 		const float dstar = d[kEff - 1];
 		std::vector<Hit> lower;
 		for (uint32_t j = 0; j < kEff && d[j] < dstar; ++j) {
 			lower.push_back(Hit{d[j], ii[j], ll[j]});
 		}
-		if (int rc = scanTopK(ix, ws, st, ws.d_queries.p + size_t(q) * ix->dim, 1, kEff, kModeTieRows, dstar, ws.d_out_dist.p,
-							  ws.d_out_idx.p, ws.d_out_label.p, ws.d_out_count.p)) {
+		RX_CUDA(ws.d_tie_dist.ensure(kEff));
+		RX_CUDA(ws.d_tie_idx.ensure(kEff));
+		RX_CUDA(ws.d_tie_label.ensure(kEff));
+		RX_CUDA(ws.d_tie_count.ensure(1));
+		if (int rc = tieRowsAfterScan(ix, ws, st, ws.d_queries.p, 1, &q, &dstar, kEff, ws.d_tie_dist.p, ws.d_tie_idx.p, ws.d_tie_label.p,
+									  ws.d_tie_count.p)) {
 			return rc;
 		}
 		std::vector<float> td(kEff);
 		std::vector<uint32_t> ti(kEff);
 		std::vector<uint64_t> tl(kEff);
 		uint32_t tc = 0;
-		RX_CUDA(cudaMemcpyAsync(td.data(), ws.d_out_dist.p, kEff * sizeof(float), cudaMemcpyDeviceToHost, st));
-		RX_CUDA(cudaMemcpyAsync(ti.data(), ws.d_out_idx.p, kEff * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-		RX_CUDA(cudaMemcpyAsync(tl.data(), ws.d_out_label.p, kEff * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-		RX_CUDA(cudaMemcpyAsync(&tc, ws.d_out_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+		RX_CUDA(cudaMemcpyAsync(td.data(), ws.d_tie_dist.p, kEff * sizeof(float), cudaMemcpyDeviceToHost, st));
+		RX_CUDA(cudaMemcpyAsync(ti.data(), ws.d_tie_idx.p, kEff * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+		RX_CUDA(cudaMemcpyAsync(tl.data(), ws.d_tie_label.p, kEff * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+		RX_CUDA(cudaMemcpyAsync(&tc, ws.d_tie_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
 		RX_CUDA(cudaStreamSynchronize(st));
 		std::vector<Hit> first;
 		for (uint32_t j = 0; j < std::min(tc, kEff); ++j) {
 			first.push_back(Hit{td[j], ti[j], tl[j]});
 		}
 		res = tieReplay(kEff, dstar, lower, first);
-		g_stats.tie_replays += 1;
 	}
 	return 0;
 }

@@ -144,6 +144,16 @@ struct Workspace {
 	PinBuf<uint64_t> h_out_label;
 	PinBuf<uint32_t> h_out_count;
 	PinBuf<uint64_t> h_range;
+	// state of the last scanTopK on this workspace: when the tensor-core filter answered it, the per-query candidate lists
+	// (d_cand_rows / h_cand_count) hold every row at or below each query's k1-th distance -- tieRowsAfterScan reads them
+	bool tc_lists_valid = false;
+	uint32_t tc_lists_nq = 0;
+	uint64_t tc_lists_version = 0;
+	DevBuf<uint32_t> d_sel;
+	DevBuf<float> d_selbound;
+	DevBuf<float> d_tie_dist;
+	DevBuf<uint32_t> d_tie_idx, d_tie_count;
+	DevBuf<uint64_t> d_tie_label;
 	~Workspace() {
 		if (stream) {
 			cudaStreamDestroy(stream);
@@ -197,7 +207,7 @@ struct rxgpu_index {
 	mutable uint32_t pitch_bf = 0;
 	mutable uint64_t shadow_version = ~0ull;
 	uint32_t tc_mode = 0;  // 0 auto, 1 force on, 2 off
-	uint32_t tc_variant = 0;      // 0 = query-in-TMEM kernel when the dimension allows; 3 / 4 = first-generation kernel (1 CTA / CTA pair)
+	uint32_t tc_variant = 0;      // 0 = knn_tc_filter_k (K-split query block) when the dimension allows; 5 = knn_tc_filter_q; 3 / 4 = first-generation kernel (1 CTA / CTA pair)
 	uint32_t tc_cluster_max = 0;  // 0 = up to 4 CTAs per cluster
 
 	~rxgpu_index() {
@@ -255,6 +265,17 @@ struct WsLease {
 		idx->ws_free.emplace_back(std::move(ws));
 	}
 };
+
+// index.cu -- shared with shard.cu
+// Top-k1 rows per query under (dist, internal row) [kModeTopK], or the first k1 rows in internal order with dist <= bound
+// [kModeTieRows, one query]; large batches go through the tensor-core filter + exact re-rank (same bits).  Device in / out.
+int scanTopK(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, const float* d_queries, uint32_t nq, uint32_t k1, int mode, float bound,
+			 float* d_out_dist, uint32_t* d_out_idx, uint64_t* d_out_label, uint32_t* d_out_count);
+// After a scanTopK(kModeTopK) of `d_queries` on the SAME workspace: for the selected queries sel[i] the first k rows in internal order
+// with dist <= dstar[i] (what the reference's tie rule needs, SURVEY.md 8a rule 2), [nsel][k] device outputs.  Served from the
+// filter's candidate lists when they exist (no second pass over the rows), else by one kModeTieRows scan per selected query.
+int tieRowsAfterScan(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, const float* d_queries, uint32_t nsel, const uint32_t* sel,
+					 const float* dstar, uint32_t k, float* d_out_dist, uint32_t* d_out_idx, uint64_t* d_out_label, uint32_t* d_out_count);
 
 inline int checkIndex(const rxgpu_index* ix) {
 	if (!ix) {

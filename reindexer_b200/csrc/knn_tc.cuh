@@ -503,10 +503,16 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 template <bool kIsL2>
 __global__ void __launch_bounds__(kScanThreads) knn_rerank(const float* rows, uint32_t pitch, uint32_t dim, const float* norm_coefs,
 															const float* queries, const uint32_t* cand_rows, const unsigned int* cand_count,
-															uint32_t cand_cap, uint32_t k1, uint64_t* lists /* [nq][k1] */) {
+															uint32_t cand_cap, uint32_t k1, uint64_t* lists /* [gridDim.x][k1] */,
+															const uint32_t* qsel = nullptr, const float* tie_bound = nullptr) {
+	// qsel: CTA b serves query qsel[b] (default: query b).  tie_bound != nullptr = tie mode (kModeTieRows): among the candidates
+	// with dist <= tie_bound[b], the first k1 in internal row order (key = row << 32 | ord(dist)) -- every row at or below the k-th
+	// distance is a candidate, so this replaces a second scan of the whole shard when the reference's tie rule must be replayed.
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t q = blockIdx.x;
+	const uint32_t q = qsel ? qsel[blockIdx.x] : blockIdx.x;
+	const bool tie = tie_bound != nullptr;
+	const float bound = tie ? tie_bound[blockIdx.x] : 0.f;
 	const uint32_t nch = (dim + 127u) / 128u, dp4 = nch * 32u, pitch4 = pitch >> 2;
 	const uint32_t m = k1 + kCandBuf;
 	float4* sq4 = reinterpret_cast<float4*>(smem_raw);
@@ -559,7 +565,7 @@ __global__ void __launch_bounds__(kScanThreads) knn_rerank(const float* rows, ui
 		if (!kIsL2 && norm_coefs != nullptr) {
 			dist *= norm_coefs[row];
 		}
-		const uint64_t key = make_key(dist, row);
+		const uint64_t key = !tie ? make_key(dist, row) : (dist <= bound ? ((uint64_t(row) << 32) | float_ord(dist)) : kKeyNone);
 		if (key < thr) {  // warp-uniform
 			if (lane == 0) {
 				wkeys[k1 + cnt] = key;
@@ -595,7 +601,7 @@ __global__ void __launch_bounds__(kScanThreads) knn_rerank(const float* rows, ui
 				best = ok < best ? ok : best;
 			}
 			if (lane == 0) {
-				lists[size_t(q) * k1 + r] = best;
+				lists[size_t(blockIdx.x) * k1 + r] = best;
 			}
 			last = best;
 			first = false;

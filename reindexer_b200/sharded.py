@@ -32,6 +32,21 @@ class ShardedBruteforceSearch:
         self._local_search = local_search or self._device_search
         self._local_tie_rows = local_tie_rows or self._device_tie_rows
         self.replay_ties = True  # the brute-force map reproduces the reference's heap tie rule; approximate maps have none
+        # On GPUs the whole search is ONE C-ABI call per rank (rxgpu_sharded_search_knn: local scan, ncclAllGather, device merge, tie
+        # replay from the filter's candidate lists); torch.distributed only ships the NCCL unique id once.  The Python exchange below
+        # remains for the CPU (gloo) tests of the merge / tie logic and for maps without a C-side sharded call (HNSW shards).
+        self.comm = None
+        if local_search is None and local_tie_rows is None and type(self) is ShardedBruteforceSearch and self.device.type == "cuda":
+            dev = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            if self.world > 1:
+                ident = torch.zeros(B.COMM_ID_BYTES, dtype=torch.uint8)
+                if self.rank == 0:
+                    ident = torch.frombuffer(bytearray(B.comm_unique_id()), dtype=torch.uint8).clone()
+                ident = ident.to(self.device)
+                dist.broadcast(ident, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+                self.comm = B.ShardComm(self.world, self.rank, bytes(ident.cpu().numpy().tobytes()), dev)
+            else:
+                self.comm = B.ShardComm(1, 0, None, dev)
 
     # -- plumbing ----------------------------------------------------------------------------------------------------------
     def _all_gather_small(self, t: torch.Tensor) -> torch.Tensor:
@@ -65,6 +80,12 @@ class ShardedBruteforceSearch:
     def search_knn(self, queries, k: int):
         """queries: host ndarray [nq, dim] or device tensor (identical on every rank).  Returns (dist, label, count) on every
         rank, best-first, reference tie rule applied globally."""
+        if self.comm is not None:  # the product path: one C-ABI call per rank
+            if isinstance(queries, np.ndarray):
+                return self.comm.search_knn(self.idx, queries, k)
+            assert queries.is_cuda and queries.dtype == torch.float32 and queries.is_contiguous()
+            torch.cuda.current_stream().synchronize()  # the library runs on its own stream: the queries must be complete
+            return self.comm.search_knn(self.idx, queries.data_ptr(), k, nq=queries.shape[0])
         if isinstance(queries, np.ndarray):
             d_queries = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32)).to(self.device, non_blocking=True)
         else:
