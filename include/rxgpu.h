@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RXGPU_ABI_VERSION 1
+#define RXGPU_ABI_VERSION 2
 
 /* subset of reindexer::ErrorCode (core/type_consts.h:136-181) that this library produces */
 enum { RXGPU_OK = 0, RXGPU_ERR_PARAMS = 3, RXGPU_ERR_LOGIC = 4, RXGPU_ERR_NOT_FOUND = 13, RXGPU_ERR_SYSTEM = 37 };
@@ -254,6 +254,7 @@ typedef struct { /* FTConfig members read by the merger */
 	double distance_boost, distance_weight, full_match_boost;
 	uint32_t nfields;
 	const rxgpu_ft_field_config* fields;
+	double summation_ranks_by_fields_ratio; /* FTConfig::summationRanksByFieldsRatio (ftconfig.h:210): 0 = off (the default) */
 } rxgpu_ft_config;
 typedef struct { /* one TermResults */
 	int32_t op; /* OpType: 1 = OpOr, 2 = OpAnd, 3 = OpNot */
@@ -263,6 +264,7 @@ typedef struct { /* one TermResults */
 	uint32_t nsubterms;
 	const uint32_t* postings; /* ids returned by rxgpu_ft_add_postings */
 	const float* procs;
+	const uint8_t* need_sum_rank; /* nfields flags FtDslFieldOpts::needSumRank (ftdsl.h:15), or NULL = all false; at most 16 set */
 } rxgpu_ft_term;
 typedef struct { /* ft::MergeInfo */
 	int32_t id;

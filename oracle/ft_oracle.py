@@ -32,12 +32,13 @@ class FieldConfig(C.Structure):
 class Config(C.Structure):
     _fields_ = [("merge_limit", C.c_uint32), ("min_rank", C.c_int32), ("bm25_k1", C.c_double), ("bm25_b", C.c_double),
                 ("bm25_type", C.c_int32), ("distance_boost", C.c_double), ("distance_weight", C.c_double),
-                ("full_match_boost", C.c_double), ("nfields", C.c_uint32), ("fields", C.POINTER(FieldConfig))]
+                ("full_match_boost", C.c_double), ("nfields", C.c_uint32), ("fields", C.POINTER(FieldConfig)),
+                ("summation_ranks_by_fields_ratio", C.c_double)]
 
 
 class Term(C.Structure):
     _fields_ = [("op", C.c_int32), ("boost", C.c_float), ("term_len_boost", C.c_float), ("field_boosts", _f32p), ("nsubterms", C.c_uint32),
-                ("postings", _u32p), ("procs", _f32p)]
+                ("postings", _u32p), ("procs", _f32p), ("need_sum_rank", _u8p)]
 
 
 class MergeInfo(C.Structure):
@@ -70,7 +71,7 @@ class FtProblem:
         self.lists = []  # (doc_ids, pos_begin, positions)
         self.terms = []  # dict(op, boost, term_len_boost, field_boosts, postings, procs)
         self.cfg = dict(merge_limit=20000, min_rank=5, bm25_k1=2.0, bm25_b=0.75, bm25_type=0, distance_boost=1.0, distance_weight=0.5,
-                        full_match_boost=1.1)
+                        full_match_boost=1.1, summation_ranks_by_fields_ratio=0.0)
         self.field_cfg = [dict(bm25_boost=1.0, bm25_weight=0.1, term_len_boost=1.0, term_len_weight=0.3, position_boost=1.0,
                                position_weight=0.1) for _ in range(self.nfields)]
 
@@ -91,10 +92,11 @@ class FtProblem:
                            np.ascontiguousarray(positions, np.uint32)))
         return len(self.lists) - 1
 
-    def add_term(self, subterms, op=OP_OR, boost=1.0, term_len_boost=1.0, field_boosts=None):
+    def add_term(self, subterms, op=OP_OR, boost=1.0, term_len_boost=1.0, field_boosts=None, need_sum_rank=None):
         """subterms: list of (list id, proc)"""
         fb = np.ones(self.nfields, np.float32) if field_boosts is None else np.ascontiguousarray(field_boosts, np.float32)
-        self.terms.append(dict(op=op, boost=boost, term_len_boost=term_len_boost, field_boosts=fb,
+        ns = None if need_sum_rank is None else np.ascontiguousarray(need_sum_rank, np.uint8)
+        self.terms.append(dict(op=op, boost=boost, term_len_boost=term_len_boost, field_boosts=fb, need_sum_rank=ns,
                                postings=np.ascontiguousarray([s[0] for s in subterms], np.uint32),
                                procs=np.ascontiguousarray([s[1] for s in subterms], np.float32)))
 
@@ -108,13 +110,15 @@ class FtProblem:
     def c_config(self):
         self._fc = (FieldConfig * self.nfields)(*[FieldConfig(**f) for f in self.field_cfg])
         return Config(self.cfg["merge_limit"], self.cfg["min_rank"], self.cfg["bm25_k1"], self.cfg["bm25_b"], self.cfg["bm25_type"],
-                      self.cfg["distance_boost"], self.cfg["distance_weight"], self.cfg["full_match_boost"], self.nfields, self._fc)
+                      self.cfg["distance_boost"], self.cfg["distance_weight"], self.cfg["full_match_boost"], self.nfields, self._fc,
+                      self.cfg.get("summation_ranks_by_fields_ratio", 0.0))
 
     def c_terms(self):
         arr = (Term * max(len(self.terms), 1))()
         for i, t in enumerate(self.terms):
             arr[i] = Term(t["op"], t["boost"], t["term_len_boost"], _p(t["field_boosts"], _f32p), len(t["postings"]),
-                          _p(t["postings"], _u32p), _p(t["procs"], _f32p))
+                          _p(t["postings"], _u32p), _p(t["procs"], _f32p),
+                          None if t.get("need_sum_rank") is None else _p(t["need_sum_rank"], _u8p))
         return arr
 
 

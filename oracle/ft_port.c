@@ -76,11 +76,15 @@ typedef struct {
 	const uint8_t* removed;
 } stats_t;
 
-/* phrasemergerimpl.h:13-91 with summationRanksByFieldsRatio == 0 (its default) */
+/* phrasemergerimpl.h:13-91, incl. the summation of the other fields' ranks (summationRanksByFieldsRatio > 0, needSumRank fields) */
 static float calc_term_rank(const ft_term* term, const bm25_t* bm, uint32_t doc, const uint32_t* pos, uint32_t npos, float proc,
 							const ft_config* cfg, const stats_t* st, uint8_t* fieldOut) {
 	uint8_t fieldWithMaxRank = 0;
 	float termRank = 0.f;
+	float ranksInFields[64];
+	uint32_t nranks = 0;
+	int needToSumWinner = 0;
+	const int needSumRanks = cfg->summation_ranks_by_fields_ratio > 0.0;
 	for (uint32_t idx = 0; idx < npos;) {
 		const unsigned f = pos[idx] >> 24;
 		const uint32_t fieldBegin = idx;
@@ -98,9 +102,29 @@ static float calc_term_rank(const ft_term* term, const bm25_t* bm, uint32_t doc,
 		const float positionRank = bound_f(pos2rank(pos[fieldBegin] & 0xFFFFFF), (float)fc->position_weight, (float)fc->position_boost);
 		const float termLenBoost = bound_f(term->term_len_boost, (float)fc->term_len_weight, (float)fc->term_len_boost);
 		const float termRankTmp = term->field_boosts[f] * normBm25 * termLenBoost * positionRank;
+		const int needSum = term->need_sum_rank && term->need_sum_rank[f];
 		if (termRankTmp > termRank) {
 			fieldWithMaxRank = (uint8_t)f;
 			termRank = termRankTmp;
+			needToSumWinner = needSum;
+		}
+		if (needSum) {
+			ranksInFields[nranks++] = termRankTmp;
+		}
+	}
+	if (termRank > 0.0 && needSumRanks) { /* :70-78: ranks descending, geometric weights k, k^2, ...; the winner is not added twice */
+		for (uint32_t i = 1; i < nranks; ++i) {
+			const float v = ranksInFields[i];
+			uint32_t j = i;
+			for (; j > 0 && ranksInFields[j - 1] < v; --j) {
+				ranksInFields[j] = ranksInFields[j - 1];
+			}
+			ranksInFields[j] = v;
+		}
+		float k = (float)cfg->summation_ranks_by_fields_ratio;
+		for (uint32_t i = needToSumWinner ? 1 : 0; i < nranks; ++i) {
+			termRank += (k * ranksInFields[i]);
+			k = (float)(k * cfg->summation_ranks_by_fields_ratio);
 		}
 	}
 	*fieldOut = fieldWithMaxRank;

@@ -28,6 +28,7 @@ typedef struct { /* the FTConfig members the merger reads, ftconfig.h:151-236 */
 	double distance_boost, distance_weight, full_match_boost;
 	uint32_t nfields;
 	const ft_field_config* fields;
+	double summation_ranks_by_fields_ratio; /* ftconfig.h:210 */
 } ft_config;
 
 typedef struct { /* one TermResults: FtDslOpts (ftdsl.h:18-30) + its SubtermResults (querymergedata.h) */
@@ -38,6 +39,7 @@ typedef struct { /* one TermResults: FtDslOpts (ftdsl.h:18-30) + its SubtermResu
 	uint32_t nsubterms;
 	const uint32_t* postings; /* indexes into the lists array */
 	const float* procs;
+	const uint8_t* need_sum_rank; /* nfields flags (FtDslFieldOpts::needSumRank) or NULL */
 } ft_term;
 
 typedef struct { /* ft::MergeInfo, ft_fast/phrasemerger.h:57-62 */

@@ -40,6 +40,7 @@ void fillConfig(reindexer::FTConfig& c, const ft_config* in) {
 	c.distanceBoost = in->distance_boost;
 	c.distanceWeight = in->distance_weight;
 	c.fullMatchBoost = in->full_match_boost;
+	c.summationRanksByFieldsRatio = in->summation_ranks_by_fields_ratio;
 	for (uint32_t f = 0; f < in->nfields; ++f) {
 		auto& fc = c.fieldsCfg[f];
 		fc.bm25Boost = in->fields[f].bm25_boost;
@@ -90,6 +91,7 @@ int64_t runMerge(uint32_t totalDocs, const Stats& stats, const uint8_t* excluded
 		e.Opts().fieldsOpts.resize(stats.nfields);
 		for (uint32_t f = 0; f < stats.nfields; ++f) {
 			e.Opts().fieldsOpts[f].boost = terms[t].field_boosts[f];
+			e.Opts().fieldsOpts[f].needSumRank = terms[t].need_sum_rank && terms[t].need_sum_rank[f];
 		}
 		reindexer::ft::TermResults<IdCont> tr(std::move(e));
 		for (uint32_t s = 0; s < terms[t].nsubterms; ++s) {
@@ -206,6 +208,7 @@ int ref_ft_calc_term_rank(uint32_t nfields, const ft_config* cfg, const ft_term*
 		opts.fieldsOpts.resize(nfields);
 		for (uint32_t f = 0; f < nfields; ++f) {
 			opts.fieldsOpts[f].boost = term->field_boosts[f];
+			opts.fieldsOpts[f].needSumRank = term->need_sum_rank && term->need_sum_rank[f];
 		}
 		reindexer::IdRelType rel(1);
 		for (uint32_t p = 0; p < npos; ++p) {

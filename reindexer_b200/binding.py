@@ -55,12 +55,13 @@ class FtFieldConfig(C.Structure):
 class FtConfig(C.Structure):
     _fields_ = [("merge_limit", C.c_uint32), ("min_rank", C.c_int32), ("bm25_k1", C.c_double), ("bm25_b", C.c_double),
                 ("bm25_type", C.c_int32), ("distance_boost", C.c_double), ("distance_weight", C.c_double),
-                ("full_match_boost", C.c_double), ("nfields", C.c_uint32), ("fields", C.POINTER(FtFieldConfig))]
+                ("full_match_boost", C.c_double), ("nfields", C.c_uint32), ("fields", C.POINTER(FtFieldConfig)),
+                ("summation_ranks_by_fields_ratio", C.c_double)]
 
 
 class FtTerm(C.Structure):
     _fields_ = [("op", C.c_int32), ("boost", C.c_float), ("term_len_boost", C.c_float), ("field_boosts", _f32p), ("nsubterms", C.c_uint32),
-                ("postings", _u32p), ("procs", _f32p)]
+                ("postings", _u32p), ("procs", _f32p), ("need_sum_rank", _u8p)]
 
 
 class FtStats(C.Structure):
@@ -489,15 +490,17 @@ class GpuFtIndex:
         postings, procs).  Returns a structured array (id, proc, field, normalized_proc)."""
         fc = (FtFieldConfig * self.nfields)(*[FtFieldConfig(**f) for f in field_cfg])
         c = FtConfig(cfg["merge_limit"], cfg["min_rank"], cfg["bm25_k1"], cfg["bm25_b"], cfg["bm25_type"], cfg["distance_boost"],
-                     cfg["distance_weight"], cfg["full_match_boost"], self.nfields, fc)
+                     cfg["distance_weight"], cfg["full_match_boost"], self.nfields, fc, cfg.get("summation_ranks_by_fields_ratio", 0.0))
         keep = []
         arr = (FtTerm * max(len(terms), 1))()
         for i, t in enumerate(terms):
             fb = np.ascontiguousarray(t["field_boosts"], np.float32)
             po = np.ascontiguousarray(t["postings"], np.uint32)
             pr = np.ascontiguousarray(t["procs"], np.float32)
-            keep += [fb, po, pr]
-            arr[i] = FtTerm(t["op"], t["boost"], t["term_len_boost"], _p(fb, _f32p), len(po), _p(po, _u32p), _p(pr, _f32p))
+            ns = None if t.get("need_sum_rank") is None else np.ascontiguousarray(t["need_sum_rank"], np.uint8)
+            keep += [fb, po, pr, ns]
+            arr[i] = FtTerm(t["op"], t["boost"], t["term_len_boost"], _p(fb, _f32p), len(po), _p(po, _u32p), _p(pr, _f32p),
+                            None if ns is None else _p(ns, _u8p))
         ex = None if excluded is None else np.ascontiguousarray(excluded, np.uint8)
         max_out = self.total_docs if max_out is None else max_out
         out = np.zeros(max(max_out, 1), FT_MERGE_INFO_DTYPE)

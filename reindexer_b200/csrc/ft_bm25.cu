@@ -51,6 +51,8 @@ struct TermParams {
 	int bm25_type;
 	uint32_t nfields;
 	float dist_weight, dist_boost;
+	unsigned long long need_sum_mask;  // FtDslFieldOpts::needSumRank per field (bit f)
+	double sum_ratio;                  // FTConfig::summationRanksByFieldsRatio (0 = off)
 };
 
 struct MergeState {
@@ -106,11 +108,17 @@ __device__ __forceinline__ double bm25_get(const TermParams& t, double termCount
 	return __ddiv_rn(num, __dadd_rn(tf, __dmul_rn(t.k1, inner)));
 }
 
-// calcTermRank (phrasemergerimpl.h:13-91, summationRanksByFieldsRatio == 0)
+// calcTermRank (phrasemergerimpl.h:13-91), incl. the summation of the other fields' ranks (summationRanksByFieldsRatio > 0 and fields
+// with needSumRank; at most kMaxSumFields of them, checked on the host)
+constexpr int kMaxSumFields = 16;
 __device__ __forceinline__ float calc_term_rank(const TermParams& t, const uint32_t* words, const float* avg, uint32_t doc,
 												const uint32_t* pos, uint32_t npos, uint8_t* fieldOut) {
 	uint8_t best_field = 0;
 	float termRank = 0.f;
+	const bool summing = t.sum_ratio > 0.0 && t.need_sum_mask != 0ull;
+	float ranks[kMaxSumFields];  // descending (insertion): the reference sorts them before the weighted sum
+	int nranks = 0;
+	bool sumWinner = false;
 	for (uint32_t idx = 0; idx < npos;) {
 		const uint32_t f = pos[idx] >> 24;
 		const uint32_t begin = idx;
@@ -126,9 +134,25 @@ __device__ __forceinline__ float calc_term_rank(const TermParams& t, const uint3
 		const float positionRank = bound_f(pos2rank(pos[begin] & 0xFFFFFFu), t.fc[f].pos_weight, t.fc[f].pos_boost);
 		const float termLenBoost = bound_f(t.term_len_boost, t.fc[f].len_weight, t.fc[f].len_boost);
 		const float tmp = __fmul_rn(__fmul_rn(__fmul_rn(t.field_boosts[f], normBm25), termLenBoost), positionRank);
+		const bool needSum = summing && ((t.need_sum_mask >> f) & 1ull);
 		if (tmp > termRank) {
 			best_field = uint8_t(f);
 			termRank = tmp;
+			sumWinner = needSum;
+		}
+		if (needSum && nranks < kMaxSumFields) {
+			int j = nranks++;
+			for (; j > 0 && ranks[j - 1] < tmp; --j) {
+				ranks[j] = ranks[j - 1];
+			}
+			ranks[j] = tmp;
+		}
+	}
+	if (summing && termRank > 0.f) {  // :70-78
+		float k = __double2float_rn(t.sum_ratio);
+		for (int i = sumWinner ? 1 : 0; i < nranks; ++i) {
+			termRank = __fadd_rn(termRank, __fmul_rn(k, ranks[i]));
+			k = __double2float_rn(__dmul_rn(double(k), t.sum_ratio));
 		}
 	}
 	*fieldOut = best_field;
@@ -895,6 +919,16 @@ int rxgpu_ft_merge(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nter
 				return fail(RXGPU_ERR_PARAMS, "rxgpu: unknown posting list id");
 			}
 		}
+		uint32_t summed = 0;
+		for (uint32_t f = 0; terms[t].need_sum_rank && f < ft->nfields; ++f) {
+			summed += terms[t].need_sum_rank[f] ? 1u : 0u;
+		}
+		if (summed > uint32_t(kMaxSumFields)) {
+			return fail(RXGPU_ERR_PARAMS, "rxgpu: at most 16 fields of a term may carry needSumRank on the device path");
+		}
+	}
+	if (!(cfg->summation_ranks_by_fields_ratio >= 0.0)) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: summation_ranks_by_fields_ratio must be >= 0");
 	}
 	std::lock_guard<std::mutex> lck(ft->mtx);
 	cudaStream_t st = ft->stream;
@@ -1008,6 +1042,10 @@ int rxgpu_ft_merge(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nter
 		p.nfields = ft->nfields;
 		p.dist_weight = float(cfg->distance_weight);
 		p.dist_boost = float(cfg->distance_boost);
+		p.sum_ratio = cfg->summation_ranks_by_fields_ratio;
+		for (uint32_t f = 0; terms[t].need_sum_rank && f < ft->nfields; ++f) {
+			p.need_sum_mask |= terms[t].need_sum_rank[f] ? (1ull << f) : 0ull;
+		}
 		const double totalDocCount = double(N - 1), matched = double(l.ndocs);  // mergerimpl.h:122-124
 		if (cfg->bm25_type == 0) {  // Bm25Rx::IDF (bm25.h:21-27), on the host: the same libm as the reference
 			double f = std::log((totalDocCount - matched + 1) / matched) / std::log(1 + totalDocCount);

@@ -330,8 +330,9 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 		// (K-split query block, accumulators of 128 rows); tc_variant 5: knn_tc_filter_q (whole block in TMEM, accumulators of 64 rows)
 		using TqKernel = void (*)(TqArgs);
 		const bool ksplit = ix->tc_variant == 0;
-		const TqKernel kernels[3] = {ksplit ? knn_tc_filter_k<1> : knn_tc_filter_q<1>, ksplit ? knn_tc_filter_k<2> : knn_tc_filter_q<2>,
-									 ksplit ? knn_tc_filter_k<4> : knn_tc_filter_q<4>};
+		const TqKernel kernels[4] = {ksplit ? knn_tc_filter_k<1> : knn_tc_filter_q<1>, ksplit ? knn_tc_filter_k<2> : knn_tc_filter_q<2>,
+									 ksplit ? knn_tc_filter_k<4> : knn_tc_filter_q<4>, ksplit ? knn_tc_filter_k<4> : knn_tc_filter_q<8>};
+		auto kernelOf = [&](int c) { return kernels[c == 8 ? 3 : (c == 4 ? 2 : (c == 2 ? 1 : 0))]; };
 		const uint32_t tileRows = ksplit ? kTkTileRows : kTqTileRows;
 		auto smemOf = [&](uint32_t st) { return ksplit ? tk_smem_bytes(st) : tq_smem_bytes(st); };
 		const uint32_t qblocks = (nq + kTqQueries - 1) / kTqQueries;
@@ -344,9 +345,9 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			RX_CUDA(raiseSmemCeilingOnce(kfn, ix->device, int(kTcSmemLimit)));
 		}
 		// a cluster of C CTAs reads every row tile from HBM once for C x 128 queries (TMA multicast)
-		const uint32_t clusterMax = ix->tc_cluster_max ? ix->tc_cluster_max : 4u;
-		int cluster = qblocks >= 3 ? 4 : (qblocks == 2 ? 2 : 1);
-		cluster = std::min<int>(cluster, int(clusterMax));
+		const uint32_t clusterMax = ix->tc_cluster_max ? ix->tc_cluster_max : 4u;  // mode 9: up to 8 (one launch serves 1024 queries)
+		int cluster = qblocks >= 5 ? 8 : (qblocks >= 3 ? 4 : (qblocks == 2 ? 2 : 1));
+		cluster = std::min<int>(cluster, int(ksplit ? std::min(clusterMax, 4u) : clusterMax));
 		const uint32_t qtiles = uint32_t((ix->size + tileRows - 1) / tileRows);
 		unsigned grid = 0;
 		for (;;) {  // how many clusters of this size can be resident at once (GPC boundaries strand SMs for size 4)
@@ -362,7 +363,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			cfg.attrs = attr;
 			cfg.numAttrs = 1;
 			int maxClusters = 0;
-			const cudaError_t e = cudaOccupancyMaxActiveClusters(&maxClusters, kernels[cluster == 4 ? 2 : (cluster == 2 ? 1 : 0)], &cfg);
+			const cudaError_t e = cudaOccupancyMaxActiveClusters(&maxClusters, kernelOf(cluster), &cfg);
 			if (e == cudaSuccess && maxClusters > 0) {
 				grid = unsigned(std::min<uint64_t>(uint64_t(maxClusters), std::max<uint32_t>(qtiles, 1))) * cluster;
 				break;
@@ -398,7 +399,9 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			a.metric = ix->metric;
 			{
 				static const char* pf = std::getenv("RXGPU_TC_PREFETCH");  // tuning aid: L2 prefetch distance in tiles
-				a.prefetch = pf ? uint32_t(std::atoi(pf)) : 0u;  // measured: no effect (the ring is not what limits the kernel), off by default
+				a.prefetch = pf ? uint32_t(std::atoi(pf)) : 0u;
+				static const char* si = std::getenv("RXGPU_TC_SINGLE_ISSUER");  // tuning aid for knn_tc_filter_q
+				a.single_issuer = si ? uint32_t(std::atoi(si)) : 0u;  // measured: no effect (the ring is not what limits the kernel), off by default
 			}
 			static DevBuf<unsigned long long> traceBuf;  // profiling aid: RXGPU_TC_TRACE=<file> dumps per-tile timestamps of CTA 0
 			const char* tracePath = std::getenv("RXGPU_TC_TRACE");
@@ -427,7 +430,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			attr[0].val.clusterDim.z = 1;
 			cfg.attrs = attr;
 			cfg.numAttrs = 1;
-			RX_CUDA(cudaLaunchKernelEx(&cfg, kernels[cluster == 4 ? 2 : (cluster == 2 ? 1 : 0)], a));
+			RX_CUDA(cudaLaunchKernelEx(&cfg, kernelOf(cluster), a));
 			RX_CUDA(cudaGetLastError());
 			if (e0) {
 				RX_CUDA(cudaEventRecord(e1, st));
@@ -1006,12 +1009,12 @@ int rxgpu_set_query_tile(rxgpu_index* ix, uint32_t qt) {
 	return 0;
 }
 int rxgpu_set_tensor_core_filter(rxgpu_index* ix, int mode) {
-	if (!ix || mode < 0 || mode > 8) {
-		return fail(RXGPU_ERR_PARAMS, "rxgpu: tensor-core filter mode must be in 0..8");
+	if (!ix || mode < 0 || mode > 9) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: tensor-core filter mode must be in 0..9");
 	}
 	ix->tc_mode = uint32_t(mode >= 3 ? 1 : mode);
-	ix->tc_variant = (mode == 3 || mode == 4) ? uint32_t(mode) : ((mode == 5 || mode == 6) ? 5u : 0u);
-	ix->tc_cluster_max = (mode == 5 || mode == 7) ? 1u : ((mode == 6 || mode == 8) ? 4u : 0u);
+	ix->tc_variant = (mode == 3 || mode == 4) ? uint32_t(mode) : ((mode == 5 || mode == 6 || mode == 9) ? 5u : 0u);
+	ix->tc_cluster_max = (mode == 5 || mode == 7) ? 1u : ((mode == 6 || mode == 8) ? 4u : (mode == 9 ? 8u : 0u));
 	return 0;
 }
 int rxgpu_set_profile(int on) {

@@ -10,8 +10,8 @@
 // TMEM map (512 columns): [0, 256) query dims 0..511 (two bf16 per column, lane = query), [256, 384) and [384, 512) the two fp32
 //                         accumulators D[128 queries x 128 rows].
 // Shared memory: [A tail: 4 K chunks x 16 KB][row ring: stages x 16 KB (one K chunk of a 128-row tile per stage)][(||v||, w) ring]
-// Roles (192 threads, 1 CTA / SM): warp 0 producer (bulk copies of the pre-swizzled shadow; in a cluster of C CTAs each fetches 1/C of
-// every chunk and multicasts it), warp 1 MMA issuer (tiles alternate between the accumulators), warps 2-5 epilogue (thread = one
+// Roles (320 threads, 1 CTA / SM): warp 0 producer (bulk copies of the pre-swizzled shadow; in a cluster of C CTAs each fetches 1/C of
+// every chunk and multicasts it), warp 1 MMA issuer (tiles alternate between the accumulators), warps 2-5 / 6-9 epilogue of the even / odd tiles (thread = one
 // query = one TMEM lane; one FFMA + compare per (query, row); the rare hit path is shared with knn_tc_filter_q).
 // All single-thread instructions are issued from warp-uniform code under elect.sync (operands in uniform registers).
 // Requires padded dim <= 768.  Same certified-bound candidate logic as knn_tc.cuh: results stay exact after the re-rank.
@@ -26,8 +26,8 @@ constexpr uint32_t kTkTmemChunks = 8;                      // K chunks of the qu
 constexpr uint32_t kTkTailChunks = kTqMaxKchunks - kTkTmemChunks;  // 4: K chunks of the query block held in shared memory
 constexpr uint32_t kTkTailBytes = kTkTailChunks * kTqQueries * 128;  // 64 KB
 constexpr uint32_t kTkAccCol0 = 256;
-constexpr uint32_t kTkVwSlots = 8, kTkVwAhead = 4;
-constexpr int kTkThreads = 192;                            // producer, issuer, 4 epilogue warps
+constexpr uint32_t kTkVwSlots = 16, kTkVwAhead = 4;
+constexpr int kTkThreads = 320;                            // producer, issuer, two epilogue groups of 4 warps (even / odd tiles)
 
 __host__ __device__ inline size_t tk_smem_bytes(uint32_t stages) {
 	return 1024 + kTkTailBytes + size_t(stages) * kTkChunkBytes + kTkVwSlots * kTkTileRows * 8 + (2 * size_t(stages) + 8 + kTkVwSlots) * 8 + 64;
@@ -183,14 +183,17 @@ __global__ void __launch_bounds__(kTkThreads, 1) knn_tc_filter_k(const TqArgs a)
 			}
 		}
 	} else {
-		// ===== epilogue warps 2..5: thread = query (TMEM lane quadrant = warp % 4) =====
+		// ===== epilogue: group 0 = warps 2..5 (even tiles, accumulator 0), group 1 = warps 6..9 (odd tiles, accumulator 1);
+		// thread = query (TMEM lane quadrant = warp % 4) =====
 		const uint32_t quad = warp & 3;
+		const uint32_t grp = warp >= 6 ? 1u : 0u;
+		const bool leader = warp == 2 || warp == 6;
 		const uint32_t qrow = quad * 32 + lane;             // query row inside the block = TMEM lane
 		const uint32_t my_q = q0 + qrow;                    // global query index
 		const bool q_ok = my_q < a.nq_total;
 		// 1. my query -> TMEM (K chunks 0..7, 32 columns = 64 bf16 per store) and -> shared memory (K chunks 8.., SWIZZLE_128B K-major:
-		//    8-row groups 1024 B apart, the 16-byte units of row r XOR-permuted with r % 8)
-		{
+		//    8-row groups 1024 B apart, the 16-byte units of row r XOR-permuted with r % 8); group 0 only
+		if (grp == 0) {
 			const uint4* src = reinterpret_cast<const uint4*>(a.qbf + size_t(q_ok ? my_q : 0) * a.pitch_bf);
 			const uint32_t ntm = min(a.kchunks, kTkTmemChunks);
 			for (uint32_t kc = 0; kc < ntm; ++kc) {
@@ -225,9 +228,9 @@ __global__ void __launch_bounds__(kTkThreads, 1) knn_tc_filter_k(const TqArgs a)
 		const float qe = q_ok ? kTcErrCoef * a.qnorm[my_q] : 0.f;
 		float tau = q_ok ? ord_float(a.tau[my_q]) : -INFINITY;
 		float2 pr = q_ok ? tc_make_pr(a.metric, tau, qe) : make_float2(0.f, INFINITY);
-		// per-row terms (||v||, w): one 1 KB bulk copy per tile into a ring, issued kTkVwAhead tiles ahead by the first epilogue warp
-		// (slot reuse argument as in knn_tc_filter_q: slots >= ahead + 4)
-		static_assert(kTkVwSlots >= kTkVwAhead + 4, "vw ring reuse distance");
+		// per-row terms (||v||, w): one 1 KB bulk copy per tile into a ring, issued kTkVwAhead tiles (two of the group's own) ahead by the
+		// group's first warp (slot reuse argument as in knn_tc_filter_q: slots >= ahead + 12)
+		static_assert(kTkVwSlots >= kTkVwAhead + 12, "vw ring reuse distance");
 		auto issue_vw = [&](uint32_t j) {
 			const uint64_t t = uint64_t(cid) + uint64_t(j) * ncl;
 			if (t < ntiles) {
@@ -237,20 +240,18 @@ __global__ void __launch_bounds__(kTkThreads, 1) knn_tc_filter_k(const TqArgs a)
 						  reinterpret_cast<const unsigned char*>(a.vw + t * kTkTileRows), kTkTileRows * 8, &vw_full[slot]);
 			}
 		};
-		if (warp == 2) {
+		if (leader) {
 			if (elect_one_sync()) {
-				for (uint32_t j = 0; j < kTkVwAhead; ++j) {
-					issue_vw(j);
-				}
+				issue_vw(grp);
+				issue_vw(grp + 2);
 			}
 			__syncwarp();
 		}
 		unsigned int tau_ahead = q_ok ? a.tau[my_q] : 0u;
-		uint32_t it = 0;
-		for (uint32_t t = cid; t < ntiles; t += ncl, ++it) {
-			const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+		for (uint32_t it = grp, t = cid + grp * ncl; t < ntiles; it += 2, t += 2 * ncl) {
+			const uint32_t acc = grp, acc_phase = (it >> 1) & 1;
 			const uint32_t rows_valid = min(uint32_t(kTkTileRows), a.n - t * kTkTileRows);
-			if (warp == 2) {
+			if (leader) {
 				if (elect_one_sync()) {
 					issue_vw(it + kTkVwAhead);
 				}

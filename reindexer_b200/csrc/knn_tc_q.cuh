@@ -9,10 +9,11 @@
 //
 // TMEM map (512 columns): [0, dim_padded/2) the 128 x dim bf16 query block (two K elements per 32-bit column, lane = query),
 //                         [384, 448) and [448, 512) two fp32 accumulators D[128 queries x 64 rows] (double buffered).
-// Roles (224 threads): warp 0 TMA producer (its 64/C-row slice of every stage, multicast to the cluster); warps 1 and 6 issue the
-// MMAs of the even / odd tiles into accumulator 0 / 1 (two issuers keep the tensor pipe fed: the serial mbarrier-wait + issue +
-// commit latency of one thread is comparable to the MMA time of a tile); warps 2-5 epilogue: thread = one query (TMEM lane) with
-// P/R/tau of its query in registers, per-row terms broadcast from shared memory, one FFMA + compare per (query, row).
+// Roles (352 threads): warp 0 TMA producer (its 64/C-row slice of every stage, multicast to the cluster); warps 1 and 6 issue the
+// MMAs of the even / odd tiles into accumulator 0 / 1; TWO epilogue groups of four warps, warps 2-5 drain the even tiles
+// (accumulator 0) and warps 7-10 the odd ones (accumulator 1), so a slow tile (the rare candidate path takes global atomics)
+// never delays the hand-back of the other accumulator: thread = one query (TMEM lane) with P/R/tau of its query in registers,
+// per-row terms broadcast from shared memory, one FFMA + compare per (query, row).
 // Requires dim_padded <= 768.
 #pragma once
 #include "knn_tc.cuh"
@@ -23,7 +24,7 @@ constexpr int kTqTileRows = 64;                           // UMMA N
 constexpr int kTqSubBytes = kTqTileRows * 128;            // 8 KB: 64 rows x 64 bf16 (one 128-byte swizzle atom wide)
 constexpr int kTqSubsPerStage = 4;                        // K chunks per stage
 constexpr int kTqStageBytes = kTqSubsPerStage * kTqSubBytes;  // a stage = 64 rows x 256 bf16 = 32 KB behind ONE mbarrier
-constexpr int kTqThreads = 224;                           // producer, issuer A, 4 epilogue warps, issuer B
+constexpr int kTqThreads = 352;                           // producer, issuer A, epilogue group 0 (4 warps), issuer B, epilogue group 1 (4 warps)
 constexpr int kTqQueries = 128;                           // UMMA M = queries per CTA
 constexpr uint32_t kTqAccCol0 = 384;                      // first accumulator column
 constexpr uint32_t kTqMaxKchunks = 12;                    // 768 / 64
@@ -53,10 +54,11 @@ struct TqArgs {
 	unsigned long long* trace;  // profiling aid (RXGPU_TC_TRACE): per-tile timestamps of CTA 0, or nullptr
 	uint32_t trace_first;       // first local tile index recorded (RXGPU_TC_TRACE_FIRST)
 	uint32_t prefetch;          // L2 prefetch distance of the producers in tiles (0 = off)
+	uint32_t single_issuer;     // knn_tc_filter_q: 1 = warp 1 issues every tile in order (stages are released at the full pipe rate)
 };
 
-constexpr uint32_t kTqVwSlots = 8;  // ring of per-tile (||v||, w) blocks, filled kTqVwAhead tiles ahead by the epilogue itself
-constexpr uint32_t kTqVwAhead = 4;  // slots >= ahead + 4: see the reuse argument in the epilogue
+constexpr uint32_t kTqVwSlots = 16;  // ring of per-tile (||v||, w) blocks, filled kTqVwAhead tiles ahead by the epilogue itself
+constexpr uint32_t kTqVwAhead = 4;   // slots >= ahead + 12: see the reuse argument in the epilogue
 __host__ __device__ inline size_t tq_smem_bytes(uint32_t stages) {
 	return 1024 + size_t(stages) * kTqStageBytes + kTqVwSlots * kTqTileRows * 8 + (2 * size_t(stages) + 8 + kTqVwSlots) * 8 + 64;
 }
@@ -227,7 +229,13 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 				const unsigned char* src = tile_src + size_t(kTqSubsPerStage * kp) * kTqSubBytes;
 				if (elect_one_sync()) {
 					mbar_expect_tx(&full_bar[stage], nsub * kTqSubBytes);
-					if constexpr (kCluster > 1) {
+					if constexpr (kCluster > kTqSubsPerStage) {  // 8 CTAs: every 8 KB K chunk of the stage is fetched in two halves
+						constexpr uint32_t kParts = kCluster / kTqSubsPerStage, kPart = kTqSubBytes / kParts;
+						const uint32_t sub = crank / kParts, off = sub * kTqSubBytes + (crank % kParts) * kPart;
+						if (sub < nsub) {
+							bulk_load_mc(dst + off, src + off, kPart, &full_bar[stage], uint16_t((1u << kCluster) - 1u));
+						}
+					} else if constexpr (kCluster > 1) {
 						for (uint32_t sub = crank; sub < nsub; sub += kCluster) {
 							bulk_load_mc(dst + sub * kTqSubBytes, src + size_t(sub) * kTqSubBytes, kTqSubBytes, &full_bar[stage],
 										 uint16_t((1u << kCluster) - 1u));
@@ -252,19 +260,24 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 	} else if (warp == 1 || warp == 6) {
 		// ===== MMA issuers: warp 1 -> even tiles / accumulator 0, warp 6 -> odd tiles / accumulator 1 =====
 		// D[128 queries x 64 rows] += A(TMEM) x B(smem stage)^T.  Whole warp in the loop, one elected lane issues (see the producer).
+		const bool single = a.single_issuer != 0;
 		const uint32_t parity = warp == 1 ? 0u : 1u;
 		const uint32_t idesc = umma_idesc_bf16(kTqQueries, kTqTileRows);
 		const uint32_t kpairs = (a.kchunks + kTqSubsPerStage - 1) / kTqSubsPerStage;
 		mbar_wait(q_ready, 0);
 		asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-		const uint32_t tmem_d = tmem_base + kTqAccCol0 + parity * kTqTileRows;
-		// stages are consumed in tile order by the two issuers alternately: mine are [it * kpairs, (it + 1) * kpairs) for it = parity, parity + 2, ...
-		uint32_t stage = (parity * kpairs) % a.stages, phase = ((parity * kpairs) / a.stages) & 1;
-		for (uint32_t it = parity, t = cid + parity * ncl; t < ntiles; it += 2, t += 2 * ncl) {
+		// two issuers: stages are consumed in tile order alternately, mine are [it * kpairs, (it + 1) * kpairs) for it = parity, parity + 2, ...
+		// one issuer (a.single_issuer): warp 1 walks every tile in order, the accumulators alternate; warp 6 has nothing to do
+		const uint32_t step = single ? 1u : 2u;
+		const uint32_t first = single ? 0u : parity;
+		uint32_t stage = (first * kpairs) % a.stages, phase = ((first * kpairs) / a.stages) & 1;
+		for (uint32_t it = first, t = cid + first * ncl; t < ntiles && !(single && parity); it += step, t += step * ncl) {
+			const uint32_t acc = single ? (it & 1u) : parity;
+			const uint32_t tmem_d = tmem_base + kTqAccCol0 + acc * kTqTileRows;
 			if (lane == 0) {
 				TQ_TRACE(0, it);
 			}
-			mbar_wait(&acc_empty[parity], ((it >> 1) & 1) ^ 1);
+			mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1);
 			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 			if (lane == 0) {
 				TQ_TRACE(1, it);
@@ -292,7 +305,7 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 						umma_commit(&empty_bar[stage]);
 					}
 					if (kp + 1 == kpairs) {
-						umma_commit(&acc_full[parity]);
+						umma_commit(&acc_full[acc]);
 					}
 				}
 				__syncwarp();
@@ -304,7 +317,7 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 			if (lane == 0) {
 				TQ_TRACE(3, it);
 			}
-			for (uint32_t kp = 0; kp < kpairs; ++kp) {  // skip the other issuer's stages
+			for (uint32_t kp = 0; kp < kpairs && !single; ++kp) {  // skip the other issuer's stages
 				if (++stage == a.stages) {
 					stage = 0;
 					phase ^= 1;
@@ -312,12 +325,15 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 			}
 		}
 	} else {
-		// ===== epilogue warps 2..5: thread = query (TMEM lane quadrant = warp % 4) =====
+		// ===== epilogue: group 0 = warps 2..5 (even tiles, accumulator 0), group 1 = warps 7..10 (odd tiles, accumulator 1);
+		// thread = query (TMEM lane quadrant = warp % 4) =====
 		const uint32_t quad = warp & 3;
+		const uint32_t grp = warp >= 7 ? 1u : 0u;
+		const bool leader = warp == 2 || warp == 7;        // issues the group's (||v||, w) copies
 		const uint32_t my_q = q0 + quad * 32 + lane;       // global query index of this TMEM lane
 		const bool q_ok = my_q < a.nq_total;
-		// 1. my query -> TMEM (A operand): 32 columns (64 bf16) per store
-		{
+		// 1. my query -> TMEM (A operand): 32 columns (64 bf16) per store (group 0 only)
+		if (grp == 0) {
 			const uint4* src = reinterpret_cast<const uint4*>(a.qbf + size_t(q_ok ? my_q : 0) * a.pitch_bf);
 			for (uint32_t kc = 0; kc < a.kchunks; ++kc) {
 				uint32_t r[32];
@@ -342,12 +358,12 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 		const float qe = q_ok ? kTcErrCoef * a.qnorm[my_q] : 0.f;
 		float tau = q_ok ? ord_float(a.tau[my_q]) : -INFINITY;
 		float2 pr = q_ok ? tc_make_pr(a.metric, tau, qe) : make_float2(0.f, INFINITY);
-		// per-row terms (||v||, w): one 512-byte bulk copy per tile into a ring of kTqVwSlots slots, issued kTqVwAhead tiles ahead by
-		// the first epilogue warp, so no global-load latency and no CTA barrier sits on the epilogue path.  Slot reuse is safe
-		// without an "empty" barrier: when this thread starts tile `it` it has passed acc_full(it - 1); those MMAs waited for the
-		// acc_empty arrivals of tile it - 3 from all four warps, which every warp issues after finishing tile it - 4 -- the last
-		// reader of slot (it + kTqVwAhead) % kTqVwSlots.
-		static_assert(kTqVwSlots >= kTqVwAhead + 4, "vw ring reuse distance");
+		// per-row terms (||v||, w): one 512-byte bulk copy per tile into a ring of kTqVwSlots slots, issued kTqVwAhead tiles (two
+		// of the group's own) ahead by the group's first warp, so no global-load latency and no CTA barrier sits on the epilogue path.
+		// Slot reuse is safe without an "empty" barrier: the group's tiles are it, it + 2, ...; when its leader starts tile `it` it has
+		// passed acc_full(it - 2); those MMAs waited for the acc_empty arrivals of tile it - 4 from all four warps of the group, so
+		// every warp is at least inside tile it - 4 and has finished tile it - 6 -- slot (it + 4) % 16 was last read for tile it - 12.
+		static_assert(kTqVwSlots >= kTqVwAhead + 12, "vw ring reuse distance");
 		auto issue_vw = [&](uint32_t j) {
 			const uint64_t t = uint64_t(cid) + uint64_t(j) * ncl;
 			if (t < ntiles) {
@@ -357,20 +373,18 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 						  reinterpret_cast<const unsigned char*>(a.vw + t * kTqTileRows), kTqTileRows * 8, &vw_full[slot]);
 			}
 		};
-		if (warp == 2) {  // first epilogue warp: convergent, one elected lane issues the copies
+		if (leader) {  // convergent, one elected lane issues the copies of the group's first two tiles
 			if (elect_one_sync()) {
-				for (uint32_t j = 0; j < kTqVwAhead; ++j) {
-					issue_vw(j);
-				}
+				issue_vw(grp);
+				issue_vw(grp + 2);
 			}
 			__syncwarp();
 		}
 		unsigned int tau_ahead = q_ok ? a.tau[my_q] : 0u;
-		uint32_t it = 0;
-		for (uint32_t t = cid; t < ntiles; t += ncl, ++it) {
-			const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+		for (uint32_t it = grp, t = cid + grp * ncl; t < ntiles; it += 2, t += 2 * ncl) {
+			const uint32_t acc = grp, acc_phase = (it >> 1) & 1;
 			const uint32_t rows_valid = min(uint32_t(kTqTileRows), a.n - t * kTqTileRows);
-			if (warp == 2) {
+			if (leader) {
 				if (elect_one_sync()) {
 					issue_vw(it + kTqVwAhead);
 				}

@@ -1,0 +1,193 @@
+// Drop-in replacement for ft::Merger<IdCont, ft::MergeData, OffsetT>::Merge at the ft_fast seam
+// Selector<IdCont>::mergeResults (cpp_src/core/ft/ft_fast/selecterimpl.h:609-627): takes exactly what the reference hands its merger --
+// ft::QueryMergeData<IdCont> (querymergedata.h:13-242), FtMergeStatuses::Statuses, FTConfig, a DocsStatsGetter duck-type
+// (index/indextext/indextext.h:245-258) -- converts it to the C ABI of librxgpu (include/rxgpu.h: rxgpu_ft_*) and returns ft::MergeData
+// (phrasemerger.h:57-78).  One GpuFtMerger lives next to the index's DataHolder: document statistics are uploaded once per commit,
+// every posting list (IdRelVec or PackedIdRelVec) once at its first use (keyed by the container's address, which is stable until the
+// next commit rebuilds the holder -- the owner then calls Reset()).
+// Meant to be dropped into cpp_src/core/ft/ft_fast/; it includes the reference's own headers and is compiled only where that tree is
+// available (tests/cpp/dropin_ft_check.cc does so in the authoring container).  INTEGRATION.md section 6 shows the patch.
+//
+// Covered on the device: query parts that are plain terms with their variant subterms (AND / OR / NOT), the preselect step, all three
+// BM25 variants, summationRanksByFieldsRatio.  Phrases and multi-word synonyms are NOT: Mergeable() says so and the caller keeps
+// ft::Merger for those queries (an explicit dispatch at the seam, not a fallback inside the library).
+#pragma once
+
+#include <cstdlib>
+#include <stdexcept>
+#include <unordered_map>
+#include <vector>
+
+// clang-format off
+#include "tools/float_comparison.h"
+#include "core/ft/ft_fast/mergerimpl.h"
+// clang-format on
+#include "core/ft/idrelset.h"
+#include "rxgpu.h"
+
+namespace reindexer {
+namespace ft {
+
+template <typename IdCont>
+class [[nodiscard]] GpuFtMerger {
+public:
+	template <typename DocsStatsGetter>
+	GpuFtMerger(size_t totalNumDocs, size_t fieldSize, const DocsStatsGetter& stats) : totalDocs_(uint32_t(totalNumDocs)), nfields_(uint32_t(fieldSize)) {
+		std::vector<uint32_t> words(size_t(totalDocs_) * nfields_);
+		std::vector<uint8_t> removed(totalDocs_);
+		std::vector<float> avg(nfields_);
+		for (uint32_t d = 0; d < totalDocs_; ++d) {
+			removed[d] = stats.DocRemoved(d) ? 1 : 0;
+			for (uint32_t f = 0; f < nfields_; ++f) {
+				words[size_t(d) * nfields_ + f] = uint32_t(stats.NumWordsInField(d, f));
+			}
+		}
+		for (uint32_t f = 0; f < nfields_; ++f) {
+			avg[f] = stats.AvgWordsCount(f);
+		}
+		check(rxgpu_ft_create(&h_, totalDocs_, nfields_, words.data(), avg.data(), removed.data(), deviceFromEnv()));
+	}
+	GpuFtMerger(const GpuFtMerger&) = delete;
+	GpuFtMerger& operator=(const GpuFtMerger&) = delete;
+	~GpuFtMerger() { rxgpu_ft_destroy(h_); }
+
+	// what the device path covers; everything else stays with ft::Merger (the caller dispatches)
+	static bool Mergeable(const QueryMergeData<IdCont>& q) noexcept {
+		if (!q.synonyms.empty()) {
+			return false;
+		}
+		for (const auto& qp : q.queryParts) {
+			if (!qp.IsTerm()) {
+				return false;
+			}
+		}
+		return true;
+	}
+
+	MergeData Merge(QueryMergeData<IdCont>& q, RankSortType rankSortType, const FtMergeStatuses::Statuses& docsExcluded, const FTConfig& cfg) {
+		MergeData out;
+		if (!Mergeable(q)) {
+			throw std::logic_error("GpuFtMerger: phrases and multi-word synonyms are merged by ft::Merger (see Mergeable())");
+		}
+		if (q.Empty() || totalDocs_ == 0) {
+			return out;  // Merger::Merge, mergerimpl.h:472-474
+		}
+		q.SortSubterms();  // mergerimpl.h:479 -- the same (unstable) sort on the same data; the library keeps this order
+		std::vector<rxgpu_ft_field_config> fields(nfields_);
+		for (uint32_t f = 0; f < nfields_; ++f) {
+			const auto& fc = cfg.fieldsCfg[f];
+			fields[f] = rxgpu_ft_field_config{fc.bm25Boost, fc.bm25Weight, fc.termLenBoost, fc.termLenWeight, fc.positionBoost, fc.positionWeight};
+		}
+		rxgpu_ft_config c{};
+		c.merge_limit = uint32_t(cfg.mergeLimit);
+		c.min_rank = int32_t(cfg.minRank);
+		c.bm25_k1 = cfg.bm25Config.bm25k1;
+		c.bm25_b = cfg.bm25Config.bm25b;
+		switch (cfg.bm25Config.bm25Type) {
+			case FTConfig::Bm25Config::Bm25Type::rx:
+				c.bm25_type = 0;
+				break;
+			case FTConfig::Bm25Config::Bm25Type::classic:
+				c.bm25_type = 1;
+				break;
+			case FTConfig::Bm25Config::Bm25Type::wordCount:
+				c.bm25_type = 2;
+				break;
+		}
+		c.distance_boost = cfg.distanceBoost;
+		c.distance_weight = cfg.distanceWeight;
+		c.full_match_boost = cfg.fullMatchBoost;
+		c.nfields = nfields_;
+		c.fields = fields.data();
+		c.summation_ranks_by_fields_ratio = cfg.summationRanksByFieldsRatio;
+
+		const size_t nterms = q.queryParts.size();
+		std::vector<rxgpu_ft_term> terms(nterms);
+		std::vector<std::vector<float>> boosts(nterms), procs(nterms);
+		std::vector<std::vector<uint8_t>> needSum(nterms);
+		std::vector<std::vector<uint32_t>> lists(nterms);
+		for (size_t t = 0; t < nterms; ++t) {
+			const TermResults<IdCont>& tr = q.queryParts[t].Term();
+			const FtDslOpts& o = tr.Opts();
+			boosts[t].resize(nfields_);
+			needSum[t].resize(nfields_);
+			for (uint32_t f = 0; f < nfields_; ++f) {
+				boosts[t][f] = o.fieldsOpts[f].boost;
+				needSum[t][f] = o.fieldsOpts[f].needSumRank ? 1 : 0;
+			}
+			for (const SubtermResults<IdCont>& st : tr) {
+				lists[t].push_back(postingsId(&st.Occurences()));
+				procs[t].push_back(st.Proc());
+			}
+			terms[t] = rxgpu_ft_term{int32_t(o.op), o.boost, o.termLenBoost, boosts[t].data(), uint32_t(lists[t].size()), lists[t].data(),
+									 procs[t].data(), needSum[t].data()};
+		}
+		std::vector<uint8_t> excluded(totalDocs_);
+		bool anyExcluded = false;
+		for (uint32_t d = 0; d < totalDocs_ && d < docsExcluded.size(); ++d) {
+			excluded[d] = docsExcluded[d] ? 1 : 0;
+			anyExcluded |= excluded[d] != 0;
+		}
+		const uint64_t maxOut = std::min<uint64_t>(cfg.mergeLimit, q.totalORVids) + 1;
+		std::vector<rxgpu_ft_merge_info> res(maxOut);
+		uint64_t n = 0;
+		check(rxgpu_ft_merge(h_, &c, uint32_t(nterms), terms.data(), anyExcluded ? excluded.data() : nullptr, int(rankSortType), maxOut, res.data(),
+							 &n));
+		out.reserve(n);
+		for (uint64_t i = 0; i < n && i < maxOut; ++i) {
+			MergeInfo mi;
+			mi.id = IdType::FromNumber(res[i].id);
+			mi.proc = res[i].proc;
+			mi.field = res[i].field;
+			mi.normalizedProc = res[i].normalized_proc;
+			out.emplace_back(mi);
+		}
+		return out;
+	}
+
+	// the holder was rebuilt (commit): cached posting ids refer to containers that no longer exist
+	void Reset() { cache_.clear(); }
+	size_t UploadedLists() const noexcept { return cache_.size(); }
+
+private:
+	static int deviceFromEnv() {
+		const char* e = std::getenv("RX_GPU_DEVICE");
+		return e ? std::atoi(e) : 0;
+	}
+	static void check(int rc) {
+		if (rc != RXGPU_OK) {
+			throw std::runtime_error(rxgpu_last_error());
+		}
+	}
+	// one posting list -> SoA arrays (the iterator of either container decodes; positions keep the reference's order) -> HBM, once
+	uint32_t postingsId(const IdCont* list) {
+		if (const auto it = cache_.find(list); it != cache_.end()) {
+			return it->second;
+		}
+		std::vector<uint32_t> docs, begin{0}, positions;
+		docs.reserve(list->size());
+		begin.reserve(list->size() + 1);
+		for (auto&& rel : *list) {
+			docs.push_back(uint32_t(rel.Id()));
+			for (const PosType& p : rel.Pos()) {
+				if (p.pos() >= (1u << 24) || p.field() > 255u || p.arrayIdx() != 0) {
+					throw std::runtime_error("GpuFtMerger: word position / field / array index outside the device posting format");
+				}
+				positions.push_back(uint32_t(p.pos()) | (uint32_t(p.field()) << 24));
+			}
+			begin.push_back(uint32_t(positions.size()));
+		}
+		rxgpu_ft_postings pl{uint32_t(docs.size()), docs.data(), begin.data(), positions.data()};
+		uint32_t id = 0;
+		check(rxgpu_ft_add_postings(h_, &pl, &id));
+		cache_.emplace(list, id);
+		return id;
+	}
+
+	uint32_t totalDocs_, nfields_;
+	rxgpu_ft_index* h_ = nullptr;
+	std::unordered_map<const IdCont*, uint32_t> cache_;
+};
+
+}  // namespace ft
+}  // namespace reindexer

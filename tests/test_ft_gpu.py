@@ -59,6 +59,25 @@ def test_config_knobs_and_bm25_variants():
         assert_same_merge(F.best_merge(p)[0], gpu_merge(p)[0], F.RANK_AND_ID, ctx=f"seed {seed}")
 
 
+def test_summation_of_ranks_by_fields():
+    """FTConfig::summationRanksByFieldsRatio > 0 with needSumRank fields (phrasemergerimpl.h:21,58-78): the ranks of the other
+    matching fields are added with geometric weights"""
+    hit = 0
+    for seed in range(40):
+        rng = np.random.default_rng(5000 + seed)
+        nfields = 2 + seed % 4
+        p = random_problem(5000 + seed, total_docs=500, nfields=nfields, nterms=1 + seed % 3, max_pos=6)
+        p.cfg["summation_ranks_by_fields_ratio"] = float(rng.choice([0.3, 0.5, 0.9, 1.0]))
+        for t in p.terms:
+            t["need_sum_rank"] = (rng.random(nfields) < 0.7).astype(np.uint8)
+        a, _ = F.best_merge(p)
+        b, _ = gpu_merge(p)
+        assert_same_merge(a, b, F.RANK_AND_ID, ctx=f"seed {seed}")
+        p.cfg["summation_ranks_by_fields_ratio"] = 0.0
+        hit += int(len(a) != len(F.best_merge(p)[0]) or (a["normalized_proc"] != F.best_merge(p)[0]["normalized_proc"][:len(a)]).any())
+    assert hit > 5  # the knob changes results
+
+
 def test_empty_and_degenerate_queries():
     p = random_problem(5, total_docs=100, nterms=1)
     p.terms[0]["op"] = F.OP_NOT  # a lone NOT term: Empty()

@@ -70,3 +70,16 @@ def test_bm25_variants_and_config_knobs():
         a, _ = F.ref_merge(p)
         b, _ = F.port_merge(p)
         assert_same_merge(a, b, F.RANK_AND_ID, ctx=f"seed {seed}")
+
+
+def test_port_summation_of_ranks_by_fields_matches_reference():
+    if not F.ref_available():
+        pytest.skip("oracle/_ref not built")
+    for seed in range(40):
+        rng = np.random.default_rng(5000 + seed)
+        nfields = 2 + seed % 4
+        p = random_problem(5000 + seed, total_docs=300, nfields=nfields, nterms=1 + seed % 3, max_pos=6)
+        p.cfg["summation_ranks_by_fields_ratio"] = float(rng.choice([0.3, 0.5, 0.9, 1.0]))
+        for t in p.terms:
+            t["need_sum_rank"] = (rng.random(nfields) < 0.7).astype(np.uint8)
+        assert_same_merge(F.ref_merge(p)[0], F.port_merge(p)[0], F.RANK_AND_ID, ctx=f"seed {seed}")

@@ -37,7 +37,8 @@ def test_tc_path_is_bit_identical_to_exact_scan(metric, n, dim, nq, k):
     # every kernel variant gives the same bits: 3 / 4 = queries in shared memory (1 CTA / CTA pair with TMA multicast),
     # 5 / 6 = whole query block in TMEM (accumulators of 64 rows) with single CTAs / clusters of up to 4 CTAs,
     # 7 / 8 = K-split query block (TMEM + shared memory, accumulators of 128 rows; the default) with single CTAs / clusters
-    for mode, kernel in ((3, 1), (4, 1), (5, 2), (6, 2), (7, 3), (8, 3)):
+    # 9 = knn_tc_filter_q with clusters of up to 8 CTAs (one launch serves 1024 queries)
+    for mode, kernel in ((3, 1), (4, 1), (5, 2), (6, 2), (7, 3), (8, 3), (9, 2)):
         gpu.set_tensor_core_filter(mode)
         d2, l2, c2 = gpu.search_knn(queries, k)
         s2 = rx.last_search_stats()
