@@ -292,6 +292,17 @@ int rxgpu_ft_decode_packed(const uint8_t* data, uint64_t len, uint32_t count, ui
  * Writes min(*out_n, max_out) entries; *out_n = number of merged documents. */
 int rxgpu_ft_merge(rxgpu_ft_index*, const rxgpu_ft_config* cfg, uint32_t nterms, const rxgpu_ft_term* terms, const uint8_t* excluded,
 				   int rank_sort_type, uint64_t max_out, rxgpu_ft_merge_info* out, uint64_t* out_n);
+/* IndexText::afterSelect + sortAfterSelect on top of the merge, without leaving the device (core/index/indextext/indextext.cc:480-611;
+ * Merger::postProcessResults, ft_fast/merger.h:111-155): ranks below min_rank are dropped, the rest is normalised to uint8 by the
+ * global maximum, every merged vdoc expands to its row ids, rows whose external status is 0 are skipped (FtUseExternStatuses::Yes),
+ * and the rows come back ordered by (rank descending, row id ascending) for RankSortType::RankAndID (1) or by row id for IDOnly (3) --
+ * the deterministic "integer top-k, ties by id".  Only the first `limit` rows are copied to the host; *out_n = number of rows that
+ * qualify.  rxgpu_ft_set_rows uploads vdocs_[vdoc].RowIds() as CSR (row_begin[total_docs + 1], row_ids) once per commit; without it
+ * (or with NULL) vdoc i is row i. */
+int rxgpu_ft_set_rows(rxgpu_ft_index*, const uint32_t* row_begin, const int32_t* row_ids);
+int rxgpu_ft_select(rxgpu_ft_index*, const rxgpu_ft_config* cfg, uint32_t nterms, const rxgpu_ft_term* terms, const uint8_t* excluded,
+					const uint8_t* row_status /* u8 per row id, or NULL */, int rank_sort_type, uint64_t limit, int32_t* out_row_ids,
+					float* out_ranks /* RankT = the uint8 rank as float */, uint64_t* out_n);
 /* statistics of the last merge on this thread */
 typedef struct {
 	uint32_t launches;
@@ -330,10 +341,10 @@ typedef struct {
 void rxgpu_last_search_stats(rxgpu_search_stats* out);
 /* large query batches: bf16 tensor-core filter + exact fp32 re-rank (results identical to the exact scan).
  * mode 0 = automatic (batches >= 64 queries on >= 100k rows, k <= 15), 1 = whenever possible, 2 = never;
- * 3..8 force kernel variants for tests/benchmarks (all give the same bits): 3 / 4 = first-generation kernel (queries in shared
- * memory) with 1 CTA / a CTA pair per row tile; 5 / 6 = knn_tc_filter_q (query block in TMEM, accumulators of 64 rows) with single
- * CTAs / clusters of up to 4; 7 / 8 = knn_tc_filter_k (K-split query block, accumulators of 128 rows; the default) with single CTAs /
- * clusters of up to 4.  DESIGN.md section 9 has the measurements. */
+ * 3..9 force kernel variants for tests/benchmarks (all give the same bits): 3 / 4 = first-generation kernel (queries in shared
+ * memory) with 1 CTA / a CTA pair per row tile; 5 / 6 = knn_tc_filter_q (query block in TMEM, accumulators of 64 rows; the default)
+ * with single CTAs / clusters of up to 4; 7 / 8 = knn_tc_filter_k (K-split query block, accumulators of 128 rows) with single CTAs /
+ * clusters of up to 4; 9 = knn_tc_filter_q with clusters of up to 8.  DESIGN.md section 9 has the measurements. */
 int rxgpu_set_tensor_core_filter(rxgpu_index*, int mode);
 /* process-wide switch: bracket every scan-kernel launch with CUDA events (used by bench.py for the roofline figure) */
 int rxgpu_set_profile(int on);

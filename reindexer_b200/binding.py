@@ -137,6 +137,9 @@ _SIGNATURES = {
     "rxgpu_ft_decode_packed": (C.c_int, [_u8p, C.c_uint64, C.c_uint32, _u32p, _u32p, _u32p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "rxgpu_ft_merge": (C.c_int, [C.c_void_p, C.POINTER(FtConfig), C.c_uint32, C.POINTER(FtTerm), _u8p, C.c_int, C.c_uint64, C.c_void_p,
                                  C.POINTER(C.c_uint64)]),
+    "rxgpu_ft_set_rows": (C.c_int, [C.c_void_p, _u32p, _i32p]),
+    "rxgpu_ft_select": (C.c_int, [C.c_void_p, C.POINTER(FtConfig), C.c_uint32, C.POINTER(FtTerm), _u8p, _u8p, C.c_int, C.c_uint64, _i32p, _f32p,
+                                  C.POINTER(C.c_uint64)]),
     "rxgpu_ft_last_stats": (None, [C.POINTER(FtStats)]),
     "rxgpu_index_append_synth": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
     "rxgpu_synth_fill_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]),
@@ -488,10 +491,39 @@ class GpuFtIndex:
     def merge(self, cfg: dict, field_cfg: list, terms: list, excluded=None, rank_sort_type=1, max_out=None):
         """cfg / field_cfg: dicts with the FtConfig / FtFieldConfig member names; terms: dicts(op, boost, term_len_boost, field_boosts,
         postings, procs).  Returns a structured array (id, proc, field, normalized_proc)."""
+        c, arr, keep = self._config_and_terms(cfg, field_cfg, terms)
+        ex = None if excluded is None else np.ascontiguousarray(excluded, np.uint8)
+        max_out = self.total_docs if max_out is None else max_out
+        out = np.zeros(max(max_out, 1), FT_MERGE_INFO_DTYPE)
+        n = C.c_uint64(0)
+        _check(self._lib.rxgpu_ft_merge(self._h, C.byref(c), len(terms), arr, None if ex is None else _p(ex, _u8p), rank_sort_type, max_out,
+                                        out.ctypes.data, C.byref(n)))
+        return out[:min(n.value, max_out)].copy()
+
+    def set_rows(self, row_begin, row_ids):
+        """vdoc -> row ids (CSR), the IndexText::vdocs_[vdoc].RowIds() of the reference"""
+        rb = np.ascontiguousarray(row_begin, np.uint32)
+        ri = np.ascontiguousarray(row_ids, np.int32)
+        _check(self._lib.rxgpu_ft_set_rows(self._h, _p(rb, _u32p), _p(ri, _i32p)))
+
+    def select(self, cfg, field_cfg, terms, limit, excluded=None, row_status=None, rank_sort_type=1):
+        """merge + postProcessResults + afterSelect + sortAfterSelect on the device: (row_ids, ranks, total rows)"""
+        c, arr, keep = self._config_and_terms(cfg, field_cfg, terms)
+        ex = None if excluded is None else np.ascontiguousarray(excluded, np.uint8)
+        rs = None if row_status is None else np.ascontiguousarray(row_status, np.uint8)
+        ids = np.zeros(max(limit, 1), np.int32)
+        ranks = np.zeros(max(limit, 1), np.float32)
+        n = C.c_uint64(0)
+        _check(self._lib.rxgpu_ft_select(self._h, C.byref(c), len(terms), arr, None if ex is None else _p(ex, _u8p),
+                                         None if rs is None else _p(rs, _u8p), rank_sort_type, limit, _p(ids, _i32p), _p(ranks, _f32p), C.byref(n)))
+        m = min(n.value, limit)
+        return ids[:m], ranks[:m], n.value
+
+    def _config_and_terms(self, cfg, field_cfg, terms):
         fc = (FtFieldConfig * self.nfields)(*[FtFieldConfig(**f) for f in field_cfg])
         c = FtConfig(cfg["merge_limit"], cfg["min_rank"], cfg["bm25_k1"], cfg["bm25_b"], cfg["bm25_type"], cfg["distance_boost"],
                      cfg["distance_weight"], cfg["full_match_boost"], self.nfields, fc, cfg.get("summation_ranks_by_fields_ratio", 0.0))
-        keep = []
+        keep = [fc]
         arr = (FtTerm * max(len(terms), 1))()
         for i, t in enumerate(terms):
             fb = np.ascontiguousarray(t["field_boosts"], np.float32)
@@ -501,13 +533,7 @@ class GpuFtIndex:
             keep += [fb, po, pr, ns]
             arr[i] = FtTerm(t["op"], t["boost"], t["term_len_boost"], _p(fb, _f32p), len(po), _p(po, _u32p), _p(pr, _f32p),
                             None if ns is None else _p(ns, _u8p))
-        ex = None if excluded is None else np.ascontiguousarray(excluded, np.uint8)
-        max_out = self.total_docs if max_out is None else max_out
-        out = np.zeros(max(max_out, 1), FT_MERGE_INFO_DTYPE)
-        n = C.c_uint64(0)
-        _check(self._lib.rxgpu_ft_merge(self._h, C.byref(c), len(terms), arr, None if ex is None else _p(ex, _u8p), rank_sort_type, max_out,
-                                        out.ctypes.data, C.byref(n)))
-        return out[:min(n.value, max_out)].copy()
+        return c, arr, keep
 
     def last_stats(self) -> dict:
         s = FtStats()

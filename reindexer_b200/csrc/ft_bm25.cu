@@ -20,6 +20,8 @@
 #include <memory>
 #include <vector>
 
+#include <cub/cub.cuh>
+
 #include "internal.h"
 #include "../host/packed_postings.h"
 
@@ -692,6 +694,81 @@ __global__ void ft_full_match(MergeState st, const uint32_t* words, uint32_t nfi
 	}
 }
 
+
+// ---- device-side postProcessResults + IndexText::afterSelect / sortAfterSelect (merger.h:111-155, indextext.cc:480-611) ----------------
+// d_post: [0] scale (float bits) [1] rows total (u32)
+__global__ void ft_post_scale(const float* proc, const uint32_t* n_docs, uint32_t* d_post) {
+	__shared__ float s_max[32];
+	const uint32_t n = *n_docs;
+	float m = 0.f;
+	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+		m = fmaxf(m, proc[i]);
+	}
+	for (int off = 16; off > 0; off >>= 1) {
+		m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+	}
+	if ((threadIdx.x & 31) == 0) {
+		s_max[threadIdx.x >> 5] = m;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (uint32_t w = 0; w < blockDim.x / 32; ++w) {
+			m = fmaxf(m, s_max[w]);
+		}
+		// scalingFactor = maxProc > 255 ? 255.0 / maxProc : 1.0 (a float: the double quotient is narrowed at the assignment)
+		const float scale = m > 255.f ? __double2float_rn(__ddiv_rn(255.0, double(m))) : 1.0f;
+		d_post[0] = __float_as_uint(scale);
+	}
+}
+// rows a merged document contributes: 0 when its rank is below minRank, else its row ids that pass the external statuses
+__global__ void ft_post_count(const int32_t* md_id, const float* proc, const uint32_t* n_docs, float min_proc, const uint32_t* row_begin,
+							  const int32_t* row_ids, const uint8_t* row_status, uint32_t cap, uint32_t* cnt) {
+	const uint32_t n = *n_docs;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+		uint32_t c = 0;
+		if (i < n && !(proc[i] < min_proc)) {
+			const uint32_t d = uint32_t(md_id[i]);
+			if (!row_begin) {
+				c = (!row_status || row_status[d]) ? 1u : 0u;
+			} else {
+				for (uint32_t r = row_begin[d]; r < row_begin[d + 1]; ++r) {
+					c += (!row_status || row_status[row_ids[r]]) ? 1u : 0u;
+				}
+			}
+		}
+		cnt[i] = c;
+	}
+}
+// key per row: RankAndID -> (255 - rank) << 32 | rowId   (rank descending, row id ascending, indextext.cc:487-498)
+//              IDOnly    -> rowId << 8 | rank           (row id ascending)
+__global__ void ft_post_emit(const int32_t* md_id, const float* proc, const uint32_t* n_docs, const uint32_t* d_post, const uint32_t* row_begin,
+							 const int32_t* row_ids, const uint8_t* row_status, const uint32_t* cnt, const uint32_t* off, int rank_and_id,
+							 unsigned long long* keys, uint32_t* rows_total) {
+	const uint32_t n = *n_docs;
+	const float scale = __uint_as_float(d_post[0]);
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		if (i + 1 == n) {
+			*rows_total = off[i] + cnt[i];
+		}
+		if (cnt[i] == 0) {
+			continue;
+		}
+		const uint32_t rank = uint32_t(uint8_t(__fmul_rn(proc[i], scale)));  // normalizedProc = static_cast<uint8_t>(proc * scalingFactor)
+		const uint32_t d = uint32_t(md_id[i]);
+		uint32_t o = off[i];
+		if (!row_begin) {
+			keys[o] = rank_and_id ? ((unsigned long long)(255u - rank) << 32) | d : ((unsigned long long)d << 8) | rank;
+		} else {
+			for (uint32_t r = row_begin[d]; r < row_begin[d + 1]; ++r) {
+				const uint32_t row = uint32_t(row_ids[r]);
+				if (!row_status || row_status[row]) {
+					keys[o++] = rank_and_id ? ((unsigned long long)(255u - rank) << 32) | row : ((unsigned long long)row << 8) | rank;
+				}
+			}
+		}
+	}
+}
+
 unsigned gridFor(uint64_t n, int sm) { return unsigned(std::min<uint64_t>((n + kFtThreads - 1) / kFtThreads, uint64_t(sm) * 16)); }
 
 thread_local rxgpu_ft_stats g_ft_stats{};
@@ -726,6 +803,16 @@ struct rxgpu_ft_index {
 	DevBuf<unsigned long long> last_ptr, next_ptr;
 	DevBuf<uint32_t> last_n, next_n;
 	DevBuf<uint16_t> ext_cnt, ext_last_term;
+	// vdoc -> row ids (IndexText::vdocs_[vdoc].RowIds(), rxgpu_ft_set_rows) and the scratch of rxgpu_ft_select
+	DevBuf<uint32_t> row_begin;
+	DevBuf<int32_t> row_ids;
+	bool has_rows = false;
+	uint64_t max_row = 0;
+	DevBuf<uint8_t> row_status, sort_tmp;
+	DevBuf<uint32_t> post_cnt, post_off, post_scalars;
+	DevBuf<unsigned long long> post_keys, post_keys_sorted;
+	PinBuf<unsigned long long> h_keys;
+	PinBuf<uint32_t> h_post;
 	~rxgpu_ft_index() {
 		cudaSetDevice(device);
 		for (auto& l : lists) {
@@ -892,8 +979,17 @@ void rxgpu_ft_last_stats(rxgpu_ft_stats* out) {
 	}
 }
 
-int rxgpu_ft_merge(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nterms, const rxgpu_ft_term* terms, const uint8_t* excluded,
-				   int rank_sort_type, uint64_t max_out, rxgpu_ft_merge_info* out, uint64_t* out_n) {
+}  // extern "C"
+
+namespace {
+struct SelectReq {  // rxgpu_ft_select: post-processing and IndexText::afterSelect on the device
+	const uint8_t* row_status;
+	uint64_t limit;
+	int32_t* out_row_ids;
+	float* out_ranks;
+};
+int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nterms, const rxgpu_ft_term* terms, const uint8_t* excluded,
+				int rank_sort_type, uint64_t max_out, rxgpu_ft_merge_info* out, uint64_t* out_n, const SelectReq* sel) {
 	if (!ft || !cfg || !out_n || (nterms && !terms)) {
 		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
 	}
@@ -1199,6 +1295,81 @@ int rxgpu_ft_merge(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nter
 		g_ft_stats.launches++;
 	}
 	RX_CUDA(cudaGetLastError());
+	if (sel) {
+		// postProcessResults (drop ranks below minRank, uint8 normalisation by the global maximum) + afterSelect (vdoc -> row ids, optional
+		// external statuses) + sortAfterSelect ((rank desc, row id asc) or row id asc) without leaving the device; only the first
+		// `limit` rows travel back
+		const bool rankAndId = rank_sort_type == 1;
+		RX_CUDA(ft->post_scalars.ensure(4));
+		RX_CUDA(ft->post_cnt.ensure(maxMerged));
+		RX_CUDA(ft->post_off.ensure(maxMerged));
+		RX_CUDA(ft->h_post.ensure(4));
+		const uint8_t* d_status = nullptr;
+		if (sel->row_status) {
+			const uint64_t nrows = ft->has_rows ? ft->max_row + 1 : N;
+			RX_CUDA(ft->row_status.ensure(nrows));
+			RX_CUDA(cudaMemcpyAsync(ft->row_status.p, sel->row_status, nrows, cudaMemcpyHostToDevice, st));
+			d_status = ft->row_status.p;
+		}
+		const uint32_t* rb = ft->has_rows ? ft->row_begin.p : nullptr;
+		const int32_t* ri = ft->has_rows ? ft->row_ids.p : nullptr;
+		ft_post_scale<<<1, 1024, 0, st>>>(ms.md_proc, ms.n_docs, ft->post_scalars.p);
+		ft_post_count<<<gridFor(maxMerged, sm), kFtThreads, 0, st>>>(ms.md_id, ms.md_proc, ms.n_docs, float(cfg->min_rank), rb, ri, d_status, maxMerged,
+																   ft->post_cnt.p);
+		size_t tmpBytes = 0;
+		cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, ft->post_cnt.p, ft->post_off.p, int(maxMerged), st);
+		RX_CUDA(ft->sort_tmp.ensure(tmpBytes));
+		cub::DeviceScan::ExclusiveSum(ft->sort_tmp.p, tmpBytes, ft->post_cnt.p, ft->post_off.p, int(maxMerged), st);
+		// rows total = off[n - 1] + cnt[n - 1]: read it (and n) back to size the key arrays and the sort
+		RX_CUDA(cudaMemcpyAsync(ft->h_post.p, ms.n_docs, 4, cudaMemcpyDeviceToHost, st));
+		RX_CUDA(cudaStreamSynchronize(st));
+		const uint32_t nMerged = ft->h_post.p[0];
+		uint32_t rowsTotal = 0;
+		if (nMerged) {
+			uint32_t lastOff = 0, lastCnt = 0;
+			RX_CUDA(cudaMemcpyAsync(&lastOff, ft->post_off.p + (nMerged - 1), 4, cudaMemcpyDeviceToHost, st));
+			RX_CUDA(cudaMemcpyAsync(&lastCnt, ft->post_cnt.p + (nMerged - 1), 4, cudaMemcpyDeviceToHost, st));
+			RX_CUDA(cudaStreamSynchronize(st));
+			rowsTotal = lastOff + lastCnt;
+		}
+		g_ft_stats.launches += 3;
+		if (rowsTotal) {
+			RX_CUDA(ft->post_keys.ensure(rowsTotal));
+			RX_CUDA(ft->post_keys_sorted.ensure(rowsTotal));
+			ft_post_emit<<<gridFor(nMerged, sm), kFtThreads, 0, st>>>(ms.md_id, ms.md_proc, ms.n_docs, ft->post_scalars.p, rb, ri, d_status,
+																	 ft->post_cnt.p, ft->post_off.p, rankAndId ? 1 : 0, ft->post_keys.p,
+																	 ft->post_scalars.p + 1);
+			size_t sortBytes = 0;
+			cub::DeviceRadixSort::SortKeys(nullptr, sortBytes, ft->post_keys.p, ft->post_keys_sorted.p, int(rowsTotal), 0, 40, st);
+			RX_CUDA(ft->sort_tmp.ensure(sortBytes));
+			cub::DeviceRadixSort::SortKeys(ft->sort_tmp.p, sortBytes, ft->post_keys.p, ft->post_keys_sorted.p, int(rowsTotal), 0, 40, st);
+			g_ft_stats.launches += 2;
+		}
+		if (!trivial) {
+			RX_CUDA(cudaGetLastError());
+		}
+		RX_CUDA(cudaEventRecord(e1, st));
+		const uint64_t nout = std::min<uint64_t>(rowsTotal, sel->limit);
+		RX_CUDA(ft->h_keys.ensure(std::max<uint64_t>(nout, 1)));
+		if (nout) {
+			RX_CUDA(cudaMemcpyAsync(ft->h_keys.p, ft->post_keys_sorted.p, nout * 8, cudaMemcpyDeviceToHost, st));
+		}
+		RX_CUDA(cudaStreamSynchronize(st));
+		RX_CUDA(cudaEventElapsedTime(&g_ft_stats.device_ms, e0, e1));
+		ft->idoff_clean = !trivial;
+		for (uint64_t i = 0; i < nout; ++i) {
+			const unsigned long long k = ft->h_keys.p[i];
+			if (rankAndId) {
+				sel->out_row_ids[i] = int32_t(uint32_t(k));
+				sel->out_ranks[i] = float(255u - uint32_t(k >> 32));
+			} else {
+				sel->out_row_ids[i] = int32_t(uint32_t(k >> 8));
+				sel->out_ranks[i] = float(uint32_t(k & 0xFF));
+			}
+		}
+		*out_n = rowsTotal;
+		return 0;
+	}
 	RX_CUDA(cudaEventRecord(e1, st));
 	// the merged documents (<= merge_limit entries, 9 bytes each) come back in full: their number is not known before the copy
 	RX_CUDA(cudaMemcpyAsync(ft->h_n.p, ms.n_docs, 4, cudaMemcpyDeviceToHost, st));
@@ -1253,6 +1424,67 @@ int rxgpu_ft_merge(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nter
 		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
 	}
 	return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int rxgpu_ft_merge(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nterms, const rxgpu_ft_term* terms, const uint8_t* excluded,
+				   int rank_sort_type, uint64_t max_out, rxgpu_ft_merge_info* out, uint64_t* out_n) {
+	return ftMergeImpl(ft, cfg, nterms, terms, excluded, rank_sort_type, max_out, out, out_n, nullptr);
+}
+
+int rxgpu_ft_set_rows(rxgpu_ft_index* ft, const uint32_t* row_begin, const int32_t* row_ids) {
+	if (!ft) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	RX_CUDA(cudaSetDevice(ft->device));
+	std::lock_guard<std::mutex> lck(ft->mtx);
+	if (!row_begin) {
+		ft->has_rows = false;
+		return 0;
+	}
+	const uint32_t n = ft->total_docs;
+	if (row_begin[0] != 0) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: row_begin must start at 0");
+	}
+	uint64_t maxRow = 0;
+	for (uint32_t d = 0; d < n; ++d) {
+		if (row_begin[d + 1] < row_begin[d]) {
+			return fail(RXGPU_ERR_PARAMS, "rxgpu: row_begin must be non-decreasing");
+		}
+	}
+	const uint64_t total = row_begin[n];
+	if (total && !row_ids) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	for (uint64_t i = 0; i < total; ++i) {
+		if (row_ids[i] < 0) {
+			return fail(RXGPU_ERR_PARAMS, "rxgpu: negative row id");
+		}
+		maxRow = std::max<uint64_t>(maxRow, uint64_t(row_ids[i]));
+	}
+	RX_CUDA(ft->row_begin.ensure(size_t(n) + 1));
+	RX_CUDA(ft->row_ids.ensure(std::max<uint64_t>(total, 1)));
+	RX_CUDA(cudaMemcpy(ft->row_begin.p, row_begin, (size_t(n) + 1) * 4, cudaMemcpyHostToDevice));
+	if (total) {
+		RX_CUDA(cudaMemcpy(ft->row_ids.p, row_ids, total * 4, cudaMemcpyHostToDevice));
+	}
+	ft->max_row = maxRow;
+	ft->has_rows = true;
+	return 0;
+}
+
+int rxgpu_ft_select(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nterms, const rxgpu_ft_term* terms, const uint8_t* excluded,
+					const uint8_t* row_status, int rank_sort_type, uint64_t limit, int32_t* out_row_ids, float* out_ranks, uint64_t* out_n) {
+	if (rank_sort_type != 1 && rank_sort_type != 3) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: rxgpu_ft_select orders by RankAndID (1) or IDOnly (3); use rxgpu_ft_merge for the other sort types");
+	}
+	if (limit && (!out_row_ids || !out_ranks)) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	const SelectReq sel{row_status, limit, out_row_ids, out_ranks};
+	return ftMergeImpl(ft, cfg, nterms, terms, excluded, rank_sort_type, 0, nullptr, out_n, &sel);
 }
 
 }  // extern "C"

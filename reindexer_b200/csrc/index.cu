@@ -325,11 +325,11 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 	g_stats.launches += 2;
 	const uint32_t ntiles = uint32_t((ix->size + kTcTileRows - 1) / kTcTileRows);
 	bool launched = false;
-	if ((ix->tc_variant == 0 || ix->tc_variant == 5) && kchunks <= kTqMaxKchunks) {
-		// query block in tensor memory, deep TMA ring, row tiles multicast to a cluster of up to 4 CTAs.  Default: knn_tc_filter_k
-		// (K-split query block, accumulators of 128 rows); tc_variant 5: knn_tc_filter_q (whole block in TMEM, accumulators of 64 rows)
+	if ((ix->tc_variant == 0 || ix->tc_variant == 7) && kchunks <= kTqMaxKchunks) {
+		// query block in tensor memory, deep TMA ring, row tiles multicast to a cluster of up to 4 CTAs.  Default: knn_tc_filter_q (whole
+		// block in TMEM, accumulators of 64 rows; measured fastest); tc_variant 7: knn_tc_filter_k (K-split query block, accumulators of 128 rows)
 		using TqKernel = void (*)(TqArgs);
-		const bool ksplit = ix->tc_variant == 0;
+		const bool ksplit = ix->tc_variant == 7;
 		const TqKernel kernels[4] = {ksplit ? knn_tc_filter_k<1> : knn_tc_filter_q<1>, ksplit ? knn_tc_filter_k<2> : knn_tc_filter_q<2>,
 									 ksplit ? knn_tc_filter_k<4> : knn_tc_filter_q<4>, ksplit ? knn_tc_filter_k<4> : knn_tc_filter_q<8>};
 		auto kernelOf = [&](int c) { return kernels[c == 8 ? 3 : (c == 4 ? 2 : (c == 2 ? 1 : 0))]; };
@@ -1013,7 +1013,7 @@ int rxgpu_set_tensor_core_filter(rxgpu_index* ix, int mode) {
 		return fail(RXGPU_ERR_PARAMS, "rxgpu: tensor-core filter mode must be in 0..9");
 	}
 	ix->tc_mode = uint32_t(mode >= 3 ? 1 : mode);
-	ix->tc_variant = (mode == 3 || mode == 4) ? uint32_t(mode) : ((mode == 5 || mode == 6 || mode == 9) ? 5u : 0u);
+	ix->tc_variant = (mode == 3 || mode == 4) ? uint32_t(mode) : ((mode == 7 || mode == 8) ? 7u : 0u);
 	ix->tc_cluster_max = (mode == 5 || mode == 7) ? 1u : ((mode == 6 || mode == 8) ? 4u : (mode == 9 ? 8u : 0u));
 	return 0;
 }

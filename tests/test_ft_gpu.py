@@ -133,3 +133,47 @@ def test_packed_posting_lists_give_the_same_merge():
             x, _ = F.best_merge(q)
             y, _ = gpu_merge(q, packed=packed)
             assert_same_merge(x, y, F.RANK_AND_ID, ctx=f"seed {seed}")
+
+
+def test_select_after_merge_on_device():
+    """rxgpu_ft_select = merge + postProcessResults + IndexText::afterSelect + sortAfterSelect on the device: the first `limit` rows in
+    (rank desc, row id asc) order must equal the oracle's merge followed by the reference's ordering rule (indextext.cc:480-520), with
+    a vdoc -> row ids expansion and external row statuses too"""
+    import reindexer_b200 as rx
+
+    for seed in range(30):
+        rng = np.random.default_rng(7000 + seed)
+        total = int(rng.integers(200, 4000))
+        p = random_problem(7000 + seed, total_docs=total, nfields=1 + seed % 2, nterms=1 + seed % 3,
+                           merge_limit=int(rng.integers(20, 200)) if seed % 3 == 0 else 20000)
+        ref, _ = F.best_merge(p, F.RANK_AND_ID)
+        ft = rx.GpuFtIndex(p.total_docs, p.words, p.avg, p.removed)
+        ids = [ft.add_postings(d, b, q) for d, b, q in p.lists]
+        terms = [dict(t, postings=[ids[int(x)] for x in t["postings"]]) for t in p.terms]
+        # (a) identity rows: vdoc i = row i
+        want = F.after_select_order(ref)
+        for limit in (10, 100, len(ref) + 5):
+            got_ids, got_ranks, n = ft.select(p.cfg, p.field_cfg, terms, limit, excluded=p.excluded)
+            assert n == len(want)
+            m = min(limit, len(want))
+            assert (got_ids == want["id"][:m]).all() and (got_ranks == want["normalized_proc"][:m].astype(np.float32)).all(), (seed, limit)
+        got_ids, got_ranks, n = ft.select(p.cfg, p.field_cfg, terms, len(ref) + 5, excluded=p.excluded, rank_sort_type=F.ID_ONLY)
+        o = np.argsort(ref["id"], kind="stable")
+        assert (got_ids == ref["id"][o]).all() and (got_ranks == ref["normalized_proc"][o].astype(np.float32)).all()
+        # (b) vdocs that own several rows (duplicated documents share one vdoc) + external statuses on rows
+        nrows_of = rng.integers(0, 4, size=total).astype(np.uint32)
+        nrows_of[0] = 0
+        row_begin = np.concatenate([[0], np.cumsum(nrows_of)]).astype(np.uint32)
+        row_ids = rng.permutation(int(row_begin[-1])).astype(np.int32)
+        status = (rng.random(int(row_begin[-1]) + 1) < 0.8).astype(np.uint8)
+        ft.set_rows(row_begin, row_ids)
+        exp = []
+        for e in ref:
+            for r in row_ids[row_begin[e["id"]]:row_begin[e["id"] + 1]]:
+                if status[r]:
+                    exp.append((int(r), int(e["normalized_proc"])))
+        exp.sort(key=lambda x: (-x[1], x[0]))
+        got_ids, got_ranks, n = ft.select(p.cfg, p.field_cfg, terms, 50, excluded=p.excluded, row_status=status)
+        assert n == len(exp)
+        assert got_ids.tolist() == [x[0] for x in exp[:50]] and got_ranks.tolist() == [float(x[1]) for x in exp[:50]], seed
+        ft.close()

@@ -35,8 +35,8 @@ def test_tc_path_is_bit_identical_to_exact_scan(metric, n, dim, nq, k):
     assert (d0.view(np.uint32) == d1.view(np.uint32)).all()
     assert st["tc_fallbacks"] == 0 and 0 < st["tc_candidates"] < nq * 4096
     # every kernel variant gives the same bits: 3 / 4 = queries in shared memory (1 CTA / CTA pair with TMA multicast),
-    # 5 / 6 = whole query block in TMEM (accumulators of 64 rows) with single CTAs / clusters of up to 4 CTAs,
-    # 7 / 8 = K-split query block (TMEM + shared memory, accumulators of 128 rows; the default) with single CTAs / clusters
+    # 5 / 6 = whole query block in TMEM (accumulators of 64 rows; the default) with single CTAs / clusters of up to 4 CTAs,
+    # 7 / 8 = K-split query block (TMEM + shared memory, accumulators of 128 rows) with single CTAs / clusters
     # 9 = knn_tc_filter_q with clusters of up to 8 CTAs (one launch serves 1024 queries)
     for mode, kernel in ((3, 1), (4, 1), (5, 2), (6, 2), (7, 3), (8, 3), (9, 2)):
         gpu.set_tensor_core_filter(mode)
@@ -45,7 +45,7 @@ def test_tc_path_is_bit_identical_to_exact_scan(metric, n, dim, nq, k):
         if dim <= 768:
             assert s2["tc_kernel"] == kernel, (mode, s2)
         assert (l2 == l0).all() and (d2.view(np.uint32) == d0.view(np.uint32)).all(), mode
-    assert st["tc_kernel"] == (3 if dim <= 768 else 1)
+    assert st["tc_kernel"] == (2 if dim <= 768 else 1)
     if nq > 128 and dim <= 768:
         assert st["tc_cluster"] == (4 if nq > 256 else 2)  # default: clusters of up to four CTAs share every row tile
 
