@@ -162,6 +162,11 @@ typedef struct {
 } rxgpu_select_params;
 int rxgpu_select_knn(const rxgpu_index*, const float* query /* dim floats, NOT normalised */, const rxgpu_select_params*,
 					 uint64_t max_out, int32_t* out_row_ids, float* out_ranks, uint64_t* out_n);
+/* the post-processing step alone, on the host (no device involved): `dist` / `label` = a map's answer best-first in map space (what
+ * SearchKnn / SearchRange return after the worst->best drain); writes at most n rows.  Used by adapters that get their hits elsewhere
+ * (a sharded search, an HNSW or IVF map) and pinned against the reference's own select code by tests/test_select_pin.py. */
+int rxgpu_select_postprocess(int metric, const rxgpu_select_params*, uint64_t n, const float* dist, const uint64_t* label, int32_t* out_row_ids,
+							 float* out_ranks, uint64_t* out_n);
 
 /* ---------------------------------------------------------------- HNSW search on a reference-built graph
  * hnswlib::HierarchicalNSWImpl<float>::SearchKnn                core/index/float_vector/hnswlib/hnswalg.h:1978-2012

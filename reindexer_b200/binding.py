@@ -119,6 +119,7 @@ _SIGNATURES = {
     "rxgpu_tie_replay": (C.c_int, [C.c_uint32, C.c_float, C.c_uint32, _f32p, _u64p, _u64p, C.c_uint32, _f32p, _u64p, _u64p, _f32p,
                                    _u64p, _u32p]),
     "rxgpu_select_knn": (C.c_int, [C.c_void_p, _f32p, C.POINTER(SelectParams), C.c_uint64, _i32p, _f32p, _u64p]),
+    "rxgpu_select_postprocess": (C.c_int, [C.c_int, C.POINTER(SelectParams), C.c_uint64, _f32p, _u64p, _i32p, _f32p, _u64p]),
     "rxgpu_hnsw_import": (C.c_int, [C.c_void_p, C.POINTER(HnswGraph)]),
     "rxgpu_hnsw_search_knn": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, C.c_uint32, C.c_uint32, _f32p, _u64p, _u32p, _u32p]),
     "rxgpu_hnsw_mark_deleted": (C.c_int, [C.c_void_p, C.c_uint64]),
@@ -419,6 +420,18 @@ class ShardComm:
         oc = np.zeros(nq, np.uint32)
         _check(self._lib.rxgpu_sharded_search_knn(self._h, shard._h, nq, qp, on_dev, k, _p(od, _f32p), _p(ol, _u64p), _p(oc, _u32p)))
         return od, ol, oc
+
+
+def select_postprocess(metric, dist, label, k=None, has_radius=False, need_sort=True, is_array=False, raw=False):
+    """HnswIndexBase::select / selectRaw post-processing of a map's best-first answer (host only): (row_ids, ranks)"""
+    d = np.ascontiguousarray(dist, np.float32)
+    l = np.ascontiguousarray(label, np.uint64)
+    prm = SelectParams(k or 0, int(has_radius), 0.0, int(need_sort), int(is_array), int(raw))
+    ids = np.zeros(max(len(d), 1), np.int32)
+    ranks = np.zeros(max(len(d), 1), np.float32)
+    n = C.c_uint64(0)
+    _check(lib().rxgpu_select_postprocess(metric, C.byref(prm), len(d), _p(d, _f32p), _p(l, _u64p), _p(ids, _i32p), _p(ranks, _f32p), C.byref(n)))
+    return ids[:n.value], ranks[:n.value]
 
 
 def merge_shards(k, dist, idx, label, count, shard_base):

@@ -807,7 +807,7 @@ struct rxgpu_ft_index {
 	DevBuf<uint32_t> row_begin;
 	DevBuf<int32_t> row_ids;
 	bool has_rows = false;
-	uint64_t max_row = 0;
+	uint64_t max_row = 0, max_rows_per_doc = 1;
 	DevBuf<uint8_t> row_status, sort_tmp;
 	DevBuf<uint32_t> post_cnt, post_off, post_scalars;
 	DevBuf<unsigned long long> post_keys, post_keys_sorted;
@@ -1320,41 +1320,63 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nterms,
 		cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, ft->post_cnt.p, ft->post_off.p, int(maxMerged), st);
 		RX_CUDA(ft->sort_tmp.ensure(tmpBytes));
 		cub::DeviceScan::ExclusiveSum(ft->sort_tmp.p, tmpBytes, ft->post_cnt.p, ft->post_off.p, int(maxMerged), st);
-		// rows total = off[n - 1] + cnt[n - 1]: read it (and n) back to size the key arrays and the sort
-		RX_CUDA(cudaMemcpyAsync(ft->h_post.p, ms.n_docs, 4, cudaMemcpyDeviceToHost, st));
-		RX_CUDA(cudaStreamSynchronize(st));
-		const uint32_t nMerged = ft->h_post.p[0];
-		uint32_t rowsTotal = 0;
-		if (nMerged) {
-			uint32_t lastOff = 0, lastCnt = 0;
-			RX_CUDA(cudaMemcpyAsync(&lastOff, ft->post_off.p + (nMerged - 1), 4, cudaMemcpyDeviceToHost, st));
-			RX_CUDA(cudaMemcpyAsync(&lastCnt, ft->post_cnt.p + (nMerged - 1), 4, cudaMemcpyDeviceToHost, st));
-			RX_CUDA(cudaStreamSynchronize(st));
-			rowsTotal = lastOff + lastCnt;
-		}
 		g_ft_stats.launches += 3;
-		if (rowsTotal) {
-			RX_CUDA(ft->post_keys.ensure(rowsTotal));
-			RX_CUDA(ft->post_keys_sorted.ensure(rowsTotal));
+		// Key capacity: every merged document contributes at most max_rows_per_doc rows.  When that bound is small the whole chain
+		// (emit -> sort -> copy of the first `limit` keys) is enqueued without stopping for the host; unused slots hold a key above every
+		// valid one.  Otherwise the row total is read back first to size the sort.
+		const uint64_t capBound = uint64_t(maxMerged) * (ft->has_rows ? std::max<uint64_t>(ft->max_rows_per_doc, 1) : 1);
+		uint32_t rowsTotal = 0, nMerged = maxMerged;
+		uint64_t sortItems = capBound;
+		const bool noSync = capBound <= (1u << 20);
+		if (!noSync) {
+			RX_CUDA(cudaMemcpyAsync(ft->h_post.p, ms.n_docs, 4, cudaMemcpyDeviceToHost, st));
+			RX_CUDA(cudaStreamSynchronize(st));
+			nMerged = ft->h_post.p[0];
+			if (nMerged) {
+				uint32_t lastOff = 0, lastCnt = 0;
+				RX_CUDA(cudaMemcpyAsync(&lastOff, ft->post_off.p + (nMerged - 1), 4, cudaMemcpyDeviceToHost, st));
+				RX_CUDA(cudaMemcpyAsync(&lastCnt, ft->post_cnt.p + (nMerged - 1), 4, cudaMemcpyDeviceToHost, st));
+				RX_CUDA(cudaStreamSynchronize(st));
+				rowsTotal = lastOff + lastCnt;
+			}
+			sortItems = rowsTotal;
+		}
+		if (sortItems) {
+			RX_CUDA(ft->post_keys.ensure(sortItems));
+			RX_CUDA(ft->post_keys_sorted.ensure(sortItems));
+			if (noSync) {
+				RX_CUDA(cudaMemsetAsync(ft->post_keys.p, 0xFF, sortItems * 8, st));  // padding: bits 0..40 all set > any valid 40-bit key
+				RX_CUDA(cudaMemsetAsync(ft->post_scalars.p + 1, 0, 4, st));
+			}
 			ft_post_emit<<<gridFor(nMerged, sm), kFtThreads, 0, st>>>(ms.md_id, ms.md_proc, ms.n_docs, ft->post_scalars.p, rb, ri, d_status,
 																	 ft->post_cnt.p, ft->post_off.p, rankAndId ? 1 : 0, ft->post_keys.p,
 																	 ft->post_scalars.p + 1);
 			size_t sortBytes = 0;
-			cub::DeviceRadixSort::SortKeys(nullptr, sortBytes, ft->post_keys.p, ft->post_keys_sorted.p, int(rowsTotal), 0, 40, st);
+			cub::DeviceRadixSort::SortKeys(nullptr, sortBytes, ft->post_keys.p, ft->post_keys_sorted.p, int(sortItems), 0, 41, st);
 			RX_CUDA(ft->sort_tmp.ensure(sortBytes));
-			cub::DeviceRadixSort::SortKeys(ft->sort_tmp.p, sortBytes, ft->post_keys.p, ft->post_keys_sorted.p, int(rowsTotal), 0, 40, st);
+			cub::DeviceRadixSort::SortKeys(ft->sort_tmp.p, sortBytes, ft->post_keys.p, ft->post_keys_sorted.p, int(sortItems), 0, 41, st);
 			g_ft_stats.launches += 2;
 		}
-		if (!trivial) {
-			RX_CUDA(cudaGetLastError());
-		}
+		RX_CUDA(cudaGetLastError());
 		RX_CUDA(cudaEventRecord(e1, st));
-		const uint64_t nout = std::min<uint64_t>(rowsTotal, sel->limit);
-		RX_CUDA(ft->h_keys.ensure(std::max<uint64_t>(nout, 1)));
-		if (nout) {
-			RX_CUDA(cudaMemcpyAsync(ft->h_keys.p, ft->post_keys_sorted.p, nout * 8, cudaMemcpyDeviceToHost, st));
+		if (noSync) {  // one copy of what the caller asked for + the row total, one synchronisation
+			const uint64_t want = std::min<uint64_t>(sortItems, sel->limit);
+			RX_CUDA(ft->h_keys.ensure(std::max<uint64_t>(want, 1)));
+			if (want) {
+				RX_CUDA(cudaMemcpyAsync(ft->h_keys.p, ft->post_keys_sorted.p, want * 8, cudaMemcpyDeviceToHost, st));
+			}
+			RX_CUDA(cudaMemcpyAsync(ft->h_post.p, ft->post_scalars.p + 1, 4, cudaMemcpyDeviceToHost, st));
+			RX_CUDA(cudaStreamSynchronize(st));
+			rowsTotal = ft->h_post.p[0];
 		}
-		RX_CUDA(cudaStreamSynchronize(st));
+		const uint64_t nout = std::min<uint64_t>(rowsTotal, sel->limit);
+		if (!noSync) {
+			RX_CUDA(ft->h_keys.ensure(std::max<uint64_t>(nout, 1)));
+			if (nout) {
+				RX_CUDA(cudaMemcpyAsync(ft->h_keys.p, ft->post_keys_sorted.p, nout * 8, cudaMemcpyDeviceToHost, st));
+			}
+			RX_CUDA(cudaStreamSynchronize(st));
+		}
 		RX_CUDA(cudaEventElapsedTime(&g_ft_stats.device_ms, e0, e1));
 		ft->idoff_clean = !trivial;
 		for (uint64_t i = 0; i < nout; ++i) {
@@ -1448,11 +1470,12 @@ int rxgpu_ft_set_rows(rxgpu_ft_index* ft, const uint32_t* row_begin, const int32
 	if (row_begin[0] != 0) {
 		return fail(RXGPU_ERR_PARAMS, "rxgpu: row_begin must start at 0");
 	}
-	uint64_t maxRow = 0;
+	uint64_t maxRow = 0, maxPerDoc = 1;
 	for (uint32_t d = 0; d < n; ++d) {
 		if (row_begin[d + 1] < row_begin[d]) {
 			return fail(RXGPU_ERR_PARAMS, "rxgpu: row_begin must be non-decreasing");
 		}
+		maxPerDoc = std::max<uint64_t>(maxPerDoc, row_begin[d + 1] - row_begin[d]);
 	}
 	const uint64_t total = row_begin[n];
 	if (total && !row_ids) {
@@ -1471,6 +1494,7 @@ int rxgpu_ft_set_rows(rxgpu_ft_index* ft, const uint32_t* row_begin, const int32
 		RX_CUDA(cudaMemcpy(ft->row_ids.p, row_ids, total * 4, cudaMemcpyHostToDevice));
 	}
 	ft->max_row = maxRow;
+	ft->max_rows_per_doc = maxPerDoc;
 	ft->has_rows = true;
 	return 0;
 }

@@ -1355,6 +1355,38 @@ int rxgpu_last_range_results(uint64_t offset, uint64_t n, float* out_dist, uint6
 	return 0;
 }
 
+int rxgpu_select_postprocess(int metric, const rxgpu_select_params* p, uint64_t n, const float* dist, const uint64_t* label, int32_t* out_row_ids,
+							 float* out_ranks, uint64_t* out_n) {
+	if (!p || !out_n || (n && (!dist || !label || !out_row_ids || !out_ranks)) || metric < 0 || metric > 2) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: bad argument");
+	}
+	try {
+		std::vector<Hit> res(n);
+		for (uint64_t i = 0; i < n; ++i) {
+			res[i] = Hit{dist[i], 0, label[i]};
+		}
+		SelectParams sp;
+		sp.metric = metric;
+		sp.needSort = p->need_sort != 0;
+		sp.isArray = p->is_array != 0;
+		sp.raw = p->raw != 0;
+		sp.hasK = p->k != 0;
+		sp.k = p->k;
+		sp.hasRadius = p->has_radius != 0;
+		std::vector<int32_t> ids;
+		std::vector<float> ranks;
+		selectPostprocess(sp, res, ids, ranks);
+		for (size_t i = 0; i < ids.size(); ++i) {
+			out_row_ids[i] = ids[i];
+			out_ranks[i] = ranks[i];
+		}
+		*out_n = ids.size();
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
+	}
+	return 0;
+}
+
 int rxgpu_select_knn(const rxgpu_index* ix, const float* query, const rxgpu_select_params* p, uint64_t max_out, int32_t* out_row_ids,
 					 float* out_ranks, uint64_t* out_n) {
 	if (int rc = checkIndex(ix)) {
