@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstring>
 #include <span>
+#include <string>
+#include <atomic>
 #include <utility>
 #include <vector>
 
@@ -19,10 +21,51 @@ extern "C" float port_synth_value(uint64_t seed, uint64_t index);  // oracle/knn
 
 using Results = std::vector<std::vector<std::pair<float, uint64_t>>>;
 
+// In-memory stand-ins for the namespace's index-cache writer / reader (hnsw_index.cc:389-507): the graph goes out WITHOUT the vectors
+// (only the primary key of every live element), the reader fetches each vector back by its key -- here from a map the test keeps.
+struct Token {
+	uint64_t u = 0;
+	int64_t i = 0;
+	float f = 0.f;
+	std::string s;
+};
+class MemWriter final : public hnswlib::IWriter {
+public:
+	std::vector<Token> tokens;
+	void PutVarUInt(uint64_t v) override { tokens.push_back(Token{v, 0, 0.f, {}}); }
+	void PutVarUInt(uint32_t v) override { tokens.push_back(Token{v, 0, 0.f, {}}); }
+	void PutVarInt(int64_t v) override { tokens.push_back(Token{0, v, 0.f, {}}); }
+	void PutVarInt(int32_t v) override { tokens.push_back(Token{0, v, 0.f, {}}); }
+	void PutVString(std::string_view v) override { tokens.push_back(Token{0, 0, 0.f, std::string(v)}); }
+	void PutFloat(float v) override { tokens.push_back(Token{0, 0, v, {}}); }
+	void AppendPKByID(hnswlib::labeltype label) override { tokens.push_back(Token{label, 0, 0.f, {}}); }
+};
+class MemReader final : public hnswlib::IReader {
+public:
+	MemReader(const std::vector<Token>& t, const std::vector<std::vector<float>>& rows) : tokens_(t), rows_(rows) {}
+	uint64_t GetVarUInt() override { return tokens_[pos_++].u; }
+	int64_t GetVarInt() override { return tokens_[pos_++].i; }
+	std::string_view GetVString() override { return tokens_[pos_++].s; }
+	float GetFloat() override { return tokens_[pos_++].f; }
+	hnswlib::labeltype ReadPkEncodedData(float* destBuf) override {
+		const uint64_t label = tokens_[pos_++].u;
+		const auto& v = rows_[size_t(label >> 32)];
+		std::memcpy(destBuf, v.data(), v.size() * sizeof(float));
+		return label;
+	}
+	bool WithQuantizer() const override { return false; }
+
+private:
+	const std::vector<Token>& tokens_;
+	const std::vector<std::vector<float>>& rows_;
+	size_t pos_ = 0;
+};
+
 template <typename Map>
 Results drive(reindexer::VectorMetric metric, size_t dim, size_t n, size_t k, size_t ef, size_t nq) {
 	Map map(reindexer::IsArray_False, metric, dim, n / 2, 16, 200);
 	std::vector<float> v(dim);
+	std::vector<std::vector<float>> rowsByPk;  // what the namespace holds: vectors by row id
 	auto add = [&](size_t i) {
 		if (map.CurrentElementCount() >= map.MaxElements()) {
 			map.ResizeIndex(map.MaxElements() * 2);  // HnswIndexBase::upsert grows the map (hnsw_index.cc:89-92)
@@ -31,6 +74,10 @@ Results drive(reindexer::VectorMetric metric, size_t dim, size_t n, size_t k, si
 			v[c] = port_synth_value(177, i * dim + c) + 0.6f * port_synth_value(178, (i % 37) * dim + c);  // clustered
 		}
 		map.AddPointNoLock(reindexer::ConstFloatVectorView{std::span<const float>{v}}, reindexer::FloatVectorId{reindexer::IdType::FromNumber(int(i)), 0});
+		if (rowsByPk.size() <= i) {
+			rowsByPk.resize(i + 1);
+		}
+		rowsByPk[i] = v;
 	};
 	Results out;
 	std::vector<float> q(dim), qn(dim);
@@ -68,6 +115,14 @@ Results drive(reindexer::VectorMetric metric, size_t dim, size_t n, size_t k, si
 	search(map, false);
 	const Map clone(std::as_const(map), map.MaxElements() + 10);  // COW namespace clone (hnsw_index.cc:66-68)
 	search(clone, false);
+	// index cache round trip (WriteIndexCache / LoadIndexCache, hnsw_index.cc:389-507; hnswalg.h:1213-1263, loader :297-...)
+	MemWriter w;
+	const std::atomic_int32_t cancel{0};
+	map.SaveIndex(w, cancel);
+	Map loaded(reindexer::IsArray_False, metric, dim, map.MaxElements(), 16, 200);
+	MemReader r(w.tokens, rowsByPk);
+	loaded.LoadIndex(r);
+	search(loaded, false);
 	return out;
 }
 
@@ -92,7 +147,7 @@ int main() {
 			nonEmpty += !ref[i].empty();
 		}
 		const bool ok = total == gpu.size() && same * 100 >= total * 95 && closeDist * 100 >= total * 95 && nonEmpty * 2 >= total;
-		std::printf("metric %d: %zu searches (knn, knn with tombstones, range, knn after more inserts, knn on a clone), identical ids %zu, distances within 1e-4 %zu, "
+		std::printf("metric %d: %zu searches (knn, knn with tombstones, range, knn after more inserts, knn on a clone, knn on a map restored from its index cache), identical ids %zu, distances within 1e-4 %zu, "
 					"non-empty %zu -> %s\n",
 					int(metric), total, same, closeDist, nonEmpty, ok ? "MATCH" : "MISMATCH");
 		bad += !ok;
