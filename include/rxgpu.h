@@ -215,6 +215,31 @@ int rxgpu_gather_labels_device(const rxgpu_index*, uint64_t n, const uint32_t* d
 int rxgpu_hnsw_search_range(const rxgpu_index*, const float* query /* host */, float radius, uint32_t ef, uint64_t max_out,
 							float* out_dist, uint64_t* out_label, uint64_t* out_n);
 
+/* ---------------------------------------------------------------- SQ8 scalar quantisation (the quantised HNSW map of the reference)
+ * HierarchicalNSWImpl<uint8_t> keeps every vector as dim uint8 codes plus ONE additive corrective offset
+ * (scalar_quantization/quantizer.h:93-125; hnswlib/hnswlib.h:255) and measures
+ *     dist(a, b) = alpha_2 * int_dist(code_a, code_b) + offset_a + offset_b        (hnswlib.h:192-197; IP / Cosine: negated;
+ *                  Cosine: times the row's norm coefficient and the query's 1 / ||q||, hnswalg.h:801,1854-1863)
+ * with int_dist = sum (a - b)^2 or sum a * b over the codes (tools/distances/l2_dist.cc:169, ip_dist.cc:163 -- exact integers).
+ * rxgpu_sq8_attach puts codes + offsets next to the fp32 rows in HBM: imported from the reference (codes != NULL: [size][dim] bytes and
+ * [size] floats, by internal id = row) or produced on the device from the rows with the reference's arithmetic (codes == NULL).
+ * Distances computed from them are bit-identical to the reference's: the integer part is exact, the float epilogue repeats its order. */
+typedef struct { /* hnswlib::QuantizingParams (scalar_quantization/quantization_params.h:47-106) */
+	float min_q, max_q, alpha, alpha_2, delta;
+} rxgpu_sq8_params;
+int rxgpu_sq8_attach(rxgpu_index*, const rxgpu_sq8_params*, const uint8_t* codes, const float* offsets);
+int rxgpu_sq8_export(const rxgpu_index*, uint8_t* codes /* size x dim */, float* offsets /* size */);
+/* the query as HierarchicalNSWImpl<uint8_t>::search prepares it (prepareData, hnswalg.h:510-535): codes[dim] + its corrective offset.
+ * query: pre-normalised for Cosine, query_norm = ||q|| then (ignored otherwise).  Host only. */
+int rxgpu_sq8_prepare_query(const rxgpu_index*, const float* query, float query_norm, uint8_t* codes, float* offset);
+/* exact top-k under the quantised metric: a dp4a scan of all codes with the fused top-k (the ground truth of the quantised HNSW
+ * search; 4x fewer HBM bytes than the fp32 scan).  query_norms: nq values of ||q|| for Cosine, NULL otherwise.  k <= 256. */
+int rxgpu_sq8_search_knn(const rxgpu_index*, uint32_t nq, const float* queries /* host, pre-normalised for Cosine */, const float* query_norms,
+						 uint32_t k, float* out_dist, uint64_t* out_label, uint32_t* out_count);
+/* HierarchicalNSWImpl<uint8_t>::SearchKnn on the imported graph: the HNSW kernel gathers codes instead of fp32 rows */
+int rxgpu_hnsw_search_knn_sq8(const rxgpu_index*, uint32_t nq, const float* queries /* host */, const float* query_norms, uint32_t k, uint32_t ef,
+							  float* out_dist, uint64_t* out_label, uint32_t* out_count, uint32_t* stats /* nq x 2 or NULL */);
+
 /* ---------------------------------------------------------------- IVF index (faiss::IndexIVFFlat as reindexer::IvfIndex drives it)
  * Replaces the search side of IvfIndex: map_->search(1, key, k, dists, ids, &IVFSearchParameters{nprobe})
  *   core/index/float_vector/ivf_index.cc:150-204 (callers), vendor_subdirs/faiss/IndexIVF.cpp (search_preassigned), IndexIVFFlat.cpp

@@ -487,11 +487,11 @@ class RefHnswSq8:
         assert self.lib.ref_hnsw_q_prepare_query(self.h, _p(q, _f32p), codes.ctypes.data, _p(off, _f32p)) == 0
         return codes, float(off[0])
 
-    def search_knn(self, q, k, ef=0):
+    def search_knn(self, q, k, ef=0, qnorm=None):
         q = np.ascontiguousarray(q, np.float32)
         d = np.empty(max(k, 1), np.float32)
         l = np.empty(max(k, 1), np.uint64)
-        n = self.lib.ref_hnsw_q_search_knn(self.h, _p(q, _f32p), 0, 0.0, k, ef, _p(d, _f32p), _p(l, _u64p))
+        n = self.lib.ref_hnsw_q_search_knn(self.h, _p(q, _f32p), int(qnorm is not None), float(qnorm or 0.0), k, ef, _p(d, _f32p), _p(l, _u64p))
         assert n >= 0, self.lib.ref_last_error().decode()
         return d[:n].copy(), l[:n].copy()
 

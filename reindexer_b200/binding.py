@@ -64,6 +64,10 @@ class FtTerm(C.Structure):
                 ("postings", _u32p), ("procs", _f32p), ("need_sum_rank", _u8p)]
 
 
+class Sq8Params(C.Structure):
+    _fields_ = [("min_q", C.c_float), ("max_q", C.c_float), ("alpha", C.c_float), ("alpha_2", C.c_float), ("delta", C.c_float)]
+
+
 class FtStats(C.Structure):
     _fields_ = [("launches", C.c_uint32), ("preselected", C.c_uint32), ("postings_scanned", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
                 ("device_ms", C.c_float)]
@@ -128,6 +132,11 @@ _SIGNATURES = {
     "rxgpu_hnsw_search_range": (C.c_int, [C.c_void_p, _f32p, C.c_float, C.c_uint32, C.c_uint64, _f32p, _u64p, C.POINTER(C.c_uint64)]),
     "rxgpu_hnsw_search_knn_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rxgpu_sq8_attach": (C.c_int, [C.c_void_p, C.POINTER(Sq8Params), _u8p, _f32p]),
+    "rxgpu_sq8_export": (C.c_int, [C.c_void_p, _u8p, _f32p]),
+    "rxgpu_sq8_prepare_query": (C.c_int, [C.c_void_p, _f32p, C.c_float, _u8p, _f32p]),
+    "rxgpu_sq8_search_knn": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, _f32p, C.c_uint32, _f32p, _u64p, _u32p]),
+    "rxgpu_hnsw_search_knn_sq8": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, _f32p, C.c_uint32, C.c_uint32, _f32p, _u64p, _u32p, _u32p]),
     "rxgpu_ivf_import": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, _u64p]),
     "rxgpu_ivf_search_knn": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, C.c_uint32, C.c_uint32, _f32p, _u64p, _u32p]),
     "rxgpu_ivf_search_range": (C.c_int, [C.c_void_p, _f32p, C.c_float, C.c_uint32, C.c_uint64, _f32p, _u64p, C.POINTER(C.c_uint64)]),
@@ -340,6 +349,56 @@ class GpuBruteforceSearch:
         _check(self._lib.rxgpu_hnsw_search_range(self._h, _p(q, _f32p), radius, ef, max_out, _p(d, _f32p), _p(l, _u64p), C.byref(n)))
         m = min(n.value, max_out)
         return d[:m], l[:m], n.value
+
+    # -- SQ8 (the reference's scalar quantisation of an HNSW map) ---------------------------------------------------------
+    def sq8_attach(self, params: dict, codes=None, offsets=None):
+        """params: min_q, max_q, alpha, alpha_2, delta (hnswlib::QuantizingParams).  codes/offsets from the reference, or None to
+        quantise the rows on the device with the reference's arithmetic."""
+        p = Sq8Params(params["min_q"], params["max_q"], params["alpha"], params["alpha_2"], params["delta"])
+        if codes is None:
+            _check(self._lib.rxgpu_sq8_attach(self._h, C.byref(p), None, None))
+        else:
+            c = np.ascontiguousarray(codes, np.uint8)
+            o = np.ascontiguousarray(offsets, np.float32)
+            assert c.shape == (self.size(), self.dim) and o.shape == (self.size(),)
+            _check(self._lib.rxgpu_sq8_attach(self._h, C.byref(p), _p(c, _u8p), _p(o, _f32p)))
+
+    def sq8_export(self):
+        codes = np.zeros((self.size(), self.dim), np.uint8)
+        offs = np.zeros(self.size(), np.float32)
+        _check(self._lib.rxgpu_sq8_export(self._h, _p(codes, _u8p), _p(offs, _f32p)))
+        return codes, offs
+
+    def sq8_prepare_query(self, query, query_norm=1.0):
+        q = np.ascontiguousarray(query, np.float32)
+        codes = np.zeros(self.dim, np.uint8)
+        off = C.c_float(0)
+        _check(self._lib.rxgpu_sq8_prepare_query(self._h, _p(q, _f32p), query_norm, _p(codes, _u8p), C.byref(off)))
+        return codes, off.value
+
+    def _sq8_search(self, fn, queries, k, query_norms, extra):
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
+        nq = q.shape[0]
+        qn = None if query_norms is None else np.ascontiguousarray(query_norms, np.float32)
+        d = np.zeros((nq, max(k, 1)), np.float32)
+        l = np.zeros((nq, max(k, 1)), np.uint64)
+        c = np.zeros(nq, np.uint32)
+        _check(fn(self._h, nq, _p(q, _f32p), None if qn is None else _p(qn, _f32p), k, *extra, _p(d, _f32p), _p(l, _u64p), _p(c, _u32p)))
+        return d, l, c
+
+    def sq8_search_knn(self, queries, k: int, query_norms=None):
+        return self._sq8_search(self._lib.rxgpu_sq8_search_knn, queries, k, query_norms, ())
+
+    def hnsw_search_knn_sq8(self, queries, k: int, ef: int = 0, query_norms=None):
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
+        nq = q.shape[0]
+        qn = None if query_norms is None else np.ascontiguousarray(query_norms, np.float32)
+        d = np.zeros((nq, max(k, 1)), np.float32)
+        l = np.zeros((nq, max(k, 1)), np.uint64)
+        c = np.zeros(nq, np.uint32)
+        _check(self._lib.rxgpu_hnsw_search_knn_sq8(self._h, nq, _p(q, _f32p), None if qn is None else _p(qn, _f32p), k, ef, _p(d, _f32p),
+                                                   _p(l, _u64p), _p(c, _u32p), None))
+        return d, l, c
 
     # -- IVF (lists trained and assigned by the reference's FAISS; rows of this index grouped by list) -------------------
     def ivf_import(self, centroids, list_sizes):

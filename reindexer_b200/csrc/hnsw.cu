@@ -23,6 +23,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "sq8.cuh"
 #include "../host/knn_select.h"
 
 using namespace rxgpu;
@@ -61,6 +62,14 @@ struct HnswArgs {
 	uint32_t enterpoint;
 	uint32_t nq, k, ef, words;
 	uint32_t out_stride;  // entries per query in out_dist / out_idx: the caller's k (a.k may be clamped to the row count)
+	// SQ8 (HierarchicalNSWImpl<uint8_t>): codes != null -> distances from the codes and corrective offsets, queries = qcodes
+	const uint8_t* codes;
+	const float* corr;
+	const uint8_t* qcodes;  // [nq][code_pitch]
+	const float* qcorr;     // [nq]
+	const float* qcoef;     // [nq] query norm coefficient (1 unless Cosine)
+	uint32_t code_pitch;
+	float alpha2;
 };
 
 __device__ __forceinline__ float4 ldg4(const float4* p) {
@@ -70,9 +79,63 @@ __device__ __forceinline__ float4 ldg4(const float4* p) {
 }
 
 // distances of `cnt` rows (ids in s_ids) to the query in sq4; results to s_d.  Per-row arithmetic == knn_scan_warp.
+// SQ8: two rows per step (16 lanes each, 16 codes per load); dist = qcoef * (+-(alpha2 * int_dist + qcorr + corr[row]) * norm_coef[row])
+// in the reference's operation order (hnswlib.h:147-165,192-197; hnswalg.h:801,935)
+template <bool kIsL2>
+__device__ __forceinline__ void warp_dists_sq8(const HnswArgs& a, const uint4* squ, const uint32_t* s_ids, uint32_t cnt, float* s_d, int lane,
+											   float qcorr, float qcoef) {
+	const uint32_t nch = a.code_pitch / 16;
+	const int half = lane >> 4, hl = lane & 15;
+	for (uint32_t g = 0; g < cnt; g += 2) {
+		const uint32_t id = s_ids[min(g + half, cnt - 1)];
+		const uint4* rp = reinterpret_cast<const uint4*>(a.codes + size_t(id) * a.code_pitch);
+		unsigned acc = 0;
+		for (uint32_t c = hl; c < nch; c += 16) {
+			uint4 v;
+			asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(rp + c));
+			const uint4 q = squ[c];
+			if constexpr (kIsL2) {
+				unsigned d;
+				d = __vabsdiffu4(v.x, q.x);
+				acc = __dp4a(d, d, acc);
+				d = __vabsdiffu4(v.y, q.y);
+				acc = __dp4a(d, d, acc);
+				d = __vabsdiffu4(v.z, q.z);
+				acc = __dp4a(d, d, acc);
+				d = __vabsdiffu4(v.w, q.w);
+				acc = __dp4a(d, d, acc);
+			} else {
+				acc = __dp4a(v.x, q.x, acc);
+				acc = __dp4a(v.y, q.y, acc);
+				acc = __dp4a(v.z, q.z, acc);
+				acc = __dp4a(v.w, q.w, acc);
+			}
+		}
+#pragma unroll
+		for (int off = 8; off > 0; off >>= 1) {
+			acc += __shfl_xor_sync(0xffffffffu, acc, off);
+		}
+		if (hl == 0 && g + half < cnt) {
+			float dist = __fadd_rn(__fadd_rn(__fmul_rn(a.alpha2, __uint2float_rn(acc)), qcorr), a.corr[id]);
+			if (!kIsL2) {
+				dist = -dist;
+				if (a.norm_coefs != nullptr) {
+					dist = __fmul_rn(dist, a.norm_coefs[id]);
+				}
+			}
+			s_d[g + half] = __fmul_rn(qcoef, dist);
+		}
+	}
+	__syncwarp();
+}
+
 template <bool kIsL2>
 __device__ __forceinline__ void warp_dists(const HnswArgs& a, const float4* sq4, const uint32_t* s_ids, uint32_t cnt, float* s_d,
-										   int lane) {
+										   int lane, float qcorr = 0.f, float qcoef = 1.f) {
+	if (a.codes != nullptr) {  // warp-uniform
+		warp_dists_sq8<kIsL2>(a, reinterpret_cast<const uint4*>(sq4), s_ids, cnt, s_d, lane, qcorr, qcoef);
+		return;
+	}
 	const float4* rows4 = reinterpret_cast<const float4*>(a.rows);
 	const uint32_t pitch4 = a.pitch >> 2;
 	const uint32_t nch = (a.dim + 127u) / 128u;
@@ -168,7 +231,16 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(const HnswArg
 		if (qi >= a.nq) {
 			break;
 		}
-		{  // stage the query, zero padded
+		float qcorr = 0.f, qcoef = 1.f;
+		if (a.codes != nullptr) {  // SQ8: the query's codes (already zero padded to code_pitch) + its corrective offset and coefficient
+			uint4* squ = reinterpret_cast<uint4*>(sq4);
+			const uint4* q = reinterpret_cast<const uint4*>(a.qcodes + size_t(qi) * a.code_pitch);
+			for (uint32_t c = lane; c < a.code_pitch / 16; c += 32) {
+				squ[c] = q[c];
+			}
+			qcorr = a.qcorr[qi];
+			qcoef = a.qcoef[qi];
+		} else {  // stage the query, zero padded
 			float* sq = reinterpret_cast<float*>(sq4);
 			const float* q = a.queries + size_t(qi) * a.dim;
 			for (uint32_t c = lane; c < dp4 * 4; c += 32) {
@@ -184,7 +256,7 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(const HnswArg
 			s_ids[0] = cur;
 		}
 		__syncwarp();
-		warp_dists<kIsL2>(a, sq4, s_ids, 1, s_d, lane);
+		warp_dists<kIsL2>(a, sq4, s_ids, 1, s_d, lane, qcorr, qcoef);
 		float curdist = s_d[0];
 		__syncwarp();
 		for (int level = a.maxlevel; level > 0; --level) {
@@ -200,7 +272,7 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(const HnswArg
 				n_hops++;
 				n_dist += cnt;
 				if (cnt) {
-					warp_dists<kIsL2>(a, sq4, s_ids, cnt, s_d, lane);
+					warp_dists<kIsL2>(a, sq4, s_ids, cnt, s_d, lane, qcorr, qcoef);
 				}
 				for (uint32_t j = 0; j < cnt; ++j) {  // sequential like the reference: strict <, first minimum wins
 					const float d = s_d[j];
@@ -317,7 +389,7 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(const HnswArg
 			if (ucnt == 0) {
 				continue;
 			}
-			warp_dists<kIsL2>(a, sq4, s_ids, ucnt, s_d, lane);
+			warp_dists<kIsL2>(a, sq4, s_ids, ucnt, s_d, lane, qcorr, qcoef);
 			// sequential accept logic of runLayer0Step (:931-957) over the batch, in neighbour order
 			for (uint32_t j = 0; j < ucnt; ++j) {
 				const float d = s_d[j];
@@ -658,8 +730,16 @@ int rxgpu_hnsw_import(rxgpu_index* ix, const rxgpu_hnsw_graph* g) {
 	return 0;
 }
 
-int rxgpu_hnsw_search_knn_device(const rxgpu_index* ix, uint32_t nq, const float* d_queries, uint32_t k, uint32_t ef, float* d_out_dist,
-								 uint32_t* d_out_idx, uint32_t* d_out_count, uint32_t* d_stats, void* stream) {
+}  // extern "C"
+
+namespace {
+struct Sq8Query {  // device pointers of the quantised query batch (rxgpu_hnsw_search_knn_sq8)
+	const uint8_t* qcodes;
+	const float* qcorr;
+	const float* qcoef;
+};
+int hnswSearchDevice(const rxgpu_index* ix, uint32_t nq, const float* d_queries, uint32_t k, uint32_t ef, float* d_out_dist, uint32_t* d_out_idx,
+					 uint32_t* d_out_count, uint32_t* d_stats, void* stream, const Sq8Query* sq) {
 	if (int rc = checkIndex(ix)) {
 		return rc;
 	}
@@ -723,6 +803,19 @@ int rxgpu_hnsw_search_knn_device(const rxgpu_index* ix, uint32_t nq, const float
 	a.out_stride = outStride;
 	a.ef = ef;
 	a.words = h->words;
+	if (sq) {
+		const rxgpu_sq8_device* s8 = ix->sq8;
+		if (!s8 || s8->index_version != ix->version || s8->n != h->n) {
+			return fail(RXGPU_ERR_LOGIC, "rxgpu: no SQ8 codes attached to this index (or the index changed since)");
+		}
+		a.codes = s8->codes.p;
+		a.corr = s8->corr.p;
+		a.code_pitch = s8->code_pitch;
+		a.alpha2 = s8->params.alpha_2;
+		a.qcodes = sq->qcodes;
+		a.qcorr = sq->qcorr;
+		a.qcoef = sq->qcoef;
+	}
 	const uint32_t dp4 = ((ix->dim + 127u) / 128u) * 32u;
 	const size_t smem = (size_t(dp4) * 16 + size_t((ef + 3u) & ~3u) * 8 + kMaxNeighbours * 8) * kHnswWarps;
 	if (smem > 200 * 1024) {
@@ -750,6 +843,98 @@ int rxgpu_hnsw_search_knn_device(const rxgpu_index* ix, uint32_t nq, const float
 												 " for the device search (more than 4096 waiting at once); rebuild the graph or search on the CPU map");
 			}
 		}
+	}
+	return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int rxgpu_hnsw_search_knn_device(const rxgpu_index* ix, uint32_t nq, const float* d_queries, uint32_t k, uint32_t ef, float* d_out_dist,
+								 uint32_t* d_out_idx, uint32_t* d_out_count, uint32_t* d_stats, void* stream) {
+	return hnswSearchDevice(ix, nq, d_queries, k, ef, d_out_dist, d_out_idx, d_out_count, d_stats, stream, nullptr);
+}
+
+// HierarchicalNSWImpl<uint8_t>::SearchKnn: the queries are quantised on the host exactly like prepareData does (hnswalg.h:510-535),
+// the kernel gathers codes + corrective offsets instead of fp32 rows
+int rxgpu_hnsw_search_knn_sq8(const rxgpu_index* ix, uint32_t nq, const float* queries, const float* query_norms, uint32_t k, uint32_t ef,
+							  float* out_dist, uint64_t* out_label, uint32_t* out_count, uint32_t* stats) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	if (nq == 0) {
+		return 0;
+	}
+	if (!queries || !out_dist || !out_label || !out_count) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	rxgpu_sq8_device* s8 = ix->sq8;
+	if (!ix->hnsw || !s8) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: the quantised HNSW search needs an imported graph and attached SQ8 codes");
+	}
+	if (ix->metric == RXGPU_COS && !query_norms) {
+		return fail(RXGPU_ERR_PARAMS, "Norm is required for Cosine-metric during corrective offsets calculation in quantized graph");  // hnswalg.h:1857
+	}
+	if (ix->size == 0) {
+		std::memset(out_count, 0, nq * sizeof(uint32_t));
+		return 0;
+	}
+	const uint32_t kEff = uint32_t(std::min<uint64_t>(k, ix->size));
+	if (kEff == 0) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: k must be positive");
+	}
+	try {
+		const uint32_t cp = s8->code_pitch;
+		std::vector<uint8_t> hq(size_t(nq) * cp, 0);
+		std::vector<float> hcorr(nq), hcoef(nq, 1.f);
+		for (uint32_t q = 0; q < nq; ++q) {
+			const float coef = ix->metric == RXGPU_COS ? 1.f / query_norms[q] : 1.f;  // queryNormCoef, hnswalg.h:1854-1863
+			hcoef[q] = coef;
+			hcorr[q] = sq8QuantizeHost(s8, ix->metric, ix->dim, queries + size_t(q) * ix->dim, ix->metric == RXGPU_COS ? 1.f / coef : 1.f,
+									   hq.data() + size_t(q) * cp);
+		}
+		std::lock_guard<std::mutex> hostLock(ix->hnsw->host_mtx);
+		std::lock_guard<std::mutex> sqLock(s8->mtx);
+		DevBuf<float>& dd = ix->hnsw->h_d;
+		DevBuf<uint32_t>&di = ix->hnsw->h_i, &dc = ix->hnsw->h_c, &ds = ix->hnsw->h_s;
+		RX_CUDA(s8->d_q.ensure(hq.size()));
+		RX_CUDA(s8->d_qcorr.ensure(nq));
+		RX_CUDA(s8->d_qcoef.ensure(nq));
+		RX_CUDA(dd.ensure(size_t(nq) * kEff));
+		RX_CUDA(di.ensure(size_t(nq) * kEff));
+		RX_CUDA(dc.ensure(nq));
+		RX_CUDA(ds.ensure(size_t(nq) * 2));
+		RX_CUDA(cudaMemcpy(s8->d_q.p, hq.data(), hq.size(), cudaMemcpyHostToDevice));
+		RX_CUDA(cudaMemcpy(s8->d_qcorr.p, hcorr.data(), size_t(nq) * 4, cudaMemcpyHostToDevice));
+		RX_CUDA(cudaMemcpy(s8->d_qcoef.p, hcoef.data(), size_t(nq) * 4, cudaMemcpyHostToDevice));
+		const Sq8Query sq{s8->d_q.p, s8->d_qcorr.p, s8->d_qcoef.p};
+		if (int rc = hnswSearchDevice(ix, nq, nullptr, kEff, ef, dd.p, di.p, dc.p, ds.p, nullptr, &sq)) {
+			return rc;
+		}
+		std::vector<float> hd(size_t(nq) * kEff);
+		std::vector<uint32_t> hi(size_t(nq) * kEff), hc(nq);
+		RX_CUDA(cudaMemcpy(hd.data(), dd.p, hd.size() * 4, cudaMemcpyDeviceToHost));
+		RX_CUDA(cudaMemcpy(hi.data(), di.p, hi.size() * 4, cudaMemcpyDeviceToHost));
+		RX_CUDA(cudaMemcpy(hc.data(), dc.p, hc.size() * 4, cudaMemcpyDeviceToHost));
+		if (stats) {
+			RX_CUDA(cudaMemcpy(stats, ds.p, size_t(nq) * 2 * 4, cudaMemcpyDeviceToHost));
+		}
+		std::vector<Hit> hits;
+		for (uint32_t q = 0; q < nq; ++q) {
+			hits.clear();
+			for (uint32_t j = 0; j < hc[q]; ++j) {
+				const uint32_t row = hi[size_t(q) * kEff + j];
+				hits.push_back(Hit{hd[size_t(q) * kEff + j], row, ix->h_labels[row]});
+			}
+			orderTiesByLabel(hits);
+			for (size_t j = 0; j < hits.size(); ++j) {
+				out_dist[size_t(q) * k + j] = hits[j].dist;
+				out_label[size_t(q) * k + j] = hits[j].label;
+			}
+			out_count[q] = uint32_t(hits.size());
+		}
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
 	}
 	return 0;
 }

@@ -165,9 +165,11 @@ struct Workspace {
 
 struct rxgpu_hnsw_device;  // hnsw.cu
 struct rxgpu_ivf_device;   // index.cu
+struct rxgpu_sq8_device;   // sq8.cu
 namespace rxgpu {
 void hnswRelease(rxgpu_hnsw_device*);
 void ivfRelease(rxgpu_ivf_device*);
+void sq8Release(rxgpu_sq8_device*);
 }
 
 struct rxgpu_index {
@@ -198,6 +200,7 @@ struct rxgpu_index {
 	mutable std::vector<std::unique_ptr<rxgpu::Workspace>> ws_free;
 	rxgpu_hnsw_device* hnsw = nullptr;  // graph attached by rxgpu_hnsw_import (hnsw.cu)
 	rxgpu_ivf_device* ivf = nullptr;    // centroids + list boundaries attached by rxgpu_ivf_import
+	rxgpu_sq8_device* sq8 = nullptr;    // SQ8 codes + corrective offsets attached by rxgpu_sq8_attach (sq8.cu)
 
 	// tensor-core filter state, built lazily by the first large-batch search: bf16 shadow of the rows + row norms
 	mutable std::mutex tc_mtx;
@@ -218,6 +221,9 @@ struct rxgpu_index {
 		}
 		if (ivf) {
 			rxgpu::ivfRelease(ivf);
+		}
+		if (sq8) {
+			rxgpu::sq8Release(sq8);
 		}
 		if (d_rows) {
 			cudaFree(d_rows);
