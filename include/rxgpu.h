@@ -215,6 +215,17 @@ int rxgpu_gather_labels_device(const rxgpu_index*, uint64_t n, const uint32_t* d
 int rxgpu_hnsw_search_range(const rxgpu_index*, const float* query /* host */, float radius, uint32_t ef, uint64_t max_out,
 							float* out_dist, uint64_t* out_label, uint64_t* out_n);
 
+/* Streaming (resumable) search: HierarchicalNSWImpl::BeginStreamingSearch / ContinueStreamingSearch   hnswlib/hnswalg.h:1864-1975
+ * (the KNN iterator of filtered queries pulls batches until enough rows pass the other conditions,
+ * core/nsselecter/knn_streaming_index_iterator.cc).  The session state -- visited set, candidate set, top candidates, extras, lower
+ * bound -- stays in HBM between calls; a call expands nodes in (distance, id) order until the reference's stop rule holds and returns
+ * the next `batch_size` closest expanded nodes, best first (ties by label).  ef == 0 -> 100 (kDefaultStreamingEf); ef, batch <= 1024.
+ * Query pre-normalised for Cosine.  The session must end before the index changes or is destroyed. */
+typedef struct rxgpu_hnsw_stream rxgpu_hnsw_stream;
+int rxgpu_hnsw_stream_begin(const rxgpu_index*, const float* query /* host */, uint32_t ef, rxgpu_hnsw_stream** out);
+int rxgpu_hnsw_stream_next(rxgpu_hnsw_stream*, uint32_t batch_size, float* out_dist, uint64_t* out_label, uint32_t* out_count, int* exhausted);
+void rxgpu_hnsw_stream_end(rxgpu_hnsw_stream*);
+
 /* ---------------------------------------------------------------- SQ8 scalar quantisation (the quantised HNSW map of the reference)
  * HierarchicalNSWImpl<uint8_t> keeps every vector as dim uint8 codes plus ONE additive corrective offset
  * (scalar_quantization/quantizer.h:93-125; hnswlib/hnswlib.h:255) and measures

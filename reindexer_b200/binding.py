@@ -132,6 +132,9 @@ _SIGNATURES = {
     "rxgpu_hnsw_search_range": (C.c_int, [C.c_void_p, _f32p, C.c_float, C.c_uint32, C.c_uint64, _f32p, _u64p, C.POINTER(C.c_uint64)]),
     "rxgpu_hnsw_search_knn_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rxgpu_hnsw_stream_begin": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "rxgpu_hnsw_stream_next": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, _u64p, _u32p, C.POINTER(C.c_int)]),
+    "rxgpu_hnsw_stream_end": (None, [C.c_void_p]),
     "rxgpu_sq8_attach": (C.c_int, [C.c_void_p, C.POINTER(Sq8Params), _u8p, _f32p]),
     "rxgpu_sq8_export": (C.c_int, [C.c_void_p, _u8p, _f32p]),
     "rxgpu_sq8_prepare_query": (C.c_int, [C.c_void_p, _f32p, C.c_float, _u8p, _f32p]),
@@ -349,6 +352,23 @@ class GpuBruteforceSearch:
         _check(self._lib.rxgpu_hnsw_search_range(self._h, _p(q, _f32p), radius, ef, max_out, _p(d, _f32p), _p(l, _u64p), C.byref(n)))
         m = min(n.value, max_out)
         return d[:m], l[:m], n.value
+
+    def hnsw_stream(self, query, batch_size: int, ef: int = 0, max_batches: int = 10**9):
+        """Begin/ContinueStreamingSearch: yields (dist, label) batches, best first inside a batch, until exhausted"""
+        q = np.ascontiguousarray(query, np.float32)
+        s = C.c_void_p()
+        _check(self._lib.rxgpu_hnsw_stream_begin(self._h, _p(q, _f32p), ef, C.byref(s)))
+        try:
+            for _ in range(max_batches):
+                d = np.zeros(max(batch_size, 1), np.float32)
+                l = np.zeros(max(batch_size, 1), np.uint64)
+                n, ex = C.c_uint32(0), C.c_int(0)
+                _check(self._lib.rxgpu_hnsw_stream_next(s, batch_size, _p(d, _f32p), _p(l, _u64p), C.byref(n), C.byref(ex)))
+                yield d[:n.value].copy(), l[:n.value].copy()
+                if ex.value:
+                    break
+        finally:
+            self._lib.rxgpu_hnsw_stream_end(s)
 
     # -- SQ8 (the reference's scalar quantisation of an HNSW map) ---------------------------------------------------------
     def sq8_attach(self, params: dict, codes=None, offsets=None):

@@ -593,6 +593,326 @@ __global__ void __launch_bounds__(kHnswThreads) hnsw_range_expand(RangeArgs a, u
 	}
 }
 
+// ---- streaming (resumable) search: HierarchicalNSWImpl::Begin/ContinueStreamingSearch (hnswalg.h:1864-1975) ------------------------------
+// A session keeps, in HBM between calls: the visited bitmap, candidate_set (every visited, not yet expanded node), top_candidates (the
+// <= ef closest EXPANDED nodes), top_candidates_extras (expanded nodes pushed out of top_candidates) and lowerBound.  One warp runs a
+// ContinueStreamingSearch call: the closest candidates (<= kStreamList keys) and top_candidates live sorted in shared memory for the
+// duration of the call; candidates that do not fit wait in an unsorted HBM spill array that is only ever worse than the shared list
+// (spill_min guards the invariant; the list is refilled from it when it runs dry), so nodes are expanded in exact (distance, id) order.
+constexpr uint32_t kStreamList = 1024;
+struct StreamHeader {
+	uint32_t initialized, n_top, n_cand, n_spill, n_extra, exhausted, overflow, pad;
+	float lower_bound, spill_min;
+};
+struct StreamArgs {
+	HnswArgs h;             // graph / rows (queries, nq, k, out_* unused)
+	StreamHeader* hdr;
+	uint64_t* top;          // [kMaxEf]
+	uint64_t* cand;         // [kStreamList]
+	uint64_t* spill;        // [cap]
+	uint64_t* extras;       // [cap]
+	uint32_t* visited;      // [words]
+	uint32_t cap, ef, batch;
+	float* out_dist;        // [batch]
+	uint32_t* out_idx;
+	uint32_t* out_count;    // [0] results, [1] exhausted
+};
+__device__ __forceinline__ uint64_t stream_key(float d, uint32_t id) { return (uint64_t(float_ord(d)) << 32) | id; }
+__device__ __forceinline__ float stream_dist(uint64_t k) { return ord_float(uint32_t(k >> 32)); }
+// sorted insert into list[0, n) (ascending); returns the new size.  When the list is full (n == cap) the largest key falls out and
+// is returned through *evicted (kKeyNone otherwise); a key larger than every entry of a full list is itself the one that falls out.
+__device__ __forceinline__ uint32_t stream_insert(uint64_t* list, uint32_t n, uint32_t cap, uint64_t key, uint64_t* evicted, int lane) {
+	*evicted = kKeyNone;
+	if (n == cap) {
+		if (key >= list[n - 1]) {
+			*evicted = key;
+			return n;
+		}
+		*evicted = list[n - 1];
+		n -= 1;
+	}
+	uint32_t pos = 0;  // entries smaller than key
+	for (uint32_t b = 0; b < n; b += 32) {
+		const uint32_t i = b + lane;
+		pos += __popc(__ballot_sync(0xffffffffu, i < n && list[i] < key));
+	}
+	for (int b = int((n - pos + 31) / 32) - 1; b >= 0; --b) {  // shift [pos, n) up by one, highest block first
+		const uint32_t i = pos + uint32_t(b) * 32 + lane;
+		const uint64_t v = i < n ? list[i] : 0;
+		__syncwarp();
+		if (i < n) {
+			list[i + 1] = v;
+		}
+		__syncwarp();
+	}
+	if (lane == 0) {
+		list[pos] = key;
+	}
+	__syncwarp();
+	return n + 1;
+}
+// index of the smallest key of arr[0, n) (n > 0), warp-wide
+__device__ __forceinline__ uint32_t stream_argmin(const uint64_t* arr, uint32_t n, uint64_t* best_out, int lane) {
+	uint64_t best = kKeyNone;
+	uint32_t bpos = 0;
+	for (uint32_t i = lane; i < n; i += 32) {
+		const uint64_t k = arr[i];
+		if (k < best) {
+			best = k;
+			bpos = i;
+		}
+	}
+#pragma unroll
+	for (int off = 16; off > 0; off >>= 1) {
+		const uint64_t ok = __shfl_xor_sync(0xffffffffu, best, off);
+		const uint32_t op = __shfl_xor_sync(0xffffffffu, bpos, off);
+		if (ok < best) {
+			best = ok;
+			bpos = op;
+		}
+	}
+	*best_out = best;
+	return bpos;
+}
+
+template <bool kIsL2>
+__global__ void __launch_bounds__(32) hnsw_stream_kernel(const StreamArgs s) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const HnswArgs& a = s.h;
+	const int lane = threadIdx.x;
+	const uint32_t nch = (a.dim + 127u) / 128u;
+	const uint32_t dp4 = nch * 32u;
+	float4* sq4 = reinterpret_cast<float4*>(smem_raw);
+	uint64_t* l_top = reinterpret_cast<uint64_t*>(smem_raw + size_t(dp4) * 16);
+	uint64_t* l_cand = l_top + kMaxEf;
+	uint32_t* s_ids = reinterpret_cast<uint32_t*>(l_cand + kStreamList);
+	float* s_d = reinterpret_cast<float*>(s_ids + kMaxNeighbours);
+	StreamHeader hd = *s.hdr;
+	{
+		float* sq = reinterpret_cast<float*>(sq4);
+		for (uint32_t c = lane; c < dp4 * 4; c += 32) {
+			sq[c] = c < a.dim ? a.queries[c] : 0.f;
+		}
+	}
+	for (uint32_t i = lane; i < hd.n_top; i += 32) {
+		l_top[i] = s.top[i];
+	}
+	for (uint32_t i = lane; i < hd.n_cand; i += 32) {
+		l_cand[i] = s.cand[i];
+	}
+	__syncwarp();
+	const bool has_deleted = a.deleted != nullptr;
+	auto is_deleted = [&](uint32_t id) { return has_deleted && ((a.deleted[id >> 5] >> (id & 31)) & 1u); };
+	uint32_t n_top = hd.n_top, n_cand = hd.n_cand, n_spill = hd.n_spill, n_extra = hd.n_extra;
+	float lower = hd.lower_bound, spill_min = hd.spill_min;
+	bool overflow = hd.overflow != 0;
+	uint64_t ev;
+	if (!hd.initialized) {
+		// getLayer0EntryPoint (hnswalg.h:799-827) + initLayer0SearchState in streaming mode (:829-858): the entry point is a candidate only
+		uint32_t cur = a.enterpoint;
+		if (lane == 0) {
+			s_ids[0] = cur;
+		}
+		__syncwarp();
+		warp_dists<kIsL2>(a, sq4, s_ids, 1, s_d, lane);
+		float curdist = s_d[0];
+		__syncwarp();
+		for (int level = a.maxlevel; level > 0; --level) {
+			bool changed = true;
+			while (changed) {
+				changed = false;
+				const uint32_t* ll = a.upper + (size_t(a.upper_off[cur]) + size_t(level - 1)) * a.up_stride;
+				const uint32_t cnt = min(ll[0], uint32_t(kMaxNeighbours));
+				for (uint32_t j = lane; j < cnt; j += 32) {
+					s_ids[j] = ll[1 + j];
+				}
+				__syncwarp();
+				if (cnt) {
+					warp_dists<kIsL2>(a, sq4, s_ids, cnt, s_d, lane);
+				}
+				for (uint32_t j = 0; j < cnt; ++j) {
+					const float d = s_d[j];
+					if (d < curdist) {
+						curdist = d;
+						cur = s_ids[j];
+						changed = true;
+					}
+				}
+				__syncwarp();
+			}
+		}
+		const bool epDeleted = is_deleted(cur);
+		lower = epDeleted ? 3.402823466e+38f : curdist;
+		if (lane == 0) {
+			l_cand[0] = stream_key(lower, cur);
+			atomicOr(&s.visited[cur >> 5], 1u << (cur & 31));
+		}
+		n_cand = 1;
+		spill_min = INFINITY;
+		__syncwarp();
+	}
+	const uint32_t ef = max(s.ef, s.batch);  // ContinueStreamingSearch: state.ef = max(state.ef, batchSize)
+	// mergeExtrasIntoTopCandidates (:1894-1925): the best extras refill top_candidates up to ef
+	while (n_top < ef && n_extra > 0) {
+		uint64_t best;
+		const uint32_t pos = stream_argmin(s.extras, n_extra, &best, lane);
+		if (lane == 0) {
+			s.extras[pos] = s.extras[n_extra - 1];
+		}
+		n_extra -= 1;
+		__syncwarp();
+		n_top = stream_insert(l_top, n_top, kMaxEf, best, &ev, lane);
+		lower = stream_dist(l_top[n_top - 1]);
+	}
+	for (;;) {
+		if (n_cand == 0 && n_spill > 0) {  // refill the shared list with the closest spilled candidates
+			while (n_cand < kStreamList / 2 && n_spill > 0) {
+				uint64_t best;
+				const uint32_t pos = stream_argmin(s.spill, n_spill, &best, lane);
+				if (lane == 0) {
+					s.spill[pos] = s.spill[n_spill - 1];
+				}
+				n_spill -= 1;
+				__syncwarp();
+				n_cand = stream_insert(l_cand, n_cand, kStreamList, best, &ev, lane);
+			}
+			spill_min = INFINITY;
+			if (n_spill) {
+				uint64_t best;
+				stream_argmin(s.spill, n_spill, &best, lane);
+				spill_min = stream_dist(best);
+			}
+		}
+		if (n_cand == 0) {
+			break;  // candidate_set.empty() (layer0ShouldStopBeforePop :861-863)
+		}
+		const uint64_t ck = l_cand[0];
+		const float cdist = stream_dist(ck);
+		const uint32_t cid = uint32_t(ck);
+		if (cdist > lower && n_top >= ef) {
+			break;  // :868
+		}
+		// pop the closest candidate
+		for (uint32_t b = 0; b + 1 < n_cand; b += 32) {
+			const uint32_t i = b + lane;
+			const uint64_t v = i + 1 < n_cand ? l_cand[i + 1] : 0;
+			__syncwarp();
+			if (i + 1 < n_cand) {
+				l_cand[i] = v;
+			}
+			__syncwarp();
+		}
+		n_cand -= 1;
+		// runLayer0Step, streaming branch (:880-893): an expanded live node enters top_candidates (or pushes its worst entry to extras)
+		if (!is_deleted(cid)) {
+			if (n_top < ef) {
+				n_top = stream_insert(l_top, n_top, kMaxEf, ck, &ev, lane);
+			} else if (lower > cdist) {
+				const uint64_t worst = l_top[n_top - 1];
+				__syncwarp();
+				n_top = stream_insert(l_top, n_top - 1, kMaxEf, ck, &ev, lane);
+				if (n_extra < s.cap) {
+					if (lane == 0) {
+						s.extras[n_extra] = worst;
+					}
+					n_extra += 1;
+				} else {
+					overflow = true;
+				}
+			}
+			lower = stream_dist(l_top[n_top - 1]);
+		}
+		// expand: every unvisited neighbour becomes a candidate (:931-938)
+		const uint32_t* ll = a.level0 + size_t(cid) * a.l0_stride;
+		const uint32_t cnt = min(ll[0], uint32_t(kMaxNeighbours));
+		uint32_t ucnt = 0;
+		for (uint32_t b = 0; b < cnt; b += 32) {
+			const uint32_t j = b + lane;
+			uint32_t nid = 0;
+			bool fresh = false;
+			if (j < cnt) {
+				nid = ll[1 + j];
+				const uint32_t bit = 1u << (nid & 31);
+				fresh = !(s.visited[nid >> 5] & bit);
+			}
+			// two neighbours may share a bitmap word: set the bits after the ballot, one lane per word is not needed for correctness of
+			// `fresh` because a list holds every neighbour once
+			if (fresh) {
+				atomicOr(&s.visited[nid >> 5], 1u << (nid & 31));
+			}
+			const unsigned fm = __ballot_sync(0xffffffffu, fresh);
+			if (fresh) {
+				s_ids[ucnt + __popc(fm & ((1u << lane) - 1u))] = nid;
+			}
+			ucnt += __popc(fm);
+		}
+		__syncwarp();
+		if (ucnt) {
+			warp_dists<kIsL2>(a, sq4, s_ids, ucnt, s_d, lane);
+			for (uint32_t j = 0; j < ucnt; ++j) {
+				const float d = s_d[j];
+				const uint64_t key = stream_key(d, s_ids[j]);
+				if (d < spill_min) {
+					n_cand = stream_insert(l_cand, n_cand, kStreamList, key, &ev, lane);
+				} else {
+					ev = key;
+				}
+				if (ev != kKeyNone) {  // does not fit the shared list: it is worse than everything in it
+					if (n_spill < s.cap) {
+						if (lane == 0) {
+							s.spill[n_spill] = ev;
+						}
+						n_spill += 1;
+						spill_min = fminf(spill_min, stream_dist(ev));
+					} else {
+						overflow = true;
+					}
+				}
+			}
+		}
+		__syncwarp();
+	}
+	// emitStreamingBatch (:1927-1945): the `batch` closest entries of top_candidates leave it
+	const uint32_t nout = min(s.batch, n_top);
+	for (uint32_t i = lane; i < nout; i += 32) {
+		s.out_dist[i] = stream_dist(l_top[i]);
+		s.out_idx[i] = uint32_t(l_top[i]);
+	}
+	__syncwarp();
+	for (uint32_t b = 0; b < n_top - nout; b += 32) {
+		const uint32_t i = b + lane;
+		const uint64_t v = i < n_top - nout ? l_top[i + nout] : 0;
+		__syncwarp();
+		if (i < n_top - nout) {
+			l_top[i] = v;
+		}
+		__syncwarp();
+	}
+	n_top -= nout;
+	for (uint32_t i = lane; i < n_top; i += 32) {
+		s.top[i] = l_top[i];
+	}
+	for (uint32_t i = lane; i < n_cand; i += 32) {
+		s.cand[i] = l_cand[i];
+	}
+	if (lane == 0) {
+		StreamHeader o{};
+		o.initialized = 1;
+		o.n_top = n_top;
+		o.n_cand = n_cand;
+		o.n_spill = n_spill;
+		o.n_extra = n_extra;
+		o.exhausted = (n_cand == 0 && n_spill == 0 && n_top == 0 && n_extra == 0) ? 1u : 0u;  // :1972
+		o.overflow = overflow ? 1u : 0u;
+		o.lower_bound = lower;
+		o.spill_min = spill_min;
+		*s.hdr = o;
+		s.out_count[0] = nout;
+		s.out_count[1] = o.exhausted;
+		s.out_count[2] = o.overflow;
+	}
+}
+
 __global__ void gather_labels_kernel(const uint64_t* labels, uint64_t size, uint64_t n, const uint32_t* idx, uint64_t* out) {
 	const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
 	if (i < n) {
@@ -1098,6 +1418,174 @@ int rxgpu_hnsw_search_range(const rxgpu_index* ix, const float* query, float rad
 		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
 	}
 	return 0;
+}
+
+}  // extern "C"
+
+struct rxgpu_hnsw_stream {
+	const rxgpu_index* ix = nullptr;
+	uint64_t index_version = 0;
+	uint32_t ef = 0, cap = 0;
+	bool finished = false;
+	DevBuf<float> query, out_dist;
+	DevBuf<StreamHeader> hdr;
+	DevBuf<uint64_t> top, cand, spill, extras;
+	DevBuf<uint32_t> visited, out_idx, out_count;
+};
+
+extern "C" {
+
+// BeginStreamingSearch (hnswalg.h:1864-1892): nothing is searched yet -- the first ContinueStreamingSearch descends to the entry point
+int rxgpu_hnsw_stream_begin(const rxgpu_index* ix, const float* query, uint32_t ef, rxgpu_hnsw_stream** out) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	if (!query || !out) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	*out = nullptr;
+	rxgpu_hnsw_device* h = ix->hnsw;
+	if (!h) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: no HNSW graph imported into this index");
+	}
+	if (h->n != ix->size || h->index_version != ix->version) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: the index changed after the HNSW graph was imported");
+	}
+	ef = ef ? ef : 100u;  // kDefaultStreamingEf (hnswalg.h:1866)
+	if (ef > kMaxEf) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: ef must be <= 1024 on the device path");
+	}
+	try {
+		auto s = std::make_unique<rxgpu_hnsw_stream>();
+		s->ix = ix;
+		s->index_version = ix->version;
+		s->ef = ef;
+		s->cap = uint32_t(std::min<uint64_t>(std::max<uint64_t>(h->n, 1), 1u << 20));  // spill / extras never hold more than the visited nodes
+		RX_CUDA(s->query.ensure(ix->dim));
+		RX_CUDA(s->hdr.ensure(1));
+		RX_CUDA(s->top.ensure(kMaxEf));
+		RX_CUDA(s->cand.ensure(kStreamList));
+		RX_CUDA(s->spill.ensure(s->cap));
+		RX_CUDA(s->extras.ensure(s->cap));
+		RX_CUDA(s->visited.ensure(h->words));
+		RX_CUDA(s->out_dist.ensure(kMaxEf));
+		RX_CUDA(s->out_idx.ensure(kMaxEf));
+		RX_CUDA(s->out_count.ensure(4));
+		RX_CUDA(cudaMemcpyAsync(s->query.p, query, size_t(ix->dim) * 4, cudaMemcpyHostToDevice, ix->stream));
+		RX_CUDA(cudaMemsetAsync(s->hdr.p, 0, sizeof(StreamHeader), ix->stream));
+		RX_CUDA(cudaMemsetAsync(s->visited.p, 0, size_t(h->words) * 4, ix->stream));
+		RX_CUDA(cudaStreamSynchronize(ix->stream));
+		*out = s.release();
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
+	}
+	return 0;
+}
+
+// ContinueStreamingSearch (hnswalg.h:1947-1975): the next `batch_size` closest expanded nodes, best first (ties by label);
+// *exhausted != 0 when the whole reachable graph has been returned
+int rxgpu_hnsw_stream_next(rxgpu_hnsw_stream* s, uint32_t batch_size, float* out_dist, uint64_t* out_label, uint32_t* out_count, int* exhausted) {
+	if (!s || !out_count || !exhausted || (batch_size && (!out_dist || !out_label))) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	const rxgpu_index* ix = s->ix;
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	*out_count = 0;
+	*exhausted = s->finished ? 1 : 0;
+	if (batch_size == 0 || s->finished) {
+		return 0;  // hnswalg.h:1960-1962
+	}
+	rxgpu_hnsw_device* h = ix->hnsw;
+	if (!h || s->index_version != ix->version || h->index_version != ix->version) {
+		*exhausted = 1;  // the session's graph is gone (the reference answers "exhausted" for a foreign graph, :1956-1959)
+		return 0;
+	}
+	if (batch_size > kMaxEf) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: batch size must be <= 1024 on the device path");
+	}
+	StreamArgs a{};
+	a.h.rows = ix->d_rows;
+	a.h.norm_coefs = ix->metric == RXGPU_COS ? ix->d_norms : nullptr;
+	a.h.level0 = h->level0.p;
+	a.h.levels = h->levels.p;
+	a.h.upper_off = h->upper_off.p;
+	a.h.upper = h->upper.p;
+	a.h.queries = s->query.p;
+	a.h.deleted = h->num_deleted ? h->deleted.p : nullptr;
+	a.h.pitch = ix->pitch;
+	a.h.dim = ix->dim;
+	a.h.n = h->n;
+	a.h.l0_stride = 1 + h->maxM0;
+	a.h.up_stride = 1 + h->M;
+	a.h.maxlevel = h->maxlevel;
+	a.h.enterpoint = h->enterpoint;
+	a.hdr = s->hdr.p;
+	a.top = s->top.p;
+	a.cand = s->cand.p;
+	a.spill = s->spill.p;
+	a.extras = s->extras.p;
+	a.visited = s->visited.p;
+	a.cap = s->cap;
+	a.ef = s->ef;
+	a.batch = batch_size;
+	a.out_dist = s->out_dist.p;
+	a.out_idx = s->out_idx.p;
+	a.out_count = s->out_count.p;
+	const uint32_t dp4 = ((ix->dim + 127u) / 128u) * 32u;
+	const size_t smem = size_t(dp4) * 16 + size_t(kMaxEf) * 8 + size_t(kStreamList) * 8 + kMaxNeighbours * 8;
+	if (smem > 200 * 1024) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: dimension exceeds the shared-memory budget of the streaming HNSW kernel");
+	}
+	cudaStream_t st = ix->stream;
+	if (ix->metric == RXGPU_L2) {
+		RX_CUDA(raiseSmemCeilingOnce(hnsw_stream_kernel<true>, ix->device, 200 * 1024));
+		hnsw_stream_kernel<true><<<1, 32, smem, st>>>(a);
+	} else {
+		RX_CUDA(raiseSmemCeilingOnce(hnsw_stream_kernel<false>, ix->device, 200 * 1024));
+		hnsw_stream_kernel<false><<<1, 32, smem, st>>>(a);
+	}
+	RX_CUDA(cudaGetLastError());
+	uint32_t cnt[4] = {0, 0, 0, 0};
+	RX_CUDA(cudaMemcpyAsync(cnt, s->out_count.p, 16, cudaMemcpyDeviceToHost, st));
+	RX_CUDA(cudaStreamSynchronize(st));
+	if (cnt[2]) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: the streaming session outgrew its device buffers (more than 2^20 waiting nodes)");
+	}
+	const uint32_t n = std::min(cnt[0], batch_size);
+	try {
+		std::vector<float> hd(n);
+		std::vector<uint32_t> hi(n);
+		if (n) {
+			RX_CUDA(cudaMemcpy(hd.data(), s->out_dist.p, size_t(n) * 4, cudaMemcpyDeviceToHost));
+			RX_CUDA(cudaMemcpy(hi.data(), s->out_idx.p, size_t(n) * 4, cudaMemcpyDeviceToHost));
+		}
+		std::vector<Hit> hits(n);
+		for (uint32_t j = 0; j < n; ++j) {
+			hits[j] = Hit{hd[j], hi[j], ix->h_labels[hi[j]]};
+		}
+		orderTiesByLabel(hits);  // the batch is a SearchResultQueue under std::less<pair<float, label>> (:1928-1944)
+		for (uint32_t j = 0; j < n; ++j) {
+			out_dist[j] = hits[j].dist;
+			out_label[j] = hits[j].label;
+		}
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
+	}
+	*out_count = n;
+	s->finished = cnt[1] != 0;
+	*exhausted = s->finished ? 1 : 0;
+	g_stats = rxgpu_search_stats{};
+	g_stats.launches = 1;
+	return 0;
+}
+
+void rxgpu_hnsw_stream_end(rxgpu_hnsw_stream* s) {
+	if (s) {
+		cudaSetDevice(s->ix->device);
+		delete s;
+	}
 }
 
 int rxgpu_gather_labels_device(const rxgpu_index* ix, uint64_t n, const uint32_t* d_idx, uint64_t* d_out_label, void* stream) {

@@ -241,3 +241,62 @@ def test_hnsw_search_with_deleted_nodes_matches_reference(metric, frac):
     assert "already deleted" in e.value.what
     with pytest.raises(rx.RxGpuError):
         gpu.hnsw_mark_deleted(0xDEAD << 40)
+
+
+@pytest.mark.parametrize("metric", [rx.L2, rx.COS])
+def test_streaming_search_matches_reference_batches(metric):
+    """rxgpu_hnsw_stream_* vs HierarchicalNSWImpl::Begin/ContinueStreamingSearch (hnswalg.h:1864-1975) on the same graph: the
+    device keeps the session state in HBM and must hand out the same batches (labels and order; the reference's heaps break exact
+    distance ties by heap mechanics, which random float data does not produce), never repeat a label, end exhausted having returned
+    every reachable row, and follow tombstones like the reference (expanded, never returned)."""
+    n, dim = 4000, 40
+    rng = np.random.default_rng(77 + metric)
+    vecs = rng.normal(0, 0.3, size=(n, dim)).astype(np.float32)
+    labels = O.row_labels(n)
+    ref = O.RefHnsw(metric, dim, n, M=16, ef_construction=100, seed=100, multithread=False)
+    ref.add_batch(labels, vecs)
+    g = ref.export(with_vectors=False)
+    gpu = rx.GpuBruteforceSearch(metric, dim, n)
+    gpu.add_points(g["labels"], vecs[(g["labels"] >> np.uint64(32)).astype(np.int64)])
+    gpu.hnsw_import(g)
+    queries = [prep_query(metric, q) for q in rng.normal(0, 0.3, size=(12, dim)).astype(np.float32)]
+
+    def compare(batch, ef, max_batches, qs):
+        same = total = 0
+        for q in qs:
+            it_ref = ref.stream(q, batch, ef=ef, max_batches=max_batches)
+            it_gpu = gpu.hnsw_stream(q, batch, ef=ef, max_batches=max_batches)
+            seen = set()
+            for (dr, lr), (dg, lg) in zip(it_ref, it_gpu):
+                total += 1
+                assert (np.diff(dg) >= 0).all() and not (set(lg.tolist()) & seen)
+                seen |= set(lg.tolist())
+                if len(lr) == len(lg) and (lr == lg).all():
+                    same += 1
+                    assert np.allclose(dg, dr, rtol=RTOL, atol=ATOL)
+        return same, total
+
+    same, total = compare(20, 64, 8, queries)
+    assert total == 8 * len(queries) and same >= 0.95 * total, (same, total)
+    same, total = compare(150, 32, 4, queries[:4])  # batch larger than ef: ContinueStreamingSearch widens ef for the call
+    assert same >= 0.9 * total, (same, total)
+    # a whole stream: exhausted exactly when every row was returned once
+    got = []
+    nb = 0
+    for d, l in gpu.hnsw_stream(queries[0], 256, ef=100):
+        got += l.tolist()
+        nb += 1
+    assert len(got) == len(set(got)) and len(got) >= 0.99 * n and nb >= n // 256
+    ref_all = []
+    for d, l in ref.stream(queries[0], 256, ef=100):
+        ref_all += l.tolist()
+    assert set(got) == set(ref_all)
+    # tombstones
+    for lab in g["labels"][::7]:
+        ref.mark_delete(int(lab))
+        gpu.hnsw_mark_deleted(int(lab))
+    dead = set(int(x) for x in g["labels"][::7])
+    same, total = compare(25, 64, 6, queries[:6])
+    assert same >= 0.9 * total, (same, total)
+    for d, l in gpu.hnsw_stream(queries[1], 100, ef=64, max_batches=10):
+        assert not (set(l.tolist()) & dead)
