@@ -199,6 +199,22 @@ int rxgpu_hnsw_search_knn(const rxgpu_index*, uint32_t nq, const float* queries 
 int rxgpu_hnsw_search_knn_device(const rxgpu_index*, uint32_t nq, const float* d_queries, uint32_t k, uint32_t ef, float* d_out_dist,
 								 uint32_t* d_out_idx, uint32_t* d_out_count, uint32_t* d_stats /* nq x 2 or NULL */, void* stream);
 
+/* Incremental maintenance of the imported graph after the reference's inserter added a point (HierarchicalNSWImpl::addPoint,
+ * hnswalg.h:1695-1852): the caller passes the nodes whose lists changed -- the new node (with its vector and label; a tombstoned slot
+ * that was reused for another vector counts as new) and the neighbours it was linked to -- and the graph's current top level and
+ * enter point.  The device copy is patched in place: O(M) small copies per upsert instead of a re-import.  New nodes must arrive in
+ * internal-id order; capacity is what the index had at import (rxgpu_index_resize + re-import beyond it: errLogic). */
+typedef struct {
+	uint32_t node;          /* internal id */
+	int32_t level;          /* element_levels_[node] */
+	const uint32_t* level0; /* 1 + maxM0: [count | neighbour ids] */
+	const uint32_t* upper;  /* level x (1 + M), or NULL when level == 0 */
+	const float* vec;       /* dim floats for a new / reused node, NULL for a node whose lists only were rewritten */
+	uint64_t label;         /* with vec */
+	int deleted;            /* IsMarkedDeleted(node) */
+} rxgpu_hnsw_node_update;
+int rxgpu_hnsw_update(rxgpu_index*, int32_t maxlevel, uint32_t enterpoint, uint32_t nupdates, const rxgpu_hnsw_node_update* updates);
+uint64_t rxgpu_hnsw_update_count(const rxgpu_index*); /* nodes patched in place since the import */
 /* HierarchicalNSWImpl::MarkDelete (hnswalg.h:1303-1335): the row stays in the graph as a tombstone -- searches traverse it but never
  * return it (searchBaseLayerST<bare_bone = false>, :829-975).  Errors: label unknown (errNotFound), already deleted (errLogic).
  * A search that meets more than 4096 deleted nodes waiting for expansion at once fails with errLogic (rebuild the graph). */

@@ -37,6 +37,11 @@ class SelectParams(C.Structure):
                 ("raw", C.c_int)]
 
 
+class HnswNodeUpdate(C.Structure):
+    _fields_ = [("node", C.c_uint32), ("level", C.c_int32), ("level0", C.c_void_p), ("upper", C.c_void_p), ("vec", C.c_void_p),
+                ("label", C.c_uint64), ("deleted", C.c_int)]
+
+
 class HnswGraph(C.Structure):
     _fields_ = [("n", C.c_uint32), ("M", C.c_uint32), ("maxM0", C.c_uint32), ("maxlevel", C.c_int32), ("enterpoint", C.c_uint32),
                 ("upper_slots", C.c_uint64), ("level0", C.c_void_p), ("levels", C.c_void_p), ("upper_offsets", C.c_void_p),
@@ -132,6 +137,8 @@ _SIGNATURES = {
     "rxgpu_hnsw_search_range": (C.c_int, [C.c_void_p, _f32p, C.c_float, C.c_uint32, C.c_uint64, _f32p, _u64p, C.POINTER(C.c_uint64)]),
     "rxgpu_hnsw_search_knn_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rxgpu_hnsw_update": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "rxgpu_hnsw_update_count": (C.c_uint64, [C.c_void_p]),
     "rxgpu_hnsw_stream_begin": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, C.POINTER(C.c_void_p)]),
     "rxgpu_hnsw_stream_next": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, _u64p, _u32p, C.POINTER(C.c_int)]),
     "rxgpu_hnsw_stream_end": (None, [C.c_void_p]),
@@ -329,6 +336,32 @@ class GpuBruteforceSearch:
         _check(self._lib.rxgpu_hnsw_search_knn(self._h, nq, _p(q, _f32p), k, ef, _p(d, _f32p), _p(l, _u64p), _p(c, _u32p),
                                                _p(st, _u32p)))
         return (d, l, c, st) if with_stats else (d, l, c)
+
+    def hnsw_update(self, graph: dict, nodes, new_rows=None, deleted=()):
+        """Patch the imported graph in place (rxgpu_hnsw_update): `nodes` = internal ids whose lists changed, taken from `graph`
+        (same layout as hnsw_import); `new_rows` = {internal id: (label, vector)} for inserted / replaced rows."""
+        new_rows = new_rows or {}
+        order = sorted(new_rows) + [int(v) for v in nodes if int(v) not in new_rows]
+        l0 = np.ascontiguousarray(graph["level0"], np.uint32)
+        up = np.ascontiguousarray(graph["upper"], np.uint32).reshape(-1, 1 + graph["M"])
+        uo = graph["upper_offsets"]
+        upd = (HnswNodeUpdate * max(len(order), 1))()
+        keep = []
+        dele = set(int(v) for v in deleted)
+        for i, v in enumerate(order):
+            lvl = int(graph["levels"][v])
+            upd[i].node, upd[i].level = v, lvl
+            upd[i].level0 = l0[v].ctypes.data
+            upd[i].upper = up[int(uo[v])].ctypes.data if lvl > 0 else None
+            if v in new_rows:
+                vec = np.ascontiguousarray(new_rows[v][1], np.float32)
+                keep.append(vec)
+                upd[i].vec, upd[i].label = vec.ctypes.data, int(new_rows[v][0])
+            upd[i].deleted = 1 if v in dele else 0
+        _check(self._lib.rxgpu_hnsw_update(self._h, graph["maxlevel"], graph["enterpoint"], len(order), upd))
+
+    def hnsw_update_count(self) -> int:
+        return int(self._lib.rxgpu_hnsw_update_count(self._h))
 
     def hnsw_mark_deleted(self, label: int):
         _check(self._lib.rxgpu_hnsw_mark_deleted(self._h, int(label)))

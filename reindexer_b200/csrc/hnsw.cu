@@ -927,6 +927,11 @@ struct rxgpu_hnsw_device {
 	int32_t maxlevel = -1;
 	uint32_t enterpoint = 0;
 	uint64_t index_version = 0;
+	size_t cap_nodes = 0;      // nodes the arrays below are sized for
+	uint64_t upper_slots = 0;  // used slots of `upper`
+	uint64_t updates = 0;      // nodes rewritten in place by rxgpu_hnsw_update since the import
+	std::vector<long long> h_upper_off;  // first upper-level slot of every node (host copy)
+	std::vector<int32_t> h_levels;       // element_levels_ (host copy)
 	DevBuf<uint32_t> level0;
 	DevBuf<int32_t> levels;
 	DevBuf<long long> upper_off;
@@ -1017,11 +1022,17 @@ int rxgpu_hnsw_import(rxgpu_index* ix, const rxgpu_hnsw_graph* g) {
 	h->maxM0 = g->maxM0;
 	h->maxlevel = g->maxlevel;
 	h->enterpoint = g->enterpoint;
+	// sized for the index's capacity so that rxgpu_hnsw_update can append nodes without reallocating
+	const size_t capNodes = std::max<size_t>(ix->capacity, g->n);
 	const size_t l0 = size_t(g->n) * (1 + g->maxM0), up = std::max<size_t>(1, size_t(g->upper_slots) * (1 + g->M));
-	RX_CUDA(h->level0.ensure(l0));
-	RX_CUDA(h->levels.ensure(g->n));
-	RX_CUDA(h->upper_off.ensure(size_t(g->n) + 1));
-	RX_CUDA(h->upper.ensure(up));
+	RX_CUDA(h->level0.ensure(capNodes * (1 + g->maxM0)));
+	RX_CUDA(h->levels.ensure(capNodes));
+	RX_CUDA(h->upper_off.ensure(capNodes + 1));
+	RX_CUDA(h->upper.ensure(up + (capNodes - g->n) / 8 * (1 + g->M) + 64 * (1 + g->M)));
+	h->cap_nodes = capNodes;
+	h->upper_slots = g->upper_slots;
+	h->h_upper_off.assign(g->upper_offsets, g->upper_offsets + g->n);
+	h->h_levels.assign(g->levels, g->levels + g->n);
 	RX_CUDA(cudaMemcpy(h->level0.p, g->level0, l0 * 4, cudaMemcpyHostToDevice));
 	RX_CUDA(cudaMemcpy(h->levels.p, g->levels, size_t(g->n) * 4, cudaMemcpyHostToDevice));
 	RX_CUDA(cudaMemcpy(h->upper_off.p, g->upper_offsets, (size_t(g->n) + 1) * 8, cudaMemcpyHostToDevice));
@@ -1034,7 +1045,7 @@ int rxgpu_hnsw_import(rxgpu_index* ix, const rxgpu_hnsw_graph* g) {
 		const uint32_t perSm = e ? std::max(1, std::min(16, std::atoi(e))) : 8u;
 		h->slots = uint32_t(ix->sm_count) * perSm * kHnswWarps;
 	}
-	h->words = (g->n + 31) / 32;
+	h->words = uint32_t((capNodes + 31) / 32);
 	RX_CUDA(h->visited.ensure(size_t(h->slots) * h->words));
 	RX_CUDA(h->vlog.ensure(size_t(h->slots) * kVlogCap));
 	RX_CUDA(h->counter.ensure(1));
@@ -1606,6 +1617,113 @@ int rxgpu_gather_labels_device(const rxgpu_index* ix, uint64_t n, const uint32_t
 	}
 	return 0;
 }
+
+// Incremental maintenance after the reference's inserter changed the host graph: HierarchicalNSWImpl::addPoint (hnswalg.h:1695-1852)
+// touches the new node's lists and the lists of the neighbours it was linked to (mutuallyConnectNewElement, :1070-1180); the adapter
+// hands over exactly those nodes.  Nothing else of the device copy moves: an upsert costs O(M) small copies, not a re-import.
+int rxgpu_hnsw_update(rxgpu_index* ix, int32_t maxlevel, uint32_t enterpoint, uint32_t nupdates, const rxgpu_hnsw_node_update* upd) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	rxgpu_hnsw_device* h = ix->hnsw;
+	if (!h) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: no HNSW graph imported into this index");
+	}
+	if (nupdates && !upd) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	std::lock_guard<std::mutex> lck(h->mtx);
+	const size_t s0 = size_t(1) + h->maxM0, s1 = size_t(1) + h->M;
+	// validate first: nothing is applied when any update is malformed
+	uint64_t newRows = 0, newSlots = 0;
+	for (uint32_t i = 0; i < nupdates; ++i) {
+		const rxgpu_hnsw_node_update& u = upd[i];
+		if (!u.level0 || u.level < 0 || (u.level > 0 && !u.upper) || u.level0[0] > h->maxM0) {
+			return fail(RXGPU_ERR_PARAMS, "rxgpu: HNSW update: malformed node");
+		}
+		const bool appended = u.node >= ix->size;
+		if (appended) {
+			if (!u.vec || u.node != ix->size + newRows) {
+				return fail(RXGPU_ERR_PARAMS, "rxgpu: HNSW update: new nodes carry their vector and arrive in internal-id order");
+			}
+			newRows += 1;
+			newSlots += uint64_t(u.level);
+		} else if (u.level != h->h_levels[u.node]) {
+			return fail(RXGPU_ERR_PARAMS, "rxgpu: HNSW update: the level of an existing node cannot change");
+		}
+	}
+	const uint64_t nAfter = ix->size + newRows;
+	if (nAfter > ix->capacity || nAfter > h->cap_nodes || h->upper_slots + newSlots > h->upper.n / s1) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: HNSW update exceeds the device copy's capacity (re-import the graph)");
+	}
+	for (uint32_t i = 0; i < nupdates; ++i) {
+		const rxgpu_hnsw_node_update& u = upd[i];
+		for (uint32_t j = 1; j <= u.level0[0]; ++j) {
+			if (u.level0[j] >= nAfter) {
+				return fail(RXGPU_ERR_PARAMS, "rxgpu: HNSW update: neighbour id out of range");
+			}
+		}
+		for (int32_t lv = 0; lv < u.level; ++lv) {
+			const uint32_t* l = u.upper + size_t(lv) * s1;
+			if (l[0] > h->M) {
+				return fail(RXGPU_ERR_PARAMS, "rxgpu: HNSW update: malformed upper list");
+			}
+			for (uint32_t j = 1; j <= l[0]; ++j) {
+				if (l[j] >= nAfter) {
+					return fail(RXGPU_ERR_PARAMS, "rxgpu: HNSW update: neighbour id out of range");
+				}
+			}
+		}
+	}
+	cudaStream_t st = ix->stream;
+	for (uint32_t i = 0; i < nupdates; ++i) {
+		const rxgpu_hnsw_node_update& u = upd[i];
+		if (u.vec) {  // a new node, or a slot whose vector was replaced (updatePoint; a reused tombstone, hnswalg.h:1445-1451): row + label
+			const bool appended = u.node >= ix->size;
+			const uint32_t other = ix->dict.find(u.label);
+			if (other != LabelMap::kNotFound && other != u.node && ((h->h_deleted[other >> 5] >> (other & 31)) & 1u)) {
+				// the label lives again in another slot: its tombstone takes a label of its own
+				const uint64_t tomb = (uint64_t(1) << 63) | uint64_t(other);
+				ix->dict.erase(u.label);
+				ix->dict.put(tomb, other);
+				ix->h_labels[other] = tomb;
+				RX_CUDA(cudaMemcpyAsync(ix->d_labels + other, &ix->h_labels[other], 8, cudaMemcpyHostToDevice, st));
+			}
+			if (int rc = setRowAt(ix, u.node, u.label, u.vec)) {
+				return rc;
+			}
+			if (appended) {
+				const long long off = (long long)h->upper_slots;  // its upper-level lists take fresh slots at the end of the slab
+				h->upper_slots += uint64_t(u.level);
+				h->h_upper_off.push_back(off);
+				h->h_levels.push_back(u.level);
+				RX_CUDA(cudaMemcpyAsync(h->upper_off.p + u.node, &h->h_upper_off[u.node], 8, cudaMemcpyHostToDevice, st));
+				RX_CUDA(cudaMemcpyAsync(h->levels.p + u.node, &h->h_levels[u.node], 4, cudaMemcpyHostToDevice, st));
+				RX_CUDA(cudaStreamSynchronize(st));  // the vectors above may reallocate on the next push_back
+			}
+		}
+		RX_CUDA(cudaMemcpyAsync(h->level0.p + size_t(u.node) * s0, u.level0, s0 * 4, cudaMemcpyHostToDevice, st));
+		if (u.level > 0) {
+			RX_CUDA(cudaMemcpyAsync(h->upper.p + size_t(h->h_upper_off[u.node]) * s1, u.upper, size_t(u.level) * s1 * 4, cudaMemcpyHostToDevice, st));
+		}
+		// tombstone bit follows the host graph (a reused slot is alive again)
+		const uint32_t bit = 1u << (u.node & 31);
+		const bool was = (h->h_deleted[u.node >> 5] & bit) != 0;
+		if (was != (u.deleted != 0)) {
+			h->h_deleted[u.node >> 5] ^= bit;
+			h->num_deleted += u.deleted ? 1 : -1;
+			RX_CUDA(cudaMemcpyAsync(h->deleted.p + (u.node >> 5), &h->h_deleted[u.node >> 5], 4, cudaMemcpyHostToDevice, st));
+		}
+	}
+	RX_CUDA(cudaStreamSynchronize(st));
+	h->maxlevel = maxlevel;
+	h->enterpoint = enterpoint;
+	h->n = uint32_t(ix->size);
+	h->index_version = ix->version;
+	h->updates += nupdates;
+	return 0;
+}
+uint64_t rxgpu_hnsw_update_count(const rxgpu_index* ix) { return ix && ix->hnsw ? ix->hnsw->updates : 0; }
 
 int rxgpu_hnsw_mark_deleted(rxgpu_index* ix, uint64_t label) {
 	if (int rc = checkIndex(ix)) {

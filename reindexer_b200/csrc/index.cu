@@ -594,6 +594,41 @@ int scanTopK(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, const float*
 	return scanTopKExact(ix, ws, st, d_queries, nq, k1, mode, bound, d_out_dist, d_out_idx, d_out_label, d_out_count);
 }
 
+int setRowAt(rxgpu_index* ix, uint32_t idx, uint64_t label, const float* vec) {
+	if (idx > ix->size || (idx == ix->size && ix->size >= ix->capacity)) {
+		return fail(RXGPU_ERR_LOGIC, "The number of elements exceeds the specified limit\n");
+	}
+	const uint32_t other = ix->dict.find(label);
+	if (other != LabelMap::kNotFound && other != idx) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: label already belongs to another row");
+	}
+	RX_CUDA(ix->st_rows.ensure(ix->pitch));
+	RX_CUDA(cudaMemsetAsync(ix->st_rows.p, 0, size_t(ix->pitch) * 4, ix->stream));
+	RX_CUDA(cudaMemcpyAsync(ix->st_rows.p, vec, size_t(ix->dim) * 4, cudaMemcpyHostToDevice, ix->stream));
+	RX_CUDA(cudaMemcpyAsync(ix->d_rows + size_t(idx) * ix->pitch, ix->st_rows.p, size_t(ix->pitch) * 4, cudaMemcpyDeviceToDevice, ix->stream));
+	RX_CUDA(cudaMemcpyAsync(ix->d_labels + idx, &label, 8, cudaMemcpyHostToDevice, ix->stream));
+	if (ix->metric == RXGPU_COS) {
+		norm_coef_kernel<<<1, 32, 0, ix->stream>>>(ix->d_rows, ix->pitch, ix->dim, idx, idx + 1, ix->d_norms);
+		RX_CUDA(cudaGetLastError());
+	}
+	RX_CUDA(cudaStreamSynchronize(ix->stream));
+	if (idx < ix->size) {
+		if (ix->h_labels[idx] != label) {
+			ix->dict.erase(ix->h_labels[idx]);
+		}
+		ix->h_labels[idx] = label;
+	} else {
+		ix->h_labels.push_back(label);
+		ix->size += 1;
+	}
+	ix->dict.put(label, idx);
+	if (ix->flags & RXGPU_FLAG_HOST_MIRROR) {
+		std::memcpy(ix->h_rows.data() + size_t(idx) * ix->dim, vec, ix->dim * sizeof(float));
+	}
+	ix->version++;
+	return 0;
+}
+
 int tieRowsAfterScan(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, const float* d_queries, uint32_t nsel, const uint32_t* sel,
 					 const float* dstar, uint32_t k, float* d_out_dist, uint32_t* d_out_idx, uint64_t* d_out_label, uint32_t* d_out_count) {
 	if (nsel == 0) {

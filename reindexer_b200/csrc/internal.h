@@ -283,6 +283,9 @@ int scanTopK(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, const float*
 int tieRowsAfterScan(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, const float* d_queries, uint32_t nsel, const uint32_t* sel,
 					 const float* dstar, uint32_t k, float* d_out_dist, uint32_t* d_out_idx, uint64_t* d_out_label, uint32_t* d_out_count);
 
+// writes row `idx` (== size: appends) with a new vector and label, keeping the label dictionary consistent (index.cu)
+int setRowAt(rxgpu_index* ix, uint32_t idx, uint64_t label, const float* vec);
+
 inline int checkIndex(const rxgpu_index* ix) {
 	if (!ix) {
 		return fail(RXGPU_ERR_PARAMS, "rxgpu: null index handle");

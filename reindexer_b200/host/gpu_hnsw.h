@@ -2,8 +2,10 @@
 // hnswlib::HierarchicalNSW<synchronization> (cpp_src/core/index/float_vector/hnswlib/hnsw.h:13-73): graph CONSTRUCTION stays with
 // the reference's own inserter (HierarchicalNSWImpl::addPoint, hnswalg.h:1695-1852 -- heuristic neighbour selection, level RNG seeded
 // with 100, tombstone replacement), SEARCH runs on the GPU through librxgpu (include/rxgpu.h: rxgpu_hnsw_import / _search_knn /
-// _search_range / _mark_deleted).  The device copy (rows in internal-id order + level-0 slab + upper levels) is rebuilt lazily by
-// the first search after an insertion; MarkDelete is applied in place (a tombstone bit, like hnswalg.h:1303-1335).
+// _search_range / _mark_deleted / _update).  The device copy (rows in internal-id order + level-0 slab + upper levels) is imported by
+// the first search; after that single-writer inserts patch it in place (rxgpu_hnsw_update: the inserted row and the lists of the nodes
+// the reference's inserter rewrote), MarkDelete sets a tombstone bit (like hnswalg.h:1303-1335).  Concurrent bulk inserts, resizes and
+// cache loads re-import.
 // Meant to be dropped into cpp_src/core/index/float_vector/hnswlib/ next to hnsw.h; it includes the reference's own headers and is
 // therefore compiled only where that tree is available (tests/cpp/dropin_hnsw_check.cc does so in the authoring container).
 // INTEGRATION.md section 5 shows the patch of hnsw_index.cc.
@@ -12,12 +14,14 @@
 // streaming search (Begin/ContinueStreamingSearch run the reference's own routine on the host graph this adapter keeps for inserts).
 #pragma once
 
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 #include <memory>
 #include <mutex>
 #include <optional>
 #include <stdexcept>
+#include <string>
 #include <utility>
 #include <vector>
 
@@ -46,6 +50,10 @@ public:
 		cpu_ = std::move(o.cpu_);
 		gpu_ = std::exchange(o.gpu_, nullptr);
 		dirty_.store(o.dirty_.load());
+		hasPending_.store(o.hasPending_.load());
+		pendingRows_ = std::move(o.pendingRows_);
+		pendingLists_ = std::move(o.pendingLists_);
+		deviceCapacity_ = o.deviceCapacity_;
 		return *this;
 	}
 	~GpuHnsw() { releaseDevice(); }
@@ -63,22 +71,66 @@ public:
 
 	void MarkDelete(reindexer::FloatVectorId id) {
 		const labeltype label = id.AsNumber();
+		if (gpu_ && !dirty_.load(std::memory_order_acquire) && hasPending_.load(std::memory_order_acquire)) {
+			try {
+				flushPending();  // the label may belong to a row that is not on the device yet
+			} catch (const std::exception& e) {
+				lastPatchError_ = e.what();
+				dirty_.store(true, std::memory_order_release);
+			}
+		}
 		cpu_->MarkDelete(label);  // throws "markDelete: Label not found: ..." / "... already deleted" like the reference
 		if (gpu_ && !dirty_.load(std::memory_order_acquire)) {
 			if (rxgpu_hnsw_mark_deleted(gpu_, label) != RXGPU_OK) {
+				lastPatchError_ = rxgpu_last_error();
 				dirty_.store(true, std::memory_order_release);  // the device copy is rebuilt by the next search
 			}
 		}
 	}
+	// Single-writer insert (the namespace's exclusive lock): the device copy is patched in place by the next search -- the nodes whose
+	// lists addPoint / updatePoint rewrote are known exactly (one-hop neighbours before and after the call), so an upsert costs O(M) small copies, not a re-import.
 	void AddPointNoLock(reindexer::ConstFloatVectorView vect, reindexer::FloatVectorId id) {
-		cpu_->AddPointNoLock(vect.Data(), id.AsNumber());
-		dirty_.store(true, std::memory_order_release);
+		const labeltype label = id.AsNumber();
+		if (!gpu_ || dirty_.load(std::memory_order_acquire)) {
+			cpu_->AddPointNoLock(vect.Data(), label);
+			dirty_.store(true, std::memory_order_release);
+			return;
+		}
+		// which slot the reference will write (hnswalg.h:1401-1470): a vacant tombstone first, else the label's own node, else a new one
+		const size_t before = cpu_->cur_element_count.load();
+		const auto known = cpu_->label_lookup_.find(label);
+		const bool vacant = !cpu_->deleted_elements.empty();
+		bool trackable = !(vacant && known != cpu_->label_lookup_.end());
+		tableint node = vacant ? *cpu_->deleted_elements.begin() : known != cpu_->label_lookup_.end() ? known->second : tableint(before);
+		std::vector<tableint> touched;
+		if (node < before) {
+			neighboursOf(node, touched);  // updatePoint re-selects the lists of the old one-hop neighbours (hnswalg.h:1512-1583)
+		}
+		cpu_->AddPointNoLock(vect.Data(), label);
+		trackable = trackable && cpu_->cur_element_count.load() == (node < before ? before : before + 1) && cpu_->MaxElements() == deviceCapacity_;
+		if (!trackable) {
+			lastPatchError_ = "insert not trackable (label lives in another slot while a tombstone is vacant, or the map was resized)";
+			dirty_.store(true, std::memory_order_release);
+			return;
+		}
+		neighboursOf(node, touched);  // mutuallyConnectNewElement rewrote the lists of the selected neighbours (hnswalg.h:1070-1180)
+		std::lock_guard<std::mutex> lck(mtx_);
+		pendingRows_.push_back(node);
+		pendingLists_.insert(pendingLists_.end(), touched.begin(), touched.end());
+		if (pendingLists_.size() > std::max<size_t>(4096, before / 4)) {  // a bulk load: one import is cheaper than the patches
+			dirty_.store(true, std::memory_order_release);
+		}
+		hasPending_.store(true, std::memory_order_release);
 	}
+	// concurrent inserts interleave their list rewrites, so the set of touched nodes is not known per call: full re-import
 	void AddPointConcurrent(reindexer::ConstFloatVectorView vect, reindexer::FloatVectorId id) {
 		cpu_->AddPointConcurrent(vect.Data(), id.AsNumber());
 		dirty_.store(true, std::memory_order_release);
 	}
-	void ResizeIndex(size_t newMaxElements) { cpu_->ResizeIndex(newMaxElements); }  // capacity only; the device copy is sized by rows
+	void ResizeIndex(size_t newMaxElements) {
+		cpu_->ResizeIndex(newMaxElements);
+		dirty_.store(true, std::memory_order_release);  // the device copy is re-imported at the new capacity
+	}
 	void SaveIndex(IWriter& writer, const std::atomic_int32_t& cancel) const {
 		writer.PutVarUInt(uint32_t(0));  // not quantised (HierarchicalNSW::serializeQuantizingParams, hnsw.cc:52-58)
 		cpu_->SaveIndex(writer, cancel);
@@ -151,6 +203,9 @@ public:
 
 	// number of times the device copy was (re)built -- exposed for tests
 	size_t DeviceImports() const noexcept { return imports_.load(); }
+	// nodes patched in place since the last import
+	const std::string& LastPatchError() const noexcept { return lastPatchError_; }  // why the copy was last scheduled for a re-import
+	size_t DevicePatchedNodes() const noexcept { return gpu_ ? size_t(rxgpu_hnsw_update_count(gpu_)) : 0; }
 
 private:
 	constexpr static int kHnswRandomSeed = 100;  // hnsw.h:73
@@ -184,14 +239,96 @@ private:
 
 	// Searches run concurrently under the namespace's shared lock; inserts under its exclusive lock.  The first search after an
 	// insertion rebuilds the device copy; the others wait on the mutex.
+	void neighboursOf(tableint node, std::vector<tableint>& out) const {
+		const Cpu& g = *cpu_;
+		for (int lvl = 0; lvl <= g.element_levels_[node]; ++lvl) {
+			const auto* ll = lvl == 0 ? g.get_linklist0(node) : g.get_linklist(node, lvl);
+			const unsigned cnt = g.getListCount(ll);
+			for (unsigned j = 0; j < cnt; ++j) {
+				out.push_back(readLinkListNeighbor(ll, j));
+			}
+		}
+	}
+	// pushes the current lists of every touched node (and the rows of the inserted ones) to the device copy
+	void flushPending() const {
+		std::lock_guard<std::mutex> lck(mtx_);
+		flushPendingLocked();
+	}
+	void flushPendingLocked() const {
+		if (!hasPending_.load(std::memory_order_acquire)) {
+			return;
+		}
+		const Cpu& g = *cpu_;
+		const size_t m0 = g.maxM0_, m = g.M_;
+		std::vector<tableint> rows = pendingRows_, lists = pendingLists_;
+		std::sort(rows.begin(), rows.end());
+		rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+		std::sort(lists.begin(), lists.end());
+		lists.erase(std::unique(lists.begin(), lists.end()), lists.end());
+		std::vector<tableint> order = rows;  // rows first, in internal-id order (appends must arrive that way)
+		for (const tableint v : lists) {
+			if (!std::binary_search(rows.begin(), rows.end(), v)) {
+				order.push_back(v);
+			}
+		}
+		size_t slots = 0;
+		for (const tableint v : order) {
+			slots += size_t(g.element_levels_[v]);
+		}
+		std::vector<uint32_t> level0(order.size() * (1 + m0)), upper(slots * (1 + m));
+		std::vector<rxgpu_hnsw_node_update> upd(order.size());
+		size_t slot = 0;
+		for (size_t i = 0; i < order.size(); ++i) {
+			const tableint v = order[i];
+			uint32_t* dst0 = level0.data() + i * (1 + m0);
+			const auto* ll0 = g.get_linklist0(v);
+			const unsigned cnt0 = g.getListCount(ll0);
+			dst0[0] = cnt0;
+			for (size_t j = 0; j < cnt0; ++j) {
+				dst0[1 + j] = readLinkListNeighbor(ll0, j);
+			}
+			rxgpu_hnsw_node_update& u = upd[i];
+			u.node = v;
+			u.level = g.element_levels_[v];
+			u.level0 = dst0;
+			u.upper = u.level > 0 ? upper.data() + slot * (1 + m) : nullptr;
+			for (int lvl = 1; lvl <= u.level; ++lvl, ++slot) {
+				const auto* ll = g.get_linklist(v, lvl);
+				const unsigned cnt = g.getListCount(ll);
+				uint32_t* dst = upper.data() + slot * (1 + m);
+				dst[0] = cnt;
+				for (size_t j = 0; j < cnt; ++j) {
+					dst[1 + j] = readLinkListNeighbor(ll, j);
+				}
+			}
+			const bool isRow = i < rows.size();
+			u.vec = isRow ? reinterpret_cast<const float*>(g.getDataByInternalId(v)) : nullptr;
+			u.deleted = g.IsMarkedDeleted(v) ? 1 : 0;
+			u.label = u.deleted ? ((uint64_t(1) << 63) | uint64_t(v)) : uint64_t(g.ExternalLabel(v));
+		}
+		check(rxgpu_hnsw_update(gpu_, g.maxlevel_, uint32_t(g.enterpoint_node_), uint32_t(upd.size()), upd.data()));
+		pendingRows_.clear();
+		pendingLists_.clear();
+		hasPending_.store(false, std::memory_order_release);
+	}
+
 	void ensureDevice() const {
-		if (gpu_ && !dirty_.load(std::memory_order_acquire)) {
+		if (gpu_ && !dirty_.load(std::memory_order_acquire) && !hasPending_.load(std::memory_order_acquire)) {
 			return;
 		}
 		std::lock_guard<std::mutex> lck(mtx_);
 		if (gpu_ && !dirty_.load(std::memory_order_acquire)) {
-			return;
+			try {
+				flushPendingLocked();
+				return;
+			} catch (const std::exception& e) {  // e.g. the slab of upper-level lists is full: rebuild the copy from the host graph
+				lastPatchError_ = e.what();
+				dirty_.store(true, std::memory_order_release);
+			}
 		}
+		pendingRows_.clear();
+		pendingLists_.clear();
+		hasPending_.store(false, std::memory_order_release);
 		const Cpu& g = *cpu_;
 		const size_t n = g.cur_element_count.load();
 		const size_t m0 = g.maxM0_, m = g.M_;
@@ -200,7 +337,8 @@ private:
 			gpu_ = nullptr;
 		}
 		rxgpu_index* ix = nullptr;
-		check(rxgpu_index_create(&ix, toMetric(metric_), uint32_t(dim_), n, deviceFromEnv(), 0));
+		check(rxgpu_index_create(&ix, toMetric(metric_), uint32_t(dim_), std::max(n, g.MaxElements()), deviceFromEnv(), 0));
+		deviceCapacity_ = std::max(n, g.MaxElements());
 		std::unique_ptr<rxgpu_index, void (*)(rxgpu_index*)> guard(ix, rxgpu_index_destroy);
 		// rows in internal-id order (internal id i = row i), in slices; a tombstone keeps its slot but gets a label of its own:
 		// with replace_deleted the same external label may live again in another slot (hnswalg.h:1710-1760)
@@ -276,7 +414,11 @@ private:
 	size_t dim_;
 	std::unique_ptr<Cpu> cpu_;
 	mutable rxgpu_index* gpu_ = nullptr;
-	mutable std::atomic<bool> dirty_{true};
+	mutable std::atomic<bool> dirty_{true};        // the device copy must be rebuilt from the host graph
+	mutable std::atomic<bool> hasPending_{false};  // ... or only patched: rows written / nodes whose lists were rewritten since
+	mutable std::vector<tableint> pendingRows_, pendingLists_;
+	mutable size_t deviceCapacity_ = 0;
+	mutable std::string lastPatchError_;
 	mutable std::atomic<size_t> imports_{0};
 	mutable std::mutex mtx_;
 };

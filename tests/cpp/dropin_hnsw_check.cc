@@ -113,6 +113,31 @@ Results drive(reindexer::VectorMetric metric, size_t dim, size_t n, size_t k, si
 		add(i);
 	}
 	search(map, false);
+	// steady state: upserts and deletes interleaved with searches.  The device copy must be PATCHED (rxgpu_hnsw_update), not re-imported.
+	size_t importsBefore = 0;
+	if constexpr (requires { map.DeviceImports(); }) {
+		importsBefore = map.DeviceImports();
+	}
+	for (size_t i = n + n / 4, round = 0; round < 4; ++round) {
+		for (size_t j = 0; j < 40; ++j, ++i) {
+			add(i);
+			if (j % 8 == 3) {  // a tombstone, reused by the insert after the next one
+				map.MarkDelete(reindexer::FloatVectorId{reindexer::IdType::FromNumber(int(i - 2)), 0});
+			}
+			if (j % 16 == 9) {  // the same id again with another vector (updatePoint on the live node)
+				add(i - 1);
+			}
+		}
+		search(map, false);
+	}
+	if constexpr (requires { map.DeviceImports(); }) {
+		if (map.DeviceImports() != importsBefore || map.DevicePatchedNodes() == 0) {
+			std::printf("steady-state upserts re-imported the device copy (%zu -> %zu imports, %zu patched nodes): %s\n", importsBefore, map.DeviceImports(),
+						map.DevicePatchedNodes(), map.LastPatchError().c_str());
+			std::exit(2);
+		}
+		std::printf("  steady state: 160 upserts + tombstones patched %zu nodes in place, %zu imports in total\n", map.DevicePatchedNodes(), map.DeviceImports());
+	}
 	const Map clone(std::as_const(map), map.MaxElements() + 10);  // COW namespace clone (hnsw_index.cc:66-68)
 	search(clone, false);
 	// index cache round trip (WriteIndexCache / LoadIndexCache, hnsw_index.cc:389-507; hnswalg.h:1213-1263, loader :297-...)
@@ -147,7 +172,7 @@ int main() {
 			nonEmpty += !ref[i].empty();
 		}
 		const bool ok = total == gpu.size() && same * 100 >= total * 95 && closeDist * 100 >= total * 95 && nonEmpty * 2 >= total;
-		std::printf("metric %d: %zu searches (knn, knn with tombstones, range, knn after more inserts, knn on a clone, knn on a map restored from its index cache), identical ids %zu, distances within 1e-4 %zu, "
+		std::printf("metric %d: %zu searches (knn, knn with tombstones, range, knn after more inserts, knn between steady-state upserts, knn on a clone, knn on a map restored from its index cache), identical ids %zu, distances within 1e-4 %zu, "
 					"non-empty %zu -> %s\n",
 					int(metric), total, same, closeDist, nonEmpty, ok ? "MATCH" : "MISMATCH");
 		bad += !ok;
