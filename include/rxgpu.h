@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RXGPU_ABI_VERSION 2
+#define RXGPU_ABI_VERSION 3
 
 /* subset of reindexer::ErrorCode (core/type_consts.h:136-181) that this library produces */
 enum { RXGPU_OK = 0, RXGPU_ERR_PARAMS = 3, RXGPU_ERR_LOGIC = 4, RXGPU_ERR_NOT_FOUND = 13, RXGPU_ERR_SYSTEM = 37 };
@@ -322,7 +322,21 @@ typedef struct { /* one TermResults */
 	const uint32_t* postings; /* ids returned by rxgpu_ft_add_postings */
 	const float* procs;
 	const uint8_t* need_sum_rank; /* nfields flags FtDslFieldOpts::needSumRank (ftdsl.h:15), or NULL = all false; at most 16 set */
+	const uint8_t* suppressed;    /* nsubterms flags SubtermResults::Suppressed (querymergedata.h:32; set on the subterms of multi-word
+	                               * synonyms that repeat a word of the query, :221-241), or NULL = none */
+	uint32_t nsynonyms;           /* PhraseOrTerm::SynonymsIds (querymergedata.h:160): indexes into rxgpu_ft_query::synonyms; query parts only */
+	const uint32_t* synonym_ids;
 } rxgpu_ft_term;
+typedef struct { /* ft::Synonym (querymergedata.h:168-188): the terms of one multi-word substitution */
+	uint32_t nterms;
+	const rxgpu_ft_term* terms;
+} rxgpu_ft_synonym;
+typedef struct { /* ft::QueryMergeData (querymergedata.h:191-242) without phrases */
+	uint32_t nterms;
+	const rxgpu_ft_term* terms; /* queryParts */
+	uint32_t nsynonyms;
+	const rxgpu_ft_synonym* synonyms;
+} rxgpu_ft_query;
 typedef struct { /* ft::MergeInfo */
 	int32_t id;
 	float proc;
@@ -349,6 +363,11 @@ int rxgpu_ft_decode_packed(const uint8_t* data, uint64_t len, uint32_t count, ui
  * Writes min(*out_n, max_out) entries; *out_n = number of merged documents. */
 int rxgpu_ft_merge(rxgpu_ft_index*, const rxgpu_ft_config* cfg, uint32_t nterms, const rxgpu_ft_term* terms, const uint8_t* excluded,
 				   int rank_sort_type, uint64_t max_out, rxgpu_ft_merge_info* out, uint64_t* out_n);
+/* The same with multi-word synonyms (Merger::Merge, mergerimpl.h:510-560): a synonym's terms are merged after the query parts; a
+ * document that entered the result through synonyms stays only if it holds every term of one of them; an AND part is also satisfied by
+ * a document that holds all terms of one of its synonyms (buildRestrictingBitmask, :352-363). */
+int rxgpu_ft_merge_query(rxgpu_ft_index*, const rxgpu_ft_config* cfg, const rxgpu_ft_query* query, const uint8_t* excluded, int rank_sort_type,
+						 uint64_t max_out, rxgpu_ft_merge_info* out, uint64_t* out_n);
 /* IndexText::afterSelect + sortAfterSelect on top of the merge, without leaving the device (core/index/indextext/indextext.cc:480-611;
  * Merger::postProcessResults, ft_fast/merger.h:111-155): ranks below min_rank are dropped, the rest is normalised to uint8 by the
  * global maximum, every merged vdoc expands to its row ids, rows whose external status is 0 are skipped (FtUseExternStatuses::Yes),
@@ -360,6 +379,8 @@ int rxgpu_ft_set_rows(rxgpu_ft_index*, const uint32_t* row_begin, const int32_t*
 int rxgpu_ft_select(rxgpu_ft_index*, const rxgpu_ft_config* cfg, uint32_t nterms, const rxgpu_ft_term* terms, const uint8_t* excluded,
 					const uint8_t* row_status /* u8 per row id, or NULL */, int rank_sort_type, uint64_t limit, int32_t* out_row_ids,
 					float* out_ranks /* RankT = the uint8 rank as float */, uint64_t* out_n);
+int rxgpu_ft_select_query(rxgpu_ft_index*, const rxgpu_ft_config* cfg, const rxgpu_ft_query* query, const uint8_t* excluded,
+						  const uint8_t* row_status, int rank_sort_type, uint64_t limit, int32_t* out_row_ids, float* out_ranks, uint64_t* out_n);
 /* statistics of the last merge on this thread */
 typedef struct {
 	uint32_t launches;

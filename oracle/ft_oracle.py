@@ -38,7 +38,12 @@ class Config(C.Structure):
 
 class Term(C.Structure):
     _fields_ = [("op", C.c_int32), ("boost", C.c_float), ("term_len_boost", C.c_float), ("field_boosts", _f32p), ("nsubterms", C.c_uint32),
-                ("postings", _u32p), ("procs", _f32p), ("need_sum_rank", _u8p)]
+                ("postings", _u32p), ("procs", _f32p), ("need_sum_rank", _u8p), ("suppressed", _u8p), ("nsynonyms", C.c_uint32),
+                ("synonym_ids", _u32p)]
+
+
+class Synonym(C.Structure):
+    _fields_ = [("nterms", C.c_uint32), ("terms", C.POINTER(Term))]
 
 
 class MergeInfo(C.Structure):
@@ -70,6 +75,7 @@ class FtProblem:
         self.excluded = None if excluded is None else np.ascontiguousarray(excluded, np.uint8)
         self.lists = []  # (doc_ids, pos_begin, positions)
         self.terms = []  # dict(op, boost, term_len_boost, field_boosts, postings, procs)
+        self.synonyms = []  # multi-word synonyms: lists of term dicts (ft::Synonym)
         self.cfg = dict(merge_limit=20000, min_rank=5, bm25_k1=2.0, bm25_b=0.75, bm25_type=0, distance_boost=1.0, distance_weight=0.5,
                         full_match_boost=1.1, summation_ranks_by_fields_ratio=0.0)
         self.field_cfg = [dict(bm25_boost=1.0, bm25_weight=0.1, term_len_boost=1.0, term_len_weight=0.3, position_boost=1.0,
@@ -92,13 +98,25 @@ class FtProblem:
                            np.ascontiguousarray(positions, np.uint32)))
         return len(self.lists) - 1
 
-    def add_term(self, subterms, op=OP_OR, boost=1.0, term_len_boost=1.0, field_boosts=None, need_sum_rank=None):
-        """subterms: list of (list id, proc)"""
+    def _term(self, subterms, op, boost, term_len_boost, field_boosts, need_sum_rank, synonym_ids=()):
         fb = np.ones(self.nfields, np.float32) if field_boosts is None else np.ascontiguousarray(field_boosts, np.float32)
         ns = None if need_sum_rank is None else np.ascontiguousarray(need_sum_rank, np.uint8)
-        self.terms.append(dict(op=op, boost=boost, term_len_boost=term_len_boost, field_boosts=fb, need_sum_rank=ns,
-                               postings=np.ascontiguousarray([s[0] for s in subterms], np.uint32),
-                               procs=np.ascontiguousarray([s[1] for s in subterms], np.float32)))
+        sup = np.ascontiguousarray([1 if len(s) > 2 and s[2] else 0 for s in subterms], np.uint8)
+        return dict(op=op, boost=boost, term_len_boost=term_len_boost, field_boosts=fb, need_sum_rank=ns,
+                    postings=np.ascontiguousarray([s[0] for s in subterms], np.uint32),
+                    procs=np.ascontiguousarray([s[1] for s in subterms], np.float32), suppressed=sup if sup.any() else None,
+                    synonym_ids=np.ascontiguousarray(list(synonym_ids), np.uint32))
+
+    def add_term(self, subterms, op=OP_OR, boost=1.0, term_len_boost=1.0, field_boosts=None, need_sum_rank=None, synonym_ids=()):
+        """subterms: list of (list id, proc); synonym_ids: indexes of multi-word synonyms of this query part (add_synonym)"""
+        self.terms.append(self._term(subterms, op, boost, term_len_boost, field_boosts, need_sum_rank, synonym_ids))
+
+    def add_synonym(self, terms):
+        """terms: list of dict(subterms=[(list id, proc[, suppressed])], op=..., boost=..., term_len_boost=..., field_boosts=...);
+        returns the synonym's index"""
+        self.synonyms.append([self._term(t["subterms"], t.get("op", OP_OR), t.get("boost", 1.0), t.get("term_len_boost", 1.0),
+                                         t.get("field_boosts"), t.get("need_sum_rank")) for t in terms])
+        return len(self.synonyms) - 1
 
     # ctypes views --------------------------------------------------------------------------------------------------------
     def c_lists(self):
@@ -113,12 +131,26 @@ class FtProblem:
                       self.cfg["distance_boost"], self.cfg["distance_weight"], self.cfg["full_match_boost"], self.nfields, self._fc,
                       self.cfg.get("summation_ranks_by_fields_ratio", 0.0))
 
+    @staticmethod
+    def _c_term(t):
+        return Term(t["op"], t["boost"], t["term_len_boost"], _p(t["field_boosts"], _f32p), len(t["postings"]), _p(t["postings"], _u32p),
+                    _p(t["procs"], _f32p), None if t.get("need_sum_rank") is None else _p(t["need_sum_rank"], _u8p),
+                    None if t.get("suppressed") is None else _p(t["suppressed"], _u8p), len(t.get("synonym_ids", ())),
+                    _p(t["synonym_ids"], _u32p) if len(t.get("synonym_ids", ())) else None)
+
     def c_terms(self):
         arr = (Term * max(len(self.terms), 1))()
         for i, t in enumerate(self.terms):
-            arr[i] = Term(t["op"], t["boost"], t["term_len_boost"], _p(t["field_boosts"], _f32p), len(t["postings"]),
-                          _p(t["postings"], _u32p), _p(t["procs"], _f32p),
-                          None if t.get("need_sum_rank") is None else _p(t["need_sum_rank"], _u8p))
+            arr[i] = self._c_term(t)
+        return arr
+
+    def c_synonyms(self):
+        arr = (Synonym * max(len(self.synonyms), 1))()
+        self._syn_terms = []
+        for i, syn in enumerate(self.synonyms):
+            ta = (Term * len(syn))(*[self._c_term(t) for t in syn])
+            self._syn_terms.append(ta)
+            arr[i] = Synonym(len(syn), ta)
         return arr
 
 
@@ -146,6 +178,10 @@ def ref_lib():
         lib = C.CDLL(os.path.join(HERE, "_ref", "liboracle_ref_ft.so"))
         lib.ref_ft_last_error.restype = C.c_char_p
         _merge_argtypes(lib.ref_ft_merge, True)
+        lib.ref_ft_merge_query.restype = C.c_int
+        lib.ref_ft_merge_query.argtypes = [C.c_uint32, C.c_uint32, _u32p, _f32p, _u8p, _u8p, C.c_uint32, C.POINTER(Postings), C.POINTER(Config),
+                                           C.c_uint32, C.POINTER(Term), C.c_uint32, C.POINTER(Synonym), C.c_int, C.c_int, C.c_uint64,
+                                           C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]
         lib.ref_ft_calc_term_rank.restype = C.c_int
         lib.ref_ft_calc_term_rank.argtypes = [C.c_uint32, C.POINTER(Config), C.POINTER(Term), C.c_float, C.c_double, C.c_double, C.c_uint32,
                                               _u32p, _u32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.POINTER(C.c_int)]
@@ -195,12 +231,24 @@ def _run(fn, prob: FtProblem, rank_sort_type, packed=None, max_out=None):
 
 
 def ref_merge(prob, rank_sort_type=RANK_AND_ID, packed=False):
+    if prob.synonyms:
+        lists, cfg, terms, syns = prob.c_lists(), prob.c_config(), prob.c_terms(), prob.c_synonyms()
+        out = np.zeros(max(prob.total_docs, 1), MERGE_INFO_DTYPE)
+        n, ns = C.c_uint64(0), C.c_int64(0)
+        rc = ref_lib().ref_ft_merge_query(prob.total_docs, prob.nfields, _p(prob.words, _u32p), _p(prob.avg, _f32p),
+                                          None if prob.removed is None else _p(prob.removed, _u8p),
+                                          None if prob.excluded is None else _p(prob.excluded, _u8p), len(prob.lists), lists, C.byref(cfg),
+                                          len(prob.terms), terms, len(prob.synonyms), syns, rank_sort_type, int(packed), prob.total_docs,
+                                          out.ctypes.data, C.byref(n), C.byref(ns))
+        assert rc == 0, ref_lib().ref_ft_last_error().decode()
+        return out[:n.value].copy(), ns.value
     rc, out, n, ns = _run(ref_lib().ref_ft_merge, prob, rank_sort_type, packed)
     assert rc == 0, ref_lib().ref_ft_last_error().decode()
     return out, ns
 
 
 def port_merge(prob, rank_sort_type=RANK_AND_ID):
+    assert not prob.synonyms, "the C port does not restate multi-word synonyms; use the reference facade (oracle/_ref)"
     rc, out, n, ns = _run(port_lib().port_ft_merge, prob, rank_sort_type)
     assert rc == 0, "port_ft_merge failed"
     return out, ns

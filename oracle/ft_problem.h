@@ -40,7 +40,15 @@ typedef struct { /* one TermResults: FtDslOpts (ftdsl.h:18-30) + its SubtermResu
 	const uint32_t* postings; /* indexes into the lists array */
 	const float* procs;
 	const uint8_t* need_sum_rank; /* nfields flags (FtDslFieldOpts::needSumRank) or NULL */
+	const uint8_t* suppressed;    /* nsubterms flags (SubtermResults::Suppressed) or NULL */
+	uint32_t nsynonyms;           /* PhraseOrTerm::SynonymsIds */
+	const uint32_t* synonym_ids;
 } ft_term;
+
+typedef struct { /* ft::Synonym, querymergedata.h:168-188 */
+	uint32_t nterms;
+	const ft_term* terms;
+} ft_synonym;
 
 typedef struct { /* ft::MergeInfo, ft_fast/phrasemerger.h:57-62 */
 	int32_t id;

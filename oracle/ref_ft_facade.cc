@@ -79,26 +79,48 @@ void buildList(const ft_postings& l, reindexer::PackedIdRelVec& out) {
 	out.insert_back(tmp.begin(), tmp.end());
 }
 
+template <typename IdCont>
+reindexer::ft::TermResults<IdCont> makeTerm(const ft_term& t, uint32_t nfields, std::vector<IdCont>& lists) {
+	reindexer::FtDSLEntry e;
+	e.Opts().op = OpType(t.op);
+	e.Opts().boost = t.boost;
+	e.Opts().termLenBoost = t.term_len_boost;
+	e.Opts().fieldsOpts.resize(nfields);
+	for (uint32_t f = 0; f < nfields; ++f) {
+		e.Opts().fieldsOpts[f].boost = t.field_boosts[f];
+		e.Opts().fieldsOpts[f].needSumRank = t.need_sum_rank && t.need_sum_rank[f];
+	}
+	reindexer::ft::TermResults<IdCont> tr(std::move(e));
+	for (uint32_t s = 0; s < t.nsubterms; ++s) {
+		tr.AddSubterm(lists[t.postings[s]], "w", reindexer::WordIdType{}, t.procs[s]);
+		if (t.suppressed && t.suppressed[s]) {
+			tr.Subterm(s).SetSuppressed(true);  // what QueryMergeData::SupressDuplicatesInSynonyms decides from the pattern ids
+		}
+	}
+	return tr;
+}
+
 template <typename IdCont, typename OffsetT>
 int64_t runMerge(uint32_t totalDocs, const Stats& stats, const uint8_t* excluded, std::vector<IdCont>& lists, reindexer::FTConfig& cfg,
-				 uint32_t nterms, const ft_term* terms, int rankSortType, std::vector<reindexer::ft::MergeInfo>& out) {
+				 uint32_t nterms, const ft_term* terms, uint32_t nsyn, const ft_synonym* syns, int rankSortType,
+				 std::vector<reindexer::ft::MergeInfo>& out) {
 	reindexer::ft::QueryMergeData<IdCont> q;
+	for (uint32_t y = 0; y < nsyn; ++y) {  // the selecter appends synonyms while it walks the terms (selecterimpl.h:440-466,580-603)
+		reindexer::ft::Synonym<IdCont> syn;
+		for (uint32_t t = 0; t < syns[y].nterms; ++t) {
+			auto tr = makeTerm(syns[y].terms[t], stats.nfields, lists);
+			q.totalORVids += tr.MaxVDocs();
+			syn.AddTerm(std::move(tr));
+		}
+		q.synonyms.emplace_back(std::move(syn));
+	}
 	for (uint32_t t = 0; t < nterms; ++t) {
-		reindexer::FtDSLEntry e;
-		e.Opts().op = OpType(terms[t].op);
-		e.Opts().boost = terms[t].boost;
-		e.Opts().termLenBoost = terms[t].term_len_boost;
-		e.Opts().fieldsOpts.resize(stats.nfields);
-		for (uint32_t f = 0; f < stats.nfields; ++f) {
-			e.Opts().fieldsOpts[f].boost = terms[t].field_boosts[f];
-			e.Opts().fieldsOpts[f].needSumRank = terms[t].need_sum_rank && terms[t].need_sum_rank[f];
-		}
-		reindexer::ft::TermResults<IdCont> tr(std::move(e));
-		for (uint32_t s = 0; s < terms[t].nsubterms; ++s) {
-			tr.AddSubterm(lists[terms[t].postings[s]], "w", reindexer::WordIdType{}, terms[t].procs[s]);
-		}
+		auto tr = makeTerm(terms[t], stats.nfields, lists);
 		q.totalORVids += tr.MaxVDocs();
 		q.queryParts.emplace_back(std::move(tr));
+		for (uint32_t y = 0; y < terms[t].nsynonyms; ++y) {
+			q.queryParts.back().AddSynonymId(terms[t].synonym_ids[y]);
+		}
 	}
 	reindexer::FtMergeStatuses::Statuses docsExcluded(totalDocs, false);
 	if (excluded) {
@@ -135,22 +157,31 @@ int64_t runMerge(uint32_t totalDocs, const Stats& stats, const uint8_t* excluded
 
 template <typename IdCont>
 int64_t dispatch(uint32_t totalDocs, const Stats& stats, const uint8_t* excluded, uint32_t nlists, const ft_postings* lists,
-				 reindexer::FTConfig& cfg, uint32_t nterms, const ft_term* terms, int rankSortType, std::vector<reindexer::ft::MergeInfo>& out) {
+				 reindexer::FTConfig& cfg, uint32_t nterms, const ft_term* terms, uint32_t nsyn, const ft_synonym* syns, int rankSortType,
+				 std::vector<reindexer::ft::MergeInfo>& out) {
 	std::vector<IdCont> conts(nlists);
 	for (uint32_t i = 0; i < nlists; ++i) {
 		buildList(lists[i], conts[i]);
 	}
 	uint64_t totalOR = 0;
+	auto count = [&](const ft_term& t) {
+		for (uint32_t s = 0; s < t.nsubterms; ++s) {
+			totalOR += lists[t.postings[s]].ndocs;
+		}
+	};
 	for (uint32_t t = 0; t < nterms; ++t) {
-		for (uint32_t s = 0; s < terms[t].nsubterms; ++s) {
-			totalOR += lists[terms[t].postings[s]].ndocs;
+		count(terms[t]);
+	}
+	for (uint32_t y = 0; y < nsyn; ++y) {
+		for (uint32_t t = 0; t < syns[y].nterms; ++t) {
+			count(syns[y].terms[t]);
 		}
 	}
 	const uint64_t maxMerged = std::min<uint64_t>(cfg.mergeLimit, totalOR);  // selecterimpl.h:637-644
 	if (maxMerged < 0xFFFF) {
-		return runMerge<IdCont, uint16_t>(totalDocs, stats, excluded, conts, cfg, nterms, terms, rankSortType, out);
+		return runMerge<IdCont, uint16_t>(totalDocs, stats, excluded, conts, cfg, nterms, terms, nsyn, syns, rankSortType, out);
 	}
-	return runMerge<IdCont, uint32_t>(totalDocs, stats, excluded, conts, cfg, nterms, terms, rankSortType, out);
+	return runMerge<IdCont, uint32_t>(totalDocs, stats, excluded, conts, cfg, nterms, terms, nsyn, syns, rankSortType, out);
 }
 
 }  // namespace
@@ -161,10 +192,10 @@ const char* ref_ft_last_error() { return g_err.c_str(); }
 
 // ft::Merger::Merge on one problem.  packed != 0 uses PackedIdRelVec (the default Optimization::Memory container).
 // *merge_ns = wall time of the Merge call alone (container construction excluded).  Returns 0 on success.
-int ref_ft_merge(uint32_t total_docs, uint32_t nfields, const uint32_t* words, const float* avg, const uint8_t* removed,
-				 const uint8_t* excluded, uint32_t nlists, const ft_postings* lists, const ft_config* cfg, uint32_t nterms,
-				 const ft_term* terms, int rank_sort_type, int packed, uint64_t max_out, ft_merge_info* out, uint64_t* out_n,
-				 int64_t* merge_ns) {
+int ref_ft_merge_query(uint32_t total_docs, uint32_t nfields, const uint32_t* words, const float* avg, const uint8_t* removed,
+					   const uint8_t* excluded, uint32_t nlists, const ft_postings* lists, const ft_config* cfg, uint32_t nterms,
+					   const ft_term* terms, uint32_t nsyn, const ft_synonym* syns, int rank_sort_type, int packed, uint64_t max_out,
+					   ft_merge_info* out, uint64_t* out_n, int64_t* merge_ns) {
 	try {
 		reindexer::FTConfig c(nfields);
 		fillConfig(c, cfg);
@@ -173,9 +204,9 @@ int ref_ft_merge(uint32_t total_docs, uint32_t nfields, const uint32_t* words, c
 																								 : 1);
 		Stats stats{words, avg, removed, nfields};
 		std::vector<reindexer::ft::MergeInfo> res;
-		const int64_t ns = packed ? dispatch<reindexer::PackedIdRelVec>(total_docs, stats, excluded, nlists, lists, c, nterms, terms,
-																		rank_sort_type, res)
-								  : dispatch<reindexer::IdRelVec>(total_docs, stats, excluded, nlists, lists, c, nterms, terms,
+		const int64_t ns = packed ? dispatch<reindexer::PackedIdRelVec>(total_docs, stats, excluded, nlists, lists, c, nterms, terms, nsyn,
+																		syns, rank_sort_type, res)
+								  : dispatch<reindexer::IdRelVec>(total_docs, stats, excluded, nlists, lists, c, nterms, terms, nsyn, syns,
 																  rank_sort_type, res);
 		if (merge_ns) {
 			*merge_ns = ns;
@@ -192,6 +223,13 @@ int ref_ft_merge(uint32_t total_docs, uint32_t nfields, const uint32_t* words, c
 		g_err = e.what();
 		return 1;
 	}
+}
+int ref_ft_merge(uint32_t total_docs, uint32_t nfields, const uint32_t* words, const float* avg, const uint8_t* removed,
+				 const uint8_t* excluded, uint32_t nlists, const ft_postings* lists, const ft_config* cfg, uint32_t nterms,
+				 const ft_term* terms, int rank_sort_type, int packed, uint64_t max_out, ft_merge_info* out, uint64_t* out_n,
+				 int64_t* merge_ns) {
+	return ref_ft_merge_query(total_docs, nfields, words, avg, removed, excluded, nlists, lists, cfg, nterms, terms, 0, nullptr,
+							  rank_sort_type, packed, max_out, out, out_n, merge_ns);
 }
 
 // calcTermRank on one posting: the numbers FTGenericApi.DebugInfo pins (gtests/tests/unit/ft/ft_generic.cc:297-445)

@@ -66,7 +66,16 @@ class FtConfig(C.Structure):
 
 class FtTerm(C.Structure):
     _fields_ = [("op", C.c_int32), ("boost", C.c_float), ("term_len_boost", C.c_float), ("field_boosts", _f32p), ("nsubterms", C.c_uint32),
-                ("postings", _u32p), ("procs", _f32p), ("need_sum_rank", _u8p)]
+                ("postings", _u32p), ("procs", _f32p), ("need_sum_rank", _u8p), ("suppressed", _u8p), ("nsynonyms", C.c_uint32),
+                ("synonym_ids", _u32p)]
+
+
+class FtSynonym(C.Structure):
+    _fields_ = [("nterms", C.c_uint32), ("terms", C.POINTER(FtTerm))]
+
+
+class FtQuery(C.Structure):
+    _fields_ = [("nterms", C.c_uint32), ("terms", C.POINTER(FtTerm)), ("nsynonyms", C.c_uint32), ("synonyms", C.POINTER(FtSynonym))]
 
 
 class Sq8Params(C.Structure):
@@ -157,6 +166,9 @@ _SIGNATURES = {
     "rxgpu_ft_decode_packed": (C.c_int, [_u8p, C.c_uint64, C.c_uint32, _u32p, _u32p, _u32p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "rxgpu_ft_merge": (C.c_int, [C.c_void_p, C.POINTER(FtConfig), C.c_uint32, C.POINTER(FtTerm), _u8p, C.c_int, C.c_uint64, C.c_void_p,
                                  C.POINTER(C.c_uint64)]),
+    "rxgpu_ft_merge_query": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _u8p, C.c_int, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "rxgpu_ft_select_query": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _u8p, _u8p, C.c_int, C.c_uint64, _i32p, _f32p,
+                                         C.POINTER(C.c_uint64)]),
     "rxgpu_ft_set_rows": (C.c_int, [C.c_void_p, _u32p, _i32p]),
     "rxgpu_ft_select": (C.c_int, [C.c_void_p, C.POINTER(FtConfig), C.c_uint32, C.POINTER(FtTerm), _u8p, _u8p, C.c_int, C.c_uint64, _i32p, _f32p,
                                   C.POINTER(C.c_uint64)]),
@@ -613,17 +625,32 @@ class GpuFtIndex:
         _check(self._lib.rxgpu_ft_add_postings_packed(self._h, _p(b, _u8p), len(b), count, C.byref(out)))
         return out.value
 
-    def merge(self, cfg: dict, field_cfg: list, terms: list, excluded=None, rank_sort_type=1, max_out=None):
+    def merge(self, cfg: dict, field_cfg: list, terms: list, excluded=None, rank_sort_type=1, max_out=None, synonyms=None):
         """cfg / field_cfg: dicts with the FtConfig / FtFieldConfig member names; terms: dicts(op, boost, term_len_boost, field_boosts,
-        postings, procs).  Returns a structured array (id, proc, field, normalized_proc)."""
+        postings, procs[, suppressed, synonym_ids]); synonyms: lists of such dicts (multi-word synonyms).  Returns a structured array
+        (id, proc, field, normalized_proc)."""
         c, arr, keep = self._config_and_terms(cfg, field_cfg, terms)
         ex = None if excluded is None else np.ascontiguousarray(excluded, np.uint8)
         max_out = self.total_docs if max_out is None else max_out
         out = np.zeros(max(max_out, 1), FT_MERGE_INFO_DTYPE)
         n = C.c_uint64(0)
-        _check(self._lib.rxgpu_ft_merge(self._h, C.byref(c), len(terms), arr, None if ex is None else _p(ex, _u8p), rank_sort_type, max_out,
-                                        out.ctypes.data, C.byref(n)))
+        if synonyms:
+            q = self._query(arr, len(terms), synonyms, keep)
+            _check(self._lib.rxgpu_ft_merge_query(self._h, C.byref(c), C.byref(q), None if ex is None else _p(ex, _u8p), rank_sort_type,
+                                                  max_out, out.ctypes.data, C.byref(n)))
+        else:
+            _check(self._lib.rxgpu_ft_merge(self._h, C.byref(c), len(terms), arr, None if ex is None else _p(ex, _u8p), rank_sort_type,
+                                            max_out, out.ctypes.data, C.byref(n)))
         return out[:min(n.value, max_out)].copy()
+
+    def _query(self, arr, nterms, synonyms, keep):
+        syn = (FtSynonym * len(synonyms))()
+        for i, terms in enumerate(synonyms):
+            ta = self._terms(terms, keep)
+            keep.append(ta)
+            syn[i] = FtSynonym(len(terms), ta)
+        keep.append(syn)
+        return FtQuery(nterms, arr, len(synonyms), syn)
 
     def set_rows(self, row_begin, row_ids):
         """vdoc -> row ids (CSR), the IndexText::vdocs_[vdoc].RowIds() of the reference"""
@@ -631,7 +658,7 @@ class GpuFtIndex:
         ri = np.ascontiguousarray(row_ids, np.int32)
         _check(self._lib.rxgpu_ft_set_rows(self._h, _p(rb, _u32p), _p(ri, _i32p)))
 
-    def select(self, cfg, field_cfg, terms, limit, excluded=None, row_status=None, rank_sort_type=1):
+    def select(self, cfg, field_cfg, terms, limit, excluded=None, row_status=None, rank_sort_type=1, synonyms=None):
         """merge + postProcessResults + afterSelect + sortAfterSelect on the device: (row_ids, ranks, total rows)"""
         c, arr, keep = self._config_and_terms(cfg, field_cfg, terms)
         ex = None if excluded is None else np.ascontiguousarray(excluded, np.uint8)
@@ -639,8 +666,15 @@ class GpuFtIndex:
         ids = np.zeros(max(limit, 1), np.int32)
         ranks = np.zeros(max(limit, 1), np.float32)
         n = C.c_uint64(0)
-        _check(self._lib.rxgpu_ft_select(self._h, C.byref(c), len(terms), arr, None if ex is None else _p(ex, _u8p),
-                                         None if rs is None else _p(rs, _u8p), rank_sort_type, limit, _p(ids, _i32p), _p(ranks, _f32p), C.byref(n)))
+        if synonyms:
+            q = self._query(arr, len(terms), synonyms, keep)
+            _check(self._lib.rxgpu_ft_select_query(self._h, C.byref(c), C.byref(q), None if ex is None else _p(ex, _u8p),
+                                                   None if rs is None else _p(rs, _u8p), rank_sort_type, limit, _p(ids, _i32p), _p(ranks, _f32p),
+                                                   C.byref(n)))
+        else:
+            _check(self._lib.rxgpu_ft_select(self._h, C.byref(c), len(terms), arr, None if ex is None else _p(ex, _u8p),
+                                             None if rs is None else _p(rs, _u8p), rank_sort_type, limit, _p(ids, _i32p), _p(ranks, _f32p),
+                                             C.byref(n)))
         m = min(n.value, limit)
         return ids[:m], ranks[:m], n.value
 
@@ -649,16 +683,24 @@ class GpuFtIndex:
         c = FtConfig(cfg["merge_limit"], cfg["min_rank"], cfg["bm25_k1"], cfg["bm25_b"], cfg["bm25_type"], cfg["distance_boost"],
                      cfg["distance_weight"], cfg["full_match_boost"], self.nfields, fc, cfg.get("summation_ranks_by_fields_ratio", 0.0))
         keep = [fc]
+        arr = self._terms(terms, keep)
+        return c, arr, keep
+
+    @staticmethod
+    def _terms(terms, keep):
         arr = (FtTerm * max(len(terms), 1))()
         for i, t in enumerate(terms):
             fb = np.ascontiguousarray(t["field_boosts"], np.float32)
             po = np.ascontiguousarray(t["postings"], np.uint32)
             pr = np.ascontiguousarray(t["procs"], np.float32)
             ns = None if t.get("need_sum_rank") is None else np.ascontiguousarray(t["need_sum_rank"], np.uint8)
-            keep += [fb, po, pr, ns]
+            su = None if t.get("suppressed") is None else np.ascontiguousarray(t["suppressed"], np.uint8)
+            sy = np.ascontiguousarray(t.get("synonym_ids", ()), np.uint32)
+            keep += [fb, po, pr, ns, su, sy]
             arr[i] = FtTerm(t["op"], t["boost"], t["term_len_boost"], _p(fb, _f32p), len(po), _p(po, _u32p), _p(pr, _f32p),
-                            None if ns is None else _p(ns, _u8p))
-        return c, arr, keep
+                            None if ns is None else _p(ns, _u8p), None if su is None else _p(su, _u8p), len(sy),
+                            _p(sy, _u32p) if len(sy) else None)
+        return arr
 
     def last_stats(self) -> dict:
         s = FtStats()

@@ -682,6 +682,51 @@ __global__ void ft_reset_idoff(const int32_t* md_id, const uint32_t* n_docs, uin
 __global__ void ft_bump_count(uint32_t* n_docs, const uint32_t* total_new, uint32_t max_merged) {
 	*n_docs = min(*n_docs + *total_new, max_merged);
 }
+__global__ void ft_mask_or(uint32_t* mask, const uint32_t* other, uint32_t words) {
+	for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += gridDim.x * blockDim.x) {
+		mask[w] |= other[w];
+	}
+}
+// a suppressed subterm of a multi-word synonym (QueryMergeData::SupressDuplicatesInSynonyms, querymergedata.h:221-241): it only counts
+// towards termsCounter of documents that are already merged (mergerimpl.h:144-151)
+__global__ void ft_suppressed_pass(DevList l, MergeState st, const uint8_t* removed, int check_removed, uint32_t sentinel, uint16_t qp_idx) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= l.ndocs) {
+		return;
+	}
+	const uint32_t d = l.doc_ids[i];
+	if (!((st.mask[d >> 5] >> (d & 31)) & 1u) || (check_removed && removed && removed[d])) {
+		return;
+	}
+	const uint32_t slot = st.idoff[d];
+	if (slot != sentinel && st.ext_last_term[slot] < qp_idx) {
+		st.ext_cnt[slot]++;
+		st.ext_last_term[slot] = qp_idx;
+	}
+}
+// after the terms of one multi-word synonym: documents added since the synonyms began either hold all of its terms or start counting
+// again (mergerimpl.h:517-525)
+__global__ void ft_syn_mark(MergeState st, const uint32_t* before, uint16_t num_terms, uint8_t* full) {
+	const uint32_t n = *st.n_docs;
+	for (uint32_t i = *before + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		if (st.ext_cnt[i] < num_terms) {
+			st.ext_cnt[i] = 0;
+		} else {
+			full[i] = 1;
+		}
+	}
+}
+// documents that hold only a part of a multi-word synonym leave the result (mergerimpl.h:539-560): marked with proc = -inf, which the
+// post-processing drops (device) or filters in order (host)
+__global__ void ft_syn_finish(MergeState st, const uint32_t* before, const uint8_t* full) {
+	const uint32_t n = *st.n_docs;
+	for (uint32_t i = *before + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		if (!full[i]) {
+			st.md_proc[i] = -INFINITY;
+		}
+	}
+}
+__global__ void ft_copy_u32(uint32_t* dst, const uint32_t* src) { *dst = *src; }
 // addFullMatchBoost (merger.h:100-109) with canBeBoostedByFullMatch (mergerimpl.h:533-537)
 __global__ void ft_full_match(MergeState st, const uint32_t* words, uint32_t nfields, uint32_t num_terms, uint32_t need_cnt, int simple,
 							  double boost) {
@@ -789,6 +834,8 @@ struct rxgpu_ft_index {
 	std::mutex mtx;  // one merge at a time per index (the per-document scratch below is shared)
 	// scratch
 	DevBuf<uint32_t> mask, tmask, idoff, block_counts, scalar_u32;
+	DevBuf<uint32_t> syn_masks, tmask2;  // multi-word synonyms: one document mask per synonym + a per-term scratch
+	DevBuf<uint8_t> syn_full;            // MergerDocumentData::containsFullMultiWordSynonym per merged document
 	bool idoff_clean = false;  // idoff holds kNoSlot everywhere
 	PinBuf<int32_t> h_id;  // results of the last merge (pinned: one asynchronous copy per array, one synchronisation per query)
 	PinBuf<float> h_proc;
@@ -988,11 +1035,24 @@ struct SelectReq {  // rxgpu_ft_select: post-processing and IndexText::afterSele
 	int32_t* out_row_ids;
 	float* out_ranks;
 };
-int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nterms, const rxgpu_ft_term* terms, const uint8_t* excluded,
-				int rank_sort_type, uint64_t max_out, rxgpu_ft_merge_info* out, uint64_t* out_n, const SelectReq* sel) {
-	if (!ft || !cfg || !out_n || (nterms && !terms)) {
+int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_query* query, const uint8_t* excluded, int rank_sort_type,
+				uint64_t max_out, rxgpu_ft_merge_info* out, uint64_t* out_n, const SelectReq* sel) {
+	if (!ft || !cfg || !out_n || !query || (query->nterms && !query->terms) || (query->nsynonyms && !query->synonyms)) {
 		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
 	}
+	// the query parts, then the terms of the multi-word synonyms in the order Merger::Merge walks them (mergerimpl.h:510-515)
+	const uint32_t nterms = query->nterms, nsyn = query->nsynonyms;
+	std::vector<rxgpu_ft_term> flat(query->terms, query->terms + nterms);
+	std::vector<uint32_t> synBegin(nsyn + 1, nterms);
+	for (uint32_t y = 0; y < nsyn; ++y) {
+		if (query->synonyms[y].nterms == 0 || !query->synonyms[y].terms) {
+			return fail(RXGPU_ERR_PARAMS, "rxgpu: a multi-word synonym without terms");
+		}
+		flat.insert(flat.end(), query->synonyms[y].terms, query->synonyms[y].terms + query->synonyms[y].nterms);
+		synBegin[y + 1] = uint32_t(flat.size());
+	}
+	const rxgpu_ft_term* terms = flat.data();
+	const uint32_t nall = uint32_t(flat.size());
 	if (cfg->nfields != ft->nfields || !cfg->fields) {
 		return fail(RXGPU_ERR_PARAMS, "rxgpu: config field count differs from the index");
 	}
@@ -1006,9 +1066,17 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nterms,
 	if (nterms == 0 || (nterms == 1 && terms[0].op == 3) || N == 0) {  // QueryMergeData::Empty(), mergerimpl.h:472
 		return 0;
 	}
-	for (uint32_t t = 0; t < nterms; ++t) {
+	for (uint32_t t = 0; t < nall; ++t) {
 		if (terms[t].op < 1 || terms[t].op > 3 || !terms[t].field_boosts || (terms[t].nsubterms && (!terms[t].postings || !terms[t].procs))) {
 			return fail(RXGPU_ERR_PARAMS, "rxgpu: malformed query term");
+		}
+		if (terms[t].nsynonyms && (t >= nterms || !terms[t].synonym_ids)) {
+			return fail(RXGPU_ERR_PARAMS, "rxgpu: synonym ids belong to query parts only");
+		}
+		for (uint32_t y = 0; y < terms[t].nsynonyms; ++y) {
+			if (terms[t].synonym_ids[y] >= nsyn) {
+				return fail(RXGPU_ERR_PARAMS, "rxgpu: unknown synonym id");
+			}
 		}
 		for (uint32_t s = 0; s < terms[t].nsubterms; ++s) {
 			if (terms[t].postings[s] >= ft->lists.size()) {
@@ -1035,18 +1103,19 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nterms,
 	struct Sub {
 		uint32_t list;
 		float proc;
+		bool suppressed;
 	};
-	std::vector<std::vector<Sub>> subs(nterms);
-	uint64_t totalORVids = 0;
-	for (uint32_t t = 0; t < nterms; ++t) {
+	std::vector<std::vector<Sub>> subs(nall);
+	uint64_t totalORVids = 0;  // selecterimpl.h:443,462,546,595: the synonyms' terms count as well
+	for (uint32_t t = 0; t < nall; ++t) {
 		for (uint32_t s = 0; s < terms[t].nsubterms; ++s) {
-			subs[t].push_back(Sub{terms[t].postings[s], terms[t].procs[s]});
+			subs[t].push_back(Sub{terms[t].postings[s], terms[t].procs[s], terms[t].suppressed && terms[t].suppressed[s]});
 			totalORVids += ft->lists[terms[t].postings[s]].ndocs;
 		}
 		std::stable_sort(subs[t].begin(), subs[t].end(), [](const Sub& a, const Sub& b) { return a.proc > b.proc; });
 	}
 	const uint32_t maxMerged = uint32_t(std::min<uint64_t>(cfg->merge_limit, totalORVids));  // init(), merger.h:66-67
-	const bool simple = nterms == 1 && terms[0].op != 3;
+	const bool simple = nterms == 1 && terms[0].op != 3 && nsyn == 0;  // QueryMergeData::Simple()
 	const bool trivial = simple && terms[0].nsubterms == 1;
 	if (maxMerged == 0) {
 		return 0;
@@ -1059,7 +1128,12 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nterms,
 	RX_CUDA(ft->mask.ensure(mwords));
 	RX_CUDA(ft->tmask.ensure(mwords));
 	RX_CUDA(ft->block_counts.ensure(std::max(nblocks_list, nblocks_docs)));
-	RX_CUDA(ft->scalar_u32.ensure(4));
+	RX_CUDA(ft->scalar_u32.ensure(8));
+	if (nsyn) {
+		RX_CUDA(ft->syn_masks.ensure(size_t(nsyn) * mwords));
+		RX_CUDA(ft->tmask2.ensure(mwords));
+		RX_CUDA(ft->syn_full.ensure(maxMerged));
+	}
 	RX_CUDA(ft->popc.ensure(1));
 	RX_CUDA(ft->tmp_rank.ensure(std::max<size_t>(1, ft->max_list)));
 	RX_CUDA(ft->tmp_field.ensure(std::max<size_t>(1, ft->max_list)));
@@ -1111,7 +1185,7 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nterms,
 	RX_CUDA(ft->h_field.ensure(maxMerged));
 	RX_CUDA(ft->h_n.ensure(1));
 	RX_CUDA(cudaEventRecord(e0, st));
-	RX_CUDA(cudaMemsetAsync(ft->scalar_u32.p, 0, 16, st));
+	RX_CUDA(cudaMemsetAsync(ft->scalar_u32.p, 0, 32, st));
 	if (!trivial) {  // idoffsets_: every merge leaves the table clean again (ft_reset_idoff), so the 4 N byte fill runs only once
 		if (!ft->idoff_clean) {
 			ft_fill_u32<<<gridFor(N, sm), kFtThreads, 0, st>>>(ft->idoff.p, kNoSlot, N);
@@ -1156,6 +1230,7 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nterms,
 	int checkRemoved = 1;
 	if (!simple) {
 		// buildRestrictingBitmask (mergerimpl.h:326-384)
+		std::vector<uint8_t> synMaskDone(nsyn, 0);
 		for (uint32_t t = 0; t < nterms; ++t) {
 			if (terms[t].op != 2) {
 				continue;
@@ -1173,6 +1248,36 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nterms,
 					g_ft_stats.postings_scanned += l.ndocs;
 					g_ft_stats.algorithmic_bytes += bytesOfPass(l);
 				}
+			}
+			for (uint32_t y = 0; y < terms[t].nsynonyms; ++y) {  // termMask |= AND over the synonym's terms (mergerimpl.h:352-363)
+				const uint32_t sy = terms[t].synonym_ids[y];
+				uint32_t* synMask = ft->syn_masks.p + size_t(sy) * mwords;
+				if (!synMaskDone[sy]) {
+					for (uint32_t u = synBegin[sy]; u < synBegin[sy + 1]; ++u) {
+						uint32_t* dst = u == synBegin[sy] ? synMask : ft->tmask2.p;
+						RX_CUDA(cudaMemsetAsync(dst, 0, size_t(mwords) * 4, st));
+						int allPos = 1;
+						for (uint32_t f = 0; f < ft->nfields; ++f) {
+							allPos &= terms[u].field_boosts[f] != 0.f;
+						}
+						for (const Sub& sub : subs[u]) {
+							const DevList& l = ft->lists[sub.list];
+							if (l.ndocs) {
+								ft_and_mark<<<gridFor(l.ndocs, sm), kFtThreads, 0, st>>>(l, termParams(u, sub, l), allPos, dst);
+								g_ft_stats.launches++;
+								g_ft_stats.postings_scanned += l.ndocs;
+								g_ft_stats.algorithmic_bytes += bytesOfPass(l);
+							}
+						}
+						if (u != synBegin[sy]) {
+							ft_mask_and<<<gridFor(mwords, sm), kFtThreads, 0, st>>>(synMask, ft->tmask2.p, mwords);
+							g_ft_stats.launches++;
+						}
+					}
+					synMaskDone[sy] = 1;
+				}
+				ft_mask_or<<<gridFor(mwords, sm), kFtThreads, 0, st>>>(ft->tmask.p, synMask, mwords);
+				g_ft_stats.launches++;
 			}
 			ft_mask_and<<<gridFor(mwords, sm), kFtThreads, 0, st>>>(ft->mask.p, ft->tmask.p, mwords);
 			g_ft_stats.launches++;
@@ -1200,6 +1305,11 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nterms,
 			for (const Sub& sub : subs[t]) {
 				nd += ft->lists[sub.list].ndocs;
 			}
+			for (uint32_t y = 0; y < terms[t].nsynonyms; ++y) {  // + the first term of each of its synonyms (merger.h:253-256)
+				for (const Sub& sub : subs[synBegin[terms[t].synonym_ids[y]]]) {
+					nd += ft->lists[sub.list].ndocs;
+				}
+			}
 			if (terms[t].op == 2) {
 				estAnd = std::min(estAnd, nd);
 			} else {
@@ -1224,8 +1334,9 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nterms,
 			RX_CUDA(ft->hist.ensure(65536));
 			RX_CUDA(cudaMemsetAsync(ft->score.p, 0, size_t(mwords) * 64, st));
 			RX_CUDA(cudaMemsetAsync(ft->hist.p, 0, 65536 * 8, st));
-			for (uint32_t t = 0; t < nterms; ++t) {
-				if (terms[t].op == 3) {
+			for (uint32_t tt = 0; tt < nall; ++tt) {
+				const uint32_t t = tt < nall - nterms ? nterms + tt : tt - (nall - nterms);  // the synonyms' terms first (mergerimpl.h:392-396)
+				if (t < nterms && terms[t].op == 3) {
 					continue;
 				}
 				RX_CUDA(cudaMemsetAsync(ft->tmask.p, 0, size_t(mwords) * 4, st));
@@ -1261,21 +1372,38 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nterms,
 	const uint32_t* d_words = ft->words.p;
 	const uint8_t* d_removed = ft->has_removed ? ft->removed.p : nullptr;
 	uint16_t qpIdx = 0;
-	for (uint32_t t = 0; t < nterms; ++t) {
-		if (terms[t].op == 3) {
-			continue;
+	uint32_t* d_before = ft->scalar_u32.p + 4;  // [4] numDocsBeforeSynonyms
+	for (uint32_t t = 0; t < nall; ++t) {
+		if (t == nterms) {
+			ft_copy_u32<<<1, 1, 0, st>>>(d_before, ms.n_docs);
+			RX_CUDA(cudaMemsetAsync(ft->syn_full.p, 0, maxMerged, st));
+			g_ft_stats.launches++;
 		}
-		++qpIdx;
-		if (!simple) {
+		// mergeTerm returns at once for OpNot (mergerimpl.h:113-115); a NOT query part does not even take an index (:497-499)
+		const bool isNot = terms[t].op == 3;
+		if (!isNot || t >= nterms) {
+			++qpIdx;
+		}
+		if (!simple && !isNot) {
 			ft_switch<<<gridFor(maxMerged, sm), kFtThreads, 0, st>>>(ms);
 			g_ft_stats.launches++;
 		}
 		for (const Sub& sub : subs[t]) {
+			if (isNot) {
+				break;
+			}
 			const DevList& l = ft->lists[sub.list];
 			if (!l.ndocs) {
 				continue;
 			}
 			const unsigned lb = (l.ndocs + kFtThreads - 1) / kFtThreads;
+			if (sub.suppressed) {
+				ft_suppressed_pass<<<lb, kFtThreads, 0, st>>>(l, ms, d_removed, checkRemoved, kNoSlot, qpIdx);
+				g_ft_stats.launches++;
+				g_ft_stats.postings_scanned += l.ndocs;
+				g_ft_stats.algorithmic_bytes += uint64_t(l.ndocs) * 8;
+				continue;
+			}
 			ft_rank_pass<<<lb, kFtThreads, 0, st>>>(l, termParams(t, sub, l), ms, d_words, ft->avg.p, d_removed, checkRemoved, simple ? 1 : 0,
 													kNoSlot, qpIdx, ft->tmp_rank.p, ft->tmp_field.p, ft->block_counts.p);
 			ft_scan_blocks<<<1, 1024, 0, st>>>(ft->block_counts.p, lb, d_total_new);
@@ -1285,11 +1413,21 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nterms,
 			g_ft_stats.postings_scanned += l.ndocs;
 			g_ft_stats.algorithmic_bytes += bytesOfPass(l) + uint64_t(l.ndocs) * 9;
 		}
+		for (uint32_t y = 0; y < nsyn; ++y) {
+			if (t + 1 == synBegin[y + 1]) {  // the last term of synonym y
+				ft_syn_mark<<<gridFor(maxMerged, sm), kFtThreads, 0, st>>>(ms, d_before, uint16_t(synBegin[y + 1] - synBegin[y]), ft->syn_full.p);
+				g_ft_stats.launches++;
+			}
+		}
 	}
 	// canBeBoostedByFullMatch: termsCounter == queryParts.size() (NOT parts never count) ; QueryLength == nterms
 	ft_full_match<<<gridFor(maxMerged, sm), kFtThreads, 0, st>>>(ms, d_words, ft->nfields, simple ? 1u : nterms, nterms, simple ? 1 : 0,
 																 cfg->full_match_boost);
 	g_ft_stats.launches++;
+	if (nsyn) {
+		ft_syn_finish<<<gridFor(maxMerged, sm), kFtThreads, 0, st>>>(ms, d_before, ft->syn_full.p);
+		g_ft_stats.launches++;
+	}
 	if (!trivial) {
 		ft_reset_idoff<<<gridFor(maxMerged, sm), kFtThreads, 0, st>>>(ms.md_id, ms.n_docs, ft->idoff.p);
 		g_ft_stats.launches++;
@@ -1408,10 +1546,14 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nterms,
 		const int32_t* ids = ft->h_id.p;
 		const float* procs = ft->h_proc.p;
 		const uint8_t* fields = ft->h_field.p;
-		std::vector<rxgpu_ft_merge_info> md(n);
+		std::vector<rxgpu_ft_merge_info> md;
+		md.reserve(n);
 		float maxProc = 0.f;
 		for (uint32_t i = 0; i < n; ++i) {
-			md[i] = rxgpu_ft_merge_info{ids[i], procs[i], fields[i], 0};
+			if (nsyn && procs[i] == -INFINITY) {
+				continue;  // held only a part of a multi-word synonym: removed in order (mergerimpl.h:539-560)
+			}
+			md.push_back(rxgpu_ft_merge_info{ids[i], procs[i], fields[i], 0});
 			maxProc = std::max(maxProc, procs[i]);
 		}
 		const float scalingFactor = maxProc > 255 ? float(255.0 / maxProc) : 1.0f;
@@ -1453,7 +1595,12 @@ extern "C" {
 
 int rxgpu_ft_merge(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nterms, const rxgpu_ft_term* terms, const uint8_t* excluded,
 				   int rank_sort_type, uint64_t max_out, rxgpu_ft_merge_info* out, uint64_t* out_n) {
-	return ftMergeImpl(ft, cfg, nterms, terms, excluded, rank_sort_type, max_out, out, out_n, nullptr);
+	const rxgpu_ft_query q{nterms, terms, 0, nullptr};
+	return ftMergeImpl(ft, cfg, &q, excluded, rank_sort_type, max_out, out, out_n, nullptr);
+}
+int rxgpu_ft_merge_query(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_query* query, const uint8_t* excluded, int rank_sort_type,
+						 uint64_t max_out, rxgpu_ft_merge_info* out, uint64_t* out_n) {
+	return ftMergeImpl(ft, cfg, query, excluded, rank_sort_type, max_out, out, out_n, nullptr);
 }
 
 int rxgpu_ft_set_rows(rxgpu_ft_index* ft, const uint32_t* row_begin, const int32_t* row_ids) {
@@ -1499,16 +1646,31 @@ int rxgpu_ft_set_rows(rxgpu_ft_index* ft, const uint32_t* row_begin, const int32
 	return 0;
 }
 
-int rxgpu_ft_select(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nterms, const rxgpu_ft_term* terms, const uint8_t* excluded,
-					const uint8_t* row_status, int rank_sort_type, uint64_t limit, int32_t* out_row_ids, float* out_ranks, uint64_t* out_n) {
+static int ftSelectCheck(int rank_sort_type, uint64_t limit, const int32_t* out_row_ids, const float* out_ranks) {
 	if (rank_sort_type != 1 && rank_sort_type != 3) {
 		return fail(RXGPU_ERR_PARAMS, "rxgpu: rxgpu_ft_select orders by RankAndID (1) or IDOnly (3); use rxgpu_ft_merge for the other sort types");
 	}
 	if (limit && (!out_row_ids || !out_ranks)) {
 		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
 	}
+	return 0;
+}
+int rxgpu_ft_select(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, uint32_t nterms, const rxgpu_ft_term* terms, const uint8_t* excluded,
+					const uint8_t* row_status, int rank_sort_type, uint64_t limit, int32_t* out_row_ids, float* out_ranks, uint64_t* out_n) {
+	if (int rc = ftSelectCheck(rank_sort_type, limit, out_row_ids, out_ranks)) {
+		return rc;
+	}
 	const SelectReq sel{row_status, limit, out_row_ids, out_ranks};
-	return ftMergeImpl(ft, cfg, nterms, terms, excluded, rank_sort_type, 0, nullptr, out_n, &sel);
+	const rxgpu_ft_query q{nterms, terms, 0, nullptr};
+	return ftMergeImpl(ft, cfg, &q, excluded, rank_sort_type, 0, nullptr, out_n, &sel);
+}
+int rxgpu_ft_select_query(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_query* query, const uint8_t* excluded,
+						  const uint8_t* row_status, int rank_sort_type, uint64_t limit, int32_t* out_row_ids, float* out_ranks, uint64_t* out_n) {
+	if (int rc = ftSelectCheck(rank_sort_type, limit, out_row_ids, out_ranks)) {
+		return rc;
+	}
+	const SelectReq sel{row_status, limit, out_row_ids, out_ranks};
+	return ftMergeImpl(ft, cfg, query, excluded, rank_sort_type, 0, nullptr, out_n, &sel);
 }
 
 }  // extern "C"

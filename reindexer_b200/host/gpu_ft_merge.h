@@ -9,8 +9,8 @@
 // available (tests/cpp/dropin_ft_check.cc does so in the authoring container).  INTEGRATION.md section 6 shows the patch.
 //
 // Covered on the device: query parts that are plain terms with their variant subterms (AND / OR / NOT), the preselect step, all three
-// BM25 variants, summationRanksByFieldsRatio.  Phrases and multi-word synonyms are NOT: Mergeable() says so and the caller keeps
-// ft::Merger for those queries (an explicit dispatch at the seam, not a fallback inside the library).
+// BM25 variants, summationRanksByFieldsRatio, multi-word synonyms (with their suppressed subterms).  Phrases are NOT: Mergeable() says
+// so and the caller keeps ft::Merger for those queries (an explicit dispatch at the seam, not a fallback inside the library).
 #pragma once
 
 #include <cstdlib>
@@ -53,9 +53,6 @@ public:
 
 	// what the device path covers; everything else stays with ft::Merger (the caller dispatches)
 	static bool Mergeable(const QueryMergeData<IdCont>& q) noexcept {
-		if (!q.synonyms.empty()) {
-			return false;
-		}
 		for (const auto& qp : q.queryParts) {
 			if (!qp.IsTerm()) {
 				return false;
@@ -67,7 +64,7 @@ public:
 	MergeData Merge(QueryMergeData<IdCont>& q, RankSortType rankSortType, const FtMergeStatuses::Statuses& docsExcluded, const FTConfig& cfg) {
 		MergeData out;
 		if (!Mergeable(q)) {
-			throw std::logic_error("GpuFtMerger: phrases and multi-word synonyms are merged by ft::Merger (see Mergeable())");
+			throw std::logic_error("GpuFtMerger: phrases are merged by ft::Merger (see Mergeable())");
 		}
 		if (q.Empty() || totalDocs_ == 0) {
 			return out;  // Merger::Merge, mergerimpl.h:472-474
@@ -101,27 +98,67 @@ public:
 		c.fields = fields.data();
 		c.summation_ranks_by_fields_ratio = cfg.summationRanksByFieldsRatio;
 
-		const size_t nterms = q.queryParts.size();
-		std::vector<rxgpu_ft_term> terms(nterms);
-		std::vector<std::vector<float>> boosts(nterms), procs(nterms);
-		std::vector<std::vector<uint8_t>> needSum(nterms);
-		std::vector<std::vector<uint32_t>> lists(nterms);
-		for (size_t t = 0; t < nterms; ++t) {
-			const TermResults<IdCont>& tr = q.queryParts[t].Term();
-			const FtDslOpts& o = tr.Opts();
-			boosts[t].resize(nfields_);
-			needSum[t].resize(nfields_);
-			for (uint32_t f = 0; f < nfields_; ++f) {
-				boosts[t][f] = o.fieldsOpts[f].boost;
-				needSum[t][f] = o.fieldsOpts[f].needSumRank ? 1 : 0;
-			}
-			for (const SubtermResults<IdCont>& st : tr) {
-				lists[t].push_back(postingsId(&st.Occurences()));
-				procs[t].push_back(st.Proc());
-			}
-			terms[t] = rxgpu_ft_term{int32_t(o.op), o.boost, o.termLenBoost, boosts[t].data(), uint32_t(lists[t].size()), lists[t].data(),
-									 procs[t].data(), needSum[t].data()};
+		// flat copies of the query parts and of the multi-word synonyms' terms (the arrays must outlive the call)
+		struct TermArrays {
+			std::vector<float> boosts, procs;
+			std::vector<uint8_t> needSum, suppressed;
+			std::vector<uint32_t> lists, synIds;
+		};
+		size_t nSynTerms = 0;
+		for (auto& syn : q.synonyms) {
+			nSynTerms += syn.NumTerms();
 		}
+		std::vector<TermArrays> arrays(q.queryParts.size() + nSynTerms);
+		size_t next = 0;
+		auto convert = [&](TermResults<IdCont>& tr) {
+			TermArrays& a = arrays[next++];
+			const FtDslOpts& o = tr.Opts();
+			a.boosts.resize(nfields_);
+			a.needSum.resize(nfields_);
+			for (uint32_t f = 0; f < nfields_; ++f) {
+				a.boosts[f] = o.fieldsOpts[f].boost;
+				a.needSum[f] = o.fieldsOpts[f].needSumRank ? 1 : 0;
+			}
+			bool anySuppressed = false;
+			for (const SubtermResults<IdCont>& st : tr) {
+				a.lists.push_back(postingsId(&st.Occurences()));
+				a.procs.push_back(st.Proc());
+				a.suppressed.push_back(st.Suppressed() ? 1 : 0);
+				anySuppressed |= st.Suppressed();
+			}
+			rxgpu_ft_term t{};
+			t.op = int32_t(o.op);
+			t.boost = o.boost;
+			t.term_len_boost = o.termLenBoost;
+			t.field_boosts = a.boosts.data();
+			t.nsubterms = uint32_t(a.lists.size());
+			t.postings = a.lists.data();
+			t.procs = a.procs.data();
+			t.need_sum_rank = a.needSum.data();
+			t.suppressed = anySuppressed ? a.suppressed.data() : nullptr;
+			return t;
+		};
+		std::vector<rxgpu_ft_term> terms;
+		terms.reserve(q.queryParts.size());
+		for (auto& qp : q.queryParts) {
+			TermArrays& a = arrays[next];
+			rxgpu_ft_term t = convert(qp.Term());
+			for (const size_t id : qp.SynonymsIds()) {
+				a.synIds.push_back(uint32_t(id));
+			}
+			t.nsynonyms = uint32_t(a.synIds.size());
+			t.synonym_ids = a.synIds.empty() ? nullptr : a.synIds.data();
+			terms.push_back(t);
+		}
+		std::vector<std::vector<rxgpu_ft_term>> synTerms(q.synonyms.size());
+		std::vector<rxgpu_ft_synonym> syns(q.synonyms.size());
+		for (size_t y = 0; y < q.synonyms.size(); ++y) {
+			for (auto& tr : q.synonyms[y].Terms()) {
+				synTerms[y].push_back(convert(tr));
+			}
+			syns[y] = rxgpu_ft_synonym{uint32_t(synTerms[y].size()), synTerms[y].data()};
+		}
+		const rxgpu_ft_query query{uint32_t(terms.size()), terms.data(), uint32_t(syns.size()), syns.empty() ? nullptr : syns.data()};
 		std::vector<uint8_t> excluded(totalDocs_);
 		bool anyExcluded = false;
 		for (uint32_t d = 0; d < totalDocs_ && d < docsExcluded.size(); ++d) {
@@ -131,8 +168,7 @@ public:
 		const uint64_t maxOut = std::min<uint64_t>(cfg.mergeLimit, q.totalORVids) + 1;
 		std::vector<rxgpu_ft_merge_info> res(maxOut);
 		uint64_t n = 0;
-		check(rxgpu_ft_merge(h_, &c, uint32_t(nterms), terms.data(), anyExcluded ? excluded.data() : nullptr, int(rankSortType), maxOut, res.data(),
-							 &n));
+		check(rxgpu_ft_merge_query(h_, &c, &query, anyExcluded ? excluded.data() : nullptr, int(rankSortType), maxOut, res.data(), &n));
 		out.reserve(n);
 		for (uint64_t i = 0; i < n && i < maxOut; ++i) {
 			MergeInfo mi;

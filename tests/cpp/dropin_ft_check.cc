@@ -3,6 +3,7 @@
 // ft::QueryMergeData built from the reference's own containers (IdRelVec and PackedIdRelVec), exactly as Selector::Process /
 // mergeResults would (cpp_src/core/ft/ft_fast/selecterimpl.h:609-645) -- then diffs ft::MergeData entry by entry (ids, order, uint8
 // ranks, field).  Built by tests/cpp/Makefile only where /root/reference exists; the binary travels to the GPU box.
+#include <algorithm>
 #include <cstdio>
 #include <random>
 #include <vector>
@@ -32,8 +33,10 @@ struct Problem {
 		std::vector<float> fieldBoosts;
 		std::vector<bool> needSum;
 		std::vector<std::pair<size_t, float>> subterms;  // (list, proc)
+		std::vector<size_t> synonymIds;
 	};
 	std::vector<Term> terms;
+	std::vector<std::vector<Term>> synonyms;  // multi-word synonyms (ft::Synonym)
 	reindexer::FTConfig cfg;
 	std::vector<uint8_t> excluded;
 	explicit Problem(uint32_t nf) : cfg(nf) {}
@@ -97,6 +100,42 @@ Problem makeProblem(uint32_t seed, uint32_t totalDocs, uint32_t nfields, uint32_
 		}
 		p.terms.emplace_back(std::move(term));
 	}
+	// multi-word synonyms on every other problem: 2-3 terms each, attached to one or two non-NOT query parts; one of their subterms may
+	// repeat a word (= posting list) of the query, which QueryMergeData::SupressDuplicatesInSynonyms then suppresses
+	for (uint32_t y = 0; y < (seed % 2 ? 1 + seed % 3 % 2 : 0); ++y) {
+		std::vector<Problem::Term> syn;
+		const uint32_t nst = uni(2, 3);
+		for (uint32_t t = 0; t < nst; ++t) {
+			Problem::Term term;
+			term.op = OpOr;
+			term.boost = 1.f;
+			term.termLenBoost = 1.f;
+			term.fieldBoosts.assign(nfields, 1.f);
+			term.needSum.assign(nfields, false);
+			std::vector<reindexer::IdRelType> list;
+			const uint32_t step = uni(2, 5);
+			for (uint32_t d = 1 + rng() % step; d < totalDocs; d += 1 + rng() % step) {
+				reindexer::IdRelType r(d);
+				const uint32_t f = rng() % nfields;
+				r.Add(rng() % std::max<uint32_t>(1, p.stats.words[size_t(d) * nfields + f]), f, 0);
+				list.emplace_back(std::move(r));
+			}
+			p.lists.emplace_back(std::move(list));
+			term.subterms.emplace_back(p.lists.size() - 1, 45.f - 5.f * float(t));
+			if (rng() % 3 == 0) {
+				term.subterms.emplace_back(p.terms[rng() % p.terms.size()].subterms[0].first, 20.f);
+			}
+			syn.emplace_back(std::move(term));
+		}
+		p.synonyms.emplace_back(std::move(syn));
+		for (uint32_t n = 0, tries = 0; n < 1 + rng() % 2 && tries < 8; ++tries) {
+			auto& host = p.terms[rng() % p.terms.size()];
+			if (host.op != OpNot && std::find(host.synonymIds.begin(), host.synonymIds.end(), p.synonyms.size() - 1) == host.synonymIds.end()) {
+				host.synonymIds.push_back(p.synonyms.size() - 1);
+				++n;
+			}
+		}
+	}
 	return p;
 }
 
@@ -117,7 +156,7 @@ void buildCont(const std::vector<reindexer::IdRelType>& src, reindexer::PackedId
 template <typename IdCont>
 reindexer::ft::QueryMergeData<IdCont> buildQuery(const Problem& p, const std::vector<IdCont>& conts) {
 	reindexer::ft::QueryMergeData<IdCont> q;
-	for (const auto& t : p.terms) {
+	auto makeTerm = [&](const Problem::Term& t) {
 		reindexer::FtDSLEntry e;
 		e.Opts().op = t.op;
 		e.Opts().boost = t.boost;
@@ -129,11 +168,27 @@ reindexer::ft::QueryMergeData<IdCont> buildQuery(const Problem& p, const std::ve
 		}
 		reindexer::ft::TermResults<IdCont> tr(std::move(e));
 		for (const auto& [li, proc] : t.subterms) {
-			tr.AddSubterm(conts[li], "w", reindexer::WordIdType{}, proc);
+			reindexer::WordIdType wid;
+			wid.SetID(int32_t(li));  // one word per posting list
+			tr.AddSubterm(conts[li], "w", wid, proc);
 		}
 		q.totalORVids += tr.MaxVDocs();
-		q.queryParts.emplace_back(std::move(tr));
+		return tr;
+	};
+	for (const auto& syn : p.synonyms) {
+		reindexer::ft::Synonym<IdCont> s;
+		for (const auto& t : syn) {
+			s.AddTerm(makeTerm(t));
+		}
+		q.synonyms.emplace_back(std::move(s));
 	}
+	for (const auto& t : p.terms) {
+		q.queryParts.emplace_back(makeTerm(t));
+		for (const size_t id : t.synonymIds) {
+			q.queryParts.back().AddSynonymId(id);
+		}
+	}
+	q.SupressDuplicatesInSynonyms();  // selecterimpl.h:606
 	return q;
 }
 
@@ -208,7 +263,7 @@ int main() {
 		bad += !a + !b;
 		cases += 2;
 	}
-	std::printf("ft merge adapter: %d cases (IdRelVec and PackedIdRelVec, AND/OR/NOT, preselect cut, all bm25 variants, summation of field ranks): "
+	std::printf("ft merge adapter: %d cases (IdRelVec and PackedIdRelVec, AND/OR/NOT, preselect cut, all bm25 variants, summation of field ranks, multi-word synonyms with suppressed subterms): "
 				"%s\n",
 				cases, bad ? "MISMATCH" : "MATCH MATCH MATCH MATCH");
 	return bad;

@@ -42,6 +42,35 @@ def random_problem(seed, total_docs=400, nfields=1, nterms=3, max_sub=3, density
     return p
 
 
+def add_random_synonyms(p, seed, nsyn=2, density=0.25, suppress=True):
+    """Multi-word synonyms on top of random_problem: every synonym has 2-3 terms of 1-2 subterms each, is attached to one or two
+    OR / AND query parts (PhraseOrTerm::AddSynonymId), and may carry a suppressed subterm that re-uses a posting list of the query
+    (what QueryMergeData::SupressDuplicatesInSynonyms marks)."""
+    rng = np.random.default_rng(seed ^ 0x5A17)
+    total_docs, nfields = p.total_docs, p.nfields
+    hosts = [i for i, t in enumerate(p.terms) if t["op"] != F.OP_NOT]
+    for y in range(nsyn):
+        terms = []
+        for _ in range(int(rng.integers(2, 4))):
+            subs = []
+            procs = rng.choice([60.0, 52.0, 45.0, 38.0, 33.0], size=2, replace=False)
+            for s_ in range(int(rng.integers(1, 3))):
+                ndocs = max(1, int(density * float(rng.uniform(0.4, 1.4)) * (total_docs - 1)))
+                docs = np.sort(rng.choice(np.arange(1, total_docs), size=min(ndocs, total_docs - 1), replace=False))
+                pos_lists = [[(int(rng.integers(0, max(int(p.words[d, f]), 1))), f) for f in [int(rng.integers(0, nfields))]
+                              for _ in range(int(rng.integers(1, 3)))] for d in docs]
+                subs.append((p.add_list(docs, pos_lists), float(procs[s_])))
+            if suppress and rng.random() < 0.4:  # a word of the query repeated inside the synonym
+                host = p.terms[int(rng.choice(hosts))]
+                subs.append((int(host["postings"][0]), 29.0, True))
+            terms.append(dict(subterms=subs, op=F.OP_OR, boost=float(rng.choice([1.0, 0.8])), term_len_boost=1.0,
+                              field_boosts=np.ones(nfields, np.float32)))
+        sid = p.add_synonym(terms)
+        for h in rng.choice(hosts, size=min(len(hosts), int(rng.integers(1, 3))), replace=False):
+            p.terms[int(h)]["synonym_ids"] = np.append(p.terms[int(h)]["synonym_ids"], np.uint32(sid)).astype(np.uint32)
+    return p
+
+
 def assert_same_merge(a, b, rank_sort_type, ctx=""):
     """a, b: MERGE_INFO arrays.  RankAndID / IDOnly keep the merge order (deterministic); RankOnly / IDAndPositions are sorted by an
     unstable sort, so equal ranks compare as sets."""
@@ -83,7 +112,8 @@ def gpu_merge(prob, rank_sort_type=F.RANK_AND_ID, packed=None):
     else:
         ids = [ft.add_postings(d, b, p) for d, b, p in prob.lists]
     terms = [dict(t, postings=[ids[int(x)] for x in t["postings"]]) for t in prob.terms]
-    res = ft.merge(prob.cfg, prob.field_cfg, terms, excluded=prob.excluded, rank_sort_type=rank_sort_type)
+    syns = [[dict(t, postings=[ids[int(x)] for x in t["postings"]]) for t in syn] for syn in prob.synonyms]
+    res = ft.merge(prob.cfg, prob.field_cfg, terms, excluded=prob.excluded, rank_sort_type=rank_sort_type, synonyms=syns or None)
     st = ft.last_stats()
     ft.close()
     return res, st

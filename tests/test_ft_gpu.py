@@ -5,7 +5,7 @@ import os
 
 import numpy as np
 import pytest
-from ft_helpers import assert_same_merge, gpu_merge, load_golden_problem, random_problem
+from ft_helpers import add_random_synonyms, assert_same_merge, gpu_merge, load_golden_problem, random_problem
 
 from oracle import ft_oracle as F
 
@@ -76,6 +76,28 @@ def test_summation_of_ranks_by_fields():
         p.cfg["summation_ranks_by_fields_ratio"] = 0.0
         hit += int(len(a) != len(F.best_merge(p)[0]) or (a["normalized_proc"] != F.best_merge(p)[0]["normalized_proc"][:len(a)]).any())
     assert hit > 5  # the knob changes results
+
+
+@pytest.mark.skipif(not F.ref_available(), reason="oracle/_ref not built (the C port does not restate synonyms)")
+def test_multi_word_synonyms_match_reference():
+    """Merger::Merge with QueryMergeData::synonyms (mergerimpl.h:510-560, restricting mask :352-363, preselect :392-396): documents
+    reached only through a synonym stay iff they hold all of its terms; suppressed subterms only count."""
+    kept_by_syn = preselects = 0
+    for seed in range(60):
+        rng = np.random.default_rng(7000 + seed)
+        kw = dict(total_docs=int(rng.integers(60, 2500)), nfields=1 + seed % 3, nterms=1 + seed % 3, removed_frac=0.05 * (seed % 2),
+                  excluded_frac=0.05 * (seed % 3 == 0))
+        if seed % 4 == 1:
+            kw["merge_limit"] = int(rng.integers(10, 80))
+        p = add_random_synonyms(random_problem(7000 + seed, **kw), seed, nsyn=1 + seed % 2)
+        plain = random_problem(7000 + seed, **kw)
+        for rst in (F.RANK_AND_ID, F.RANK_ONLY):
+            a, _ = F.ref_merge(p, rst)
+            b, st = gpu_merge(p, rst)
+            preselects += st["preselected"]
+            assert_same_merge(a, b, rst, ctx=f"seed {seed} rst {rst}")
+        kept_by_syn += len(set(a["id"].tolist()) - set(F.ref_merge(plain)[0]["id"].tolist())) > 0
+    assert kept_by_syn > 10 and preselects > 3
 
 
 def test_empty_and_degenerate_queries():
