@@ -285,6 +285,18 @@ int rxgpu_ivf_search_knn(const rxgpu_index*, uint32_t nq, const float* queries /
 int rxgpu_ivf_search_range(const rxgpu_index*, const float* query /* host */, float radius, uint32_t nprobe, uint64_t max_out,
 						   float* out_dist, uint64_t* out_label, uint64_t* out_n);
 
+/* Mutable lists -- what IvfIndex::upsert / del do once the index is trained (ivf_index.cc:87-132: map_->add_with_ids(1, vec, &id),
+ * map_->remove_ids(IDSelectorArray{1, &id})): rxgpu_ivf_create attaches EMPTY lists to an empty index (the rows then live in the lists:
+ * every list owns a region of one row slab with slack, a full list moves to the end of the slab with 1.5x room, dead space is
+ * compacted when it exceeds the live rows); rxgpu_ivf_add appends rows to the lists the caller's coarse quantiser chose
+ * (list_nos[i] = faiss' lo_listno of the id after the CPU add, so both sides agree on the assignment bit for bit); rxgpu_ivf_remove is
+ * the inverted lists' swap-remove.  An upsert costs one row copy, never a re-import.  Searches see every completed call. */
+int rxgpu_ivf_create(rxgpu_index*, uint32_t nlist, const float* centroids /* nlist x dim, host */);
+int rxgpu_ivf_add(rxgpu_index*, uint64_t n, const uint32_t* list_nos, const uint64_t* labels, const float* vecs /* n x dim, host */);
+int rxgpu_ivf_remove(rxgpu_index*, uint64_t label); /* errNotFound when the id is in no list */
+uint64_t rxgpu_ivf_size(const rxgpu_index*);
+int rxgpu_ivf_list_stats(const rxgpu_index*, uint64_t* slab_rows, uint64_t* dead_rows, uint64_t* relocations, uint64_t* compactions);
+
 /* ---------------------------------------------------------------- ft_fast full-text merge (BM25 scoring over posting lists)
  * Replaces ft::Merger<IdCont, ft::MergeData, OffsetT>::Merge<Bm25Rx|Bm25Classic|TermCount>  core/ft/ft_fast/mergerimpl.h:466-566
  * -- the seam is Selector<IdCont>::mergeResults (ft_fast/selecterimpl.h:609-627) -- for query parts that are plain terms

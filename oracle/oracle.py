@@ -544,6 +544,27 @@ class RefIvf:
         rc = self.lib.ref_ivf_train_add(self.h, len(ids), _p(vecs, _f32p), _p(ids, _i64p))
         assert rc == 0, self.lib.ref_ivf_last_error().decode()
 
+    def add(self, labels, vecs):
+        """IvfIndex::upsert on the trained index, one add_with_ids per row"""
+        vecs = np.ascontiguousarray(vecs, np.float32)
+        ids = np.ascontiguousarray(labels).astype(np.int64)
+        self.lib.ref_ivf_add.restype = C.c_int
+        self.lib.ref_ivf_add.argtypes = [C.c_void_p, C.c_size_t, _f32p, _i64p]
+        assert self.lib.ref_ivf_add(self.h, len(ids), _p(vecs, _f32p), _p(ids, _i64p)) == 0, self.lib.ref_ivf_last_error().decode()
+
+    def remove(self, label):
+        self.lib.ref_ivf_remove.restype = C.c_int
+        self.lib.ref_ivf_remove.argtypes = [C.c_void_p, C.c_int64]
+        assert self.lib.ref_ivf_remove(self.h, int(label)) == 0, self.lib.ref_ivf_last_error().decode()
+
+    def list_of(self, labels):
+        ids = np.ascontiguousarray(labels).astype(np.int64)
+        out = np.zeros(len(ids), np.uint32)
+        self.lib.ref_ivf_list_of.restype = C.c_int
+        self.lib.ref_ivf_list_of.argtypes = [C.c_void_p, C.c_size_t, _i64p, _u32p]
+        assert self.lib.ref_ivf_list_of(self.h, len(ids), _p(ids, _i64p), _p(out, _u32p)) == 0, self.lib.ref_ivf_last_error().decode()
+        return out
+
     def search(self, q, k, nprobe):
         """returns (dist, label) best first; dist in FAISS' convention (L2: squared distance, IP: +inner product)"""
         q = np.ascontiguousarray(q, np.float32)

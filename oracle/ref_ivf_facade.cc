@@ -92,6 +92,43 @@ int ref_ivf_train_add(void* hv, size_t n, const float* vecs, const int64_t* ids)
 	});
 }
 
+// IvfIndex::upsert on a trained index: map_->add_with_ids(1, vect, &id) (ivf_index.cc:87-91); Cosine norms like train_add
+int ref_ivf_add(void* hv, size_t n, const float* vecs, const int64_t* ids) {
+	auto* h = static_cast<IvfHandle*>(hv);
+	return guarded([&] {
+		for (size_t i = 0; i < n; ++i) {
+			const faiss::idx_t id = ids[i];
+			if (h->metric == 2) {
+				const float norm = reindexer::ann::CalculateL2Module(vecs + i * h->dim, int32_t(h->dim));
+				h->map->add_with_ids(1, vecs + i * h->dim, &norm, &id);
+			} else {
+				h->map->add_with_ids(1, vecs + i * h->dim, &id);
+			}
+		}
+	});
+}
+// IvfIndex::del: map_->remove_ids(IDSelectorArray{1, &id}) (ivf_index.cc:120-124)
+int ref_ivf_remove(void* hv, int64_t id) {
+	auto* h = static_cast<IvfHandle*>(hv);
+	return guarded([&] {
+		const faiss::idx_t fid = id;
+		h->map->remove_ids(faiss::IDSelectorArray{1, &fid});
+	});
+}
+// the list every id lives in, from the direct map (the coarse quantiser's assignment at add time)
+int ref_ivf_list_of(const void* hv, size_t n, const int64_t* ids, uint32_t* list_nos) {
+	auto* h = static_cast<const IvfHandle*>(hv);
+	return guarded([&] {
+		for (size_t i = 0; i < n; ++i) {
+			const auto it = h->map->direct_map.hashtable.find(ids[i]);
+			if (it == h->map->direct_map.hashtable.end()) {
+				throw std::runtime_error("ref_ivf_list_of: unknown id");
+			}
+			list_nos[i] = uint32_t(faiss::lo_listno(it->second));
+		}
+	});
+}
+
 // returns the number of results (ids >= 0), best first as FAISS returns them; distances in FAISS' convention (L2: squared distance
 // ascending, IP: inner product descending)
 int64_t ref_ivf_search(const void* hv, const float* query, size_t k, size_t nprobe, float* dists, int64_t* ids) {

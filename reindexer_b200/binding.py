@@ -146,6 +146,11 @@ _SIGNATURES = {
     "rxgpu_hnsw_search_range": (C.c_int, [C.c_void_p, _f32p, C.c_float, C.c_uint32, C.c_uint64, _f32p, _u64p, C.POINTER(C.c_uint64)]),
     "rxgpu_hnsw_search_knn_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rxgpu_ivf_create": (C.c_int, [C.c_void_p, C.c_uint32, _f32p]),
+    "rxgpu_ivf_add": (C.c_int, [C.c_void_p, C.c_uint64, _u32p, _u64p, _f32p]),
+    "rxgpu_ivf_remove": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "rxgpu_ivf_size": (C.c_uint64, [C.c_void_p]),
+    "rxgpu_ivf_list_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "rxgpu_hnsw_update": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "rxgpu_hnsw_update_count": (C.c_uint64, [C.c_void_p]),
     "rxgpu_hnsw_stream_begin": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, C.POINTER(C.c_void_p)]),
@@ -349,6 +354,28 @@ class GpuBruteforceSearch:
                                                _p(st, _u32p)))
         return (d, l, c, st) if with_stats else (d, l, c)
 
+    def ivf_create(self, centroids):
+        c = np.ascontiguousarray(centroids, np.float32).reshape(-1, self.dim)
+        _check(self._lib.rxgpu_ivf_create(self._h, len(c), _p(c, _f32p)))
+
+    def ivf_add(self, list_nos, labels, vecs):
+        ln = np.ascontiguousarray(list_nos, np.uint32)
+        lb = np.ascontiguousarray(labels, np.uint64)
+        v = np.ascontiguousarray(vecs, np.float32).reshape(-1, self.dim)
+        assert len(ln) == len(lb) == len(v)
+        _check(self._lib.rxgpu_ivf_add(self._h, len(ln), _p(ln, _u32p), _p(lb, _u64p), _p(v, _f32p)))
+
+    def ivf_remove(self, label: int):
+        _check(self._lib.rxgpu_ivf_remove(self._h, int(label)))
+
+    def ivf_size(self) -> int:
+        return int(self._lib.rxgpu_ivf_size(self._h))
+
+    def ivf_list_stats(self) -> dict:
+        v = [C.c_uint64(0) for _ in range(4)]
+        _check(self._lib.rxgpu_ivf_list_stats(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("slab_rows", "dead_rows", "relocations", "compactions"), (x.value for x in v)))
+
     def hnsw_update(self, graph: dict, nodes, new_rows=None, deleted=()):
         """Patch the imported graph in place (rxgpu_hnsw_update): `nodes` = internal ids whose lists changed, taken from `graph`
         (same layout as hnsw_import); `new_rows` = {internal id: (label, vector)} for inserted / replaced rows."""
@@ -482,7 +509,7 @@ class GpuBruteforceSearch:
 
     def ivf_search_range(self, query, radius: float, nprobe: int, max_out: int | None = None):
         q = np.ascontiguousarray(query, dtype=np.float32)
-        max_out = self.size() if max_out is None else max_out
+        max_out = max(self.size(), self.ivf_size()) if max_out is None else max_out
         d = np.zeros(max(max_out, 1), np.float32)
         l = np.zeros(max(max_out, 1), np.uint64)
         n = C.c_uint64(0)

@@ -13,6 +13,7 @@
 #include <new>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/rxgpu.h"
@@ -1545,6 +1546,25 @@ struct rxgpu_ivf_device {
 	DevBuf<uint32_t> d_idx, d_count;
 	DevBuf<uint64_t> d_range;
 	DevBuf<unsigned long long> d_range_count;
+	// mutable lists (rxgpu_ivf_create / _add / _remove): every list owns a region [begin, begin + cap) of a row slab; size <= cap
+	bool own = false;
+	float* rows = nullptr;       // [slab_rows][pitch]
+	uint64_t* labels = nullptr;  // [slab_rows]
+	float* norms = nullptr;      // [slab_rows] (Cosine)
+	uint64_t slab_rows = 0, high_water = 0, live = 0, dead = 0;
+	std::vector<uint32_t> begin, size, cap;
+	DevBuf<uint32_t> list_end;   // begin + size (list_begin holds begin)
+	std::vector<uint64_t> h_slab_labels;                                   // host mirror of `labels`
+	std::unordered_map<uint64_t, std::pair<uint32_t, uint32_t>> where;     // id -> (list, offset), faiss::DirectMap::Hashtable
+	DevBuf<float> st_rows;
+	DevBuf<uint32_t> st_dst;
+	DevBuf<uint64_t> st_labels;
+	uint64_t relocations = 0, compactions = 0;
+	~rxgpu_ivf_device() {
+		cudaFree(rows);
+		cudaFree(labels);
+		cudaFree(norms);
+	}
 };
 namespace rxgpu {
 void ivfRelease(rxgpu_ivf_device* p) { delete p; }
@@ -1645,17 +1665,17 @@ int rxgpu_ivf_search_knn(const rxgpu_index* ix, uint32_t nq, const float* querie
 	if (ix->metric == RXGPU_L2) {
 		RX_CUDA(raiseSmemCeilingOnce(ivf_coarse_kernel<true>, ix->device, 200 * 1024));
 		ivf_coarse_kernel<true><<<nq, kScanThreads, coarseSmem, st>>>(h->centroids.p, ix->pitch, ix->dim, h->nlist, h->d_q.p, nq, nprobe,
-																	   h->list_begin.p, nullptr, h->d_work.p);
+																	   h->list_begin.p, h->own ? h->list_end.p : nullptr, nullptr, h->d_work.p);
 	} else {
 		RX_CUDA(raiseSmemCeilingOnce(ivf_coarse_kernel<false>, ix->device, 200 * 1024));
 		ivf_coarse_kernel<false><<<nq, kScanThreads, coarseSmem, st>>>(h->centroids.p, ix->pitch, ix->dim, h->nlist, h->d_q.p, nq, nprobe,
-																		h->list_begin.p, ix->metric == RXGPU_COS ? h->cnorm.p : nullptr, h->d_work.p);
+																		h->list_begin.p, h->own ? h->list_end.p : nullptr, ix->metric == RXGPU_COS ? h->cnorm.p : nullptr, h->d_work.p);
 	}
 	RX_CUDA(cudaGetLastError());
 	// list scans: the exact scan kernel in work-item mode, one CTA per (query, probed list), fused top-k per CTA
 	ScanArgs a{};
-	a.rows = ix->d_rows;
-	a.norm_coefs = ix->metric == RXGPU_COS ? ix->d_norms : nullptr;
+	a.rows = h->own ? h->rows : ix->d_rows;
+	a.norm_coefs = ix->metric != RXGPU_COS ? nullptr : h->own ? h->norms : ix->d_norms;
 	a.queries = h->d_q.p;
 	a.pitch = ix->pitch;
 	a.dim = ix->dim;
@@ -1672,7 +1692,7 @@ int rxgpu_ivf_search_knn(const rxgpu_index* ix, uint32_t nq, const float* querie
 	RX_CUDA(launchScan(ix, 1, a, &grid, st));
 	MergeArgs m{};
 	m.lists = h->d_lists.p;
-	m.labels = ix->d_labels;
+	m.labels = h->own ? h->labels : ix->d_labels;
 	m.out_dist = h->d_dist.p;
 	m.out_idx = h->d_idx.p;
 	m.out_label = h->d_label.p;
@@ -1748,12 +1768,12 @@ int rxgpu_ivf_search_range(const rxgpu_index* ix, const float* query, float radi
 	if (ix->metric == RXGPU_L2) {
 		RX_CUDA(raiseSmemCeilingOnce(ivf_coarse_kernel<true>, ix->device, 200 * 1024));
 		ivf_coarse_kernel<true><<<1, kScanThreads, coarseSmem, st>>>(h->centroids.p, ix->pitch, ix->dim, h->nlist, h->d_q.p, 1, nprobe,
-																	  h->list_begin.p, nullptr, h->d_work.p);
+																	  h->list_begin.p, h->own ? h->list_end.p : nullptr, nullptr, h->d_work.p);
 	} else {
 		RX_CUDA(raiseSmemCeilingOnce(ivf_coarse_kernel<false>, ix->device, 200 * 1024));
 		ivf_coarse_kernel<false><<<1, kScanThreads, coarseSmem, st>>>(h->centroids.p, ix->pitch, ix->dim, h->nlist, h->d_q.p, 1, nprobe,
-																	   h->list_begin.p, ix->metric == RXGPU_COS ? h->cnorm.p : nullptr,
-																	   h->d_work.p);
+																	   h->list_begin.p, h->own ? h->list_end.p : nullptr,
+																	   ix->metric == RXGPU_COS ? h->cnorm.p : nullptr, h->d_work.p);
 	}
 	RX_CUDA(cudaGetLastError());
 	g_stats.launches = 1;
@@ -1763,8 +1783,8 @@ int rxgpu_ivf_search_range(const rxgpu_index* ix, const float* query, float radi
 		RX_CUDA(h->d_range.ensure(cap));
 		RX_CUDA(cudaMemsetAsync(h->d_range_count.p, 0, sizeof(unsigned long long), st));
 		ScanArgs a{};
-		a.rows = ix->d_rows;
-		a.norm_coefs = ix->metric == RXGPU_COS ? ix->d_norms : nullptr;
+		a.rows = h->own ? h->rows : ix->d_rows;
+		a.norm_coefs = ix->metric != RXGPU_COS ? nullptr : h->own ? h->norms : ix->d_norms;
 		a.queries = h->d_q.p;
 		a.pitch = ix->pitch;
 		a.dim = ix->dim;
@@ -1796,7 +1816,7 @@ int rxgpu_ivf_search_range(const rxgpu_index* ix, const float* query, float radi
 		std::vector<Hit> res(total);
 		for (unsigned long long i = 0; i < total; ++i) {
 			const uint32_t row = uint32_t(keys[i]);
-			res[i] = Hit{ord_float(uint32_t(keys[i] >> 32)), row, ix->h_labels[row]};
+			res[i] = Hit{ord_float(uint32_t(keys[i] >> 32)), row, h->own ? h->h_slab_labels[row] : ix->h_labels[row]};
 		}
 		std::sort(res.begin(), res.end(), hitLessByLabel);  // IvfIndex sorts the range result by distance (ivf_index.cc:220-224); ties by label here
 		const uint64_t nout = std::min<uint64_t>(total, max_out);
@@ -1807,6 +1827,299 @@ int rxgpu_ivf_search_range(const rxgpu_index* ix, const float* query, float radi
 	} catch (const std::bad_alloc&) {
 		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
 	}
+	return 0;
+}
+
+}  // extern "C"
+
+// ---- mutable IVF lists -----------------------------------------------------------------------------------------------------------
+namespace {
+// grows the slab to at least `want` rows, keeping its contents
+int ivfGrowSlab(rxgpu_index* ix, rxgpu_ivf_device* h, uint64_t want) {
+	if (want <= h->slab_rows) {
+		return 0;
+	}
+	if (want > 0xFFFFFFF0ull) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: IVF row slab exceeds 2^32 rows");
+	}
+	const uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(want, h->slab_rows + h->slab_rows / 2), 0xFFFFFFF0ull);
+	float* rows = nullptr;
+	uint64_t* labels = nullptr;
+	float* norms = nullptr;
+	RX_CUDA(cudaMalloc(reinterpret_cast<void**>(&rows), cap * ix->pitch * sizeof(float)));
+	cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&labels), cap * sizeof(uint64_t));
+	if (e == cudaSuccess && ix->metric == RXGPU_COS) {
+		e = cudaMalloc(reinterpret_cast<void**>(&norms), cap * sizeof(float));
+	}
+	if (e != cudaSuccess) {
+		cudaFree(rows);
+		cudaFree(labels);
+		return fail(RXGPU_ERR_SYSTEM, std::string("CUDA error: ") + cudaGetErrorString(e) + " at cudaMalloc (IVF slab)");
+	}
+	cudaStream_t st = ix->stream;
+	if (h->high_water) {
+		cudaMemcpyAsync(rows, h->rows, h->high_water * ix->pitch * sizeof(float), cudaMemcpyDeviceToDevice, st);
+		cudaMemcpyAsync(labels, h->labels, h->high_water * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st);
+		if (norms) {
+			cudaMemcpyAsync(norms, h->norms, h->high_water * sizeof(float), cudaMemcpyDeviceToDevice, st);
+		}
+	}
+	e = cudaStreamSynchronize(st);
+	if (e != cudaSuccess) {
+		cudaFree(rows);
+		cudaFree(labels);
+		cudaFree(norms);
+		return fail(RXGPU_ERR_SYSTEM, std::string("CUDA error: ") + cudaGetErrorString(e) + " at the IVF slab copy");
+	}
+	cudaFree(h->rows);
+	cudaFree(h->labels);
+	cudaFree(h->norms);
+	h->rows = rows;
+	h->labels = labels;
+	h->norms = norms;
+	h->slab_rows = cap;
+	h->h_slab_labels.resize(cap);
+	return 0;
+}
+// moves list l to the end of the slab with room for `need` rows (amortised x1.5 growth); the old region becomes dead space
+int ivfRelocate(rxgpu_index* ix, rxgpu_ivf_device* h, uint32_t l, uint32_t need) {
+	const uint32_t newCap = std::max<uint32_t>(32u, (need + need / 2 + 31u) & ~31u);
+	if (int rc = ivfGrowSlab(ix, h, h->high_water + newCap)) {
+		return rc;
+	}
+	cudaStream_t st = ix->stream;
+	const uint64_t src = h->begin[l], dst = h->high_water, n = h->size[l];
+	if (n) {
+		RX_CUDA(cudaMemcpyAsync(h->rows + dst * ix->pitch, h->rows + src * ix->pitch, n * ix->pitch * sizeof(float), cudaMemcpyDeviceToDevice, st));
+		RX_CUDA(cudaMemcpyAsync(h->labels + dst, h->labels + src, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+		if (h->norms) {
+			RX_CUDA(cudaMemcpyAsync(h->norms + dst, h->norms + src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+		}
+		std::copy(h->h_slab_labels.begin() + src, h->h_slab_labels.begin() + src + n, h->h_slab_labels.begin() + dst);
+	}
+	h->dead += h->cap[l];
+	h->begin[l] = uint32_t(dst);
+	h->cap[l] = newCap;
+	h->high_water += newCap;
+	h->relocations++;
+	return 0;
+}
+// rewrites the slab without the dead regions (every list keeps 25 % slack)
+int ivfCompact(rxgpu_index* ix, rxgpu_ivf_device* h) {
+	uint64_t total = 0;
+	std::vector<uint32_t> newCap(h->nlist);
+	for (uint32_t l = 0; l < h->nlist; ++l) {
+		newCap[l] = std::max<uint32_t>(32u, (h->size[l] + h->size[l] / 4 + 31u) & ~31u);
+		total += newCap[l];
+	}
+	float* rows = nullptr;
+	uint64_t* labels = nullptr;
+	float* norms = nullptr;
+	RX_CUDA(cudaMalloc(reinterpret_cast<void**>(&rows), total * ix->pitch * sizeof(float)));
+	cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&labels), total * sizeof(uint64_t));
+	if (e == cudaSuccess && ix->metric == RXGPU_COS) {
+		e = cudaMalloc(reinterpret_cast<void**>(&norms), total * sizeof(float));
+	}
+	if (e != cudaSuccess) {
+		cudaFree(rows);
+		cudaFree(labels);
+		return fail(RXGPU_ERR_SYSTEM, std::string("CUDA error: ") + cudaGetErrorString(e) + " at cudaMalloc (IVF slab)");
+	}
+	cudaStream_t st = ix->stream;
+	std::vector<uint64_t> hl(total);
+	uint64_t at = 0;
+	for (uint32_t l = 0; l < h->nlist; ++l) {
+		const uint64_t src = h->begin[l], n = h->size[l];
+		if (n) {
+			cudaMemcpyAsync(rows + at * ix->pitch, h->rows + src * ix->pitch, n * ix->pitch * sizeof(float), cudaMemcpyDeviceToDevice, st);
+			cudaMemcpyAsync(labels + at, h->labels + src, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st);
+			if (norms) {
+				cudaMemcpyAsync(norms + at, h->norms + src, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+			}
+			std::copy(h->h_slab_labels.begin() + src, h->h_slab_labels.begin() + src + n, hl.begin() + at);
+		}
+		h->begin[l] = uint32_t(at);
+		h->cap[l] = newCap[l];
+		at += newCap[l];
+	}
+	e = cudaStreamSynchronize(st);
+	if (e != cudaSuccess) {
+		cudaFree(rows);
+		cudaFree(labels);
+		cudaFree(norms);
+		return fail(RXGPU_ERR_SYSTEM, std::string("CUDA error: ") + cudaGetErrorString(e) + " at the IVF slab copy");
+	}
+	cudaFree(h->rows);
+	cudaFree(h->labels);
+	cudaFree(h->norms);
+	h->rows = rows;
+	h->labels = labels;
+	h->norms = norms;
+	h->slab_rows = total;
+	h->high_water = total;
+	h->dead = 0;
+	h->h_slab_labels.swap(hl);
+	h->compactions++;
+	return 0;
+}
+int ivfPushBounds(rxgpu_index* ix, rxgpu_ivf_device* h) {
+	std::vector<uint32_t> end(h->nlist);
+	for (uint32_t l = 0; l < h->nlist; ++l) {
+		end[l] = h->begin[l] + h->size[l];
+	}
+	RX_CUDA(cudaMemcpyAsync(h->list_begin.p, h->begin.data(), size_t(h->nlist) * 4, cudaMemcpyHostToDevice, ix->stream));
+	RX_CUDA(cudaMemcpyAsync(h->list_end.p, end.data(), size_t(h->nlist) * 4, cudaMemcpyHostToDevice, ix->stream));
+	RX_CUDA(cudaStreamSynchronize(ix->stream));
+	return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int rxgpu_ivf_create(rxgpu_index* ix, uint32_t nlist, const float* centroids) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	if (ix->size != 0) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: rxgpu_ivf_create needs an empty index (the rows live in the lists)");
+	}
+	const std::vector<uint64_t> zeros(nlist ? nlist : 1, 0);
+	if (int rc = rxgpu_ivf_import(ix, nlist, centroids, zeros.data())) {
+		return rc;
+	}
+	rxgpu_ivf_device* h = ix->ivf;
+	try {
+		h->own = true;
+		h->begin.assign(nlist, 0u);
+		h->size.assign(nlist, 0u);
+		h->cap.assign(nlist, 0u);
+		RX_CUDA(h->list_end.ensure(nlist));
+		return ivfPushBounds(ix, h);
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
+	}
+}
+
+int rxgpu_ivf_add(rxgpu_index* ix, uint64_t n, const uint32_t* list_nos, const uint64_t* labels, const float* vecs) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	rxgpu_ivf_device* h = ix->ivf;
+	if (!h || !h->own) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: rxgpu_ivf_add needs lists made by rxgpu_ivf_create");
+	}
+	if (n == 0) {
+		return 0;
+	}
+	if (!list_nos || !labels || !vecs) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	std::lock_guard<std::mutex> lck(h->mtx);
+	try {
+		std::unordered_set<uint64_t> seen;
+		std::vector<uint32_t> adds(h->nlist, 0u);
+		for (uint64_t i = 0; i < n; ++i) {
+			if (list_nos[i] >= h->nlist) {
+				return fail(RXGPU_ERR_PARAMS, "rxgpu: IVF list number out of range");
+			}
+			if (h->where.count(labels[i]) || !seen.insert(labels[i]).second) {
+				return fail(RXGPU_ERR_LOGIC, "rxgpu: the id is already in the IVF lists");
+			}
+			adds[list_nos[i]]++;
+		}
+		if (h->dead > h->live + n + 4096) {  // more dead space than rows: rewrite the slab before growing it further
+			if (int rc = ivfCompact(ix, h)) {
+				return rc;
+			}
+		}
+		for (uint32_t l = 0; l < h->nlist; ++l) {
+			if (adds[l] && h->size[l] + adds[l] > h->cap[l]) {
+				if (int rc = ivfRelocate(ix, h, l, h->size[l] + adds[l])) {
+					return rc;
+				}
+			}
+		}
+		cudaStream_t st = ix->stream;
+		const uint64_t slice = std::max<uint64_t>(1, (uint64_t(64) << 20) / (size_t(ix->dim) * 4));
+		std::vector<uint32_t> dst;
+		for (uint64_t off = 0; off < n; off += slice) {
+			const uint64_t cnt = std::min(slice, n - off);
+			dst.resize(cnt);
+			for (uint64_t i = 0; i < cnt; ++i) {
+				const uint32_t l = list_nos[off + i];
+				const uint32_t row = h->begin[l] + h->size[l];
+				dst[i] = row;
+				h->where.emplace(labels[off + i], std::make_pair(l, h->size[l]));
+				h->h_slab_labels[row] = labels[off + i];
+				h->size[l]++;
+			}
+			RX_CUDA(h->st_rows.ensure(cnt * ix->dim));
+			RX_CUDA(h->st_dst.ensure(cnt));
+			RX_CUDA(h->st_labels.ensure(cnt));
+			RX_CUDA(cudaMemcpyAsync(h->st_rows.p, vecs + off * ix->dim, cnt * ix->dim * sizeof(float), cudaMemcpyHostToDevice, st));
+			RX_CUDA(cudaMemcpyAsync(h->st_dst.p, dst.data(), cnt * 4, cudaMemcpyHostToDevice, st));
+			RX_CUDA(cudaMemcpyAsync(h->st_labels.p, labels + off, cnt * 8, cudaMemcpyHostToDevice, st));
+			scatter_rows_kernel<<<unsigned(cnt), 128, 0, st>>>(h->st_rows.p, h->st_dst.p, h->st_labels.p, uint32_t(cnt), ix->dim, ix->pitch, h->rows,
+															   h->labels);
+			if (h->norms) {
+				norm_coef_at_kernel<<<unsigned((cnt * 32 + 255) / 256), 256, 0, st>>>(h->rows, ix->pitch, ix->dim, h->st_dst.p, uint32_t(cnt), h->norms);
+			}
+			RX_CUDA(cudaGetLastError());
+			RX_CUDA(cudaStreamSynchronize(st));  // `dst` is reused by the next slice
+		}
+		h->live += n;
+		return ivfPushBounds(ix, h);
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
+	}
+}
+
+int rxgpu_ivf_remove(rxgpu_index* ix, uint64_t label) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	rxgpu_ivf_device* h = ix->ivf;
+	if (!h || !h->own) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: rxgpu_ivf_remove needs lists made by rxgpu_ivf_create");
+	}
+	std::lock_guard<std::mutex> lck(h->mtx);
+	const auto it = h->where.find(label);
+	if (it == h->where.end()) {
+		return fail(RXGPU_ERR_NOT_FOUND, "rxgpu: the id is not in the IVF lists");
+	}
+	// InvertedLists swap-remove (faiss DirectMap::remove_ids, Hashtable flavour): the list's last entry fills the hole
+	const uint32_t l = it->second.first, pos = it->second.second, last = h->size[l] - 1;
+	const uint64_t at = uint64_t(h->begin[l]) + pos, from = uint64_t(h->begin[l]) + last;
+	cudaStream_t st = ix->stream;
+	if (pos != last) {
+		RX_CUDA(cudaMemcpyAsync(h->rows + at * ix->pitch, h->rows + from * ix->pitch, size_t(ix->pitch) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+		RX_CUDA(cudaMemcpyAsync(h->labels + at, h->labels + from, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+		if (h->norms) {
+			RX_CUDA(cudaMemcpyAsync(h->norms + at, h->norms + from, sizeof(float), cudaMemcpyDeviceToDevice, st));
+		}
+		const uint64_t moved = h->h_slab_labels[from];
+		h->h_slab_labels[at] = moved;
+		h->where[moved].second = pos;
+	}
+	h->where.erase(it);
+	h->size[l] = last;
+	h->live--;
+	const uint32_t end = h->begin[l] + last;
+	RX_CUDA(cudaMemcpyAsync(h->list_end.p + l, &end, 4, cudaMemcpyHostToDevice, st));
+	RX_CUDA(cudaStreamSynchronize(st));
+	return 0;
+}
+
+uint64_t rxgpu_ivf_size(const rxgpu_index* ix) { return ix && ix->ivf ? (ix->ivf->own ? ix->ivf->live : ix->size) : 0; }
+int rxgpu_ivf_list_stats(const rxgpu_index* ix, uint64_t* slab_rows, uint64_t* dead_rows, uint64_t* relocations, uint64_t* compactions) {
+	if (!ix || !ix->ivf) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: no IVF lists in this index");
+	}
+	const rxgpu_ivf_device* h = ix->ivf;
+	if (slab_rows) *slab_rows = h->slab_rows;
+	if (dead_rows) *dead_rows = h->dead;
+	if (relocations) *relocations = h->relocations;
+	if (compactions) *compactions = h->compactions;
 	return 0;
 }
 

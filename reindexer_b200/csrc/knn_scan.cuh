@@ -472,7 +472,7 @@ __device__ __forceinline__ float row_dist_warp(const float4* rows4, uint32_t pit
 // of the list scan, probe-major: work[p * nq + q] = (q, list_begin[c], list_begin[c + 1], c)
 template <bool kIsL2>
 __global__ void __launch_bounds__(kScanThreads) ivf_coarse_kernel(const float* centroids, uint32_t pitch, uint32_t dim, uint32_t nlist,
-																  const float* queries, uint32_t nq, uint32_t nprobe, const uint32_t* list_begin,
+																  const float* queries, uint32_t nq, uint32_t nprobe, const uint32_t* list_begin, const uint32_t* list_end,
 																  const float* centroid_norm_coefs, uint4* work) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	__shared__ uint64_t s_best[kScanWarps];
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(kScanThreads) ivf_coarse_kernel(const float* c
 			uint4 w = make_uint4(q, 0, 0, 0xFFFFFFFFu);  // fewer centroids than nprobe: an empty range
 			if (best != kKeyNone) {
 				const uint32_t c = uint32_t(best);
-				w = make_uint4(q, list_begin[c], list_begin[c + 1], c);
+				w = make_uint4(q, list_begin[c], list_end ? list_end[c] : list_begin[c + 1], c);
 			}
 			work[size_t(p) * nq + q] = w;
 		}
@@ -577,6 +577,32 @@ __global__ void synth_rows_kernel(float* rows, uint64_t* labels, uint32_t pitch,
 __global__ void synth_fill_kernel(float* out, uint64_t seed, uint64_t first_index, uint64_t count) {
 	for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < count; i += uint64_t(gridDim.x) * blockDim.x) {
 		out[i] = synth_value(seed, first_index + i);
+	}
+}
+
+// norm coefficients of scattered rows (one warp per entry of dst), same arithmetic as norm_coef_kernel
+__global__ void norm_coef_at_kernel(const float* rows, uint32_t pitch, uint32_t dim, const uint32_t* dst, uint32_t n, float* coefs) {
+	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) / 32;
+	const int lane = threadIdx.x & 31;
+	if (i >= n) {
+		return;
+	}
+	const uint32_t row = dst[i];
+	const float* p = rows + size_t(row) * pitch;
+	float s = 0.f;
+	for (uint32_t c = lane; c < dim; c += 32) {
+		s = fmaf(p[c], p[c], s);
+	}
+#pragma unroll
+	for (int off = 16; off > 0; off >>= 1) {
+		s += __shfl_xor_sync(0xffffffffu, s, off);
+	}
+	if (lane == 0) {
+		float k = 1.f;
+		if (s > 0.f && fabsf(1.0f - s) > 0.00001f) {
+			k = float(1.0 / double(__fsqrt_rn(s)));
+		}
+		coefs[row] = k;
 	}
 }
 

@@ -5,6 +5,9 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# The reference's vendored FAISS (oracle/_ref, tests/cpp/dropin_ivf_check) runs OpenMP teams of one thread per visible CPU; under a
+# cgroup quota (16 of 128 cores on the GPU boxes) the spinning teams starve each other.  Bound the checker's teams, not the product.
+os.environ.setdefault("OMP_NUM_THREADS", "8")
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 

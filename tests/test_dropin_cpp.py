@@ -8,6 +8,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "tests", "cpp", "_build", "dropin_check")
 BIN_HNSW = os.path.join(ROOT, "tests", "cpp", "_build", "dropin_hnsw_check")
+BIN_IVF = os.path.join(ROOT, "tests", "cpp", "_build", "dropin_ivf_check")
 BIN_FT = os.path.join(ROOT, "tests", "cpp", "_build", "dropin_ft_check")
 
 
@@ -47,3 +48,14 @@ def test_ft_merge_adapter_matches_reference_merger_on_gpu():
     out = subprocess.run([BIN_FT], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "MISMATCH" not in out.stdout and out.stdout.count("MATCH") >= 4
+
+
+@pytest.mark.gpu
+def test_ivf_adapter_matches_reference_faiss_on_gpu():
+    """reindexer_b200/host/gpu_ivf.h vs the reference's vendored faiss::IndexIVFFlat driven like IvfIndex (tests/cpp/dropin_ivf_check.cc):
+    knn + range searches between bursts of upserts and deletes, the device lists patched in place (one import)"""
+    if not os.path.exists(BIN_IVF):
+        pytest.skip("tests/cpp/_build/dropin_ivf_check was not built (needs /root/reference at build time)")
+    out = subprocess.run([BIN_IVF], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "MISMATCH" not in out.stdout and out.stdout.count("MATCH") == 3

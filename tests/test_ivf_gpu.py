@@ -81,3 +81,64 @@ def test_ivf_range_search_matches_reference_faiss(metric):
         assert (np.diff(rd) >= 0).all() and (rl == l[0, :j]).all()
     rd, rl, total = gpu.ivf_search_range(queries[0], 1e30, nlist, max_out=7)  # everything, truncated output
     assert total == n and len(rl) == 7
+
+
+@pytest.mark.parametrize("metric,dim,nlist", [(rx.L2, 40, 24), (rx.IP, 64, 16), (rx.COS, 96, 12)])
+def test_mutable_lists_follow_reference_upserts_and_deletes(metric, dim, nlist):
+    """rxgpu_ivf_create / _add / _remove against faiss::IndexIVFFlat driven like IvfIndex::upsert / del (ivf_index.cc:87-132): the device
+    lists are never re-imported; after every burst of upserts and deletes the searches agree with the reference on the same state."""
+    n0, seed = 6000, 4400 + dim
+    vecs, labels = O.synth_matrix(seed, n0 + 3000, dim), O.row_labels(n0 + 3000)
+    ref = O.RefIvf(metric, dim, nlist)
+    ref.train_add(labels[:n0], vecs[:n0])
+    st = ref.export()
+    gpu = rx.GpuBruteforceSearch(metric, dim, 16)  # rows live in the lists, not in the flat index
+    gpu.ivf_create(st["centroids"])
+    gpu.ivf_add(ref.list_of(labels[:n0]), labels[:n0], vecs[:n0])
+    queries = np.stack([prep_query(metric, q) for q in O.synth_matrix(seed + 1, 24, dim)])
+    rng = np.random.default_rng(seed)
+    alive = set(labels[:n0].tolist())
+
+    def check(ctx):
+        assert gpu.ivf_size() == len(alive)
+        for k, nprobe in [(10, 3), (20, nlist)]:
+            d, l, c = gpu.ivf_search_knn(queries, k, nprobe)
+            for i in range(len(queries)):
+                dr, lr = ref.search(queries[i], k, nprobe)
+                dr_map = dr if metric == rx.L2 else -dr
+                assert c[i] == len(lr) and np.allclose(d[i, :c[i]], dr_map, rtol=RTOL, atol=ATOL), (ctx, k, nprobe, i)
+                if not (l[i, :c[i]] == lr).all():
+                    bad = np.nonzero(l[i, :c[i]] != lr)[0]
+                    assert set(l[i, :c[i]]) == set(lr) or np.allclose(d[i, bad], dr_map[bad], rtol=1e-5), (ctx, k, nprobe, i)
+        d31 = ref.search(queries[0], 31, nlist)[0]  # best first in FAISS' convention
+        radius = float((d31[29] + d31[30]) / 2)  # between two neighbours: no boundary ambiguity
+        dg, lg, _ = gpu.ivf_search_range(queries[0], radius if metric == rx.L2 else -radius, nlist)
+        drr, lrr = ref.range_search(queries[0], radius, nlist)
+        assert set(lg.tolist()) == set(lrr.tolist()), ctx
+
+    check("initial fill")
+    done = n0
+    for burst in (1, 40, 900, 2059):
+        new = slice(done, done + burst)
+        ref.add(labels[new], vecs[new])
+        gpu.ivf_add(ref.list_of(labels[new]), labels[new], vecs[new])
+        alive |= set(labels[new].tolist())
+        done += burst
+        victims = rng.choice(sorted(alive), size=min(len(alive) // 10, 300), replace=False)
+        for v in victims:
+            ref.remove(int(v))
+            gpu.ivf_remove(int(v))
+            alive.discard(int(v))
+        check(f"after {done - n0} upserts")
+    stats = gpu.ivf_list_stats()
+    assert stats["relocations"] > 0
+    with pytest.raises(rx.RxGpuError):
+        gpu.ivf_remove(int(victims[0]))  # already gone
+    with pytest.raises(rx.RxGpuError):
+        gpu.ivf_add([0], [int(next(iter(alive)))], vecs[:1])  # duplicate id
+    # delete most rows, then keep inserting: dead space is compacted instead of growing the slab forever
+    for v in sorted(alive)[: len(alive) * 3 // 4]:
+        ref.remove(int(v))
+        gpu.ivf_remove(int(v))
+        alive.discard(int(v))
+    check("after mass delete")
