@@ -171,6 +171,7 @@ _SIGNATURES = {
     "rxgpu_ft_decode_packed": (C.c_int, [_u8p, C.c_uint64, C.c_uint32, _u32p, _u32p, _u32p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "rxgpu_ft_merge": (C.c_int, [C.c_void_p, C.POINTER(FtConfig), C.c_uint32, C.POINTER(FtTerm), _u8p, C.c_int, C.c_uint64, C.c_void_p,
                                  C.POINTER(C.c_uint64)]),
+    "rxgpu_ft_add_postings_packed_batch": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), _u32p, _u32p]),
     "rxgpu_ft_merge_query": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _u8p, C.c_int, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]),
     "rxgpu_ft_select_query": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _u8p, _u8p, C.c_int, C.c_uint64, _i32p, _f32p,
                                          C.POINTER(C.c_uint64)]),
@@ -651,6 +652,17 @@ class GpuFtIndex:
         out = C.c_uint32(0)
         _check(self._lib.rxgpu_ft_add_postings_packed(self._h, _p(b, _u8p), len(b), count, C.byref(out)))
         return out.value
+
+    def add_postings_packed_batch(self, datas, counts):
+        """datas: list of byte arrays (PackedIdRelVec streams), decoded on the device; returns the list ids"""
+        bufs = [np.ascontiguousarray(d, np.uint8) for d in datas]
+        n = len(bufs)
+        ptrs = (C.c_void_p * max(n, 1))(*[b.ctypes.data if len(b) else None for b in bufs])
+        lens = (C.c_uint64 * max(n, 1))(*[len(b) for b in bufs])
+        cnt = np.ascontiguousarray(counts, np.uint32)
+        out = np.zeros(max(n, 1), np.uint32)
+        _check(self._lib.rxgpu_ft_add_postings_packed_batch(self._h, n, ptrs, lens, _p(cnt, _u32p), _p(out, _u32p)))
+        return out[:n].tolist()
 
     def merge(self, cfg: dict, field_cfg: list, terms: list, excluded=None, rank_sort_type=1, max_out=None, synonyms=None):
         """cfg / field_cfg: dicts with the FtConfig / FtFieldConfig member names; terms: dicts(op, boost, term_len_boost, field_boosts,

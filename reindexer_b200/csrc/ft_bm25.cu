@@ -39,6 +39,7 @@ struct DevList {
 	uint32_t* doc_ids = nullptr;
 	uint32_t* pos_begin = nullptr;
 	uint32_t* positions = nullptr;
+	bool owned = true;  // false: the arrays live in a slab of rxgpu_ft_add_postings_packed_batch
 };
 
 struct FieldCfgF {  // FTFieldConfig members converted to float where the reference's bound(float, float, float) takes them
@@ -814,6 +815,117 @@ __global__ void ft_post_emit(const int32_t* md_id, const float* proc, const uint
 	}
 }
 
+// ---- device decoder of the reference's packed posting lists (PackedIdRelVec; IdRelType::unpackWithoutArrayIdxs, idrelset.cc:185-235,
+// state chain idrelset.h:172-211, varints tools/varint.h:122-175).  The stream has no skip pointers, so one thread walks one list; a
+// commit uploads thousands of lists, which is where the parallelism comes from.  Pass 1 validates and counts, pass 2 writes the SoA.
+struct PackedCursor {
+	const uint8_t* p;
+	const uint8_t* end;
+	bool ok;
+	__device__ uint32_t get() {
+		uint32_t v = 0;
+		for (unsigned shift = 0; shift < 35; shift += 7) {
+			if (p == end) {
+				ok = false;
+				return 0;
+			}
+			const uint8_t b = *p++;
+			v |= uint32_t(b & 0x7f) << shift;
+			if (!(b & 0x80)) {
+				return v;
+			}
+		}
+		ok = false;
+		return 0;
+	}
+};
+// status: 0 ok, 1 malformed / count mismatch, 2 field or position outside the SoA range, 3 document ids not ascending below total_docs
+template <bool kWrite>
+__global__ void ft_packed_decode(const uint8_t* bytes, const unsigned long long* byte_off, const uint32_t* counts, uint32_t nlists,
+								 uint32_t total_docs, uint32_t nfields, unsigned long long* npos_out, uint32_t* status,
+								 const unsigned long long* doc_off, const unsigned long long* pos_off, uint32_t* doc_ids, uint32_t* pos_begin,
+								 uint32_t* positions) {
+	const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+	if (l >= nlists) {
+		return;
+	}
+	PackedCursor c{bytes + byte_off[l], bytes + byte_off[l + 1], true};
+	uint32_t lastId = 0, lastField = 0, ndocs = 0, st = 0;
+	unsigned long long npos = 0;
+	uint32_t* d_docs = kWrite ? doc_ids + doc_off[l] : nullptr;
+	uint32_t* d_begin = kWrite ? pos_begin + doc_off[l] + l : nullptr;  // every list owns count + 1 offsets
+	uint32_t* d_pos = kWrite ? positions + pos_off[l] : nullptr;
+	if (kWrite) {
+		d_begin[0] = 0;
+	}
+	while (c.p != c.end && st == 0) {
+		uint32_t id = c.get();
+		const uint32_t head = c.get();
+		if (head & 1) {
+			id += lastId;
+		}
+		uint32_t field = lastField;
+		if (!(head & 2)) {
+			field = c.get();
+		}
+		uint32_t size = 1;
+		if (!(head & 4)) {
+			size = c.get() + 1;
+		}
+		if (!c.ok) {
+			st = 1;
+			break;
+		}
+		uint32_t pf = field, ps = head >> 3;
+		for (uint32_t i = 0; i < size; ++i) {
+			if (i) {
+				uint32_t next = c.get();
+				const bool same = next & 1;
+				next >>= 1;
+				if (same) {
+					next += ps;
+				} else {
+					pf = c.get() + pf;
+				}
+				ps = next;
+				if (!c.ok) {
+					st = 1;
+					break;
+				}
+			}
+			if (pf >= nfields || pf > 0xFFu || ps > 0xFFFFFFu) {
+				st = 2;
+				break;
+			}
+			if (kWrite) {
+				d_pos[npos] = ps | (pf << 24);
+			}
+			++npos;
+		}
+		if (st) {
+			break;
+		}
+		if (id >= total_docs || (ndocs && id <= lastId) || ndocs >= counts[l]) {
+			st = ndocs >= counts[l] ? 1 : 3;
+			break;
+		}
+		if (kWrite) {
+			d_docs[ndocs] = id;
+			d_begin[ndocs + 1] = uint32_t(npos);
+		}
+		++ndocs;
+		lastId = id;
+		lastField = field;
+	}
+	if (st == 0 && ndocs != counts[l]) {
+		st = 1;
+	}
+	if (!kWrite) {
+		npos_out[l] = npos;
+		status[l] = st;
+	}
+}
+
 unsigned gridFor(uint64_t n, int sm) { return unsigned(std::min<uint64_t>((n + kFtThreads - 1) / kFtThreads, uint64_t(sm) * 16)); }
 
 thread_local rxgpu_ft_stats g_ft_stats{};
@@ -829,6 +941,7 @@ struct rxgpu_ft_index {
 	DevBuf<uint8_t> removed;
 	bool has_removed = false;
 	std::vector<DevList> lists;
+	std::vector<void*> slabs;  // batch uploads: one allocation per array kind and batch
 	uint32_t max_list = 0;
 	cudaStream_t stream = nullptr;
 	std::mutex mtx;  // one merge at a time per index (the per-document scratch below is shared)
@@ -863,9 +976,14 @@ struct rxgpu_ft_index {
 	~rxgpu_ft_index() {
 		cudaSetDevice(device);
 		for (auto& l : lists) {
-			cudaFree(l.doc_ids);
-			cudaFree(l.pos_begin);
-			cudaFree(l.positions);
+			if (l.owned) {
+				cudaFree(l.doc_ids);
+				cudaFree(l.pos_begin);
+				cudaFree(l.positions);
+			}
+		}
+		for (void* p : slabs) {
+			cudaFree(p);
 		}
 		if (ev0) {
 			cudaEventDestroy(ev0);
@@ -1018,6 +1136,154 @@ int rxgpu_ft_add_postings_packed(rxgpu_ft_index* ft, const uint8_t* data, uint64
 	} catch (const std::bad_alloc&) {
 		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
 	}
+}
+
+int rxgpu_ft_add_postings_packed_batch(rxgpu_ft_index* ft, uint32_t nlists, const uint8_t* const* data, const uint64_t* lens,
+									   const uint32_t* counts, uint32_t* out_ids) {
+	if (!ft || (nlists && (!data || !lens || !counts || !out_ids))) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	if (nlists == 0) {
+		return 0;
+	}
+	RX_CUDA(cudaSetDevice(ft->device));
+	// One thread decodes one list; a list longer than this would hold the whole batch back, so it takes the host decoder instead
+	// (an explicit split by size, both sides produce the same arrays)
+	constexpr uint64_t kDeviceDecodeMaxBytes = 256u << 10;
+	try {
+		std::vector<uint32_t> dev;  // indexes of the lists decoded on the device
+		uint64_t bytes = 0;
+		for (uint32_t i = 0; i < nlists; ++i) {
+			if (lens[i] && !data[i]) {
+				return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+			}
+			if (lens[i] <= kDeviceDecodeMaxBytes) {
+				dev.push_back(i);
+				bytes += lens[i];
+			}
+		}
+		const size_t firstId = ft->lists.size();
+		std::vector<DevList> fresh;
+		std::vector<void*> slabs;
+		auto dropSlabs = [&] {
+			for (void* p : slabs) {
+				cudaFree(p);
+			}
+		};
+		const uint32_t nd = uint32_t(dev.size());
+		std::vector<DevList> devLists(nd);
+		if (nd) {
+			std::vector<uint8_t> blob(std::max<uint64_t>(bytes, 1));
+			std::vector<unsigned long long> byteOff(size_t(nd) + 1, 0), docOff(size_t(nd) + 1, 0), posOff(size_t(nd) + 1, 0), npos(nd);
+			std::vector<uint32_t> cnt(nd), status(nd);
+			for (uint32_t j = 0; j < nd; ++j) {
+				const uint32_t i = dev[j];
+				if (lens[i]) {
+					std::memcpy(blob.data() + byteOff[j], data[i], lens[i]);
+				}
+				byteOff[j + 1] = byteOff[j] + lens[i];
+				cnt[j] = counts[i];
+				docOff[j + 1] = docOff[j] + counts[i];
+			}
+			DevBuf<uint8_t> dBlob;
+			DevBuf<unsigned long long> dByteOff, dNpos, dDocOff, dPosOff;
+			DevBuf<uint32_t> dCnt, dStatus;
+			RX_CUDA(dBlob.ensure(blob.size()));
+			RX_CUDA(dByteOff.ensure(byteOff.size()));
+			RX_CUDA(dNpos.ensure(nd));
+			RX_CUDA(dDocOff.ensure(docOff.size()));
+			RX_CUDA(dPosOff.ensure(posOff.size()));
+			RX_CUDA(dCnt.ensure(nd));
+			RX_CUDA(dStatus.ensure(nd));
+			cudaStream_t st = ft->stream;
+			RX_CUDA(cudaMemcpyAsync(dBlob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
+			RX_CUDA(cudaMemcpyAsync(dByteOff.p, byteOff.data(), byteOff.size() * 8, cudaMemcpyHostToDevice, st));
+			RX_CUDA(cudaMemcpyAsync(dCnt.p, cnt.data(), size_t(nd) * 4, cudaMemcpyHostToDevice, st));
+			const unsigned grid = (nd + 63) / 64;
+			ft_packed_decode<false><<<grid, 64, 0, st>>>(dBlob.p, dByteOff.p, dCnt.p, nd, ft->total_docs, ft->nfields, dNpos.p, dStatus.p, nullptr,
+														   nullptr, nullptr, nullptr, nullptr);
+			RX_CUDA(cudaGetLastError());
+			RX_CUDA(cudaMemcpyAsync(npos.data(), dNpos.p, size_t(nd) * 8, cudaMemcpyDeviceToHost, st));
+			RX_CUDA(cudaMemcpyAsync(status.data(), dStatus.p, size_t(nd) * 4, cudaMemcpyDeviceToHost, st));
+			RX_CUDA(cudaStreamSynchronize(st));
+			for (uint32_t j = 0; j < nd; ++j) {
+				if (status[j] == 2) {
+					return fail(RXGPU_ERR_PARAMS, "rxgpu: packed posting list holds a field outside the index / > 255 or a word position >= 2^24");
+				}
+				if (status[j] == 3) {
+					return fail(RXGPU_ERR_PARAMS, "rxgpu: posting list must hold ascending document ids below total_docs");
+				}
+				if (status[j]) {
+					return fail(RXGPU_ERR_PARAMS, "rxgpu: malformed packed posting list (or it contains array indexes / a different record count)");
+				}
+				if (npos[j] > 0xFFFFFFFFull) {
+					return fail(RXGPU_ERR_PARAMS, "rxgpu: posting list with more than 2^32 positions");
+				}
+				posOff[j + 1] = posOff[j] + npos[j];
+			}
+			uint32_t *docs = nullptr, *begin = nullptr, *pos = nullptr;
+			RX_CUDA(cudaMalloc(reinterpret_cast<void**>(&docs), std::max<uint64_t>(docOff[nd], 1) * 4));
+			slabs.push_back(docs);
+			cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&begin), (docOff[nd] + nd) * 4);
+			if (e == cudaSuccess) {
+				slabs.push_back(begin);
+				e = cudaMalloc(reinterpret_cast<void**>(&pos), std::max<uint64_t>(posOff[nd], 1) * 4);
+			}
+			if (e != cudaSuccess) {
+				dropSlabs();
+				return fail(RXGPU_ERR_SYSTEM, std::string("CUDA error: ") + cudaGetErrorString(e) + " at cudaMalloc (posting slab)");
+			}
+			slabs.push_back(pos);
+			cudaMemcpyAsync(dDocOff.p, docOff.data(), docOff.size() * 8, cudaMemcpyHostToDevice, st);
+			cudaMemcpyAsync(dPosOff.p, posOff.data(), posOff.size() * 8, cudaMemcpyHostToDevice, st);
+			ft_packed_decode<true><<<grid, 64, 0, st>>>(dBlob.p, dByteOff.p, dCnt.p, nd, ft->total_docs, ft->nfields, nullptr, nullptr, dDocOff.p,
+														  dPosOff.p, docs, begin, pos);
+			e = cudaGetLastError();
+			if (e == cudaSuccess) {
+				e = cudaStreamSynchronize(st);
+			}
+			if (e != cudaSuccess) {
+				dropSlabs();
+				return fail(RXGPU_ERR_SYSTEM, std::string("CUDA error: ") + cudaGetErrorString(e) + " at the packed decode");
+			}
+			for (uint32_t j = 0; j < nd; ++j) {
+				DevList& l = devLists[j];
+				l.ndocs = cnt[j];
+				l.npos = npos[j];
+				l.doc_ids = docs + docOff[j];
+				l.pos_begin = begin + docOff[j] + j;
+				l.positions = pos + posOff[j];
+				l.owned = false;
+			}
+		}
+		// commit: ids in the caller's order; the long lists go through the host decoder one by one
+		uint32_t j = 0;
+		for (uint32_t i = 0; i < nlists; ++i) {
+			if (j < nd && dev[j] == i) {
+				ft->lists.push_back(devLists[j]);
+				ft->max_list = std::max(ft->max_list, devLists[j].ndocs);
+				out_ids[i] = uint32_t(ft->lists.size() - 1);
+				++j;
+			} else if (int rc = rxgpu_ft_add_postings_packed(ft, data[i], lens[i], counts[i], &out_ids[i])) {
+				// roll back: nothing of a failed batch stays (slab-backed entries are dropped with their slabs)
+				while (ft->lists.size() > firstId) {
+					DevList& l = ft->lists.back();
+					if (l.owned) {
+						cudaFree(l.doc_ids);
+						cudaFree(l.pos_begin);
+						cudaFree(l.positions);
+					}
+					ft->lists.pop_back();
+				}
+				dropSlabs();
+				return rc;
+			}
+		}
+		ft->slabs.insert(ft->slabs.end(), slabs.begin(), slabs.end());
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
+	}
+	return 0;
 }
 
 void rxgpu_ft_last_stats(rxgpu_ft_stats* out) {

@@ -101,13 +101,15 @@ def load_golden_problem(g, name):
     return p
 
 
-def gpu_merge(prob, rank_sort_type=F.RANK_AND_ID, packed=None):
+def gpu_merge(prob, rank_sort_type=F.RANK_AND_ID, packed=None, batch=False):
     """Run one problem through the product (rxgpu_ft_*); returns (result, stats).  packed: per-list byte streams of the reference's
     PackedIdRelVec -- the lists are then uploaded through rxgpu_ft_add_postings_packed."""
     import reindexer_b200 as rx
 
     ft = rx.GpuFtIndex(prob.total_docs, prob.words, prob.avg, prob.removed)
-    if packed is not None:
+    if packed is not None and batch:  # the raw streams travel to the device and are decoded there (rxgpu_ft_add_postings_packed_batch)
+        ids = ft.add_postings_packed_batch(packed, [len(l[0]) for l in prob.lists])
+    elif packed is not None:
         ids = [ft.add_postings_packed(packed[i], len(prob.lists[i][0])) for i in range(len(prob.lists))]
     else:
         ids = [ft.add_postings(d, b, p) for d, b, p in prob.lists]

@@ -148,6 +148,8 @@ def test_packed_posting_lists_give_the_same_merge():
     c, _ = gpu_merge(p, packed=[g["multi_field/packed"]])
     assert_same_merge(a, c, F.RANK_AND_ID)
     assert len(a) > 100
+    e, _ = gpu_merge(p, packed=[g["multi_field/packed"]], batch=True)  # decoded on the device
+    assert_same_merge(a, e, F.RANK_AND_ID)
     if F.ref_available():
         for seed in range(10):
             q = random_problem(1000 + seed, total_docs=1500, nfields=1 + seed % 3, nterms=2 + seed % 2)
@@ -155,6 +157,55 @@ def test_packed_posting_lists_give_the_same_merge():
             x, _ = F.best_merge(q)
             y, _ = gpu_merge(q, packed=packed)
             assert_same_merge(x, y, F.RANK_AND_ID, ctx=f"seed {seed}")
+            z, _ = gpu_merge(q, packed=packed, batch=True)
+            assert_same_merge(x, z, F.RANK_AND_ID, ctx=f"seed {seed} device decode")
+
+
+def test_device_decode_of_packed_lists_batch():
+    """rxgpu_ft_add_postings_packed_batch: many lists decoded by the device in one call give the lists the host decoder gives (checked
+    through merges over every list), a list above the per-thread size limit takes the host decoder inside the same batch, and a
+    malformed stream rejects the whole batch"""
+    import reindexer_b200 as rx
+    g = np.load(os.path.join(ROOT, "tests", "golden", "packed_golden.npz"))
+    names = sorted({k.split("/")[0] for k in g.files if k.endswith("/packed")})
+    total = max(max(int(g[f"{n}/doc_ids"].max()) for n in names) + 2, 60000)
+    nfields = max(int((g[f"{n}/positions"] >> 24).max()) for n in names) + 1
+    rng = np.random.default_rng(5)
+    words = rng.integers(3000, 4000, size=(total, nfields)).astype(np.uint32)
+    words[0] = 0
+    avg = words[1:].mean(axis=0).astype(np.float32)
+    # a long list (> 256 KiB of stream) next to the short golden ones, packed by the reference's own encoder
+    big_docs = np.arange(1, total, dtype=np.uint32)
+    big_begin = np.arange(0, 3 * len(big_docs) + 1, 3, dtype=np.uint32)
+    big_pos = (rng.integers(0, 2900, size=3 * len(big_docs)).astype(np.uint32).reshape(-1, 3))
+    big_pos.sort(axis=1)
+    big_pos = (big_pos + np.arange(3, dtype=np.uint32)).reshape(-1)  # strictly ascending within a document, field 0
+    streams = [g[f"{n}/packed"] for n in names]
+    counts = [len(g[f"{n}/doc_ids"]) for n in names]
+    soa = [(g[f"{n}/doc_ids"], g[f"{n}/pos_begin"], g[f"{n}/positions"]) for n in names]
+    big_stream = F.ref_pack_list(big_docs, big_begin, big_pos) if F.ref_available() else np.zeros(0, np.uint8)
+    if len(big_stream) > (256 << 10):
+        streams.append(big_stream)
+        counts.append(len(big_docs))
+        soa.append((big_docs, big_begin, big_pos))
+    a = rx.GpuFtIndex(total, words, avg)
+    ids_a = a.add_postings_packed_batch(streams * 40, counts * 40)  # 40 copies: a few hundred lists in one call
+    assert not F.ref_available() or len(big_stream) > (256 << 10)
+    b = rx.GpuFtIndex(total, words, avg)
+    ids_b = [b.add_postings(*t) for t in soa]
+    p = F.FtProblem(total, words)
+    for k in range(len(soa)):
+        term = dict(op=F.OP_OR, boost=1.0, term_len_boost=1.0, field_boosts=np.ones(nfields, np.float32), procs=[100.0])
+        for copy in (0, 17, 39):
+            ra = a.merge(p.cfg, p.field_cfg, [dict(term, postings=[ids_a[copy * len(soa) + k]])])
+            rb = b.merge(p.cfg, p.field_cfg, [dict(term, postings=[ids_b[k]])])
+            assert_same_merge(ra, rb, F.RANK_AND_ID, ctx=f"list {k} copy {copy}")
+            assert len(ra) > 0
+    bad = [streams[0], streams[1][:-1] if len(streams) > 1 else streams[0][:-1]]
+    c = rx.GpuFtIndex(total, words, avg)
+    with pytest.raises(rx.RxGpuError):
+        c.add_postings_packed_batch(bad, [counts[0], counts[1] if len(counts) > 1 else counts[0]])
+    assert c.add_postings_packed_batch([streams[0]], [counts[0]]) == [0]  # nothing of the failed batch stayed
 
 
 def test_select_after_merge_on_device():
