@@ -199,6 +199,26 @@ int rxgpu_hnsw_search_knn(const rxgpu_index*, uint32_t nq, const float* queries 
 int rxgpu_hnsw_search_knn_device(const rxgpu_index*, uint32_t nq, const float* d_queries, uint32_t k, uint32_t ef, float* d_out_dist,
 								 uint32_t* d_out_idx, uint32_t* d_out_count, uint32_t* d_stats /* nq x 2 or NULL */, void* stream);
 
+/* Restores a graph from the reference's HNSW index cache without building a host graph.  The byte stream is what
+ * HierarchicalNSWImpl::SaveIndex writes (hnswalg.h:1213-1263) and the loader constructor reads (:297-403): header (max elements, count,
+ * max level, enter point, M, efConstruction), per element the level-0 list + either the primary key (alive) or the vector (deleted),
+ * then per element the blob of its upper-level lists.  Tokens are pulled through callbacks that mirror hnswlib::IReader
+ * (hnswlib.h; implemented by HnswIndexBase's Reader over the storage blob and the namespace's primary keys, hnsw_index.cc:455-483).
+ * The index must be empty with capacity >= the element count; rows, labels (tombstones get a label of their own), lists and
+ * tombstone bits are uploaded as they are decoded.  get_vstring returns non-zero on failure; the views stay valid until the next call. */
+typedef struct {
+	void* ctx;
+	uint64_t (*get_var_uint)(void* ctx);
+	int64_t (*get_var_int)(void* ctx);
+	int (*get_vstring)(void* ctx, const char** data, uint64_t* len);
+	uint64_t (*read_pk_encoded_data)(void* ctx, float* dest /* dim floats */); /* IReader::ReadPkEncodedData: returns the label */
+} rxgpu_hnsw_cache_reader;
+typedef struct {
+	uint64_t max_elements, count;
+	int32_t maxlevel;
+	uint32_t enterpoint, M, ef_construction, deleted;
+} rxgpu_hnsw_cache_info;
+int rxgpu_hnsw_load_index_cache(rxgpu_index*, const rxgpu_hnsw_cache_reader* reader, rxgpu_hnsw_cache_info* info /* or NULL */);
 /* Incremental maintenance of the imported graph after the reference's inserter added a point (HierarchicalNSWImpl::addPoint,
  * hnswalg.h:1695-1852): the caller passes the nodes whose lists changed -- the new node (with its vector and label; a tombstoned slot
  * that was reused for another vector counts as new) and the neighbours it was linked to -- and the graph's current top level and
@@ -338,12 +358,17 @@ typedef struct { /* one TermResults */
 	                               * synonyms that repeat a word of the query, :221-241), or NULL = none */
 	uint32_t nsynonyms;           /* PhraseOrTerm::SynonymsIds (querymergedata.h:160): indexes into rxgpu_ft_query::synonyms; query parts only */
 	const uint32_t* synonym_ids;
+	int32_t phrase_num;           /* FtDslOpts::phraseNum (ftdsl.h): 0 = a plain term; consecutive terms with the same non-zero number
+	                               * form ONE query part, a phrase (PhraseResults, querymergedata.h:103-139; merged by PhraseMerger,
+	                               * phrasemerger.h:285-399, then Merger::mergePhrase, mergerimpl.h:41-90).  The phrase's op is its first
+	                               * term's; subterms of phrase terms keep the caller's order (the reference merges phrases before it sorts) */
+	int32_t distance;             /* FtDslOpts::distance: how far after the previous term of the phrase this one may stand (terms 2..) */
 } rxgpu_ft_term;
 typedef struct { /* ft::Synonym (querymergedata.h:168-188): the terms of one multi-word substitution */
 	uint32_t nterms;
 	const rxgpu_ft_term* terms;
 } rxgpu_ft_synonym;
-typedef struct { /* ft::QueryMergeData (querymergedata.h:191-242) without phrases */
+typedef struct { /* ft::QueryMergeData (querymergedata.h:191-242) */
 	uint32_t nterms;
 	const rxgpu_ft_term* terms; /* queryParts */
 	uint32_t nsynonyms;

@@ -39,7 +39,7 @@ class Config(C.Structure):
 class Term(C.Structure):
     _fields_ = [("op", C.c_int32), ("boost", C.c_float), ("term_len_boost", C.c_float), ("field_boosts", _f32p), ("nsubterms", C.c_uint32),
                 ("postings", _u32p), ("procs", _f32p), ("need_sum_rank", _u8p), ("suppressed", _u8p), ("nsynonyms", C.c_uint32),
-                ("synonym_ids", _u32p)]
+                ("synonym_ids", _u32p), ("phrase_num", C.c_int32), ("distance", C.c_int32)]
 
 
 class Synonym(C.Structure):
@@ -98,18 +98,20 @@ class FtProblem:
                            np.ascontiguousarray(positions, np.uint32)))
         return len(self.lists) - 1
 
-    def _term(self, subterms, op, boost, term_len_boost, field_boosts, need_sum_rank, synonym_ids=()):
+    def _term(self, subterms, op, boost, term_len_boost, field_boosts, need_sum_rank, synonym_ids=(), phrase_num=0, distance=0):
         fb = np.ones(self.nfields, np.float32) if field_boosts is None else np.ascontiguousarray(field_boosts, np.float32)
         ns = None if need_sum_rank is None else np.ascontiguousarray(need_sum_rank, np.uint8)
         sup = np.ascontiguousarray([1 if len(s) > 2 and s[2] else 0 for s in subterms], np.uint8)
         return dict(op=op, boost=boost, term_len_boost=term_len_boost, field_boosts=fb, need_sum_rank=ns,
                     postings=np.ascontiguousarray([s[0] for s in subterms], np.uint32),
                     procs=np.ascontiguousarray([s[1] for s in subterms], np.float32), suppressed=sup if sup.any() else None,
-                    synonym_ids=np.ascontiguousarray(list(synonym_ids), np.uint32))
+                    synonym_ids=np.ascontiguousarray(list(synonym_ids), np.uint32), phrase_num=int(phrase_num), distance=int(distance))
 
-    def add_term(self, subterms, op=OP_OR, boost=1.0, term_len_boost=1.0, field_boosts=None, need_sum_rank=None, synonym_ids=()):
-        """subterms: list of (list id, proc); synonym_ids: indexes of multi-word synonyms of this query part (add_synonym)"""
-        self.terms.append(self._term(subterms, op, boost, term_len_boost, field_boosts, need_sum_rank, synonym_ids))
+    def add_term(self, subterms, op=OP_OR, boost=1.0, term_len_boost=1.0, field_boosts=None, need_sum_rank=None, synonym_ids=(), phrase_num=0,
+                 distance=0):
+        """subterms: list of (list id, proc); synonym_ids: indexes of multi-word synonyms of this query part (add_synonym);
+        phrase_num: consecutive terms with the same non-zero number form a phrase, distance = FtDslOpts::distance of the term"""
+        self.terms.append(self._term(subterms, op, boost, term_len_boost, field_boosts, need_sum_rank, synonym_ids, phrase_num, distance))
 
     def add_synonym(self, terms):
         """terms: list of dict(subterms=[(list id, proc[, suppressed])], op=..., boost=..., term_len_boost=..., field_boosts=...);
@@ -136,7 +138,7 @@ class FtProblem:
         return Term(t["op"], t["boost"], t["term_len_boost"], _p(t["field_boosts"], _f32p), len(t["postings"]), _p(t["postings"], _u32p),
                     _p(t["procs"], _f32p), None if t.get("need_sum_rank") is None else _p(t["need_sum_rank"], _u8p),
                     None if t.get("suppressed") is None else _p(t["suppressed"], _u8p), len(t.get("synonym_ids", ())),
-                    _p(t["synonym_ids"], _u32p) if len(t.get("synonym_ids", ())) else None)
+                    _p(t["synonym_ids"], _u32p) if len(t.get("synonym_ids", ())) else None, t.get("phrase_num", 0), t.get("distance", 0))
 
     def c_terms(self):
         arr = (Term * max(len(self.terms), 1))()
@@ -231,7 +233,7 @@ def _run(fn, prob: FtProblem, rank_sort_type, packed=None, max_out=None):
 
 
 def ref_merge(prob, rank_sort_type=RANK_AND_ID, packed=False):
-    if prob.synonyms:
+    if prob.synonyms or any(t.get("phrase_num", 0) for t in prob.terms):
         lists, cfg, terms, syns = prob.c_lists(), prob.c_config(), prob.c_terms(), prob.c_synonyms()
         out = np.zeros(max(prob.total_docs, 1), MERGE_INFO_DTYPE)
         n, ns = C.c_uint64(0), C.c_int64(0)
@@ -248,7 +250,8 @@ def ref_merge(prob, rank_sort_type=RANK_AND_ID, packed=False):
 
 
 def port_merge(prob, rank_sort_type=RANK_AND_ID):
-    assert not prob.synonyms, "the C port does not restate multi-word synonyms; use the reference facade (oracle/_ref)"
+    assert not prob.synonyms and not any(t.get("phrase_num", 0) for t in prob.terms), \
+        "the C port does not restate multi-word synonyms and phrases; use the reference facade (oracle/_ref)"
     rc, out, n, ns = _run(port_lib().port_ft_merge, prob, rank_sort_type)
     assert rc == 0, "port_ft_merge failed"
     return out, ns

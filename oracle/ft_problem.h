@@ -43,6 +43,8 @@ typedef struct { /* one TermResults: FtDslOpts (ftdsl.h:18-30) + its SubtermResu
 	const uint8_t* suppressed;    /* nsubterms flags (SubtermResults::Suppressed) or NULL */
 	uint32_t nsynonyms;           /* PhraseOrTerm::SynonymsIds */
 	const uint32_t* synonym_ids;
+	int32_t phrase_num;           /* FtDslOpts::phraseNum: consecutive terms with the same non-zero number form a phrase */
+	int32_t distance;             /* FtDslOpts::distance */
 } ft_term;
 
 typedef struct { /* ft::Synonym, querymergedata.h:168-188 */

@@ -85,6 +85,8 @@ reindexer::ft::TermResults<IdCont> makeTerm(const ft_term& t, uint32_t nfields, 
 	e.Opts().op = OpType(t.op);
 	e.Opts().boost = t.boost;
 	e.Opts().termLenBoost = t.term_len_boost;
+	e.Opts().phraseNum = t.phrase_num;
+	e.Opts().distance = t.distance;
 	e.Opts().fieldsOpts.resize(nfields);
 	for (uint32_t f = 0; f < nfields; ++f) {
 		e.Opts().fieldsOpts[f].boost = t.field_boosts[f];
@@ -114,13 +116,32 @@ int64_t runMerge(uint32_t totalDocs, const Stats& stats, const uint8_t* excluded
 		}
 		q.synonyms.emplace_back(std::move(syn));
 	}
+	reindexer::ft::PhraseResults<IdCont> nextPhrase;  // grouped like the selecter does (selecterimpl.h:546-566)
+	int curPhraseNum = 0;
 	for (uint32_t t = 0; t < nterms; ++t) {
 		auto tr = makeTerm(terms[t], stats.nfields, lists);
 		q.totalORVids += tr.MaxVDocs();
+		if (terms[t].phrase_num != 0) {
+			if (nextPhrase.NumTerms() && curPhraseNum != terms[t].phrase_num) {
+				q.queryParts.emplace_back(std::move(nextPhrase));
+				nextPhrase.clear();
+			}
+			curPhraseNum = terms[t].phrase_num;
+			nextPhrase.Add(std::move(tr));
+			continue;
+		}
+		if (nextPhrase.NumTerms()) {
+			q.queryParts.emplace_back(std::move(nextPhrase));
+			nextPhrase.clear();
+		}
 		q.queryParts.emplace_back(std::move(tr));
 		for (uint32_t y = 0; y < terms[t].nsynonyms; ++y) {
 			q.queryParts.back().AddSynonymId(terms[t].synonym_ids[y]);
 		}
+	}
+	if (nextPhrase.NumTerms()) {
+		q.queryParts.emplace_back(std::move(nextPhrase));
+		nextPhrase.clear();
 	}
 	reindexer::FtMergeStatuses::Statuses docsExcluded(totalDocs, false);
 	if (excluded) {

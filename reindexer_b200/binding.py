@@ -67,7 +67,7 @@ class FtConfig(C.Structure):
 class FtTerm(C.Structure):
     _fields_ = [("op", C.c_int32), ("boost", C.c_float), ("term_len_boost", C.c_float), ("field_boosts", _f32p), ("nsubterms", C.c_uint32),
                 ("postings", _u32p), ("procs", _f32p), ("need_sum_rank", _u8p), ("suppressed", _u8p), ("nsynonyms", C.c_uint32),
-                ("synonym_ids", _u32p)]
+                ("synonym_ids", _u32p), ("phrase_num", C.c_int32), ("distance", C.c_int32)]
 
 
 class FtSynonym(C.Structure):
@@ -151,6 +151,7 @@ _SIGNATURES = {
     "rxgpu_ivf_remove": (C.c_int, [C.c_void_p, C.c_uint64]),
     "rxgpu_ivf_size": (C.c_uint64, [C.c_void_p]),
     "rxgpu_ivf_list_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "rxgpu_hnsw_load_index_cache": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "rxgpu_hnsw_update": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "rxgpu_hnsw_update_count": (C.c_uint64, [C.c_void_p]),
     "rxgpu_hnsw_stream_begin": (C.c_int, [C.c_void_p, _f32p, C.c_uint32, C.POINTER(C.c_void_p)]),
@@ -738,7 +739,7 @@ class GpuFtIndex:
             keep += [fb, po, pr, ns, su, sy]
             arr[i] = FtTerm(t["op"], t["boost"], t["term_len_boost"], _p(fb, _f32p), len(po), _p(po, _u32p), _p(pr, _f32p),
                             None if ns is None else _p(ns, _u8p), None if su is None else _p(su, _u8p), len(sy),
-                            _p(sy, _u32p) if len(sy) else None)
+                            _p(sy, _u32p) if len(sy) else None, int(t.get("phrase_num", 0)), int(t.get("distance", 0)))
         return arr
 
     def last_stats(self) -> dict:

@@ -40,6 +40,7 @@ struct DevList {
 	uint32_t* pos_begin = nullptr;
 	uint32_t* positions = nullptr;
 	bool owned = true;  // false: the arrays live in a slab of rxgpu_ft_add_postings_packed_batch
+	uint32_t max_doc_npos = 0;  // most positions any document has in this list (sizes the phrase merger's per-document buffers)
 };
 
 struct FieldCfgF {  // FTFieldConfig members converted to float where the reference's bound(float, float, float) takes them
@@ -162,6 +163,9 @@ __device__ __forceinline__ float calc_term_rank(const TermParams& t, const uint3
 	return __fmul_rn(__fmul_rn(t.boost, t.proc), termRank);
 }
 
+// PosType::fullField() (idrelset.h:20) narrows (arrayIdx | field << 28) to 32 bits: with no array indexes only the low four bits of the
+// field survive, so fields 16 apart compare equal there.  Kept, because the ranks depend on it.
+__device__ __forceinline__ bool same_full_field(uint32_t a, uint32_t b) { return (((a ^ b) >> 24) & 0xFu) == 0u; }
 // PositionsDistance (mergerimpl.h:20-37): the walk advances by word position (fullPos() truncates the field away), a pair counts
 // only when the fields match
 __device__ __forceinline__ unsigned positions_distance(const uint32_t* a, uint32_t na, const uint32_t* b, uint32_t nb) {
@@ -170,7 +174,7 @@ __device__ __forceinline__ unsigned positions_distance(const uint32_t* a, uint32
 	while (i < na && j < nb) {
 		const uint32_t pa = a[i] & 0xFFFFFFu, pb = b[j] & 0xFFFFFFu;
 		const bool sign = pa > pb;
-		if ((a[i] >> 24) == (b[j] >> 24)) {
+		if (same_full_field(a[i], b[j])) {
 			const unsigned dst = sign ? pa - pb : pb - pa;
 			if (dst < res) {
 				res = dst;
@@ -728,6 +732,280 @@ __global__ void ft_syn_finish(MergeState st, const uint32_t* before, const uint8
 	}
 }
 __global__ void ft_copy_u32(uint32_t* dst, const uint32_t* src) { *dst = *src; }
+
+// ---- phrases: PhraseMerger (phrasemerger.h:285-399, phrasemergerimpl.h:166-312) and Merger::mergePhrase (mergerimpl.h:41-90) ------------
+// Per merged document the phrase merger keeps two position sets (lastPhrasePositions / nextPhrasePositions); here they are rows of two
+// [slots][cap] arrays, cap = the most positions one document can collect in one term (known from the lists).
+struct PhraseState {
+	uint32_t* pre;    // preselectedDocs_
+	uint32_t* idoff;  // idoffsets_ (sentinel = kNoSlot)
+	int32_t* id;
+	float* proc;
+	uint8_t* field;
+	float* rank;
+	uint32_t* last;
+	uint32_t* last_n;
+	uint32_t* next;
+	uint32_t* next_n;
+	uint32_t cap, max_merged;
+	uint32_t* n;  // NumDocsMerged()
+};
+__global__ void ft_phrase_mark(DevList l, const uint8_t* removed, uint32_t* bits) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < l.ndocs) {
+		const uint32_t d = l.doc_ids[i];
+		if (!(removed && removed[d])) {
+			atomicOr(&bits[d >> 5], 1u << (d & 31));
+		}
+	}
+}
+// first term of a phrase, one subterm pass (phrasemergerimpl.h:203-221): ranks, documents already merged updated in place, new ones flagged
+__global__ void ft_phrase_first_pass(DevList l, TermParams t, PhraseState ps, const uint32_t* words, const float* avg, float* tmp_rank,
+									 uint8_t* tmp_field, uint32_t* block_counts) {
+	__shared__ uint32_t s_cnt;
+	if (threadIdx.x == 0) {
+		s_cnt = 0;
+	}
+	__syncthreads();
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	bool is_new = false;
+	if (i < l.ndocs) {
+		const uint32_t d = l.doc_ids[i];
+		tmp_rank[i] = 0.f;
+		if ((ps.pre[d >> 5] >> (d & 31)) & 1u) {
+			const uint32_t* pos = l.positions + l.pos_begin[i];
+			const uint32_t npos = l.pos_begin[i + 1] - l.pos_begin[i];
+			uint8_t field;
+			const float rank = calc_term_rank(t, words, avg, d, pos, npos, &field);
+			if (rank != 0.f) {
+				const uint32_t slot = ps.idoff[d];
+				if (slot == kNoSlot) {
+					is_new = true;
+					tmp_rank[i] = rank;
+					tmp_field[i] = field;
+				} else {
+					if (rank > ps.rank[slot]) {
+						ps.rank[slot] = rank;
+						ps.proc[slot] = rank;
+					}
+					uint32_t n = ps.next_n[slot];  // AddPositions: appended, sorted and deduplicated at the end of the term
+					for (uint32_t k = 0; k < npos && n < ps.cap; ++k) {
+						ps.next[size_t(slot) * ps.cap + n++] = pos[k];
+					}
+					ps.next_n[slot] = n;
+				}
+			}
+		}
+	}
+	const unsigned m = __ballot_sync(0xffffffffu, is_new);
+	if ((threadIdx.x & 31) == 0 && m) {
+		atomicAdd(&s_cnt, __popc(m));
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		block_counts[blockIdx.x] = s_cnt;
+	}
+}
+__global__ void ft_phrase_first_assign(DevList l, PhraseState ps, const float* tmp_rank, const uint8_t* tmp_field, const uint32_t* block_offsets) {
+	__shared__ uint32_t s_warp[kFtThreads / 32];
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool is_new = i < l.ndocs && tmp_rank[i] != 0.f;
+	const uint32_t slot = *ps.n + block_offsets[blockIdx.x] + block_exclusive_rank(is_new, s_warp);
+	if (is_new && slot < ps.max_merged) {
+		const uint32_t d = l.doc_ids[i];
+		ps.id[slot] = int32_t(d);
+		ps.proc[slot] = tmp_rank[i];
+		ps.field[slot] = tmp_field[i];
+		ps.rank[slot] = tmp_rank[i];
+		ps.idoff[d] = slot;
+		const uint32_t* pos = l.positions + l.pos_begin[i];
+		const uint32_t npos = min(l.pos_begin[i + 1] - l.pos_begin[i], ps.cap);
+		for (uint32_t k = 0; k < npos; ++k) {
+			ps.next[size_t(slot) * ps.cap + k] = pos[k];
+		}
+		ps.next_n[slot] = npos;
+		ps.last_n[slot] = 0;
+	}
+}
+// a later term of the phrase, one subterm pass (phrasemergerimpl.h:222-241): MergePositionsWithDist (phrasemerger.h:23-54) against the
+// positions the previous term left, rank scaled by the smallest distance
+__global__ void ft_phrase_next_pass(DevList l, TermParams t, PhraseState ps, uint32_t dist, const uint32_t* words, const float* avg) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= l.ndocs) {
+		return;
+	}
+	const uint32_t d = l.doc_ids[i];
+	if (!((ps.pre[d >> 5] >> (d & 31)) & 1u)) {
+		return;
+	}
+	const uint32_t slot = ps.idoff[d];
+	if (slot == kNoSlot) {
+		return;
+	}
+	const uint32_t* pos = l.positions + l.pos_begin[i];
+	const uint32_t npos = l.pos_begin[i + 1] - l.pos_begin[i];
+	uint8_t field;
+	const float rank = calc_term_rank(t, words, avg, d, pos, npos, &field);
+	if (rank == 0.f) {
+		return;
+	}
+	const uint32_t* left = ps.last + size_t(slot) * ps.cap;
+	const uint32_t nl = ps.last_n[slot];
+	uint32_t* out = ps.next + size_t(slot) * ps.cap;
+	uint32_t no = ps.next_n[slot];
+	unsigned minDist = 0x7FFFFFFFu;  // std::numeric_limits<int>::max()
+	uint32_t r = 0;
+	for (uint32_t a = 0; a < nl; ++a) {
+		const uint32_t lp = left[a] & 0xFFFFFFu;  // fullPos(): the word position (the field is compared separately)
+		while (r < npos && (pos[r] & 0xFFFFFFu) < lp) {
+			++r;
+		}
+		if (r == npos) {
+			break;
+		}
+		while (r < npos && same_full_field(pos[r], left[a]) && (pos[r] & 0xFFFFFFu) - lp <= dist) {
+			minDist = min((pos[r] & 0xFFFFFFu) - lp, minDist);
+			if (no < ps.cap) {
+				out[no++] = pos[r];
+			}
+			++r;
+		}
+	}
+	ps.next_n[slot] = no;
+	if (no == 0) {
+		return;
+	}
+	const int md = int(minDist);
+	const float normDist = bound_f(__double2float_rn(__ddiv_rn(1.0, double(md < 1 ? 1 : md))), t.dist_weight, t.dist_boost);
+	const float finalRank = __fmul_rn(normDist, rank);
+	if (finalRank > ps.rank[slot]) {
+		float p = ps.proc[slot];
+		p = __fsub_rn(p, ps.rank[slot]);
+		ps.rank[slot] = finalRank;
+		ps.proc[slot] = __fadd_rn(p, finalRank);
+	}
+}
+// end of a phrase term (phrasemergerimpl.h:245-259): documents without a continuation drop out, the others SwitchPositions (sort, unique)
+__global__ void ft_phrase_end_term(PhraseState ps) {
+	const uint32_t n = min(*ps.n, ps.max_merged);
+	for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
+		uint32_t* nx = ps.next + size_t(slot) * ps.cap;
+		const uint32_t cnt = ps.next_n[slot];
+		if (cnt == 0) {
+			const uint32_t d = uint32_t(ps.id[slot]);
+			atomicAnd(&ps.pre[d >> 5], ~(1u << (d & 31)));
+			ps.proc[slot] = 0.f;
+			ps.last_n[slot] = 0;
+			ps.rank[slot] = 0.f;
+			continue;
+		}
+		for (uint32_t a = 1; a < cnt; ++a) {  // insertion sort: a handful of positions per document
+			const uint32_t v = nx[a];
+			uint32_t b = a;
+			for (; b > 0 && nx[b - 1] > v; --b) {
+				nx[b] = nx[b - 1];
+			}
+			nx[b] = v;
+		}
+		uint32_t* ls = ps.last + size_t(slot) * ps.cap;
+		uint32_t m = 0;
+		for (uint32_t a = 0; a < cnt; ++a) {
+			if (a == 0 || nx[a] != nx[a - 1]) {
+				ls[m++] = nx[a];
+			}
+		}
+		ps.last_n[slot] = m;
+		ps.next_n[slot] = 0;
+		ps.rank[slot] = 0.f;
+	}
+}
+// GetMergedDocsBitmask / ExcludeMergedDocsFromBitmask (phrasemerger.h:311-329)
+__global__ void ft_phrase_bits(PhraseState ps, uint32_t* bits, int set) {
+	const uint32_t n = min(*ps.n, ps.max_merged);
+	for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
+		if (ps.proc[slot] > 0.f) {
+			const uint32_t d = uint32_t(ps.id[slot]);
+			if (set) {
+				atomicOr(&bits[d >> 5], 1u << (d & 31));
+			} else {
+				atomicAnd(&bits[d >> 5], ~(1u << (d & 31)));
+			}
+		}
+	}
+}
+// GetMergedDocsScore (phrasemerger.h:331-338)
+__global__ void ft_phrase_score(PhraseState ps, uint16_t* score, uint32_t phrase_proc) {
+	const uint32_t n = min(*ps.n, ps.max_merged);
+	for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
+		if (ps.proc[slot] > 0.f) {
+			const uint32_t d = uint32_t(ps.id[slot]);
+			const uint32_t cur = score[d];
+			score[d] = uint16_t(cur + min(phrase_proc, 65535u - cur));
+		}
+	}
+}
+// Merger::mergePhrase (mergerimpl.h:41-90): the phrase's documents enter the merge in the phrase merger's order
+__global__ void ft_phrase_merge_pass(PhraseState ps, MergeState st, uint16_t qp_idx, uint8_t* flags, uint32_t* block_counts) {
+	__shared__ uint32_t s_cnt;
+	if (threadIdx.x == 0) {
+		s_cnt = 0;
+	}
+	__syncthreads();
+	const uint32_t n = min(*ps.n, ps.max_merged);
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	bool is_new = false;
+	if (i < n) {
+		const float proc = ps.proc[i];
+		const uint32_t d = uint32_t(ps.id[i]);
+		if (proc != 0.f && ((st.mask[d >> 5] >> (d & 31)) & 1u)) {
+			const uint32_t slot = st.idoff[d];
+			if (slot == kNoSlot) {
+				is_new = true;
+			} else {
+				if (st.ext_last_term[slot] < qp_idx) {
+					st.ext_cnt[slot]++;
+					st.ext_last_term[slot] = qp_idx;
+				}
+				st.md_proc[slot] = __fadd_rn(st.md_proc[slot], proc);
+				st.last_ptr[slot] = reinterpret_cast<unsigned long long>(ps.last + size_t(i) * ps.cap);
+				st.last_n[slot] = ps.last_n[i];
+				st.ext_rank[slot] = 0.f;
+			}
+		}
+	}
+	if (i < ps.max_merged) {
+		flags[i] = is_new ? 1 : 0;
+	}
+	const unsigned m = __ballot_sync(0xffffffffu, is_new);
+	if ((threadIdx.x & 31) == 0 && m) {
+		atomicAdd(&s_cnt, __popc(m));
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		block_counts[blockIdx.x] = s_cnt;
+	}
+}
+__global__ void ft_phrase_merge_assign(PhraseState ps, MergeState st, uint32_t max_merged, uint16_t qp_idx, const uint8_t* flags,
+									   const uint32_t* block_offsets) {
+	__shared__ uint32_t s_warp[kFtThreads / 32];
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool is_new = i < ps.max_merged && flags[i];
+	const uint32_t slot = *st.n_docs + block_offsets[blockIdx.x] + block_exclusive_rank(is_new, s_warp);
+	if (is_new && slot < max_merged) {
+		const uint32_t d = uint32_t(ps.id[i]);
+		st.md_id[slot] = int32_t(d);
+		st.md_proc[slot] = ps.proc[i];
+		st.md_field[slot] = ps.field[i];
+		st.idoff[d] = slot;
+		st.last_ptr[slot] = reinterpret_cast<unsigned long long>(ps.last + size_t(i) * ps.cap);
+		st.last_n[slot] = ps.last_n[i];
+		st.next_ptr[slot] = 0;
+		st.next_n[slot] = 0;
+		st.ext_rank[slot] = 0.f;  // MergerDocumentData(phraseDocMergeDataExt.rank): the phrase merger left 0 there
+		st.ext_cnt[slot] = 1;
+		st.ext_last_term[slot] = qp_idx;
+	}
+}
 // addFullMatchBoost (merger.h:100-109) with canBeBoostedByFullMatch (mergerimpl.h:533-537)
 __global__ void ft_full_match(MergeState st, const uint32_t* words, uint32_t nfields, uint32_t num_terms, uint32_t need_cnt, int simple,
 							  double boost) {
@@ -842,7 +1120,7 @@ struct PackedCursor {
 // status: 0 ok, 1 malformed / count mismatch, 2 field or position outside the SoA range, 3 document ids not ascending below total_docs
 template <bool kWrite>
 __global__ void ft_packed_decode(const uint8_t* bytes, const unsigned long long* byte_off, const uint32_t* counts, uint32_t nlists,
-								 uint32_t total_docs, uint32_t nfields, unsigned long long* npos_out, uint32_t* status,
+								 uint32_t total_docs, uint32_t nfields, unsigned long long* npos_out, uint32_t* status, uint32_t* max_doc_npos,
 								 const unsigned long long* doc_off, const unsigned long long* pos_off, uint32_t* doc_ids, uint32_t* pos_begin,
 								 uint32_t* positions) {
 	const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
@@ -850,7 +1128,7 @@ __global__ void ft_packed_decode(const uint8_t* bytes, const unsigned long long*
 		return;
 	}
 	PackedCursor c{bytes + byte_off[l], bytes + byte_off[l + 1], true};
-	uint32_t lastId = 0, lastField = 0, ndocs = 0, st = 0;
+	uint32_t lastId = 0, lastField = 0, ndocs = 0, st = 0, maxDoc = 0;
 	unsigned long long npos = 0;
 	uint32_t* d_docs = kWrite ? doc_ids + doc_off[l] : nullptr;
 	uint32_t* d_begin = kWrite ? pos_begin + doc_off[l] + l : nullptr;  // every list owns count + 1 offsets
@@ -913,6 +1191,7 @@ __global__ void ft_packed_decode(const uint8_t* bytes, const unsigned long long*
 			d_docs[ndocs] = id;
 			d_begin[ndocs + 1] = uint32_t(npos);
 		}
+		maxDoc = max(maxDoc, size);
 		++ndocs;
 		lastId = id;
 		lastField = field;
@@ -923,6 +1202,7 @@ __global__ void ft_packed_decode(const uint8_t* bytes, const unsigned long long*
 	if (!kWrite) {
 		npos_out[l] = npos;
 		status[l] = st;
+		max_doc_npos[l] = maxDoc;
 	}
 }
 
@@ -949,6 +1229,16 @@ struct rxgpu_ft_index {
 	DevBuf<uint32_t> mask, tmask, idoff, block_counts, scalar_u32;
 	DevBuf<uint32_t> syn_masks, tmask2;  // multi-word synonyms: one document mask per synonym + a per-term scratch
 	DevBuf<uint8_t> syn_full;            // MergerDocumentData::containsFullMultiWordSynonym per merged document
+	struct PhraseBufs {                  // one PhraseMerger (phrasemerger.h:285-399)
+		DevBuf<uint32_t> pre, last, last_n, next, next_n, n;
+		DevBuf<int32_t> id;
+		DevBuf<float> proc, rank;
+		DevBuf<uint8_t> field, flags;
+		uint32_t cap = 0, max_merged = 0, phrase_proc = 0, num_merged = 0;
+	};
+	std::vector<std::unique_ptr<PhraseBufs>> phrases;
+	DevBuf<uint32_t> p_idoff, p_term_mask;  // the phrase mergers' idoffsets_ (shared, cleaned after each) and nextTermDocs_
+	bool p_idoff_clean = false;
 	bool idoff_clean = false;  // idoff holds kNoSlot everywhere
 	PinBuf<int32_t> h_id;  // results of the last merge (pinned: one asynchronous copy per array, one synchronisation per query)
 	PinBuf<float> h_proc;
@@ -1053,6 +1343,7 @@ int rxgpu_ft_add_postings(rxgpu_ft_index* ft, const rxgpu_ft_postings* list, uin
 		if (list->pos_begin[i + 1] < list->pos_begin[i]) {
 			return fail(RXGPU_ERR_PARAMS, "rxgpu: posting list: pos_begin must be non-decreasing");
 		}
+		l.max_doc_npos = std::max(l.max_doc_npos, list->pos_begin[i + 1] - list->pos_begin[i]);
 	}
 	if (l.npos && !list->positions) {
 		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
@@ -1200,8 +1491,12 @@ int rxgpu_ft_add_postings_packed_batch(rxgpu_ft_index* ft, uint32_t nlists, cons
 			RX_CUDA(cudaMemcpyAsync(dByteOff.p, byteOff.data(), byteOff.size() * 8, cudaMemcpyHostToDevice, st));
 			RX_CUDA(cudaMemcpyAsync(dCnt.p, cnt.data(), size_t(nd) * 4, cudaMemcpyHostToDevice, st));
 			const unsigned grid = (nd + 63) / 64;
-			ft_packed_decode<false><<<grid, 64, 0, st>>>(dBlob.p, dByteOff.p, dCnt.p, nd, ft->total_docs, ft->nfields, dNpos.p, dStatus.p, nullptr,
-														   nullptr, nullptr, nullptr, nullptr);
+			DevBuf<uint32_t> dMaxDoc;
+			std::vector<uint32_t> maxDoc(nd);
+			RX_CUDA(dMaxDoc.ensure(nd));
+			ft_packed_decode<false><<<grid, 64, 0, st>>>(dBlob.p, dByteOff.p, dCnt.p, nd, ft->total_docs, ft->nfields, dNpos.p, dStatus.p, dMaxDoc.p,
+														   nullptr, nullptr, nullptr, nullptr, nullptr);
+			RX_CUDA(cudaMemcpyAsync(maxDoc.data(), dMaxDoc.p, size_t(nd) * 4, cudaMemcpyDeviceToHost, st));
 			RX_CUDA(cudaGetLastError());
 			RX_CUDA(cudaMemcpyAsync(npos.data(), dNpos.p, size_t(nd) * 8, cudaMemcpyDeviceToHost, st));
 			RX_CUDA(cudaMemcpyAsync(status.data(), dStatus.p, size_t(nd) * 4, cudaMemcpyDeviceToHost, st));
@@ -1236,8 +1531,8 @@ int rxgpu_ft_add_postings_packed_batch(rxgpu_ft_index* ft, uint32_t nlists, cons
 			slabs.push_back(pos);
 			cudaMemcpyAsync(dDocOff.p, docOff.data(), docOff.size() * 8, cudaMemcpyHostToDevice, st);
 			cudaMemcpyAsync(dPosOff.p, posOff.data(), posOff.size() * 8, cudaMemcpyHostToDevice, st);
-			ft_packed_decode<true><<<grid, 64, 0, st>>>(dBlob.p, dByteOff.p, dCnt.p, nd, ft->total_docs, ft->nfields, nullptr, nullptr, dDocOff.p,
-														  dPosOff.p, docs, begin, pos);
+			ft_packed_decode<true><<<grid, 64, 0, st>>>(dBlob.p, dByteOff.p, dCnt.p, nd, ft->total_docs, ft->nfields, nullptr, nullptr, nullptr,
+														  dDocOff.p, dPosOff.p, docs, begin, pos);
 			e = cudaGetLastError();
 			if (e == cudaSuccess) {
 				e = cudaStreamSynchronize(st);
@@ -1254,6 +1549,7 @@ int rxgpu_ft_add_postings_packed_batch(rxgpu_ft_index* ft, uint32_t nlists, cons
 				l.pos_begin = begin + docOff[j] + j;
 				l.positions = pos + posOff[j];
 				l.owned = false;
+				l.max_doc_npos = maxDoc[j];
 			}
 		}
 		// commit: ids in the caller's order; the long lists go through the host decoder one by one
@@ -1329,7 +1625,40 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 	g_ft_stats = rxgpu_ft_stats{};
 	*out_n = 0;
 	const uint32_t N = ft->total_docs;
-	if (nterms == 0 || (nterms == 1 && terms[0].op == 3) || N == 0) {  // QueryMergeData::Empty(), mergerimpl.h:472
+	// query parts: a plain term, or a phrase = consecutive terms that share a non-zero phrase_num (FtDslOpts::phraseNum; the selecter
+	// groups them the same way, selecterimpl.h:548-558).  head[t]: term t opens a part; inPhrase[t]: it belongs to a phrase.
+	std::vector<uint8_t> head(nterms, 1), inPhrase(nterms, 0);
+	std::vector<uint32_t> phraseLen(nterms, 0);
+	uint32_t nparts = 0, queryLength = 0, nphrases = 0;
+	for (uint32_t t = 0; t < nterms; ++t) {
+		if (terms[t].phrase_num != 0) {
+			inPhrase[t] = 1;
+			if (t > 0 && terms[t - 1].phrase_num == terms[t].phrase_num) {
+				head[t] = 0;
+			}
+		}
+		nparts += head[t];
+	}
+	for (uint32_t t = 0; t < nterms; ++t) {
+		if (head[t] && inPhrase[t]) {
+			uint32_t e = t + 1;
+			while (e < nterms && !head[e]) {
+				++e;
+			}
+			phraseLen[t] = e - t;
+			++nphrases;
+			if (phraseLen[t] < 2) {
+				return fail(RXGPU_ERR_PARAMS, "rxgpu: a phrase needs at least two terms");
+			}
+			for (uint32_t u = t; u < e; ++u) {
+				if (terms[u].nsynonyms || terms[u].distance < 0) {
+					return fail(RXGPU_ERR_PARAMS, "rxgpu: malformed phrase term (synonym ids / negative distance)");
+				}
+			}
+		}
+	}
+	queryLength = nterms;  // QueryLength(): every phrase counts its terms (querymergedata.h:212-219)
+	if (nparts == 0 || (nparts == 1 && terms[0].op == 3) || N == 0) {  // QueryMergeData::Empty(), mergerimpl.h:472
 		return 0;
 	}
 	for (uint32_t t = 0; t < nall; ++t) {
@@ -1378,10 +1707,13 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 			subs[t].push_back(Sub{terms[t].postings[s], terms[t].procs[s], terms[t].suppressed && terms[t].suppressed[s]});
 			totalORVids += ft->lists[terms[t].postings[s]].ndocs;
 		}
+		if (t < nterms && inPhrase[t]) {
+			continue;  // PhraseMerger::Merge runs inside Merger::init (merger.h:84-90), BEFORE SortSubterms: the caller's order stands
+		}
 		std::stable_sort(subs[t].begin(), subs[t].end(), [](const Sub& a, const Sub& b) { return a.proc > b.proc; });
 	}
 	const uint32_t maxMerged = uint32_t(std::min<uint64_t>(cfg->merge_limit, totalORVids));  // init(), merger.h:66-67
-	const bool simple = nterms == 1 && terms[0].op != 3 && nsyn == 0;  // QueryMergeData::Simple()
+	const bool simple = nparts == 1 && !inPhrase[0] && terms[0].op != 3 && nsyn == 0;  // QueryMergeData::Simple()
 	const bool trivial = simple && terms[0].nsubterms == 1;
 	if (maxMerged == 0) {
 		return 0;
@@ -1493,15 +1825,140 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 	};
 	auto bytesOfPass = [&](const DevList& l) { return uint64_t(l.ndocs) * 20 + l.npos * 4; };
 
+	// ---- PhraseMerger::Merge for every phrase part (Merger::init, merger.h:82-90) -- before anything else, on docsExcluded as given
+	std::vector<int> phraseOf(nterms, -1);  // head term -> index into ft->phrases
+	std::vector<PhraseState> pstates;
+	if (nphrases) {
+		while (ft->phrases.size() < nphrases) {
+			ft->phrases.emplace_back(std::make_unique<rxgpu_ft_index::PhraseBufs>());
+		}
+		RX_CUDA(ft->p_idoff.ensure(N));
+		RX_CUDA(ft->p_term_mask.ensure(mwords));
+		if (!ft->p_idoff_clean) {
+			ft_fill_u32<<<gridFor(N, sm), kFtThreads, 0, st>>>(ft->p_idoff.p, kNoSlot, N);
+			g_ft_stats.launches++;
+			ft->p_idoff_clean = true;
+		}
+		uint32_t pi = 0;
+		for (uint32_t t = 0; t < nterms; ++t) {
+			if (!(head[t] && inPhrase[t])) {
+				continue;
+			}
+			const uint32_t len = phraseLen[t];
+			rxgpu_ft_index::PhraseBufs& pb = *ft->phrases[pi];
+			phraseOf[t] = int(pi++);
+			// init (phrasemerger.h:341-358)
+			uint64_t firstVDocs = 0;
+			for (const Sub& sub : subs[t]) {
+				firstVDocs += ft->lists[sub.list].ndocs;
+			}
+			pb.max_merged = uint32_t(std::min<uint64_t>(cfg->merge_limit, firstVDocs));
+			long long sumProc = 0;  // PhraseResults::CalcProc16 (querymergedata.h:121-131): the FIRST subterm of every term
+			uint64_t cap = 1;
+			for (uint32_t u = t; u < t + len; ++u) {
+				if (!subs[u].empty()) {
+					sumProc += (long long)(subs[u][0].proc);
+				}
+				uint64_t c = 0;
+				for (const Sub& sub : subs[u]) {
+					c += ft->lists[sub.list].max_doc_npos;
+				}
+				cap = std::max(cap, c);
+			}
+			if (sumProc < 0 || sumProc >= 65535) {
+				return fail(RXGPU_ERR_PARAMS, "rxgpu: the procs of a phrase's terms do not fit 16 bits (PhraseResults::CalcProc16)");
+			}
+			pb.phrase_proc = uint32_t(sumProc);
+			const uint64_t slots = std::max<uint32_t>(pb.max_merged, 1);
+			if (slots * cap * 8 > (uint64_t(4) << 30)) {
+				return fail(RXGPU_ERR_LOGIC, "rxgpu: the phrase's position buffers would exceed 4 GiB on the device (merge_limit x positions per document)");
+			}
+			pb.cap = uint32_t(cap);
+			RX_CUDA(pb.pre.ensure(mwords));
+			RX_CUDA(pb.n.ensure(2));
+			RX_CUDA(pb.id.ensure(slots));
+			RX_CUDA(pb.proc.ensure(slots));
+			RX_CUDA(pb.rank.ensure(slots));
+			RX_CUDA(pb.field.ensure(slots));
+			RX_CUDA(pb.flags.ensure(slots));
+			RX_CUDA(pb.last_n.ensure(slots));
+			RX_CUDA(pb.next_n.ensure(slots));
+			RX_CUDA(pb.last.ensure(slots * cap));
+			RX_CUDA(pb.next.ensure(slots * cap));
+			RX_CUDA(cudaMemsetAsync(pb.n.p, 0, 8, st));
+			PhraseState ps{pb.pre.p, ft->p_idoff.p, pb.id.p, pb.proc.p, pb.field.p, pb.rank.p, pb.last.p, pb.last_n.p,
+						   pb.next.p, pb.next_n.p, pb.cap, pb.max_merged, pb.n.p};
+			// preselectDocsContainingAllTerms (phrasemergerimpl.h:262-300): AND of the terms' document sets, removed documents leave with
+			// the last term, excluded ones at the end
+			ft_mask_init<<<gridFor(mwords, sm), kFtThreads, 0, st>>>(pb.pre.p, d_excluded, N, mwords);
+			g_ft_stats.launches++;
+			for (uint32_t u = t; u < t + len; ++u) {
+				RX_CUDA(cudaMemsetAsync(ft->p_term_mask.p, 0, size_t(mwords) * 4, st));
+				for (const Sub& sub : subs[u]) {
+					const DevList& l = ft->lists[sub.list];
+					if (l.ndocs) {
+						ft_phrase_mark<<<gridFor(l.ndocs, sm), kFtThreads, 0, st>>>(l, u + 1 == t + len && ft->has_removed ? ft->removed.p : nullptr,
+																					  ft->p_term_mask.p);
+						g_ft_stats.launches++;
+						g_ft_stats.postings_scanned += l.ndocs;
+					}
+				}
+				ft_mask_and<<<gridFor(mwords, sm), kFtThreads, 0, st>>>(pb.pre.p, ft->p_term_mask.p, mwords);
+				g_ft_stats.launches++;
+			}
+			// mergePhraseTerm for every term (phrasemergerimpl.h:166-259)
+			for (uint32_t u = t; u < t + len; ++u) {
+				for (const Sub& sub : subs[u]) {
+					const DevList& l = ft->lists[sub.list];
+					if (!l.ndocs) {
+						continue;
+					}
+					const unsigned lb = (l.ndocs + kFtThreads - 1) / kFtThreads;
+					if (u == t) {
+						if (pb.max_merged == 0) {
+							continue;
+						}
+						ft_phrase_first_pass<<<lb, kFtThreads, 0, st>>>(l, termParams(u, sub, l), ps, ft->words.p, ft->avg.p, ft->tmp_rank.p, ft->tmp_field.p,
+																		 ft->block_counts.p);
+						ft_scan_blocks<<<1, 1024, 0, st>>>(ft->block_counts.p, lb, pb.n.p + 1);
+						ft_phrase_first_assign<<<lb, kFtThreads, 0, st>>>(l, ps, ft->tmp_rank.p, ft->tmp_field.p, ft->block_counts.p);
+						ft_bump_count<<<1, 1, 0, st>>>(pb.n.p, pb.n.p + 1, pb.max_merged);
+						g_ft_stats.launches += 4;
+					} else {
+						ft_phrase_next_pass<<<lb, kFtThreads, 0, st>>>(l, termParams(u, sub, l), ps, uint32_t(terms[u].distance), ft->words.p, ft->avg.p);
+						g_ft_stats.launches++;
+					}
+					g_ft_stats.postings_scanned += l.ndocs;
+					g_ft_stats.algorithmic_bytes += bytesOfPass(l);
+				}
+				ft_phrase_end_term<<<gridFor(std::max<uint32_t>(pb.max_merged, 1), sm), kFtThreads, 0, st>>>(ps);
+				g_ft_stats.launches++;
+			}
+			ft_reset_idoff<<<gridFor(std::max<uint32_t>(pb.max_merged, 1), sm), kFtThreads, 0, st>>>(pb.id.p, pb.n.p, ft->p_idoff.p);
+			g_ft_stats.launches++;
+			RX_CUDA(cudaMemcpyAsync(&pb.num_merged, pb.n.p, 4, cudaMemcpyDeviceToHost, st));  // NumDocsMerged() feeds estimateNumDocsInMerge
+			pstates.push_back(ps);
+		}
+		RX_CUDA(cudaGetLastError());
+		RX_CUDA(cudaStreamSynchronize(st));
+	}
+
 	int checkRemoved = 1;
 	if (!simple) {
 		// buildRestrictingBitmask (mergerimpl.h:326-384)
 		std::vector<uint8_t> synMaskDone(nsyn, 0);
 		for (uint32_t t = 0; t < nterms; ++t) {
-			if (terms[t].op != 2) {
+			if (!head[t] || terms[t].op != 2) {
 				continue;
 			}
 			RX_CUDA(cudaMemsetAsync(ft->tmask.p, 0, size_t(mwords) * 4, st));
+			if (inPhrase[t]) {  // phraseMergers_[i].GetMergedDocsBitmask (mergerimpl.h:346-347)
+				const PhraseState& ps = pstates[phraseOf[t]];
+				ft_phrase_bits<<<gridFor(std::max<uint32_t>(ps.max_merged, 1), sm), kFtThreads, 0, st>>>(ps, ft->tmask.p, 1);
+				ft_mask_and<<<gridFor(mwords, sm), kFtThreads, 0, st>>>(ft->mask.p, ft->tmask.p, mwords);
+				g_ft_stats.launches += 2;
+				continue;
+			}
 			int allPositive = 1;
 			for (uint32_t f = 0; f < ft->nfields; ++f) {
 				allPositive &= terms[t].field_boosts[f] != 0.f;
@@ -1549,7 +2006,13 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 			g_ft_stats.launches++;
 		}
 		for (uint32_t t = 0; t < nterms; ++t) {
-			if (terms[t].op != 3) {
+			if (!head[t] || terms[t].op != 3) {
+				continue;
+			}
+			if (inPhrase[t]) {  // ExcludeMergedDocsFromBitmask (mergerimpl.h:378-379)
+				const PhraseState& ps = pstates[phraseOf[t]];
+				ft_phrase_bits<<<gridFor(std::max<uint32_t>(ps.max_merged, 1), sm), kFtThreads, 0, st>>>(ps, ft->mask.p, 0);
+				g_ft_stats.launches++;
 				continue;
 			}
 			for (const Sub& sub : subs[t]) {
@@ -1564,12 +2027,15 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 		// estimateNumDocsInMerge (merger.h:239-267)
 		uint64_t estOr = 0, estAnd = UINT64_MAX;
 		for (uint32_t t = 0; t < nterms; ++t) {
-			if (terms[t].op == 3) {
+			if (!head[t] || terms[t].op == 3) {
 				continue;
 			}
 			uint64_t nd = 0;
 			for (const Sub& sub : subs[t]) {
 				nd += ft->lists[sub.list].ndocs;
+			}
+			if (inPhrase[t]) {
+				nd = ft->phrases[phraseOf[t]]->num_merged;  // phraseMergers_[i].NumDocsMerged() (merger.h:252)
 			}
 			for (uint32_t y = 0; y < terms[t].nsynonyms; ++y) {  // + the first term of each of its synonyms (merger.h:253-256)
 				for (const Sub& sub : subs[synBegin[terms[t].synonym_ids[y]]]) {
@@ -1602,7 +2068,14 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 			RX_CUDA(cudaMemsetAsync(ft->hist.p, 0, 65536 * 8, st));
 			for (uint32_t tt = 0; tt < nall; ++tt) {
 				const uint32_t t = tt < nall - nterms ? nterms + tt : tt - (nall - nterms);  // the synonyms' terms first (mergerimpl.h:392-396)
-				if (t < nterms && terms[t].op == 3) {
+				if (t < nterms && (!head[t] || terms[t].op == 3)) {
+					continue;
+				}
+				if (t < nterms && inPhrase[t]) {  // GetMergedDocsScore (mergerimpl.h:408-409)
+					const PhraseState& ps = pstates[phraseOf[t]];
+					ft_phrase_score<<<gridFor(std::max<uint32_t>(ps.max_merged, 1), sm), kFtThreads, 0, st>>>(ps, ft->score.p,
+																											   ft->phrases[phraseOf[t]]->phrase_proc);
+					g_ft_stats.launches++;
 					continue;
 				}
 				RX_CUDA(cudaMemsetAsync(ft->tmask.p, 0, size_t(mwords) * 4, st));
@@ -1645,10 +2118,27 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 			RX_CUDA(cudaMemsetAsync(ft->syn_full.p, 0, maxMerged, st));
 			g_ft_stats.launches++;
 		}
+		if (t < nterms && !head[t]) {
+			continue;  // inside a phrase: merged with its head
+		}
 		// mergeTerm returns at once for OpNot (mergerimpl.h:113-115); a NOT query part does not even take an index (:497-499)
 		const bool isNot = terms[t].op == 3;
 		if (!isNot || t >= nterms) {
 			++qpIdx;
+		}
+		if (t < nterms && inPhrase[t]) {
+			if (!isNot) {  // mergePhrase (mergerimpl.h:41-90): no switchToNextWord, the phrase's last positions become the document's
+				const PhraseState& ps = pstates[phraseOf[t]];
+				uint8_t* flags = ft->phrases[phraseOf[t]]->flags.p;
+				const unsigned lb = (std::max<uint32_t>(ps.max_merged, 1) + kFtThreads - 1) / kFtThreads;
+				RX_CUDA(ft->block_counts.ensure(lb + 1));
+				ft_phrase_merge_pass<<<lb, kFtThreads, 0, st>>>(ps, ms, qpIdx, flags, ft->block_counts.p);
+				ft_scan_blocks<<<1, 1024, 0, st>>>(ft->block_counts.p, lb, d_total_new);
+				ft_phrase_merge_assign<<<lb, kFtThreads, 0, st>>>(ps, ms, maxMerged, qpIdx, flags, ft->block_counts.p);
+				ft_bump_count<<<1, 1, 0, st>>>(ms.n_docs, d_total_new, maxMerged);
+				g_ft_stats.launches += 4;
+			}
+			continue;
 		}
 		if (!simple && !isNot) {
 			ft_switch<<<gridFor(maxMerged, sm), kFtThreads, 0, st>>>(ms);
@@ -1687,7 +2177,7 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 		}
 	}
 	// canBeBoostedByFullMatch: termsCounter == queryParts.size() (NOT parts never count) ; QueryLength == nterms
-	ft_full_match<<<gridFor(maxMerged, sm), kFtThreads, 0, st>>>(ms, d_words, ft->nfields, simple ? 1u : nterms, nterms, simple ? 1 : 0,
+	ft_full_match<<<gridFor(maxMerged, sm), kFtThreads, 0, st>>>(ms, d_words, ft->nfields, simple ? 1u : queryLength, nparts, simple ? 1 : 0,
 																 cfg->full_match_boost);
 	g_ft_stats.launches++;
 	if (nsyn) {

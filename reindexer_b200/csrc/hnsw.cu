@@ -1618,6 +1618,130 @@ int rxgpu_gather_labels_device(const rxgpu_index* ix, uint64_t n, const uint32_t
 	return 0;
 }
 
+// Restores a graph straight from the reference's index cache (what HierarchicalNSWImpl::SaveIndex writes, hnswalg.h:1213-1263, and its
+// loader constructor reads, :297-403; the token stream is hnswlib::IReader's, hnswlib.h -- hnsw_index.cc:455-483 implements it over the
+// storage blob and the namespace's primary keys): no host-side graph is built, rows and lists go to the device as they are decoded.
+int rxgpu_hnsw_load_index_cache(rxgpu_index* ix, const rxgpu_hnsw_cache_reader* r, rxgpu_hnsw_cache_info* info) {
+	if (int rc = checkIndex(ix)) {
+		return rc;
+	}
+	if (!r || !r->get_var_uint || !r->get_var_int || !r->get_vstring || !r->read_pk_encoded_data) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	if (ix->size != 0) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: the index cache is loaded into an empty index");
+	}
+	try {
+		void* c = r->ctx;
+		const uint64_t maxElements = r->get_var_uint(c);
+		const uint64_t count = r->get_var_uint(c);
+		if (count > maxElements) {
+			return fail(RXGPU_ERR_PARAMS, "Current elements count is larger than max elements count");  // hnswalg.h:303
+		}
+		const int64_t maxlevel = r->get_var_int(c);
+		const uint64_t enterpoint = r->get_var_uint(c);
+		if (count ? enterpoint >= count : enterpoint != 0xFFFFFFFFull) {
+			return fail(RXGPU_ERR_PARAMS, count ? "Incorrect entrypoint node ID" : "Unexpected entrypoint node ID for empty HNSW");  // :325-330
+		}
+		const uint64_t M = r->get_var_uint(c);
+		const uint64_t efConstruction = r->get_var_uint(c);
+		if (M == 0 || M > 4096 || count > 0xFFFFFFF0ull || count > ix->capacity) {
+			return fail(RXGPU_ERR_PARAMS, count > ix->capacity ? "rxgpu: the index cache holds more elements than the index's capacity"
+																: "rxgpu: malformed HNSW index cache header");
+		}
+		if (info) {
+			*info = rxgpu_hnsw_cache_info{maxElements, count, int32_t(maxlevel), uint32_t(enterpoint), uint32_t(M), uint32_t(efConstruction), 0};
+		}
+		if (count == 0) {
+			return 0;
+		}
+		const uint32_t n = uint32_t(count), m0 = uint32_t(2 * M);
+		std::vector<uint32_t> level0(size_t(n) * (1 + m0), 0u);
+		std::vector<uint64_t> labels(n);
+		std::vector<uint32_t> deleted;
+		const size_t slice = std::max<size_t>(1, (size_t(64) << 20) / (size_t(ix->dim) * 4));
+		std::vector<float> rows(std::min<size_t>(slice, n) * ix->dim);
+		size_t sliceBase = 0;
+		for (uint32_t i = 0; i < n; ++i) {
+			const uint32_t marked = uint32_t(r->get_var_uint(c));  // [u16 count | u8 flags | pad] (hnswalg.h:221-228)
+			const uint32_t cnt = marked & 0xFFFFu;
+			if (cnt > m0) {
+				return fail(RXGPU_ERR_PARAMS, "rxgpu: HNSW index cache: a level-0 neighbour count exceeds 2*M");
+			}
+			uint32_t* l0 = level0.data() + size_t(i) * (1 + m0);
+			l0[0] = cnt;
+			for (uint32_t j = 0; j < cnt; ++j) {
+				l0[1 + j] = uint32_t(r->get_var_uint(c));
+			}
+			float* dst = rows.data() + (i - sliceBase) * ix->dim;
+			if ((marked >> 16) & 0x01u) {  // DELETE_MARK: the vector itself is stored, the label is gone (:372-375)
+				const char* data = nullptr;
+				uint64_t len = 0;
+				if (r->get_vstring(c, &data, &len) || len != size_t(ix->dim) * 4) {
+					return fail(RXGPU_ERR_PARAMS, "rxgpu: HNSW index cache: a deleted element's vector has the wrong size");
+				}
+				std::memcpy(dst, data, len);
+				labels[i] = (uint64_t(1) << 63) | uint64_t(i);  // a tombstone's slot keeps a label of its own
+				deleted.push_back(i);
+			} else {
+				labels[i] = r->read_pk_encoded_data(c, dst);  // the namespace resolves the primary key and copies the row's vector
+			}
+			if (i + 1 - sliceBase == slice || i + 1 == n) {
+				if (int rc = rxgpu_index_upsert_batch(ix, i + 1 - sliceBase, labels.data() + sliceBase, rows.data())) {
+					return rc;
+				}
+				sliceBase = i + 1;
+			}
+		}
+		const size_t s1 = 1 + size_t(M);
+		std::vector<int32_t> levels(n);
+		std::vector<int64_t> upperOff(size_t(n) + 1, 0);
+		std::vector<uint32_t> upper;
+		for (uint32_t i = 0; i < n; ++i) {
+			const char* data = nullptr;
+			uint64_t len = 0;
+			if (r->get_vstring(c, &data, &len) || len % (s1 * 4) != 0) {
+				return fail(RXGPU_ERR_PARAMS, "rxgpu: HNSW index cache: an upper-level list blob has the wrong size");
+			}
+			levels[i] = int32_t(len / (s1 * 4));  // element_levels_[i] = size / size_links_per_element_ (:1278)
+			upperOff[i + 1] = upperOff[i] + levels[i];
+			const size_t at = upper.size();
+			upper.resize(at + len / 4);
+			std::memcpy(upper.data() + at, data, len);
+			for (int32_t lv = 0; lv < levels[i]; ++lv) {
+				upper[at + size_t(lv) * s1] &= 0xFFFFu;  // the count word carries flag bits
+			}
+		}
+		rxgpu_hnsw_graph g{};
+		g.n = n;
+		g.M = uint32_t(M);
+		g.maxM0 = m0;
+		g.maxlevel = int32_t(maxlevel);
+		g.enterpoint = uint32_t(enterpoint);
+		g.upper_slots = uint64_t(upperOff[n]);
+		g.level0 = level0.data();
+		g.levels = levels.data();
+		g.upper_offsets = upperOff.data();
+		g.upper = upper.empty() ? nullptr : upper.data();
+		if (int rc = rxgpu_hnsw_import(ix, &g)) {
+			return rc;
+		}
+		for (const uint32_t i : deleted) {
+			if (int rc = rxgpu_hnsw_mark_deleted(ix, labels[i])) {
+				return rc;
+			}
+		}
+		if (info) {
+			info->deleted = uint32_t(deleted.size());
+		}
+		return 0;
+	} catch (const std::bad_alloc&) {
+		return fail(RXGPU_ERR_SYSTEM, "rxgpu: out of host memory");
+	} catch (const std::exception& e) {  // the reader's callbacks may throw (corrupted blob, missing row)
+		return fail(RXGPU_ERR_PARAMS, std::string("rxgpu: HNSW index cache: ") + e.what());
+	}
+}
+
 // Incremental maintenance after the reference's inserter changed the host graph: HierarchicalNSWImpl::addPoint (hnswalg.h:1695-1852)
 // touches the new node's lists and the lists of the neighbours it was linked to (mutuallyConnectNewElement, :1070-1180); the adapter
 // hands over exactly those nodes.  Nothing else of the device copy moves: an upsert costs O(M) small copies, not a re-import.

@@ -9,8 +9,8 @@
 // available (tests/cpp/dropin_ft_check.cc does so in the authoring container).  INTEGRATION.md section 6 shows the patch.
 //
 // Covered on the device: query parts that are plain terms with their variant subterms (AND / OR / NOT), the preselect step, all three
-// BM25 variants, summationRanksByFieldsRatio, multi-word synonyms (with their suppressed subterms).  Phrases are NOT: Mergeable() says
-// so and the caller keeps ft::Merger for those queries (an explicit dispatch at the seam, not a fallback inside the library).
+// BM25 variants, summationRanksByFieldsRatio, multi-word synonyms (with their suppressed subterms), phrases.  The area / highlight
+// result types (MergeDataAreas) are not: the caller keeps ft::Merger for those (an explicit dispatch on the result type at the seam).
 #pragma once
 
 #include <cstdlib>
@@ -51,25 +51,27 @@ public:
 	GpuFtMerger& operator=(const GpuFtMerger&) = delete;
 	~GpuFtMerger() { rxgpu_ft_destroy(h_); }
 
-	// what the device path covers; everything else stays with ft::Merger (the caller dispatches)
-	static bool Mergeable(const QueryMergeData<IdCont>& q) noexcept {
-		for (const auto& qp : q.queryParts) {
-			if (!qp.IsTerm()) {
-				return false;
-			}
-		}
-		return true;
-	}
+	// what the device path covers: every QueryMergeData (terms, phrases, multi-word synonyms) whose result type is ft::MergeData; the
+	// area / highlight variants (MergeDataAreas<Area|AreaDebug>) stay with ft::Merger -- the caller dispatches on the result type
+	static bool Mergeable(const QueryMergeData<IdCont>&) noexcept { return true; }
 
 	MergeData Merge(QueryMergeData<IdCont>& q, RankSortType rankSortType, const FtMergeStatuses::Statuses& docsExcluded, const FTConfig& cfg) {
 		MergeData out;
-		if (!Mergeable(q)) {
-			throw std::logic_error("GpuFtMerger: phrases are merged by ft::Merger (see Mergeable())");
-		}
 		if (q.Empty() || totalDocs_ == 0) {
 			return out;  // Merger::Merge, mergerimpl.h:472-474
 		}
-		q.SortSubterms();  // mergerimpl.h:479 -- the same (unstable) sort on the same data; the library keeps this order
+		// mergerimpl.h:479 sorts the subterms AFTER the phrases were merged (Merger::init): plain and synonym terms are sorted here with
+		// the same (unstable) sort on the same data and the library keeps that order; phrase terms are handed over in their own order
+		for (auto& qp : q.queryParts) {
+			if (qp.IsTerm()) {
+				qp.SortSubterms();
+			}
+		}
+		for (auto& syn : q.synonyms) {
+			for (auto& term : syn.Terms()) {
+				term.SortSubterms();
+			}
+		}
 		std::vector<rxgpu_ft_field_config> fields(nfields_);
 		for (uint32_t f = 0; f < nfields_; ++f) {
 			const auto& fc = cfg.fieldsCfg[f];
@@ -108,7 +110,11 @@ public:
 		for (auto& syn : q.synonyms) {
 			nSynTerms += syn.NumTerms();
 		}
-		std::vector<TermArrays> arrays(q.queryParts.size() + nSynTerms);
+		size_t nQueryTerms = 0;
+		for (auto& qp : q.queryParts) {
+			nQueryTerms += qp.IsPhrase() ? qp.Phrase().NumTerms() : 1;
+		}
+		std::vector<TermArrays> arrays(nQueryTerms + nSynTerms);
 		size_t next = 0;
 		auto convert = [&](TermResults<IdCont>& tr) {
 			TermArrays& a = arrays[next++];
@@ -139,8 +145,20 @@ public:
 			return t;
 		};
 		std::vector<rxgpu_ft_term> terms;
-		terms.reserve(q.queryParts.size());
+		terms.reserve(arrays.size());
+		int32_t phraseNum = 0;
 		for (auto& qp : q.queryParts) {
+			if (qp.IsPhrase()) {  // the phrase's terms follow one another under one phrase number, like in the DSL
+				++phraseNum;
+				auto& ph = qp.Phrase();
+				for (size_t i = 0; i < ph.NumTerms(); ++i) {
+					rxgpu_ft_term t = convert(ph.Term(i));
+					t.phrase_num = phraseNum;
+					t.distance = int32_t(ph.Term(i).Distance());
+					terms.push_back(t);
+				}
+				continue;
+			}
 			TermArrays& a = arrays[next];
 			rxgpu_ft_term t = convert(qp.Term());
 			for (const size_t id : qp.SynonymsIds()) {

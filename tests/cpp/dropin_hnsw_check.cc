@@ -148,6 +148,65 @@ Results drive(reindexer::VectorMetric metric, size_t dim, size_t n, size_t k, si
 	MemReader r(w.tokens, rowsByPk);
 	loaded.LoadIndex(r);
 	search(loaded, false);
+	if constexpr (requires { map.DeviceImports(); }) {
+		// the same cache restored by the library itself, with NO host graph (rxgpu_hnsw_load_index_cache): the token callbacks sit on the
+		// same reader; the answers must equal those of the map restored through the reference's loader
+		MemReader r2(w.tokens, rowsByPk);
+		(void)r2.GetVarUInt();  // the quantisation header HierarchicalNSW::SaveIndex puts first (hnsw.cc:52-58)
+		rxgpu_hnsw_cache_reader cb{};
+		cb.ctx = &r2;
+		cb.get_var_uint = [](void* c) { return static_cast<MemReader*>(c)->GetVarUInt(); };
+		cb.get_var_int = [](void* c) { return static_cast<MemReader*>(c)->GetVarInt(); };
+		cb.get_vstring = [](void* c, const char** data, uint64_t* len) {
+			const std::string_view v = static_cast<MemReader*>(c)->GetVString();
+			*data = v.data();
+			*len = v.size();
+			return 0;
+		};
+		cb.read_pk_encoded_data = [](void* c, float* dest) { return uint64_t(static_cast<MemReader*>(c)->ReadPkEncodedData(dest)); };
+		rxgpu_index* ix = nullptr;
+		const auto m = metric == reindexer::VectorMetric::L2 ? RXGPU_L2 : metric == reindexer::VectorMetric::Cosine ? RXGPU_COS : RXGPU_IP;
+		if (rxgpu_index_create(&ix, m, uint32_t(dim), map.MaxElements(), 0, 0) != RXGPU_OK) {
+			std::printf("rxgpu_index_create: %s\n", rxgpu_last_error());
+			std::exit(3);
+		}
+		rxgpu_hnsw_cache_info info{};
+		if (rxgpu_hnsw_load_index_cache(ix, &cb, &info) != RXGPU_OK || info.count != map.CurrentElementCount() ||
+			info.deleted != map.DeletedCountUnsafe()) {
+			std::printf("rxgpu_hnsw_load_index_cache: %s (count %llu of %zu, deleted %u of %zu)\n", rxgpu_last_error(),
+						(unsigned long long)info.count, map.CurrentElementCount(), info.deleted, map.DeletedCountUnsafe());
+			std::exit(3);
+		}
+		const size_t first = out.size() - nq;  // the answers of `loaded`
+		size_t same = 0;
+		for (size_t qi = 0; qi < nq; ++qi) {
+			for (size_t c = 0; c < dim; ++c) {
+				q[c] = port_synth_value(179, qi * dim + c) + 0.6f * port_synth_value(178, (qi % 37) * dim + c);
+			}
+			const float* key = q.data();
+			if (metric == reindexer::VectorMetric::Cosine) {
+				(void)reindexer::ann::NormalizeCopyVector(q.data(), int32_t(dim), qn.data());
+				key = qn.data();
+			}
+			std::vector<float> d(k);
+			std::vector<uint64_t> l(k);
+			uint32_t cnt = 0;
+			if (rxgpu_hnsw_search_knn(ix, 1, key, uint32_t(k), uint32_t(ef), d.data(), l.data(), &cnt, nullptr) != RXGPU_OK) {
+				std::printf("search on the restored index: %s\n", rxgpu_last_error());
+				std::exit(3);
+			}
+			bool eq = cnt == out[first + qi].size();
+			for (uint32_t j = 0; eq && j < cnt; ++j) {
+				eq = l[j] == out[first + qi][j].second && d[j] == out[first + qi][j].first;
+			}
+			same += eq;
+		}
+		rxgpu_index_destroy(ix);
+		std::printf("  index cache restored by the library (no host graph): %zu of %zu answers bit-identical to the adapter's restored map\n", same, nq);
+		if (same != nq) {
+			std::exit(3);
+		}
+	}
 	return out;
 }
 

@@ -71,6 +71,63 @@ def add_random_synonyms(p, seed, nsyn=2, density=0.25, suppress=True):
     return p
 
 
+def corpus_problem(seed, total_docs=600, nfields=2, vocab=24, merge_limit=20000, removed_frac=0.0, excluded_frac=0.0, with_synonym=False):
+    """A problem built from an actual token corpus, so that PHRASES match: every document holds random words of a small vocabulary in
+    every field; posting lists are derived from it.  The query mixes one or two phrases (2-3 terms, distances 1-3, 1-2 variant subterms
+    per term, in the caller's -- unsorted -- order) with plain terms under OR / AND / NOT."""
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(4, 22, size=(total_docs, nfields))
+    lens[0] = 0
+    words = lens.astype(np.uint32)
+    removed = (rng.random(total_docs) < removed_frac).astype(np.uint8) if removed_frac else None
+    excluded = (rng.random(total_docs) < excluded_frac).astype(np.uint8) if excluded_frac else None
+    p = F.FtProblem(total_docs, words, removed=removed, excluded=excluded)
+    p.cfg["merge_limit"] = merge_limit
+    tokens = [[rng.integers(0, vocab, size=lens[d, f]) for f in range(nfields)] for d in range(total_docs)]
+    list_of_word = {}
+
+    def postings(w):
+        if w not in list_of_word:
+            docs, pos_lists = [], []
+            for d in range(1, total_docs):
+                pp = [(int(i), f) for f in range(nfields) for i in np.nonzero(tokens[d][f] == w)[0]]
+                if pp:
+                    docs.append(d)
+                    pos_lists.append(pp)
+            list_of_word[w] = p.add_list(docs, pos_lists)
+        return list_of_word[w]
+
+    def subterms(primary):
+        subs = [(postings(int(primary)), float(rng.choice([100.0, 90.0, 85.0])))]
+        if rng.random() < 0.5:  # a variant (typo / stem) of lower relevancy, possibly listed FIRST
+            v = (postings(int(rng.integers(0, vocab))), float(rng.choice([72.0, 65.0, 57.0])))
+            subs = [v] + subs if rng.random() < 0.5 else subs + [v]
+        return subs
+
+    nparts = int(rng.integers(1, 4))
+    phrase_num = 0
+    for part in range(nparts):
+        op = F.OP_OR if part == 0 else int(rng.choice([F.OP_OR, F.OP_OR, F.OP_AND, F.OP_NOT]))
+        fb = rng.choice([1.0, 0.5, 2.0], size=nfields).astype(np.float32) if nfields > 1 else np.ones(1, np.float32)
+        if part == 0 or rng.random() < 0.5:  # a phrase taken from a real document, so that it occurs
+            phrase_num += 1
+            d, f = int(rng.integers(1, total_docs)), int(rng.integers(0, nfields))
+            n = int(rng.integers(2, 4))
+            at = int(rng.integers(0, max(1, lens[d, f] - 2 * n)))
+            step = int(rng.integers(1, 3))
+            chosen = [int(tokens[d][f][min(at + k * step, lens[d, f] - 1)]) for k in range(n)]
+            for k, w in enumerate(chosen):
+                p.add_term(subterms(w), op=op, boost=float(rng.choice([1.0, 0.8])), term_len_boost=float(rng.choice([1.0, 0.9])),
+                           field_boosts=fb, phrase_num=phrase_num, distance=int(rng.integers(1, 4)) if k else 0)
+        else:
+            syn = ()
+            if with_synonym and op != F.OP_NOT:
+                syn = (p.add_synonym([dict(subterms=[(postings(int(rng.integers(0, vocab))), 45.0)], field_boosts=np.ones(nfields, np.float32))
+                                      for _ in range(2)]),)
+            p.add_term(subterms(int(rng.integers(0, vocab))), op=op, boost=1.0, term_len_boost=1.0, field_boosts=fb, synonym_ids=syn)
+    return p
+
+
 def assert_same_merge(a, b, rank_sort_type, ctx=""):
     """a, b: MERGE_INFO arrays.  RankAndID / IDOnly keep the merge order (deterministic); RankOnly / IDAndPositions are sorted by an
     unstable sort, so equal ranks compare as sets."""

@@ -5,7 +5,7 @@ import os
 
 import numpy as np
 import pytest
-from ft_helpers import add_random_synonyms, assert_same_merge, gpu_merge, load_golden_problem, random_problem
+from ft_helpers import add_random_synonyms, assert_same_merge, corpus_problem, gpu_merge, load_golden_problem, random_problem
 
 from oracle import ft_oracle as F
 
@@ -98,6 +98,29 @@ def test_multi_word_synonyms_match_reference():
             assert_same_merge(a, b, rst, ctx=f"seed {seed} rst {rst}")
         kept_by_syn += len(set(a["id"].tolist()) - set(F.ref_merge(plain)[0]["id"].tolist())) > 0
     assert kept_by_syn > 10 and preselects > 3
+
+
+@pytest.mark.skipif(not F.ref_available(), reason="oracle/_ref not built (the C port does not restate phrases)")
+def test_phrases_match_reference():
+    """PhraseMerger (phrasemerger.h:285-399, phrasemergerimpl.h:166-312) + Merger::mergePhrase (mergerimpl.h:41-90) on the device:
+    phrases drawn from a token corpus, 2-3 terms with distances 1-3 and variant subterms in the caller's order, mixed with plain terms
+    under OR / AND / NOT, with and without the merge-limit cut-off, removed / excluded documents, multi-word synonyms"""
+    nonempty = preselects = 0
+    for seed in range(70):
+        p = corpus_problem(seed, total_docs=300 + 17 * seed, nfields=1 + seed % 3, merge_limit=(30 if seed % 4 == 1 else 20000),
+                           removed_frac=0.05 * (seed % 2), excluded_frac=0.05 * (seed % 3 == 0), with_synonym=seed % 5 == 0)
+        for rst in (F.RANK_AND_ID, F.RANK_ONLY):
+            a, _ = F.ref_merge(p, rst)
+            b, st = gpu_merge(p, rst)
+            preselects += st["preselected"]
+            assert_same_merge(a, b, rst, ctx=f"seed {seed} rst {rst}")
+        nonempty += len(a) > 0
+    assert nonempty > 60 and preselects > 3
+    import reindexer_b200 as rx
+    q = corpus_problem(3)
+    q.terms = [dict(q.terms[0], phrase_num=9)]  # a one-term phrase
+    with pytest.raises(rx.RxGpuError):
+        gpu_merge(q)
 
 
 def test_empty_and_degenerate_queries():
