@@ -235,6 +235,8 @@ __global__ void ft_not_clear(DevList l, uint32_t* mask) {
 		atomicAnd(&mask[d >> 5], ~(1u << (d & 31)));
 	}
 }
+// restrictingMask_.PopCount() > cfg_->mergeLimit (mergerimpl.h:486-489), decided where the count lives
+__global__ void ft_decide_preselect(const unsigned long long* popc, uint32_t merge_limit, uint32_t* flag) { *flag = *popc > merge_limit ? 1u : 0u; }
 __global__ void ft_popcount(const uint32_t* mask, uint32_t words, unsigned long long* out) {
 	unsigned long long c = 0;
 	for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += gridDim.x * blockDim.x) {
@@ -248,7 +250,10 @@ __global__ void ft_popcount(const uint32_t* mask, uint32_t words, unsigned long 
 	}
 }
 // calcTermScores (mergerimpl.h:289-324): one pass per subterm; a document scores once per term (tmask)
-__global__ void ft_score_pass(DevList l, TermParams t, int all_same, const uint32_t* mask, uint32_t* tmask, uint16_t* score) {
+__global__ void ft_score_pass(DevList l, TermParams t, int all_same, const uint32_t* mask, uint32_t* tmask, uint16_t* score, const uint32_t* enabled) {
+	if (enabled && !*enabled) {  // preselect decided on the device (ft_decide_preselect): the host enqueues the whole query ahead
+		return;
+	}
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < l.ndocs; i += gridDim.x * blockDim.x) {
 		const uint32_t d = l.doc_ids[i];
 		const uint32_t bit = 1u << (d & 31);
@@ -305,12 +310,16 @@ __device__ __forceinline__ Scores32 load_scores32(const uint16_t* score, uint32_
 // shared memory and flushes them once; only scores >= 8192 go to the global bins directly.
 constexpr uint32_t kFtHistSmemBins = 8192;
 __global__ void __launch_bounds__(kFtThreads) ft_hist(uint16_t* score, const uint32_t* mask, const uint8_t* removed, uint32_t words,
-													  unsigned long long* hist) {
+													  unsigned long long* hist, uint32_t* max_score, const uint32_t* enabled) {
+	if (enabled && !*enabled) {  // preselect decided on the device (ft_decide_preselect): the host enqueues the whole query ahead
+		return;
+	}
 	__shared__ uint32_t s_hist[kFtHistSmemBins];
 	for (uint32_t i = threadIdx.x; i < kFtHistSmemBins; i += blockDim.x) {
 		s_hist[i] = 0;
 	}
 	__syncthreads();
+	uint32_t top = 0;  // the highest score seen: ft_pick_threshold only walks the bins below it
 	for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += gridDim.x * blockDim.x) {
 		const Scores32 sc = load_scores32(score, w);
 		if (!sc.any()) {
@@ -326,11 +335,17 @@ __global__ void __launch_bounds__(kFtThreads) ft_hist(uint16_t* score, const uin
 					score[d] = 0;
 				} else if (s < kFtHistSmemBins) {
 					atomicAdd(&s_hist[s], 1u);
+					top = max(top, s);
 				} else {
 					atomicAdd(&hist[s], 1ull);
+					top = max(top, s);
 				}
 			}
 		}
+	}
+	top = __reduce_max_sync(0xffffffffu, top);
+	if ((threadIdx.x & 31) == 0 && top) {
+		atomicMax(max_score, top);
 	}
 	__syncthreads();
 	for (uint32_t i = threadIdx.x; i < kFtHistSmemBins; i += blockDim.x) {
@@ -342,18 +357,25 @@ __global__ void __launch_bounds__(kFtThreads) ft_hist(uint16_t* score, const uin
 // threshold of the counting sort (mergerimpl.h:425-446), on the device so the merge does not stop for the host:
 //   A(sc) = number of docs with score > sc;  minScore = the smallest sc >= 1 with A(sc) < maxMerged (sc = 65535 always qualifies);
 //   minScoreDocs = maxMerged - A(minScore).   thr[0] = minScore, thr[1] = minScoreDocs.  One block of 1024 threads, 64 bins each.
-__global__ void __launch_bounds__(1024) ft_pick_threshold(const unsigned long long* hist, uint32_t max_merged, uint32_t* thr) {
-	// thread r owns the 64 scores [hi - 63, hi], hi = 65535 - 64 r (thread 0 the highest), cached in registers: one read of the
-	// histogram; A(hi) = docs in the bins of the threads before r = an exclusive prefix sum over r
+__global__ void __launch_bounds__(1024) ft_pick_threshold(const unsigned long long* hist, uint32_t max_merged, const uint32_t* max_score,
+														  uint32_t* thr, const uint32_t* enabled) {
+	if (enabled && !*enabled) {  // preselect decided on the device (ft_decide_preselect): the host enqueues the whole query ahead
+		return;
+	}
+	// thread r owns the 64 scores [hi - 63, hi], hi = top - 64 r with top = the highest score present rounded up to 64 k + 63 (thread 0
+	// the highest), cached in registers: one read of the occupied part of the histogram -- a few hundred bins for a handful of terms,
+	// not all 65 536; A(hi) = docs in the bins of the threads before r = an exclusive prefix sum over r
 	__shared__ unsigned long long s_scan[1024];
 	__shared__ uint32_t s_min;
 	const uint32_t r = threadIdx.x;
-	const uint32_t hi = 65535u - 64u * r;
+	const uint32_t top = min(65535u, *max_score | 63u);
+	const bool live = 64u * r <= top;  // hi >= 63
+	const uint32_t hi = live ? top - 64u * r : 63u;
 	uint32_t bins[64];  // bins[i] = hist[hi - i]; a bin holds at most total_docs < 2^32 documents
 	unsigned long long mine = 0;
 #pragma unroll
 	for (int i = 0; i < 64; ++i) {
-		bins[i] = uint32_t(hist[hi - i]);
+		bins[i] = live ? uint32_t(hist[hi - i]) : 0u;
 		mine += bins[i];
 	}
 	s_scan[r] = mine;
@@ -373,7 +395,7 @@ __global__ void __launch_bounds__(1024) ft_pick_threshold(const unsigned long lo
 #pragma unroll
 	for (int i = 0; i < 64; ++i) {
 		const uint32_t sc = hi - i;
-		if (sc >= 1 && a < max_merged) {
+		if (live && sc >= 1 && a < max_merged) {
 			local = sc;
 		}
 		a += bins[i];
@@ -383,7 +405,7 @@ __global__ void __launch_bounds__(1024) ft_pick_threshold(const unsigned long lo
 	}
 	__syncthreads();
 	const uint32_t ms = s_min;
-	if ((65535u - ms) / 64u == r) {
+	if (live && ms <= top && (top - ms) / 64u == r) {
 		a = above;
 #pragma unroll
 		for (int i = 0; i < 64; ++i) {
@@ -413,7 +435,10 @@ __device__ __forceinline__ void ft_classify(const Scores32& sc, uint32_t m, uint
 	gt &= m;
 }
 __global__ void __launch_bounds__(kFtThreads) ft_thresh_count(const uint16_t* score, const uint32_t* mask, uint32_t words, const uint32_t* thr,
-															  uint32_t* block_counts) {
+															  uint32_t* block_counts, const uint32_t* enabled) {
+	if (enabled && !*enabled) {  // preselect decided on the device (ft_decide_preselect): the host enqueues the whole query ahead
+		return;
+	}
 	__shared__ uint32_t s_cnt;
 	if (threadIdx.x == 0) {
 		s_cnt = 0;
@@ -443,7 +468,10 @@ __global__ void __launch_bounds__(kFtThreads) ft_thresh_count(const uint16_t* sc
 	}
 }
 __global__ void __launch_bounds__(kFtThreads) ft_thresh_apply(const uint16_t* score, uint32_t* mask, uint32_t words, const uint32_t* thr,
-															  const uint32_t* block_counts) {
+															  const uint32_t* block_counts, const uint32_t* enabled) {
+	if (enabled && !*enabled) {  // preselect decided on the device (ft_decide_preselect): the host enqueues the whole query ahead
+		return;
+	}
 	__shared__ uint32_t s_warp[kFtThreads / 32];
 	__shared__ uint32_t s_base;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -588,7 +616,10 @@ __global__ void ft_switch(MergeState st) {
 // one subterm pass of mergeTerm / mergeSimple: rank every posting, update documents already merged in place, flag new ones
 __global__ void ft_rank_pass(DevList l, TermParams t, MergeState st, const uint32_t* words, const float* avg, const uint8_t* removed,
 							 int check_removed, int simple, uint32_t sentinel, uint16_t qp_idx, float* tmp_rank, uint8_t* tmp_field,
-							 uint32_t* block_counts) {
+							 uint32_t* block_counts, const uint32_t* preselected) {
+	if (preselected && *preselected) {
+		check_removed = 0;  // needToCheckRemoved_ = false after preselectMostRelevantDocs (mergerimpl.h:463)
+	}
 	__shared__ uint32_t s_cnt;
 	if (threadIdx.x == 0) {
 		s_cnt = 0;
@@ -694,7 +725,11 @@ __global__ void ft_mask_or(uint32_t* mask, const uint32_t* other, uint32_t words
 }
 // a suppressed subterm of a multi-word synonym (QueryMergeData::SupressDuplicatesInSynonyms, querymergedata.h:221-241): it only counts
 // towards termsCounter of documents that are already merged (mergerimpl.h:144-151)
-__global__ void ft_suppressed_pass(DevList l, MergeState st, const uint8_t* removed, int check_removed, uint32_t sentinel, uint16_t qp_idx) {
+__global__ void ft_suppressed_pass(DevList l, MergeState st, const uint8_t* removed, int check_removed, uint32_t sentinel, uint16_t qp_idx,
+								   const uint32_t* preselected) {
+	if (preselected && *preselected) {
+		check_removed = 0;
+	}
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= l.ndocs) {
 		return;
@@ -934,7 +969,10 @@ __global__ void ft_phrase_bits(PhraseState ps, uint32_t* bits, int set) {
 	}
 }
 // GetMergedDocsScore (phrasemerger.h:331-338)
-__global__ void ft_phrase_score(PhraseState ps, uint16_t* score, uint32_t phrase_proc) {
+__global__ void ft_phrase_score(PhraseState ps, uint16_t* score, uint32_t phrase_proc, const uint32_t* enabled) {
+	if (enabled && !*enabled) {  // preselect decided on the device (ft_decide_preselect): the host enqueues the whole query ahead
+		return;
+	}
 	const uint32_t n = min(*ps.n, ps.max_merged);
 	for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
 		if (ps.proc[slot] > 0.f) {
@@ -1781,7 +1819,7 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 	RX_CUDA(ft->h_id.ensure(maxMerged));
 	RX_CUDA(ft->h_proc.ensure(maxMerged));
 	RX_CUDA(ft->h_field.ensure(maxMerged));
-	RX_CUDA(ft->h_n.ensure(1));
+	RX_CUDA(ft->h_n.ensure(2));
 	RX_CUDA(cudaEventRecord(e0, st));
 	RX_CUDA(cudaMemsetAsync(ft->scalar_u32.p, 0, 32, st));
 	if (!trivial) {  // idoffsets_: every merge leaves the table clean again (ft_reset_idoff), so the 4 N byte fill runs only once
@@ -1944,6 +1982,7 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 	}
 
 	int checkRemoved = 1;
+	const uint32_t* preselFlag = nullptr;
 	if (!simple) {
 		// buildRestrictingBitmask (mergerimpl.h:326-384)
 		std::vector<uint8_t> synMaskDone(nsyn, 0);
@@ -2050,18 +2089,16 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 		}
 		const uint64_t est = std::min<uint64_t>(std::min(estOr, estAnd), N);
 		bool preselect = est > cfg->merge_limit && N > cfg->merge_limit && !std::getenv("REINDEXER_NO_2PHASE_FT_MERGE");
+		uint32_t* d_presel = ft->scalar_u32.p + 6;  // [6] 1 when preselectMostRelevantDocs runs
 		if (preselect) {
 			RX_CUDA(cudaMemsetAsync(ft->popc.p, 0, 8, st));
 			ft_popcount<<<gridFor(mwords, sm), kFtThreads, 0, st>>>(ft->mask.p, mwords, ft->popc.p);
-			g_ft_stats.launches++;
-			unsigned long long pop = 0;
-			RX_CUDA(cudaMemcpyAsync(&pop, ft->popc.p, 8, cudaMemcpyDeviceToHost, st));
-			RX_CUDA(cudaStreamSynchronize(st));
-			preselect = pop > cfg->merge_limit;
+			ft_decide_preselect<<<1, 1, 0, st>>>(ft->popc.p, cfg->merge_limit, d_presel);
+			g_ft_stats.launches += 2;
+			preselFlag = d_presel;  // the last condition is known on the device only: the kernels below test it, the host does not wait
 		}
 		if (preselect) {
 			// preselectMostRelevantDocs (mergerimpl.h:386-464)
-			g_ft_stats.preselected = 1;
 			RX_CUDA(ft->score.ensure(size_t(mwords) * 32));
 			RX_CUDA(ft->hist.ensure(65536));
 			RX_CUDA(cudaMemsetAsync(ft->score.p, 0, size_t(mwords) * 64, st));
@@ -2074,7 +2111,7 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 				if (t < nterms && inPhrase[t]) {  // GetMergedDocsScore (mergerimpl.h:408-409)
 					const PhraseState& ps = pstates[phraseOf[t]];
 					ft_phrase_score<<<gridFor(std::max<uint32_t>(ps.max_merged, 1), sm), kFtThreads, 0, st>>>(ps, ft->score.p,
-																											   ft->phrases[phraseOf[t]]->phrase_proc);
+																											   ft->phrases[phraseOf[t]]->phrase_proc, preselFlag);
 					g_ft_stats.launches++;
 					continue;
 				}
@@ -2087,7 +2124,7 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 					const DevList& l = ft->lists[sub.list];
 					if (l.ndocs) {
 						ft_score_pass<<<gridFor(l.ndocs, sm), kFtThreads, 0, st>>>(l, termParams(t, sub, l), allSame, ft->mask.p, ft->tmask.p,
-																					ft->score.p);
+																					ft->score.p, preselFlag);
 						g_ft_stats.launches++;
 						g_ft_stats.postings_scanned += l.ndocs;
 						g_ft_stats.algorithmic_bytes += bytesOfPass(l);
@@ -2097,13 +2134,12 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 			const unsigned pg = unsigned(sm) * 4;  // persistent grid of the per-document passes
 			uint32_t* d_thr = ft->scalar_u32.p + 2;  // [2] minScore, [3] minScoreDocs
 			RX_CUDA(ft->block_counts.ensure(pg));
-			ft_hist<<<pg, kFtThreads, 0, st>>>(ft->score.p, ft->mask.p, ft->has_removed ? ft->removed.p : nullptr, mwords, ft->hist.p);
-			ft_pick_threshold<<<1, 1024, 0, st>>>(ft->hist.p, maxMerged, d_thr);
-			ft_thresh_count<<<pg, kFtThreads, 0, st>>>(ft->score.p, ft->mask.p, mwords, d_thr, ft->block_counts.p);
-			ft_thresh_apply<<<pg, kFtThreads, 0, st>>>(ft->score.p, ft->mask.p, mwords, d_thr, ft->block_counts.p);
+			ft_hist<<<pg, kFtThreads, 0, st>>>(ft->score.p, ft->mask.p, ft->has_removed ? ft->removed.p : nullptr, mwords, ft->hist.p, ft->scalar_u32.p + 5, preselFlag);
+			ft_pick_threshold<<<1, 1024, 0, st>>>(ft->hist.p, maxMerged, ft->scalar_u32.p + 5, d_thr, preselFlag);
+			ft_thresh_count<<<pg, kFtThreads, 0, st>>>(ft->score.p, ft->mask.p, mwords, d_thr, ft->block_counts.p, preselFlag);
+			ft_thresh_apply<<<pg, kFtThreads, 0, st>>>(ft->score.p, ft->mask.p, mwords, d_thr, ft->block_counts.p, preselFlag);
 			g_ft_stats.launches += 4;
 			g_ft_stats.algorithmic_bytes += uint64_t(N) * 6;
-			checkRemoved = 0;  // needToCheckRemoved_ = false (:463)
 		}
 	}
 
@@ -2154,14 +2190,14 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 			}
 			const unsigned lb = (l.ndocs + kFtThreads - 1) / kFtThreads;
 			if (sub.suppressed) {
-				ft_suppressed_pass<<<lb, kFtThreads, 0, st>>>(l, ms, d_removed, checkRemoved, kNoSlot, qpIdx);
+				ft_suppressed_pass<<<lb, kFtThreads, 0, st>>>(l, ms, d_removed, checkRemoved, kNoSlot, qpIdx, preselFlag);
 				g_ft_stats.launches++;
 				g_ft_stats.postings_scanned += l.ndocs;
 				g_ft_stats.algorithmic_bytes += uint64_t(l.ndocs) * 8;
 				continue;
 			}
 			ft_rank_pass<<<lb, kFtThreads, 0, st>>>(l, termParams(t, sub, l), ms, d_words, ft->avg.p, d_removed, checkRemoved, simple ? 1 : 0,
-													kNoSlot, qpIdx, ft->tmp_rank.p, ft->tmp_field.p, ft->block_counts.p);
+													kNoSlot, qpIdx, ft->tmp_rank.p, ft->tmp_field.p, ft->block_counts.p, preselFlag);
 			ft_scan_blocks<<<1, 1024, 0, st>>>(ft->block_counts.p, lb, d_total_new);
 			ft_assign<<<lb, kFtThreads, 0, st>>>(l, ms, simple ? 1 : 0, maxMerged, qpIdx, ft->tmp_rank.p, ft->tmp_field.p, ft->block_counts.p);
 			ft_bump_count<<<1, 1, 0, st>>>(ms.n_docs, d_total_new, maxMerged);
@@ -2224,6 +2260,7 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 		const bool noSync = capBound <= (1u << 20);
 		if (!noSync) {
 			RX_CUDA(cudaMemcpyAsync(ft->h_post.p, ms.n_docs, 4, cudaMemcpyDeviceToHost, st));
+			RX_CUDA(cudaMemcpyAsync(ft->h_post.p + 1, ft->scalar_u32.p + 6, 4, cudaMemcpyDeviceToHost, st));
 			RX_CUDA(cudaStreamSynchronize(st));
 			nMerged = ft->h_post.p[0];
 			if (nMerged) {
@@ -2260,6 +2297,7 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 				RX_CUDA(cudaMemcpyAsync(ft->h_keys.p, ft->post_keys_sorted.p, want * 8, cudaMemcpyDeviceToHost, st));
 			}
 			RX_CUDA(cudaMemcpyAsync(ft->h_post.p, ft->post_scalars.p + 1, 4, cudaMemcpyDeviceToHost, st));
+			RX_CUDA(cudaMemcpyAsync(ft->h_post.p + 1, ft->scalar_u32.p + 6, 4, cudaMemcpyDeviceToHost, st));
 			RX_CUDA(cudaStreamSynchronize(st));
 			rowsTotal = ft->h_post.p[0];
 		}
@@ -2273,6 +2311,7 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 		}
 		RX_CUDA(cudaEventElapsedTime(&g_ft_stats.device_ms, e0, e1));
 		ft->idoff_clean = !trivial;
+		g_ft_stats.preselected = preselFlag ? ft->h_post.p[1] : 0;
 		for (uint64_t i = 0; i < nout; ++i) {
 			const unsigned long long k = ft->h_keys.p[i];
 			if (rankAndId) {
@@ -2289,6 +2328,7 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 	RX_CUDA(cudaEventRecord(e1, st));
 	// the merged documents (<= merge_limit entries, 9 bytes each) come back in full: their number is not known before the copy
 	RX_CUDA(cudaMemcpyAsync(ft->h_n.p, ms.n_docs, 4, cudaMemcpyDeviceToHost, st));
+	RX_CUDA(cudaMemcpyAsync(ft->h_n.p + 1, ft->scalar_u32.p + 6, 4, cudaMemcpyDeviceToHost, st));
 	RX_CUDA(cudaMemcpyAsync(ft->h_id.p, ms.md_id, size_t(maxMerged) * 4, cudaMemcpyDeviceToHost, st));
 	RX_CUDA(cudaMemcpyAsync(ft->h_proc.p, ms.md_proc, size_t(maxMerged) * 4, cudaMemcpyDeviceToHost, st));
 	RX_CUDA(cudaMemcpyAsync(ft->h_field.p, ms.md_field, size_t(maxMerged), cudaMemcpyDeviceToHost, st));
@@ -2296,6 +2336,7 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 	RX_CUDA(cudaEventElapsedTime(&g_ft_stats.device_ms, e0, e1));
 	ft->idoff_clean = !trivial;
 	const uint32_t n = ft->h_n.p[0];
+	g_ft_stats.preselected = preselFlag ? ft->h_n.p[1] : 0;
 
 	// postProcessResults (merger.h:111-155) on the host: <= merge_limit entries
 	try {
