@@ -198,7 +198,7 @@ __device__ __forceinline__ void warp_dists(const HnswArgs& a, const float4* sq4,
 }
 
 template <bool kIsL2>
-__global__ void __launch_bounds__(kHnswThreads) hnsw_search_kernel(const HnswArgs a) {
+__global__ void __launch_bounds__(kHnswThreads, 8) hnsw_search_kernel(const HnswArgs a) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
