@@ -120,7 +120,8 @@ class ClockSampler:
 
     def start(self):
         q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,"
+             "enforced.power.limit")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50", "-i",
                                           str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -143,7 +144,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        sm, smax, reasons, watts, limit = [], [], set(), [], None
         inside = [ln for (ts, ln) in self.lines if t_begin is None or (t_begin <= ts <= t_end + 0.2)]
         window = "timed region"
         if not inside:  # region shorter than one sampling period: report the samples under the same load (warm-up + region)
@@ -160,8 +161,14 @@ class ClockSampler:
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
+            try:  # board power next to its enforced limit: the filter kernel runs AT the limit, which is what bounds it
+                watts.append(float(f[3]))
+                limit = float(f[9]) if len(f) > 9 else limit
+            except ValueError:
+                pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm), "window": window}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window,
+                "power_w": float(np.median(watts)) if watts else None, "power_limit_w": limit}
 
 
 # ----------------------------------------------------------------------------------------------------------------- CPU arm
@@ -277,7 +284,7 @@ def roofline_record(stats_sum, ms_total, rows, tc_used, qt, nlaunch_timed, scan_
     peaks_all = load_peaks()
     if tc_used:  # dominant kernel = the tensor-core filter: bf16 shadow rows + row norms + the resident query block, per launch
         per_launch_bytes = rows * DIM * 2 + rows * 8 + qt * DIM * 2
-        kernel = "knn_tc_filter_k" if stats_sum.get("tc_kernel") == 3 else "knn_tc_filter_q"
+        kernel = {5: "knn_tc_filter_p"}.get(stats_sum.get("tc_kernel"), "knn_tc_filter_q")
     else:
         per_launch_bytes = alg_bytes / max(passes, 1)
         kernel = "knn_scan_warp"
@@ -564,7 +571,7 @@ def run_ours(args):
         value = world * NQ / (ms_per_step / 1000.0)
         e2e_value = world * NQ / (e2e_s / args.steps)
         roofline = roofline_record(main_stats, ms_total, rows, tc_used, qt, scan_launches, scan_ms, alg_bytes, passes)
-        kernel_name = {3: "knn_tc_filter_k (tcgen05 bf16 filter, K-split query block in TMEM + smem, UMMA N=128, certified bound) + knn_rerank (exact fp32)",
+        kernel_name = {5: "knn_tc_filter_p (tcgen05 cta_group::2 bf16 filter: CTA pairs, queries in TMEM, half a row tile per SM, certified bound) + knn_rerank (exact fp32)",
                        2: "knn_tc_filter_q (tcgen05 bf16 filter, queries in TMEM, certified bound) + knn_rerank (exact fp32)",
                        1: "knn_tc_filter (tcgen05 bf16 filter, queries in shared memory) + knn_rerank (exact fp32)"}.get(
             main_stats.get("tc_kernel") if tc_used else 0, "knn_scan_warp (fp32 FMA, fused top-k)")
@@ -639,7 +646,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default 10M = BASELINE config)")
     ap.add_argument("--query-tile", type=int, default=0)
-    ap.add_argument("--tc", type=int, default=0, help="tensor-core filter: 0 auto, 1 on, 2 off (exact fp32 scan only), 3..8 kernel variants")
+    ap.add_argument("--tc", type=int, default=0, help="tensor-core filter: 0 auto, 1 on, 2 off (exact fp32 scan only), 3..6, 9, 14..16 kernel variants")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sub", action="store_true", help="skip the sub-records of the other BASELINE configs")
     ap.add_argument("--quick-sub", action="store_true", help="small sub-record sizes (smoke)")

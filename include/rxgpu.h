@@ -457,16 +457,16 @@ typedef struct {
 	uint32_t tc_fallbacks;      /* queries whose candidate list overflowed and were answered by the exact scan */
 	uint64_t tc_candidates;     /* rows re-ranked exactly */
 	uint32_t tc_cluster;        /* CTAs per cluster in the filter kernel (row tiles are TMA-multicast inside a cluster) */
-	uint32_t tc_kernel;         /* 1 = knn_tc_filter (queries in shared memory), 2 = knn_tc_filter_q (queries in TMEM), 3 = knn_tc_filter_k
-								 * (K-split query block: TMEM + shared memory, UMMA N = 128) */
+	uint32_t tc_kernel;         /* 1 = knn_tc_filter (queries in shared memory), 2 = knn_tc_filter_q (queries in TMEM), 5 = knn_tc_filter_p
+								 * (CTA pairs multiply as one: tcgen05 cta_group::2, UMMA M = 256, N = 128) */
 } rxgpu_search_stats;
 void rxgpu_last_search_stats(rxgpu_search_stats* out);
 /* large query batches: bf16 tensor-core filter + exact fp32 re-rank (results identical to the exact scan).
  * mode 0 = automatic (batches >= 64 queries on >= 100k rows, k <= 15), 1 = whenever possible, 2 = never;
- * 3..9 force kernel variants for tests/benchmarks (all give the same bits): 3 / 4 = first-generation kernel (queries in shared
- * memory) with 1 CTA / a CTA pair per row tile; 5 / 6 = knn_tc_filter_q (query block in TMEM, accumulators of 64 rows; the default)
- * with single CTAs / clusters of up to 4; 7 / 8 = knn_tc_filter_k (K-split query block, accumulators of 128 rows) with single CTAs /
- * clusters of up to 4; 9 = knn_tc_filter_q with clusters of up to 8.  DESIGN.md section 9 has the measurements. */
+ * the other values force kernel variants for tests/benchmarks (all give the same bits): 3 / 4 = first-generation kernel (queries in
+ * shared memory) with 1 CTA / a CTA pair per row tile; 5 / 6 / 9 = knn_tc_filter_q (query block in TMEM, accumulators of 64 rows;
+ * the default) with single CTAs / clusters of up to 4 / up to 8; 14 / 15 / 16 = knn_tc_filter_p (CTA pairs multiply as one,
+ * cta_group::2, every SM stages half a 128-row tile) with clusters of up to 4 / 2 / 8 CTAs.  DESIGN.md section 9 has the measurements. */
 int rxgpu_set_tensor_core_filter(rxgpu_index*, int mode);
 /* process-wide switch: bracket every scan-kernel launch with CUDA events (used by bench.py for the roofline figure) */
 int rxgpu_set_profile(int on);

@@ -22,7 +22,7 @@
 #include "knn_scan.cuh"
 #include "knn_tc.cuh"
 #include "knn_tc_q.cuh"
-#include "knn_tc_k.cuh"
+#include "knn_tc_p.cuh"
 
 using namespace rxgpu;
 
@@ -326,16 +326,18 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 	g_stats.launches += 2;
 	const uint32_t ntiles = uint32_t((ix->size + kTcTileRows - 1) / kTcTileRows);
 	bool launched = false;
-	if ((ix->tc_variant == 0 || ix->tc_variant == 7) && kchunks <= kTqMaxKchunks) {
-		// query block in tensor memory, deep TMA ring, row tiles multicast to a cluster of up to 4 CTAs.  Default: knn_tc_filter_q (whole
-		// block in TMEM, accumulators of 64 rows; measured fastest); tc_variant 7: knn_tc_filter_k (K-split query block, accumulators of 128 rows)
+	if ((ix->tc_variant == 0 || ix->tc_variant == 14) && kchunks <= kTqMaxKchunks) {
+		// query block in tensor memory, deep TMA ring, row tiles multicast inside a cluster.  tc_variant 0: knn_tc_filter_q (every CTA
+		// multiplies on its own, two accumulators of 64 rows; default); 14: knn_tc_filter_p (CTA pairs multiply as one, cta_group::2, every
+		// SM stages half a 128-row tile, one accumulator).  Both run at the board's power limit and land on the same time.
 		using TqKernel = void (*)(TqArgs);
-		const bool ksplit = ix->tc_variant == 7;
-		const TqKernel kernels[4] = {ksplit ? knn_tc_filter_k<1> : knn_tc_filter_q<1>, ksplit ? knn_tc_filter_k<2> : knn_tc_filter_q<2>,
-									 ksplit ? knn_tc_filter_k<4> : knn_tc_filter_q<4>, ksplit ? knn_tc_filter_k<4> : knn_tc_filter_q<8>};
+		const bool pairs = ix->tc_variant == 14;
+		const TqKernel kernels[4] = {pairs ? knn_tc_filter_p<2> : knn_tc_filter_q<1>, pairs ? knn_tc_filter_p<2> : knn_tc_filter_q<2>,
+									 pairs ? knn_tc_filter_p<4> : knn_tc_filter_q<4>, pairs ? knn_tc_filter_p<8> : knn_tc_filter_q<8>};
 		auto kernelOf = [&](int c) { return kernels[c == 8 ? 3 : (c == 4 ? 2 : (c == 2 ? 1 : 0))]; };
-		const uint32_t tileRows = ksplit ? kTkTileRows : kTqTileRows;
-		auto smemOf = [&](uint32_t st) { return ksplit ? tk_smem_bytes(st) : tq_smem_bytes(st); };
+		const uint32_t tileRows = pairs ? kTpTileRows : kTqTileRows;
+		const unsigned threads = pairs ? kTpThreads : kTqThreads;
+		auto smemOf = [&](uint32_t st) { return pairs ? tp_smem_bytes(st) : tq_smem_bytes(st); };
 		const uint32_t qblocks = (nq + kTqQueries - 1) / kTqQueries;
 		uint32_t stages = 2;
 		while (smemOf(stages + 1) <= kTcSmemLimit && stages < 64) {
@@ -348,13 +350,16 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 		// a cluster of C CTAs reads every row tile from HBM once for C x 128 queries (TMA multicast)
 		const uint32_t clusterMax = ix->tc_cluster_max ? ix->tc_cluster_max : 4u;  // mode 9: up to 8 (one launch serves 1024 queries)
 		int cluster = qblocks >= 5 ? 8 : (qblocks >= 3 ? 4 : (qblocks == 2 ? 2 : 1));
-		cluster = std::min<int>(cluster, int(ksplit ? std::min(clusterMax, 4u) : clusterMax));
+		cluster = std::min<int>(cluster, int(clusterMax));
+		if (pairs) {
+			cluster = std::max(cluster, 2);  // whole CTA pairs (a second CTA without queries multiplies zeros)
+		}
 		const uint32_t qtiles = uint32_t((ix->size + tileRows - 1) / tileRows);
 		unsigned grid = 0;
 		for (;;) {  // how many clusters of this size can be resident at once (GPC boundaries strand SMs for size 4)
 			cudaLaunchConfig_t cfg{};
 			cfg.gridDim = dim3(unsigned(ix->sm_count) / cluster * cluster);
-			cfg.blockDim = dim3(ksplit ? kTkThreads : kTqThreads);
+			cfg.blockDim = dim3(threads);
 			cfg.dynamicSmemBytes = smem;
 			cudaLaunchAttribute attr[1];
 			attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -370,7 +375,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 				break;
 			}
 			cudaGetLastError();
-			if (cluster == 1) {
+			if (cluster == (pairs ? 2 : 1)) {
 				return fail(RXGPU_ERR_SYSTEM, "rxgpu: tensor-core filter kernel cannot be made resident");
 			}
 			cluster /= 2;
@@ -421,7 +426,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			}
 			cudaLaunchConfig_t cfg{};
 			cfg.gridDim = dim3(grid);
-			cfg.blockDim = dim3(ksplit ? kTkThreads : kTqThreads);
+			cfg.blockDim = dim3(threads);
 			cfg.dynamicSmemBytes = smem;
 			cfg.stream = st;
 			cudaLaunchAttribute attr[1];
@@ -454,7 +459,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			}
 		}
 		g_stats.tc_cluster = uint32_t(cluster);
-		g_stats.tc_kernel = ksplit ? 3 : 2;
+		g_stats.tc_kernel = pairs ? 5 : 2;
 		g_stats.query_tile = uint32_t(kTqQueries * cluster);
 		g_stats.algorithmic_bytes += uint64_t((qblocks + cluster - 1) / cluster) * (uint64_t(ix->size) * pitchBf * 2 + uint64_t(ix->size) * 4) +
 									 uint64_t(nq) * pitchBf * 2;
@@ -1045,12 +1050,12 @@ int rxgpu_set_query_tile(rxgpu_index* ix, uint32_t qt) {
 	return 0;
 }
 int rxgpu_set_tensor_core_filter(rxgpu_index* ix, int mode) {
-	if (!ix || mode < 0 || mode > 9) {
-		return fail(RXGPU_ERR_PARAMS, "rxgpu: tensor-core filter mode must be in 0..9");
+	if (!ix || mode < 0 || mode > 16 || mode == 7 || mode == 8 || (mode >= 10 && mode <= 13)) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: tensor-core filter mode must be 0..6, 9 or 14..16");
 	}
 	ix->tc_mode = uint32_t(mode >= 3 ? 1 : mode);
-	ix->tc_variant = (mode == 3 || mode == 4) ? uint32_t(mode) : ((mode == 7 || mode == 8) ? 7u : 0u);
-	ix->tc_cluster_max = (mode == 5 || mode == 7) ? 1u : ((mode == 6 || mode == 8) ? 4u : (mode == 9 ? 8u : 0u));
+	ix->tc_variant = (mode == 3 || mode == 4) ? uint32_t(mode) : (mode >= 14 ? 14u : 0u);
+	ix->tc_cluster_max = mode == 5 ? 1u : ((mode == 6 || mode == 14) ? 4u : ((mode == 9 || mode == 16) ? 8u : (mode == 15 ? 2u : 0u)));
 	return 0;
 }
 int rxgpu_set_profile(int on) {

@@ -210,7 +210,7 @@ struct rxgpu_index {
 	mutable uint32_t pitch_bf = 0;
 	mutable uint64_t shadow_version = ~0ull;
 	uint32_t tc_mode = 0;  // 0 auto, 1 force on, 2 off
-	uint32_t tc_variant = 0;      // 0 = knn_tc_filter_q (query block in TMEM) when the dimension allows; 7 = knn_tc_filter_k (K-split); 3 / 4 = first-generation kernel (1 CTA / CTA pair)
+	uint32_t tc_variant = 0;      // 0 = knn_tc_filter_q (query block in TMEM) when the dimension allows; 14 = knn_tc_filter_p (CTA pairs, cta_group::2); 3 / 4 = first-generation kernel (1 CTA / CTA pair)
 	uint32_t tc_cluster_max = 0;  // 0 = up to 4 CTAs per cluster
 
 	~rxgpu_index() {

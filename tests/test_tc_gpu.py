@@ -35,10 +35,9 @@ def test_tc_path_is_bit_identical_to_exact_scan(metric, n, dim, nq, k):
     assert (d0.view(np.uint32) == d1.view(np.uint32)).all()
     assert st["tc_fallbacks"] == 0 and 0 < st["tc_candidates"] < nq * 4096
     # every kernel variant gives the same bits: 3 / 4 = queries in shared memory (1 CTA / CTA pair with TMA multicast),
-    # 5 / 6 = whole query block in TMEM (accumulators of 64 rows; the default) with single CTAs / clusters of up to 4 CTAs,
-    # 7 / 8 = K-split query block (TMEM + shared memory, accumulators of 128 rows) with single CTAs / clusters
-    # 9 = knn_tc_filter_q with clusters of up to 8 CTAs (one launch serves 1024 queries)
-    for mode, kernel in ((3, 1), (4, 1), (5, 2), (6, 2), (7, 3), (8, 3), (9, 2)):
+    # 5 / 6 / 9 = whole query block in TMEM (accumulators of 64 rows; the default) with single CTAs / clusters of up to 4 / 8 CTAs,
+    # 14 / 15 / 16 = CTA pairs multiply as one (cta_group::2, half a 128-row tile per SM) with clusters of up to 4 / 2 / 8 CTAs
+    for mode, kernel in ((3, 1), (4, 1), (5, 2), (6, 2), (9, 2), (14, 5), (15, 5), (16, 5)):
         gpu.set_tensor_core_filter(mode)
         d2, l2, c2 = gpu.search_knn(queries, k)
         s2 = rx.last_search_stats()
