@@ -132,6 +132,11 @@ int rxgpu_tie_replay(uint32_t k, float dstar, uint32_t n_lower, const float* low
 typedef struct rxgpu_comm rxgpu_comm;
 int rxgpu_comm_unique_id(void* out_id /* RXGPU_COMM_ID_BYTES */);
 int rxgpu_comm_create(rxgpu_comm** out, int nranks, int rank, const void* id /* RXGPU_COMM_ID_BYTES, or NULL when nranks == 1 */, int device);
+/* the ranks of ONE process (a reindexer process that drives several GPUs: one host thread per rank; the devices may repeat, which is
+ * how a one-GPU box exercises the cross-shard paths): out[0..nranks) receive the communicators, rank r on devices[r] (NULL = all on
+ * device 0).  Their exchanges go through host memory behind a rendezvous; every rank must make the same collective calls, each from its
+ * own thread.  Serves rxgpu_sharded_ft_select; rxgpu_sharded_search_knn exchanges over NCCL only. */
+int rxgpu_comm_create_local(rxgpu_comm** out, int nranks, const int* devices);
 void rxgpu_comm_destroy(rxgpu_comm*);
 int rxgpu_comm_rank(const rxgpu_comm*);
 int rxgpu_comm_size(const rxgpu_comm*);
@@ -425,6 +430,17 @@ int rxgpu_ft_select(rxgpu_ft_index*, const rxgpu_ft_config* cfg, uint32_t nterms
 					float* out_ranks /* RankT = the uint8 rank as float */, uint64_t* out_n);
 int rxgpu_ft_select_query(rxgpu_ft_index*, const rxgpu_ft_config* cfg, const rxgpu_ft_query* query, const uint8_t* excluded,
 						  const uint8_t* row_status, int rank_sort_type, uint64_t limit, int32_t* out_row_ids, float* out_ranks, uint64_t* out_n);
+/* ---------------------------------------------------------------- ft_fast merge over docid-range shards
+ * Shard r of the communicator holds the documents [doc_base_r, doc_base_r + total_docs_r) of the namespace under LOCAL ids, the posting
+ * lists restricted to them (the same list ids on every shard; a list may be empty on a shard) and the namespace-wide average field
+ * lengths.  One collective call per rank = rxgpu_ft_select over the whole namespace: BM25's document and posting counts, the
+ * restricting mask's popcount, the 65 536-bin preselect histogram, the ordered cut at the threshold score (lower shards first) and the
+ * largest rank (uint8 normalisation) are exchanged between the shards (five exchanges of a few bytes to 512 KB), every rank's first
+ * `limit` rows are gathered and merged, and EVERY rank returns the same rows the unsharded call returns.  Row ids: doc_base + local id,
+ * or the shard's rxgpu_ft_set_rows table (global row ids).  Not served: phrases, multi-word synonyms (their slot order is global). */
+int rxgpu_sharded_ft_select(rxgpu_comm*, rxgpu_ft_index* shard, uint32_t doc_base, const rxgpu_ft_config* cfg, uint32_t nterms,
+							const rxgpu_ft_term* terms, const uint8_t* excluded, const uint8_t* row_status, int rank_sort_type, uint64_t limit,
+							int32_t* out_row_ids, float* out_ranks, uint64_t* out_n);
 /* statistics of the last merge on this thread */
 typedef struct {
 	uint32_t launches;

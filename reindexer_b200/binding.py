@@ -177,6 +177,9 @@ _SIGNATURES = {
     "rxgpu_ft_select_query": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _u8p, _u8p, C.c_int, C.c_uint64, _i32p, _f32p,
                                          C.POINTER(C.c_uint64)]),
     "rxgpu_ft_set_rows": (C.c_int, [C.c_void_p, _u32p, _i32p]),
+    "rxgpu_sharded_ft_select": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(FtConfig), C.c_uint32, C.POINTER(FtTerm), _u8p, _u8p,
+                                           C.c_int, C.c_uint64, _i32p, _f32p, C.POINTER(C.c_uint64)]),
+    "rxgpu_comm_create_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_int)]),
     "rxgpu_ft_select": (C.c_int, [C.c_void_p, C.POINTER(FtConfig), C.c_uint32, C.POINTER(FtTerm), _u8p, _u8p, C.c_int, C.c_uint64, _i32p, _f32p,
                                   C.POINTER(C.c_uint64)]),
     "rxgpu_ft_last_stats": (None, [C.POINTER(FtStats)]),
@@ -543,11 +546,22 @@ def comm_unique_id() -> bytes:
 class ShardComm:
     """rxgpu_comm: this rank's end of the NCCL communicator the sharded search exchanges its per-shard lists over."""
 
-    def __init__(self, nranks: int, rank: int, comm_id: bytes | None, device: int):
+    def __init__(self, nranks: int, rank: int, comm_id: bytes | None, device: int, _handle=None):
         self._lib = lib()
+        if _handle is not None:  # one of the communicators rxgpu_comm_create_local made
+            self._h = _handle
+            return
         self._h = C.c_void_p()
         idbuf = C.create_string_buffer(comm_id, COMM_ID_BYTES) if comm_id is not None else None
         _check(self._lib.rxgpu_comm_create(C.byref(self._h), nranks, rank, idbuf, device))
+
+    @staticmethod
+    def local_group(nranks: int, devices=None):
+        """rxgpu_comm_create_local: the ranks of ONE process (one host thread per rank); devices may repeat"""
+        hs = (C.c_void_p * nranks)()
+        dv = None if devices is None else (C.c_int * nranks)(*devices)
+        _check(lib().rxgpu_comm_create_local(hs, nranks, dv))
+        return [ShardComm(nranks, r, None, 0, _handle=C.c_void_p(hs[r])) for r in range(nranks)]
 
     def close(self):
         if self._h:
@@ -715,6 +729,20 @@ class GpuFtIndex:
             _check(self._lib.rxgpu_ft_select(self._h, C.byref(c), len(terms), arr, None if ex is None else _p(ex, _u8p),
                                              None if rs is None else _p(rs, _u8p), rank_sort_type, limit, _p(ids, _i32p), _p(ranks, _f32p),
                                              C.byref(n)))
+        m = min(n.value, limit)
+        return ids[:m], ranks[:m], n.value
+
+    def sharded_select(self, comm: "ShardComm", doc_base: int, cfg, field_cfg, terms, limit, excluded=None, row_status=None, rank_sort_type=1):
+        """rxgpu_sharded_ft_select: collective over the docid-range shards of one namespace; every rank gets the namespace's rows"""
+        c, arr, keep = self._config_and_terms(cfg, field_cfg, terms)
+        ex = None if excluded is None else np.ascontiguousarray(excluded, np.uint8)
+        rs = None if row_status is None else np.ascontiguousarray(row_status, np.uint8)
+        ids = np.zeros(max(limit, 1), np.int32)
+        ranks = np.zeros(max(limit, 1), np.float32)
+        n = C.c_uint64(0)
+        _check(self._lib.rxgpu_sharded_ft_select(comm._h, self._h, doc_base, C.byref(c), len(terms), arr, None if ex is None else _p(ex, _u8p),
+                                                 None if rs is None else _p(rs, _u8p), rank_sort_type, limit, _p(ids, _i32p), _p(ranks, _f32p),
+                                                 C.byref(n)))
         m = min(n.value, limit)
         return ids[:m], ranks[:m], n.value
 

@@ -1080,7 +1080,42 @@ __global__ void ft_post_scale(const float* proc, const uint32_t* n_docs, uint32_
 		// scalingFactor = maxProc > 255 ? 255.0 / maxProc : 1.0 (a float: the double quotient is narrowed at the assignment)
 		const float scale = m > 255.f ? __double2float_rn(__ddiv_rn(255.0, double(m))) : 1.0f;
 		d_post[0] = __float_as_uint(scale);
+		d_post[2] = __float_as_uint(m);  // >= 0: its bits order like the value (the shards' maxima are combined with an integer max)
 	}
+}
+// docid-range shards: the scaling factor again, from the maximum over ALL shards (d_post[2] after the all-reduce)
+__global__ void ft_post_rescale(uint32_t* d_post) {
+	const float m = __uint_as_float(d_post[2]);
+	d_post[0] = __float_as_uint(m > 255.f ? __double2float_rn(__ddiv_rn(255.0, double(m))) : 1.0f);
+}
+// docid-range shards, ordered cut of the preselect: this shard's threshold documents rank behind those of the lower shards
+__global__ void ft_sum_u32(const uint32_t* v, uint32_t n, uint32_t* out) {
+	__shared__ uint32_t s_sum;
+	if (threadIdx.x == 0) {
+		s_sum = 0;
+	}
+	__syncthreads();
+	uint32_t c = 0;
+	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+		c += v[i];
+	}
+	for (int off = 16; off > 0; off >>= 1) {
+		c += __shfl_xor_sync(0xffffffffu, c, off);
+	}
+	if ((threadIdx.x & 31) == 0 && c) {
+		atomicAdd(&s_sum, c);
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		*out = s_sum;
+	}
+}
+__global__ void ft_shard_budget(uint32_t* thr, const uint32_t* counts, uint32_t rank) {
+	unsigned long long before = 0;
+	for (uint32_t r = 0; r < rank; ++r) {
+		before += counts[r];
+	}
+	thr[1] = thr[1] > before ? uint32_t(thr[1] - before) : 0u;
 }
 // rows a merged document contributes: 0 when its rank is below minRank, else its row ids that pass the external statuses
 __global__ void ft_post_count(const int32_t* md_id, const float* proc, const uint32_t* n_docs, float min_proc, const uint32_t* row_begin,
@@ -1105,7 +1140,7 @@ __global__ void ft_post_count(const int32_t* md_id, const float* proc, const uin
 //              IDOnly    -> rowId << 8 | rank           (row id ascending)
 __global__ void ft_post_emit(const int32_t* md_id, const float* proc, const uint32_t* n_docs, const uint32_t* d_post, const uint32_t* row_begin,
 							 const int32_t* row_ids, const uint8_t* row_status, const uint32_t* cnt, const uint32_t* off, int rank_and_id,
-							 unsigned long long* keys, uint32_t* rows_total) {
+							 unsigned long long* keys, uint32_t* rows_total, uint32_t row_base) {
 	const uint32_t n = *n_docs;
 	const float scale = __uint_as_float(d_post[0]);
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -1118,8 +1153,9 @@ __global__ void ft_post_emit(const int32_t* md_id, const float* proc, const uint
 		const uint32_t rank = uint32_t(uint8_t(__fmul_rn(proc[i], scale)));  // normalizedProc = static_cast<uint8_t>(proc * scalingFactor)
 		const uint32_t d = uint32_t(md_id[i]);
 		uint32_t o = off[i];
-		if (!row_begin) {
-			keys[o] = rank_and_id ? ((unsigned long long)(255u - rank) << 32) | d : ((unsigned long long)d << 8) | rank;
+		if (!row_begin) {  // vdoc i is row i (+ the first document of this docid-range shard)
+			const unsigned long long row = (unsigned long long)d + row_base;
+			keys[o] = rank_and_id ? ((unsigned long long)(255u - rank) << 32) | row : (row << 8) | rank;
 		} else {
 			for (uint32_t r = row_begin[d]; r < row_begin[d + 1]; ++r) {
 				const uint32_t row = uint32_t(row_ids[r]);
@@ -1285,6 +1321,8 @@ struct rxgpu_ft_index {
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	DevBuf<uint16_t> score;
 	DevBuf<unsigned long long> hist, popc;
+	DevBuf<unsigned long long> shard_counts, shard_keys;  // docid-range shards: exchanged counts, gathered result keys
+	DevBuf<uint32_t> shard_u32;
 	DevBuf<uint8_t> excluded, tmp_field, md_field;
 	DevBuf<float> tmp_rank, md_proc, ext_rank;
 	DevBuf<int32_t> md_id;
@@ -1635,8 +1673,19 @@ struct SelectReq {  // rxgpu_ft_select: post-processing and IndexText::afterSele
 	int32_t* out_row_ids;
 	float* out_ranks;
 };
+// One docid-range shard of a namespace: this index holds the documents [doc_base, doc_base + total_docs) with LOCAL ids, the
+// posting lists restricted to them, the GLOBAL average field lengths.  The merge then needs five exchanges with the other shards, all
+// tiny: (1) document and posting counts (BM25's IDF, maxMerged and the preselect estimate are namespace-wide), (2) the popcount of the
+// restricting mask, (3) the 65 536-bin score histogram and the highest score, (4) how many documents AT the threshold score the lower
+// shards hold (the ordered cut keeps the lowest ids), (5) the largest rank (uint8 normalisation) -- and at the end the shards' first
+// `limit` rows are gathered and merged.  Everything else is per document.  After the preselect at most maxMerged documents survive in
+// all shards together, so the slot order inside a shard never decides anything the select output shows.
+struct FtShard {
+	rxgpu_comm* comm;
+	uint32_t doc_base;
+};
 int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_query* query, const uint8_t* excluded, int rank_sort_type,
-				uint64_t max_out, rxgpu_ft_merge_info* out, uint64_t* out_n, const SelectReq* sel) {
+				uint64_t max_out, rxgpu_ft_merge_info* out, uint64_t* out_n, const SelectReq* sel, const FtShard* sh = nullptr) {
 	if (!ft || !cfg || !out_n || !query || (query->nterms && !query->terms) || (query->nsynonyms && !query->synonyms)) {
 		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
 	}
@@ -1663,6 +1712,9 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 	g_ft_stats = rxgpu_ft_stats{};
 	*out_n = 0;
 	const uint32_t N = ft->total_docs;
+	if (sh && (!sel || query->nsynonyms || N == 0)) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: a sharded merge serves the select path, query parts without multi-word synonyms, non-empty shards");
+	}
 	// query parts: a plain term, or a phrase = consecutive terms that share a non-zero phrase_num (FtDslOpts::phraseNum; the selecter
 	// groups them the same way, selecterimpl.h:548-558).  head[t]: term t opens a part; inPhrase[t]: it belongs to a phrase.
 	std::vector<uint8_t> head(nterms, 1), inPhrase(nterms, 0);
@@ -1696,6 +1748,9 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 		}
 	}
 	queryLength = nterms;  // QueryLength(): every phrase counts its terms (querymergedata.h:212-219)
+	if (sh && nphrases) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: phrases are not served by the sharded merge (a phrase's slot order is global)");
+	}
 	if (nparts == 0 || (nparts == 1 && terms[0].op == 3) || N == 0) {  // QueryMergeData::Empty(), mergerimpl.h:472
 		return 0;
 	}
@@ -1737,13 +1792,41 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 		uint32_t list;
 		float proc;
 		bool suppressed;
+		uint64_t gdocs;  // documents of the list over the whole namespace (= the list's length unless the index is one shard of several)
 	};
 	std::vector<std::vector<Sub>> subs(nall);
 	uint64_t totalORVids = 0;  // selecterimpl.h:443,462,546,595: the synonyms' terms count as well
+	uint64_t gN = N;           // documents of the whole namespace
+	if (sh) {  // exchange 1: the shards' document and posting counts, summed
+		std::vector<unsigned long long> counts{N};
+		for (uint32_t t = 0; t < nall; ++t) {
+			for (uint32_t s = 0; s < terms[t].nsubterms; ++s) {
+				counts.push_back(ft->lists[terms[t].postings[s]].ndocs);
+			}
+		}
+		RX_CUDA(ft->shard_counts.ensure(counts.size()));
+		RX_CUDA(cudaMemcpyAsync(ft->shard_counts.p, counts.data(), counts.size() * 8, cudaMemcpyHostToDevice, st));
+		if (int rc = commAllReduce(sh->comm, ft->shard_counts.p, counts.size(), CommOp::SumU64, st)) {
+			return rc;
+		}
+		RX_CUDA(cudaMemcpyAsync(counts.data(), ft->shard_counts.p, counts.size() * 8, cudaMemcpyDeviceToHost, st));
+		RX_CUDA(cudaStreamSynchronize(st));
+		gN = counts[0];
+		size_t at = 1;
+		for (uint32_t t = 0; t < nall; ++t) {
+			subs[t].reserve(terms[t].nsubterms);
+			for (uint32_t s = 0; s < terms[t].nsubterms; ++s) {
+				subs[t].push_back(Sub{terms[t].postings[s], terms[t].procs[s], terms[t].suppressed && terms[t].suppressed[s], counts[at++]});
+			}
+		}
+	}
 	for (uint32_t t = 0; t < nall; ++t) {
-		for (uint32_t s = 0; s < terms[t].nsubterms; ++s) {
-			subs[t].push_back(Sub{terms[t].postings[s], terms[t].procs[s], terms[t].suppressed && terms[t].suppressed[s]});
-			totalORVids += ft->lists[terms[t].postings[s]].ndocs;
+		for (uint32_t s = 0; s < terms[t].nsubterms && !sh; ++s) {
+			subs[t].push_back(Sub{terms[t].postings[s], terms[t].procs[s], terms[t].suppressed && terms[t].suppressed[s],
+								  ft->lists[terms[t].postings[s]].ndocs});
+		}
+		for (const Sub& sub : subs[t]) {
+			totalORVids += sub.gdocs;
 		}
 		if (t < nterms && inPhrase[t]) {
 			continue;  // PhraseMerger::Merge runs inside Merger::init (merger.h:84-90), BEFORE SortSubterms: the caller's order stands
@@ -1852,7 +1935,7 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 		for (uint32_t f = 0; terms[t].need_sum_rank && f < ft->nfields; ++f) {
 			p.need_sum_mask |= terms[t].need_sum_rank[f] ? (1ull << f) : 0ull;
 		}
-		const double totalDocCount = double(N - 1), matched = double(l.ndocs);  // mergerimpl.h:122-124
+		const double totalDocCount = double(gN - 1), matched = double(sub.gdocs);  // mergerimpl.h:122-124 (namespace-wide counts)
 		if (cfg->bm25_type == 0) {  // Bm25Rx::IDF (bm25.h:21-27), on the host: the same libm as the reference
 			double f = std::log((totalDocCount - matched + 1) / matched) / std::log(1 + totalDocCount);
 			p.idf = f < 0.2 ? 0.2 : f;
@@ -2071,14 +2154,14 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 			}
 			uint64_t nd = 0;
 			for (const Sub& sub : subs[t]) {
-				nd += ft->lists[sub.list].ndocs;
+				nd += sub.gdocs;
 			}
 			if (inPhrase[t]) {
 				nd = ft->phrases[phraseOf[t]]->num_merged;  // phraseMergers_[i].NumDocsMerged() (merger.h:252)
 			}
 			for (uint32_t y = 0; y < terms[t].nsynonyms; ++y) {  // + the first term of each of its synonyms (merger.h:253-256)
 				for (const Sub& sub : subs[synBegin[terms[t].synonym_ids[y]]]) {
-					nd += ft->lists[sub.list].ndocs;
+					nd += sub.gdocs;
 				}
 			}
 			if (terms[t].op == 2) {
@@ -2087,12 +2170,17 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 				estOr += nd;
 			}
 		}
-		const uint64_t est = std::min<uint64_t>(std::min(estOr, estAnd), N);
-		bool preselect = est > cfg->merge_limit && N > cfg->merge_limit && !std::getenv("REINDEXER_NO_2PHASE_FT_MERGE");
+		const uint64_t est = std::min<uint64_t>(std::min(estOr, estAnd), gN);
+		bool preselect = est > cfg->merge_limit && gN > cfg->merge_limit && !std::getenv("REINDEXER_NO_2PHASE_FT_MERGE");
 		uint32_t* d_presel = ft->scalar_u32.p + 6;  // [6] 1 when preselectMostRelevantDocs runs
 		if (preselect) {
 			RX_CUDA(cudaMemsetAsync(ft->popc.p, 0, 8, st));
 			ft_popcount<<<gridFor(mwords, sm), kFtThreads, 0, st>>>(ft->mask.p, mwords, ft->popc.p);
+			if (sh) {  // exchange 2: restrictingMask_.PopCount() over all shards
+				if (int rc = commAllReduce(sh->comm, ft->popc.p, 1, CommOp::SumU64, st)) {
+					return rc;
+				}
+			}
 			ft_decide_preselect<<<1, 1, 0, st>>>(ft->popc.p, cfg->merge_limit, d_presel);
 			g_ft_stats.launches += 2;
 			preselFlag = d_presel;  // the last condition is known on the device only: the kernels below test it, the host does not wait
@@ -2135,8 +2223,26 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 			uint32_t* d_thr = ft->scalar_u32.p + 2;  // [2] minScore, [3] minScoreDocs
 			RX_CUDA(ft->block_counts.ensure(pg));
 			ft_hist<<<pg, kFtThreads, 0, st>>>(ft->score.p, ft->mask.p, ft->has_removed ? ft->removed.p : nullptr, mwords, ft->hist.p, ft->scalar_u32.p + 5, preselFlag);
+			if (sh) {  // exchange 3: the score histogram and the highest score of the whole namespace -> the same threshold on every shard
+				if (int rc = commAllReduce(sh->comm, ft->hist.p, 65536, CommOp::SumU64, st)) {
+					return rc;
+				}
+				if (int rc = commAllReduce(sh->comm, ft->scalar_u32.p + 5, 1, CommOp::MaxU32, st)) {
+					return rc;
+				}
+			}
 			ft_pick_threshold<<<1, 1024, 0, st>>>(ft->hist.p, maxMerged, ft->scalar_u32.p + 5, d_thr, preselFlag);
 			ft_thresh_count<<<pg, kFtThreads, 0, st>>>(ft->score.p, ft->mask.p, mwords, d_thr, ft->block_counts.p, preselFlag);
+			if (sh) {  // exchange 4: the documents AT the threshold score are kept in ascending GLOBAL id order = lower shards first
+				const uint32_t R = uint32_t(commSize(sh->comm));
+				RX_CUDA(ft->shard_u32.ensure(size_t(R) + 1));
+				ft_sum_u32<<<1, 256, 0, st>>>(ft->block_counts.p, pg, ft->shard_u32.p + R);
+				if (int rc = commAllGather(sh->comm, ft->shard_u32.p + R, ft->shard_u32.p, 4, st)) {
+					return rc;
+				}
+				ft_shard_budget<<<1, 1, 0, st>>>(d_thr, ft->shard_u32.p, uint32_t(commRank(sh->comm)));
+				g_ft_stats.launches += 2;
+			}
 			ft_thresh_apply<<<pg, kFtThreads, 0, st>>>(ft->score.p, ft->mask.p, mwords, d_thr, ft->block_counts.p, preselFlag);
 			g_ft_stats.launches += 4;
 			g_ft_stats.algorithmic_bytes += uint64_t(N) * 6;
@@ -2244,6 +2350,13 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 		const uint32_t* rb = ft->has_rows ? ft->row_begin.p : nullptr;
 		const int32_t* ri = ft->has_rows ? ft->row_ids.p : nullptr;
 		ft_post_scale<<<1, 1024, 0, st>>>(ms.md_proc, ms.n_docs, ft->post_scalars.p);
+		if (sh) {  // exchange 5: the uint8 normalisation divides by the largest rank of the whole namespace
+			if (int rc = commAllReduce(sh->comm, ft->post_scalars.p + 2, 1, CommOp::MaxU32, st)) {
+				return rc;
+			}
+			ft_post_rescale<<<1, 1, 0, st>>>(ft->post_scalars.p);
+			g_ft_stats.launches++;
+		}
 		ft_post_count<<<gridFor(maxMerged, sm), kFtThreads, 0, st>>>(ms.md_id, ms.md_proc, ms.n_docs, float(cfg->min_rank), rb, ri, d_status, maxMerged,
 																   ft->post_cnt.p);
 		size_t tmpBytes = 0;
@@ -2281,7 +2394,7 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 			}
 			ft_post_emit<<<gridFor(nMerged, sm), kFtThreads, 0, st>>>(ms.md_id, ms.md_proc, ms.n_docs, ft->post_scalars.p, rb, ri, d_status,
 																	 ft->post_cnt.p, ft->post_off.p, rankAndId ? 1 : 0, ft->post_keys.p,
-																	 ft->post_scalars.p + 1);
+																	 ft->post_scalars.p + 1, sh ? sh->doc_base : 0u);
 			size_t sortBytes = 0;
 			cub::DeviceRadixSort::SortKeys(nullptr, sortBytes, ft->post_keys.p, ft->post_keys_sorted.p, int(sortItems), 0, 41, st);
 			RX_CUDA(ft->sort_tmp.ensure(sortBytes));
@@ -2289,6 +2402,62 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 			g_ft_stats.launches += 2;
 		}
 		RX_CUDA(cudaGetLastError());
+		if (sh) {
+			// the shards' first `limit` rows (keys are globally comparable: rank and GLOBAL row id) gathered and merged; the row totals summed
+			const uint32_t R = uint32_t(commSize(sh->comm));
+			const uint64_t lim = sel->limit;
+			RX_CUDA(ft->shard_keys.ensure(std::max<uint64_t>(lim, 1) * (R + 1)));
+			unsigned long long* snd = ft->shard_keys.p + lim * R;
+			if (lim) {
+				RX_CUDA(cudaMemsetAsync(snd, 0xFF, lim * 8, st));
+				const uint64_t have = std::min<uint64_t>(sortItems, lim);
+				if (have) {
+					RX_CUDA(cudaMemcpyAsync(snd, ft->post_keys_sorted.p, have * 8, cudaMemcpyDeviceToDevice, st));
+				}
+				if (int rc = commAllGather(sh->comm, snd, ft->shard_keys.p, lim * 8, st)) {
+					return rc;
+				}
+			}
+			if (!noSync) {  // the row total was read back to size the sort: put it where the other path leaves it
+				RX_CUDA(cudaMemcpyAsync(ft->post_scalars.p + 1, &rowsTotal, 4, cudaMemcpyHostToDevice, st));
+			} else if (!sortItems) {
+				RX_CUDA(cudaMemsetAsync(ft->post_scalars.p + 1, 0, 4, st));
+			}
+			if (int rc = commAllReduce(sh->comm, ft->post_scalars.p + 1, 1, CommOp::SumU32, st)) {
+				return rc;
+			}
+			RX_CUDA(cudaEventRecord(e1, st));
+			RX_CUDA(ft->h_keys.ensure(std::max<uint64_t>(lim * R, 1)));
+			if (lim) {
+				RX_CUDA(cudaMemcpyAsync(ft->h_keys.p, ft->shard_keys.p, lim * R * 8, cudaMemcpyDeviceToHost, st));
+			}
+			RX_CUDA(cudaMemcpyAsync(ft->h_post.p, ft->post_scalars.p + 1, 4, cudaMemcpyDeviceToHost, st));
+			RX_CUDA(cudaMemcpyAsync(ft->h_post.p + 1, ft->scalar_u32.p + 6, 4, cudaMemcpyDeviceToHost, st));
+			RX_CUDA(cudaStreamSynchronize(st));
+			RX_CUDA(cudaEventElapsedTime(&g_ft_stats.device_ms, e0, e1));
+			ft->idoff_clean = !trivial;
+			g_ft_stats.preselected = preselFlag ? ft->h_post.p[1] : 0;
+			std::vector<unsigned long long> all;
+			for (uint64_t i = 0; i < lim * R; ++i) {
+				if (ft->h_keys.p[i] != ~0ull) {
+					all.push_back(ft->h_keys.p[i]);
+				}
+			}
+			std::sort(all.begin(), all.end());  // every shard's slice is sorted and row ids are disjoint: a plain sort of <= R x limit keys
+			const uint64_t nres = std::min<uint64_t>(all.size(), lim);
+			for (uint64_t i = 0; i < nres; ++i) {
+				const unsigned long long k = all[i];
+				if (rankAndId) {
+					sel->out_row_ids[i] = int32_t(uint32_t(k));
+					sel->out_ranks[i] = float(255u - uint32_t(k >> 32));
+				} else {
+					sel->out_row_ids[i] = int32_t(uint32_t(k >> 8));
+					sel->out_ranks[i] = float(uint32_t(k & 0xFF));
+				}
+			}
+			*out_n = ft->h_post.p[0];
+			return 0;
+		}
 		RX_CUDA(cudaEventRecord(e1, st));
 		if (noSync) {  // one copy of what the caller asked for + the row total, one synchronisation
 			const uint64_t want = std::min<uint64_t>(sortItems, sel->limit);
@@ -2468,6 +2637,28 @@ int rxgpu_ft_select_query(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const 
 	}
 	const SelectReq sel{row_status, limit, out_row_ids, out_ranks};
 	return ftMergeImpl(ft, cfg, query, excluded, rank_sort_type, 0, nullptr, out_n, &sel);
+}
+
+int rxgpu_sharded_ft_select(rxgpu_comm* comm, rxgpu_ft_index* shard, uint32_t doc_base, const rxgpu_ft_config* cfg, uint32_t nterms,
+							const rxgpu_ft_term* terms, const uint8_t* excluded, const uint8_t* row_status, int rank_sort_type, uint64_t limit,
+							int32_t* out_row_ids, float* out_ranks, uint64_t* out_n) {
+	if (!comm || !shard) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
+	}
+	if (int rc = ftSelectCheck(rank_sort_type, limit, out_row_ids, out_ranks)) {
+		return rc;
+	}
+	if (limit > (1u << 20)) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: the sharded select gathers `limit` rows per shard: limit <= 2^20");
+	}
+	if (commDevice(comm) != shard->device) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: the shard lives on another device than its communicator");
+	}
+	std::lock_guard<std::mutex> lck(commMutex(comm));
+	const SelectReq sel{row_status, limit, out_row_ids, out_ranks};
+	const rxgpu_ft_query q{nterms, terms, 0, nullptr};
+	const FtShard sh{comm, doc_base};
+	return ftMergeImpl(shard, cfg, &q, excluded, rank_sort_type, 0, nullptr, out_n, &sel, &sh);
 }
 
 }  // extern "C"

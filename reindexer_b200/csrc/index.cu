@@ -318,9 +318,10 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 	RX_CUDA(ws.d_lists.ensure(size_t(nq) * k1));
 	tc_prepare_queries<<<(nqPad * 32 + 255) / 256, 256, 0, st>>>(d_queries, nq, nqPad, ix->dim, pitchBf,
 																 reinterpret_cast<__nv_bfloat16*>(ws.d_qbf.p), ws.d_qnorm.p);
-	tc_init_tau<<<nq, 256, 0, st>>>(ix->d_rows, ix->pitch, ix->dim, ix->metric == RXGPU_COS ? ix->d_norms : nullptr,
-									uint32_t(std::min<uint64_t>(ix->size, 1024)), d_queries, k1, ix->metric, ws.d_tau.p, ws.d_ub_list.p,
-									ws.d_ub_lock.p);
+	RX_CUDA(raiseSmemCeilingOnce(tc_init_tau, ix->device, int(tc_init_smem_bytes(2048))));
+	tc_init_tau<<<(nq + kTcInitQ - 1) / kTcInitQ, 256, tc_init_smem_bytes(ix->pitch), st>>>(
+		ix->d_rows, ix->pitch, ix->dim, ix->metric == RXGPU_COS ? ix->d_norms : nullptr, uint32_t(std::min<uint64_t>(ix->size, kTcInitRows)),
+		d_queries, nq, k1, ix->metric, ws.d_tau.p, ws.d_ub_list.p, ws.d_ub_lock.p);
 	RX_CUDA(cudaMemsetAsync(ws.d_cand_count.p, 0, size_t(nqPad) * 4, st));
 	RX_CUDA(cudaGetLastError());
 	g_stats.launches += 2;
@@ -394,7 +395,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			a.cand_rows = ws.d_cand_rows.p;
 			a.cand_count = ws.d_cand_count.p;
 			a.cand_cap = kTcCandCap;
-			a.init_rows = uint32_t(std::min<uint64_t>(ix->size, 1024));
+			a.init_rows = uint32_t(std::min<uint64_t>(ix->size, kTcInitRows));
 			a.n = uint32_t(ix->size);
 			a.kchunks = kchunks;
 			a.pitch_bf = pitchBf;
@@ -486,7 +487,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 		a.tau = ws.d_tau.p;
 		a.ub_list = ws.d_ub_list.p;
 		a.ub_lock = ws.d_ub_lock.p;
-		a.init_rows = uint32_t(std::min<uint64_t>(ix->size, 1024));
+		a.init_rows = uint32_t(std::min<uint64_t>(ix->size, kTcInitRows));
 		a.cand_rows = ws.d_cand_rows.p;
 		a.cand_count = ws.d_cand_count.p;
 		a.cand_cap = kTcCandCap;

@@ -294,4 +294,13 @@ inline int checkIndex(const rxgpu_index* ix) {
 	return 0;
 }
 
+// ---- collectives over an rxgpu_comm (shard.cu): NCCL between processes, a host rendezvous between the threads of one process -------
+enum class CommOp { SumU64, SumU32, MaxU32 };
+int commRank(const rxgpu_comm*);
+int commSize(const rxgpu_comm*);
+int commDevice(const rxgpu_comm*);
+std::mutex& commMutex(rxgpu_comm*);
+int commAllReduce(rxgpu_comm*, void* d_buf, size_t count, CommOp op, cudaStream_t st);        // in place
+int commAllGather(rxgpu_comm*, const void* d_send, void* d_recv, size_t bytes, cudaStream_t st);  // d_recv: nranks x bytes
+
 }  // namespace rxgpu

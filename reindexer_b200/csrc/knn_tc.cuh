@@ -648,64 +648,126 @@ __global__ void tc_convert_rows(const float* rows, uint32_t pitch, uint32_t dim,
 	}
 }
 
-// tau_init[q] = upper bound of the k1-th best distance among the first `rows` rows (fp32 dot products, one block per query).
-// Any upper bound is valid; a small relative slack covers the difference to the arithmetic order of knn_scan_warp.
+// tau_init[q] = upper bound of the k1-th best distance among the first `nrows` (<= 1024) rows, fp32 dot products.  Any upper bound is
+// valid; a small relative slack covers the difference to the arithmetic order of knn_scan_warp.  One block serves kTcInitQ queries
+// (staged in shared memory, zero padded to the row pitch) so the rows come from L2 once per kTcInitQ queries; a warp keeps four rows
+// (128-bit loads) in flight; the k1 smallest distances of a query are then picked by one warp (k1 rounds of a warp-wide argmin).
+constexpr int kTcInitQ = 4;
+constexpr uint32_t kTcInitRows = 1024;
+__host__ __device__ inline size_t tc_init_smem_bytes(uint32_t pitch) { return size_t(kTcInitQ) * (pitch + kTcInitRows) * sizeof(float); }
 __global__ void __launch_bounds__(256) tc_init_tau(const float* rows, uint32_t pitch, uint32_t dim, const float* norm_coefs, uint32_t nrows,
-												   const float* queries, uint32_t k1, int metric, unsigned int* tau, float* ub_list,
+												   const float* queries, uint32_t nq, uint32_t k1, int metric, unsigned int* tau, float* ub_list,
 												   unsigned int* ub_lock) {
-	__shared__ float s_d[1024];
-	const uint32_t q = blockIdx.x;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const float* qv = queries + size_t(q) * dim;
-	for (uint32_t r = warp; r < 1024; r += 8) {
-		float d = INFINITY;
-		if (r < nrows) {
-			const float* p = rows + size_t(r) * pitch;
-			float s = 0.f;
-			for (uint32_t c = lane; c < dim; c += 32) {
-				if (metric == kL2) {
-					const float x = qv[c] - p[c];
-					s = fmaf(x, x, s);
-				} else {
-					s = fmaf(qv[c], p[c], s);
+	extern __shared__ __align__(16) float s_init[];
+	float* s_q = s_init;                     // [kTcInitQ][pitch]
+	float* s_d = s_init + kTcInitQ * pitch;  // [kTcInitQ][kTcInitRows]
+	const uint32_t q0 = blockIdx.x * kTcInitQ;
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (uint32_t i = threadIdx.x; i < kTcInitQ * pitch; i += blockDim.x) {
+		const uint32_t qi = i / pitch, c = i % pitch;
+		s_q[i] = (q0 + qi < nq && c < dim) ? queries[size_t(q0 + qi) * dim + c] : 0.f;
+	}
+	__syncthreads();
+	const uint32_t pitch4 = pitch / 4;
+	constexpr uint32_t kRows = 4;  // rows in flight per warp
+	for (uint32_t r0 = warp * kRows; r0 < kTcInitRows; r0 += 8 * kRows) {
+		float acc[kRows][kTcInitQ];
+#pragma unroll
+		for (uint32_t x = 0; x < kRows; ++x) {
+#pragma unroll
+			for (int qi = 0; qi < kTcInitQ; ++qi) {
+				acc[x][qi] = 0.f;
+			}
+		}
+		if (r0 < nrows) {
+			const float4* p4[kRows];
+#pragma unroll
+			for (uint32_t x = 0; x < kRows; ++x) {
+				p4[x] = reinterpret_cast<const float4*>(rows + size_t(min(r0 + x, nrows - 1)) * pitch);
+			}
+#pragma unroll 3
+			for (uint32_t c = lane; c < pitch4; c += 32) {
+				float4 v[kRows];
+#pragma unroll
+				for (uint32_t x = 0; x < kRows; ++x) {
+					v[x] = __ldg(p4[x] + c);
+				}
+#pragma unroll
+				for (int qi = 0; qi < kTcInitQ; ++qi) {
+					const float4 qq = reinterpret_cast<const float4*>(s_q + qi * pitch)[c];
+#pragma unroll
+					for (uint32_t x = 0; x < kRows; ++x) {
+						if (metric == kL2) {
+							const float a0 = qq.x - v[x].x, a1 = qq.y - v[x].y, a2 = qq.z - v[x].z, a3 = qq.w - v[x].w;
+							acc[x][qi] = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, fmaf(a3, a3, acc[x][qi]))));
+						} else {
+							acc[x][qi] = fmaf(qq.x, v[x].x, fmaf(qq.y, v[x].y, fmaf(qq.z, v[x].z, fmaf(qq.w, v[x].w, acc[x][qi]))));
+						}
+					}
 				}
 			}
-			for (int off = 16; off > 0; off >>= 1) {
-				s += __shfl_xor_sync(0xffffffffu, s, off);
-			}
-			d = metric == kL2 ? s : -s;
-			if (metric == kCos) {
-				d *= norm_coefs[r];
-			}
-			d += 1e-4f * fabsf(d) + 1e-6f;
 		}
-		if (lane == 0) {
-			s_d[r] = d;
+#pragma unroll
+		for (uint32_t x = 0; x < kRows; ++x) {
+#pragma unroll
+			for (int qi = 0; qi < kTcInitQ; ++qi) {
+				float s = acc[x][qi];
+				for (int off = 16; off > 0; off >>= 1) {
+					s += __shfl_xor_sync(0xffffffffu, s, off);
+				}
+				if (lane == uint32_t(qi)) {
+					const uint32_t r = r0 + x;
+					float d = INFINITY;
+					if (r < nrows) {
+						d = metric == kL2 ? s : -s;
+						if (metric == kCos) {
+							d *= norm_coefs[r];
+						}
+						d += 1e-4f * fabsf(d) + 1e-6f;
+					}
+					s_d[qi * kTcInitRows + r] = d;
+				}
+			}
 		}
 	}
 	__syncthreads();
-	// bitonic sort of 1024 floats, 256 threads
-	for (uint32_t size = 2; size <= 1024; size <<= 1) {
-		for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-			for (uint32_t i = threadIdx.x; i < 512; i += 256) {
-				const uint32_t lo = 2 * i - (i & (stride - 1));
-				const uint32_t hi = lo + stride;
-				const bool up = (lo & size) == 0;
-				const float x = s_d[lo], y = s_d[hi];
-				if ((x > y) == up) {
-					s_d[lo] = y;
-					s_d[hi] = x;
+	if (warp < kTcInitQ && q0 + warp < nq) {  // warp w: the k1 smallest of query q0 + w (rows < nrows sort first, the rest are +inf)
+		const uint32_t q = q0 + warp;
+		float* d = s_d + warp * kTcInitRows;
+		float last = INFINITY;
+		for (uint32_t round = 0; round < kTcMaxK1; ++round) {
+			float best = INFINITY;
+			uint32_t at = lane;
+			if (round < k1) {
+				for (uint32_t j = lane; j < kTcInitRows; j += 32) {
+					const float y = d[j];
+					if (y < best) {
+						best = y;
+						at = j;
+					}
 				}
+				for (int off = 16; off > 0; off >>= 1) {
+					const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+					const uint32_t oa = __shfl_xor_sync(0xffffffffu, at, off);
+					if (ob < best || (ob == best && oa < at)) {
+						best = ob;
+						at = oa;
+					}
+				}
+				if (lane == 0) {
+					d[at] = INFINITY;
+				}
+				__syncwarp();
+				last = best;
 			}
-			__syncthreads();
+			if (lane == 0) {
+				ub_list[size_t(q) * kTcMaxK1 + round] = round < k1 ? best : -INFINITY;
+			}
 		}
-	}
-	if (threadIdx.x < kTcMaxK1) {  // the k1 smallest upper bounds of the first rows seed the shared list (rows < nrows sort first)
-		ub_list[size_t(q) * kTcMaxK1 + threadIdx.x] = threadIdx.x < k1 ? s_d[threadIdx.x] : -INFINITY;
-	}
-	if (threadIdx.x == 0) {
-		tau[q] = float_ord(s_d[k1 - 1]);  // +inf while fewer than k1 rows exist
-		ub_lock[q] = 0;
+		if (lane == 0) {
+			tau[q] = float_ord(last);  // +inf while fewer than k1 rows exist
+			ub_lock[q] = 0;
+		}
 	}
 }
 

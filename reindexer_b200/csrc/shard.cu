@@ -9,6 +9,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -29,6 +30,7 @@ struct NcclApi {
 	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
 	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
 	ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
 	const char* (*GetErrorString)(ncclResult_t) = nullptr;
 	bool ok = false;
 };
@@ -46,8 +48,9 @@ const NcclApi& nccl() {
 		a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
 		a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
 		a.AllGather = reinterpret_cast<decltype(a.AllGather)>(dlsym(h, "ncclAllGather"));
+		a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(h, "ncclAllReduce"));
 		a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
-		a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.GetErrorString;
+		a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.AllReduce && a.GetErrorString;
 		return a;
 	}();
 	return api;
@@ -143,8 +146,35 @@ __global__ void shard_merge_kernel(const unsigned char* all, uint32_t nshards, u
 
 }  // namespace
 
+// Ranks that live in ONE process (one host thread per rank; the GPUs may differ or be the same): the exchange goes through pinned host
+// memory behind a rendezvous instead of NCCL, which refuses two ranks on one device.  This is what a single reindexer process driving
+// several GPUs uses, and what lets a one-GPU box exercise every cross-shard code path.
+struct LocalGroup {
+	int n = 0;
+	std::mutex m;
+	std::condition_variable cv;
+	int arrived = 0;
+	uint64_t generation = 0;
+	std::vector<std::vector<unsigned char>> contrib;  // per rank
+	std::vector<unsigned char> result;
+	template <class F>
+	void rendezvous(F&& leader_work) {  // the last rank to arrive runs leader_work, then everybody leaves
+		std::unique_lock<std::mutex> lck(m);
+		if (++arrived == n) {
+			leader_work();
+			arrived = 0;
+			++generation;
+			cv.notify_all();
+		} else {
+			const uint64_t g = generation;
+			cv.wait(lck, [&] { return generation != g; });
+		}
+	}
+};
+
 struct rxgpu_comm {
 	ncclComm_t comm = nullptr;
+	std::shared_ptr<LocalGroup> local;  // set: the ranks of this communicator are threads of this process
 	int nranks = 1, rank = 0, device = 0;
 	cudaStream_t stream = nullptr;
 	std::mutex mtx;  // one collective call at a time per communicator
@@ -170,6 +200,79 @@ struct rxgpu_comm {
 		}
 	}
 };
+
+// ---- collectives for the other translation units (declared in internal.h): in place on device buffers, on the caller's stream ------
+namespace rxgpu {
+int commRank(const rxgpu_comm* c) { return c ? c->rank : 0; }
+int commSize(const rxgpu_comm* c) { return c ? c->nranks : 1; }
+int commDevice(const rxgpu_comm* c) { return c ? c->device : 0; }
+std::mutex& commMutex(rxgpu_comm* c) { return c->mtx; }
+
+int commAllReduce(rxgpu_comm* c, void* d_buf, size_t count, CommOp op, cudaStream_t st) {
+	if (!c || c->nranks == 1 || count == 0) {
+		return 0;
+	}
+	const size_t esz = op == CommOp::SumU64 ? 8 : 4;
+	if (c->local) {
+		LocalGroup& g = *c->local;
+		std::vector<unsigned char>& mine = g.contrib[size_t(c->rank)];
+		mine.resize(count * esz);
+		RX_CUDA(cudaMemcpyAsync(mine.data(), d_buf, count * esz, cudaMemcpyDeviceToHost, st));
+		RX_CUDA(cudaStreamSynchronize(st));
+		g.rendezvous([&] {
+			g.result = g.contrib[0];
+			for (int r = 1; r < g.n; ++r) {
+				for (size_t i = 0; i < count; ++i) {
+					if (op == CommOp::SumU64) {
+						reinterpret_cast<unsigned long long*>(g.result.data())[i] += reinterpret_cast<const unsigned long long*>(g.contrib[size_t(r)].data())[i];
+					} else if (op == CommOp::SumU32) {
+						reinterpret_cast<uint32_t*>(g.result.data())[i] += reinterpret_cast<const uint32_t*>(g.contrib[size_t(r)].data())[i];
+					} else {
+						uint32_t& a = reinterpret_cast<uint32_t*>(g.result.data())[i];
+						a = std::max(a, reinterpret_cast<const uint32_t*>(g.contrib[size_t(r)].data())[i]);
+					}
+				}
+			}
+		});
+		RX_CUDA(cudaMemcpyAsync(d_buf, g.result.data(), count * esz, cudaMemcpyHostToDevice, st));
+		RX_CUDA(cudaStreamSynchronize(st));
+		g.rendezvous([] {});  // nobody starts the next exchange (which rewrites `result`) before everybody has copied this one
+		return 0;
+	}
+	const ncclDataType_t ty = op == CommOp::SumU64 ? ncclUint64 : ncclUint32;
+	RX_NCCL(nccl().AllReduce(d_buf, d_buf, count, ty, op == CommOp::MaxU32 ? ncclMax : ncclSum, c->comm, st));
+	return 0;
+}
+
+int commAllGather(rxgpu_comm* c, const void* d_send, void* d_recv, size_t bytes, cudaStream_t st) {
+	if (bytes == 0) {
+		return 0;
+	}
+	if (!c || c->nranks == 1) {
+		RX_CUDA(cudaMemcpyAsync(d_recv, d_send, bytes, cudaMemcpyDeviceToDevice, st));
+		return 0;
+	}
+	if (c->local) {
+		LocalGroup& g = *c->local;
+		std::vector<unsigned char>& mine = g.contrib[size_t(c->rank)];
+		mine.resize(bytes);
+		RX_CUDA(cudaMemcpyAsync(mine.data(), d_send, bytes, cudaMemcpyDeviceToHost, st));
+		RX_CUDA(cudaStreamSynchronize(st));
+		g.rendezvous([&] {
+			g.result.resize(bytes * size_t(g.n));
+			for (int r = 0; r < g.n; ++r) {
+				std::memcpy(g.result.data() + bytes * size_t(r), g.contrib[size_t(r)].data(), bytes);
+			}
+		});
+		RX_CUDA(cudaMemcpyAsync(d_recv, g.result.data(), bytes * size_t(g.n), cudaMemcpyHostToDevice, st));
+		RX_CUDA(cudaStreamSynchronize(st));
+		g.rendezvous([] {});
+		return 0;
+	}
+	RX_NCCL(nccl().AllGather(d_send, d_recv, bytes, ncclChar, c->comm, st));
+	return 0;
+}
+}  // namespace rxgpu
 
 extern "C" {
 
@@ -216,6 +319,37 @@ int rxgpu_comm_create(rxgpu_comm** out, int nranks, int rank, const void* id128,
 	return 0;
 }
 
+int rxgpu_comm_create_local(rxgpu_comm** out, int nranks, const int* devices) {
+	if (!out || nranks < 1 || nranks > 32) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: bad communicator arguments (1..32 ranks)");
+	}
+	for (int r = 0; r < nranks; ++r) {
+		out[r] = nullptr;
+	}
+	auto group = std::make_shared<LocalGroup>();
+	group->n = nranks;
+	group->contrib.resize(size_t(nranks));
+	std::vector<std::unique_ptr<rxgpu_comm>> made;
+	for (int r = 0; r < nranks; ++r) {
+		const int device = devices ? devices[r] : 0;
+		if (rxgpu_device_count() <= device || device < 0) {
+			return fail(RXGPU_ERR_SYSTEM, "rxgpu: no usable CUDA device (this library has no CPU fallback)");
+		}
+		RX_CUDA(cudaSetDevice(device));
+		auto c = std::make_unique<rxgpu_comm>();
+		c->nranks = nranks;
+		c->rank = r;
+		c->device = device;
+		c->local = group;
+		RX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+		made.push_back(std::move(c));
+	}
+	for (int r = 0; r < nranks; ++r) {
+		out[r] = made[size_t(r)].release();
+	}
+	return 0;
+}
+
 void rxgpu_comm_destroy(rxgpu_comm* c) { delete c; }
 int rxgpu_comm_rank(const rxgpu_comm* c) { return c ? c->rank : -1; }
 int rxgpu_comm_size(const rxgpu_comm* c) { return c ? c->nranks : 0; }
@@ -248,6 +382,9 @@ int rxgpu_sharded_search_knn(rxgpu_comm* c, const rxgpu_index* ix, uint32_t nq, 
 	}
 	if (ix->device != c->device) {
 		return fail(RXGPU_ERR_PARAMS, "rxgpu: the shard lives on another device than its communicator");
+	}
+	if (c->local && c->nranks > 1) {
+		return fail(RXGPU_ERR_LOGIC, "rxgpu: the sharded KNN search exchanges over NCCL (one process per GPU); in-process rank groups serve the ft_fast merge");
 	}
 	if (nq && (!queries || !out_count || (k && (!out_dist || !out_label)))) {
 		return fail(RXGPU_ERR_PARAMS, "rxgpu: null argument");
