@@ -1,6 +1,7 @@
 """torchrun script (world >= 2, one GPU per rank): the C-ABI sharded search (rxgpu_sharded_search_knn over NCCL) must return, on every
 rank, exactly what ONE index holding all rows returns through rxgpu_search_knn -- same labels, same order, same distance bits, the
-reference's tie rule included -- for the exact-scan path (few queries) and the tensor-core filter path (a batch)."""
+reference's tie rule included -- for the exact-scan path (few queries) and the tensor-core filter path (a batch).  Then the ft_fast merge
+over docid-range shards (rxgpu_sharded_ft_select, the same communicator) against rxgpu_ft_select over all documents."""
 import os
 import sys
 
@@ -56,6 +57,32 @@ def main():
         full.close()
         shard.close()
         dist.barrier()
+    # ---- ft_fast merge over docid-range shards: NCCL all-reduces / all-gathers between the ranks (tests/test_ft_sharded_gpu.py has the
+    # same checks with the ranks as threads of one process)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from ft_helpers import random_problem  # noqa: E402
+    from test_ft_sharded_gpu import shard_of, upload  # noqa: E402
+    from oracle import ft_oracle as F  # noqa: E402
+
+    anchor = rx.GpuBruteforceSearch(rx.L2, 4, 8, device=local)  # the communicator of a sharded index on this device
+    comm = ShardedBruteforceSearch(anchor, 8).comm
+    for seed, merge_limit in ((1, 60), (2, 20000), (3, 150), (4, 20000)):
+        totald = 2400 + 100 * seed
+        prob = random_problem(40 + seed, total_docs=totald, nfields=1 + seed % 2, nterms=3, density=0.3, merge_limit=merge_limit,
+                              removed_frac=0.04 if seed == 3 else 0.0)
+        cuts = [0] + [totald * (r + 1) // world + (7 * r) % 13 for r in range(world - 1)] + [totald]
+        for sort_type in (F.RANK_AND_ID, F.ID_ONLY):
+            ft, ids = shard_of(prob, cuts[rank], cuts[rank + 1], device=local)
+            terms = [dict(t, postings=[ids[int(x)] for x in t["postings"]]) for t in prob.terms]
+            got = ft.sharded_select(comm, cuts[rank], prob.cfg, prob.field_cfg, terms, 300, rank_sort_type=sort_type)
+            ft.close()
+            whole, wids = upload(prob, device=local)
+            wterms = [dict(t, postings=[wids[int(x)] for x in t["postings"]]) for t in prob.terms]
+            want = whole.select(prob.cfg, prob.field_cfg, wterms, 300, rank_sort_type=sort_type)
+            whole.close()
+            assert got[2] == want[2] and (got[0] == want[0]).all() and (got[1] == want[1]).all(), ("ft", seed, sort_type, rank)
+        dist.barrier()
+    anchor.close()
     if rank == 0:
         print("mp_sharded_nccl ok", flush=True)
     dist.destroy_process_group()

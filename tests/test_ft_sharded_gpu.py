@@ -16,15 +16,15 @@ from oracle import ft_oracle as F
 pytestmark = pytest.mark.gpu
 
 
-def upload(prob):
-    ft = rx.GpuFtIndex(prob.total_docs, prob.words, prob.avg, prob.removed)
+def upload(prob, device=0):
+    ft = rx.GpuFtIndex(prob.total_docs, prob.words, prob.avg, prob.removed, device=device)
     ids = [ft.add_postings(d, b, p) for d, b, p in prob.lists]
     return ft, ids
 
 
-def shard_of(prob, lo, hi):
+def shard_of(prob, lo, hi, device=0):
     """documents [lo, hi) under local ids: word counts, removed flags and every posting list cut to the range"""
-    ft = rx.GpuFtIndex(hi - lo, prob.words[lo:hi], prob.avg, None if prob.removed is None else prob.removed[lo:hi])
+    ft = rx.GpuFtIndex(hi - lo, prob.words[lo:hi], prob.avg, None if prob.removed is None else prob.removed[lo:hi], device=device)
     ids = []
     for d, b, p in prob.lists:
         d, b, p = np.asarray(d, np.uint32), np.asarray(b, np.uint32), np.asarray(p, np.uint32)
