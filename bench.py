@@ -633,6 +633,19 @@ def run_ours(args):
                 sub.append({"error": f"{type(e).__name__}: {e}"})
             line["sub"] = sub
             line["sub_seconds"] = round(time.perf_counter() - t_sub, 1)
+    if world > 1 and not args.no_sub and rows == ROWS_FULL:
+        # config 3 over docid-range shards: a collective, so every rank takes part; rank 0 reports it
+        rec = None
+        try:
+            idx.close()
+            import bench_extra as X
+
+            rec = X.ft_sharded_record(sharded.comm, rank, world, 50_000_000 if not args.quick_sub else 2_000_000, local_rank)
+        except Exception as e:  # a sub-record must never take the headline down with it
+            rec = {"error": f"{type(e).__name__}: {e}"}
+        if rank == 0:
+            line["sub"] = [rec]
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

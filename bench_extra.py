@@ -241,6 +241,62 @@ def ft_record(ndocs):
         "data": "synthetic postings, Poisson(100) document lengths"}
 
 
+def ft_sharded_record(comm, rank, world, docs_per_rank, device):
+    """BASELINE configs[3] sharded by docid range: every rank holds `docs_per_rank` documents of a world x docs_per_rank
+    namespace; one collective rxgpu_sharded_ft_select per query (five small exchanges + the top-100 gather over NCCL).  Collective: every
+    rank calls it; the record is meaningful on rank 0.  The answer is checked against the unsharded call in tests/ (bit-equal rows)."""
+    import torch
+    import torch.distributed as dist
+
+    import reindexer_b200 as rx
+    from oracle import ft_oracle as F
+
+    rng = np.random.default_rng(700 + rank)
+    words = (rng.poisson(100, size=docs_per_rank).astype(np.uint32) + 1).reshape(-1, 1)
+    avg = np.asarray([101.0], np.float32)  # the namespace-wide average field length: the same on every shard
+    ft = rx.GpuFtIndex(docs_per_rank, words, avg, device=device)
+    p = F.FtProblem(2, np.zeros((2, 1), np.uint32))  # only its config dictionaries are used
+    ids, npost = [], 0
+    for df in (0.10, 0.01, 0.001):
+        nd = int(df * docs_per_rank)
+        docs = np.unique(rng.integers(0, docs_per_rank, size=int(nd * 1.06), dtype=np.int64))[:nd].astype(np.uint32)
+        npos = rng.integers(1, 4, size=len(docs)).astype(np.uint32)
+        begin = np.concatenate([[0], np.cumsum(npos, dtype=np.int64)]).astype(np.uint32)
+        first = (rng.random(len(docs)) * np.minimum(words[docs, 0], 60)).astype(np.uint32)
+        pos = np.repeat(first, npos) + (np.arange(begin[-1], dtype=np.uint32) - np.repeat(begin[:-1], npos)) * 2
+        ids.append(ft.add_postings(docs, begin, pos))
+        npost += len(docs)
+    terms = [dict(op=F.OP_OR, boost=1.0, term_len_boost=1.0, field_boosts=np.ones(1, np.float32), postings=[i], procs=[100.0]) for i in ids]
+    base = rank * docs_per_rank
+    out = ft.sharded_select(comm, base, p.cfg, p.field_cfg, terms, 100)  # warm-up (allocates scratch)
+    reps = 10
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(reps):
+        out = ft.sharded_select(comm, base, p.cfg, p.field_cfg, terms, 100)
+        dev_ms += ft.last_stats()["device_ms"]
+    dist.barrier()
+    sec = (time.perf_counter() - t0) / reps
+    st = ft.last_stats()
+    t = torch.tensor([sec, dev_ms / reps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ft.close()
+    sec, dev = float(t[0]), float(t[1])
+    return {
+        "workload": f"ft_fast BM25 merge over {world} docid-range shards, {docs_per_rank} docs and {npost} postings per GPU, 3-term OR "
+                    f"(df 10% / 1% / 0.1%), merge_limit 20000, top-100 (BASELINE configs[3], one shard per GPU)",
+        "metric": "ft_fast top-100 queries/s over all shards", "value": 1.0 / sec, "unit": "queries/s", "higher_is_better": True,
+        "e2e": {"value": 1.0 / sec, "unit": "queries/s", "h2d_bytes_per_step": 512, "d2h_bytes_per_step": 100 * 8 * world + 16,
+                "ms_per_query": sec * 1e3, "call": "rxgpu_sharded_ft_select (collective; max over ranks, host clock around the call)"},
+        "ms_per_query_device_max_over_ranks": dev, "launches": st["launches"], "preselected": st["preselected"], "rows_total": int(out[2]),
+        "top_rank": float(out[1][0]) if len(out[1]) else None, "total_docs": docs_per_rank * world, "scaling": "weak",
+        "exchanges": "NCCL: all-reduce of posting counts, mask popcount, 65536-bin histogram (512 KB), max score, max rank; all-gather of the "
+                     "threshold-document counts and of every shard's top-100 keys",
+        "data": "synthetic postings, Poisson(100) document lengths"}
+
+
 def run_ft(args):
     print(json.dumps(ft_record(args.docs)))
 
