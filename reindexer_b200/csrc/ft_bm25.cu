@@ -238,6 +238,11 @@ __global__ void ft_not_clear(DevList l, uint32_t* mask) {
 // restrictingMask_.PopCount() > cfg_->mergeLimit (mergerimpl.h:486-489), decided where the count lives
 __global__ void ft_decide_preselect(const unsigned long long* popc, uint32_t merge_limit, uint32_t* flag) { *flag = *popc > merge_limit ? 1u : 0u; }
 __global__ void ft_popcount(const uint32_t* mask, uint32_t words, unsigned long long* out) {
+	__shared__ unsigned long long s_sum;
+	if (threadIdx.x == 0) {
+		s_sum = 0;
+	}
+	__syncthreads();
 	unsigned long long c = 0;
 	for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += gridDim.x * blockDim.x) {
 		c += __popc(mask[w]);
@@ -246,7 +251,11 @@ __global__ void ft_popcount(const uint32_t* mask, uint32_t words, unsigned long 
 		c += __shfl_xor_sync(0xffffffffu, c, off);
 	}
 	if ((threadIdx.x & 31) == 0 && c) {
-		atomicAdd(out, c);
+		atomicAdd(&s_sum, c);
+	}
+	__syncthreads();
+	if (threadIdx.x == 0 && s_sum) {  // one global atomic per block: 19 000 warps on one address were most of this kernel's time
+		atomicAdd(out, s_sum);
 	}
 }
 // calcTermScores (mergerimpl.h:289-324): one pass per subterm; a document scores once per term (tmask)
@@ -362,59 +371,64 @@ __global__ void __launch_bounds__(1024) ft_pick_threshold(const unsigned long lo
 	if (enabled && !*enabled) {  // preselect decided on the device (ft_decide_preselect): the host enqueues the whole query ahead
 		return;
 	}
-	// thread r owns the 64 scores [hi - 63, hi], hi = top - 64 r with top = the highest score present rounded up to 64 k + 63 (thread 0
-	// the highest), cached in registers: one read of the occupied part of the histogram -- a few hundred bins for a handful of terms,
-	// not all 65 536; A(hi) = docs in the bins of the threads before r = an exclusive prefix sum over r
-	__shared__ unsigned long long s_scan[1024];
-	__shared__ uint32_t s_min;
-	const uint32_t r = threadIdx.x;
-	const uint32_t top = min(65535u, *max_score | 63u);
-	const bool live = 64u * r <= top;  // hi >= 63
-	const uint32_t hi = live ? top - 64u * r : 63u;
-	uint32_t bins[64];  // bins[i] = hist[hi - i]; a bin holds at most total_docs < 2^32 documents
-	unsigned long long mine = 0;
-#pragma unroll
-	for (int i = 0; i < 64; ++i) {
-		bins[i] = live ? uint32_t(hist[hi - i]) : 0u;
-		mine += bins[i];
-	}
-	s_scan[r] = mine;
-	if (r == 0) {
-		s_min = 65535;
+	// Scores are walked from the highest one present downwards, 1024 bins per round (thread t of a round looks at score hi - t: coalesced
+	// loads, one block-wide inclusive scan per round): A(sc) = docs above the round + the scan up to t - the bin itself.  A(sc) only grows
+	// as sc falls, so the qualifying scores of a round are a prefix of its threads; the walk ends in the first round that holds a
+	// non-qualifying score or reaches sc = 1.  A handful of terms gives a few hundred occupied bins: one round.
+	__shared__ unsigned long long s_warp[32];
+	__shared__ unsigned long long s_above;
+	__shared__ uint32_t s_min, s_docs, s_stop;
+	const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+	const uint32_t top = min(65535u, *max_score);
+	if (t == 0) {
+		s_above = 0;
+		s_min = 1;              // every score down to 1 qualifies unless a round says otherwise
+		s_docs = max_merged;    // minScoreDocs for that case: A(1) is subtracted below
+		s_stop = 0;
 	}
 	__syncthreads();
-	for (uint32_t off = 1; off < 1024; off <<= 1) {  // inclusive Hillis-Steele scan over the thread totals
-		const unsigned long long add = r >= off ? s_scan[r - off] : 0ull;
-		__syncthreads();
-		s_scan[r] += add;
-		__syncthreads();
-	}
-	const unsigned long long above = s_scan[r] - mine;  // docs with score > hi
-	unsigned long long a = above;
-	uint32_t local = 0xFFFFFFFFu;
-#pragma unroll
-	for (int i = 0; i < 64; ++i) {
-		const uint32_t sc = hi - i;
-		if (live && sc >= 1 && a < max_merged) {
-			local = sc;
-		}
-		a += bins[i];
-	}
-	if (local != 0xFFFFFFFFu) {
-		atomicMin(&s_min, local);
-	}
-	__syncthreads();
-	const uint32_t ms = s_min;
-	if (live && ms <= top && (top - ms) / 64u == r) {
-		a = above;
-#pragma unroll
-		for (int i = 0; i < 64; ++i) {
-			if (hi - i > ms) {
-				a += bins[i];
+	for (int64_t hi = top; hi >= 1; hi -= 1024) {
+		const int64_t sc = hi - int64_t(t);
+		const unsigned long long cnt = sc >= 1 ? hist[sc] : 0ull;
+		unsigned long long incl = cnt;
+		for (int off = 1; off < 32; off <<= 1) {
+			const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, off);
+			if (lane >= uint32_t(off)) {
+				incl += y;
 			}
 		}
-		thr[0] = ms;
-		thr[1] = uint32_t(max_merged - a);
+		if (lane == 31) {
+			s_warp[warp] = incl;
+		}
+		__syncthreads();
+		unsigned long long before = s_above;
+		for (uint32_t x = 0; x < warp; ++x) {
+			before += s_warp[x];
+		}
+		const unsigned long long a = before + incl - cnt;  // docs with a score above sc
+		const bool ok = sc >= 1 && a < max_merged;
+		const bool next_ok = sc - 1 >= 1 && a + cnt < max_merged;  // the score below me (the next thread's, or the next round's first)
+		if (ok && !next_ok) {  // exactly one thread over all rounds: the smallest qualifying score
+			s_min = uint32_t(sc);
+			s_docs = uint32_t(max_merged - a);
+			s_stop = 1;
+		}
+		__syncthreads();
+		if (s_stop) {
+			break;
+		}
+		if (t == 0) {
+			unsigned long long sum = s_above;
+			for (uint32_t x = 0; x < 32; ++x) {
+				sum += s_warp[x];
+			}
+			s_above = sum;
+		}
+		__syncthreads();
+	}
+	if (t == 0) {
+		thr[0] = s_min;
+		thr[1] = s_stop ? s_docs : uint32_t(s_above < max_merged ? max_merged - s_above : 0ull);
 	}
 }
 // ordered cut at the threshold score: keep score > min, and the first `budget` docs (ascending id) with score == min (:448-462).
@@ -540,16 +554,25 @@ __global__ void __launch_bounds__(kFtThreads) ft_thresh_apply(const uint16_t* sc
 }
 // exclusive scan of block counts, single block (counts <= ~200k entries)
 __global__ void ft_scan_blocks(uint32_t* counts, uint32_t n, uint32_t* total) {
+	// one block; a thread owns kItems consecutive counts per round (a round = blockDim.x * kItems counts: 19 532 block counts of a
+	// 5 M-posting list are 3 rounds of 8192 instead of 20 rounds of 1024, each with its three barriers)
+	constexpr uint32_t kItems = 8;
 	__shared__ uint32_t s_warp[32];
 	__shared__ uint32_t s_carry;
 	if (threadIdx.x == 0) {
 		s_carry = 0;
 	}
 	__syncthreads();
-	for (uint32_t base = 0; base < n; base += blockDim.x) {
-		const uint32_t i = base + threadIdx.x;
-		const uint32_t v = i < n ? counts[i] : 0;
-		uint32_t x = v;
+	for (uint32_t base = 0; base < n; base += blockDim.x * kItems) {
+		const uint32_t i0 = base + threadIdx.x * kItems;
+		uint32_t v[kItems];
+		uint32_t mine = 0;
+#pragma unroll
+		for (uint32_t x = 0; x < kItems; ++x) {
+			v[x] = i0 + x < n ? counts[i0 + x] : 0;
+			mine += v[x];
+		}
+		uint32_t x = mine;
 		for (int off = 1; off < 32; off <<= 1) {
 			const uint32_t y = __shfl_up_sync(0xffffffffu, x, off);
 			if ((threadIdx.x & 31) >= off) {
@@ -573,8 +596,13 @@ __global__ void ft_scan_blocks(uint32_t* counts, uint32_t n, uint32_t* total) {
 		__syncthreads();
 		const uint32_t warp_off = (threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0;
 		const uint32_t incl = s_carry + warp_off + x;
-		if (i < n) {
-			counts[i] = incl - v;
+		uint32_t run = incl - mine;  // exclusive prefix of my first item
+#pragma unroll
+		for (uint32_t y = 0; y < kItems; ++y) {
+			if (i0 + y < n) {
+				counts[i0 + y] = run;
+			}
+			run += v[y];
 		}
 		__syncthreads();
 		if (threadIdx.x == blockDim.x - 1) {
@@ -2175,7 +2203,7 @@ int ftMergeImpl(rxgpu_ft_index* ft, const rxgpu_ft_config* cfg, const rxgpu_ft_q
 		uint32_t* d_presel = ft->scalar_u32.p + 6;  // [6] 1 when preselectMostRelevantDocs runs
 		if (preselect) {
 			RX_CUDA(cudaMemsetAsync(ft->popc.p, 0, 8, st));
-			ft_popcount<<<gridFor(mwords, sm), kFtThreads, 0, st>>>(ft->mask.p, mwords, ft->popc.p);
+			ft_popcount<<<std::min<unsigned>(gridFor(mwords, sm), unsigned(sm) * 4), kFtThreads, 0, st>>>(ft->mask.p, mwords, ft->popc.p);
 			if (sh) {  // exchange 2: restrictingMask_.PopCount() over all shards
 				if (int rc = commAllReduce(sh->comm, ft->popc.p, 1, CommOp::SumU64, st)) {
 					return rc;
