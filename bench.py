@@ -582,6 +582,9 @@ def run_ours(args):
             "config": workload_config(world, rows),
             "details": {"query_tile": qt, "kernel": kernel_name, "tc_candidates_per_step": main_stats["tc_candidates"],
                         "tc_fallbacks": main_stats["tc_fallbacks"], "tc_cluster": main_stats["tc_cluster"],
+                        "tail_grid": "clusters of 4 fit 33 times (132 of 148 SMs); 2-CTA clusters of the same kernel scan the last ~10 % of the "
+                                     "row tiles on the other 16 SMs beside every main launch (second stream); roofline.avg_launch_ms is the main "
+                                     "launch, whose window covers all rows for its 512 queries",
                         "l2_policy": "inputs (30.7 GB/GPU) larger than L2, no flush",
                         "global_queries_per_s": NQ / (ms_per_step / 1000.0), "index_fill_s": round(fill_s, 2),
                         "value_definition": "(query x 10M-row shard) scans per second over all ranks",

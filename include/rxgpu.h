@@ -482,7 +482,8 @@ void rxgpu_last_search_stats(rxgpu_search_stats* out);
  * the other values force kernel variants for tests/benchmarks (all give the same bits): 3 / 4 = first-generation kernel (queries in
  * shared memory) with 1 CTA / a CTA pair per row tile; 5 / 6 / 9 = knn_tc_filter_q (query block in TMEM, accumulators of 64 rows;
  * the default) with single CTAs / clusters of up to 4 / up to 8; 14 / 15 / 16 = knn_tc_filter_p (CTA pairs multiply as one,
- * cta_group::2, every SM stages half a 128-row tile) with clusters of up to 4 / 2 / 8 CTAs.  DESIGN.md section 9 has the measurements. */
+ * cta_group::2, every SM stages half a 128-row tile) with clusters of up to 4 / 2 / 8 CTAs; 17 = the default kernel without its tail grid
+ * (2-CTA clusters that scan the last row tiles on the SMs a cluster-of-4 grid cannot use).  DESIGN.md section 9 has the measurements. */
 int rxgpu_set_tensor_core_filter(rxgpu_index*, int mode);
 /* process-wide switch: bracket every scan-kernel launch with CUDA events (used by bench.py for the roofline figure) */
 int rxgpu_set_profile(int on);

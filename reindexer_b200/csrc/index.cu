@@ -357,6 +357,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 		}
 		const uint32_t qtiles = uint32_t((ix->size + tileRows - 1) / tileRows);
 		unsigned grid = 0;
+		int residentClusters = 0;
 		for (;;) {  // how many clusters of this size can be resident at once (GPC boundaries strand SMs for size 4)
 			cudaLaunchConfig_t cfg{};
 			cfg.gridDim = dim3(unsigned(ix->sm_count) / cluster * cluster);
@@ -373,6 +374,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			const cudaError_t e = cudaOccupancyMaxActiveClusters(&maxClusters, kernelOf(cluster), &cfg);
 			if (e == cudaSuccess && maxClusters > 0) {
 				grid = unsigned(std::min<uint64_t>(uint64_t(maxClusters), std::max<uint32_t>(qtiles, 1))) * cluster;
+				residentClusters = maxClusters;
 				break;
 			}
 			cudaGetLastError();
@@ -381,6 +383,34 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			}
 			cluster /= 2;
 		}
+		// Tail grid: clusters of 4 fit 33 times on a B200 (132 of 148 SMs, GPC boundaries).  The kernel is power-bound, so more
+		// units at a lower clock is the lever left: 2-CTA clusters of the same kernel take the stranded SMs and scan the last
+		// Ct / (2 Cm + Ct) of the row tiles -- twice per main launch, once for each half of its 4 query blocks -- on a second stream.
+		// Candidate lists, thresholds and bound lists are per query and global, so both grids feed the same re-rank.
+		uint32_t tailClusters = 0, tilesMain = qtiles;
+		if (ix->tc_tail && cluster == 4 && int(grid) == residentClusters * cluster && qtiles >= 256) {
+			const uint32_t spare = uint32_t(ix->sm_count) - grid;
+			tailClusters = spare / 2;
+			if (tailClusters) {
+				const uint32_t cm = grid / cluster;
+				// the tail's share by SM count would be Ct / (2 Cm + Ct) = 10.8 %; measured best at 10 % (80 / 100 / 120 / 140 permille:
+			// 71.4 / 72.5 / 70.8 / 68.1 k queries/s on one box): a 2-CTA cluster reads its rows from HBM once per 256 queries, not 512
+			uint32_t tilesTail = uint32_t(uint64_t(qtiles) * tailClusters * 15 / ((2ull * cm + tailClusters) * 16));
+			static const char* tp = std::getenv("RXGPU_TC_TAIL_PERMILLE");  // tuning aid: the tail's share of the row tiles
+			if (tp) {
+				tilesTail = uint32_t(uint64_t(qtiles) * uint32_t(std::atoi(tp)) / 1000);
+			}
+				tilesMain = qtiles - tilesTail;
+				if (!ws.tail_stream) {
+					RX_CUDA(cudaStreamCreateWithFlags(&ws.tail_stream, cudaStreamNonBlocking));
+					RX_CUDA(cudaEventCreateWithFlags(&ws.tail_fork, cudaEventDisableTiming));
+					RX_CUDA(cudaEventCreateWithFlags(&ws.tail_join, cudaEventDisableTiming));
+				}
+				RX_CUDA(cudaEventRecord(ws.tail_fork, st));
+				RX_CUDA(cudaStreamWaitEvent(ws.tail_stream, ws.tail_fork, 0));
+			}
+		}
+		const uint32_t rowsMain = uint32_t(std::min<uint64_t>(ix->size, uint64_t(tilesMain) * tileRows));
 		for (uint32_t b = 0; b < qblocks; b += cluster) {
 			TqArgs a{};
 			a.shadow = static_cast<const unsigned char*>(ix->d_shadow);
@@ -396,7 +426,7 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			a.cand_count = ws.d_cand_count.p;
 			a.cand_cap = kTcCandCap;
 			a.init_rows = uint32_t(std::min<uint64_t>(ix->size, kTcInitRows));
-			a.n = uint32_t(ix->size);
+			a.n = rowsMain;
 			a.kchunks = kchunks;
 			a.pitch_bf = pitchBf;
 			a.nq_total = nq;
@@ -445,6 +475,30 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 			}
 			g_stats.launches += 1;
 			g_stats.passes += 1;
+			for (uint32_t pb = b; tailClusters && pb < std::min<uint32_t>(b + uint32_t(cluster), qblocks); pb += 2) {
+				TqArgs t = a;
+				t.trace = nullptr;
+				t.row_base = rowsMain;
+				t.shadow = a.shadow + size_t(rowsMain) * pitchBf * 2;
+				t.vw = a.vw + rowsMain;
+				t.n = uint32_t(ix->size) - rowsMain;
+				t.q0 = pb * kTqQueries;
+				cudaLaunchConfig_t tcfg{};
+				tcfg.gridDim = dim3(tailClusters * 2);
+				tcfg.blockDim = dim3(threads);
+				tcfg.dynamicSmemBytes = smem;
+				tcfg.stream = ws.tail_stream;
+				cudaLaunchAttribute tattr[1];
+				tattr[0].id = cudaLaunchAttributeClusterDimension;
+				tattr[0].val.clusterDim.x = 2;
+				tattr[0].val.clusterDim.y = 1;
+				tattr[0].val.clusterDim.z = 1;
+				tcfg.attrs = tattr;
+				tcfg.numAttrs = 1;
+				RX_CUDA(cudaLaunchKernelEx(&tcfg, kernelOf(2), t));
+				RX_CUDA(cudaGetLastError());
+				g_stats.launches += 1;
+			}
 			if (a.trace) {
 				std::vector<unsigned long long> h(256 * 16);
 				RX_CUDA(cudaStreamSynchronize(st));
@@ -458,6 +512,10 @@ int scanTopKTensorCore(const rxgpu_index* ix, Workspace& ws, cudaStream_t st, co
 					std::fclose(f);
 				}
 			}
+		}
+		if (tailClusters) {
+			RX_CUDA(cudaEventRecord(ws.tail_join, ws.tail_stream));
+			RX_CUDA(cudaStreamWaitEvent(st, ws.tail_join, 0));
 		}
 		g_stats.tc_cluster = uint32_t(cluster);
 		g_stats.tc_kernel = pairs ? 5 : 2;
@@ -1051,11 +1109,12 @@ int rxgpu_set_query_tile(rxgpu_index* ix, uint32_t qt) {
 	return 0;
 }
 int rxgpu_set_tensor_core_filter(rxgpu_index* ix, int mode) {
-	if (!ix || mode < 0 || mode > 16 || mode == 7 || mode == 8 || (mode >= 10 && mode <= 13)) {
-		return fail(RXGPU_ERR_PARAMS, "rxgpu: tensor-core filter mode must be 0..6, 9 or 14..16");
+	if (!ix || mode < 0 || mode > 17 || mode == 7 || mode == 8 || (mode >= 10 && mode <= 13)) {
+		return fail(RXGPU_ERR_PARAMS, "rxgpu: tensor-core filter mode must be 0..6, 9 or 14..17");
 	}
 	ix->tc_mode = uint32_t(mode >= 3 ? 1 : mode);
-	ix->tc_variant = (mode == 3 || mode == 4) ? uint32_t(mode) : (mode >= 14 ? 14u : 0u);
+	ix->tc_variant = (mode == 3 || mode == 4) ? uint32_t(mode) : ((mode >= 14 && mode <= 16) ? 14u : 0u);
+	ix->tc_tail = mode == 17 ? 0u : 1u;
 	ix->tc_cluster_max = mode == 5 ? 1u : ((mode == 6 || mode == 14) ? 4u : ((mode == 9 || mode == 16) ? 8u : (mode == 15 ? 2u : 0u)));
 	return 0;
 }

@@ -123,6 +123,8 @@ inline cudaError_t raiseSmemCeilingOnce(Kernel kfn, int device, int bytes) {  //
 // per-call scratch: searches are re-entrant, each takes one workspace from the pool
 struct Workspace {
 	cudaStream_t stream = nullptr;
+	cudaStream_t tail_stream = nullptr;  // the filter's tail grid (CTA pairs on the SMs the cluster-of-4 grid strands) runs beside the main one
+	cudaEvent_t tail_fork = nullptr, tail_join = nullptr;
 	DevBuf<float> d_queries;
 	DevBuf<uint64_t> d_lists;
 	DevBuf<uint64_t> d_floor;  // per-query floor keys between the rounds of a k > 255 search
@@ -157,6 +159,11 @@ struct Workspace {
 	~Workspace() {
 		if (stream) {
 			cudaStreamDestroy(stream);
+		}
+		if (tail_stream) {
+			cudaStreamDestroy(tail_stream);
+			cudaEventDestroy(tail_fork);
+			cudaEventDestroy(tail_join);
 		}
 	}
 };
@@ -210,6 +217,7 @@ struct rxgpu_index {
 	mutable uint32_t pitch_bf = 0;
 	mutable uint64_t shadow_version = ~0ull;
 	uint32_t tc_mode = 0;  // 0 auto, 1 force on, 2 off
+	uint32_t tc_tail = 1;         // 1 = a tail grid of 2-CTA clusters scans a slice of the rows on the SMs the main grid cannot use
 	uint32_t tc_variant = 0;      // 0 = knn_tc_filter_q (query block in TMEM) when the dimension allows; 14 = knn_tc_filter_p (CTA pairs, cta_group::2); 3 / 4 = first-generation kernel (1 CTA / CTA pair)
 	uint32_t tc_cluster_max = 0;  // 0 = up to 4 CTAs per cluster
 

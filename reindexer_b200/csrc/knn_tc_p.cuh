@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(kTpThreads, 1) knn_tc_filter_p(const TqArgs a)
 						if (!(any_hits & (1u << j)) || !(hits & (1u << j))) {
 							continue;
 						}
-						const float nt = tq_candidate(cc, my_q, row0 + c0 + j, __uint_as_float(v[j]), vw_tile[c0 + j].x, qe, tau);
+						const float nt = tq_candidate(cc, my_q, a.row_base + row0 + c0 + j, __uint_as_float(v[j]), vw_tile[c0 + j].x, qe, tau);
 						if (nt < tau) {
 							tau = nt;
 							pr = tc_make_pr(a.metric, tau, qe);

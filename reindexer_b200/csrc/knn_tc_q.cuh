@@ -55,6 +55,8 @@ struct TqArgs {
 	uint32_t trace_first;       // first local tile index recorded (RXGPU_TC_TRACE_FIRST)
 	uint32_t prefetch;          // L2 prefetch distance of the producers in tiles (0 = off)
 	uint32_t single_issuer;     // knn_tc_filter_q: 1 = warp 1 issues every tile in order (stages are released at the full pipe rate)
+	uint32_t row_base;          // global internal row of this launch's tile 0 (shadow / vw point at it, n counts the rows from there): the tail
+	                            // grid on the SMs a cluster-of-4 grid strands scans its own row range
 };
 
 constexpr uint32_t kTqVwSlots = 16;  // ring of per-tile (||v||, w) blocks, filled kTqVwAhead tiles ahead by the epilogue itself
@@ -441,7 +443,7 @@ __global__ void __launch_bounds__(kTqThreads, 1) knn_tc_filter_q(const TqArgs a)
 						if (!(any_hits & (1u << j)) || !(hits & (1u << j))) {
 							continue;
 						}
-						const float nt = tq_candidate(cc, my_q, t * kTqTileRows + c0 + j, __uint_as_float(v[j]), vw_tile[c0 + j].x, qe, tau);
+						const float nt = tq_candidate(cc, my_q, a.row_base + t * kTqTileRows + c0 + j, __uint_as_float(v[j]), vw_tile[c0 + j].x, qe, tau);
 						if (nt < tau) {
 							tau = nt;
 							pr = tc_make_pr(a.metric, tau, qe);

@@ -37,7 +37,8 @@ def test_tc_path_is_bit_identical_to_exact_scan(metric, n, dim, nq, k):
     # every kernel variant gives the same bits: 3 / 4 = queries in shared memory (1 CTA / CTA pair with TMA multicast),
     # 5 / 6 / 9 = whole query block in TMEM (accumulators of 64 rows; the default) with single CTAs / clusters of up to 4 / 8 CTAs,
     # 14 / 15 / 16 = CTA pairs multiply as one (cta_group::2, half a 128-row tile per SM) with clusters of up to 4 / 2 / 8 CTAs
-    for mode, kernel in ((3, 1), (4, 1), (5, 2), (6, 2), (9, 2), (14, 5), (15, 5), (16, 5)):
+    # 17 = the default kernel without the tail grid (the 2-CTA clusters that scan the last row tiles on the SMs a cluster-of-4 grid strands)
+    for mode, kernel in ((3, 1), (4, 1), (5, 2), (6, 2), (9, 2), (14, 5), (15, 5), (16, 5), (17, 2)):
         gpu.set_tensor_core_filter(mode)
         d2, l2, c2 = gpu.search_knn(queries, k)
         s2 = rx.last_search_stats()
