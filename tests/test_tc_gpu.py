@@ -24,7 +24,8 @@ def both_paths(gpu, queries, k):
 
 @pytest.mark.parametrize("metric", [rx.L2, rx.IP, rx.COS])
 @pytest.mark.parametrize("n,dim,nq,k", [(20000, 128, 64, 10), (30000, 100, 100, 10), (12000, 768, 96, 10), (9000, 64, 300, 15),
-                                        (5000, 200, 33, 1), (30000, 768, 400, 10), (40000, 256, 700, 5), (6000, 1000, 150, 10)])
+                                        (5000, 200, 33, 1), (30000, 768, 400, 10), (40000, 256, 700, 5), (6000, 1000, 150, 10),
+                                        (60000, 128, 520, 40), (50000, 96, 200, 63)])
 def test_tc_path_is_bit_identical_to_exact_scan(metric, n, dim, nq, k):
     gpu = rx.GpuBruteforceSearch(metric, dim, n)
     gpu.append_synth(0xABC0 + dim, 0, n)
@@ -33,7 +34,7 @@ def test_tc_path_is_bit_identical_to_exact_scan(metric, n, dim, nq, k):
     assert (c0 == c1).all() and (c0 == k).all()
     assert (l0 == l1).all(), np.argwhere(l0 != l1)[:5]
     assert (d0.view(np.uint32) == d1.view(np.uint32)).all()
-    assert st["tc_fallbacks"] == 0 and 0 < st["tc_candidates"] < nq * 4096
+    assert st["tc_fallbacks"] == 0 and 0 < st["tc_candidates"] < nq * 4096, st
     # every kernel variant gives the same bits: 3 / 4 = queries in shared memory (1 CTA / CTA pair with TMA multicast),
     # 5 / 6 / 9 = whole query block in TMEM (accumulators of 64 rows; the default) with single CTAs / clusters of up to 4 / 8 CTAs,
     # 14 / 15 / 16 = CTA pairs multiply as one (cta_group::2, half a 128-row tile per SM) with clusters of up to 4 / 2 / 8 CTAs
