@@ -478,7 +478,7 @@ typedef struct {
 } rxgpu_search_stats;
 void rxgpu_last_search_stats(rxgpu_search_stats* out);
 /* large query batches: bf16 tensor-core filter + exact fp32 re-rank (results identical to the exact scan).
- * mode 0 = automatic (batches >= 64 queries on >= 100k rows, k <= 63), 1 = whenever possible, 2 = never;
+ * mode 0 = automatic (batches >= 64 queries on >= 100k rows, k <= 127), 1 = whenever possible, 2 = never;
  * the other values force kernel variants for tests/benchmarks (all give the same bits): 3 / 4 = first-generation kernel (queries in
  * shared memory) with 1 CTA / a CTA pair per row tile; 5 / 6 / 9 = knn_tc_filter_q (query block in TMEM, accumulators of 64 rows;
  * the default) with single CTAs / clusters of up to 4 / up to 8; 14 / 15 / 16 = knn_tc_filter_p (CTA pairs multiply as one,

@@ -37,8 +37,8 @@ constexpr int kTcTileRows = 128;     // UMMA M
 constexpr int kTcChunkK = 64;        // bf16 elements per 128-byte swizzle row
 constexpr int kTcStages = 4;
 constexpr int kTcStageBytes = kTcTileRows * kTcChunkK * 2;  // 16 KB
-constexpr uint32_t kTcMaxK1 = 64;  // k + 1 <= 64: the bound list is scanned linearly under the per-query lock and ~35 (k + 1) candidates per
-                                   // query must fit the 4096-entry lists (k = 10: 350; k = 63: ~2300); larger k takes the exact scan
+constexpr uint32_t kTcMaxK1 = 128;  // k + 1 <= 128: the bound list is scanned linearly under the per-query lock and ~25-35 (k + 1) candidates
+                                    // per query must fit the 4096-entry lists (k = 10: 330; k = 63: 1600; an overflowing query takes the exact scan)
 constexpr uint32_t kTcQueueCap = 512;
 constexpr float kTcErrCoef = 0.0042f;  // see header comment
 

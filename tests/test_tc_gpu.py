@@ -25,7 +25,7 @@ def both_paths(gpu, queries, k):
 @pytest.mark.parametrize("metric", [rx.L2, rx.IP, rx.COS])
 @pytest.mark.parametrize("n,dim,nq,k", [(20000, 128, 64, 10), (30000, 100, 100, 10), (12000, 768, 96, 10), (9000, 64, 300, 15),
                                         (5000, 200, 33, 1), (30000, 768, 400, 10), (40000, 256, 700, 5), (6000, 1000, 150, 10),
-                                        (60000, 128, 520, 40), (50000, 96, 200, 63)])
+                                        (60000, 128, 520, 40), (50000, 96, 200, 63), (80000, 64, 260, 100), (45000, 160, 130, 127)])
 def test_tc_path_is_bit_identical_to_exact_scan(metric, n, dim, nq, k):
     gpu = rx.GpuBruteforceSearch(metric, dim, n)
     gpu.append_synth(0xABC0 + dim, 0, n)
