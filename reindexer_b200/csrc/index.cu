@@ -278,11 +278,30 @@ int ensureShadow(const rxgpu_index* ix, cudaStream_t st) {
 		RX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ix->d_vw), cap * sizeof(float2)));
 		ix->pitch_bf = pitchBf;
 		ix->shadow_version = ~0ull;
+		ix->shadow_dirty_all = true;
+		ix->shadow_dirty.clear();
 	}
 	if (ix->shadow_version != ix->version) {
-		const unsigned blocks = unsigned((uint64_t(ix->size) * 32 + 255) / 256);
-		tc_convert_rows<<<blocks, 256, 0, st>>>(ix->d_rows, ix->pitch, ix->dim, 0, uint32_t(ix->size),
-												static_cast<__nv_bfloat16*>(ix->d_shadow), pitchBf / kTcChunkK, ix->d_vnorm);
+		// only the rows the mutations since the last search rewrote (an upsert, a swap-remove, an appended run), unless the log gave up
+		auto convert = [&](uint32_t b, uint32_t e) {
+			const unsigned blocks = unsigned((uint64_t(e - b) * 32 + 255) / 256);
+			tc_convert_rows<<<blocks, 256, 0, st>>>(ix->d_rows, ix->pitch, ix->dim, b, e, static_cast<__nv_bfloat16*>(ix->d_shadow),
+													pitchBf / kTcChunkK, ix->d_vnorm);
+		};
+		if (ix->shadow_dirty_all) {
+			if (ix->size) {
+				convert(0, uint32_t(ix->size));
+			}
+		} else {
+			for (const auto& r : ix->shadow_dirty) {
+				const uint32_t e = uint32_t(std::min<uint64_t>(r.second, ix->size));
+				if (r.first < e) {
+					convert(r.first, e);
+				}
+			}
+		}
+		ix->shadow_dirty_all = false;
+		ix->shadow_dirty.clear();
 		const uint32_t padded = uint32_t((ix->size + kTcTileRows - 1) / kTcTileRows * kTcTileRows);
 		tc_make_vw<<<(padded + 255) / 256, 256, 0, st>>>(ix->d_vnorm, uint32_t(ix->size), padded, ix->metric, ix->d_vw);
 		RX_CUDA(cudaGetLastError());
@@ -690,6 +709,7 @@ int setRowAt(rxgpu_index* ix, uint32_t idx, uint64_t label, const float* vec) {
 	if (ix->flags & RXGPU_FLAG_HOST_MIRROR) {
 		std::memcpy(ix->h_rows.data() + size_t(idx) * ix->dim, vec, ix->dim * sizeof(float));
 	}
+	ix->touchRows(idx, uint64_t(idx) + 1);
 	ix->version++;
 	return 0;
 }
@@ -1023,6 +1043,14 @@ int rxgpu_index_upsert_batch(rxgpu_index* ix, uint64_t n, const uint64_t* labels
 					std::memcpy(ix->h_rows.data() + size_t(dst[i]) * ix->dim, vecs + i * ix->dim, ix->dim * sizeof(float));
 				}
 			}
+			for (uint64_t i = 0; i < m;) {  // maximal runs of consecutive destinations (an appended batch is one range)
+				uint64_t j = i + 1;
+				while (j < m && dst[j] == dst[j - 1] + 1) {
+					++j;
+				}
+				ix->touchRows(dst[i], uint64_t(dst[j - 1]) + 1);
+				i = j;
+			}
 			ix->size = newSize;
 			ix->version++;
 		}
@@ -1049,6 +1077,7 @@ int rxgpu_index_remove(rxgpu_index* ix, uint64_t label) {
 	ix->version++;
 	const uint64_t last = ix->size - 1;
 	if (cur != last) {  // move the last row into the hole (bruteforce.cc:78-82)
+		ix->touchRows(cur, uint64_t(cur) + 1);
 		const uint64_t lastLabel = ix->h_labels[last];
 		ix->dict.put(lastLabel, cur);
 		ix->h_labels[cur] = lastLabel;
@@ -1578,6 +1607,7 @@ int rxgpu_index_append_synth(rxgpu_index* ix, uint64_t seed, uint64_t first_row,
 		return rc;
 	}
 	RX_CUDA(cudaStreamSynchronize(ix->stream));
+	ix->touchRows(ix->size, ix->size + n);
 	ix->size += n;
 	ix->version++;
 	return 0;

@@ -216,6 +216,25 @@ struct rxgpu_index {
 	mutable float2* d_vw = nullptr;    // [capacity] per-row (max(||row||, tiny), w) pairs the filter epilogue consumes, 512 B per 64-row tile
 	mutable uint32_t pitch_bf = 0;
 	mutable uint64_t shadow_version = ~0ull;
+	// rows rewritten since the shadow was last brought up to date (the mutations log them beside `version`): ensureShadow converts
+	// only these; the log gives up (full rebuild) beyond kShadowLogMax ranges
+	static constexpr size_t kShadowLogMax = 4096;
+	mutable std::vector<std::pair<uint32_t, uint32_t>> shadow_dirty;
+	mutable bool shadow_dirty_all = true;
+	void touchRows(uint64_t begin, uint64_t end) {
+		std::lock_guard<std::mutex> lck(tc_mtx);
+		if (!d_shadow || shadow_dirty_all || begin >= end) {
+			return;
+		}
+		if (!shadow_dirty.empty() && shadow_dirty.back().second == begin) {
+			shadow_dirty.back().second = uint32_t(end);
+		} else if (shadow_dirty.size() < kShadowLogMax) {
+			shadow_dirty.emplace_back(uint32_t(begin), uint32_t(end));
+		} else {
+			shadow_dirty_all = true;
+			shadow_dirty.clear();
+		}
+	}
 	uint32_t tc_mode = 0;  // 0 auto, 1 force on, 2 off
 	uint32_t tc_tail = 1;         // 1 = a tail grid of 2-CTA clusters scans a slice of the rows on the SMs the main grid cannot use
 	uint32_t tc_variant = 0;      // 0 = knn_tc_filter_q (query block in TMEM) when the dimension allows; 14 = knn_tc_filter_p (CTA pairs, cta_group::2); 3 / 4 = first-generation kernel (1 CTA / CTA pair)

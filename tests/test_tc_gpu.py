@@ -100,3 +100,32 @@ def test_tc_shadow_follows_index_mutations():
     (d0, l0, c0), (d1, l1, c1), st = both_paths(gpu, queries, k)
     assert (l0 == l1).all() and (d0.view(np.uint32) == d1.view(np.uint32)).all()
     assert all(l1[i, 0] == (n + i) << 32 for i in range(8))
+
+
+def test_tc_shadow_incremental_updates_equal_a_rebuild():
+    """the bf16 shadow is brought up to date row by row (the mutations log the rows they rewrite): after rounds of upserts of existing
+    labels, appended runs, swap-removes and a resize the tensor-core path must still equal the exact scan bit for bit -- and equal a
+    second index built from scratch with the same final content"""
+    rng = np.random.default_rng(9)
+    n, dim, nq, k = 30000, 96, 128, 10
+    gpu = rx.GpuBruteforceSearch(rx.L2, dim, n + 4000)
+    vecs = O.synth_matrix(61, n, dim)
+    labels = O.row_labels(n)
+    gpu.add_points(labels, vecs)
+    queries = O.synth_matrix(62, nq, dim)
+    both_paths(gpu, queries, k)  # builds the shadow
+    next_row = n
+    for rnd in range(4):
+        hit = rng.choice(n, size=40, replace=False)  # rewrite existing rows close to some queries
+        newv = (queries[rng.integers(0, nq, size=40)] + rng.normal(0, 0.01, size=(40, dim))).astype(np.float32)
+        gpu.add_points(labels[hit], newv)
+        fresh = (queries[rng.integers(0, nq, size=300)] * rng.uniform(0.9, 1.1, size=(300, 1))).astype(np.float32)
+        gpu.add_points(O.row_labels(300, first_row=next_row), fresh)
+        next_row += 300
+        for lab in labels[rng.choice(n, size=25, replace=False)]:
+            gpu.remove_point(int(lab))
+        if rnd == 2:
+            gpu.resize_index(n + 8000)  # the shadow is rebuilt at the new capacity
+        (d0, l0, c0), (d1, l1, c1), st = both_paths(gpu, queries, k)
+        assert (l0 == l1).all() and (d0.view(np.uint32) == d1.view(np.uint32)).all(), rnd
+    gpu.close()
