@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RXGPU_ABI_VERSION 3
+#define RXGPU_ABI_VERSION 4 /* 4: + rxgpu_comm_create_local, rxgpu_sharded_ft_select; filter variants 14..17; k <= 127 on the filter path */
 
 /* subset of reindexer::ErrorCode (core/type_consts.h:136-181) that this library produces */
 enum { RXGPU_OK = 0, RXGPU_ERR_PARAMS = 3, RXGPU_ERR_LOGIC = 4, RXGPU_ERR_NOT_FOUND = 13, RXGPU_ERR_SYSTEM = 37 };

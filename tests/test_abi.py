@@ -26,7 +26,7 @@ def test_every_declared_symbol_is_exported():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/rxgpu.h but not exported by librxgpu.so"
     assert set(syms) == set(binding._SIGNATURES), set(syms) ^ set(binding._SIGNATURES)
-    assert rx.lib().rxgpu_abi_version() == 3
+    assert rx.lib().rxgpu_abi_version() == 4
 
 
 def test_library_does_not_link_oracle_or_libcuda():
