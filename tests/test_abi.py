@@ -43,6 +43,9 @@ def test_no_cpu_fallback_without_device():
     with pytest.raises(rx.RxGpuError) as e:
         rx.GpuBruteforceSearch(rx.L2, 16, 100)
     assert e.value.code == 37 and "no CPU fallback" in e.value.what
+    with pytest.raises(rx.RxGpuError) as e:  # the in-process communicators of the sharded ft_fast merge need their devices as well
+        rx.ShardComm.local_group(2)
+    assert e.value.code == 37 and "no CPU fallback" in e.value.what
 
 
 def test_product_package_never_imports_oracle():
